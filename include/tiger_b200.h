@@ -1,0 +1,270 @@
+/*
+ * tiger_b200.h - C ABI of libtiger_b200.so: hand-written sm_100a kernels for TIGER's
+ * per-batch temporal memory path (reference: yzhang1918/www2023tiger, 100 % Python).
+ *
+ * The reference has no FFI layer: its "operator API" is the tiger/model + tiger/data class
+ * surface.  Each entry point below replaces the device work of the
+ * reference method cited beside it; www2023tiger_b200/ mirrors those classes and calls
+ * these functions through ctypes.
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes + cudaStream_t (passed as void*); no torch types.
+ *   - the CALLER owns every buffer; functions never allocate, never synchronise and are
+ *     stream-ordered, so a whole batch is capturable in a CUDA graph.
+ *   - node / edge ids are int64 (the reference's LongTensor); the CSR stores int32.
+ *   - values fp32; finder timestamps fp64 (reference graph.py:51 compares float64).
+ *   - data-dependent counts (involved U, outdated O, restarted R) stay on the device:
+ *     kernels take an `int32_t* count` and size their loops from it.
+ *   - return 0 on success, TIGER_EINVAL for a rejected argument, TIGER_ECUDA when the launch
+ *     failed (cudaGetLastError).  Invariant violations that the reference raises through
+ *     `.item()` host syncs are OR-ed into a device word `err_flags` (TIGER_ERR_*).
+ */
+#ifndef TIGER_B200_H
+#define TIGER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIGER_OK 0
+#define TIGER_EINVAL (-1)
+#define TIGER_ECUDA (-2)
+
+/* bits of the device-side error word */
+#define TIGER_ERR_PAST_MEMORY 1u      /* memory.py:45  "not allowed to modify past memory"      */
+#define TIGER_ERR_UNUSED_MSG 2u       /* memory.py:87  "Node has unused messages"               */
+#define TIGER_ERR_MSG_BEFORE_MEM 4u   /* message_modules.py:158 "Messages happened later ..."   */
+#define TIGER_ERR_MSG_TS_MISMATCH 8u  /* tiger.py:325  msg ts != left update ts                 */
+#define TIGER_ERR_EVENT_BEFORE_MEM 16u /* tiger.py:437 "Events occur before the updated memory" */
+#define TIGER_ERR_CAPACITY 32u        /* a caller-provided list capacity was exceeded           */
+
+int tiger_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Temporal graph (tiger/data/graph.py)
+ * ------------------------------------------------------------------------------------- */
+
+/* a1  Graph.__init__ / data2adjlist (graph.py:11-36,226-241): per-node time-sorted CSR from
+ * a time-ordered stream (src,dst,ts,eid)[n_events].  Entry 2e belongs to src[e] (flag 0), 2e+1
+ * to dst[e] (flag 1); per node, entries keep stream order - the stable sort of the reference.
+ * Implemented as a stable LSD radix sort of the entry indices by owner id (deterministic).
+ * `work` needs tiger_csr_build_work_bytes() bytes.  Output arrays have 2*n_events entries,
+ * indptr n_nodes+1. */
+int64_t tiger_csr_build_work_bytes(int64_t n_events, int64_t n_nodes);
+int tiger_csr_build(const int64_t* src, const int64_t* dst, const double* ts, const int64_t* eid,
+                    int64_t n_events, int64_t n_nodes, int64_t* indptr, int32_t* adj_nbr,
+                    int32_t* adj_eid, double* adj_ts, uint8_t* adj_flag, void* work, void* stream);
+
+/* a2  Graph.find_before + sample_temporal_neighbor['recent_edges'] + get_history
+ * (graph.py:44-53,117-127,150-155).  One warp per query, 32-ary cooperative search for the
+ * strict-'<' cut, right-aligned zero-padded K most recent entries.
+ * q_ts has ts_period entries, query i uses q_ts[i % ts_period] (np.tile of the collator).
+ * out_dirs, out_ts32 and mark_bitmap may be NULL.  mark_bitmap (ceil(n_nodes/32) words)
+ * receives one bit per query node and per returned neighbor (involved-node marking of
+ * collate_memory_nodes, data_loader.py:109-121).  out_ts32 (ts_period floats) receives
+ * (float)q_ts - the model-side timestamps of GraphCollator.__call__ (data_loader.py:92). */
+int tiger_find_recent(const int64_t* indptr, const int32_t* adj_nbr, const int32_t* adj_eid,
+                      const double* adj_ts, const uint8_t* adj_flag, const int64_t* q_nids,
+                      const double* q_ts, int64_t n_query, int64_t ts_period, int k,
+                      int64_t* out_nids, int64_t* out_eids, float* out_ts, int64_t* out_dirs,
+                      float* out_ts32, uint32_t* mark_bitmap, void* stream);
+
+/* a4  GraphCollator.check_in_window (data_loader.py:61-67): hit[i,k] = (center[i]==neigh[i,k]). */
+int tiger_hit_window(const int64_t* center, const int64_t* neigh, int64_t n, int k, float* hit,
+                     void* stream);
+
+/* mark ids in a node bitmap (first half of the sorted-unique of collate_memory_nodes). */
+int tiger_mark_nodes(const int64_t* ids, int64_t n, uint32_t* bitmap, int64_t n_nodes, void* stream);
+
+/* a3 + a5 + a12  second half: ordered compaction of the bitmap (cleared on exit) into
+ *   involved[]      sorted unique involved ids                 (data_loader.py:121)
+ *   local_index[u]  = rank of u in involved (may be NULL)       (data_classes.py:163-165)
+ *   restart_nodes[] involved nodes not yet up to date; marks them up to date and drops
+ *                   their pending-message flag (train_self_supervised.py:158-163,
+ *                   tiger.py:603, memory.py:136).  uptodate==NULL disables this list.
+ *   outdated[]      involved nodes with a pending message, ascending
+ *                   (MessageStoreNoGradLastOnly.get_outdated_node_ids, memory.py:108-126)
+ *   gru_row[u]      = rank of u in outdated, -1 for involved nodes without a message (may be NULL)
+ * counts[0..2] = U, O, R.  Single CTA; cost O(n_nodes/32). */
+int tiger_compact_involved(uint32_t* bitmap, int64_t n_nodes, uint8_t* has_msg, uint8_t* uptodate,
+                           int64_t* involved, int64_t cap_involved, int64_t* local_index,
+                           int64_t* outdated, int32_t* gru_row, int64_t* restart_nodes,
+                           int32_t* counts, uint32_t* err_flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Index utilities (tiger/model/utils.py)
+ * ------------------------------------------------------------------------------------- */
+
+/* a8  select_latest_nids (utils.py:10-16) with torch_scatter's CPU tie rule (lowest position
+ * among the maxima).  ts_is_f64 selects float64 (collator) or float32 (model) timestamps;
+ * position i uses ts[i % ts_period] (ts.repeat(2) of tiger.py:232,255; 0 means n).
+ * slot_ts / slot_pos are caller-owned per-node scratch tables (n_nodes entries, all-zero on
+ * entry, all-zero again on exit).  Outputs:
+ *   winner[i]   1 when position i is its node's selected position      (n, may be NULL)
+ *   unique_ids  ascending distinct ids, index[j] the selected position (may both be NULL)
+ *   count       number of distinct ids (device)
+ * Four stream-ordered kernels (max-ts atomics, min-pos atomics, flag, ordered compaction). */
+int tiger_select_latest(const int64_t* nids, const void* ts, int ts_is_f64, int64_t n,
+                        int64_t ts_period, int64_t n_nodes, uint64_t* slot_ts, uint32_t* slot_pos, uint32_t* bitmap,
+                        uint8_t* winner, int64_t* unique_ids, int64_t* index, int32_t* count,
+                        void* stream);
+
+/* a22  anonymized_reindex (utils.py:19-27): per row rank by last occurrence, 0 stays 0. */
+int tiger_anonymized_reindex(const int64_t* hist_nids, int64_t n, int len, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Memory / message store (tiger/model/memory.py, time_encoding.py)
+ * ------------------------------------------------------------------------------------- */
+
+/* a11 Memory.get (memory.py:36-39): out[i,:] = table[ids[i],:] (+ optional ts gather). */
+int tiger_gather_rows(const float* table, int64_t width, const int64_t* ids, int64_t n, float* out,
+                      const float* ts_table, float* out_ts, void* stream);
+
+/* a11 Memory.set (memory.py:41-52): table[ids[i],:] = vals[i,:]; ts_table[ids[i]] = ts[i];
+ * active[ids[i]] = 1.  With check!=0 sets TIGER_ERR_PAST_MEMORY when ts_table[id] > ts[i].
+ * count (device) overrides n when non-NULL. */
+int tiger_scatter_rows(float* table, int64_t width, const int64_t* ids, int64_t n,
+                       const int32_t* count, const float* vals, float* ts_table, const float* ts,
+                       uint8_t* active, int check, uint32_t* err_flags, void* stream);
+
+/* a10 TimeEncode.forward (time_encoding.py:16-27): out[i,:] = cos(ts[i]*w + b), product and
+ * sum rounded separately (no FMA contraction) like the CPU reference. */
+int tiger_time_encode(const float* ts, int64_t n, const float* w, const float* b, int dim, float* out,
+                      void* stream);
+
+/* a9  TIGE.store_events + MessageStoreNoGradLastOnly.store_events (tiger.py:422-442,
+ * memory.py:77-106).  For every selected position p (winner[p]!=0) of pos=[src;dst] builds
+ *   [mem(self)+nf(self) | mem(other)+nf(other) | ef(eid) | cos((t - mem_ts(self))*w + b)]
+ * and writes it to msg_vals[self], msg_ts[self]=t, has_msg[self]=1.  mem = message-source
+ * memory (left or right).  nfeats / efeats may be NULL (zeros of width d / de). */
+int tiger_store_messages(const int64_t* src, const int64_t* dst, const int64_t* eids, const float* ts,
+                         int64_t batch, const uint8_t* winner, const float* mem_vals,
+                         const float* mem_ts, const float* nfeats, const float* efeats, int d, int de,
+                         const float* time_w, const float* time_b, float* msg_vals, float* msg_ts,
+                         uint8_t* has_msg, uint32_t* err_flags, void* stream);
+
+/* a17 TIGE.contrast_learning step 4 (tiger.py:230-241,396-406): for selected positions whose
+ * node has a pending message: right_vals[u] = h_new[gru_row[u]], right_ts[u] = msg_ts[u],
+ * has_msg[u] = 0.  a19: when hprev_left/right are non-NULL also copies left_vals[pos] (before
+ * step 6) and right_vals[pos] (after step 4) - hprev_* are written by a second phase launched
+ * after the write-back, so the pair of launches honours tiger.py:246-251. */
+int tiger_right_writeback(const int64_t* pos_ids, int64_t n_pos, const uint8_t* winner,
+                          const int32_t* gru_row, const float* h_new, int d, float* right_vals,
+                          float* right_ts, uint8_t* right_active, const float* msg_ts,
+                          uint8_t* has_msg, const float* left_vals, float* hprev_left,
+                          float* hprev_right, uint32_t* err_flags, void* stream);
+
+/* a18 TIGE.update_left_memory (tiger.py:408-420): left_vals[u] = h_left[p], left_ts[u] = ts[p]
+ * for selected positions p (ts indexed modulo batch). */
+int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64_t batch, const uint8_t* winner,
+                         const float* h_left, int d, const float* ts, float* left_vals, float* left_ts,
+                         uint8_t* left_active, uint32_t* err_flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Parameter packing: kernels read weights from k-major ("transposed") copies so that
+ * consecutive threads read consecutive addresses.  Re-run whenever the weights change.
+ * ------------------------------------------------------------------------------------- */
+
+/* out[k*ld_out + n] = w[n*ld_in + k] for k<cols, n<rows; columns n in [rows, pad_rows) are zeroed;
+ * columns >= pad_rows are left untouched (several blocks can share one packed row). */
+int tiger_transpose_pad(const float* w, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                        int64_t ld_out, int64_t pad_rows, void* stream);
+
+/* out[r*ld_out + c] = w[r*ld_in + c] for c<cols, zero for c in [cols, ld_out). */
+int tiger_copy_pad(const float* w, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                   int64_t ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense operators
+ * ------------------------------------------------------------------------------------- */
+
+/* a6 + a13  LastMessageAggregatorNoGradLastOnly.forward gather + GRUUpdater.forward
+ * (message_modules.py:150-160, update_modules.py:30-37 = nn.GRUCell, gates r,z,n):
+ *   h_new[r,:] = GRUCell(x = msg rows, h = state rows)
+ * node_ids==NULL: x/h are dense [n,M]/[n,d]; otherwise row r reads x_table[node_ids[r]] and
+ * h_table[node_ids[r]].  count (device, may be NULL) overrides n_rows (n_rows stays the grid
+ * bound).  wT_ih [M][ldw], wT_hh [d][ldw]: k-major packs with ldw >= 3*dp, gate g of hidden
+ * unit j at column g*dp + j (dp = d rounded up to 32).  Also checks the message invariants of
+ * tiger.py:319-327 when check_mem_ts != NULL. */
+int tiger_gru_update(const int64_t* node_ids, const int32_t* count, int64_t n_rows,
+                     const float* x_table, int64_t x_stride, const float* h_table, int64_t h_stride,
+                     int m_dim, int d, const float* wT_ih, const float* wT_hh, int64_t ldw,
+                     const float* b_ih, const float* b_hh, float* h_new,
+                     const float* msg_ts, const float* check_mem_ts, int check_equal,
+                     uint32_t* err_flags, void* stream);
+
+/* packed temporal-attention parameters (device pointers), produced by the host from
+ * temporal_embedding_fn.fns.0.* with tiger_transpose_pad */
+/* E = 2d, C = 2d + de; leading dimensions are rounded up to 4 floats (ldE, ldC, ldD) and every
+ * matrix starts on a 16-byte boundary, so the kernel can stream them with cp.async.bulk. */
+typedef struct {
+  const float* wqT;   /* [E][ldE]   k-major q_proj_weight                     */
+  const float* wk;    /* [E][ldC]   k_proj_weight as stored (row n, col c)    */
+  const float* wvT;   /* [C][ldE]   k-major v_proj_weight                     */
+  const float* woT;   /* [E][ldE]   k-major out_proj.weight                   */
+  const float* fc1T;  /* [E+d][ldD] k-major merger.fc1.weight                 */
+  const float* fc2T;  /* [d][ldD]   k-major merger.fc2.weight                 */
+  const float* in_bias;  /* [3E] in_proj_bias (q,k,v)                         */
+  const float* out_bias; /* [E]                                                */
+  const float* fc1_b;    /* [d]                                                */
+  const float* fc2_b;    /* [d]                                                */
+  const float* time_w;   /* [d] time_encoder.basis_freq                        */
+  const float* time_b;   /* [d] time_encoder.phase                             */
+} tiger_attn_params;
+
+/* a15 + a16  GraphEmbedding.compute_embedding_with_computation_graph (n_layers=1) +
+ * TemporalAttention.forward (temporal_agg_modules.py:29-83,210-235), eval mode, as ONE kernel:
+ * gather (center + K neighbors + edge rows) -> time encoding -> q projection -> folded
+ * single-query attention (scores through W_k^T q, values through W_v applied to the
+ * softmax-pooled keys) -> out projection -> merger MLP.
+ * Node representations: row(u) = sel[u] >= 0 ? rows_b[sel[u]] : rows_a[u]
+ *   fused engine : rows_a = right memory, rows_b = GRU output, sel = gru_row
+ *   class surface: rows_a = NULL, rows_b = involved_node_reprs, sel = local_index
+ * sel is int32 when sel_is_i64==0, int64 otherwise.  q_ts has ts_period entries (ts.repeat(3)).
+ * out [n_query, d]. */
+int tiger_temporal_attention(const int64_t* center_nids, const float* q_ts, int64_t n_query,
+                             int64_t ts_period, const int64_t* neigh_nids, const int64_t* neigh_eids,
+                             const float* neigh_ts, int k, const float* rows_a, const float* rows_b,
+                             const void* sel, int sel_is_i64, const float* nfeats,
+                             const float* efeats, int d, int de, int n_head,
+                             const tiger_attn_params* params, float* out, void* stream);
+
+/* Same operator with the dense argument list of TemporalAttention.forward
+ * (temporal_agg_modules.py:210-235): qx [n,d], qt [n,d], kx [n,K,d], ky [n,K,de], kt [n,K,d],
+ * padding_mask [n,K] (1 = padding). */
+int tiger_temporal_attention_dense(const float* qx, const float* qt, const float* kx, const float* ky,
+                                   const float* kt, const uint8_t* padding_mask, int64_t n_query, int k,
+                                   int d, int de, int n_head, const tiger_attn_params* params, float* out,
+                                   void* stream);
+
+/* step 7 of TIGE.contrast_learning (tiger.py:259-288), hit_type 'bin' or 'none': hit flags
+ * from the neighbor table, hit embedding, score_fn MergeLayer on positive / negative pairs,
+ * BCE-with-logits mean.  h [3B,d] = embeddings of [src;dst;neg]; neigh_nids [3B,K] (may be
+ * NULL when hit_emb is NULL).  fc1T [2d][ldD] k-major (ldD = d rounded up to 4), fc2_w [d].  scores [2B] = pos then neg. */
+int tiger_link_score(const float* h, int64_t batch, int d, const int64_t* src, const int64_t* dst,
+                     const int64_t* neg, const int64_t* neigh_nids, int k, const float* hit_emb,
+                     const float* fc1T, const float* fc1_b, const float* fc2_w, const float* fc2_b,
+                     float* scores, float* loss, uint32_t* done_counter, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Restarters (tiger/model/restarters.py, tiger.py:594-609)
+ * ------------------------------------------------------------------------------------- */
+
+/* a23 + a24  StaticRestarter.forward + TIGER.restart: for each listed node u:
+ *   prev_ts = time of the last event of u strictly before t (0 if none), t = min(batch_ts) when
+ *   batch_ts != NULL (restart() is called with ts.min(), train_self_supervised.py:161), else
+ *   q_ts[i];  left_vals[u]=left_emb[u], right_vals[u]=right_emb[u], both update_ts = prev_ts,
+ *   has_msg[u] = 0.  out_prev_ts (may be NULL) receives prev_ts per listed node. */
+int tiger_static_restart(const int64_t* nids, const int32_t* count, int64_t n,
+                         const float* batch_ts, int64_t batch, const double* q_ts,
+                         const int64_t* indptr, const double* adj_ts, const float* left_emb,
+                         const float* right_emb, int d, float* left_vals, float* left_ts,
+                         uint8_t* left_active, float* right_vals, float* right_ts,
+                         uint8_t* right_active, uint8_t* has_msg, float* out_prev_ts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIGER_B200_H */

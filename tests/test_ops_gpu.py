@@ -1,0 +1,276 @@
+"""GPU parity of every C-ABI operator against the CPU oracle (and the reference's golden
+vectors).  Index results are compared bit-exactly, fp32 results with max|a-b|/max|b| <= 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tiger_oracle as O
+from golden_utils import CASES, Golden, assert_close
+from www2023tiger_b200 import ops
+from www2023tiger_b200.init import perturb_biases, random_weights
+from www2023tiger_b200.synthetic import StreamShape, make_stream
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def gu():
+    import gpu_utils
+    return gpu_utils
+
+
+def small_stream(seed=0, n_events=6000, horizon=4000.):
+    return make_stream(StreamShape('t', 300, 40, n_events, 8, None, horizon=horizon), seed=seed)
+
+
+# ------------------------------------------------------------------ a1: CSR build
+@pytest.mark.parametrize('n_events', [0, 1, 37, 6000, 70000])
+def test_csr_build_matches_oracle(gu, n_events):
+    st = small_stream(n_events=max(n_events, 1))
+    src, dst, ts, eids = (x[:n_events] for x in (st.src, st.dst, st.ts, st.eids))
+    N = st.n_nodes
+    g = O.OracleGraph(src, dst, ts, eids, n_nodes=N)
+    c = gu.device_csr(src, dst, ts, eids, N)
+    assert np.array_equal(gu.cpu(c.indptr), g.indptr)
+    assert np.array_equal(gu.cpu(c.nbr), g.nbr) and np.array_equal(gu.cpu(c.eid), g.eid)
+    assert np.array_equal(gu.cpu(c.ts), g.ts) and np.array_equal(gu.cpu(c.flag), g.flag)
+
+
+def test_csr_build_many_nodes(gu):
+    # > 2^16 node ids exercises three radix passes
+    rng = np.random.RandomState(0)
+    E, N = 50000, 200001
+    src = rng.randint(1, 100000, E).astype(np.int64)
+    dst = rng.randint(100000, N, E).astype(np.int64)
+    ts = np.floor(np.sort(rng.uniform(0, 1e5, E)))
+    eids = np.arange(1, E + 1, dtype=np.int64)
+    g = O.OracleGraph(src, dst, ts, eids, n_nodes=N)
+    c = gu.device_csr(src, dst, ts, eids, N)
+    assert np.array_equal(gu.cpu(c.indptr), g.indptr) and np.array_equal(gu.cpu(c.nbr), g.nbr)
+    assert np.array_equal(gu.cpu(c.eid), g.eid) and np.array_equal(gu.cpu(c.flag), g.flag)
+
+
+# ------------------------------------------------------------------ a2: finder
+@pytest.mark.parametrize('k', [1, 10, 40])
+def test_find_recent_matches_oracle(gu, k):
+    st = small_stream(seed=3, n_events=30000, horizon=3000.)   # popular items have > 1000 events: deep search
+    N = st.n_nodes
+    g = O.OracleGraph(st.src, st.dst, st.ts, st.eids, n_nodes=N)
+    c = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
+    rng = np.random.RandomState(k)
+    q_n = np.concatenate([rng.randint(0, N, 3000), st.dst[rng.randint(0, len(st.dst), 2000)]]).astype(np.int64)
+    q_t = np.concatenate([np.floor(rng.uniform(-5, 3100, 4000)), st.ts[rng.randint(0, len(st.ts), 1000)]])
+    ref = g.find_recent(q_n, q_t, k)
+    got = ops.find_recent(c, gu.dev(q_n), gu.dev(q_t, torch.float64), k)
+    for a, b in zip(got, ref):
+        assert np.array_equal(gu.cpu(a), b)
+    assert gu.cpu(got[2]).dtype == np.float32
+
+
+def test_find_recent_ts_period_and_bitmap(gu):
+    st = small_stream(seed=5)
+    N = st.n_nodes
+    g = O.OracleGraph(st.src, st.dst, st.ts, st.eids, n_nodes=N)
+    c = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
+    B, K = 50, 7
+    lo = 3000
+    src, dst, ts = st.src[lo:lo + B], st.dst[lo:lo + B], st.ts[lo:lo + B]
+    neg = np.random.RandomState(0).randint(301, N, B).astype(np.int64)
+    b = O.collate(g, src, dst, neg, ts, st.eids[lo:lo + B], K)
+    bitmap = torch.zeros(ops.bitmap_words(N), dtype=torch.int32, device='cuda')
+    ts32 = torch.zeros(B, device='cuda')
+    nn_, ne_, nt_, _ = ops.find_recent(c, gu.dev(np.concatenate([src, dst, neg])), gu.dev(ts, torch.float64), K,
+                                       ts_period=B, want_dirs=False, ts32_out=ts32, bitmap=bitmap)
+    assert np.array_equal(gu.cpu(nn_), b.neigh_nids) and np.array_equal(gu.cpu(ne_), b.neigh_eids)
+    assert np.array_equal(gu.cpu(nt_), b.neigh_ts) and np.array_equal(gu.cpu(ts32), b.ts)
+    # compaction: involved / local_index / outdated
+    has_msg = torch.zeros(N, dtype=torch.uint8, device='cuda')
+    pend = b.involved[::3]
+    has_msg[gu.dev(pend)] = 1
+    cap = 3 * B * (K + 1)
+    involved = torch.zeros(cap, dtype=torch.int64, device='cuda')
+    outdated = torch.zeros(cap, dtype=torch.int64, device='cuda')
+    local_index = torch.zeros(N, dtype=torch.int64, device='cuda')
+    gru_row = torch.full((N,), -7, dtype=torch.int32, device='cuda')
+    counts = torch.zeros(4, dtype=torch.int32, device='cuda')
+    ops.compact_involved(bitmap, N, involved, counts, has_msg=has_msg, local_index=local_index, outdated=outdated,
+                         gru_row=gru_row)
+    U, Oc = int(counts[0]), int(counts[1])
+    assert np.array_equal(gu.cpu(involved[:U]), b.involved)
+    assert np.array_equal(gu.cpu(local_index), b.local_index)
+    assert np.array_equal(gu.cpu(outdated[:Oc]), pend)
+    gr = gu.cpu(gru_row)
+    assert np.array_equal(gr[pend], np.arange(len(pend))) and (gr[np.setdiff1d(b.involved, pend)] == -1).all()
+    assert int(bitmap.abs().sum()) == 0
+    # hit windows
+    for center, rows, want in ((src, nn_[B:2 * B], b.src_hits), (dst, nn_[:B], b.dst_hits),
+                               (src, nn_[2 * B:], b.neg_src_hits), (neg, nn_[:B], b.neg_dst_hits)):
+        assert np.array_equal(gu.cpu(ops.hit_window(gu.dev(center), rows.contiguous())), want)
+
+
+def test_golden_history_known_answers(gu):
+    for name in CASES:
+        g = Golden(name)
+        c = gu.device_csr(g.src, g.dst, g.ts, g.eids, g.N)
+        z = g.z
+        got = ops.find_recent(c, gu.dev(z['kat_hist_q_nids']), gu.dev(z['kat_hist_q_ts'], torch.float64), 7)
+        for a, key in zip(got, ('kat_hist_nids', 'kat_hist_eids', 'kat_hist_ts', 'kat_hist_dirs')):
+            assert np.array_equal(gu.cpu(a), z[key]), (name, key)
+
+
+# ------------------------------------------------------------------ a8 / a22
+@pytest.mark.parametrize('n,dtype', [(1, np.float32), (60, np.float32), (400, np.float32), (400, np.float64),
+                                     (2048, np.float32), (2049, np.float32), (20000, np.float64)])
+def test_select_latest_matches_oracle(gu, n, dtype):
+    rng = np.random.RandomState(n)
+    n_nodes = 5000
+    ids = rng.randint(0, max(2, min(n_nodes, n // 3 + 2)), n).astype(np.int64)
+    ts = np.floor(rng.uniform(0, 25, n)).astype(dtype)      # many ties
+    if dtype == np.float64:
+        ts = ts + 1e-9 * rng.randint(0, 3, n)                # distinct in f64, equal in f32
+    u, ix = O.select_latest_scan(ids, ts)
+    scratch = ops.SelectScratch(n_nodes, 'cuda')
+    winner, du, dix, cnt = ops.select_latest(gu.dev(ids), gu.dev(ts), scratch)
+    c = int(cnt)
+    assert c == len(u)
+    assert np.array_equal(gu.cpu(du[:c]), u) and np.array_equal(gu.cpu(dix[:c]), ix)
+    w = np.zeros(n, dtype=np.uint8)
+    w[ix] = 1
+    assert np.array_equal(gu.cpu(winner), w)
+    assert int(scratch.slot_ts.abs().sum()) == 0 and int(scratch.slot_pos.abs().sum()) == 0
+    assert int(scratch.bitmap.abs().sum()) == 0
+    # flags only (engine form)
+    winner2, _, _, _ = ops.select_latest(gu.dev(ids), gu.dev(ts), scratch, want_unique=False)
+    assert np.array_equal(gu.cpu(winner2), w)
+    assert int(scratch.slot_ts.abs().sum()) == 0 and int(scratch.slot_pos.abs().sum()) == 0
+
+
+def test_select_latest_golden_and_repeat_semantics(gu):
+    z = Golden(CASES[0]).z
+    _, du, dix, cnt = ops.select_latest(gu.dev(z['kat_sl_ids']), gu.dev(z['kat_sl_ts']))
+    c = int(cnt)
+    assert np.array_equal(gu.cpu(du[:c]), z['kat_sl_unique']) and np.array_equal(gu.cpu(dix[:c]), z['kat_sl_index'])
+    # ts.repeat(2): ts shorter than ids
+    rng = np.random.RandomState(1)
+    src, dst = rng.randint(1, 30, 100), rng.randint(30, 40, 100)
+    ts = np.floor(np.sort(rng.uniform(0, 40, 100))).astype(np.float32)
+    u, ix = O.select_latest(np.concatenate([src, dst]), np.tile(ts, 2))
+    _, du, dix, cnt = ops.select_latest(gu.dev(np.concatenate([src, dst])), gu.dev(ts))
+    c = int(cnt)
+    assert np.array_equal(gu.cpu(du[:c]), u) and np.array_equal(gu.cpu(dix[:c]), ix)
+
+
+def test_anonymized_reindex(gu):
+    z = Golden(CASES[0]).z
+    assert np.array_equal(gu.cpu(ops.anonymized_reindex(gu.dev(z['kat_anon_in']))), z['kat_anon_out'])
+    rng = np.random.RandomState(0)
+    h = rng.randint(0, 9, (300, 40)).astype(np.int64)
+    h[:, :10][rng.rand(300, 10) < 0.5] = 0
+    assert np.array_equal(gu.cpu(ops.anonymized_reindex(gu.dev(h))), O.anonymized_reindex(h))
+    ex = np.array([[0, 0, 5, 7, 5], [3, 4, 3, 3, 9]], dtype=np.int64)
+    assert gu.cpu(ops.anonymized_reindex(gu.dev(ex))).tolist() == [[0, 0, 1, 2, 1], [2, 3, 2, 2, 1]]
+
+
+# ------------------------------------------------------------------ a10 / a11
+def test_time_encode_and_memory_rows(gu):
+    d = 172
+    W = perturb_biases(random_weights(d, d))
+    w, b = W['time_encoder.basis_freq'], W['time_encoder.phase']
+    ts = torch.cat([torch.zeros(3), torch.rand(500) * 2.6e6, torch.tensor([2.678e6, 1.0, 86400.])])
+    got = ops.time_encode(gu.dev(ts), gu.dev(w), gu.dev(b))
+    assert_close(gu.cpu(got), O.time_encode(ts, w, b).numpy(), TOL, 'time_encode')
+    table = torch.randn(1000, d)
+    tst = torch.rand(1000)
+    ids = torch.randint(0, 1000, (333,))
+    v, t = ops.gather_rows(gu.dev(table), gu.dev(ids), gu.dev(tst))
+    assert torch.equal(v.cpu(), table[ids]) and torch.equal(t.cpu(), tst[ids])
+    dt, dts = gu.dev(table), gu.dev(tst)
+    uid = torch.randperm(1000)[:200]
+    vals, nts = torch.randn(200, d), tst[uid] + 1
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    act = torch.zeros(1000, dtype=torch.uint8, device='cuda')
+    ops.scatter_rows(dt, gu.dev(uid), gu.dev(vals), ts_table=dts, ts=gu.dev(nts), active=act, check=True, err_flags=err)
+    table[uid], tst[uid] = vals, nts
+    assert torch.equal(dt.cpu(), table) and torch.equal(dts.cpu(), tst) and int(err) == 0
+    assert int(act.sum()) == 200
+    ops.scatter_rows(dt, gu.dev(uid[:5]), gu.dev(vals[:5]), ts_table=dts, ts=gu.dev(nts[:5] - 5), check=True,
+                     err_flags=err)
+    assert int(err) == 1       # "not allowed to modify past memory"
+
+
+# ------------------------------------------------------------------ a13: GRU
+@pytest.mark.parametrize('d,de,n', [(172, 172, 1426), (172, 172, 1), (100, 4, 65), (100, 100, 64), (10, 4, 37),
+                                    (12, 8, 200), (8, 8, 63)])
+def test_gru_update_matches_oracle(gu, d, de, n):
+    W = random_weights(d, de, seed=d + n)
+    c = 'right_mem_updater.cell.'
+    M = 3 * d + de
+    g = torch.Generator().manual_seed(n)
+    x, h = torch.randn(n, M, generator=g), torch.randn(n, d, generator=g)
+    want = O.gru_cell(x, h, W[c + 'weight_ih'], W[c + 'weight_hh'], W[c + 'bias_ih'], W[c + 'bias_hh'])
+    pack = ops.GruPack(*(gu.dev(W[c + k]) for k in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')))
+    got = ops.gru_update(pack, node_ids=None, x_table=gu.dev(x), h_table=gu.dev(h), n_rows=n)
+    assert_close(gu.cpu(got), want.numpy(), TOL, f'gru dense d={d}')
+    # gathered form with a device-side count
+    N = 3 * n + 5
+    xt, ht = torch.randn(N, M, generator=g), torch.randn(N, d, generator=g)
+    ids = torch.randperm(N, generator=g)[:n]
+    want = O.gru_cell(xt[ids], ht[ids], W[c + 'weight_ih'], W[c + 'weight_hh'], W[c + 'bias_ih'], W[c + 'bias_hh'])
+    ids_pad = torch.cat([ids, torch.zeros(100, dtype=torch.int64)])
+    out = torch.full((n + 100, d), 7.0, device='cuda')
+    cnt = torch.tensor([n], dtype=torch.int32, device='cuda')
+    ops.gru_update(pack, node_ids=gu.dev(ids_pad), x_table=gu.dev(xt), h_table=gu.dev(ht), n_rows=n + 100, out=out,
+                   count=cnt)
+    assert_close(gu.cpu(out[:n]), want.numpy(), TOL, f'gru gathered d={d}')
+    assert float(out[n:].min()) == 7.0 and float(out[n:].max()) == 7.0
+
+
+# ------------------------------------------------------------------ a15/a16: attention
+@pytest.mark.parametrize('d,de,n,k,H', [(172, 172, 600, 10, 2), (172, 172, 5, 10, 2), (100, 4, 300, 10, 2),
+                                        (100, 100, 151, 10, 2), (10, 4, 75, 5, 2), (12, 8, 90, 5, 2),
+                                        (8, 8, 120, 5, 4), (16, 6, 33, 3, 1)])
+def test_temporal_attention_dense_matches_oracle(gu, d, de, n, k, H):
+    W = perturb_biases(random_weights(d, de, seed=n))
+    g = torch.Generator().manual_seed(n)
+    qx, qt = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+    kx, ky, kt = torch.randn(n, k, d, generator=g), torch.randn(n, k, de, generator=g), torch.randn(n, k, d, generator=g)
+    mask = torch.rand(n, k, generator=g) < 0.3
+    mask[::7] = True                     # rows where every slot is padding
+    mask[1::7, :-1] = True               # exactly one live slot
+    p = 'temporal_embedding_fn.fns.0.'
+    want = O.temporal_attention(W, p, H, qx, qt, kx, ky, kt, mask)
+    pack = ops.AttnPack(d, de, 'cuda')
+    m = p + 'mha_fn.'
+    pack.refresh(*(gu.dev(W[x]) for x in (m + 'q_proj_weight', m + 'k_proj_weight', m + 'v_proj_weight',
+                                            m + 'in_proj_bias', m + 'out_proj.weight', m + 'out_proj.bias',
+                                            p + 'merger.fc1.weight', p + 'merger.fc1.bias', p + 'merger.fc2.weight',
+                                            p + 'merger.fc2.bias', 'time_encoder.basis_freq', 'time_encoder.phase')))
+    got = ops.temporal_attention_dense(pack, H, gu.dev(qx), gu.dev(qt), gu.dev(kx), gu.dev(ky), gu.dev(kt),
+                                       gu.dev(mask))
+    assert_close(gu.cpu(got), want.numpy(), TOL, f'attention dense d={d} de={de} n={n}')
+
+
+# ------------------------------------------------------------------ step 7: scorer
+@pytest.mark.parametrize('d,B,k', [(172, 200, 10), (100, 37, 10), (10, 25, 5)])
+def test_link_score_matches_oracle(gu, d, B, k):
+    W = perturb_biases(random_weights(d, d, seed=B))
+    g = torch.Generator().manual_seed(B)
+    h = torch.randn(3 * B, d, generator=g)
+    src, dst, neg = (torch.randint(1, 40, (B,), generator=g) for _ in range(3))
+    neigh = torch.randint(0, 40, (3 * B, k), generator=g)
+    x, y, ny = h.reshape(3, B, d)
+    emb = W['hit_embedding.weight']
+    flag = lambda c, rows: (c[:, None] == rows).any(1).long()
+    xp, yp = x + emb[flag(src, neigh[B:2 * B])], y + emb[flag(dst, neigh[:B])]
+    xn, yn = x + emb[flag(src, neigh[2 * B:])], ny + emb[flag(neg, neigh[:B])]
+    sw = [W['score_fn.' + n] for n in ('fc1.weight', 'fc1.bias', 'fc2.weight', 'fc2.bias')]
+    ps, ns = O.merge_layer(xp, yp, *sw).squeeze(1), O.merge_layer(xn, yn, *sw).squeeze(1)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(torch.cat([ps, ns]),
+                                                                torch.cat([torch.ones(B), torch.zeros(B)]))
+    pack = ops.ScorePack(d, 'cuda')
+    pack.refresh(*(gu.dev(t) for t in sw), gu.dev(emb))
+    for _ in range(2):                    # twice: the done-counter must reset itself
+        scores, dl = ops.link_score(pack, gu.dev(h), gu.dev(src), gu.dev(dst), gu.dev(neg), gu.dev(neigh))
+        assert_close(gu.cpu(scores), torch.cat([ps, ns]).numpy(), TOL, 'scores')
+        assert_close(gu.cpu(dl), loss.reshape(1).numpy(), TOL, 'loss')

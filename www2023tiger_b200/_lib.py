@@ -1,0 +1,118 @@
+"""ctypes binding of libtiger_b200.so (the C ABI declared in include/tiger_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails,
+the operators raise.  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import os
+import re
+from typing import Dict, List
+
+import torch
+
+from .build import INCLUDE, LIB_PATH
+
+P, L, I = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+
+# argument kinds per entry point: p = device/host pointer, l = int64, i = int
+_SIGNATURES: Dict[str, str] = {
+    'tiger_abi_version': '',
+    'tiger_csr_build_work_bytes': 'll',
+    'tiger_csr_build': 'ppppll' + 'ppppp' + 'p' + 'p',
+    'tiger_find_recent': 'ppppp' + 'pp' + 'lli' + 'pppp' + 'pp' + 'p',
+    'tiger_hit_window': 'ppli' + 'p' + 'p',
+    'tiger_mark_nodes': 'plpl' + 'p',
+    'tiger_compact_involved': 'plpp' + 'plp' + 'ppp' + 'pp' + 'p',
+    'tiger_select_latest': 'ppil' + 'llppp' + 'pppp' + 'p',
+    'tiger_anonymized_reindex': 'plip' + 'p',
+    'tiger_gather_rows': 'plplp' + 'pp' + 'p',
+    'tiger_scatter_rows': 'plplp' + 'ppp' + 'pip' + 'p',
+    'tiger_time_encode': 'plppip' + 'p',
+    'tiger_store_messages': 'ppppl' + 'ppp' + 'ppii' + 'pppp' + 'pp' + 'p',
+    'tiger_right_writeback': 'plp' + 'ppi' + 'pppp' + 'pppp' + 'p' + 'p',
+    'tiger_left_writeback': 'pllp' + 'pip' + 'ppp' + 'p' + 'p',
+    'tiger_transpose_pad': 'plllpll' + 'p',
+    'tiger_copy_pad': 'plllpl' + 'p',
+    'tiger_gru_update': 'ppl' + 'plpl' + 'ii' + 'ppl' + 'ppp' + 'ppi' + 'p' + 'p',
+    'tiger_temporal_attention': 'ppll' + 'pppi' + 'pppi' + 'pp' + 'iii' + 'pp' + 'p',
+    'tiger_temporal_attention_dense': 'pppppp' + 'li' + 'iii' + 'pp' + 'p',
+    'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
+    'tiger_static_restart': 'ppl' + 'plp' + 'pp' + 'ppi' + 'ppp' + 'ppp' + 'pp' + 'p',
+}
+_KIND = {'p': P, 'l': L, 'i': I}
+
+ERR_BITS = {
+    1: 'You are not allowed to modify past memory.',
+    2: 'Node has unused messages.',
+    4: 'Messages happened later than memory updating.',
+    8: "Messages' ts should be equal to last update ts when using left memory as msg source.",
+    16: 'Events occur before the udpated memory.',
+    32: 'involved-node capacity exceeded',
+}
+
+
+class TigerLibraryError(RuntimeError):
+    pass
+
+
+def header_symbols() -> List[str]:
+    """Every function name include/tiger_b200.h declares."""
+    text = open(os.path.join(INCLUDE, 'tiger_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(tiger_[a-z0-9_]+)\s*\(', text)))
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (built in-tree by www2023tiger_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TigerLibraryError(
+            f'{LIB_PATH} is missing: run `python -m www2023tiger_b200.build` (or __graft_entry__.build()). '
+            'There is no CPU fallback for the TIGER memory path.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, sig in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_KIND[c] for c in sig]
+        fn.restype = L if name == 'tiger_csr_build_work_bytes' else I
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device (or pinned host) pointer of a tensor; None -> NULL."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an entry point on the current CUDA stream (appended as the last argument)."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    if rc != 0:
+        raise TigerLibraryError(f'{name} failed with code {rc} '
+                                f'({"invalid argument" if rc == -1 else "CUDA launch error"})')
+
+
+def check_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TigerLibraryError('TIGER B200 operators need CUDA tensors; there is no CPU fallback.')
+        if t is not None and not t.is_contiguous():
+            raise TigerLibraryError('TIGER B200 operators need contiguous tensors.')
+
+
+def raise_on_err_flags(flags: int):
+    """Translate the device error word into the reference's ValueError messages."""
+    if flags:
+        msgs = [m for b, m in ERR_BITS.items() if flags & b]
+        raise ValueError('; '.join(msgs))

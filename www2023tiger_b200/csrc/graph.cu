@@ -1,0 +1,204 @@
+// Temporal neighbor finder over a per-node time-sorted CSR, involved-node marking and
+// ordered compaction.  Integer / index work: every result is bit-exact with the reference
+// (tiger/data/graph.py:44-53,117-127,150-155; tiger/data/data_loader.py:61-67,105-131;
+// tiger/data/data_classes.py:163-165; tiger/model/memory.py:108-126).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// K1  one warp per query: 32-ary cooperative lower-bound search on the float64 timestamps of
+// the node's CSR segment (strict '<', np.searchsorted side='left'), then a coalesced gather of
+// the K entries that precede the cut, right-aligned, zero-padded on the left.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+find_recent_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ adj_nbr,
+                   const int32_t* __restrict__ adj_eid, const double* __restrict__ adj_ts,
+                   const uint8_t* __restrict__ adj_flag, const int64_t* __restrict__ q_nids,
+                   const double* __restrict__ q_ts, int64_t n_query, int64_t ts_period, int k,
+                   int64_t* __restrict__ out_nids, int64_t* __restrict__ out_eids,
+                   float* __restrict__ out_ts, int64_t* __restrict__ out_dirs,
+                   float* __restrict__ out_ts32, uint32_t* __restrict__ bitmap) {
+  const int lane = lane_id();
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block();
+  if (q >= n_query) return;
+  const int64_t nid = q_nids[q];
+  const double t = q_ts[q % ts_period];
+  if (out_ts32 != nullptr && q < ts_period && lane == 0) out_ts32[q] = (float)t;
+  const int64_t beg = indptr[nid];
+  const int64_t end = indptr[nid + 1];
+  const int64_t cut = warp_lower_bound(adj_ts, beg, end, t, lane);
+  if (bitmap != nullptr && lane == 0) atomicOr(bitmap + (nid >> 5), 1u << (nid & 31));
+  for (int kk = lane; kk < k; kk += 32) {
+    const int64_t s = cut - k + kk;
+    int64_t nb = 0, ei = 0, dr = 0;
+    float tv = 0.f;
+    if (s >= beg) {
+      nb = adj_nbr[s];
+      ei = adj_eid[s];
+      tv = (float)adj_ts[s];  // float64 -> float32, round-to-nearest (graph.py:91,126)
+      dr = adj_flag[s];
+    }
+    const int64_t o = q * k + kk;
+    out_nids[o] = nb;
+    out_eids[o] = ei;
+    out_ts[o] = tv;
+    if (out_dirs != nullptr) out_dirs[o] = dr;
+    if (bitmap != nullptr) atomicOr(bitmap + (nb >> 5), 1u << (nb & 31));
+  }
+}
+
+extern "C" int tiger_find_recent(const int64_t* indptr, const int32_t* adj_nbr, const int32_t* adj_eid,
+                                 const double* adj_ts, const uint8_t* adj_flag, const int64_t* q_nids,
+                                 const double* q_ts, int64_t n_query, int64_t ts_period, int k,
+                                 int64_t* out_nids, int64_t* out_eids, float* out_ts, int64_t* out_dirs,
+                                 float* out_ts32, uint32_t* mark_bitmap, void* stream) {
+  if (n_query < 0 || k <= 0 || ts_period < 0) return TIGER_EINVAL;
+  if (n_query == 0) return TIGER_OK;
+  if (ts_period == 0) ts_period = n_query;
+  const int warps = 8;
+  const unsigned grid = (unsigned)((n_query + warps - 1) / warps);
+  find_recent_kernel<<<grid, warps * 32, 0, as_stream(stream)>>>(
+      indptr, adj_nbr, adj_eid, adj_ts, adj_flag, q_nids, q_ts, n_query, ts_period, k, out_nids, out_eids,
+      out_ts, out_dirs, out_ts32, mark_bitmap);
+  return tiger_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// hit window (data_loader.py:61-67)
+// ------------------------------------------------------------------------------------------
+__global__ void hit_window_kernel(const int64_t* __restrict__ center, const int64_t* __restrict__ neigh,
+                                  int64_t total, int k, float* __restrict__ hit) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  hit[i] = (center[i / k] == neigh[i]) ? 1.0f : 0.0f;
+}
+
+extern "C" int tiger_hit_window(const int64_t* center, const int64_t* neigh, int64_t n, int k, float* hit,
+                                void* stream) {
+  if (n < 0 || k <= 0) return TIGER_EINVAL;
+  const int64_t total = n * k;
+  if (total == 0) return TIGER_OK;
+  hit_window_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(center, neigh, total, k, hit);
+  return tiger_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// involved-node bitmap: mark + ordered compaction
+// ------------------------------------------------------------------------------------------
+__global__ void mark_nodes_kernel(const int64_t* __restrict__ ids, int64_t n, uint32_t* __restrict__ bitmap,
+                                  int64_t n_nodes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t u = ids[i];
+  if (u >= 0 && u < n_nodes) atomicOr(bitmap + (u >> 5), 1u << (u & 31));
+}
+
+extern "C" int tiger_mark_nodes(const int64_t* ids, int64_t n, uint32_t* bitmap, int64_t n_nodes, void* stream) {
+  if (n < 0) return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  mark_nodes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(ids, n, bitmap, n_nodes);
+  return tiger_launch_status();
+}
+
+// exclusive scan of three per-thread counters over a 1024-thread block
+__device__ __forceinline__ void block_exscan3(int& a, int& b, int& c, int* total, int (*sm)[32]) {
+  const int lane = lane_id(), warp = warp_id_in_block();
+  int ia = a, ib = b, ic = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ta = __shfl_up_sync(TIGER_FULL_MASK, ia, o);
+    const int tb = __shfl_up_sync(TIGER_FULL_MASK, ib, o);
+    const int tc = __shfl_up_sync(TIGER_FULL_MASK, ic, o);
+    if (lane >= o) { ia += ta; ib += tb; ic += tc; }
+  }
+  if (lane == 31) { sm[0][warp] = ia; sm[1][warp] = ib; sm[2][warp] = ic; }
+  __syncthreads();
+  if (warp == 0) {
+    int va = sm[0][lane], vb = sm[1][lane], vc = sm[2][lane];
+    int sa = va, sb = vb, sc = vc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(TIGER_FULL_MASK, sa, o);
+      const int tb = __shfl_up_sync(TIGER_FULL_MASK, sb, o);
+      const int tc = __shfl_up_sync(TIGER_FULL_MASK, sc, o);
+      if (lane >= o) { sa += ta; sb += tb; sc += tc; }
+    }
+    sm[0][lane] = sa - va; sm[1][lane] = sb - vb; sm[2][lane] = sc - vc;
+    if (lane == 31) { total[0] = sa; total[1] = sb; total[2] = sc; }
+  }
+  __syncthreads();
+  a = ia - a + sm[0][warp];
+  b = ib - b + sm[1][warp];
+  c = ic - c + sm[2][warp];
+}
+
+__global__ void __launch_bounds__(1024)
+compact_involved_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, uint8_t* __restrict__ has_msg,
+                        uint8_t* __restrict__ uptodate, int64_t* __restrict__ involved, int64_t cap,
+                        int64_t* __restrict__ local_index, int64_t* __restrict__ outdated,
+                        int32_t* __restrict__ gru_row, int64_t* __restrict__ restart_nodes,
+                        int32_t* __restrict__ counts, uint32_t* __restrict__ err_flags) {
+  __shared__ int sm[3][32];
+  __shared__ int total[3];
+  const int tid = threadIdx.x;
+  const int64_t wpt = (n_words + blockDim.x - 1) / blockDim.x;
+  const int64_t w0 = (int64_t)tid * wpt;
+  const int64_t w1 = (w0 + wpt < n_words) ? (w0 + wpt) : n_words;
+  int c_inv = 0, c_out = 0, c_rst = 0;
+  for (int64_t w = w0; w < w1; ++w) {
+    uint32_t bits = bitmap[w];
+    c_inv += __popc(bits);
+    while (bits) {
+      const int64_t u = w * 32 + (__ffs(bits) - 1);
+      bits &= bits - 1;
+      const bool rst = (uptodate != nullptr) && (uptodate[u] == 0);
+      c_rst += rst;
+      c_out += (has_msg != nullptr) && (has_msg[u] != 0) && !rst;
+    }
+  }
+  int o_inv = c_inv, o_out = c_out, o_rst = c_rst;
+  block_exscan3(o_inv, o_out, o_rst, total, sm);
+  for (int64_t w = w0; w < w1; ++w) {
+    uint32_t bits = bitmap[w];
+    if (bits) bitmap[w] = 0u;
+    while (bits) {
+      const int64_t u = w * 32 + (__ffs(bits) - 1);
+      bits &= bits - 1;
+      if (o_inv < cap) involved[o_inv] = u;
+      if (local_index != nullptr) local_index[u] = o_inv;
+      ++o_inv;
+      const bool rst = (uptodate != nullptr) && (uptodate[u] == 0);
+      const bool pend = (has_msg != nullptr) && (has_msg[u] != 0) && !rst;
+      if (rst) {
+        if (o_rst < cap) restart_nodes[o_rst] = u;
+        ++o_rst;
+        uptodate[u] = 1;
+        if (has_msg != nullptr) has_msg[u] = 0;  // msg_store.clear(nids): memory.py:136
+      }
+      if (gru_row != nullptr) gru_row[u] = pend ? o_out : -1;
+      if (pend) {
+        if (o_out < cap) outdated[o_out] = u;
+        ++o_out;
+      }
+    }
+  }
+  if (tid == 0) {
+    counts[0] = total[0] < cap ? total[0] : (int)cap;
+    counts[1] = total[1] < cap ? total[1] : (int)cap;
+    counts[2] = total[2] < cap ? total[2] : (int)cap;
+    if (total[0] > cap && err_flags != nullptr) atomicOr(err_flags, TIGER_ERR_CAPACITY);
+  }
+}
+
+extern "C" int tiger_compact_involved(uint32_t* bitmap, int64_t n_nodes, uint8_t* has_msg, uint8_t* uptodate,
+                                      int64_t* involved, int64_t cap_involved, int64_t* local_index,
+                                      int64_t* outdated, int32_t* gru_row, int64_t* restart_nodes,
+                                      int32_t* counts, uint32_t* err_flags, void* stream) {
+  if (n_nodes <= 0 || cap_involved <= 0 || counts == nullptr || involved == nullptr) return TIGER_EINVAL;
+  if (has_msg != nullptr && outdated == nullptr) return TIGER_EINVAL;
+  if (uptodate != nullptr && restart_nodes == nullptr) return TIGER_EINVAL;
+  const int64_t n_words = (n_nodes + 31) / 32;
+  compact_involved_kernel<<<1, 1024, 0, as_stream(stream)>>>(bitmap, n_words, has_msg, uptodate, involved,
+                                                            cap_involved, local_index, outdated, gru_row,
+                                                            restart_nodes, counts, err_flags);
+  return tiger_launch_status();
+}

@@ -1,0 +1,268 @@
+// Node memory tables, the last-message store and their write-backs: HBM-bound row gathers and
+// scatters, one warp per row, 16-byte vectors where the row alignment allows it.
+// Reference: tiger/model/memory.py:12-138, tiger/model/time_encoding.py,
+// tiger/model/tiger.py:230-255,396-442.
+#include "common.cuh"
+
+#define ROW_WARPS 8  // warps (rows) per CTA for the row kernels
+
+__device__ __forceinline__ int64_t effective_count(const int32_t* count, int64_t n) {
+  if (count == nullptr) return n;
+  const int64_t c = *count;
+  return c < n ? c : n;
+}
+
+// ---------------------------------------------------------------- a11 Memory.get
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+gather_rows_kernel(const float* __restrict__ table, int64_t width, const int64_t* __restrict__ ids, int64_t n,
+                   float* __restrict__ out, const float* __restrict__ ts_table, float* __restrict__ out_ts) {
+  const int64_t r = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
+  if (r >= n) return;
+  const int lane = lane_id();
+  const int64_t u = ids[r];
+  if (out != nullptr) warp_copy_row(out + r * width, table + u * width, (int)width, lane);
+  if (out_ts != nullptr && lane == 0) out_ts[r] = ts_table[u];
+}
+
+extern "C" int tiger_gather_rows(const float* table, int64_t width, const int64_t* ids, int64_t n, float* out,
+                                 const float* ts_table, float* out_ts, void* stream) {
+  if (n < 0 || width < 0) return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  gather_rows_kernel<<<(unsigned)((n + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      table, width, ids, n, out, ts_table, out_ts);
+  return tiger_launch_status();
+}
+
+// ---------------------------------------------------------------- a11 Memory.set
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+scatter_rows_kernel(float* __restrict__ table, int64_t width, const int64_t* __restrict__ ids, int64_t n,
+                    const int32_t* __restrict__ count, const float* __restrict__ vals,
+                    float* __restrict__ ts_table, const float* __restrict__ ts, uint8_t* __restrict__ active,
+                    int check, uint32_t* __restrict__ err_flags) {
+  const int64_t r = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
+  if (r >= effective_count(count, n)) return;
+  const int lane = lane_id();
+  const int64_t u = ids[r];
+  if (lane == 0) {
+    if (ts_table != nullptr) {
+      if (check && err_flags != nullptr && ts_table[u] > ts[r]) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+      ts_table[u] = ts[r];
+    }
+    if (active != nullptr) active[u] = 1;
+  }
+  if (table != nullptr) warp_copy_row(table + u * width, vals + r * width, (int)width, lane);
+}
+
+extern "C" int tiger_scatter_rows(float* table, int64_t width, const int64_t* ids, int64_t n,
+                                  const int32_t* count, const float* vals, float* ts_table, const float* ts,
+                                  uint8_t* active, int check, uint32_t* err_flags, void* stream) {
+  if (n < 0 || width < 0) return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  scatter_rows_kernel<<<(unsigned)((n + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      table, width, ids, n, count, vals, ts_table, ts, active, check, err_flags);
+  return tiger_launch_status();
+}
+
+// ---------------------------------------------------------------- a10 TimeEncode
+__global__ void time_encode_kernel(const float* __restrict__ ts, int64_t total, const float* __restrict__ w,
+                                   const float* __restrict__ b, int dim, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % dim);
+  out[i] = time_enc(ts[i / dim], w[c], b[c]);
+}
+
+extern "C" int tiger_time_encode(const float* ts, int64_t n, const float* w, const float* b, int dim, float* out,
+                                 void* stream) {
+  if (n < 0 || dim <= 0) return TIGER_EINVAL;
+  const int64_t total = n * dim;
+  if (total == 0) return TIGER_OK;
+  time_encode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(ts, total, w, b, dim, out);
+  return tiger_launch_status();
+}
+
+// ---------------------------------------------------------------- a9 store_events
+// one warp per position p of pos = [src ; dst]; only selected positions build and write a row.
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+store_messages_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                      const int64_t* __restrict__ eids, const float* __restrict__ ts, int64_t batch,
+                      const uint8_t* __restrict__ winner, const float* __restrict__ mem_vals,
+                      const float* __restrict__ mem_ts, const float* __restrict__ nfeats,
+                      const float* __restrict__ efeats, int d, int de, const float* __restrict__ time_w,
+                      const float* __restrict__ time_b, float* __restrict__ msg_vals, float* __restrict__ msg_ts,
+                      uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags) {
+  const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
+  if (p >= 2 * batch) return;
+  const int lane = lane_id();
+  const int64_t e = p < batch ? p : p - batch;
+  const int64_t self = p < batch ? src[e] : dst[e];
+  const int64_t other = p < batch ? dst[e] : src[e];
+  const float t = ts[e];
+  const float prev = mem_ts[self];
+  if (lane == 0 && err_flags != nullptr) {
+    if (prev > t) atomicOr(err_flags, TIGER_ERR_EVENT_BEFORE_MEM);   // tiger.py:436-438
+    if (has_msg[self] != 0) atomicOr(err_flags, TIGER_ERR_UNUSED_MSG);  // memory.py:85-87
+  }
+  if (!winner[p]) return;
+  const int64_t m_dim = 3 * (int64_t)d + de;
+  float* row = msg_vals + self * m_dim;
+  warp_add_row(row, mem_vals + self * d, nfeats ? nfeats + self * d : nullptr, d, lane);
+  warp_add_row(row + d, mem_vals + other * d, nfeats ? nfeats + other * d : nullptr, d, lane);
+  if (efeats != nullptr) {
+    warp_copy_row(row + 2 * d, efeats + eids[e] * de, de, lane);
+  } else {
+    for (int i = lane; i < de; i += 32) row[2 * d + i] = 0.f;
+  }
+  const float dt = t - prev;
+  float* trow = row + 2 * d + de;
+  for (int i = lane; i < d; i += 32) trow[i] = time_enc(dt, time_w[i], time_b[i]);
+  if (lane == 0) msg_ts[self] = t;
+}
+
+// has_msg is raised by a second launch so that the unused-message check above never observes
+// a flag set by another warp of the same batch (a node can occur at several positions)
+__global__ void raise_has_msg_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                     int64_t batch, const uint8_t* __restrict__ winner,
+                                     uint8_t* __restrict__ has_msg) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= 2 * batch || !winner[p]) return;
+  has_msg[p < batch ? src[p] : dst[p - batch]] = 1;
+}
+
+extern "C" int tiger_store_messages(const int64_t* src, const int64_t* dst, const int64_t* eids, const float* ts,
+                                    int64_t batch, const uint8_t* winner, const float* mem_vals,
+                                    const float* mem_ts, const float* nfeats, const float* efeats, int d, int de,
+                                    const float* time_w, const float* time_b, float* msg_vals, float* msg_ts,
+                                    uint8_t* has_msg, uint32_t* err_flags, void* stream) {
+  if (batch < 0 || d <= 0 || de <= 0) return TIGER_EINVAL;
+  if (batch == 0) return TIGER_OK;
+  const int64_t n = 2 * batch;
+  store_messages_kernel<<<(unsigned)((n + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      src, dst, eids, ts, batch, winner, mem_vals, mem_ts, nfeats, efeats, d, de, time_w, time_b, msg_vals,
+      msg_ts, has_msg, err_flags);
+  raise_has_msg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, batch, winner,
+                                                                                  has_msg);
+  return tiger_launch_status();
+}
+
+// ---------------------------------------------------------------- a17 right write-back (+ a19)
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+right_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, const uint8_t* __restrict__ winner,
+                       const int32_t* __restrict__ gru_row, const float* __restrict__ h_new, int d,
+                       float* __restrict__ right_vals, float* __restrict__ right_ts,
+                       uint8_t* __restrict__ right_active, const float* __restrict__ msg_ts,
+                       uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags) {
+  const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
+  if (p >= n_pos || !winner[p]) return;
+  const int lane = lane_id();
+  const int64_t u = pos_ids[p];
+  if (has_msg[u] == 0) return;           // positive without a pending message: nothing to persist
+  const int32_t r = gru_row[u];
+  const float t = msg_ts[u];
+  __syncwarp();
+  if (lane == 0) {
+    if (err_flags != nullptr && right_ts[u] > t) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+    right_ts[u] = t;
+    if (right_active != nullptr) right_active[u] = 1;
+    has_msg[u] = 0;                       // the message is consumed (tiger.py:240)
+  }
+  warp_copy_row(right_vals + u * (int64_t)d, h_new + (int64_t)r * d, d, lane);
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+hprev_copy_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, int d, const float* __restrict__ left_vals,
+                  const float* __restrict__ right_vals, float* __restrict__ hprev_left,
+                  float* __restrict__ hprev_right) {
+  const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
+  if (p >= n_pos) return;
+  const int lane = lane_id();
+  const int64_t u = pos_ids[p];
+  warp_copy_row(hprev_left + p * d, left_vals + u * d, d, lane);
+  warp_copy_row(hprev_right + p * d, right_vals + u * d, d, lane);
+}
+
+extern "C" int tiger_right_writeback(const int64_t* pos_ids, int64_t n_pos, const uint8_t* winner,
+                                     const int32_t* gru_row, const float* h_new, int d, float* right_vals,
+                                     float* right_ts, uint8_t* right_active, const float* msg_ts,
+                                     uint8_t* has_msg, const float* left_vals, float* hprev_left,
+                                     float* hprev_right, uint32_t* err_flags, void* stream) {
+  if (n_pos < 0 || d <= 0) return TIGER_EINVAL;
+  if ((hprev_left == nullptr) != (hprev_right == nullptr)) return TIGER_EINVAL;
+  if (n_pos == 0) return TIGER_OK;
+  const unsigned grid = (unsigned)((n_pos + ROW_WARPS - 1) / ROW_WARPS);
+  right_writeback_kernel<<<grid, ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      pos_ids, n_pos, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg, err_flags);
+  if (hprev_left != nullptr)
+    hprev_copy_kernel<<<grid, ROW_WARPS * 32, 0, as_stream(stream)>>>(pos_ids, n_pos, d, left_vals, right_vals,
+                                                                     hprev_left, hprev_right);
+  return tiger_launch_status();
+}
+
+// ---------------------------------------------------------------- a18 left write-back
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+left_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, int64_t batch,
+                      const uint8_t* __restrict__ winner, const float* __restrict__ h_left, int d,
+                      const float* __restrict__ ts, float* __restrict__ left_vals, float* __restrict__ left_ts,
+                      uint8_t* __restrict__ left_active, uint32_t* __restrict__ err_flags) {
+  const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
+  if (p >= n_pos || !winner[p]) return;
+  const int lane = lane_id();
+  const int64_t u = pos_ids[p];
+  if (lane == 0) {
+    const float t = ts[p % batch];
+    if (err_flags != nullptr && left_ts[u] > t) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+    left_ts[u] = t;
+    if (left_active != nullptr) left_active[u] = 1;
+  }
+  warp_copy_row(left_vals + u * (int64_t)d, h_left + p * d, d, lane);
+}
+
+extern "C" int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64_t batch, const uint8_t* winner,
+                                    const float* h_left, int d, const float* ts, float* left_vals, float* left_ts,
+                                    uint8_t* left_active, uint32_t* err_flags, void* stream) {
+  if (n_pos < 0 || d <= 0 || batch <= 0) return TIGER_EINVAL;
+  if (n_pos == 0) return TIGER_OK;
+  left_writeback_kernel<<<(unsigned)((n_pos + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      pos_ids, n_pos, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags);
+  return tiger_launch_status();
+}
+
+// ---------------------------------------------------------------- parameter packing
+__global__ void transpose_pad_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld_in,
+                                     float* __restrict__ out, int64_t ld_out, int64_t pad_rows) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t n = n0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < rows && k < cols) ? w[n * ld_in + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t k = k0 + i, n = n0 + threadIdx.x;
+    if (k < cols && n < pad_rows) out[k * ld_out + n] = tile[threadIdx.x][i];
+  }
+}
+
+extern "C" int tiger_transpose_pad(const float* w, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                                   int64_t ld_out, int64_t pad_rows, void* stream) {
+  if (rows <= 0 || cols <= 0 || ld_in < cols || pad_rows < rows || ld_out < pad_rows) return TIGER_EINVAL;
+  dim3 grid((unsigned)((pad_rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  transpose_pad_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(w, rows, cols, ld_in, out, ld_out, pad_rows);
+  return tiger_launch_status();
+}
+
+__global__ void copy_pad_kernel(const float* __restrict__ w, int64_t rows, int64_t cols, int64_t ld_in,
+                                float* __restrict__ out, int64_t ld_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld_out) return;
+  const int64_t r = i / ld_out, c = i % ld_out;
+  out[i] = c < cols ? w[r * ld_in + c] : 0.f;
+}
+
+extern "C" int tiger_copy_pad(const float* w, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                              int64_t ld_out, void* stream) {
+  if (rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols) return TIGER_EINVAL;
+  const int64_t total = rows * ld_out;
+  copy_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(w, rows, cols, ld_in, out, ld_out);
+  return tiger_launch_status();
+}

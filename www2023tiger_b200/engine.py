@@ -1,0 +1,276 @@
+"""The per-batch temporal memory path as one fixed, sync-free launch sequence.
+
+`TigerEngine` owns the device state of TIGE/TIGER (both memories, the last-message store, the
+pending / up-to-date flags) and runs TIGE.contrast_learning (reference tiger/model/tiger.py:174-290)
+as ten kernel launches whose data-dependent sizes (involved U, outdated O, restarted R) stay on
+the device.  `StreamRunner` adds the device neighbor finder in front, captures the sequence in a
+CUDA graph and feeds it from pinned host buffers.
+
+Launch sequence of one batch (B events, K neighbors):
+  1 tiger_find_recent        3B queries -> neighbor tables, involved bitmap, float32 batch times
+  2 tiger_compact_involved   involved / outdated / restart lists + gru_row map
+  3 tiger_static_restart     (lazy-restart mode only) re-initialise not-yet-seen nodes
+  4 tiger_gru_update         h(t'+) for the O outdated nodes      (steps 1-2 of the reference)
+  5 tiger_temporal_attention h(t-) for [src;dst;neg]              (step 3)
+  6 tiger_select_latest      argmax-by-timestamp winners of [src;dst]
+  7 tiger_right_writeback    persist h(t'+) of outdated positives (step 4) [+ restarter targets]
+  8 tiger_store_messages     build + store the new raw messages   (step 5)
+  9 tiger_left_writeback     persist h(t-) of positives           (step 6)
+ 10 tiger_link_score         hit flags, scorer, BCE loss          (step 7)
+"""
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import ops
+from ._lib import raise_on_err_flags
+from .ops import f32, f64, i32, i64, u8
+
+KERNELS_PER_STEP = {  # launches of our kernels per batch (for the bench `gpu_launches` field)
+    'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 1, 'select_latest': 1,
+    'right_writeback': 1, 'store_messages': 2, 'left_writeback': 1, 'link_score': 1,
+}
+
+
+class TigerEngine:
+    def __init__(self, weights: Dict[str, Tensor], csr: ops.DeviceCSR, *, n_nodes: int, dim: int,
+                 efeats: Optional[Tensor], nfeats: Optional[Tensor] = None, n_neighbors: int = 10,
+                 n_head: int = 2, batch_size: int = 200, msg_src: str = 'left', upd_src: str = 'right',
+                 restarter: Optional[str] = None, hit_type: str = 'bin', lazy_restart: bool = False,
+                 want_restarter_targets: bool = False, device='cuda'):
+        if msg_src not in ('left', 'right') or upd_src not in ('left', 'right'):
+            raise ValueError(f'Invalid msg_src={msg_src} / upd_src={upd_src}')   # tiger.py:156-160
+        if hit_type not in ('bin', 'none'):
+            raise NotImplementedError(f'hit_type={hit_type}')
+        if lazy_restart and restarter != 'static':
+            raise NotImplementedError('fused lazy restart is implemented for the static restarter')
+        dev = torch.device(device)
+        self.device, self.csr = dev, csr
+        self.N, self.K, self.H, self.B = n_nodes, n_neighbors, n_head, batch_size
+        self.efeats = efeats
+        self.nfeats = nfeats
+        self.d = nfeats.shape[1] if nfeats is not None else dim              # feature_getter.py:76-77
+        self.de = efeats.shape[1] if efeats is not None else dim
+        self.M = 3 * self.d + self.de                                          # tiger.py:62
+        self.msg_src, self.upd_src = msg_src, upd_src
+        self.restarter, self.hit_type, self.lazy_restart = restarter, hit_type, lazy_restart
+        self.want_targets = want_restarter_targets
+        N, d, B, K = self.N, self.d, self.B, self.K
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        # ---- persistent state (reference: Memory x2, MessageStoreNoGradLastOnly) ----
+        self.left_vals, self.left_ts, self.left_active = z(N, d), z(N), z(N, dt=u8)
+        self.right_vals, self.right_ts, self.right_active = z(N, d), z(N), z(N, dt=u8)
+        self.msg_vals, self.msg_ts, self.has_msg = z(N, self.M), z(N), z(N, dt=u8)
+        self.uptodate = z(N, dt=u8)
+        # ---- per-batch scratch (fixed capacity) ----
+        self.cap = 3 * B * (K + 1)
+        self.bitmap = z(ops.bitmap_words(N), dt=i32)
+        self.involved, self.outdated, self.restart_nodes = z(self.cap, dt=i64), z(self.cap, dt=i64), z(self.cap, dt=i64)
+        self.gru_row = torch.full((N,), -1, dtype=i32, device=dev)
+        self.counts = z(4, dt=i32)
+        self.err_flags = z(1, dt=i32)
+        self.neigh_nids, self.neigh_eids = z(3 * B, K, dt=i64), z(3 * B, K, dt=i64)
+        self.neigh_ts = z(3 * B, K)
+        self.ts32 = z(B)
+        self.h_new = z(self.cap, d)
+        self.emb = z(3 * B, d)
+        self.winner = z(2 * B, dt=u8)
+        self.sel_count = z(1, dt=i32)
+        self.out_buf = z(2 * B + 1)                    # [pos scores | neg scores | loss]
+        self.scores, self.loss = self.out_buf[:2 * B], self.out_buf[2 * B:]
+        self.hprev_left = z(2 * B, d) if want_restarter_targets else None
+        self.hprev_right = z(2 * B, d) if want_restarter_targets else None
+        # ---- batch inputs: [src | dst | neg | eids] int64 and ts float64, one contiguous buffer ----
+        self.inp = z(5 * B, dt=i64)
+        self.batch_nids = self.inp[:3 * B]
+        self.src, self.dst, self.neg = self.inp[:B], self.inp[B:2 * B], self.inp[2 * B:3 * B]
+        self.pos = self.inp[:2 * B]
+        self.eids = self.inp[3 * B:4 * B]
+        self.ts64 = self.inp[4 * B:].view(f64)
+        # ---- parameters ----
+        self.gru_pack = None
+        self.attn_pack = ops.AttnPack(self.d, self.de, dev)
+        self.score_pack = ops.ScorePack(self.d, dev)
+        self.load_weights(weights)
+
+    # ------------------------------------------------------------------ parameters
+    def load_weights(self, W: Dict[str, Tensor]):
+        """(Re)pack parameters given under the reference's state_dict names."""
+        g = lambda k: W[k].detach().to(self.device, f32).contiguous()
+        c = 'right_mem_updater.cell.'
+        args = (g(c + 'weight_ih'), g(c + 'weight_hh'), g(c + 'bias_ih'), g(c + 'bias_hh'))
+        if self.gru_pack is None:
+            self.gru_pack = ops.GruPack(*args)
+        else:
+            self.gru_pack.refresh(*args)
+        a = 'temporal_embedding_fn.fns.0.'
+        self.time_w, self.time_b = g('time_encoder.basis_freq'), g('time_encoder.phase')
+        self.attn_pack.refresh(g(a + 'mha_fn.q_proj_weight'), g(a + 'mha_fn.k_proj_weight'),
+                               g(a + 'mha_fn.v_proj_weight'), g(a + 'mha_fn.in_proj_bias'),
+                               g(a + 'mha_fn.out_proj.weight'), g(a + 'mha_fn.out_proj.bias'),
+                               g(a + 'merger.fc1.weight'), g(a + 'merger.fc1.bias'),
+                               g(a + 'merger.fc2.weight'), g(a + 'merger.fc2.bias'), self.time_w, self.time_b)
+        s = 'score_fn.'
+        self.score_pack.refresh(g(s + 'fc1.weight'), g(s + 'fc1.bias'), g(s + 'fc2.weight'), g(s + 'fc2.bias'),
+                                g('hit_embedding.weight') if self.hit_type == 'bin' else None)
+        if self.restarter == 'static':
+            self.left_emb = g('restarter_fn.left_emb.weight')
+            self.right_emb = g('restarter_fn.right_emb.weight')
+
+    # ------------------------------------------------------------------ state
+    def reset(self):
+        """TIGE.reset (tiger.py:457-463) + a fresh up-to-date set."""
+        for t in (self.left_vals, self.left_ts, self.left_active, self.right_vals, self.right_ts,
+                  self.right_active, self.has_msg, self.uptodate, self.err_flags):
+            t.zero_()
+
+    def clear_messages(self):
+        """msg_store.clear() + uptodate_nodes = set() of the restart trigger
+        (train_self_supervised.py:153-156)."""
+        self.has_msg.zero_()
+        self.uptodate.zero_()
+
+    def _mem(self, which):
+        if which == 'left':
+            return self.left_vals, self.left_ts
+        return self.right_vals, self.right_ts
+
+    def check_errors(self):
+        """Host sync: raise the reference's ValueError if an invariant kernel flag is set."""
+        raise_on_err_flags(int(self.err_flags.item()) & 0xffffffff)
+
+    def set_batch(self, src, dst, neg, ts, eids):
+        """Copy one batch (numpy or tensors; ts float64) into the device input buffer."""
+        B = self.B
+        host = torch.empty(5 * B, dtype=i64)
+        h = host.numpy()
+        h[:B], h[B:2 * B], h[2 * B:3 * B], h[3 * B:4 * B] = src, dst, neg, eids
+        h[4 * B:].view(np.float64)[:] = ts
+        self.inp.copy_(host)
+
+    # ------------------------------------------------------------------ the launch sequence
+    def launch_finder(self):
+        ops.find_recent(self.csr, self.batch_nids, self.ts64, self.K, ts_period=self.B, want_dirs=False,
+                        ts32_out=self.ts32, bitmap=self.bitmap,
+                        out=(self.neigh_nids, self.neigh_eids, self.neigh_ts, None))
+
+    def launch_model(self):
+        d, B = self.d, self.B
+        msg_vals_mem, msg_ts_mem = self._mem(self.msg_src)
+        upd_vals, _ = self._mem(self.upd_src)
+        ops.compact_involved(self.bitmap, self.N, self.involved, self.counts, has_msg=self.has_msg,
+                             uptodate=self.uptodate if self.lazy_restart else None, outdated=self.outdated,
+                             gru_row=self.gru_row, restart_nodes=self.restart_nodes if self.lazy_restart else None,
+                             err_flags=self.err_flags)
+        if self.lazy_restart:
+            ops.static_restart(self.restart_nodes, self.cap, self.csr, self.left_emb, self.right_emb, d,
+                               count=self.counts[2:], batch_ts=self.ts32, left_vals=self.left_vals,
+                               left_ts=self.left_ts, left_active=self.left_active, right_vals=self.right_vals,
+                               right_ts=self.right_ts, right_active=self.right_active, has_msg=self.has_msg)
+        ops.gru_update(self.gru_pack, node_ids=self.outdated, x_table=self.msg_vals, h_table=upd_vals,
+                       n_rows=self.cap, out=self.h_new, count=self.counts[1:], msg_ts=self.msg_ts,
+                       check_mem_ts=msg_ts_mem, check_equal=(self.msg_src == 'left'), err_flags=self.err_flags)
+        ops.temporal_attention(self.attn_pack, self.H, self.batch_nids, self.ts32, self.neigh_nids, self.neigh_eids,
+                               self.neigh_ts, rows_a=self.right_vals, rows_b=self.h_new, sel=self.gru_row,
+                               nfeats=self.nfeats, efeats=self.efeats, out=self.emb)
+        ops.select_latest(self.pos, self.ts32, want_unique=False, winner=self.winner, count=self.sel_count)
+        ops.right_writeback(self.pos, self.winner, self.gru_row, self.h_new, d, self.right_vals, self.right_ts,
+                            self.right_active, self.msg_ts, self.has_msg, self.left_vals, self.hprev_left,
+                            self.hprev_right, self.err_flags)
+        ops.store_messages(self.src, self.dst, self.eids, self.ts32, self.winner, msg_vals_mem, msg_ts_mem,
+                           self.nfeats, self.efeats, d, self.de, self.time_w, self.time_b, self.msg_vals,
+                           self.msg_ts, self.has_msg, self.err_flags)
+        ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
+                           self.left_active, self.err_flags)
+        ops.link_score(self.score_pack, self.emb, self.src, self.dst, self.neg,
+                       self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
+
+    def launches_per_step(self) -> int:
+        n = sum(KERNELS_PER_STEP.values())
+        if self.lazy_restart:
+            n += 1
+        if self.want_targets:
+            n += 1
+        return n
+
+    def step(self):
+        """One batch, eager launches on the current stream (inputs already in self.inp)."""
+        self.launch_finder()
+        self.launch_model()
+
+
+class StreamRunner:
+    """Replays an event stream through a TigerEngine: CUDA-graph capture of the whole batch,
+    pinned host staging for the host-buffer (e2e) path."""
+
+    def __init__(self, engine: TigerEngine, n_slots: int = 4):
+        self.e = engine
+        self.graph = None
+        B = engine.B
+        self.n_slots = n_slots
+        self.h_in = [torch.empty(5 * B, dtype=i64).pin_memory() for _ in range(n_slots)]
+        self.h_out = [torch.empty(2 * B + 1, dtype=f32).pin_memory() for _ in range(n_slots)]
+        self.events = [torch.cuda.Event() for _ in range(n_slots)]
+        self.slot_busy = [False] * n_slots
+        self.slot = 0
+
+    def capture(self, warmup: int = 2):
+        """Warm up (eagerly, state restored afterwards is the caller's business) and capture."""
+        e = self.e
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                e.step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            e.step()
+        torch.cuda.synchronize()
+
+    def run_device(self):
+        """Inputs already resident in engine.inp."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.e.step()
+
+    def fill_host(self, slot: int, src, dst, neg, ts, eids):
+        B = self.e.B
+        h = self.h_in[slot].numpy()
+        h[:B], h[B:2 * B], h[2 * B:3 * B], h[3 * B:4 * B] = src, dst, neg, eids
+        h[4 * B:].view(np.float64)[:] = ts
+
+    def submit_host(self, src, dst, neg, ts, eids) -> int:
+        """Host-buffer step: H2D of the batch, the graph, D2H of scores + loss.  Returns the slot whose
+        results become readable after `wait(slot)`."""
+        slot = self.slot
+        self.slot = (slot + 1) % self.n_slots
+        if self.slot_busy[slot]:
+            self.events[slot].synchronize()
+        self.fill_host(slot, src, dst, neg, ts, eids)
+        e = self.e
+        e.inp.copy_(self.h_in[slot], non_blocking=True)
+        self.run_device()
+        self.h_out[slot].copy_(e.out_buf, non_blocking=True)
+        self.events[slot].record()
+        self.slot_busy[slot] = True
+        return slot
+
+    def wait(self, slot: int):
+        self.events[slot].synchronize()
+        self.slot_busy[slot] = False
+        out = self.h_out[slot]
+        B = self.e.B
+        return out[:B], out[B:2 * B], out[2 * B]
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self.h_in[0].numel() * 8
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return self.h_out[0].numel() * 4

@@ -1,0 +1,354 @@
+"""Tensor-level wrappers of the C-ABI kernels (one function per entry point).
+
+Every function takes CUDA tensors, allocates its outputs with torch (device memory is the
+only thing torch does here), launches on the current stream and never synchronises.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import call, check_cuda, ptr
+
+i64, i32, f32, f64, u8 = torch.int64, torch.int32, torch.float32, torch.float64, torch.uint8
+
+
+def _empty(shape, dtype, like: Tensor) -> Tensor:
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------
+# graph
+# ------------------------------------------------------------------------------------------
+class DeviceCSR:
+    """Per-node time-sorted adjacency in HBM: indptr int64 [N+1]; nbr/eid int32, ts float64,
+    flag uint8, each [2E]."""
+
+    def __init__(self, indptr, nbr, eid, ts, flag):
+        self.indptr, self.nbr, self.eid, self.ts, self.flag = indptr, nbr, eid, ts, flag
+        self.n_nodes = indptr.numel() - 1
+
+    @property
+    def device(self):
+        return self.indptr.device
+
+
+def csr_build(src: Tensor, dst: Tensor, ts: Tensor, eids: Tensor, n_nodes: int) -> DeviceCSR:
+    """a1: device CSR from a time-ordered stream (int64 ids, float64 times)."""
+    check_cuda(src, dst, ts, eids)
+    assert src.dtype == i64 and dst.dtype == i64 and eids.dtype == i64 and ts.dtype == f64
+    E = src.numel()
+    indptr = _empty(n_nodes + 1, i64, src)
+    nbr = _empty(2 * E, i32, src)
+    eid = _empty(2 * E, i32, src)
+    ats = _empty(2 * E, f64, src)
+    flag = _empty(2 * E, u8, src)
+    work = _empty(_lib.load().tiger_csr_build_work_bytes(E, n_nodes), u8, src)
+    call('tiger_csr_build', ptr(src), ptr(dst), ptr(ts), ptr(eids), E, n_nodes, ptr(indptr), ptr(nbr), ptr(eid),
+         ptr(ats), ptr(flag), ptr(work))
+    return DeviceCSR(indptr, nbr, eid, ats, flag)
+
+
+def find_recent(csr: DeviceCSR, q_nids: Tensor, q_ts: Tensor, k: int, *, ts_period: int = 0,
+                want_dirs: bool = True, ts32_out: Optional[Tensor] = None, bitmap: Optional[Tensor] = None,
+                out: Optional[Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]] = None):
+    """a2: K most recent events strictly before q_ts, right-aligned and zero-padded."""
+    check_cuda(q_nids, q_ts)
+    assert q_nids.dtype == i64 and q_ts.dtype == f64
+    n = q_nids.numel()
+    if out is None:
+        o_n = _empty((n, k), i64, q_nids)
+        o_e = _empty((n, k), i64, q_nids)
+        o_t = _empty((n, k), f32, q_nids)
+        o_d = _empty((n, k), i64, q_nids) if want_dirs else None
+    else:
+        o_n, o_e, o_t, o_d = out
+    call('tiger_find_recent', ptr(csr.indptr), ptr(csr.nbr), ptr(csr.eid), ptr(csr.ts), ptr(csr.flag),
+         ptr(q_nids), ptr(q_ts), n, ts_period or q_ts.numel(), k, ptr(o_n), ptr(o_e), ptr(o_t), ptr(o_d),
+         ptr(ts32_out), ptr(bitmap))
+    return o_n, o_e, o_t, o_d
+
+
+def hit_window(center: Tensor, neigh: Tensor) -> Tensor:
+    check_cuda(center, neigh)
+    n, k = neigh.shape
+    hit = _empty((n, k), f32, neigh)
+    call('tiger_hit_window', ptr(center), ptr(neigh), n, k, ptr(hit))
+    return hit
+
+
+def bitmap_words(n_nodes: int) -> int:
+    return (n_nodes + 31) // 32
+
+
+def mark_nodes(ids: Tensor, bitmap: Tensor, n_nodes: int):
+    check_cuda(ids, bitmap)
+    call('tiger_mark_nodes', ptr(ids), ids.numel(), ptr(bitmap), n_nodes)
+
+
+def compact_involved(bitmap: Tensor, n_nodes: int, involved: Tensor, counts: Tensor, *,
+                     has_msg: Optional[Tensor] = None, uptodate: Optional[Tensor] = None,
+                     local_index: Optional[Tensor] = None, outdated: Optional[Tensor] = None,
+                     gru_row: Optional[Tensor] = None, restart_nodes: Optional[Tensor] = None,
+                     err_flags: Optional[Tensor] = None):
+    call('tiger_compact_involved', ptr(bitmap), n_nodes, ptr(has_msg), ptr(uptodate), ptr(involved),
+         involved.numel(), ptr(local_index), ptr(outdated), ptr(gru_row), ptr(restart_nodes), ptr(counts),
+         ptr(err_flags))
+
+
+# ------------------------------------------------------------------------------------------
+# index utilities
+# ------------------------------------------------------------------------------------------
+class SelectScratch:
+    """Per-node scratch of tiger_select_latest (zero on entry and on exit)."""
+
+    def __init__(self, n_nodes: int, device):
+        self.n_nodes = n_nodes
+        self.slot_ts = torch.zeros(n_nodes, dtype=i64, device=device)
+        self.slot_pos = torch.zeros(n_nodes, dtype=i32, device=device)
+        self.bitmap = torch.zeros(bitmap_words(n_nodes), dtype=i32, device=device)
+
+
+def select_latest(nids: Tensor, ts: Tensor, scratch: Optional[SelectScratch] = None, *,
+                  want_unique: bool = True, winner: Optional[Tensor] = None, count: Optional[Tensor] = None):
+    """a8: returns (winner uint8 [n], unique_ids, index, count) - unique_ids/index have n slots,
+    the first `count` (device int32) are valid."""
+    check_cuda(nids, ts)
+    assert nids.dtype == i64 and ts.dtype in (f32, f64)
+    n = nids.numel()
+    if winner is None:
+        winner = _empty(n, u8, nids)
+    uniq = _empty(n, i64, nids) if want_unique else None
+    index = _empty(n, i64, nids) if want_unique else None
+    if count is None:
+        count = _empty(1, i32, nids)
+    if n > 2048 and scratch is None:
+        raise _lib.TigerLibraryError('select_latest over more than 2048 positions needs a SelectScratch')
+    call('tiger_select_latest', ptr(nids), ptr(ts), int(ts.dtype == f64), n, ts.numel(),
+         scratch.n_nodes if scratch else 0, ptr(scratch.slot_ts) if scratch else None,
+         ptr(scratch.slot_pos) if scratch else None, ptr(scratch.bitmap) if scratch else None,
+         ptr(winner), ptr(uniq), ptr(index), ptr(count))
+    return winner, uniq, index, count
+
+
+def anonymized_reindex(hist_nids: Tensor) -> Tensor:
+    check_cuda(hist_nids)
+    n, length = hist_nids.shape
+    out = torch.empty_like(hist_nids)
+    call('tiger_anonymized_reindex', ptr(hist_nids), n, length, ptr(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# memory / message store
+# ------------------------------------------------------------------------------------------
+def gather_rows(table: Tensor, ids: Tensor, ts_table: Optional[Tensor] = None):
+    check_cuda(table, ids, ts_table)
+    n = ids.numel()
+    width = table.shape[1]
+    out = _empty((n, width), f32, table)
+    out_ts = _empty(n, f32, table) if ts_table is not None else None
+    call('tiger_gather_rows', ptr(table), width, ptr(ids), n, ptr(out), ptr(ts_table), ptr(out_ts))
+    return out, out_ts
+
+
+def scatter_rows(table: Optional[Tensor], ids: Tensor, vals: Optional[Tensor], *, ts_table=None, ts=None,
+                 active=None, check: bool = False, err_flags=None, count=None, width: Optional[int] = None):
+    check_cuda(table, ids, vals, ts_table, ts)
+    w = width if width is not None else (table.shape[1] if table is not None else 0)
+    call('tiger_scatter_rows', ptr(table), w, ptr(ids), ids.numel(), ptr(count), ptr(vals), ptr(ts_table), ptr(ts),
+         ptr(active), int(check), ptr(err_flags))
+
+
+def time_encode(ts: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    check_cuda(ts, w, b)
+    dim = w.numel()
+    out = _empty((*ts.shape, dim), f32, ts)
+    call('tiger_time_encode', ptr(ts), ts.numel(), ptr(w), ptr(b), dim, ptr(out))
+    return out
+
+
+def store_messages(src, dst, eids, ts, winner, mem_vals, mem_ts, nfeats, efeats, d, de, time_w, time_b,
+                   msg_vals, msg_ts, has_msg, err_flags=None):
+    call('tiger_store_messages', ptr(src), ptr(dst), ptr(eids), ptr(ts), src.numel(), ptr(winner), ptr(mem_vals),
+         ptr(mem_ts), ptr(nfeats), ptr(efeats), d, de, ptr(time_w), ptr(time_b), ptr(msg_vals), ptr(msg_ts),
+         ptr(has_msg), ptr(err_flags))
+
+
+def right_writeback(pos_ids, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg,
+                    left_vals=None, hprev_left=None, hprev_right=None, err_flags=None):
+    call('tiger_right_writeback', ptr(pos_ids), pos_ids.numel(), ptr(winner), ptr(gru_row), ptr(h_new), d,
+         ptr(right_vals), ptr(right_ts), ptr(right_active), ptr(msg_ts), ptr(has_msg), ptr(left_vals),
+         ptr(hprev_left), ptr(hprev_right), ptr(err_flags))
+
+
+def left_writeback(pos_ids, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags=None):
+    call('tiger_left_writeback', ptr(pos_ids), pos_ids.numel(), batch, ptr(winner), ptr(h_left), d, ptr(ts),
+         ptr(left_vals), ptr(left_ts), ptr(left_active), ptr(err_flags))
+
+
+# ------------------------------------------------------------------------------------------
+# parameter packing
+# ------------------------------------------------------------------------------------------
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def transpose_pad(w: Tensor, out: Tensor, ld_out: int, pad_rows: Optional[int] = None):
+    """out[k*ld_out + n] = w[n, k]; w is a (possibly row-sliced) contiguous 2-D parameter."""
+    check_cuda(w, out)
+    rows, cols = w.shape
+    call('tiger_transpose_pad', ptr(w), rows, cols, w.stride(0), ptr(out), ld_out,
+         pad_rows if pad_rows is not None else ld_out)
+
+
+def copy_pad(w: Tensor, out: Tensor, ld_out: int):
+    check_cuda(w, out)
+    rows, cols = w.shape
+    call('tiger_copy_pad', ptr(w), rows, cols, w.stride(0), ptr(out), ld_out)
+
+
+class GruPack:
+    """k-major packs of nn.GRUCell weights: wT_ih [M][3*dp], wT_hh [d][3*dp] (dp = d rounded up to
+    32), gate g of hidden unit j at column g*dp + j."""
+
+    def __init__(self, weight_ih: Tensor, weight_hh: Tensor, bias_ih: Tensor, bias_hh: Tensor):
+        self.d = weight_hh.shape[1]
+        self.m_dim = weight_ih.shape[1]
+        self.dp = round_up(self.d, 32)
+        self.ldw = 3 * self.dp
+        dev = weight_ih.device
+        self.wT_ih = torch.zeros(self.m_dim * self.ldw, dtype=f32, device=dev)
+        self.wT_hh = torch.zeros(self.d * self.ldw, dtype=f32, device=dev)
+        self.refresh(weight_ih, weight_hh, bias_ih, bias_hh)
+
+    def refresh(self, weight_ih, weight_hh, bias_ih, bias_hh):
+        wi, wh = weight_ih.detach(), weight_hh.detach()
+        d, dp = self.d, self.dp
+        for g in range(3):
+            transpose_pad(wi[g * d:(g + 1) * d], self.wT_ih[g * dp:], self.ldw, dp)
+            transpose_pad(wh[g * d:(g + 1) * d], self.wT_hh[g * dp:], self.ldw, dp)
+        self.b_ih = bias_ih.detach().contiguous()
+        self.b_hh = bias_hh.detach().contiguous()
+
+
+def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_table: Tensor, n_rows: int,
+               out: Optional[Tensor] = None, count: Optional[Tensor] = None, msg_ts: Optional[Tensor] = None,
+               check_mem_ts: Optional[Tensor] = None, check_equal: bool = False,
+               err_flags: Optional[Tensor] = None) -> Tensor:
+    """a6+a13: h_new[r] = GRUCell(x_table[ids[r]], h_table[ids[r]]) (ids None => dense rows)."""
+    check_cuda(node_ids, x_table, h_table)
+    if out is None:
+        out = _empty((n_rows, pack.d), f32, x_table)
+    call('tiger_gru_update', ptr(node_ids), ptr(count), n_rows, ptr(x_table), x_table.stride(0), ptr(h_table),
+         h_table.stride(0), pack.m_dim, pack.d, ptr(pack.wT_ih), ptr(pack.wT_hh), pack.ldw, ptr(pack.b_ih),
+         ptr(pack.b_hh), ptr(out), ptr(msg_ts), ptr(check_mem_ts), int(check_equal), ptr(err_flags))
+    return out
+
+
+class AttnParamsC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ('wqT', 'wk', 'wvT', 'woT', 'fc1T', 'fc2T', 'in_bias', 'out_bias', 'fc1_b', 'fc2_b', 'time_w',
+                 'time_b')]
+
+
+class AttnPack:
+    """k-major, 16-byte-aligned packs of TemporalAttention's parameters (one blob)."""
+
+    def __init__(self, d: int, de: int, device):
+        self.d, self.de = d, de
+        E, C = 2 * d, 2 * d + de
+        self.ldE, self.ldC, self.ldD = round_up(E, 4), round_up(C, 4), round_up(d, 4)
+        sizes = [E * self.ldE, E * self.ldC, C * self.ldE, E * self.ldE, (E + d) * self.ldD, d * self.ldD]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + round_up(s, 4))
+        self.blob = torch.zeros(self.offsets[-1], dtype=f32, device=device)
+        self.struct = AttnParamsC()
+        self._keep = None
+
+    def part(self, i: int) -> Tensor:
+        return self.blob[self.offsets[i]:self.offsets[i + 1]]
+
+    def refresh(self, q_w, k_w, v_w, in_bias, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b, time_w, time_b):
+        det = lambda t: t.detach().contiguous()
+        transpose_pad(det(q_w), self.part(0), self.ldE)
+        copy_pad(det(k_w), self.part(1), self.ldC)
+        transpose_pad(det(v_w), self.part(2), self.ldE)
+        transpose_pad(det(out_w), self.part(3), self.ldE)
+        transpose_pad(det(fc1_w), self.part(4), self.ldD)
+        transpose_pad(det(fc2_w), self.part(5), self.ldD)
+        keep = [det(in_bias), det(out_b), det(fc1_b), det(fc2_b), det(time_w), det(time_b)]
+        self._keep = keep
+        s = self.struct
+        s.wqT, s.wk, s.wvT, s.woT, s.fc1T, s.fc2T = (self.part(i).data_ptr() for i in range(6))
+        s.in_bias, s.out_bias, s.fc1_b, s.fc2_b, s.time_w, s.time_b = (t.data_ptr() for t in keep)
+
+    def byref(self):
+        return ctypes.addressof(self.struct)
+
+
+def temporal_attention(pack: AttnPack, n_head: int, center_nids: Tensor, q_ts: Tensor, neigh_nids: Tensor,
+                       neigh_eids: Tensor, neigh_ts: Tensor, *, rows_a: Optional[Tensor], rows_b: Tensor,
+                       sel: Tensor, nfeats: Optional[Tensor], efeats: Optional[Tensor],
+                       out: Optional[Tensor] = None) -> Tensor:
+    """a15+a16 (gather form).  q_ts may be shorter than center_nids (ts.repeat semantics)."""
+    check_cuda(center_nids, q_ts, neigh_nids, neigh_eids, neigh_ts, rows_a, rows_b, sel, nfeats, efeats)
+    n, k = neigh_nids.shape
+    if out is None:
+        out = _empty((n, pack.d), f32, rows_b)
+    assert sel.dtype in (i32, i64)
+    call('tiger_temporal_attention', ptr(center_nids), ptr(q_ts), n, q_ts.numel(), ptr(neigh_nids), ptr(neigh_eids),
+         ptr(neigh_ts), k, ptr(rows_a), ptr(rows_b), ptr(sel), int(sel.dtype == i64), ptr(nfeats), ptr(efeats),
+         pack.d, pack.de, n_head, pack.byref(), ptr(out))
+    return out
+
+
+def temporal_attention_dense(pack: AttnPack, n_head: int, qx, qt, kx, ky, kt, padding_mask) -> Tensor:
+    check_cuda(qx, qt, kx, ky, kt, padding_mask)
+    n, k = kx.shape[0], kx.shape[1]
+    out = _empty((n, pack.d), f32, qx)
+    mask = padding_mask.to(u8).contiguous()
+    call('tiger_temporal_attention_dense', ptr(qx), ptr(qt), ptr(kx), ptr(ky), ptr(kt), ptr(mask), n, k, pack.d,
+         pack.de, n_head, pack.byref(), ptr(out))
+    return out
+
+
+class ScorePack:
+    """k-major pack of score_fn (MergeLayer(d, d, d, 1)) + optional hit embedding."""
+
+    def __init__(self, d: int, device):
+        self.d = d
+        self.ldD = round_up(d, 4)
+        self.fc1T = torch.zeros(2 * d * self.ldD, dtype=f32, device=device)
+        self.done = torch.zeros(1, dtype=i32, device=device)
+
+    def refresh(self, fc1_w, fc1_b, fc2_w, fc2_b, hit_emb: Optional[Tensor]):
+        transpose_pad(fc1_w.detach().contiguous(), self.fc1T, self.ldD)
+        self.fc1_b = fc1_b.detach().contiguous()
+        self.fc2_w = fc2_w.detach().reshape(-1).contiguous()
+        self.fc2_b = fc2_b.detach().contiguous()
+        self.hit_emb = None if hit_emb is None else hit_emb.detach().contiguous()
+
+
+def link_score(pack: ScorePack, h: Tensor, src: Tensor, dst: Tensor, neg: Tensor, neigh_nids: Optional[Tensor],
+               scores: Optional[Tensor] = None, loss: Optional[Tensor] = None):
+    B = src.numel()
+    if scores is None:
+        scores = _empty(2 * B, f32, h)
+    if loss is None:
+        loss = _empty(1, f32, h)
+    k = neigh_nids.shape[1] if neigh_nids is not None else 0
+    call('tiger_link_score', ptr(h), B, pack.d, ptr(src), ptr(dst), ptr(neg), ptr(neigh_nids), k, ptr(pack.hit_emb),
+         ptr(pack.fc1T), ptr(pack.fc1_b), ptr(pack.fc2_w), ptr(pack.fc2_b), ptr(scores), ptr(loss), ptr(pack.done))
+    return scores, loss
+
+
+def static_restart(nids: Tensor, n: int, csr: DeviceCSR, left_emb: Tensor, right_emb: Tensor, d: int, *,
+                   count=None, batch_ts=None, q_ts=None, left_vals=None, left_ts=None, left_active=None,
+                   right_vals=None, right_ts=None, right_active=None, has_msg=None, out_prev_ts=None):
+    call('tiger_static_restart', ptr(nids), ptr(count), n, ptr(batch_ts), batch_ts.numel() if batch_ts is not None else 0,
+         ptr(q_ts), ptr(csr.indptr), ptr(csr.ts), ptr(left_emb), ptr(right_emb), d, ptr(left_vals), ptr(left_ts),
+         ptr(left_active), ptr(right_vals), ptr(right_ts), ptr(right_active), ptr(has_msg), ptr(out_prev_ts))
