@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""Benchmark of TIGER's per-batch temporal memory path on B200 ("Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload reddit|wikipedia|mooc|lastfm|scaled]
+    python bench.py --impl reference ...      # the CPU restatement of the reference path (oracle/), host cores
+
+One step = one batch of 200 events through the whole fused path: temporal neighbor finder ->
+involved/outdated compaction -> lazy restart -> pending-message gather + GRU -> temporal
+attention embedding -> argmax-by-timestamp selection -> right write-back -> message build +
+store -> left write-back -> link scorer + loss.  `value` is measured with the batch inputs already
+resident in HBM (CUDA-graph replay, CUDA events); `e2e` goes through pinned HOST buffers (H2D of the
+batch, the graph, D2H of scores + loss inside the timed region).
+
+Only the `cpu_baseline` leg and `--impl reference` import oracle/ (the CPU checker); the product
+path never does.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'events/sec (memory update + embedding, batch 200)'
+UNIT = 'events/s'
+BATCH = 200
+K_NEIGH = 10
+N_HEAD = 2
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=1000)
+    p.add_argument('--warmup', type=int, default=20)
+    p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    p.add_argument('--workload', default='reddit', choices=['wikipedia', 'reddit', 'mooc', 'lastfm', 'scaled'])
+    p.add_argument('--events', type=int, default=0, help='override the number of events of the stream')
+    p.add_argument('--skip-batches', type=int, default=1000, help='batches skipped so that histories are populated')
+    p.add_argument('--cpu-batches', type=int, default=40, help='bounded sample of the cpu_baseline leg (0 = off)')
+    p.add_argument('--profile-steps', type=int, default=100, help='eager steps with per-kernel CUDA events')
+    p.add_argument('--no-e2e', action='store_true')
+    p.add_argument('--seed', type=int, default=0)
+    return p.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+# ------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------
+def load_workload(args, with_efeats=True):
+    from www2023tiger_b200.synthetic import SHAPES, NegativeSampler, make_stream
+    shape = SHAPES[args.workload]
+    n_events = args.events or shape.n_events
+    st = make_stream(shape, seed=args.seed, n_events=n_events, with_efeats=with_efeats)
+    neg = NegativeSampler(st.src, st.dst, seed=args.seed).pre_sample_neg_dsts(st.n_events, BATCH)
+    return shape, st, neg
+
+
+def chunk_bounds(n, rank, world, bs, seed=0):
+    """The reference's ChunkSampler partition (tiger/data/data_loader.py:27-37)."""
+    import torch
+    g = torch.Generator()
+    g.manual_seed(seed)
+    residual = n % (world * bs)
+    shift = int(torch.randint(0, residual + 1, size=(), generator=g))
+    length = n // (world * bs) * bs
+    return shift + length * rank, shift + length * (rank + 1)
+
+
+def batch_window(args, n_events, rank, world):
+    """[first batch start, number of whole batches available] for this rank."""
+    if world > 1:
+        lo, hi = chunk_bounds(n_events, rank, world, BATCH, args.seed)
+    else:
+        lo = min(args.skip_batches, max(0, n_events // BATCH - 2)) * BATCH
+        hi = n_events
+    return lo, (hi - lo) // BATCH
+
+
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), f'--query-gpu={self.FIELDS}',
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, names, reasons = [], ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], set()
+        for r in rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                out['sm_max_mhz'] = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(n)
+        if sm:
+            out['sm_mhz'] = float(np.median(sm))
+            out['samples'] = len(sm)
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU leg: the oracle restatement of the reference path on the host cores
+# ------------------------------------------------------------------------------------------
+def oracle_runner(args, shape, st, neg, lo):
+    """Returns step(i) running batch i (collate + lazy restart + contrast step) on the CPU."""
+    import torch
+    from oracle import tiger_oracle as O
+    from www2023tiger_b200.init import random_weights
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N, d = st.n_nodes, st.dim
+    de = st.efeats.shape[1] if st.efeats is not None else d
+    W = random_weights(d, de, n_nodes=N, restarter='static', seed=args.seed)
+    graph = O.OracleGraph(st.src, st.dst, st.ts, st.eids, n_nodes=N)
+    model = O.OracleTIGER(W, graph, N, d, st.efeats, None, n_neighbors=K_NEIGH, n_head=N_HEAD,
+                          msg_src=shape.msg_src, upd_src=shape.upd_src, restarter='static')
+    uptodate = np.zeros(N, dtype=bool)
+
+    def step(i):
+        s = slice(lo + i * BATCH, lo + (i + 1) * BATCH)
+        b = O.collate(graph, st.src[s], st.dst[s], neg[s], st.ts[s], st.eids[s], K_NEIGH)
+        rn = O.lazy_restart_nodes(b.involved, uptodate)
+        model.restart(rn, np.full(len(rn), b.ts.min(), dtype=np.float32))
+        with torch.no_grad():
+            model.contrast_step(b)
+    return step, cores
+
+
+def time_oracle(step, n_batches, warmup=2):
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(warmup, warmup + n_batches):
+        step(i)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    shape, st, neg = load_workload(args)
+    lo, avail = batch_window(args, st.n_events, 0, max(world, 1))
+    step, cores = oracle_runner(args, shape, st, neg, lo)
+    budget_s = 240.0
+    W = min(args.warmup, max(avail - 1, 0))
+    t0 = time.perf_counter()
+    for i in range(W):
+        step(i)
+    per = (time.perf_counter() - t0) / max(W, 1)
+    K = min(args.steps, avail - W)
+    if per > 0 and K * per > budget_s:
+        K = max(3, int(budget_s / per))
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        step(i)
+    dt = time.perf_counter() - t0
+    value = K * BATCH / dt
+    sample = f'{K} consecutive batches of {BATCH} events of the {args.workload}-shaped stream from event {lo}'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': K,
+        'warmup': W, 'ms_per_step': dt / K * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, shape, st, world),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, shape, st, world):
+    return {'workload': f'{args.workload}-shaped synthetic stream ({st.n_nodes - 1} nodes, {st.n_events} events, '
+                        f'd={st.dim}, de={shape.efeat_dim or st.dim}), static restarter, lazy restart, '
+                        f'msg_src={shape.msg_src}, upd_src={shape.upd_src}',
+            'batch': BATCH, 'n_neighbors': K_NEIGH, 'n_heads': N_HEAD, 'n_layers': 1,
+            'partition': 'ChunkSampler time chunks, rank-local memory replicas, no data-path collective'
+            if world > 1 else 'single stream',
+            'l2': 'tables read per step (edge features + message store + memories) exceed the 126 MB L2 for '
+                  'reddit/scaled; no flush between steps: consecutive batches are state-dependent and run '
+                  'back to back exactly as in the real workload'}
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(kernel, c, d, de, M, B, K):
+    """Bytes each kernel must move per launch; c = mean device counters."""
+    U, O, R, P, Po, deg = c['U'], c['O'], c['R'], c['P'], c['Po'], c['log_deg']
+    f = 4
+    return {
+        'tiger_find_recent': 3 * B * (deg * 8 + K * 16 + K * 20) + 3 * B * 16,
+        'tiger_compact_involved': c['bitmap_words'] * 4 * 2 + U * (8 + 4 + 1) + O * 8 + R * 8,
+        'tiger_static_restart': R * (2 * 2 * d * f + deg * 8 + 16),
+        'tiger_gru_update': O * (M + 1) * f + O * d * f + O * d * f,
+        'tiger_temporal_attention': 3 * B * K * (d + de) * f + 3 * B * K * 20 + 3 * B * d * f * 2,
+        'tiger_select_latest': 2 * B * (8 + 4 + 1),
+        'tiger_right_writeback': Po * (2 * d + 2) * f + 2 * B * 9,
+        'tiger_store_messages': P * ((2 * d + de) * f + M * f + 8) + 2 * B * 13,
+        'tiger_left_writeback': P * (2 * d + 2) * f + 2 * B * 9,
+        'tiger_link_score': 3 * B * d * f + 3 * B * K * 8 + 2 * B * f,
+    }.get(kernel, 0)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from www2023tiger_b200 import _lib, ops
+    from www2023tiger_b200.engine import StreamRunner, TigerEngine
+    from www2023tiger_b200.init import random_weights
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the TIGER B200 path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()
+
+    # ---- workload: stream, features, CSR, weights, engine ----
+    shape, st, neg = load_workload(args, with_efeats=st_fits_host(args))
+    N, d = st.n_nodes, st.dim
+    de = shape.efeat_dim or d
+    if shape.efeat_dim > 0:
+        if st.efeats is not None:
+            efeats = torch.from_numpy(st.efeats).to(dev)
+        else:
+            efeats = torch.empty(st.n_events + 1, de, device=dev)
+            g = torch.Generator(device=dev).manual_seed(args.seed)
+            chunk = 1 << 22
+            for i in range(0, st.n_events + 1, chunk):
+                efeats[i:i + chunk].normal_(generator=g)
+            efeats[0] = 0
+    else:
+        efeats = None
+    to = lambda x, dt: torch.as_tensor(x).to(dt).to(dev).contiguous()
+    csr = ops.csr_build(to(st.src, torch.int64), to(st.dst, torch.int64), to(st.ts, torch.float64),
+                        to(st.eids, torch.int64), N)
+    W = random_weights(d, de, n_nodes=N, restarter='static', seed=args.seed)
+    eng = TigerEngine(W, csr, n_nodes=N, dim=d, efeats=efeats, n_neighbors=K_NEIGH, n_head=N_HEAD,
+                      batch_size=BATCH, msg_src=shape.msg_src, upd_src=shape.upd_src, restarter='static',
+                      lazy_restart=True, device=dev)
+    lo, avail = batch_window(args, st.n_events, rank, world)
+    if avail < 8:
+        raise SystemExit('stream too short for this rank')
+    B = BATCH
+
+    # all batch inputs of this rank's window, resident in HBM: [avail, 5B] int64 (ts as float64 bits)
+    host_in = np.empty((avail, 5 * B), dtype=np.int64)
+    s = slice(lo, lo + avail * B)
+    host_in[:, :B] = st.src[s].reshape(avail, B)
+    host_in[:, B:2 * B] = st.dst[s].reshape(avail, B)
+    host_in[:, 2 * B:3 * B] = neg[s].reshape(avail, B)
+    host_in[:, 3 * B:4 * B] = st.eids[s].reshape(avail, B)
+    host_in[:, 4 * B:] = st.ts[s].reshape(avail, B).view(np.int64)
+    dev_in = torch.from_numpy(host_in).to(dev)
+
+    runner = StreamRunner(eng)
+    eng.inp.copy_(dev_in[0])
+    runner.capture(warmup=2)
+    eng.reset()
+
+    def device_step(i):
+        j = i % avail
+        if j == 0 and i > 0:
+            eng.reset()           # epoch boundary (train_self_supervised.py:127-128): the window wraps
+        eng.inp.copy_(dev_in[j], non_blocking=True)
+        runner.run_device()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Wm, K = args.warmup, args.steps
+    for i in range(Wm):
+        device_step(i)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(Wm, Wm + K):
+        device_step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    eng.check_errors()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * K * B / (ms * 1e-3)
+
+    # ---- e2e: pinned host buffers -> H2D -> graph -> D2H of scores + loss, every step ----
+    e2e = None
+    if not args.no_e2e:
+        eng.reset()
+        cols = lambda j: (host_in[j, :B], host_in[j, B:2 * B], host_in[j, 2 * B:3 * B],
+                          host_in[j, 4 * B:].view(np.float64), host_in[j, 3 * B:4 * B])
+        slots = []
+        for i in range(Wm):
+            slots.append(runner.submit_host(*cols(i % avail)))
+        for sl in set(slots):
+            runner.wait(sl)
+        barrier()
+        checksum = 0.0
+        t0 = time.perf_counter()
+        pending = []
+        for i in range(Wm, Wm + K):
+            j = i % avail
+            if j == 0:
+                eng.reset()
+            pending.append(runner.submit_host(*cols(j)))
+            if len(pending) >= runner.n_slots:
+                checksum += float(runner.wait(pending.pop(0))[2])   # the step's loss, read on the host
+        while pending:
+            checksum += float(runner.wait(pending.pop(0))[2])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        eng.check_errors()
+        e2e = {'value': world * K * B / dt, 'unit': UNIT, 'h2d_bytes_per_step': runner.h2d_bytes_per_step,
+               'd2h_bytes_per_step': runner.d2h_bytes_per_step, 'ms_per_step': dt / K * 1e3,
+               'mean_loss': checksum / K}
+    clk = clocks.stop() if clocks is not None else None
+
+    # ---- per-kernel CUDA-event breakdown (eager launches, same stream, same state progression) ----
+    roofline, kernels = None, None
+    if rank == 0 and args.profile_steps > 0:
+        kernels, counters = profile_kernels(args, eng, dev_in, avail, csr)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except OSError:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        top = max(kernels, key=lambda k: kernels[k]['us'])
+        for k, v in kernels.items():
+            v['bytes'] = int(algorithmic_bytes(k, counters, d, de, eng.M, B, K_NEIGH))
+            v['gbs'] = v['bytes'] / (v['us'] * 1e-6) / 1e9 if v['us'] > 0 else 0.0
+        traffic = None
+        tf = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tf):
+            traffic = json.load(open(tf)).get(args.workload, {}).get(top)
+        roofline = {'bound': 'hbm', 'kernel': top, 'achieved': kernels[top]['gbs'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': kernels[top]['gbs'] / peak, 'traffic': traffic,
+                    'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback',
+                    'launch_us': kernels[top]['us'], 'bytes_per_launch': kernels[top]['bytes'],
+                    'counters': counters}
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N=1 ----
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_batches > 0 and (st.efeats is not None or shape.efeat_dim == 0):
+        step, cores = oracle_runner(args, shape, st, neg, lo)
+        n = min(args.cpu_batches, avail - 2)
+        dt = time_oracle(step, n)
+        cpu = {'value': n * B / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'{n} consecutive batches of {B} events from event {lo} (oracle/tiger_oracle.py: collate + '
+                         f'lazy restart + contrast step), torch {torch.__version__} CPU, {cores} threads',
+               'ms_per_step': dt / n * 1e3}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, shape, st, world),
+            'e2e': e2e, 'gpu_launches': eng.launches_per_step() * K, 'clocks': clk, 'roofline': roofline,
+            'cpu_baseline': cpu, 'kernels': kernels,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def st_fits_host(args):
+    return args.workload != 'scaled'
+
+
+def profile_kernels(args, eng, dev_in, avail, csr):
+    """Eager pass with a CUDA-event pair around every C-ABI launch; returns mean us per entry point and
+    the mean device counters the algorithmic-byte formulas need."""
+    import torch
+    from www2023tiger_b200 import _lib
+    eng.reset()
+    records = []
+    orig_call = _lib.call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        records.append((name, e0, e1))
+
+    from www2023tiger_b200 import ops
+    n_steps = min(args.profile_steps, avail)
+    warm = min(20, n_steps // 2)
+    counts = []
+    ops.call = timed_call
+    try:
+        for i in range(n_steps):
+            if i == warm:
+                torch.cuda.synchronize()
+                records.clear()
+                counts.clear()
+            eng.inp.copy_(dev_in[i], non_blocking=True)
+            eng.step()
+            persisted = (eng.winner.bool() & (eng.gru_row[eng.pos] >= 0)).sum()
+            counts.append(torch.cat([eng.counts[:3].long(), eng.winner.sum().reshape(1), persisted.reshape(1)]))
+    finally:
+        ops.call = orig_call
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1 in records:
+        agg.setdefault(name, []).append(e0.elapsed_time(e1) * 1e3)
+    n = n_steps - warm
+    kernels = {k: {'us': float(np.sum(v)) / n, 'launches_per_step': len(v) / n} for k, v in agg.items()}
+    U, O_, R, P, Po = (float(x) for x in torch.stack(counts).double().mean(0).cpu())
+    deg = float(csr.indptr[1:].sub(csr.indptr[:-1]).float().mean().item())
+    counters = {'U': U, 'O': O_, 'R': R, 'P': P, 'Po': Po,
+                'log_deg': max(1.0, math.log2(max(deg, 2.0))), 'bitmap_words': (eng.N + 31) // 32}
+    return kernels, counters
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()
