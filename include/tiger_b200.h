@@ -64,12 +64,13 @@ int tiger_csr_build(const int64_t* src, const int64_t* dst, const double* ts, co
  * out_dirs, out_ts32 and mark_bitmap may be NULL.  mark_bitmap (ceil(n_nodes/32) words)
  * receives one bit per query node and per returned neighbor (involved-node marking of
  * collate_memory_nodes, data_loader.py:109-121).  out_ts32 (ts_period floats) receives
- * (float)q_ts - the model-side timestamps of GraphCollator.__call__ (data_loader.py:92). */
+ * (float)q_ts - the model-side timestamps of GraphCollator.__call__ (data_loader.py:92).
+ * count (device, may be NULL) limits the queries to the first *count. */
 int tiger_find_recent(const int64_t* indptr, const int32_t* adj_nbr, const int32_t* adj_eid,
                       const double* adj_ts, const uint8_t* adj_flag, const int64_t* q_nids,
                       const double* q_ts, int64_t n_query, int64_t ts_period, int k,
                       int64_t* out_nids, int64_t* out_eids, float* out_ts, int64_t* out_dirs,
-                      float* out_ts32, uint32_t* mark_bitmap, void* stream);
+                      float* out_ts32, uint32_t* mark_bitmap, const int32_t* count, void* stream);
 
 /* a4  GraphCollator.check_in_window (data_loader.py:61-67): hit[i,k] = (center[i]==neigh[i,k]). */
 int tiger_hit_window(const int64_t* center, const int64_t* neigh, int64_t n, int k, float* hit,
@@ -111,8 +112,10 @@ int tiger_select_latest(const int64_t* nids, const void* ts, int ts_is_f64, int6
                         uint8_t* winner, int64_t* unique_ids, int64_t* index, int32_t* count,
                         void* stream);
 
-/* a22  anonymized_reindex (utils.py:19-27): per row rank by last occurrence, 0 stays 0. */
-int tiger_anonymized_reindex(const int64_t* hist_nids, int64_t n, int len, int64_t* out, void* stream);
+/* a22  anonymized_reindex (utils.py:19-27): per row rank by last occurrence, 0 stays 0.
+ * count (device, may be NULL) limits the rows to the first *count. */
+int tiger_anonymized_reindex(const int64_t* hist_nids, int64_t n, int len, int64_t* out,
+                             const int32_t* count, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Memory / message store (tiger/model/memory.py, time_encoding.py)
@@ -263,6 +266,41 @@ int tiger_static_restart(const int64_t* nids, const int32_t* count, int64_t n,
                          const float* right_emb, int d, float* left_vals, float* left_ts,
                          uint8_t* left_active, float* right_vals, float* right_ts,
                          uint8_t* right_active, uint8_t* has_msg, float* out_prev_ts, void* stream);
+
+/* a21 + a24  SeqRestarter.forward (restarters.py:51-114) as a launch sequence; see restart_seq.cu.
+ *
+ * tiger_min_time: out[0] = (double)min(ts[0..n)) - the float32 ts.min() that restart() receives
+ * (train_self_supervised.py:161, eval_utils.py:40), widened for the float64 history search. */
+int tiger_min_time(const float* ts, int64_t n, double* out, void* stream);
+
+/* Event tokens of SeqRestarter.forward (restarters.py:85-104): for node i and history position j
+ *   x[i,j,:] = [nf(src) | nf(dst) | anony_emb[anony_ids] | ef(hist_eids) | cos((t_last - hist_ts)*w + b)]
+ * (width d_model = 4d + de) with the reference's literal direction rule (:93-94); the last
+ * position keeps only its time code (:104).  mask[i,j] = hist_nids==0 with the last column forced
+ * valid (:86-87); prev_ts[i] = hist_ts[i,-1].  count (device, may be NULL) overrides n. */
+int tiger_seq_tokens(const int64_t* nids, const int32_t* count, int64_t n, int len,
+                     const int64_t* hist_nids, const int64_t* hist_eids, const float* hist_ts,
+                     const int64_t* hist_dirs, const int64_t* anony_ids, const float* nfeats,
+                     const float* efeats, int d, int de, const float* anony_emb, const float* time_w,
+                     const float* time_b, float* x, uint8_t* mask, float* prev_ts, void* stream);
+
+/* C[m,n] = act(sum_k A[m,k] * W[n,k] + bias[n]): fp32 FFMA GEMM on row-major A [M,K] and nn.Linear
+ * style weights W [N,K] (bias may be NULL; relu != 0 applies max(.,0)).  The row count is
+ * min(m_rows, *count * rows_per_count) when count (device) is non-NULL.  Replaces the in/out
+ * projections of nn.MultiheadAttention, nn.Linear and MergeLayer on the restarter path
+ * (restarters.py:45-50,106-111; basic_modules.py:16-19). */
+int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
+                   int64_t ldc, int64_t m_rows, const int32_t* count, int64_t rows_per_count, int n_cols,
+                   int k_dim, int relu, void* stream);
+
+/* Self-attention weights of SeqRestarter's MHA (restarters.py:106, torch MHA need_weights branch),
+ * reduced to what the mean over positions needs: for node i and head h
+ *   p_h = softmax_keys((q_h * sqrt(1/hd)) k_h^T + mask)   [len x len], pbar_h = mean over queries,
+ *   xbar[i,h,:] = sum_j pbar_h[j] * x[i,j,:]               [d_model]
+ * qk [n*len, ld_qk] holds q in columns [0,d_model) and k in [d_model, 2*d_model).  len <= 64. */
+int tiger_seq_attn_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask,
+                        const int32_t* count, int64_t n, int len, int d_model, int n_head, float* xbar,
+                        void* stream);
 
 #ifdef __cplusplus
 }

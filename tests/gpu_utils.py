@@ -22,12 +22,13 @@ def device_csr(src, dst, ts, eids, n_nodes):
 
 
 def engine_from(W, csr, *, N, dim, efeats, nfeats, K, H, B, msg_src, upd_src, restarter=None, lazy_restart=False,
-                want_targets=True):
+                want_targets=True, hist_len=40):
     return TigerEngine({k: torch.as_tensor(v) for k, v in W.items()}, csr, n_nodes=N, dim=dim,
                        efeats=None if efeats is None else dev(efeats, torch.float32),
                        nfeats=None if nfeats is None else dev(nfeats, torch.float32),
                        n_neighbors=K, n_head=H, batch_size=B, msg_src=msg_src, upd_src=upd_src,
-                       restarter=restarter, lazy_restart=lazy_restart, want_restarter_targets=want_targets)
+                       restarter=restarter, hist_len=hist_len, lazy_restart=lazy_restart,
+                       want_restarter_targets=want_targets)
 
 
 def oracle_from(W, src, dst, ts, eids, *, N, dim, efeats, nfeats, K, H, msg_src, upd_src, restarter='static',

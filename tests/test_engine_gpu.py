@@ -36,19 +36,13 @@ def check_state(gu, e, left_vals, right_vals, left_ts, right_ts, msg_vals, msg_t
 def test_engine_replays_reference_golden(gu, name):
     g = Golden(name)
     csr = gu.device_csr(g.src, g.dst, g.ts, g.eids, g.N)
-    fused_restart = g.lazy_restart and g.restarter == 'static'
+    fused_restart = g.lazy_restart
     e = gu.engine_from(g.W, csr, N=g.N, dim=g.dim, efeats=g.efeats, nfeats=g.nfeats, K=g.K, H=g.n_heads, B=g.bs,
                        msg_src=g.msg_src, upd_src=g.upd_src, restarter=g.restarter if fused_restart else None,
-                       lazy_restart=fused_restart)
+                       lazy_restart=fused_restart, hist_len=g.hist_len)
     B = g.bs
     for ib in range(g.n_batches):
         what = f'{name} batch {ib} '
-        if g.lazy_restart and not fused_restart and g.has(ib, 'restart_hl'):
-            # seq restarter: inject the reference's restart outputs (the restarter itself is tested separately)
-            n = gu.dev(g.b(ib, 'restart_nids'))
-            e.left_vals[n], e.right_vals[n] = gu.dev(g.b(ib, 'restart_hl')), gu.dev(g.b(ib, 'restart_hr'))
-            e.left_ts[n] = e.right_ts[n] = gu.dev(g.b(ib, 'restart_pt'))
-            e.has_msg[n] = 0
         e.set_batch(*g.batch(ib))
         e.step()
         e.check_errors()
@@ -59,6 +53,11 @@ def test_engine_replays_reference_golden(gu, name):
         assert np.array_equal(gu.cpu(e.involved[:U]), g.b(ib, 'involved')), what
         if fused_restart:
             assert np.array_equal(gu.cpu(e.restart_nodes[:R]), g.b(ib, 'restart_nids')), what
+            if g.restarter == 'seq' and g.has(ib, 'restart_hl'):
+                # the seq restarter's own outputs for the lazily restarted nodes (restarters.py:51-114)
+                assert_close(gu.cpu(e.seq.h_left[:R]), g.b(ib, 'restart_hl'), TOL, what + 'restart_hl')
+                assert_close(gu.cpu(e.seq.h_right[:R]), g.b(ib, 'restart_hr'), TOL, what + 'restart_hr')
+                assert np.array_equal(gu.cpu(e.seq.prev_ts[:R]), g.b(ib, 'restart_pt')), what + 'restart_pt'
         assert np.array_equal(gu.cpu(e.outdated[:Oc]),
                               np.intersect1d(g.b(ib, 'pending_before'), g.b(ib, 'involved'))), what
         assert_close(gu.cpu(e.emb[:2 * B]), g.b(ib, 'h_left'), TOL, what + 'h_left')
@@ -88,25 +87,27 @@ def run_oracle(model, graph, st, neg, B, K, n_batches, lazy, start=0):
     return outs
 
 
-@pytest.mark.parametrize('shape,msg_src,upd_src,lazy', [
-    (StreamShape('w', 900, 120, 9000, 172, None), 'left', 'right', False),
-    (StreamShape('r', 900, 120, 9000, 172, None), 'left', 'right', True),
-    (StreamShape('m', 700, 30, 9000, 4, 100), 'right', 'right', True),
-    (StreamShape('l', 200, 200, 9000, 0, 100, horizon=1.4e8), 'left', 'right', False),
+@pytest.mark.parametrize('shape,msg_src,upd_src,lazy,restarter', [
+    (StreamShape('w', 900, 120, 9000, 172, None), 'left', 'right', False, 'static'),
+    (StreamShape('r', 900, 120, 9000, 172, None), 'left', 'right', True, 'static'),
+    (StreamShape('m', 700, 30, 9000, 4, 100), 'right', 'right', True, 'static'),
+    (StreamShape('l', 200, 200, 9000, 0, 100, horizon=1.4e8), 'left', 'right', False, 'static'),
+    (StreamShape('s', 900, 120, 9000, 32, None), 'left', 'right', True, 'seq'),
+    (StreamShape('t', 300, 60, 9000, 4, 20), 'right', 'right', True, 'seq'),
 ])
-def test_engine_matches_oracle_on_stream(gu, shape, msg_src, upd_src, lazy):
+def test_engine_matches_oracle_on_stream(gu, shape, msg_src, upd_src, lazy, restarter):
     B, K, H, n_batches, start = 200, 10, 2, 30, 2000
     st = make_stream(shape, seed=2)
     neg = NegativeSampler(st.src, st.dst, seed=0).pre_sample_neg_dsts(st.n_events)
     N, d = st.n_nodes, st.dim
     de = st.efeats.shape[1] if st.efeats is not None else d
-    W = perturb_biases(random_weights(d, de, n_nodes=N, restarter='static', nonzero_static=True, seed=1))
+    W = perturb_biases(random_weights(d, de, n_nodes=N, restarter=restarter, nonzero_static=True, seed=1))
     graph, model = gu.oracle_from(W, st.src, st.dst, st.ts, st.eids, N=N, dim=d, efeats=st.efeats, nfeats=None,
-                                  K=K, H=H, msg_src=msg_src, upd_src=upd_src)
+                                  K=K, H=H, msg_src=msg_src, upd_src=upd_src, restarter=restarter)
     outs = run_oracle(model, graph, st, neg, B, K, n_batches, lazy, start)
     csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
     e = gu.engine_from(W, csr, N=N, dim=d, efeats=st.efeats, nfeats=None, K=K, H=H, B=B, msg_src=msg_src,
-                       upd_src=upd_src, restarter='static', lazy_restart=lazy)
+                       upd_src=upd_src, restarter=restarter, lazy_restart=lazy)
     # graph-captured replay from pinned host buffers (the e2e path)
     runner = StreamRunner(e)
     lo = start

@@ -274,3 +274,84 @@ def test_link_score_matches_oracle(gu, d, B, k):
         scores, dl = ops.link_score(pack, gu.dev(h), gu.dev(src), gu.dev(dst), gu.dev(neg), gu.dev(neigh))
         assert_close(gu.cpu(scores), torch.cat([ps, ns]).numpy(), TOL, 'scores')
         assert_close(gu.cpu(dl), loss.reshape(1).numpy(), TOL, 'loss')
+
+
+# ------------------------------------------------------------------ restarter-path GEMM
+@pytest.mark.parametrize('m,n,k', [(1, 7, 5), (54, 172, 860), (300, 1720, 860), (2200, 130, 54), (33, 65, 17)])
+def test_sgemm_nt_matches_torch(gu, m, n, k):
+    g = torch.Generator().manual_seed(m * 1000 + n)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k ** 0.5
+    b = torch.randn(n, generator=g)
+    for relu in (False, True):
+        ref = a.double() @ w.double().t() + b.double()
+        ref = torch.relu(ref) if relu else ref
+        out = torch.empty(m, n, device='cuda')
+        ops.sgemm_nt(gu.dev(a), gu.dev(w), gu.dev(b), out, relu=relu)
+        assert_close(gu.cpu(out), ref.numpy(), 2e-6, f'sgemm {m}x{n}x{k}')
+
+
+def test_sgemm_nt_device_count_and_slices(gu):
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(400, 96, generator=g)
+    w = torch.randn(80, 96, generator=g)
+    big = torch.full((400, 200), -7.0, device='cuda')
+    count = torch.tensor([9], dtype=torch.int32, device='cuda')
+    # rows = count * rows_per_count = 36; output into a column slice of a wider buffer; K = first 50 columns
+    ops.sgemm_nt(gu.dev(a), gu.dev(w), None, big[:, 40:120], k_dim=50, count=count, rows_per_count=4)
+    ref = a[:36, :50].double() @ w[:, :50].double().t()
+    assert_close(gu.cpu(big[:36, 40:120]), ref.numpy(), 2e-6, 'sliced')
+    rest = gu.cpu(big)
+    assert (rest[36:] == -7).all() and (rest[:, :40] == -7).all() and (rest[:, 120:] == -7).all()
+
+
+# ------------------------------------------------------------------ a21: SeqRestarter.forward
+@pytest.mark.parametrize('name', [c for c in CASES if c.startswith('seq')])
+def test_seq_restarter_matches_reference_golden(gu, name):
+    """Restarter called with the collated restart data (training-target path, tiger.py:576-581)."""
+    g = Golden(name)
+    de = g.efeats.shape[1] if g.efeats is not None else g.dim
+    op = ops.SeqRestarterOp(g.dim, de, g.hist_len, g.n_heads, 2 * g.bs, 'cuda')
+    op.set_weights(g.W)
+    nf = None if g.nfeats is None else gu.dev(g.nfeats, torch.float32)
+    ef = None if g.efeats is None else gu.dev(g.efeats, torch.float32)
+    for ib in range(g.n_batches):
+        nids = g.b(ib, 'r_nids')
+        n = len(nids)
+        hist = tuple(gu.dev(g.b(ib, k)) for k in ('r_hist_nids', 'r_hist_eids', 'r_hist_ts', 'r_hist_dirs', 'r_anon'))
+        hl, hr, pt = op.forward(gu.dev(nids), n, nf, ef, hist=hist)
+        assert_close(gu.cpu(hl), g.b(ib, 'surrogate_left'), TOL, f'{name} b{ib} left')
+        assert_close(gu.cpu(hr), g.b(ib, 'surrogate_right'), TOL, f'{name} b{ib} right')
+        assert np.array_equal(gu.cpu(pt), g.b(ib, 'r_hist_ts')[:, -1])
+
+
+@pytest.mark.parametrize('d,de,L,with_nf', [(172, 172, 40, False), (100, 4, 40, False), (24, 10, 64, True)])
+def test_seq_restarter_matches_oracle(gu, d, de, L, with_nf):
+    """Restarter with computation_graph=None: history looked up on the device CSR (restart path)."""
+    st = make_stream(StreamShape('s', 150, 25, 8000, de, None, horizon=5000.), seed=6, nfeat_dim=d if with_nf else 0)
+    N = st.n_nodes
+    W = perturb_biases(random_weights(d, de, n_nodes=N, restarter='seq', hist_len=L, seed=3))
+    graph = O.OracleGraph(st.src, st.dst, st.ts, st.eids, n_nodes=N)
+    model = O.OracleTIGER(W, graph, N, d, st.efeats, st.nfeats, restarter='seq', hist_len=L)
+    rng = np.random.RandomState(0)
+    nids = np.concatenate([[0], rng.choice(np.arange(1, N), 70, replace=False)]).astype(np.int64)
+    t = np.float32(3000.0)
+    ref_l, ref_r, ref_pt = model.restarter_forward(nids, np.full(len(nids), t, dtype=np.float32))
+    csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
+    op = ops.SeqRestarterOp(d, de, L, 2, 128, 'cuda')
+    op.set_weights(W)
+    count = torch.tensor([len(nids)], dtype=torch.int32, device='cuda')
+    dn = torch.zeros(128, dtype=torch.int64, device='cuda')
+    dn[:len(nids)] = gu.dev(nids)
+    ops.min_time(gu.dev(np.array([5000., 3000., 4000.], dtype=np.float32)), op.tmin)
+    assert float(op.tmin) == 3000.0
+    op.history(csr, dn, op.tmin, 128, ts_period=1, count=count)
+    hn, he_, ht, hd = graph.get_history(nids, np.full(len(nids), 3000.0), L)
+    n = len(nids)
+    assert np.array_equal(gu.cpu(op.hist_nids[:n]), hn) and np.array_equal(gu.cpu(op.hist_dirs[:n]), hd)
+    assert np.array_equal(gu.cpu(op.anony[:n]), O.anonymized_reindex(hn))
+    hl, hr, pt = op.forward(dn, 128, None if st.nfeats is None else gu.dev(st.nfeats, torch.float32),
+                            gu.dev(st.efeats, torch.float32), count=count)
+    assert_close(gu.cpu(hl[:n]), ref_l.numpy(), TOL, 'h_left')
+    assert_close(gu.cpu(hr[:n]), ref_r.numpy(), TOL, 'h_right')
+    assert np.array_equal(gu.cpu(pt[:n]), ref_pt.numpy())

@@ -19,12 +19,12 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_abi_version': '',
     'tiger_csr_build_work_bytes': 'll',
     'tiger_csr_build': 'ppppll' + 'ppppp' + 'p' + 'p',
-    'tiger_find_recent': 'ppppp' + 'pp' + 'lli' + 'pppp' + 'pp' + 'p',
+    'tiger_find_recent': 'ppppp' + 'pp' + 'lli' + 'pppp' + 'pp' + 'p' + 'p',
     'tiger_hit_window': 'ppli' + 'p' + 'p',
     'tiger_mark_nodes': 'plpl' + 'p',
     'tiger_compact_involved': 'plpp' + 'plp' + 'ppp' + 'pp' + 'p',
     'tiger_select_latest': 'ppil' + 'llppp' + 'pppp' + 'p',
-    'tiger_anonymized_reindex': 'plip' + 'p',
+    'tiger_anonymized_reindex': 'plip' + 'p' + 'p',
     'tiger_gather_rows': 'plplp' + 'pp' + 'p',
     'tiger_scatter_rows': 'plplp' + 'ppp' + 'pip' + 'p',
     'tiger_time_encode': 'plppip' + 'p',
@@ -37,6 +37,10 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_temporal_attention': 'ppll' + 'pppi' + 'pppi' + 'pp' + 'iii' + 'pp' + 'p',
     'tiger_temporal_attention_dense': 'pppppp' + 'li' + 'iii' + 'pp' + 'p',
     'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
+    'tiger_min_time': 'plp' + 'p',
+    'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
+    'tiger_sgemm_nt': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
+    'tiger_seq_attn_pool': 'plpp' + 'pli' + 'iip' + 'p',
     'tiger_static_restart': 'ppl' + 'plp' + 'pp' + 'ppi' + 'ppp' + 'ppp' + 'pp' + 'p',
 }
 _KIND = {'p': P, 'l': L, 'i': I}

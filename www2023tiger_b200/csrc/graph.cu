@@ -13,13 +13,13 @@ __global__ void __launch_bounds__(256)
 find_recent_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ adj_nbr,
                    const int32_t* __restrict__ adj_eid, const double* __restrict__ adj_ts,
                    const uint8_t* __restrict__ adj_flag, const int64_t* __restrict__ q_nids,
-                   const double* __restrict__ q_ts, int64_t n_query, int64_t ts_period, int k,
-                   int64_t* __restrict__ out_nids, int64_t* __restrict__ out_eids,
+                   const double* __restrict__ q_ts, int64_t n_query, const int32_t* __restrict__ count,
+                   int64_t ts_period, int k, int64_t* __restrict__ out_nids, int64_t* __restrict__ out_eids,
                    float* __restrict__ out_ts, int64_t* __restrict__ out_dirs,
                    float* __restrict__ out_ts32, uint32_t* __restrict__ bitmap) {
   const int lane = lane_id();
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block();
-  if (q >= n_query) return;
+  if (q >= n_query || (count != nullptr && q >= *count)) return;
   const int64_t nid = q_nids[q];
   const double t = q_ts[q % ts_period];
   if (out_ts32 != nullptr && q < ts_period && lane == 0) out_ts32[q] = (float)t;
@@ -50,14 +50,14 @@ extern "C" int tiger_find_recent(const int64_t* indptr, const int32_t* adj_nbr, 
                                  const double* adj_ts, const uint8_t* adj_flag, const int64_t* q_nids,
                                  const double* q_ts, int64_t n_query, int64_t ts_period, int k,
                                  int64_t* out_nids, int64_t* out_eids, float* out_ts, int64_t* out_dirs,
-                                 float* out_ts32, uint32_t* mark_bitmap, void* stream) {
+                                 float* out_ts32, uint32_t* mark_bitmap, const int32_t* count, void* stream) {
   if (n_query < 0 || k <= 0 || ts_period < 0) return TIGER_EINVAL;
   if (n_query == 0) return TIGER_OK;
   if (ts_period == 0) ts_period = n_query;
   const int warps = 8;
   const unsigned grid = (unsigned)((n_query + warps - 1) / warps);
   find_recent_kernel<<<grid, warps * 32, 0, as_stream(stream)>>>(
-      indptr, adj_nbr, adj_eid, adj_ts, adj_flag, q_nids, q_ts, n_query, ts_period, k, out_nids, out_eids,
+      indptr, adj_nbr, adj_eid, adj_ts, adj_flag, q_nids, q_ts, n_query, count, ts_period, k, out_nids, out_eids,
       out_ts, out_dirs, out_ts32, mark_bitmap);
   return tiger_launch_status();
 }

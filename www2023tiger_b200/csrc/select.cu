@@ -180,11 +180,13 @@ extern "C" int tiger_select_latest(const int64_t* nids, const void* ts, int ts_i
 // occurrence lies to the right of v's last occurrence; padding (0) stays 0 but, like the
 // reference's OrderedDict, still counts as a distinct value for the ids to its left.
 // ------------------------------------------------------------------------------------------
-__global__ void anonymized_reindex_kernel(const int64_t* __restrict__ hist, int len, int64_t* __restrict__ out) {
+__global__ void anonymized_reindex_kernel(const int64_t* __restrict__ hist, int len, const int32_t* __restrict__ count,
+                                          int64_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int64_t* s_v = reinterpret_cast<int64_t*>(smem_raw);
   uint8_t* s_last = reinterpret_cast<uint8_t*>(s_v + len);
   const int64_t row = blockIdx.x;
+  if (count != nullptr && row >= *count) return;
   for (int j = threadIdx.x; j < len; j += blockDim.x) s_v[j] = hist[row * len + j];
   __syncthreads();
   for (int j = threadIdx.x; j < len; j += blockDim.x) {
@@ -206,10 +208,11 @@ __global__ void anonymized_reindex_kernel(const int64_t* __restrict__ hist, int 
   }
 }
 
-extern "C" int tiger_anonymized_reindex(const int64_t* hist_nids, int64_t n, int len, int64_t* out, void* stream) {
+extern "C" int tiger_anonymized_reindex(const int64_t* hist_nids, int64_t n, int len, int64_t* out,
+                                        const int32_t* count, void* stream) {
   if (n < 0 || len <= 0 || len > 4096) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
   const int threads = len >= 256 ? 256 : (len + 31) / 32 * 32;
-  anonymized_reindex_kernel<<<(unsigned)n, threads, (size_t)len * 9, as_stream(stream)>>>(hist_nids, len, out);
+  anonymized_reindex_kernel<<<(unsigned)n, threads, (size_t)len * 9, as_stream(stream)>>>(hist_nids, len, count, out);
   return tiger_launch_status();
 }

@@ -38,14 +38,14 @@ class TigerEngine:
     def __init__(self, weights: Dict[str, Tensor], csr: ops.DeviceCSR, *, n_nodes: int, dim: int,
                  efeats: Optional[Tensor], nfeats: Optional[Tensor] = None, n_neighbors: int = 10,
                  n_head: int = 2, batch_size: int = 200, msg_src: str = 'left', upd_src: str = 'right',
-                 restarter: Optional[str] = None, hit_type: str = 'bin', lazy_restart: bool = False,
-                 want_restarter_targets: bool = False, device='cuda'):
+                 restarter: Optional[str] = None, hist_len: int = 40, hit_type: str = 'bin',
+                 lazy_restart: bool = False, want_restarter_targets: bool = False, device='cuda'):
         if msg_src not in ('left', 'right') or upd_src not in ('left', 'right'):
             raise ValueError(f'Invalid msg_src={msg_src} / upd_src={upd_src}')   # tiger.py:156-160
         if hit_type not in ('bin', 'none'):
             raise NotImplementedError(f'hit_type={hit_type}')
-        if lazy_restart and restarter != 'static':
-            raise NotImplementedError('fused lazy restart is implemented for the static restarter')
+        if lazy_restart and restarter not in ('static', 'seq'):
+            raise NotImplementedError(f'lazy restart needs a seq or static restarter, got {restarter!r}')
         dev = torch.device(device)
         self.device, self.csr = dev, csr
         self.N, self.K, self.H, self.B = n_nodes, n_neighbors, n_head, batch_size
@@ -93,6 +93,8 @@ class TigerEngine:
         self.gru_pack = None
         self.attn_pack = ops.AttnPack(self.d, self.de, dev)
         self.score_pack = ops.ScorePack(self.d, dev)
+        self.hist_len = hist_len
+        self.seq = ops.SeqRestarterOp(self.d, self.de, hist_len, n_head, self.cap, dev) if restarter == 'seq' else None
         self.load_weights(weights)
 
     # ------------------------------------------------------------------ parameters
@@ -118,6 +120,8 @@ class TigerEngine:
         if self.restarter == 'static':
             self.left_emb = g('restarter_fn.left_emb.weight')
             self.right_emb = g('restarter_fn.right_emb.weight')
+        elif self.restarter == 'seq':
+            self.seq.set_weights(W)
 
     # ------------------------------------------------------------------ state
     def reset(self):
@@ -164,11 +168,23 @@ class TigerEngine:
                              uptodate=self.uptodate if self.lazy_restart else None, outdated=self.outdated,
                              gru_row=self.gru_row, restart_nodes=self.restart_nodes if self.lazy_restart else None,
                              err_flags=self.err_flags)
-        if self.lazy_restart:
+        if self.lazy_restart and self.restarter == 'static':
             ops.static_restart(self.restart_nodes, self.cap, self.csr, self.left_emb, self.right_emb, d,
                                count=self.counts[2:], batch_ts=self.ts32, left_vals=self.left_vals,
                                left_ts=self.left_ts, left_active=self.left_active, right_vals=self.right_vals,
                                right_ts=self.right_ts, right_active=self.right_active, has_msg=self.has_msg)
+        elif self.lazy_restart:
+            # TIGER.restart with the seq restarter (tiger.py:594-609, restarters.py:51-114): history at
+            # ts.min() of the batch, surrogate h(t'-) / h(t'+), both memories overwritten without checks
+            # (compact_involved has already dropped the pending-message flags of these nodes)
+            R = self.counts[2:]
+            ops.min_time(self.ts32, self.seq.tmin)
+            self.seq.history(self.csr, self.restart_nodes, self.seq.tmin, self.cap, ts_period=1, count=R)
+            hl, hr, pt = self.seq.forward(self.restart_nodes, self.cap, self.nfeats, self.efeats, count=R)
+            ops.scatter_rows(self.left_vals, self.restart_nodes, hl, ts_table=self.left_ts, ts=pt,
+                             active=self.left_active, count=R)
+            ops.scatter_rows(self.right_vals, self.restart_nodes, hr, ts_table=self.right_ts, ts=pt,
+                             active=self.right_active, count=R)
         ops.gru_update(self.gru_pack, node_ids=self.outdated, x_table=self.msg_vals, h_table=upd_vals,
                        n_rows=self.cap, out=self.h_new, count=self.counts[1:], msg_ts=self.msg_ts,
                        check_mem_ts=msg_ts_mem, check_equal=(self.msg_src == 'left'), err_flags=self.err_flags)
@@ -190,7 +206,7 @@ class TigerEngine:
     def launches_per_step(self) -> int:
         n = sum(KERNELS_PER_STEP.values())
         if self.lazy_restart:
-            n += 1
+            n += 1 if self.restarter == 'static' else ops.SeqRestarterOp.LAUNCHES + 2
         if self.want_targets:
             n += 1
         return n

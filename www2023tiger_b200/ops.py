@@ -53,7 +53,8 @@ def csr_build(src: Tensor, dst: Tensor, ts: Tensor, eids: Tensor, n_nodes: int) 
 
 def find_recent(csr: DeviceCSR, q_nids: Tensor, q_ts: Tensor, k: int, *, ts_period: int = 0,
                 want_dirs: bool = True, ts32_out: Optional[Tensor] = None, bitmap: Optional[Tensor] = None,
-                out: Optional[Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]] = None):
+                out: Optional[Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]] = None,
+                count: Optional[Tensor] = None):
     """a2: K most recent events strictly before q_ts, right-aligned and zero-padded."""
     check_cuda(q_nids, q_ts)
     assert q_nids.dtype == i64 and q_ts.dtype == f64
@@ -67,7 +68,7 @@ def find_recent(csr: DeviceCSR, q_nids: Tensor, q_ts: Tensor, k: int, *, ts_peri
         o_n, o_e, o_t, o_d = out
     call('tiger_find_recent', ptr(csr.indptr), ptr(csr.nbr), ptr(csr.eid), ptr(csr.ts), ptr(csr.flag),
          ptr(q_nids), ptr(q_ts), n, ts_period or q_ts.numel(), k, ptr(o_n), ptr(o_e), ptr(o_t), ptr(o_d),
-         ptr(ts32_out), ptr(bitmap))
+         ptr(ts32_out), ptr(bitmap), ptr(count))
     return o_n, o_e, o_t, o_d
 
 
@@ -133,11 +134,12 @@ def select_latest(nids: Tensor, ts: Tensor, scratch: Optional[SelectScratch] = N
     return winner, uniq, index, count
 
 
-def anonymized_reindex(hist_nids: Tensor) -> Tensor:
+def anonymized_reindex(hist_nids: Tensor, out: Optional[Tensor] = None, count: Optional[Tensor] = None) -> Tensor:
     check_cuda(hist_nids)
     n, length = hist_nids.shape
-    out = torch.empty_like(hist_nids)
-    call('tiger_anonymized_reindex', ptr(hist_nids), n, length, ptr(out))
+    if out is None:
+        out = torch.empty_like(hist_nids)
+    call('tiger_anonymized_reindex', ptr(hist_nids), n, length, ptr(out), ptr(count))
     return out
 
 
@@ -352,3 +354,97 @@ def static_restart(nids: Tensor, n: int, csr: DeviceCSR, left_emb: Tensor, right
     call('tiger_static_restart', ptr(nids), ptr(count), n, ptr(batch_ts), batch_ts.numel() if batch_ts is not None else 0,
          ptr(q_ts), ptr(csr.indptr), ptr(csr.ts), ptr(left_emb), ptr(right_emb), d, ptr(left_vals), ptr(left_ts),
          ptr(left_active), ptr(right_vals), ptr(right_ts), ptr(right_active), ptr(has_msg), ptr(out_prev_ts))
+
+
+# ------------------------------------------------------------------------------------------
+# seq restarter (a21, a24)
+# ------------------------------------------------------------------------------------------
+def sgemm_nt(a: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, *, m_rows: Optional[int] = None,
+             k_dim: Optional[int] = None, relu: bool = False, count: Optional[Tensor] = None,
+             rows_per_count: int = 1) -> Tensor:
+    """out[m, n] = act(a[m, :k] @ w[n, :k].T + bias[n]); a/w/out may be column slices of wider buffers."""
+    check_cuda_strided(a, w, out)
+    m = a.shape[0] if m_rows is None else m_rows
+    k = a.shape[1] if k_dim is None else k_dim
+    call('tiger_sgemm_nt', ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), m,
+         ptr(count), rows_per_count, w.shape[0], k, int(relu))
+    return out
+
+
+def check_cuda_strided(*tensors):
+    for t in tensors:
+        if not t.is_cuda or t.dtype != f32 or t.dim() != 2 or t.stride(1) != 1:
+            raise _lib.TigerLibraryError('sgemm_nt needs 2-D float32 CUDA tensors with unit inner stride')
+
+
+def min_time(ts: Tensor, out: Tensor):
+    call('tiger_min_time', ptr(ts), ts.numel(), ptr(out))
+
+
+class SeqRestarterOp:
+    """SeqRestarter.forward (reference restarters.py:51-114) on device buffers of capacity `cap` rows.
+
+    Weights are used as stored (nn.Linear / in_proj layout), so there is nothing to re-pack when they
+    change; `set_weights` only keeps contiguous fp32 views."""
+
+    def __init__(self, d: int, de: int, hist_len: int, n_head: int, cap: int, device):
+        self.d, self.de, self.L, self.H, self.cap = d, de, hist_len, n_head, cap
+        self.dm = 4 * d + de
+        z = lambda *shape, dt=f32: torch.zeros(*shape, dtype=dt, device=device)
+        L, dm = hist_len, self.dm
+        self.hist_nids, self.hist_eids, self.hist_dirs = z(cap, L, dt=i64), z(cap, L, dt=i64), z(cap, L, dt=i64)
+        self.hist_ts = z(cap, L)
+        self.anony = z(cap, L, dt=i64)
+        self.x = z(cap * L, dm)
+        self.qk = z(cap * L, 2 * dm)
+        self.mask = z(cap, L, dt=u8)
+        self.xbar = z(cap, n_head * dm)
+        self.att = z(cap, dm)
+        self.o = z(cap, dm)
+        self.h_left, self.hid, self.h_right = z(cap, d), z(cap, d), z(cap, d)
+        self.prev_ts = z(cap)
+        self.tmin = z(1, dt=f64)
+
+    def set_weights(self, W, prefix: str = 'restarter_fn.'):
+        g = lambda k: W[prefix + k].detach().to(self.x.device, f32).contiguous()
+        self.time_w, self.time_b = g('time_encoder.basis_freq'), g('time_encoder.phase')
+        self.anony_emb = g('anony_emb.weight')
+        self.in_w, self.in_b = g('mha_fn.in_proj_weight'), g('mha_fn.in_proj_bias')
+        self.out_w, self.out_b = g('mha_fn.out_proj.weight'), g('mha_fn.out_proj.bias')
+        self.fn_w, self.fn_b = g('out_fn.weight'), g('out_fn.bias')
+        self.fc1_w, self.fc1_b = g('merger.fc1.weight'), g('merger.fc1.bias')
+        self.fc2_w, self.fc2_b = g('merger.fc2.weight'), g('merger.fc2.bias')
+
+    def history(self, csr: DeviceCSR, nids: Tensor, q_ts: Tensor, n: int, *, ts_period: int = 0,
+                count: Optional[Tensor] = None):
+        """get_history (graph.py:150-155) + anonymized_reindex (utils.py:19-27) for n (or *count) nodes."""
+        find_recent(csr, nids[:n], q_ts, self.L, ts_period=ts_period, count=count,
+                    out=(self.hist_nids[:n], self.hist_eids[:n], self.hist_ts[:n], self.hist_dirs[:n]))
+        anonymized_reindex(self.hist_nids[:n], out=self.anony[:n], count=count)
+
+    def forward(self, nids: Tensor, n: int, nfeats: Optional[Tensor], efeats: Optional[Tensor], *,
+                count: Optional[Tensor] = None, hist=None):
+        """Returns views (h_left [n,d], h_right [n,d], prev_ts [n]) of the workspace.  `hist` =
+        (hist_nids, hist_eids, hist_ts, hist_dirs, anonymized_ids) overrides the internal buffers."""
+        L, dm, d, H = self.L, self.dm, self.d, self.H
+        hd = dm // H
+        hn, he, ht, hdirs, an = hist if hist is not None else (self.hist_nids, self.hist_eids, self.hist_ts,
+                                                               self.hist_dirs, self.anony)
+        call('tiger_seq_tokens', ptr(nids), ptr(count), n, L, ptr(hn), ptr(he), ptr(ht), ptr(hdirs), ptr(an),
+             ptr(nfeats), ptr(efeats), d, self.de, ptr(self.anony_emb), ptr(self.time_w), ptr(self.time_b),
+             ptr(self.x), ptr(self.mask), ptr(self.prev_ts))
+        sgemm_nt(self.x, self.in_w[:2 * dm], self.in_b[:2 * dm], self.qk, m_rows=n * L, count=count,
+                 rows_per_count=L)
+        call('tiger_seq_attn_pool', ptr(self.qk), self.qk.stride(0), ptr(self.x), ptr(self.mask), ptr(count), n, L,
+             dm, H, ptr(self.xbar))
+        for h in range(H):
+            rows = slice(2 * dm + h * hd, 2 * dm + (h + 1) * hd)
+            sgemm_nt(self.xbar[:, h * dm:(h + 1) * dm], self.in_w[rows], self.in_b[rows],
+                     self.att[:, h * hd:(h + 1) * hd], m_rows=n, count=count)
+        sgemm_nt(self.att, self.out_w, self.out_b, self.o, m_rows=n, relu=True, count=count)
+        sgemm_nt(self.o, self.fn_w, self.fn_b, self.h_left, m_rows=n, count=count)
+        sgemm_nt(self.h_left, self.fc1_w, self.fc1_b, self.hid, m_rows=n, k_dim=d, relu=True, count=count)
+        sgemm_nt(self.hid, self.fc2_w, self.fc2_b, self.h_right, m_rows=n, count=count)
+        return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
+
+    LAUNCHES = 5 + 7   # min_time, find_recent, reindex, tokens, pool + 7 GEMMs
