@@ -148,6 +148,16 @@ int tiger_store_messages(const int64_t* src, const int64_t* dst, const int64_t* 
                          const float* time_w, const float* time_b, float* msg_vals, float* msg_ts,
                          uint8_t* has_msg, uint32_t* err_flags, void* stream);
 
+/* Same operator with the argument list of MessageStoreNoGradLastOnly.store_events (memory.py:77-81):
+ * src_vals / dst_vals [batch, d] and src_prev_ts / dst_prev_ts [batch] are the copies Memory.get
+ * returned for the events' endpoints. */
+int tiger_store_messages_dense(const int64_t* src, const int64_t* dst, const int64_t* eids, const float* ts,
+                               int64_t batch, const uint8_t* winner, const float* src_vals,
+                               const float* dst_vals, const float* src_prev_ts, const float* dst_prev_ts,
+                               const float* nfeats, const float* efeats, int d, int de, const float* time_w,
+                               const float* time_b, float* msg_vals, float* msg_ts, uint8_t* has_msg,
+                               uint32_t* err_flags, void* stream);
+
 /* a17 TIGE.contrast_learning step 4 (tiger.py:230-241,396-406): for selected positions whose
  * node has a pending message: right_vals[u] = h_new[gru_row[u]], right_ts[u] = msg_ts[u],
  * has_msg[u] = 0.  a19: when hprev_left/right are non-NULL also copies left_vals[pos] (before

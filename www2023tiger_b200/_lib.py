@@ -29,6 +29,7 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_scatter_rows': 'plplp' + 'ppp' + 'pip' + 'p',
     'tiger_time_encode': 'plppip' + 'p',
     'tiger_store_messages': 'ppppl' + 'ppp' + 'ppii' + 'pppp' + 'pp' + 'p',
+    'tiger_store_messages_dense': 'ppppl' + 'p' + 'pppp' + 'ppii' + 'pppp' + 'pp' + 'p',
     'tiger_right_writeback': 'plp' + 'ppi' + 'pppp' + 'pppp' + 'p' + 'p',
     'tiger_left_writeback': 'pllp' + 'pip' + 'ppp' + 'p' + 'p',
     'tiger_transpose_pad': 'plllpll' + 'p',

@@ -83,22 +83,34 @@ extern "C" int tiger_time_encode(const float* ts, int64_t n, const float* w, con
 
 // ---------------------------------------------------------------- a9 store_events
 // one warp per position p of pos = [src ; dst]; only selected positions build and write a row.
+// Table mode: memory rows / update_ts are read from the node-indexed tables (fused engine).
+// Dense mode: they are the per-event copies Memory.get returned (class surface, memory.py:77-106).
+struct StoreSrc {
+  const float* mem_vals;   // [N, d]   table mode
+  const float* mem_ts;     // [N]
+  const float* src_vals;   // [B, d]   dense mode
+  const float* dst_vals;   // [B, d]
+  const float* src_prev;   // [B]
+  const float* dst_prev;   // [B]
+  int dense;
+};
+
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 store_messages_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                       const int64_t* __restrict__ eids, const float* __restrict__ ts, int64_t batch,
-                      const uint8_t* __restrict__ winner, const float* __restrict__ mem_vals,
-                      const float* __restrict__ mem_ts, const float* __restrict__ nfeats,
+                      const uint8_t* __restrict__ winner, const StoreSrc in, const float* __restrict__ nfeats,
                       const float* __restrict__ efeats, int d, int de, const float* __restrict__ time_w,
                       const float* __restrict__ time_b, float* __restrict__ msg_vals, float* __restrict__ msg_ts,
                       uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags) {
   const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
   if (p >= 2 * batch) return;
   const int lane = lane_id();
-  const int64_t e = p < batch ? p : p - batch;
-  const int64_t self = p < batch ? src[e] : dst[e];
-  const int64_t other = p < batch ? dst[e] : src[e];
+  const bool is_src = p < batch;
+  const int64_t e = is_src ? p : p - batch;
+  const int64_t self = is_src ? src[e] : dst[e];
+  const int64_t other = is_src ? dst[e] : src[e];
   const float t = ts[e];
-  const float prev = mem_ts[self];
+  const float prev = in.dense ? (is_src ? in.src_prev[e] : in.dst_prev[e]) : in.mem_ts[self];
   if (lane == 0 && err_flags != nullptr) {
     if (prev > t) atomicOr(err_flags, TIGER_ERR_EVENT_BEFORE_MEM);   // tiger.py:436-438
     if (has_msg[self] != 0) atomicOr(err_flags, TIGER_ERR_UNUSED_MSG);  // memory.py:85-87
@@ -106,8 +118,10 @@ store_messages_kernel(const int64_t* __restrict__ src, const int64_t* __restrict
   if (!winner[p]) return;
   const int64_t m_dim = 3 * (int64_t)d + de;
   float* row = msg_vals + self * m_dim;
-  warp_add_row(row, mem_vals + self * d, nfeats ? nfeats + self * d : nullptr, d, lane);
-  warp_add_row(row + d, mem_vals + other * d, nfeats ? nfeats + other * d : nullptr, d, lane);
+  const float* self_row = in.dense ? (is_src ? in.src_vals : in.dst_vals) + e * d : in.mem_vals + self * d;
+  const float* other_row = in.dense ? (is_src ? in.dst_vals : in.src_vals) + e * d : in.mem_vals + other * d;
+  warp_add_row(row, self_row, nfeats ? nfeats + self * d : nullptr, d, lane);
+  warp_add_row(row + d, other_row, nfeats ? nfeats + other * d : nullptr, d, lane);
   if (efeats != nullptr) {
     warp_copy_row(row + 2 * d, efeats + eids[e] * de, de, lane);
   } else {
@@ -129,20 +143,40 @@ __global__ void raise_has_msg_kernel(const int64_t* __restrict__ src, const int6
   has_msg[p < batch ? src[p] : dst[p - batch]] = 1;
 }
 
+static int launch_store(const int64_t* src, const int64_t* dst, const int64_t* eids, const float* ts, int64_t batch,
+                        const uint8_t* winner, const StoreSrc& in, const float* nfeats, const float* efeats, int d,
+                        int de, const float* time_w, const float* time_b, float* msg_vals, float* msg_ts,
+                        uint8_t* has_msg, uint32_t* err_flags, void* stream) {
+  if (batch < 0 || d <= 0 || de <= 0) return TIGER_EINVAL;
+  if (batch == 0) return TIGER_OK;
+  const int64_t n = 2 * batch;
+  store_messages_kernel<<<(unsigned)((n + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      src, dst, eids, ts, batch, winner, in, nfeats, efeats, d, de, time_w, time_b, msg_vals, msg_ts, has_msg,
+      err_flags);
+  raise_has_msg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, batch, winner,
+                                                                                  has_msg);
+  return tiger_launch_status();
+}
+
 extern "C" int tiger_store_messages(const int64_t* src, const int64_t* dst, const int64_t* eids, const float* ts,
                                     int64_t batch, const uint8_t* winner, const float* mem_vals,
                                     const float* mem_ts, const float* nfeats, const float* efeats, int d, int de,
                                     const float* time_w, const float* time_b, float* msg_vals, float* msg_ts,
                                     uint8_t* has_msg, uint32_t* err_flags, void* stream) {
-  if (batch < 0 || d <= 0 || de <= 0) return TIGER_EINVAL;
-  if (batch == 0) return TIGER_OK;
-  const int64_t n = 2 * batch;
-  store_messages_kernel<<<(unsigned)((n + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      src, dst, eids, ts, batch, winner, mem_vals, mem_ts, nfeats, efeats, d, de, time_w, time_b, msg_vals,
-      msg_ts, has_msg, err_flags);
-  raise_has_msg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, dst, batch, winner,
-                                                                                  has_msg);
-  return tiger_launch_status();
+  StoreSrc in = {mem_vals, mem_ts, nullptr, nullptr, nullptr, nullptr, 0};
+  return launch_store(src, dst, eids, ts, batch, winner, in, nfeats, efeats, d, de, time_w, time_b, msg_vals,
+                      msg_ts, has_msg, err_flags, stream);
+}
+
+extern "C" int tiger_store_messages_dense(const int64_t* src, const int64_t* dst, const int64_t* eids,
+                                          const float* ts, int64_t batch, const uint8_t* winner,
+                                          const float* src_vals, const float* dst_vals, const float* src_prev_ts,
+                                          const float* dst_prev_ts, const float* nfeats, const float* efeats, int d,
+                                          int de, const float* time_w, const float* time_b, float* msg_vals,
+                                          float* msg_ts, uint8_t* has_msg, uint32_t* err_flags, void* stream) {
+  StoreSrc in = {nullptr, nullptr, src_vals, dst_vals, src_prev_ts, dst_prev_ts, 1};
+  return launch_store(src, dst, eids, ts, batch, winner, in, nfeats, efeats, d, de, time_w, time_b, msg_vals,
+                      msg_ts, has_msg, err_flags, stream);
 }
 
 // ---------------------------------------------------------------- a17 right write-back (+ a19)

@@ -448,3 +448,11 @@ class SeqRestarterOp:
         return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
 
     LAUNCHES = 5 + 7   # min_time, find_recent, reindex, tokens, pool + 7 GEMMs
+
+
+def store_messages_dense(src, dst, eids, ts, winner, src_vals, dst_vals, src_prev_ts, dst_prev_ts, nfeats, efeats,
+                         d, de, time_w, time_b, msg_vals, msg_ts, has_msg, err_flags=None):
+    """MessageStoreNoGradLastOnly.store_events argument list (memory.py:77-81)."""
+    call('tiger_store_messages_dense', ptr(src), ptr(dst), ptr(eids), ptr(ts), src.numel(), ptr(winner),
+         ptr(src_vals), ptr(dst_vals), ptr(src_prev_ts), ptr(dst_prev_ts), ptr(nfeats), ptr(efeats), d, de,
+         ptr(time_w), ptr(time_b), ptr(msg_vals), ptr(msg_ts), ptr(has_msg), ptr(err_flags))

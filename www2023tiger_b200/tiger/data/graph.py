@@ -1,0 +1,100 @@
+"""Temporal graph: per-node time-sorted CSR resident in HBM + the most-recent-K neighbor finder.
+
+Mirrors the reference's `tiger.data.graph.Graph` surface (tiger/data/graph.py:10-155): same
+constructor / `from_data` keywords, `num_node`, `sample_temporal_neighbor`, `get_history`
+(numpy in, numpy out, dtypes int64 / int64 / float32 / int64).  The per-node Python lists and the
+Python loop over queries are replaced by `tiger_csr_build` and `tiger_find_recent`.
+Only the default `recent_edges` strategy is implemented.
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from www2023tiger_b200 import ops
+
+
+def _device(device=None) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise ops._lib.TigerLibraryError('tiger.data.graph.Graph needs a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class Graph:
+    def __init__(self, adj_list, strategy='recent_nodes', seed=None, alpha=0.0, device=None):
+        """adj_list[n] = list of (neighbor, eid, ts, flag) of node n, as data2adjlist builds it
+        (graph.py:226-241).  The per-node stable sort by time (graph.py:30-36) runs on the device."""
+        self.strategy = strategy
+        self.seed = seed
+        self.alpha = alpha
+        self.num_node = len(adj_list)
+        dev = _device(device)
+        lens = np.fromiter((len(e) for e in adj_list), dtype=np.int64, count=len(adj_list))
+        total = int(lens.sum())
+        flat = np.zeros((total, 4), dtype=np.float64)
+        pos = 0
+        for edges in adj_list:
+            if edges:
+                flat[pos:pos + len(edges)] = np.asarray(edges, dtype=np.float64)
+                pos += len(edges)
+        owner = torch.from_numpy(np.repeat(np.arange(len(adj_list)), lens)).to(dev)
+        ts = torch.from_numpy(np.ascontiguousarray(flat[:, 2])).to(dev)
+        order = torch.sort(ts, stable=True).indices
+        order = order[torch.sort(owner[order], stable=True).indices]
+        indptr = torch.zeros(self.num_node + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(torch.from_numpy(lens).to(dev), 0)
+        col = lambda j, dt: torch.from_numpy(np.ascontiguousarray(flat[:, j])).to(dev)[order].to(dt).contiguous()
+        self.csr = ops.DeviceCSR(indptr, col(0, torch.int32), col(1, torch.int32), ts[order].contiguous(),
+                                 col(3, torch.uint8))
+
+    @classmethod
+    def from_data(cls, data, strategy='recent_nodes', seed=None, max_node_id=None, device=None):
+        """Build straight from the interaction stream (reference: data2adjlist + Graph.__init__)."""
+        self = cls.__new__(cls)
+        self.strategy, self.seed, self.alpha = strategy, seed, 0.0
+        dev = _device(device)
+        src = torch.as_tensor(np.asarray(data.src), dtype=torch.int64)
+        dst = torch.as_tensor(np.asarray(data.dst), dtype=torch.int64)
+        ts = torch.as_tensor(np.asarray(data.ts), dtype=torch.float64)
+        eids = torch.as_tensor(np.asarray(data.eids), dtype=torch.int64)
+        if max_node_id is None:
+            max_node_id = int(max(src.max(), dst.max())) if len(src) else 0     # graph.py:231-232
+        self.num_node = max_node_id + 1
+        src, dst, ts, eids = (x.to(dev) for x in (src, dst, ts, eids))
+        if len(ts) > 1 and not bool((ts[1:] >= ts[:-1]).all()):
+            order = torch.sort(ts, stable=True).indices           # csr_build needs a time-ordered stream
+            src, dst, ts, eids = (x[order].contiguous() for x in (src, dst, ts, eids))
+        self.csr = ops.csr_build(src, dst, ts, eids, self.num_node)
+        return self
+
+    @property
+    def device(self) -> torch.device:
+        return self.csr.device
+
+    # ------------------------------------------------------------------ device-level API
+    def find_recent_device(self, nids: torch.Tensor, ts: torch.Tensor, n_neighbors: int, **kw):
+        """(nids int64 [n], ts float64 [m], query i uses ts[i % m]) -> device tensors
+        (neigh int64, eids int64, ts float32, dirs int64), each [n, n_neighbors]."""
+        return ops.find_recent(self.csr, nids, ts, n_neighbors, **kw)
+
+    # ------------------------------------------------------------------ reference API (numpy)
+    def sample_temporal_neighbor(self, nids: np.ndarray, ts: np.ndarray, n_neighbors: int = 20,
+                                 strategy: Optional[str] = None
+                                 ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        strategy = self.strategy if strategy is None else strategy
+        if strategy != 'recent_edges':
+            raise NotImplementedError(f"strategy '{strategy}': only 'recent_edges' is implemented on the device")
+        assert len(nids) == len(ts)                                # graph.py:87
+        dev = self.device
+        q_n = torch.as_tensor(np.ascontiguousarray(nids), dtype=torch.int64).to(dev)
+        q_t = torch.as_tensor(np.ascontiguousarray(ts)).to(torch.float64).to(dev)   # float32 queries widen exactly
+        if len(nids) == 0:
+            z = np.zeros((0, n_neighbors))
+            return z.astype(np.int64), z.astype(np.int64), z.astype(np.float32), z.astype(np.int64)
+        out = ops.find_recent(self.csr, q_n, q_t, n_neighbors)
+        return tuple(x.cpu().numpy() for x in out)
+
+    def get_history(self, nids: np.ndarray, ts: np.ndarray, hist_len: int):
+        return self.sample_temporal_neighbor(nids, ts, n_neighbors=hist_len, strategy='recent_edges')

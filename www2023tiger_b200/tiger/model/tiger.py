@@ -1,0 +1,362 @@
+"""TIGE / TIGER orchestration of the per-batch temporal memory path
+(reference tiger/model/tiger.py:27-618; same constructor keywords, methods and state_dict layout).
+
+`contrast_learning` has two routes:
+* no-grad (evaluation, warm-up, `flush_msg`): the fused launch sequence of DESIGN.md §3 - compaction
+  of the pending-message set, gather+GRU, fused temporal attention, argmax-by-timestamp selection,
+  right write-back, message build+store, left write-back, link scorer - with every
+  data-dependent size kept on the device; one host poll of the error word per batch.
+* autograd (the training loops): the seven steps of the reference, differentiable operators through
+  torch ops, index / memory operators through the kernels.
+"""
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from www2023tiger_b200 import ops
+from ._native import ErrFlags, f32c, use_kernel
+from .basic_modules import MergeLayer
+from .feature_getter import FeatureGetter
+from .memory import Memory, MessageStoreNoGradLastOnly
+from .message_modules import (IdentityMessageFunction, LastMessageAggregatorNoGradLastOnly, LinearMessageFunction,
+                              MLPMessageFunction)
+from .restarters import Restarter
+from .temporal_agg_modules import GraphAttnEmbedding
+from .time_encoding import TimeEncode
+from .update_modules import GRUUpdater, MergeUpdater
+from .utils import select_latest_nids
+
+
+class _Workspace:
+    """Per-batch device scratch of the fused route (sized for batch B, K neighbors)."""
+
+    def __init__(self, n_nodes, d, B, K, dev):
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        self.B, self.K = B, K
+        self.cap = 3 * B * (K + 1)
+        self.bitmap = z(ops.bitmap_words(n_nodes), dt=torch.int32)
+        self.involved, self.outdated = z(self.cap, dt=torch.int64), z(self.cap, dt=torch.int64)
+        self.gru_row = torch.full((n_nodes,), -1, dtype=torch.int32, device=dev)
+        self.counts = z(4, dt=torch.int32)
+        self.h_new = z(self.cap, d)
+        self.winner = z(2 * B, dt=torch.uint8)
+        self.sel_count = z(1, dt=torch.int32)
+
+
+class TIGE(nn.Module):
+    def __init__(self, *, raw_feat_getter: FeatureGetter, graph, n_neighbors: int = 20, n_layers: int = 2,
+                 n_head: int = 2, dropout: float = 0.1, msg_src: str, upd_src: str, msg_tsfm_type: str = 'id',
+                 mem_update_type: str = 'gru', tgn_mode: bool = True, msg_last_only: bool = True,
+                 hit_type: str = 'none'):
+        super().__init__()
+        self.raw_feat_getter = raw_feat_getter
+        self.n_nodes = raw_feat_getter.n_nodes
+        self.nfeat_dim = raw_feat_getter.nfeat_dim
+        self.efeat_dim = raw_feat_getter.efeat_dim
+        self.time_encoder = TimeEncode(dim=self.nfeat_dim)
+        self.tfeat_dim = self.time_encoder.dim
+        self.memory_dim = self.nfeat_dim
+        self.raw_msg_dim = self.memory_dim * 2 + self.efeat_dim + self.tfeat_dim
+        self.n_neighbors, self.n_layers = n_neighbors, n_layers
+        self.msg_src, self.upd_src = msg_src, upd_src
+        if not msg_last_only:
+            raise NotImplementedError('only msg_last_only=True (the reference CLI default) is implemented')
+        self.tgn_mode, self.msg_last_only = True, True
+        self.left_memory = Memory(self.n_nodes, self.memory_dim)
+        self.right_memory = Memory(self.n_nodes, self.memory_dim)
+        self.msg_store = MessageStoreNoGradLastOnly(self.n_nodes, dim=self.raw_msg_dim)
+        self._bind_sources()
+        self.msg_aggregate_fn = LastMessageAggregatorNoGradLastOnly(raw_feat_getter=raw_feat_getter,
+                                                                    time_encoder=self.time_encoder)
+        tsfm = {'id': IdentityMessageFunction, 'linear': LinearMessageFunction, 'mlp': MLPMessageFunction}
+        if msg_tsfm_type not in tsfm:
+            raise NotImplementedError
+        self.msg_transform_fn = tsfm[msg_tsfm_type](raw_msg_dim=self.raw_msg_dim)
+        self.msg_dim = self.msg_transform_fn.output_size
+        upd = {'gru': GRUUpdater, 'merge': MergeUpdater}
+        if mem_update_type not in upd:
+            raise NotImplementedError
+        self.right_mem_updater = upd[mem_update_type](self.msg_dim, self.memory_dim)
+        self.temporal_embedding_fn = GraphAttnEmbedding(raw_feat_getter=raw_feat_getter,
+                                                        time_encoder=self.time_encoder, graph=graph,
+                                                        n_neighbors=n_neighbors, n_layers=n_layers, n_head=n_head,
+                                                        dropout=dropout)
+        self.hit_type = hit_type
+        merge_dim = self.nfeat_dim
+        if hit_type == 'vec':
+            merge_dim = self.nfeat_dim + n_neighbors
+        elif hit_type == 'bin':
+            self.hit_embedding = nn.Embedding(2, self.nfeat_dim)
+        elif hit_type == 'count':
+            self.hit_embedding = nn.Embedding(n_neighbors + 1, self.nfeat_dim)
+        self.score_fn = MergeLayer(merge_dim, merge_dim, self.nfeat_dim, 1, dropout=dropout)
+        self.contrast_loss_fn = nn.BCEWithLogitsLoss()
+        if msg_src not in {'left', 'right'}:
+            raise ValueError(f'Invalid msg_src={msg_src}')
+        if upd_src not in {'left', 'right'}:
+            raise ValueError(f'Invalid upd_src={upd_src}')
+        self._err = ErrFlags()
+        self._ws: Optional[_Workspace] = None
+        self._score_pack, self._score_key = None, None
+
+    def _bind_sources(self):
+        self.msg_memory = self.left_memory if self.msg_src == 'left' else self.right_memory
+        self.upd_memory = self.left_memory if self.upd_src == 'left' else self.right_memory
+
+    @property
+    def graph(self):
+        return self.temporal_embedding_fn.graph
+
+    @graph.setter
+    def graph(self, new_obj):
+        self.temporal_embedding_fn.graph = new_obj
+
+    @property
+    def device(self):
+        return self.msg_memory.device
+
+    # ------------------------------------------------------------------ fused no-grad route
+    def _fusable(self) -> bool:
+        return (isinstance(self.msg_transform_fn, IdentityMessageFunction)
+                and isinstance(self.right_mem_updater, GRUUpdater) and self.n_layers == 1
+                and self.hit_type in ('bin', 'none') and self.left_memory.vals.is_cuda)
+
+    def _workspace(self, B: int, K: int) -> _Workspace:
+        dev = self.device
+        ws = self._ws
+        if ws is None or ws.B < B or ws.K != K or ws.bitmap.device != dev:
+            ws = self._ws = _Workspace(self.n_nodes, self.memory_dim, B, K, dev)
+        return ws
+
+    def _scorer(self) -> ops.ScorePack:
+        s = self.score_fn
+        params = [s.fc1.weight, s.fc1.bias, s.fc2.weight, s.fc2.bias]
+        if self.hit_type == 'bin':
+            params.append(self.hit_embedding.weight)
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._score_pack is None or key != self._score_key:
+            if self._score_pack is None or self._score_pack.fc1T.device != params[0].device:
+                self._score_pack = ops.ScorePack(self.nfeat_dim, params[0].device)
+            args = [f32c(p) for p in params] + ([None] if self.hit_type != 'bin' else [])
+            self._score_pack.refresh(*args)
+            self._score_key = key
+        return self._score_pack
+
+    def _contrast_learning_fused(self, src_ids, dst_ids, neg_dst_ids, ts, eids, cg):
+        B, d, N = len(src_ids), self.memory_dim, self.n_nodes
+        nn_, ne_, nt_ = cg.layers[1]
+        ws = self._workspace(B, nn_.shape[1])
+        dev = self.device
+        err = self._err.get(dev)
+        left, right, store = self.left_memory, self.right_memory, self.msg_store
+        batch_nids = torch.cat([src_ids, dst_ids, neg_dst_ids]).contiguous()
+        pos = batch_nids[:2 * B]
+        ts = f32c(ts)
+        fg = self.raw_feat_getter
+        # steps 1-2: pending-message set of the involved nodes, gather + GRU (tiger.py:206-221)
+        ops.mark_nodes(cg.computation_graph_nodes.contiguous(), ws.bitmap, N)
+        ops.compact_involved(ws.bitmap, N, ws.involved, ws.counts, has_msg=store.has_msg, outdated=ws.outdated,
+                             gru_row=ws.gru_row, err_flags=err)
+        ops.gru_update(self.right_mem_updater.packed(), node_ids=ws.outdated, x_table=store.node_msg_vals,
+                       h_table=self.upd_memory.vals, n_rows=ws.cap, out=ws.h_new, count=ws.counts[1:],
+                       msg_ts=store.node_msg_ts, check_mem_ts=self.msg_memory.update_ts,
+                       check_equal=(self.msg_src == 'left'), err_flags=err)
+        # step 3: temporal attention over the sampled neighbors (tiger.py:225-227)
+        fn = self.temporal_embedding_fn.fns[0]
+        emb = ops.temporal_attention(fn.packed(self.time_encoder), fn.n_head, batch_nids, ts, nn_, ne_, nt_,
+                                     rows_a=right.vals, rows_b=ws.h_new, sel=ws.gru_row, nfeats=fg.nfeats,
+                                     efeats=fg.efeats)
+        # steps 4-6 (tiger.py:230-255)
+        winner = ws.winner[:2 * B]
+        ops.select_latest(pos, ts, want_unique=False, winner=winner, count=ws.sel_count)
+        h_prev_left = torch.empty(2 * B, d, device=dev)
+        h_prev_right = torch.empty(2 * B, d, device=dev)
+        ops.right_writeback(pos, winner, ws.gru_row, ws.h_new, d, right.vals, right.update_ts, right.active_mask,
+                            store.node_msg_ts, store.has_msg, left.vals, h_prev_left, h_prev_right, err)
+        ops.store_messages(batch_nids[:B], batch_nids[B:2 * B], eids.contiguous(), ts, winner, self.msg_memory.vals,
+                           self.msg_memory.update_ts, fg.nfeats, fg.efeats, d, self.efeat_dim,
+                           f32c(self.time_encoder.basis_freq), f32c(self.time_encoder.phase), store.node_msg_vals,
+                           store.node_msg_ts, store.has_msg, err)
+        ops.left_writeback(pos, B, winner, emb, d, ts, left.vals, left.update_ts, left.active_mask, err)
+        # step 7 (tiger.py:259-288)
+        scores, loss = ops.link_score(self._scorer(), emb, batch_nids[:B], batch_nids[B:2 * B], batch_nids[2 * B:],
+                                      nn_ if self.hit_type == 'bin' else None)
+        self._err.check()
+        return loss[0], emb[:2 * B], scores[:B], scores[B:], h_prev_left, h_prev_right
+
+    # ------------------------------------------------------------------ the reference's step-by-step route
+    def contrast_learning(self, src_ids: Tensor, dst_ids: Tensor, neg_dst_ids: Tensor, ts: Tensor, eids: Tensor,
+                          computation_graph) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+        """-> (contrast_loss, h_left [2B,d], pos_scores [B], neg_scores [B], h_prev_left, h_prev_right)."""
+        cg = computation_graph
+        if use_kernel() and self._fusable():
+            return self._contrast_learning_fused(src_ids, dst_ids, neg_dst_ids, ts, eids, cg)
+        bs = len(src_ids)
+        pos_ids = torch.cat([src_ids, dst_ids])
+        batch_ids = torch.cat([src_ids, dst_ids, neg_dst_ids])
+        # steps 1-2: h(t'+) of involved nodes with a pending message, overlaid on the right-memory rows
+        outdated, msgs, msg_ts = self.compute_messages(cg.np_computation_graph_nodes)
+        involved = cg.computation_graph_nodes
+        reprs = self.right_memory.vals[involved].clone()
+        h_new = None
+        if len(outdated):
+            h_new = self.apply_messages(outdated, msgs, msg_ts)
+            reprs = reprs.index_copy(0, cg.local_index[outdated], h_new)
+        # step 3
+        h_all = self.compute_temporal_embedding_with_involved_nodes_only(reprs, batch_ids, ts.repeat(3), cg)
+        # step 4: persist h(t'+) of the outdated positives, consume their messages
+        if len(outdated):
+            uniq_pos, _ = select_latest_nids(pos_ids, ts.repeat(2))
+            row_of = torch.full((self.n_nodes,), -1, dtype=torch.long, device=outdated.device)
+            row_of[outdated] = torch.arange(len(outdated), device=outdated.device)
+            rows = row_of[uniq_pos]
+            hit = rows >= 0
+            if bool(hit.any()):
+                ids, rows = uniq_pos[hit], rows[hit]
+                self.msg_store.clear(ids)
+                self.update_right_memory(ids, h_new.detach()[rows], msg_ts[rows])
+        # step 5, restarter targets, step 6
+        self.store_events(src_ids, dst_ids, ts, eids)
+        h_prev_left = self.left_memory.get(pos_ids)[0].clone()
+        h_prev_right = self.right_memory.get(pos_ids)[0].clone()
+        h_left = h_all[:2 * bs]
+        self.update_left_memory(pos_ids, h_left, ts.repeat(2))
+        # step 7
+        x, y, neg_y = h_all.reshape(3, bs, self.nfeat_dim)
+        src_hit, dst_hit, neg_src_hit, neg_dst_hit = cg.hit_data
+        if self.hit_type == 'vec':
+            xp, yp = torch.cat([x, src_hit], 1), torch.cat([y, dst_hit], 1)
+            xn, yn = torch.cat([x, neg_src_hit], 1), torch.cat([neg_y, neg_dst_hit], 1)
+        elif self.hit_type in ('bin', 'count'):
+            code = (lambda h: h.max(1).values.long()) if self.hit_type == 'bin' else (lambda h: h.sum(1).long())
+            xp, yp = x + self.hit_embedding(code(src_hit)), y + self.hit_embedding(code(dst_hit))
+            xn, yn = x + self.hit_embedding(code(neg_src_hit)), neg_y + self.hit_embedding(code(neg_dst_hit))
+        else:
+            xp = xn = x
+            yp, yn = y, neg_y
+        pos_scores = self.score_fn(xp, yp).squeeze(1)
+        neg_scores = self.score_fn(xn, yn).squeeze(1)
+        labels = torch.cat([torch.ones_like(pos_scores), torch.zeros_like(neg_scores)])
+        loss = self.contrast_loss_fn(torch.cat([pos_scores, neg_scores]), labels)
+        return loss, h_left, pos_scores, neg_scores, h_prev_left, h_prev_right
+
+    def compute_messages(self, node_ids: Union[Tensor, np.ndarray, None] = None
+                         ) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
+        """-> (outdated ids, transformed pending messages, their timestamps); a subset of node_ids."""
+        outdated = self.msg_store.get_outdated_node_ids(node_ids).to(self.device)
+        if len(outdated) == 0:
+            return outdated, None, None
+        last_update_ts = self.msg_memory.update_ts[outdated]
+        raw_msgs, ts = self.msg_aggregate_fn(outdated, last_update_ts, self.msg_store.node_messages)
+        if self.msg_src == 'left' and not bool((ts == last_update_ts).all()):
+            raise ValueError("Messages' ts should be equal to last update ts "
+                             "when using left memory as msg source.")
+        return outdated, self.msg_transform_fn(raw_msgs.detach()), ts
+
+    def apply_messages(self, node_ids: Tensor, msgs: Tensor, ts: Tensor) -> Tensor:
+        old_vals, last_update_ts = self.upd_memory.get(node_ids)
+        return self.right_mem_updater(old_vals, msgs, ts - last_update_ts)
+
+    def compute_temporal_embedding_with_involved_nodes_only(self, involved_node_reprs: Tensor, node_ids: Tensor,
+                                                            ts: Tensor, computation_graph) -> Tensor:
+        return self.temporal_embedding_fn.compute_embedding_with_computation_graph(
+            involved_node_reprs, node_ids, ts, computation_graph)
+
+    def temporal_embedding(self, memory, node_ids, ts):
+        raise NotImplementedError('deprecated in the reference (tiger.py:377-394); use '
+                                  'compute_temporal_embedding_with_involved_nodes_only')
+
+    @torch.no_grad()
+    def update_right_memory(self, node_ids: Tensor, new_vals: Tensor, ts: Tensor):
+        self.right_memory.set(node_ids, new_vals, ts)
+
+    @torch.no_grad()
+    def update_left_memory(self, node_ids: Tensor, new_vals: Tensor, ts: Tensor):
+        node_ids, index = select_latest_nids(node_ids, ts)
+        self.left_memory.set(node_ids, new_vals[index], ts[index])
+
+    @torch.no_grad()
+    def store_events(self, src_ids: Tensor, dst_ids: Tensor, ts: Tensor, eids: Tensor):
+        src_vals, src_prev_ts = self.msg_memory.get(src_ids)
+        dst_vals, dst_prev_ts = self.msg_memory.get(dst_ids)
+        if bool((src_prev_ts > ts).any()) or bool((dst_prev_ts > ts).any()):
+            raise ValueError('Events occur before the udpated memory.')
+        self.msg_store.store_events(src_ids, dst_ids, src_prev_ts, dst_prev_ts, src_vals, dst_vals, eids, ts,
+                                    self.raw_feat_getter, self.time_encoder)
+
+    @torch.no_grad()
+    def flush_msg(self):
+        """Consume every pending message into the right memory (call before saving the model)."""
+        outdated, msgs, prev_ts = self.compute_messages()
+        if len(outdated):
+            self.update_right_memory(outdated, self.apply_messages(outdated, msgs, prev_ts), prev_ts)
+            self.msg_store.clear(outdated)
+
+    def reset(self):
+        self.left_memory.clear()
+        self.right_memory.clear()
+        self.msg_store.clear()
+
+    def save_memory_state(self):
+        return self.left_memory.clone(), self.right_memory.clone(), self.msg_store.clone()
+
+    def load_memory_state(self, data):
+        self.left_memory, self.right_memory, self.msg_store = data
+        self._bind_sources()
+
+
+class TIGER(TIGE):
+    def __init__(self, *, raw_feat_getter: FeatureGetter, graph, restarter: Restarter, n_neighbors: int = 20,
+                 n_layers: int = 2, n_head: int = 2, dropout: float = 0.1, msg_src: str, upd_src: str,
+                 msg_tsfm_type: str = 'id', mem_update_type: str = 'gru', tgn_mode: bool = True,
+                 msg_last_only: bool = True, hit_type: str = 'vec'):
+        super().__init__(raw_feat_getter=raw_feat_getter, graph=graph, n_neighbors=n_neighbors, n_layers=n_layers,
+                         n_head=n_head, dropout=dropout, msg_src=msg_src, upd_src=upd_src,
+                         msg_tsfm_type=msg_tsfm_type, mem_update_type=mem_update_type, tgn_mode=tgn_mode,
+                         msg_last_only=msg_last_only, hit_type=hit_type)
+        self.restarter_fn = restarter
+        self.mutual_loss_fn = nn.MSELoss()
+
+    def forward(self, *args, **kwargs) -> Tuple[Tensor, Tensor]:
+        """DDP entry point (DDP only hooks `forward`)."""
+        return self.contrast_and_mutual_learning(*args, **kwargs)
+
+    def contrast_and_mutual_learning(self, src_ids: Tensor, dst_ids: Tensor, neg_dst_ids: Tensor, ts: Tensor,
+                                     eids: Tensor, computation_graph, contrast_only: bool = False
+                                     ) -> Tuple[Tensor, Tensor]:
+        contrast_loss, *_, h_prev_left, h_prev_right = self.contrast_learning(
+            src_ids, dst_ids, neg_dst_ids, ts, eids, computation_graph)
+        if contrast_only:
+            return contrast_loss, torch.tensor(0, device=contrast_loss.device)
+        index = computation_graph.restart_data.index
+        nids = torch.cat([src_ids, dst_ids])[index]
+        s_left, s_right, _ = self.restarter_fn(nids, ts.repeat(2)[index], computation_graph)
+        targets = torch.cat([h_prev_left[index], h_prev_right[index]], 0)
+        preds = torch.cat([s_left, s_right], 0)
+        valid = torch.where(~(targets == 0).all(1))[0]        # never-written memory rows carry no signal
+        if len(valid):
+            return contrast_loss, self.mutual_loss_fn(preds[valid], targets[valid].detach())
+        return contrast_loss, torch.tensor(0, device=contrast_loss.device)
+
+    @torch.no_grad()
+    def restart(self, nids: Tensor, ts: Tensor, mix: float = 0.):
+        """Overwrite both memories of `nids` with the restarter's surrogate states (history cut at ts)."""
+        if len(nids):
+            self.msg_store.clear(nids)
+            h_left, h_right, prev_ts = self.restarter_fn(nids, ts)
+            if mix > 0:
+                h_left = mix * h_left + (1 - mix) * self.left_memory.vals[nids]
+                h_right = mix * h_right + (1 - mix) * self.right_memory.vals[nids]
+            self.left_memory.set(nids, h_left, prev_ts, skip_check=True)
+            self.right_memory.set(nids, h_right, prev_ts, skip_check=True)
+
+    @property
+    def graph(self):
+        return self.temporal_embedding_fn.graph
+
+    @graph.setter
+    def graph(self, new_obj):
+        self.temporal_embedding_fn.graph = new_obj
+        self.restarter_fn.graph = new_obj
