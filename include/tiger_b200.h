@@ -208,30 +208,38 @@ int tiger_gru_update(const int64_t* node_ids, const int32_t* count, int64_t n_ro
                      const float* msg_ts, const float* check_mem_ts, int check_equal,
                      uint32_t* err_flags, void* stream);
 
-/* packed temporal-attention parameters (device pointers), produced by the host from
- * temporal_embedding_fn.fns.0.* with tiger_transpose_pad */
-/* E = 2d, C = 2d + de; leading dimensions are rounded up to 4 floats (ldE, ldC, ldD) and every
- * matrix starts on a 16-byte boundary, so the kernel can stream them with cp.async.bulk. */
+/* temporal-attention parameters (device pointers): the reference's tensors as stored, plus one
+ * derived pack.  E = 2d, C = 2d + de, hd = E / n_head. */
 typedef struct {
-  const float* wqT;   /* [E][ldE]   k-major q_proj_weight                     */
-  const float* wk;    /* [E][ldC]   k_proj_weight as stored (row n, col c)    */
-  const float* wvT;   /* [C][ldE]   k-major v_proj_weight                     */
-  const float* woT;   /* [E][ldE]   k-major out_proj.weight                   */
-  const float* fc1T;  /* [E+d][ldD] k-major merger.fc1.weight                 */
-  const float* fc2T;  /* [d][ldD]   k-major merger.fc2.weight                 */
-  const float* in_bias;  /* [3E] in_proj_bias (q,k,v)                         */
-  const float* out_bias; /* [E]                                                */
-  const float* fc1_b;    /* [d]                                                */
-  const float* fc2_b;    /* [d]                                                */
-  const float* time_w;   /* [d] time_encoder.basis_freq                        */
-  const float* time_b;   /* [d] time_encoder.phase                             */
+  const float* wq;       /* [E][E]    mha_fn.q_proj_weight                                  */
+  const float* wk_fold;  /* [H][Cq][hdp] folded key projection made by tiger_attn_fold_keys */
+  const float* wv;       /* [E][C]    mha_fn.v_proj_weight                                  */
+  const float* wo;       /* [E][E]    mha_fn.out_proj.weight                                */
+  const float* fc1;      /* [d][E+d]  merger.fc1.weight                                     */
+  const float* fc2;      /* [d][d]    merger.fc2.weight                                     */
+  const float* in_bias;  /* [3E] in_proj_bias (q,k,v)                                       */
+  const float* out_bias; /* [E]                                                             */
+  const float* fc1_b;    /* [d]                                                             */
+  const float* fc2_b;    /* [d]                                                             */
+  const float* time_w;   /* [d] time_encoder.basis_freq                                     */
+  const float* time_b;   /* [d] time_encoder.phase                                          */
 } tiger_attn_params;
 
+/* Folded key projection: out[h][c][j] = k_proj_weight[h*hd + j][c] for c < C, k_bias[h*hd + j] for
+ * c == C, zero elsewhere; dims [n_head][Cq = roundup4(C+1)][hdp = roundup4(hd)].  With it
+ * q_h . (Wk_h kv + bk_h) becomes (q_h [Wk_h | bk_h]) . [kv | 1]: one GEMM per batch instead of a key
+ * projection per neighbor.  Re-run whenever k_proj_weight / in_proj_bias change. */
+int tiger_attn_fold_keys(const float* k_proj_weight, const float* k_bias, int d, int de, int n_head,
+                         float* out, void* stream);
+
+/* bytes of caller-provided, 16-byte aligned workspace for n_query queries */
+int64_t tiger_temporal_attention_work_bytes(int64_t n_query, int k, int d, int de, int n_head);
+
 /* a15 + a16  GraphEmbedding.compute_embedding_with_computation_graph (n_layers=1) +
- * TemporalAttention.forward (temporal_agg_modules.py:29-83,210-235), eval mode, as ONE kernel:
- * gather (center + K neighbors + edge rows) -> time encoding -> q projection -> folded
- * single-query attention (scores through W_k^T q, values through W_v applied to the
- * softmax-pooled keys) -> out projection -> merger MLP.
+ * TemporalAttention.forward (temporal_agg_modules.py:29-83,210-235), eval mode: gather (center + K
+ * neighbors + edge rows) -> time encoding -> q projection -> folded single-query attention (scores
+ * through Wk^T q, values through Wv applied to the softmax-pooled keys) -> out projection -> merger
+ * MLP, as the launch sequence described in csrc/attention.cu.
  * Node representations: row(u) = sel[u] >= 0 ? rows_b[sel[u]] : rows_a[u]
  *   fused engine : rows_a = right memory, rows_b = GRU output, sel = gru_row
  *   class surface: rows_a = NULL, rows_b = involved_node_reprs, sel = local_index
@@ -242,7 +250,7 @@ int tiger_temporal_attention(const int64_t* center_nids, const float* q_ts, int6
                              const float* neigh_ts, int k, const float* rows_a, const float* rows_b,
                              const void* sel, int sel_is_i64, const float* nfeats,
                              const float* efeats, int d, int de, int n_head,
-                             const tiger_attn_params* params, float* out, void* stream);
+                             const tiger_attn_params* params, float* out, void* work, void* stream);
 
 /* Same operator with the dense argument list of TemporalAttention.forward
  * (temporal_agg_modules.py:210-235): qx [n,d], qt [n,d], kx [n,K,d], ky [n,K,de], kt [n,K,d],
@@ -250,7 +258,7 @@ int tiger_temporal_attention(const int64_t* center_nids, const float* q_ts, int6
 int tiger_temporal_attention_dense(const float* qx, const float* qt, const float* kx, const float* ky,
                                    const float* kt, const uint8_t* padding_mask, int64_t n_query, int k,
                                    int d, int de, int n_head, const tiger_attn_params* params, float* out,
-                                   void* stream);
+                                   void* work, void* stream);
 
 /* step 7 of TIGE.contrast_learning (tiger.py:259-288), hit_type 'bin' or 'none': hit flags
  * from the neighbor table, hit embedding, score_fn MergeLayer on positive / negative pairs,
@@ -302,6 +310,16 @@ int tiger_seq_tokens(const int64_t* nids, const int32_t* count, int64_t n, int l
 int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
                    int64_t ldc, int64_t m_rows, const int32_t* count, int64_t rows_per_count, int n_cols,
                    int k_dim, int relu, void* stream);
+
+/* Batched / extended form: problem b uses A + b*stride_a, W + b*stride_w, bias + b*stride_bias,
+ * C + b*stride_c (strides in floats); the result is act(alpha * (A W^T + bias)); rows with
+ * row_zero[m] != 0 (may be NULL; shared by all problems) are written as zeros - the
+ * masked_fill(invalid_rows, 0) of TemporalAttention.forward (temporal_agg_modules.py:230). */
+int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw,
+                           int64_t stride_w, const float* bias, int64_t stride_bias, float* C, int64_t ldc,
+                           int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
+                           int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
+                           const uint8_t* row_zero, void* stream);
 
 /* Self-attention weights of SeqRestarter's MHA (restarters.py:106, torch MHA need_weights branch),
  * reduced to what the mean over positions needs: for node i and head h

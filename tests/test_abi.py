@@ -25,6 +25,8 @@ def header_decls():
                     kinds += 'l'
                 elif p.startswith('int '):
                     kinds += 'i'
+                elif p.startswith('float '):
+                    kinds += 'f'
                 else:
                     raise AssertionError(f'unparsed parameter {p!r} in {name}')
         decls[name] = kinds

@@ -240,7 +240,7 @@ def test_temporal_attention_dense_matches_oracle(gu, d, de, n, k, H):
     mask[1::7, :-1] = True               # exactly one live slot
     p = 'temporal_embedding_fn.fns.0.'
     want = O.temporal_attention(W, p, H, qx, qt, kx, ky, kt, mask)
-    pack = ops.AttnPack(d, de, 'cuda')
+    pack = ops.AttnPack(d, de, 'cuda', H)
     m = p + 'mha_fn.'
     pack.refresh(*(gu.dev(W[x]) for x in (m + 'q_proj_weight', m + 'k_proj_weight', m + 'v_proj_weight',
                                             m + 'in_proj_bias', m + 'out_proj.weight', m + 'out_proj.bias',

@@ -12,7 +12,7 @@ import torch
 
 from .build import INCLUDE, LIB_PATH
 
-P, L, I = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
 # argument kinds per entry point: p = device/host pointer, l = int64, i = int
 _SIGNATURES: Dict[str, str] = {
@@ -35,16 +35,19 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_transpose_pad': 'plllpll' + 'p',
     'tiger_copy_pad': 'plllpl' + 'p',
     'tiger_gru_update': 'ppl' + 'plpl' + 'ii' + 'ppl' + 'ppp' + 'ppi' + 'p' + 'p',
-    'tiger_temporal_attention': 'ppll' + 'pppi' + 'pppi' + 'pp' + 'iii' + 'pp' + 'p',
-    'tiger_temporal_attention_dense': 'pppppp' + 'li' + 'iii' + 'pp' + 'p',
+    'tiger_attn_fold_keys': 'ppiiip' + 'p',
+    'tiger_temporal_attention_work_bytes': 'liiii',
+    'tiger_temporal_attention': 'ppll' + 'pppi' + 'pppi' + 'pp' + 'iii' + 'ppp' + 'p',
+    'tiger_temporal_attention_dense': 'pppppp' + 'li' + 'iii' + 'ppp' + 'p',
     'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
     'tiger_min_time': 'plp' + 'p',
     'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
     'tiger_sgemm_nt': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
+    'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_seq_attn_pool': 'plpp' + 'pli' + 'iip' + 'p',
     'tiger_static_restart': 'ppl' + 'plp' + 'pp' + 'ppi' + 'ppp' + 'ppp' + 'pp' + 'p',
 }
-_KIND = {'p': P, 'l': L, 'i': I}
+_KIND = {'p': P, 'l': L, 'i': I, 'f': F}
 
 ERR_BITS = {
     1: 'You are not allowed to modify past memory.',
@@ -83,7 +86,7 @@ def load() -> ctypes.CDLL:
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = [_KIND[c] for c in sig]
-        fn.restype = L if name == 'tiger_csr_build_work_bytes' else I
+        fn.restype = L if name.endswith('_work_bytes') else I
     _lib = lib
     return lib
 

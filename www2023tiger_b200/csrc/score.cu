@@ -1,20 +1,25 @@
 // Link scorer: step 7 of TIGE.contrast_learning (tiger/model/tiger.py:259-288), eval mode:
 // hit flags ('bin': tiger.py:266-270, data_loader.py:61-75) -> hit embedding -> score_fn
 // MergeLayer (basic_modules.py:16-19) on positive and negative pairs -> BCE-with-logits mean.
+//
+// One CTA scores SCORE_GP pairs.  The fc1 weights (k-major, L2 resident) are streamed once per CTA with
+// coalesced loads; the reduction dimension (2d) is split over two thread halves so that 2 * ceil32(d)
+// threads are busy, each keeping SCORE_GP accumulators in registers.
 #include "common.cuh"
 
-#define SCORE_GP 8  // pairs per CTA
+#define SCORE_GP 16  // pairs per CTA
 
-__global__ void __launch_bounds__(512)
-link_score_kernel(const float* __restrict__ h, int64_t batch, int d, const int64_t* __restrict__ src,
+__global__ void __launch_bounds__(1024)
+link_score_kernel(const float* __restrict__ h, int64_t batch, int d, int dp, const int64_t* __restrict__ src,
                   const int64_t* __restrict__ dst, const int64_t* __restrict__ neg,
                   const int64_t* __restrict__ neigh, int k, const float* __restrict__ hit_emb,
                   const float* __restrict__ fc1T, int ld, const float* __restrict__ fc1_b,
                   const float* __restrict__ fc2_w, const float* __restrict__ fc2_b, float* __restrict__ scores,
                   float* __restrict__ loss, uint32_t* __restrict__ done_counter) {
   extern __shared__ __align__(16) float sm[];
-  float* xin = sm;                       // [2d][GP]
-  float* red = xin + 2 * d * SCORE_GP;   // [warps][GP]
+  float* xin = sm;                             // [2d][GP]
+  float* part = xin + 2 * d * SCORE_GP;        // [dp][GP]  partial sums of the upper K half
+  float* red = part + dp * SCORE_GP;           // [warps][GP]
   __shared__ int s_flag[SCORE_GP][2];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
@@ -42,7 +47,7 @@ link_score_kernel(const float* __restrict__ h, int64_t batch, int d, const int64
     if (lane == 0) s_flag[g][side] = flag;
   }
   __syncthreads();
-  // inputs [x + he | y + he] in [k][GP] layout
+  // inputs [x + he | y + he] in [c][GP] layout
   for (int i = tid; i < SCORE_GP * 2 * d; i += blockDim.x) {
     const int g = i / (2 * d), c = i % (2 * d);
     const int64_t p = p0 + g;
@@ -59,30 +64,45 @@ link_score_kernel(const float* __restrict__ h, int64_t batch, int d, const int64
     xin[c * SCORE_GP + g] = v;
   }
   __syncthreads();
-  float part[SCORE_GP];
+  // hidden layer: thread (half, n) accumulates K range [half*d, (half+1)*d) of output unit n
+  const int half = tid / dp, n = tid % dp;
+  float acc[SCORE_GP];
 #pragma unroll
-  for (int g = 0; g < SCORE_GP; ++g) part[g] = 0.f;
-  for (int n = tid; n < d; n += blockDim.x) {
-    float acc[SCORE_GP];
-#pragma unroll
-    for (int g = 0; g < SCORE_GP; ++g) acc[g] = 0.f;
+  for (int g = 0; g < SCORE_GP; ++g) acc[g] = 0.f;
+  if (n < d && half < 2) {
+    const float* wcol = fc1T + (int64_t)half * d * ld + n;
+    const float* xs = xin + half * d * SCORE_GP;
 #pragma unroll 4
-    for (int c = 0; c < 2 * d; ++c) {
-      const float w = __ldg(fc1T + (int64_t)c * ld + n);
-      const float4 x0 = *reinterpret_cast<const float4*>(xin + c * SCORE_GP);
-      const float4 x1 = *reinterpret_cast<const float4*>(xin + c * SCORE_GP + 4);
-      acc[0] = fmaf(w, x0.x, acc[0]); acc[1] = fmaf(w, x0.y, acc[1]);
-      acc[2] = fmaf(w, x0.z, acc[2]); acc[3] = fmaf(w, x0.w, acc[3]);
-      acc[4] = fmaf(w, x1.x, acc[4]); acc[5] = fmaf(w, x1.y, acc[5]);
-      acc[6] = fmaf(w, x1.z, acc[6]); acc[7] = fmaf(w, x1.w, acc[7]);
+    for (int c = 0; c < d; ++c) {
+      const float w = __ldg(wcol + (int64_t)c * ld);
+      const float4* x4 = reinterpret_cast<const float4*>(xs + c * SCORE_GP);
+#pragma unroll
+      for (int q = 0; q < SCORE_GP / 4; ++q) {
+        const float4 x = x4[q];
+        acc[4 * q + 0] = fmaf(w, x.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(w, x.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(w, x.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(w, x.w, acc[4 * q + 3]);
+      }
     }
+    if (half == 1) {
+#pragma unroll
+      for (int g = 0; g < SCORE_GP; ++g) part[n * SCORE_GP + g] = acc[g];
+    }
+  }
+  __syncthreads();
+  float out[SCORE_GP];
+#pragma unroll
+  for (int g = 0; g < SCORE_GP; ++g) out[g] = 0.f;
+  if (half == 0 && n < d) {
     const float b = fc1_b[n], w2 = fc2_w[n];
 #pragma unroll
-    for (int g = 0; g < SCORE_GP; ++g) part[g] = fmaf(fmaxf(acc[g] + b, 0.f), w2, part[g]);
+    for (int g = 0; g < SCORE_GP; ++g)
+      out[g] = fmaxf(acc[g] + part[n * SCORE_GP + g] + b, 0.f) * w2;
   }
 #pragma unroll
   for (int g = 0; g < SCORE_GP; ++g) {
-    const float t = warp_sum(part[g]);
+    const float t = warp_sum(out[g]);
     if (lane == 0) red[warp * SCORE_GP + g] = t;
   }
   __syncthreads();
@@ -99,14 +119,14 @@ link_score_kernel(const float* __restrict__ h, int64_t batch, int d, const int64
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  float acc = 0.f;
+  float a = 0.f;
   for (int64_t p = tid; p < n_pairs; p += blockDim.x) {
     const float x = __ldcg(scores + p);
     const float y = p < batch ? 1.f : 0.f;
-    acc += fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+    a += fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
   }
-  acc = warp_sum(acc);
-  if (lane == 0) red[warp] = acc;
+  a = warp_sum(a);
+  if (lane == 0) red[warp] = a;
   __syncthreads();
   if (tid == 0) {
     float s = 0.f;
@@ -120,18 +140,24 @@ extern "C" int tiger_link_score(const float* h, int64_t batch, int d, const int6
                                 const int64_t* neg, const int64_t* neigh_nids, int k, const float* hit_emb,
                                 const float* fc1T, const float* fc1_b, const float* fc2_w, const float* fc2_b,
                                 float* scores, float* loss, uint32_t* done_counter, void* stream) {
-  if (batch < 0 || d <= 0 || (hit_emb != nullptr && (neigh_nids == nullptr || k <= 0))) return TIGER_EINVAL;
+  if (batch < 0 || d <= 0 || d > 512 || (hit_emb != nullptr && (neigh_nids == nullptr || k <= 0))) return TIGER_EINVAL;
   if (loss != nullptr && done_counter == nullptr) return TIGER_EINVAL;
   if (batch == 0) return TIGER_OK;
-  int threads = (d + 31) / 32 * 32;
-  if (threads < 64) threads = 64;
-  if (threads > 512) threads = 512;
+  const int dp = (d + 31) / 32 * 32;
+  const int threads = 2 * dp;
   const int ld = (d + 3) / 4 * 4;
-  const size_t smem = ((size_t)2 * d * SCORE_GP + (size_t)(threads / 32) * SCORE_GP + 32) * sizeof(float);
-  if (smem > 48 * 1024) return TIGER_EINVAL;
+  const size_t smem = ((size_t)2 * d * SCORE_GP + (size_t)dp * SCORE_GP + (size_t)(threads / 32) * SCORE_GP + 32) *
+                      sizeof(float);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    if (smem > 200 * 1024 ||
+        cudaFuncSetAttribute(link_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return TIGER_EINVAL;
+    configured = smem;
+  }
   const unsigned grid = (unsigned)((2 * batch + SCORE_GP - 1) / SCORE_GP);
-  link_score_kernel<<<grid, threads, smem, as_stream(stream)>>>(h, batch, d, src, dst, neg, neigh_nids, k, hit_emb,
-                                                               fc1T, ld, fc1_b, fc2_w, fc2_b, scores, loss,
+  link_score_kernel<<<grid, threads, smem, as_stream(stream)>>>(h, batch, d, dp, src, dst, neg, neigh_nids, k,
+                                                               hit_emb, fc1T, ld, fc1_b, fc2_w, fc2_b, scores, loss,
                                                                done_counter);
   return tiger_launch_status();
 }

@@ -11,7 +11,9 @@ __device__ __forceinline__ uint64_t load_key(const void* ts, int is_f64, int64_t
 }
 
 // ------------------------------------------------------------------------------------------
-// small n: one CTA, all-pairs in shared memory.  Deterministic, no scratch tables.
+// small n: all-pairs in shared memory, one warp per position (lanes split the comparison partners).
+// Winner flags only: ceil(n/32) CTAs side by side.  Ordered (unique_ids, index) output: one CTA, which
+// then ranks the winners by id.  Deterministic, no scratch tables.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 select_latest_small_kernel(const int64_t* __restrict__ nids, const void* __restrict__ ts, int is_f64, int n,
@@ -22,36 +24,44 @@ select_latest_small_kernel(const int64_t* __restrict__ nids, const void* __restr
   uint64_t* s_key = reinterpret_cast<uint64_t*>(s_id + n);
   uint8_t* s_win = reinterpret_cast<uint8_t*>(s_key + n);
   __shared__ int s_count;
+  const int lane = lane_id(), warp = warp_id_in_block(), n_warps = blockDim.x >> 5;
   if (threadIdx.x == 0) s_count = 0;
   for (int p = threadIdx.x; p < n; p += blockDim.x) {
     s_id[p] = nids[p];
     s_key[p] = load_key(ts, is_f64, p % ts_period);
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+  for (int p = blockIdx.x * n_warps + warp; p < n; p += gridDim.x * n_warps) {
     const int64_t id = s_id[p];
     const uint64_t key = s_key[p];
-    bool win = true;
-    for (int q = 0; q < n; ++q) {
+    bool beaten = false;
+    for (int q = lane; q < n; q += 32) {
       if (s_id[q] == id) {
         const uint64_t kq = s_key[q];
-        if (kq > key || (kq == key && q < p)) win = false;
+        beaten |= (kq > key) || (kq == key && q < p);
       }
     }
-    s_win[p] = win;
-    if (winner != nullptr) winner[p] = win;
-    if (win) atomicAdd(&s_count, 1);
+    const bool win = !__any_sync(TIGER_FULL_MASK, beaten);
+    if (lane == 0) {
+      if (unique_ids != nullptr) s_win[p] = win;
+      if (winner != nullptr) winner[p] = win;
+      if (win && count != nullptr && gridDim.x == 1) atomicAdd(&s_count, 1);
+    }
   }
+  if (gridDim.x != 1) return;          // winner-only mode
   __syncthreads();
   if (count != nullptr && threadIdx.x == 0) *count = s_count;
   if (unique_ids == nullptr) return;
-  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+  for (int p = warp; p < n; p += n_warps) {
     if (!s_win[p]) continue;
     const int64_t id = s_id[p];
     int rank = 0;
-    for (int q = 0; q < n; ++q) rank += (s_win[q] && s_id[q] < id);
-    unique_ids[rank] = id;
-    index[rank] = p;
+    for (int q = lane; q < n; q += 32) rank += (s_win[q] && s_id[q] < id);
+    rank = (int)warp_sum((float)rank);   // n <= 2048: exact in float
+    if (lane == 0) {
+      unique_ids[rank] = id;
+      index[rank] = p;
+    }
   }
 }
 
@@ -155,8 +165,10 @@ extern "C" int tiger_select_latest(const int64_t* nids, const void* ts, int ts_i
   }
   if (n <= SELECT_SMALL_N) {
     const size_t smem = (size_t)n * (sizeof(int64_t) + sizeof(uint64_t) + 1);
-    const int threads = n >= 1024 ? 1024 : (int)((n + 31) / 32 * 32);
-    select_latest_small_kernel<<<1, threads, smem, st>>>(nids, ts, ts_is_f64, (int)n, ts_period, winner, unique_ids,
+    // winner flags only (and no count requested): spread the positions over several CTAs
+    const bool flags_only = unique_ids == nullptr && count == nullptr;
+    const unsigned grid = flags_only ? (unsigned)((n + 31) / 32) : 1u;
+    select_latest_small_kernel<<<grid, 1024, smem, st>>>(nids, ts, ts_is_f64, (int)n, ts_period, winner, unique_ids,
                                                         index, count);
     return tiger_launch_status();
   }

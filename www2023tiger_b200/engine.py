@@ -29,7 +29,7 @@ from ._lib import raise_on_err_flags
 from .ops import f32, f64, i32, i64, u8
 
 KERNELS_PER_STEP = {  # launches of our kernels per batch (for the bench `gpu_launches` field)
-    'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 1, 'select_latest': 1,
+    'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 8, 'select_latest': 1,
     'right_writeback': 1, 'store_messages': 2, 'left_writeback': 1, 'link_score': 1,
 }
 
@@ -91,7 +91,7 @@ class TigerEngine:
         self.ts64 = self.inp[4 * B:].view(f64)
         # ---- parameters ----
         self.gru_pack = None
-        self.attn_pack = ops.AttnPack(self.d, self.de, dev)
+        self.attn_pack = ops.AttnPack(self.d, self.de, dev, n_head)
         self.score_pack = ops.ScorePack(self.d, dev)
         self.hist_len = hist_len
         self.seq = ops.SeqRestarterOp(self.d, self.de, hist_len, n_head, self.cap, dev) if restarter == 'seq' else None
@@ -191,7 +191,7 @@ class TigerEngine:
         ops.temporal_attention(self.attn_pack, self.H, self.batch_nids, self.ts32, self.neigh_nids, self.neigh_eids,
                                self.neigh_ts, rows_a=self.right_vals, rows_b=self.h_new, sel=self.gru_row,
                                nfeats=self.nfeats, efeats=self.efeats, out=self.emb)
-        ops.select_latest(self.pos, self.ts32, want_unique=False, winner=self.winner, count=self.sel_count)
+        ops.select_latest(self.pos, self.ts32, want_unique=False, winner=self.winner, want_count=False)
         ops.right_writeback(self.pos, self.winner, self.gru_row, self.h_new, d, self.right_vals, self.right_ts,
                             self.right_active, self.msg_ts, self.has_msg, self.left_vals, self.hprev_left,
                             self.hprev_right, self.err_flags)

@@ -113,7 +113,8 @@ class SelectScratch:
 
 
 def select_latest(nids: Tensor, ts: Tensor, scratch: Optional[SelectScratch] = None, *,
-                  want_unique: bool = True, winner: Optional[Tensor] = None, count: Optional[Tensor] = None):
+                  want_unique: bool = True, winner: Optional[Tensor] = None, count: Optional[Tensor] = None,
+                  want_count: bool = True):
     """a8: returns (winner uint8 [n], unique_ids, index, count) - unique_ids/index have n slots,
     the first `count` (device int32) are valid."""
     check_cuda(nids, ts)
@@ -123,7 +124,7 @@ def select_latest(nids: Tensor, ts: Tensor, scratch: Optional[SelectScratch] = N
         winner = _empty(n, u8, nids)
     uniq = _empty(n, i64, nids) if want_unique else None
     index = _empty(n, i64, nids) if want_unique else None
-    if count is None:
+    if count is None and (want_count or want_unique):
         count = _empty(1, i32, nids)
     if n > 2048 and scratch is None:
         raise _lib.TigerLibraryError('select_latest over more than 2048 positions needs a SelectScratch')
@@ -252,44 +253,49 @@ def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_
 
 class AttnParamsC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
-                ('wqT', 'wk', 'wvT', 'woT', 'fc1T', 'fc2T', 'in_bias', 'out_bias', 'fc1_b', 'fc2_b', 'time_w',
+                ('wq', 'wk_fold', 'wv', 'wo', 'fc1', 'fc2', 'in_bias', 'out_bias', 'fc1_b', 'fc2_b', 'time_w',
                  'time_b')]
 
 
 class AttnPack:
-    """k-major, 16-byte-aligned packs of TemporalAttention's parameters (one blob)."""
+    """TemporalAttention parameters for the kernels: the reference's tensors as stored plus the folded
+    key projection [H][Cq][hdp] (tiger_attn_fold_keys), and a workspace that grows on demand."""
 
-    def __init__(self, d: int, de: int, device):
-        self.d, self.de = d, de
+    def __init__(self, d: int, de: int, device, n_head: int = 2):
+        self.d, self.de, self.n_head = d, de, n_head
         E, C = 2 * d, 2 * d + de
-        self.ldE, self.ldC, self.ldD = round_up(E, 4), round_up(C, 4), round_up(d, 4)
-        sizes = [E * self.ldE, E * self.ldC, C * self.ldE, E * self.ldE, (E + d) * self.ldD, d * self.ldD]
-        self.offsets = [0]
-        for s in sizes:
-            self.offsets.append(self.offsets[-1] + round_up(s, 4))
-        self.blob = torch.zeros(self.offsets[-1], dtype=f32, device=device)
+        self.E, self.C = E, C
+        self.Cq = round_up(C + 1, 4)
+        self.hdp = round_up(E // n_head, 4)
+        self.wk_fold = torch.zeros(n_head * self.Cq * self.hdp, dtype=f32, device=device)
         self.struct = AttnParamsC()
         self._keep = None
-
-    def part(self, i: int) -> Tensor:
-        return self.blob[self.offsets[i]:self.offsets[i + 1]]
+        self._work = None
+        self._work_key = None
 
     def refresh(self, q_w, k_w, v_w, in_bias, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b, time_w, time_b):
-        det = lambda t: t.detach().contiguous()
-        transpose_pad(det(q_w), self.part(0), self.ldE)
-        copy_pad(det(k_w), self.part(1), self.ldC)
-        transpose_pad(det(v_w), self.part(2), self.ldE)
-        transpose_pad(det(out_w), self.part(3), self.ldE)
-        transpose_pad(det(fc1_w), self.part(4), self.ldD)
-        transpose_pad(det(fc2_w), self.part(5), self.ldD)
-        keep = [det(in_bias), det(out_b), det(fc1_b), det(fc2_b), det(time_w), det(time_b)]
+        det = lambda t: t.detach().to(f32).contiguous()
+        keep = [det(t) for t in (q_w, k_w, v_w, in_bias, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b, time_w, time_b)]
+        q_w, k_w, v_w, in_bias, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b, time_w, time_b = keep
+        check_cuda(*keep)
+        call('tiger_attn_fold_keys', ptr(k_w), in_bias[self.E:].data_ptr(), self.d, self.de, self.n_head,
+             ptr(self.wk_fold))
         self._keep = keep
         s = self.struct
-        s.wqT, s.wk, s.wvT, s.woT, s.fc1T, s.fc2T = (self.part(i).data_ptr() for i in range(6))
-        s.in_bias, s.out_bias, s.fc1_b, s.fc2_b, s.time_w, s.time_b = (t.data_ptr() for t in keep)
+        s.wq, s.wk_fold, s.wv, s.wo, s.fc1, s.fc2 = (t.data_ptr() for t in (q_w, self.wk_fold, v_w, out_w, fc1_w, fc2_w))
+        s.in_bias, s.out_bias, s.fc1_b, s.fc2_b, s.time_w, s.time_b = (t.data_ptr() for t in
+                                                                       (in_bias, out_b, fc1_b, fc2_b, time_w, time_b))
 
     def byref(self):
         return ctypes.addressof(self.struct)
+
+    def work(self, n_query: int, k: int) -> Tensor:
+        key = (n_query, k)
+        if self._work is None or self._work_key is None or self._work_key[0] < n_query or self._work_key[1] != k:
+            nbytes = _lib.load().tiger_temporal_attention_work_bytes(n_query, k, self.d, self.de, self.n_head)
+            self._work = torch.empty(nbytes, dtype=u8, device=self.wk_fold.device)
+            self._work_key = key
+        return self._work
 
 
 def temporal_attention(pack: AttnPack, n_head: int, center_nids: Tensor, q_ts: Tensor, neigh_nids: Tensor,
@@ -301,10 +307,10 @@ def temporal_attention(pack: AttnPack, n_head: int, center_nids: Tensor, q_ts: T
     n, k = neigh_nids.shape
     if out is None:
         out = _empty((n, pack.d), f32, rows_b)
-    assert sel.dtype in (i32, i64)
+    assert sel.dtype in (i32, i64) and n_head == pack.n_head
     call('tiger_temporal_attention', ptr(center_nids), ptr(q_ts), n, q_ts.numel(), ptr(neigh_nids), ptr(neigh_eids),
          ptr(neigh_ts), k, ptr(rows_a), ptr(rows_b), ptr(sel), int(sel.dtype == i64), ptr(nfeats), ptr(efeats),
-         pack.d, pack.de, n_head, pack.byref(), ptr(out))
+         pack.d, pack.de, n_head, pack.byref(), ptr(out), ptr(pack.work(n, k)))
     return out
 
 
@@ -313,8 +319,9 @@ def temporal_attention_dense(pack: AttnPack, n_head: int, qx, qt, kx, ky, kt, pa
     n, k = kx.shape[0], kx.shape[1]
     out = _empty((n, pack.d), f32, qx)
     mask = padding_mask.to(u8).contiguous()
+    assert n_head == pack.n_head
     call('tiger_temporal_attention_dense', ptr(qx), ptr(qt), ptr(kx), ptr(ky), ptr(kt), ptr(mask), n, k, pack.d,
-         pack.de, n_head, pack.byref(), ptr(out))
+         pack.de, n_head, pack.byref(), ptr(out), ptr(pack.work(n, k)))
     return out
 
 

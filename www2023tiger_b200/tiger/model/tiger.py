@@ -170,7 +170,7 @@ class TIGE(nn.Module):
                                      efeats=fg.efeats)
         # steps 4-6 (tiger.py:230-255)
         winner = ws.winner[:2 * B]
-        ops.select_latest(pos, ts, want_unique=False, winner=winner, count=ws.sel_count)
+        ops.select_latest(pos, ts, want_unique=False, winner=winner, want_count=False)
         h_prev_left = torch.empty(2 * B, d, device=dev)
         h_prev_right = torch.empty(2 * B, d, device=dev)
         ops.right_writeback(pos, winner, ws.gru_row, ws.h_new, d, right.vals, right.update_ts, right.active_mask,
