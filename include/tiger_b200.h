@@ -198,12 +198,12 @@ int tiger_copy_pad(const float* w, int64_t rows, int64_t cols, int64_t ld_in, fl
  *   h_new[r,:] = GRUCell(x = msg rows, h = state rows)
  * node_ids==NULL: x/h are dense [n,M]/[n,d]; otherwise row r reads x_table[node_ids[r]] and
  * h_table[node_ids[r]].  count (device, may be NULL) overrides n_rows (n_rows stays the grid
- * bound).  wT_ih [M][ldw], wT_hh [d][ldw]: k-major packs with ldw >= 3*dp, gate g of hidden
- * unit j at column g*dp + j (dp = d rounded up to 32).  Also checks the message invariants of
- * tiger.py:319-327 when check_mem_ts != NULL. */
+ * bound).  w_ih [3d][M], w_hh [3d][d], b_ih, b_hh [3d]: nn.GRUCell's parameters as stored
+ * (contiguous rows).  The gate GEMMs run on the tensor cores in tf32x3 (fp32-accurate).  Also
+ * checks the message invariants of tiger.py:319-327 when check_mem_ts != NULL. */
 int tiger_gru_update(const int64_t* node_ids, const int32_t* count, int64_t n_rows,
                      const float* x_table, int64_t x_stride, const float* h_table, int64_t h_stride,
-                     int m_dim, int d, const float* wT_ih, const float* wT_hh, int64_t ldw,
+                     int m_dim, int d, const float* w_ih, const float* w_hh,
                      const float* b_ih, const float* b_hh, float* h_new,
                      const float* msg_ts, const float* check_mem_ts, int check_equal,
                      uint32_t* err_flags, void* stream);
@@ -320,6 +320,17 @@ int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t stride_a, const 
                            int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
                            int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
                            const uint8_t* row_zero, void* stream);
+
+/* FFMA (CUDA-core) implementation of the same two operators: the measured baseline the tensor-core
+ * kernels are compared with in bench.py --micro and tests; never on the product path. */
+int tiger_sgemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
+                     int64_t ldc, int64_t m_rows, const int32_t* count, int64_t rows_per_count, int n_cols,
+                     int k_dim, int relu, void* stream);
+int tiger_sgemm_ffma_batched(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw,
+                             int64_t stride_w, const float* bias, int64_t stride_bias, float* C, int64_t ldc,
+                             int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
+                             int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
+                             const uint8_t* row_zero, void* stream);
 
 /* Self-attention weights of SeqRestarter's MHA (restarters.py:106, torch MHA need_weights branch),
  * reduced to what the mean over positions needs: for node i and head h

@@ -34,7 +34,7 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_left_writeback': 'pllp' + 'pip' + 'ppp' + 'p' + 'p',
     'tiger_transpose_pad': 'plllpll' + 'p',
     'tiger_copy_pad': 'plllpl' + 'p',
-    'tiger_gru_update': 'ppl' + 'plpl' + 'ii' + 'ppl' + 'ppp' + 'ppi' + 'p' + 'p',
+    'tiger_gru_update': 'ppl' + 'plpl' + 'ii' + 'pp' + 'ppp' + 'ppi' + 'p' + 'p',
     'tiger_attn_fold_keys': 'ppiiip' + 'p',
     'tiger_temporal_attention_work_bytes': 'liiii',
     'tiger_temporal_attention': 'ppll' + 'pppi' + 'pppi' + 'pp' + 'iii' + 'ppp' + 'p',
@@ -44,6 +44,8 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
     'tiger_sgemm_nt': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
     'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
+    'tiger_sgemm_ffma': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
+    'tiger_sgemm_ffma_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_seq_attn_pool': 'plpp' + 'pli' + 'iip' + 'p',
     'tiger_static_restart': 'ppl' + 'plp' + 'pp' + 'ppi' + 'ppp' + 'ppp' + 'pp' + 'p',
 }

@@ -1,36 +1,52 @@
-// fp32 "NT" GEMM with fused epilogue:
+// fp32-accurate "NT" GEMM on the 5th-generation tensor cores (tcgen05, kind::tf32, tf32x3 split):
 //     C[b][m, n] = act(alpha * (sum_k A[b][m, k] * W[b][n, k] + bias[b][n])),  rows with row_zero[m] != 0 -> 0
 // A row-major [M, K] (lda), W row-major [N, K] (ldw) - the layout of nn.Linear / in_proj weights, so
 // parameters are used as stored (reference: nn.MultiheadAttention in/out projections, nn.Linear and
 // MergeLayer of tiger/model/restarters.py:45-50, temporal_agg_modules.py:203-209, basic_modules.py:5-19).
 //
-// FFMA, not tensor cores: the parity bar is fp32 max-norm 1e-5 against the CPU reference, which
-// single-pass TF32 (10-bit mantissa) cannot meet.
+// Why tensor cores, and why three passes: the parity bar is fp32 max-norm 1e-5 against the CPU
+// reference.  Single-pass TF32 (10-bit mantissa) cannot meet it; splitting every operand into a tf32
+// head and tail and accumulating head*tail + tail*head + head*head in the fp32 TMEM accumulator does
+// (error ~2^-22 per product), at 3 MMAs per k-step - still several times the FFMA rate, and the MMAs
+// run asynchronously to the threads that stage the operands.
 //
-// Structure: persistent CTAs (grid = a multiple of the SM count) walk the tiles of the ACTUAL
-// problem - the row count may live on the device (`count` * rows_per_count), which keeps the restart
-// path free of host syncs.  Tiles are 128x128 (8x8 per thread) when that still fills the GPU and
-// 32x64 (2x4 per thread) otherwise, chosen at run time.  Operands stream global -> shared with
-// cp.async (16-byte LDGSTS, zero-fill for edges) through a 3-stage ring; both operands keep their
-// natural [row][k] layout in shared memory (row stride 20 floats: conflict-free LDS.128), and each
-// thread owns rows / columns strided by 16 so that warp-wide stores to C are coalesced.
+// Structure (one CTA = one 128 x BN output tile, BN <= 128, 19 warps):
+//   warps 0-15 producers in 4 groups of 4 warps; group g fills stages g, g+4, ...: global (L2) ->
+//              registers -> tf32 split -> shared memory in the canonical K-major UMMA layout
+//              (umma.cuh), 16 floats of K per stage, up to 8 stages, full/empty mbarriers; a group's
+//              next loads are issued before it publishes the current stage, and the four groups keep
+//              four stages of loads in flight, which is what hides the L2 latency;
+//              afterwards the same warps run the epilogue: tcgen05.ld of the partial accumulators
+//              (thread = row, 16 columns at a time), bias / alpha / ReLU / row mask, 16-byte stores
+//   warps 16-18 MMA issuers: one elected thread each issues one of the three tf32x3 product streams
+//              into its own TMEM accumulator and commits each stage back to the producers
+//              (tcgen05.commit -> mbarrier); see umma.cuh for why three
+// The row count may live on the device (`count` * rows_per_count), which keeps the restart path free of
+// host syncs: CTAs whose row block starts beyond it exit before touching TMEM.
 #include "common.cuh"
+#include "umma.cuh"
 
-#define GEMM_THREADS 256
-#define GEMM_BK 16
-#define GEMM_LDS (GEMM_BK + 4)
-#define GEMM_STAGES 3
+#ifdef TIGER_TRACE
+#include <cstdio>
+#define TRACE_DECL long long tr_t[24]; int tr_n = 0; const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+#define TRACE_MARK() do { if (tr_on && tr_n < 24) tr_t[tr_n++] = clock64(); } while (0)
+#define TRACE_DUMP(tag, id) do { if (tr_on) for (int i_ = 0; i_ < tr_n; ++i_) printf("%s %d #%d %lld\n", tag, id, i_, tr_t[i_] - tr_base); } while (0)
+#else
+#define TRACE_DECL
+#define TRACE_MARK() do { } while (0)
+#define TRACE_DUMP(tag, id) do { } while (0)
+#endif
 
-template <int BM, int BN>
-struct GemmSmem {
-  float a[GEMM_STAGES][BM][GEMM_LDS];
-  float w[GEMM_STAGES][BN][GEMM_LDS];
-};
-
-union GemmSmemAll {
-  GemmSmem<128, 128> big;
-  GemmSmem<32, 64> small;
-};
+#define TCG_PRODUCER_WARPS 16
+#define TCG_THREADS ((TCG_PRODUCER_WARPS + UMMA_ISSUERS) * 32)
+#define TCG_BM 128
+#define TCG_GROUPS 4                                    // producer groups, each fills every 4th stage
+#define TCG_GROUP_WARPS (TCG_PRODUCER_WARPS / TCG_GROUPS)
+#define TCG_MAX_BN 128
+#define TCG_MAX_STAGES 8
+#define TCG_SMEM_BUDGET (200 * 1024)
+#define TCG_NA (TCG_BM / 8 / TCG_GROUP_WARPS)           // A warp-chunks per producer warp
+#define TCG_NW (TCG_MAX_BN / 8 / TCG_GROUP_WARPS)       // W warp-chunks per producer warp at the widest tile
 
 struct GemmArgs {
   const float* A;
@@ -42,145 +58,190 @@ struct GemmArgs {
   int64_t lda, ldw, ldc;
   int64_t stride_a, stride_w, stride_bias, stride_c;
   int64_t M, rows_per_count;
-  int batch, N, K;
+  int N, K;
   float alpha;
   int relu;
-  int vec_ok;  // A, W 16-byte aligned with lda, ldw, strides multiples of 4 floats
+  int vec_a, vec_w, vec_c;  // 16-byte alignment of the rows of A / W / C
+  int bn, tiles_n, stages;
+  uint32_t tmem_cols;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+__global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmArgs g) {
+  extern __shared__ __align__(128) unsigned char tcg_smem[];
+  const int BN = g.bn, S = g.stages;
+  const int a_plane = UMMA_KCH * TCG_BM * 4;  // floats
+  const int w_plane = UMMA_KCH * BN * 4;
+  const int stage_floats = 2 * a_plane + 2 * w_plane;
+  float* stage0 = reinterpret_cast<float*>(tcg_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tcg_smem + (size_t)S * stage_floats * sizeof(float));
+  uint64_t* empty = full + TCG_MAX_STAGES;
+  uint64_t* done = empty + TCG_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-// one BK slab of a [ROWS x BK] operand tile: global -> shared (rows >= rows_valid and k >= K read as zero)
-template <int ROWS>
-__device__ __forceinline__ void gemm_load(float (*sm)[GEMM_LDS], const float* __restrict__ base, int64_t ld,
-                                          int64_t row0, int64_t rows_valid, int k0, int K, int vec_ok, int tid) {
-  constexpr int CHUNKS = ROWS * (GEMM_BK / 4);
-#pragma unroll
-  for (int c = tid; c < CHUNKS; c += GEMM_THREADS) {
-    const int r = c >> 2, kq = (c & 3) << 2;
-    const int k = k0 + kq;
-    const bool row_ok = row0 + r < rows_valid;
-    int valid = row_ok ? (K - k) : 0;            // floats available from k on
-    valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
-    // clamp the address into the allocation even when nothing is read from it
-    const float* p = base + (row_ok ? (row0 + r) : row0) * ld + (valid > 0 ? k : 0);
-    if (vec_ok) {
-      cp_async16(&sm[r][kq], p, valid * 4);
-    } else {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid > 0) v.x = __ldg(p);
-      if (valid > 1) v.y = __ldg(p + 1);
-      if (valid > 2) v.z = __ldg(p + 2);
-      if (valid > 3) v.w = __ldg(p + 3);
-      *reinterpret_cast<float4*>(&sm[r][kq]) = v;
-    }
-  }
-}
-
-template <int BM, int BN, int TM, int TN>
-__device__ __forceinline__ void gemm_tile(const GemmArgs& g, GemmSmem<BM, BN>& sm, const float* __restrict__ A,
-                                          const float* __restrict__ W, const float* __restrict__ bias,
-                                          float* __restrict__ C, int64_t m0, int n0, int64_t M, int tid) {
-  constexpr int SX = BN / TN, SY = BM / TM;   // thread grid; thread (ty, tx) owns rows ty + i*SY, cols tx + j*SX
-  static_assert(SX * SY == GEMM_THREADS, "thread tiling");
-  const int tx = tid % SX, ty = tid / SX;
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  const int n_slabs = (g.K + GEMM_BK - 1) / GEMM_BK;
-#pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
-    if (s < n_slabs) {
-      gemm_load<BM>(sm.a[s], A, g.lda, m0, M, s * GEMM_BK, g.K, g.vec_ok, tid);
-      gemm_load<BN>(sm.w[s], W, g.ldw, n0, g.N, s * GEMM_BK, g.K, g.vec_ok, tid);
-    }
-    cp_async_commit();
-  }
-  for (int s = 0; s < n_slabs; ++s) {
-    cp_async_wait<GEMM_STAGES - 2>();
-    __syncthreads();   // slab s has landed for every thread; the stage refilled below is no longer being read
-    const int nxt = s + GEMM_STAGES - 1;
-    if (nxt < n_slabs) {
-      gemm_load<BM>(sm.a[nxt % GEMM_STAGES], A, g.lda, m0, M, nxt * GEMM_BK, g.K, g.vec_ok, tid);
-      gemm_load<BN>(sm.w[nxt % GEMM_STAGES], W, g.ldw, n0, g.N, nxt * GEMM_BK, g.K, g.vec_ok, tid);
-    }
-    cp_async_commit();
-    const int buf = s % GEMM_STAGES;
-#pragma unroll
-    for (int kq = 0; kq < GEMM_BK; kq += 4) {
-      float4 a[TM], w[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(&sm.a[buf][ty + i * SY][kq]);
-#pragma unroll
-      for (int j = 0; j < TN; ++j) w[j] = *reinterpret_cast<const float4*>(&sm.w[buf][tx + j * SX][kq]);
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) {
-          acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
-          acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
-          acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
-          acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
-        }
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();     // every thread is done with the ring before the next tile's prologue refills it
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int64_t m = m0 + ty + i * SY;
-    if (m >= M) continue;
-    const bool zero = g.row_zero != nullptr && g.row_zero[m] != 0;
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int n = n0 + tx + j * SX;
-      if (n >= g.N) continue;
-      float v = (acc[i][j] + (bias != nullptr ? bias[n] : 0.f)) * g.alpha;
-      if (g.relu) v = fmaxf(v, 0.f);
-      C[m * g.ldc + n] = zero ? 0.f : v;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(GEMM_THREADS, 2) sgemm_nt_kernel(const GemmArgs g, int sm_count) {
-  extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
-  GemmSmemAll& sm = *reinterpret_cast<GemmSmemAll*>(gemm_smem_raw);
   int64_t M = g.M;
   if (g.count != nullptr) {
     const int64_t c = (int64_t)(*g.count) * g.rows_per_count;
     M = c < M ? c : M;
   }
-  if (M <= 0) return;
-  const int tid = threadIdx.x;
-  const int64_t tm_big = (M + 127) / 128, tn_big = (g.N + 127) / 128;
-  if (tm_big * tn_big * g.batch >= (3 * sm_count) / 4) {
-    const int64_t per = tm_big * tn_big;
-    for (int64_t t = blockIdx.x; t < per * g.batch; t += gridDim.x) {
-      const int64_t b = t / per, r = t % per;
-      gemm_tile<128, 128, 8, 8>(g, sm.big, g.A + b * g.stride_a, g.W + b * g.stride_w,
-                                g.bias != nullptr ? g.bias + b * g.stride_bias : nullptr, g.C + b * g.stride_c,
-                                (r / tn_big) * 128, (int)(r % tn_big) * 128, M, tid);
+  const int64_t m0 = (int64_t)(blockIdx.x / g.tiles_n) * TCG_BM;
+  if (m0 >= M) return;
+  const int n0 = (int)(blockIdx.x % g.tiles_n) * BN;
+  const int b = blockIdx.y;
+  const float* __restrict__ A = g.A + b * g.stride_a;
+  const float* __restrict__ W = g.W + b * g.stride_w;
+  const float* __restrict__ bias = g.bias != nullptr ? g.bias + b * g.stride_bias : nullptr;
+  float* __restrict__ C = g.C + b * g.stride_c;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == TCG_PRODUCER_WARPS * 32) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, TCG_GROUP_WARPS);
+      mbar_init(empty + s, UMMA_ISSUERS);
     }
-  } else {
-    const int64_t tm = (M + 31) / 32, tn = (g.N + 63) / 64;
-    const int64_t per = tm * tn;
-    for (int64_t t = blockIdx.x; t < per * g.batch; t += gridDim.x) {
-      const int64_t b = t / per, r = t % per;
-      gemm_tile<32, 64, 2, 4>(g, sm.small, g.A + b * g.stride_a, g.W + b * g.stride_w,
-                              g.bias != nullptr ? g.bias + b * g.stride_bias : nullptr, g.C + b * g.stride_c,
-                              (r / tn) * 32, (int)(r % tn) * 64, M, tid);
-    }
+    mbar_init(done, UMMA_ISSUERS);
+    fence_mbar_init();
   }
+  if (warp == 0) tmem_alloc(tmem_slot, g.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t taddr = *tmem_slot;
+  const int n_blocks = (g.K + UMMA_BK - 1) / UMMA_BK;
+#ifdef TIGER_TRACE
+  __shared__ long long tr_base_s;
+  if (tid == 0) tr_base_s = clock64();
+  __syncthreads();
+  const long long tr_base = tr_base_s;
+#endif
+  TRACE_DECL
+
+  if (warp < TCG_PRODUCER_WARPS) {
+    // ---------------- producers ----------------
+    // group `grp` fills stages grp, grp + GROUPS, ...: while one group waits for its loads the others
+    // convert / publish theirs, so GROUPS stages worth of global loads are always in flight
+    const int grp = warp / TCG_GROUP_WARPS, wg = warp % TCG_GROUP_WARPS;
+    UmmaChunks<TCG_NA> ca;
+    UmmaChunks<TCG_NW> cw;
+#pragma unroll
+    for (int i = 0; i < TCG_NA; ++i) {
+      int row, kc;
+      umma_chunk_pos(wg + TCG_GROUP_WARPS * i, lane, row, kc);
+      int64_t m = m0 + row;
+      m = m < M ? m : M - 1;
+      ca.ptr[i] = A + m * g.lda + kc * 4;
+      ca.soff[i] = (kc * TCG_BM + row) * 4;
+      ca.kq[i] = kc * 4;
+    }
+#pragma unroll
+    for (int i = 0; i < TCG_NW; ++i) {
+      const int wc = wg + TCG_GROUP_WARPS * i;
+      int row, kc;
+      umma_chunk_pos(wc, lane, row, kc);
+      int n = n0 + row;
+      n = n < g.N ? n : g.N - 1;
+      cw.ptr[i] = W + (int64_t)n * g.ldw + kc * 4;
+      cw.soff[i] = wc < (BN >> 3) ? (kc * BN + row) * 4 : -1;
+      cw.kq[i] = kc * 4;
+    }
+    float4 va[TCG_NA], vw[TCG_NW];
+    if (grp < n_blocks) {
+      umma_chunks_load(va, ca, grp * UMMA_BK, g.K, g.vec_a != 0);
+      umma_chunks_load(vw, cw, grp * UMMA_BK, g.K, g.vec_w != 0);
+    }
+    for (int blk = grp; blk < n_blocks; blk += TCG_GROUPS) {
+      const int s = blk % S;
+      float* a_hi = stage0 + (size_t)s * stage_floats;
+      float* a_lo = a_hi + a_plane;
+      float* w_hi = a_lo + a_plane;
+      float* w_lo = w_hi + w_plane;
+      mbar_wait(empty + s, ((blk / S) & 1) ^ 1);
+      TRACE_MARK();
+      umma_chunks_store(a_hi, a_lo, ca, va);
+      umma_chunks_store(w_hi, w_lo, cw, vw);
+      TRACE_MARK();
+      const int nxt = blk + TCG_GROUPS;
+      if (nxt < n_blocks) {
+        umma_chunks_load(va, ca, nxt * UMMA_BK, g.K, g.vec_a != 0);
+        umma_chunks_load(vw, cw, nxt * UMMA_BK, g.K, g.vec_w != 0);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + s);
+      TRACE_MARK();
+    }
+    // ---------------- epilogue ----------------
+    mbar_wait(done, 0);
+    tc_fence_after_sync();
+    TRACE_MARK();
+    const int q = warp & 3;
+    const int64_t m = m0 + q * 32 + lane;
+    const bool row_ok = m < M;
+    const bool zero = row_ok && g.row_zero != nullptr && g.row_zero[m] != 0;
+    const uint32_t tl = taddr + ((uint32_t)(q * 32) << 16);
+    for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += 16 * (TCG_PRODUCER_WARPS / 4)) {
+      float v[16];
+      tmem_ld16(tl + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 1; j < UMMA_ACCS; ++j) {
+        float t[16];
+        tmem_ld16(tl + (uint32_t)(j * BN + c0), t);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] += t[e];
+      }
+      const int nb = n0 + c0;
+      if (!row_ok || nb >= g.N) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = nb + j;
+        float x = (v[j] + ((bias != nullptr && n < g.N) ? __ldg(bias + n) : 0.f)) * g.alpha;
+        if (g.relu) x = fmaxf(x, 0.f);
+        v[j] = zero ? 0.f : x;
+      }
+      float* dst = C + m * g.ldc + nb;
+      if (g.vec_c && nb + 16 <= g.N) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < g.N) dst[j] = v[j];
+      }
+    }
+  } else if (lane == 0) {
+    // ---------------- MMA issuers (one elected thread per role, see umma.cuh) ----------------
+    const int role = warp - TCG_PRODUCER_WARPS;
+    const UmmaRole r = umma_role(role, smem_addr_u32(stage0), (uint32_t)stage_floats * 4u, TCG_BM, BN, (uint32_t)BN);
+    const uint32_t idesc = umma_idesc_tf32(TCG_BM, BN);
+    const uint32_t d_even = taddr + r.acc_even, d_odd = taddr + r.acc_odd;
+    int s = 0;
+    uint32_t ph = 0, a = r.a_lo, b = r.b_lo;
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      mbar_wait(full + s, ph);
+      tc_fence_after_sync();
+      TRACE_MARK();
+      umma_tf32_lo(d_even, a, b, idesc, blk > 0 ? 1u : 0u);
+      umma_tf32_lo(d_odd, a + r.a_kstep, b + r.b_kstep, idesc, (role == 2 && blk == 0) ? 0u : 1u);
+      umma_commit(empty + s);
+      TRACE_MARK();
+      a += r.stage_step;
+      b += r.stage_step;
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
+        a = r.a_lo;
+        b = r.b_lo;
+      }
+    }
+    umma_commit(done);
+  }
+  TRACE_MARK();
+#ifdef TIGER_TRACE
+  if (warp % TCG_GROUP_WARPS == 0 || warp >= TCG_PRODUCER_WARPS) TRACE_DUMP(warp < TCG_PRODUCER_WARPS ? "producer" : "issuer", warp);
+#endif
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(taddr, g.tmem_cols);
 }
 
 static int g_gemm_sms = 0;
@@ -198,8 +259,8 @@ extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t strid
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    if (cudaFuncSetAttribute(sgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(GemmSmemAll)) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TCG_SMEM_BUDGET + 256) != cudaSuccess)
       return TIGER_ECUDA;
     g_gemm_sms = sms;
   }
@@ -208,13 +269,32 @@ extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t strid
   g.lda = lda; g.ldw = ldw; g.ldc = ldc;
   g.stride_a = stride_a; g.stride_w = stride_w; g.stride_bias = stride_bias; g.stride_c = stride_c;
   g.M = m_rows; g.rows_per_count = rows_per_count > 0 ? rows_per_count : 1;
-  g.batch = batch; g.N = n_cols; g.K = k_dim; g.alpha = alpha; g.relu = relu;
-  const bool strides_ok = batch == 1 || (((stride_a | stride_w) & 3) == 0);
-  g.vec_ok = ((((uintptr_t)A | (uintptr_t)W) & 15) == 0 && (lda & 3) == 0 && (ldw & 3) == 0 && strides_ok) ? 1 : 0;
-  // enough CTAs for the largest possible problem, never more than two per SM
-  const int64_t tiles_small = ((m_rows + 31) / 32) * ((n_cols + 63) / 64) * batch;
-  const int64_t grid = tiles_small < 2 * (int64_t)g_gemm_sms ? tiles_small : 2 * (int64_t)g_gemm_sms;
-  sgemm_nt_kernel<<<(unsigned)grid, GEMM_THREADS, sizeof(GemmSmemAll), as_stream(stream)>>>(g, g_gemm_sms);
+  g.N = n_cols; g.K = k_dim; g.alpha = alpha; g.relu = relu;
+  const bool multi = batch > 1;
+  g.vec_a = ((((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && (!multi || (stride_a & 3) == 0)) ? 1 : 0;
+  g.vec_w = ((((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && (!multi || (stride_w & 3) == 0)) ? 1 : 0;
+  g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0 && (!multi || (stride_c & 3) == 0)) ? 1 : 0;
+  // column tile: the widest of 128/64/32 that still yields about one CTA per SM, then balanced
+  const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
+  int bn = 32;
+  for (int cand = TCG_MAX_BN; cand >= 32; cand >>= 1) {
+    const int64_t tiles = tiles_m * ((n_cols + cand - 1) / cand) * batch;
+    if (tiles >= (3 * (int64_t)g_gemm_sms) / 4 || cand == 32) {
+      bn = cand;
+      break;
+    }
+  }
+  g.tiles_n = (n_cols + bn - 1) / bn;
+  g.bn = (((n_cols + g.tiles_n - 1) / g.tiles_n) + 15) & ~15;
+  g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn));
+  const size_t stage_bytes = (size_t)(2 * UMMA_KCH * TCG_BM * 4 + 2 * UMMA_KCH * g.bn * 4) * sizeof(float);
+  int stages = (int)(TCG_SMEM_BUDGET / stage_bytes);
+  stages = stages > TCG_MAX_STAGES ? TCG_MAX_STAGES : stages;
+  if (stages < 2) return TIGER_EINVAL;
+  g.stages = stages;
+  const size_t smem = stages * stage_bytes + 256;
+  dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)batch);
+  gemm_tf32x3_kernel<<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
   return tiger_launch_status();
 }
 

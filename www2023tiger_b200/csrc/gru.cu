@@ -1,185 +1,292 @@
-// K2  fused pending-message gather + GRUCell memory update.
+// K2  fused pending-message gather + GRUCell memory update on the tcgen05 tensor cores.
 // Reference: LastMessageAggregatorNoGradLastOnly.forward (message_modules.py:150-160) gathers
 // msg rows, TIGE.apply_messages (tiger.py:339-356) gathers the update-source memory rows and
 // GRUUpdater.forward (update_modules.py:30-37) runs nn.GRUCell (gate order r,z,n):
 //   r = s(Wir x + bir + Whr h + bhr)   z = s(Wiz x + biz + Whz h + bhz)
 //   n = tanh(Win x + bin + r*(Whn h + bhn))   h' = (h - n)*z + n
 //
-// fp32 FFMA tiled GEMM (parity tolerance 1e-5 rules out single-pass TF32): CTA tile 64 rows x
-// 32 hidden units x (3 gates + the separate Whn accumulator), 256 threads, thread tile 4 rows x
-// 2 units, K chunks of 32 double-buffered in shared memory with register-staged prefetch.
-// Rows are gathered straight from the node-indexed tables (no [O,M] staging copy in HBM).
+// One CTA = 128 gathered rows x U hidden units (U = 32): a [128 x 4U] fp32 accumulator in TMEM with
+// the column groups [ Win x | r | z | Whn h ].  The K loop runs over the message columns first
+// (x phase: one MMA group of N = 3U per k-step into [Win x | r | z], weight rows as stored in
+// weight_ih) and then over the state columns (h phase: N = 2U accumulating into [r | z] and N = U into
+// [Whn h], weight rows as stored in weight_hh), all in tf32x3 (umma.cuh) so the result keeps fp32
+// accuracy: three issuer warps, four partial accumulator sets of 4U columns = all 512 TMEM columns.
+// Rows are gathered straight from the node-indexed tables by the producer warps (no [O, M] staging copy
+// in HBM; 4 groups of 4 warps keep 4 stages of loads in flight); the same warps then run the gate
+// epilogue out of TMEM.  Weights are used in nn.GRUCell's own layout - no packed copy.
 #include "common.cuh"
+#include "umma.cuh"
 
-#define GRU_TM 64
-#define GRU_TJ 32
-#define GRU_KC 32
-#define GRU_THREADS 256
-#define GRU_APAD 4
+#define GRU_PRODUCER_WARPS 16
+#define GRU_THREADS ((GRU_PRODUCER_WARPS + UMMA_ISSUERS) * 32)
+#define GRU_BM 128
+#define GRU_U 32                       // hidden units per CTA (multiple of 16)
+#define GRU_WROWS (3 * GRU_U)          // weight rows per stage
+#define GRU_STAGES 6
+#define GRU_GROUPS 4                   // producer groups, each fills every 4th stage
+#define GRU_GROUP_WARPS (GRU_PRODUCER_WARPS / GRU_GROUPS)
+#define GRU_A_PLANE (UMMA_KCH * GRU_BM * 4)      // floats
+#define GRU_W_PLANE (UMMA_KCH * GRU_WROWS * 4)
+#define GRU_STAGE_FLOATS (2 * GRU_A_PLANE + 2 * GRU_W_PLANE)
+#define GRU_ACC_COLS (4 * GRU_U)       // one accumulator set: [ Win x | r | z | Whn h ]
+#define GRU_TMEM_COLS (UMMA_ACCS * GRU_ACC_COLS)   // 512: the four tf32x3 partial accumulators (umma.cuh)
+#define GRU_NA (GRU_BM / 8 / GRU_GROUP_WARPS)       // A warp-chunks per producer warp
+#define GRU_NW (GRU_WROWS / 8 / GRU_GROUP_WARPS)    // W warp-chunks per producer warp
+#define GRU_SMEM_BYTES (GRU_STAGES * GRU_STAGE_FLOATS * 4 + 2 * GRU_BM * 8 + 4 * GRU_U * 4 + 128)
 
-struct GruTile {
-  float a[2][GRU_TM][GRU_KC + GRU_APAD];
-  float w[2][GRU_KC][3 * GRU_TJ];
+struct GruArgs {
+  const int64_t* node_ids;
+  const int32_t* count;
+  int64_t n_rows;
+  const float* x_table;
+  int64_t x_stride;
+  const float* h_table;
+  int64_t h_stride;
+  int m_dim, d;
+  const float* w_ih;   // [3d][m_dim]
+  const float* w_hh;   // [3d][d]
+  const float* b_ih;
+  const float* b_hh;
+  float* h_new;
+  const float* msg_ts;
+  const float* check_mem_ts;
+  int check_equal;
+  uint32_t* err_flags;
+  int vec_x, vec_h, vec_wi, vec_wh;
 };
 
-// stage one K-chunk: 8 activation floats + 3 weight float4 per thread
-struct GruStage {
-  float a[8];
-  float4 w[3];
-};
+__global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArgs g) {
+  extern __shared__ __align__(128) unsigned char gru_smem[];
+  float* stage0 = reinterpret_cast<float*>(gru_smem);
+  const float** x_ptr = reinterpret_cast<const float**>(gru_smem + (size_t)GRU_STAGES * GRU_STAGE_FLOATS * 4);
+  const float** h_ptr = x_ptr + GRU_BM;
+  float* bias_s = reinterpret_cast<float*>(h_ptr + GRU_BM);   // [4][GRU_U]: b_r, b_z, b_in, b_hn
+  uint64_t* full = reinterpret_cast<uint64_t*>(bias_s + 4 * GRU_U);
+  uint64_t* empty = full + GRU_STAGES;
+  uint64_t* done = empty + GRU_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-__device__ __forceinline__ void gru_load_chunk(GruStage& st, const float* const* row_ptr, int k0, int kdim,
-                                               const float* __restrict__ wT, int64_t ldw, int dp, int j0,
-                                               int tid) {
-  const int lane = tid & 31, warp = tid >> 5;
-  const int k = k0 + lane;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float* rp = row_ptr[warp * 8 + i];
-    st.a[i] = (rp != nullptr && k < kdim) ? __ldg(rp + k) : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int f = tid + i * GRU_THREADS;  // 0..767 : 32 k x 24 float4
-    const int kk = f / 24, c4 = f % 24;
-    const int g = c4 >> 3, jj = (c4 & 7) << 2;
-    st.w[i] = (k0 + kk < kdim)
-                  ? __ldg(reinterpret_cast<const float4*>(wT + (int64_t)(k0 + kk) * ldw + g * dp + j0 + jj))
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-__device__ __forceinline__ void gru_store_chunk(const GruStage& st, GruTile& sm, int buf, int tid) {
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sm.a[buf][warp * 8 + i][lane] = st.a[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int f = tid + i * GRU_THREADS;
-    const int kk = f / 24, c4 = f % 24;
-    *reinterpret_cast<float4*>(&sm.w[buf][kk][c4 << 2]) = st.w[i];
-  }
-}
-
-// acc[g][i][c]: g = 0 (r), 1 (z), 2 (n-part of this phase)
-__device__ __forceinline__ void gru_compute_chunk(const GruTile& sm, int buf, int ty, int tx, float (&acc_r)[4][2],
-                                                  float (&acc_z)[4][2], float (&acc_n)[4][2]) {
-#pragma unroll
-  for (int kk = 0; kk < GRU_KC; kk += 4) {
-    float4 a[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&sm.a[buf][ty * 4 + i][kk]);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const float2 wr = *reinterpret_cast<const float2*>(&sm.w[buf][kk + s][tx * 2]);
-      const float2 wz = *reinterpret_cast<const float2*>(&sm.w[buf][kk + s][GRU_TJ + tx * 2]);
-      const float2 wn = *reinterpret_cast<const float2*>(&sm.w[buf][kk + s][2 * GRU_TJ + tx * 2]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float av = s == 0 ? a[i].x : (s == 1 ? a[i].y : (s == 2 ? a[i].z : a[i].w));
-        acc_r[i][0] = fmaf(av, wr.x, acc_r[i][0]);
-        acc_r[i][1] = fmaf(av, wr.y, acc_r[i][1]);
-        acc_z[i][0] = fmaf(av, wz.x, acc_z[i][0]);
-        acc_z[i][1] = fmaf(av, wz.y, acc_z[i][1]);
-        acc_n[i][0] = fmaf(av, wn.x, acc_n[i][0]);
-        acc_n[i][1] = fmaf(av, wn.y, acc_n[i][1]);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void gru_phase(GruTile& sm, const float* const* row_ptr, int kdim,
-                                          const float* __restrict__ wT, int64_t ldw, int dp, int j0, int tid,
-                                          int ty, int tx, float (&acc_r)[4][2], float (&acc_z)[4][2],
-                                          float (&acc_n)[4][2]) {
-  const int n_chunks = (kdim + GRU_KC - 1) / GRU_KC;
-  GruStage st;
-  gru_load_chunk(st, row_ptr, 0, kdim, wT, ldw, dp, j0, tid);
-  __syncthreads();  // previous phase finished reading both buffers
-  gru_store_chunk(st, sm, 0, tid);
-  __syncthreads();
-  for (int c = 0; c < n_chunks; ++c) {
-    const bool more = c + 1 < n_chunks;
-    if (more) gru_load_chunk(st, row_ptr, (c + 1) * GRU_KC, kdim, wT, ldw, dp, j0, tid);
-    gru_compute_chunk(sm, c & 1, ty, tx, acc_r, acc_z, acc_n);
-    if (more) gru_store_chunk(st, sm, (c + 1) & 1, tid);
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(GRU_THREADS)
-gru_update_kernel(const int64_t* __restrict__ node_ids, const int32_t* __restrict__ count, int64_t n_rows,
-                  const float* __restrict__ x_table, int64_t x_stride, const float* __restrict__ h_table,
-                  int64_t h_stride, int m_dim, int d, const float* __restrict__ wT_ih,
-                  const float* __restrict__ wT_hh, int64_t ldw, int dp, const float* __restrict__ b_ih,
-                  const float* __restrict__ b_hh, float* __restrict__ h_new, const float* __restrict__ msg_ts,
-                  const float* __restrict__ check_mem_ts, int check_equal, uint32_t* __restrict__ err_flags) {
-  __shared__ GruTile sm;
-  __shared__ const float* x_ptr[GRU_TM];
-  __shared__ const float* h_ptr[GRU_TM];
-  int64_t n = n_rows;
-  if (count != nullptr) {
-    const int64_t c = *count;
+  int64_t n = g.n_rows;
+  if (g.count != nullptr) {
+    const int64_t c = *g.count;
     n = c < n ? c : n;
   }
-  const int64_t row0 = (int64_t)blockIdx.y * GRU_TM;
+  const int64_t row0 = (int64_t)blockIdx.y * GRU_BM;
   if (row0 >= n) return;
-  const int j0 = blockIdx.x * GRU_TJ;
-  const int tid = threadIdx.x;
-  if (tid < GRU_TM) {
-    const int64_t r = row0 + tid;
-    const float* xp = nullptr;
-    const float* hp = nullptr;
-    if (r < n) {
-      const int64_t u = node_ids != nullptr ? node_ids[r] : r;
-      xp = x_table + u * x_stride;
-      hp = h_table + u * h_stride;
-      if (check_mem_ts != nullptr && blockIdx.x == 0 && err_flags != nullptr) {
-        const float mt = msg_ts[u], pt = check_mem_ts[u];
-        if (pt > mt) atomicOr(err_flags, TIGER_ERR_MSG_BEFORE_MEM);       // message_modules.py:157-159
-        if (check_equal && mt != pt) atomicOr(err_flags, TIGER_ERR_MSG_TS_MISMATCH);  // tiger.py:324-327
+  const int j0 = blockIdx.x * GRU_U;
+  const int d = g.d, m_dim = g.m_dim;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < GRU_BM) {
+    // rows beyond the count read the last valid row: they only feed accumulator rows nobody stores
+    int64_t r = row0 + tid;
+    const bool live = r < n;
+    r = live ? r : n - 1;
+    const int64_t u = g.node_ids != nullptr ? g.node_ids[r] : r;
+    x_ptr[tid] = g.x_table + u * g.x_stride;
+    h_ptr[tid] = g.h_table + u * g.h_stride;
+    if (live && g.check_mem_ts != nullptr && blockIdx.x == 0 && g.err_flags != nullptr) {
+      const float mt = g.msg_ts[u], pt = g.check_mem_ts[u];
+      if (pt > mt) atomicOr(g.err_flags, TIGER_ERR_MSG_BEFORE_MEM);                    // message_modules.py:157-159
+      if (g.check_equal && mt != pt) atomicOr(g.err_flags, TIGER_ERR_MSG_TS_MISMATCH);  // tiger.py:324-327
+    }
+  } else if (tid < GRU_BM + GRU_U) {
+    const int jj = tid - GRU_BM, j = j0 + jj;
+    const bool ok = j < d;
+    bias_s[jj] = ok ? g.b_ih[j] + g.b_hh[j] : 0.f;
+    bias_s[GRU_U + jj] = ok ? g.b_ih[d + j] + g.b_hh[d + j] : 0.f;
+    bias_s[2 * GRU_U + jj] = ok ? g.b_ih[2 * d + j] : 0.f;
+    bias_s[3 * GRU_U + jj] = ok ? g.b_hh[2 * d + j] : 0.f;
+  }
+  if (tid == GRU_PRODUCER_WARPS * 32) {
+    for (int s = 0; s < GRU_STAGES; ++s) {
+      mbar_init(full + s, GRU_GROUP_WARPS);
+      mbar_init(empty + s, UMMA_ISSUERS);
+    }
+    mbar_init(done, UMMA_ISSUERS);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, GRU_TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t taddr = *tmem_slot;
+  const int nbx = (m_dim + UMMA_BK - 1) / UMMA_BK, nbh = (d + UMMA_BK - 1) / UMMA_BK;
+  const int n_blocks = nbx + nbh;
+
+  if (warp < GRU_PRODUCER_WARPS) {
+    // ---------------- producers ----------------
+    // group `grp` fills stages grp, grp + GROUPS, ...: while one group waits for its loads the others
+    // convert / publish theirs, so GROUPS stages worth of global loads are always in flight
+    const int grp = warp / GRU_GROUP_WARPS, wg = warp % GRU_GROUP_WARPS;
+    UmmaChunks<GRU_NA> ca;
+    UmmaChunks<GRU_NW> cw;
+    // chunk geometry is phase-independent; only the pointers change between the x and the h phase
+    auto set_phase = [&](bool xph) {
+      const int kdim = xph ? m_dim : d;
+      const float* const* rows = xph ? x_ptr : h_ptr;
+      const float* __restrict__ wbase = xph ? g.w_ih : g.w_hh;
+#pragma unroll
+      for (int i = 0; i < GRU_NA; ++i) {
+        int row, kc;
+        umma_chunk_pos(wg + GRU_GROUP_WARPS * i, lane, row, kc);
+        ca.ptr[i] = rows[row] + kc * 4;
+        ca.soff[i] = (kc * GRU_BM + row) * 4;
+        ca.kq[i] = kc * 4;
+      }
+#pragma unroll
+      for (int i = 0; i < GRU_NW; ++i) {
+        int row, kc;
+        umma_chunk_pos(wg + GRU_GROUP_WARPS * i, lane, row, kc);
+        const int gi = row / GRU_U;
+        int j = j0 + row % GRU_U;
+        j = j < d ? j : d - 1;
+        // x phase: tile rows [n | r | z] ; h phase: [r | z | n]   (gate order in the weights: r, z, n)
+        const int gate = xph ? (gi == 0 ? 2 : gi - 1) : gi;
+        cw.ptr[i] = wbase + (int64_t)(gate * d + j) * kdim + kc * 4;
+        cw.soff[i] = (kc * GRU_WROWS + row) * 4;
+        cw.kq[i] = kc * 4;
+      }
+    };
+    float4 va[GRU_NA], vw[GRU_NW];
+    bool in_x = true;
+    set_phase(true);
+    auto load_block = [&](int blk) {
+      const bool xph = blk < nbx;
+      if (xph != in_x) {
+        set_phase(xph);
+        in_x = xph;
+      }
+      const int k0 = (xph ? blk : blk - nbx) * UMMA_BK;
+      umma_chunks_load(va, ca, k0, xph ? m_dim : d, (xph ? g.vec_x : g.vec_h) != 0);
+      umma_chunks_load(vw, cw, k0, xph ? m_dim : d, (xph ? g.vec_wi : g.vec_wh) != 0);
+    };
+    if (grp < n_blocks) load_block(grp);
+    for (int blk = grp; blk < n_blocks; blk += GRU_GROUPS) {
+      const int s = blk % GRU_STAGES;
+      float* a_hi = stage0 + (size_t)s * GRU_STAGE_FLOATS;
+      float* a_lo = a_hi + GRU_A_PLANE;
+      float* w_hi = a_lo + GRU_A_PLANE;
+      float* w_lo = w_hi + GRU_W_PLANE;
+      mbar_wait(empty + s, ((blk / GRU_STAGES) & 1) ^ 1);
+      umma_chunks_store(a_hi, a_lo, ca, va);
+      umma_chunks_store(w_hi, w_lo, cw, vw);
+      if (blk + GRU_GROUPS < n_blocks) load_block(blk + GRU_GROUPS);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + s);
+    }
+    // ---------------- gate epilogue ----------------
+    mbar_wait(done, 0);
+    tc_fence_after_sync();
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;
+    const bool row_ok = row0 + rl < n;
+    const float* hp = h_ptr[rl];
+    const uint32_t tl = taddr + ((uint32_t)(q * 32) << 16);
+    for (int c0 = (warp >> 2) * 16; c0 < GRU_U; c0 += 16 * (GRU_PRODUCER_WARPS / 4)) {
+      float an[16], ar[16], az[16], ah[16];
+      tmem_ld16(tl + (uint32_t)c0, an);
+      tmem_ld16(tl + (uint32_t)(GRU_U + c0), ar);
+      tmem_ld16(tl + (uint32_t)(2 * GRU_U + c0), az);
+      tmem_ld16(tl + (uint32_t)(3 * GRU_U + c0), ah);
+#pragma unroll
+      for (int jb = 1; jb < UMMA_ACCS; ++jb) {
+        float t[16];
+        const uint32_t tb = tl + (uint32_t)(jb * GRU_ACC_COLS + c0);
+        tmem_ld16(tb, t);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) an[e] += t[e];
+        tmem_ld16(tb + GRU_U, t);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ar[e] += t[e];
+        tmem_ld16(tb + 2 * GRU_U, t);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) az[e] += t[e];
+        tmem_ld16(tb + 3 * GRU_U, t);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ah[e] += t[e];
+      }
+      if (!row_ok) continue;
+      float* dst = g.h_new + (row0 + rl) * d;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = j0 + c0 + jj;
+        if (j < d) {
+          const float r = sigmoidf_acc(ar[jj] + bias_s[c0 + jj]);
+          const float z = sigmoidf_acc(az[jj] + bias_s[GRU_U + c0 + jj]);
+          const float nn = tanhf((an[jj] + bias_s[2 * GRU_U + c0 + jj]) + r * (ah[jj] + bias_s[3 * GRU_U + c0 + jj]));
+          const float h = hp[j];
+          dst[j] = (h - nn) * z + nn;
+        }
       }
     }
-    x_ptr[tid] = xp;
-    h_ptr[tid] = hp;
-  }
-  __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
-  float acc_r[4][2] = {}, acc_z[4][2] = {}, acc_in[4][2] = {}, acc_hn[4][2] = {};
-  gru_phase(sm, x_ptr, m_dim, wT_ih, ldw, dp, j0, tid, ty, tx, acc_r, acc_z, acc_in);
-  gru_phase(sm, h_ptr, d, wT_hh, ldw, dp, j0, tid, ty, tx, acc_r, acc_z, acc_hn);
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int j = j0 + tx * 2 + c;
-    if (j >= d) continue;
-    const float br = b_ih[j] + b_hh[j], bz = b_ih[d + j] + b_hh[d + j];
-    const float bin = b_ih[2 * d + j], bhn = b_hh[2 * d + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rl = ty * 4 + i;
-      if (row0 + rl >= n) continue;
-      const float r = sigmoidf_acc(acc_r[i][c] + br);
-      const float z = sigmoidf_acc(acc_z[i][c] + bz);
-      const float nn = tanhf((acc_in[i][c] + bin) + r * (acc_hn[i][c] + bhn));
-      const float h = h_ptr[rl][j];
-      h_new[(row0 + rl) * d + j] = (h - nn) * z + nn;
+  } else if (lane == 0) {
+    // ---------------- MMA issuers (one elected thread per role, see umma.cuh) ----------------
+    const int role = warp - GRU_PRODUCER_WARPS;
+    const UmmaRole r = umma_role(role, smem_addr_u32(stage0), GRU_STAGE_FLOATS * 4u, GRU_BM, GRU_WROWS, GRU_ACC_COLS);
+    const uint32_t id3 = umma_idesc_tf32(GRU_BM, 3 * GRU_U), id2 = umma_idesc_tf32(GRU_BM, 2 * GRU_U),
+                   id1 = umma_idesc_tf32(GRU_BM, GRU_U);
+    const uint32_t d_even = taddr + r.acc_even, d_odd = taddr + r.acc_odd;
+    int s = 0;
+    uint32_t ph = 0, a = r.a_lo, b = r.b_lo;
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      mbar_wait(full + s, ph);
+      tc_fence_after_sync();
+      const uint32_t a1 = a + r.a_kstep, b1 = b + r.b_kstep;
+      if (blk < nbx) {
+        // x phase: weight tile rows [n | r | z] -> columns [0, 3U)
+        umma_tf32_lo(d_even, a, b, id3, blk > 0 ? 1u : 0u);
+        umma_tf32_lo(d_odd, a1, b1, id3, (role == 2 && blk == 0) ? 0u : 1u);
+      } else {
+        // h phase: weight tile rows [r | z | n] -> [r | z] accumulate at column U, Whn h starts at column 3U
+        const uint32_t fresh = blk == nbx ? 0u : 1u;
+        umma_tf32_lo(d_even + GRU_U, a, b, id2, 1u);
+        umma_tf32_lo(d_even + 3 * GRU_U, a, b + 2 * GRU_U, id1, fresh);
+        umma_tf32_lo(d_odd + GRU_U, a1, b1, id2, 1u);
+        umma_tf32_lo(d_odd + 3 * GRU_U, a1, b1 + 2 * GRU_U, id1, role == 2 ? fresh : 1u);
+      }
+      umma_commit(empty + s);
+      a += r.stage_step;
+      b += r.stage_step;
+      if (++s == GRU_STAGES) {
+        s = 0;
+        ph ^= 1;
+        a = r.a_lo;
+        b = r.b_lo;
+      }
     }
+    umma_commit(done);
   }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(taddr, GRU_TMEM_COLS);
 }
 
 extern "C" int tiger_gru_update(const int64_t* node_ids, const int32_t* count, int64_t n_rows,
                                 const float* x_table, int64_t x_stride, const float* h_table, int64_t h_stride,
-                                int m_dim, int d, const float* wT_ih, const float* wT_hh, int64_t ldw,
-                                const float* b_ih, const float* b_hh, float* h_new, const float* msg_ts,
-                                const float* check_mem_ts, int check_equal, uint32_t* err_flags, void* stream) {
+                                int m_dim, int d, const float* w_ih, const float* w_hh, const float* b_ih,
+                                const float* b_hh, float* h_new, const float* msg_ts, const float* check_mem_ts,
+                                int check_equal, uint32_t* err_flags, void* stream) {
   if (n_rows < 0 || m_dim <= 0 || d <= 0) return TIGER_EINVAL;
-  const int dp = (d + 31) / 32 * 32;
-  if (ldw < 3 * (int64_t)dp || (ldw & 3) != 0 || (((uintptr_t)wT_ih | (uintptr_t)wT_hh) & 15) != 0)
-    return TIGER_EINVAL;
   if (n_rows == 0) return TIGER_OK;
-  dim3 grid((unsigned)(dp / GRU_TJ), (unsigned)((n_rows + GRU_TM - 1) / GRU_TM));
-  gru_update_kernel<<<grid, GRU_THREADS, 0, as_stream(stream)>>>(
-      node_ids, count, n_rows, x_table, x_stride, h_table, h_stride, m_dim, d, wT_ih, wT_hh, ldw, dp, b_ih, b_hh,
-      h_new, msg_ts, check_mem_ts, check_equal, err_flags);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gru_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRU_SMEM_BYTES) !=
+        cudaSuccess)
+      return TIGER_ECUDA;
+    configured = true;
+  }
+  GruArgs g;
+  g.node_ids = node_ids; g.count = count; g.n_rows = n_rows;
+  g.x_table = x_table; g.x_stride = x_stride; g.h_table = h_table; g.h_stride = h_stride;
+  g.m_dim = m_dim; g.d = d; g.w_ih = w_ih; g.w_hh = w_hh; g.b_ih = b_ih; g.b_hh = b_hh; g.h_new = h_new;
+  g.msg_ts = msg_ts; g.check_mem_ts = check_mem_ts; g.check_equal = check_equal; g.err_flags = err_flags;
+  g.vec_x = ((((uintptr_t)x_table) & 15) == 0 && (x_stride & 3) == 0) ? 1 : 0;
+  g.vec_h = ((((uintptr_t)h_table) & 15) == 0 && (h_stride & 3) == 0) ? 1 : 0;
+  g.vec_wi = ((((uintptr_t)w_ih) & 15) == 0 && (m_dim & 3) == 0) ? 1 : 0;
+  g.vec_wh = ((((uintptr_t)w_hh) & 15) == 0 && (d & 3) == 0) ? 1 : 0;
+  dim3 grid((unsigned)((d + GRU_U - 1) / GRU_U), (unsigned)((n_rows + GRU_BM - 1) / GRU_BM));
+  gru_update_kernel<<<grid, GRU_THREADS, GRU_SMEM_BYTES, as_stream(stream)>>>(g);
   return tiger_launch_status();
 }

@@ -214,27 +214,19 @@ def copy_pad(w: Tensor, out: Tensor, ld_out: int):
 
 
 class GruPack:
-    """k-major packs of nn.GRUCell weights: wT_ih [M][3*dp], wT_hh [d][3*dp] (dp = d rounded up to
-    32), gate g of hidden unit j at column g*dp + j."""
+    """nn.GRUCell parameters as the kernel reads them: the tensors as stored (weight_ih [3d, M],
+    weight_hh [3d, d], contiguous fp32) - no derived copy, so nothing goes stale when they train."""
 
     def __init__(self, weight_ih: Tensor, weight_hh: Tensor, bias_ih: Tensor, bias_hh: Tensor):
         self.d = weight_hh.shape[1]
         self.m_dim = weight_ih.shape[1]
-        self.dp = round_up(self.d, 32)
-        self.ldw = 3 * self.dp
-        dev = weight_ih.device
-        self.wT_ih = torch.zeros(self.m_dim * self.ldw, dtype=f32, device=dev)
-        self.wT_hh = torch.zeros(self.d * self.ldw, dtype=f32, device=dev)
         self.refresh(weight_ih, weight_hh, bias_ih, bias_hh)
 
     def refresh(self, weight_ih, weight_hh, bias_ih, bias_hh):
-        wi, wh = weight_ih.detach(), weight_hh.detach()
-        d, dp = self.d, self.dp
-        for g in range(3):
-            transpose_pad(wi[g * d:(g + 1) * d], self.wT_ih[g * dp:], self.ldw, dp)
-            transpose_pad(wh[g * d:(g + 1) * d], self.wT_hh[g * dp:], self.ldw, dp)
-        self.b_ih = bias_ih.detach().contiguous()
-        self.b_hh = bias_hh.detach().contiguous()
+        self.w_ih = weight_ih.detach().to(f32).contiguous()
+        self.w_hh = weight_hh.detach().to(f32).contiguous()
+        self.b_ih = bias_ih.detach().to(f32).contiguous()
+        self.b_hh = bias_hh.detach().to(f32).contiguous()
 
 
 def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_table: Tensor, n_rows: int,
@@ -246,7 +238,7 @@ def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_
     if out is None:
         out = _empty((n_rows, pack.d), f32, x_table)
     call('tiger_gru_update', ptr(node_ids), ptr(count), n_rows, ptr(x_table), x_table.stride(0), ptr(h_table),
-         h_table.stride(0), pack.m_dim, pack.d, ptr(pack.wT_ih), ptr(pack.wT_hh), pack.ldw, ptr(pack.b_ih),
+         h_table.stride(0), pack.m_dim, pack.d, ptr(pack.w_ih), ptr(pack.w_hh), ptr(pack.b_ih),
          ptr(pack.b_hh), ptr(out), ptr(msg_ts), ptr(check_mem_ts), int(check_equal), ptr(err_flags))
     return out
 
@@ -368,12 +360,13 @@ def static_restart(nids: Tensor, n: int, csr: DeviceCSR, left_emb: Tensor, right
 # ------------------------------------------------------------------------------------------
 def sgemm_nt(a: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, *, m_rows: Optional[int] = None,
              k_dim: Optional[int] = None, relu: bool = False, count: Optional[Tensor] = None,
-             rows_per_count: int = 1) -> Tensor:
-    """out[m, n] = act(a[m, :k] @ w[n, :k].T + bias[n]); a/w/out may be column slices of wider buffers."""
+             rows_per_count: int = 1, ffma_baseline: bool = False) -> Tensor:
+    """out[m, n] = act(a[m, :k] @ w[n, :k].T + bias[n]); a/w/out may be column slices of wider buffers.
+    Tensor cores (tf32x3); `ffma_baseline` selects the CUDA-core kernel kept for comparison only."""
     check_cuda_strided(a, w, out)
     m = a.shape[0] if m_rows is None else m_rows
     k = a.shape[1] if k_dim is None else k_dim
-    call('tiger_sgemm_nt', ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), m,
+    call('tiger_sgemm_ffma' if ffma_baseline else 'tiger_sgemm_nt', ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), m,
          ptr(count), rows_per_count, w.shape[0], k, int(relu))
     return out
 
