@@ -208,11 +208,12 @@ int tiger_gru_update(const int64_t* node_ids, const int32_t* count, int64_t n_ro
                      const float* msg_ts, const float* check_mem_ts, int check_equal,
                      uint32_t* err_flags, void* stream);
 
-/* temporal-attention parameters (device pointers): the reference's tensors as stored, plus one
- * derived pack.  E = 2d, C = 2d + de, hd = E / n_head. */
+/* temporal-attention parameters (device pointers): the reference's tensors as stored
+ * (temporal_embedding_fn.fns.0.*), plus one caller-allocated buffer for the folded weights.
+ * E = 2d, C = 2d + de, hd = E / n_head. */
 typedef struct {
   const float* wq;       /* [E][E]    mha_fn.q_proj_weight                                  */
-  const float* wk_fold;  /* [H][Cq][hdp] folded key projection made by tiger_attn_fold_keys */
+  const float* wk;       /* [E][C]    mha_fn.k_proj_weight                                  */
   const float* wv;       /* [E][C]    mha_fn.v_proj_weight                                  */
   const float* wo;       /* [E][E]    mha_fn.out_proj.weight                                */
   const float* fc1;      /* [d][E+d]  merger.fc1.weight                                     */
@@ -223,23 +224,23 @@ typedef struct {
   const float* fc2_b;    /* [d]                                                             */
   const float* time_w;   /* [d] time_encoder.basis_freq                                     */
   const float* time_b;   /* [d] time_encoder.phase                                          */
+  float* folded;         /* tiger_attn_fold_bytes() bytes, 16-byte aligned, filled by tiger_attn_fold */
 } tiger_attn_params;
 
-/* Folded key projection: out[h][c][j] = k_proj_weight[h*hd + j][c] for c < C, k_bias[h*hd + j] for
- * c == C, zero elsewhere; dims [n_head][Cq = roundup4(C+1)][hdp = roundup4(hd)].  With it
- * q_h . (Wk_h kv + bk_h) becomes (q_h [Wk_h | bk_h]) . [kv | 1]: one GEMM per batch instead of a key
- * projection per neighbor.  Re-run whenever k_proj_weight / in_proj_bias change. */
-int tiger_attn_fold_keys(const float* k_proj_weight, const float* k_bias, int d, int de, int n_head,
-                         float* out, void* stream);
+/* Folds the projections that are linear in the per-query vectors (exact by linearity, accumulated in
+ * double; see csrc/attention.cu):  Wqk_h = scale [Wk_h | bk_h]^T Wq_h,  bqk_h = scale [Wk_h | bk_h]^T bq_h,
+ * W2f = [W1a Wo_h Wv_h .. | W1b | W1a (Wo bv + bo)].  Re-run whenever one of the tensors above changes. */
+int64_t tiger_attn_fold_bytes(int d, int de, int n_head);
+int tiger_attn_fold(const tiger_attn_params* params, int d, int de, int n_head, void* stream);
 
 /* bytes of caller-provided, 16-byte aligned workspace for n_query queries */
 int64_t tiger_temporal_attention_work_bytes(int64_t n_query, int k, int d, int de, int n_head);
 
 /* a15 + a16  GraphEmbedding.compute_embedding_with_computation_graph (n_layers=1) +
  * TemporalAttention.forward (temporal_agg_modules.py:29-83,210-235), eval mode: gather (center + K
- * neighbors + edge rows) -> time encoding -> q projection -> folded single-query attention (scores
- * through Wk^T q, values through Wv applied to the softmax-pooled keys) -> out projection -> merger
- * MLP, as the launch sequence described in csrc/attention.cu.
+ * neighbors + edge rows) -> time encoding -> folded single-query attention (score weights through
+ * Wqk, masked softmax, pooled keys) -> folded value / out projection + merger MLP on the tensor
+ * cores, as the launch sequence described in csrc/attention.cu.
  * Node representations: row(u) = sel[u] >= 0 ? rows_b[sel[u]] : rows_a[u]
  *   fused engine : rows_a = right memory, rows_b = GRU output, sel = gru_row
  *   class surface: rows_a = NULL, rows_b = involved_node_reprs, sel = local_index

@@ -35,7 +35,8 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_transpose_pad': 'plllpll' + 'p',
     'tiger_copy_pad': 'plllpl' + 'p',
     'tiger_gru_update': 'ppl' + 'plpl' + 'ii' + 'pp' + 'ppp' + 'ppi' + 'p' + 'p',
-    'tiger_attn_fold_keys': 'ppiiip' + 'p',
+    'tiger_attn_fold_bytes': 'iii',
+    'tiger_attn_fold': 'piii' + 'p',
     'tiger_temporal_attention_work_bytes': 'liiii',
     'tiger_temporal_attention': 'ppll' + 'pppi' + 'pppi' + 'pp' + 'iii' + 'ppp' + 'p',
     'tiger_temporal_attention_dense': 'pppppp' + 'li' + 'iii' + 'ppp' + 'p',
@@ -88,7 +89,7 @@ def load() -> ctypes.CDLL:
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = [_KIND[c] for c in sig]
-        fn.restype = L if name.endswith('_work_bytes') else I
+        fn.restype = L if name.endswith('_bytes') else I
     _lib = lib
     return lib
 

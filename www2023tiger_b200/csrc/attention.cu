@@ -4,29 +4,29 @@
 // F.multi_head_attention_forward (need_weights branch) + MergeLayer (basic_modules.py:16-19).
 //
 // Math per query (h = head, hd = E / n_head, scale = sqrt(1/hd), E = 2d, C = 2d + de):
-//   q    = scale * (Wq [c | cos(b)] + bq)                       c = repr(center) + nf(center)
-//   qk_h = Wk_h^T q_h  (length C)      qb_h = q_h . bk_h        <- "folded" key projection
-//   s_hj = qk_h . kv_j + qb_h          kv_j = [repr(n_j)+nf | ef(e_j) | cos((t - t_j) w + b)]
-//   p_h  = softmax_j(s_hj) over unmasked slots
-//   o_h  = Wv_h (sum_j p_hj kv_j) + bv_h                         <- "folded" value projection
+//   q    = scale * (Wq [c | qt] + bq)                           c = repr(center) + nf(center), qt = cos(b)
+//   s_hj = q_h . (Wk_h kv_j + bk_h)        kv_j = [repr(n_j)+nf | ef(e_j) | cos((t - t_j) w + b)]
+//   p_h  = softmax_j(s_hj) over live slots
+//   o_h  = Wv_h (sum_j p_hj kv_j) + bv_h                         (sum_j p_hj = 1)
 //   out  = Wo [o_1 | o_2 ..] + bo ; 0 if every slot is padding
 //   z    = W2 relu(W1 [out | c] + b1) + b2
-// which equals the reference's softmax(q K^T) V exactly (linearity; sum_j p_hj = 1) and needs ~9x fewer
-// flops than projecting all K neighbors of every query.
+// All of it is linear in the per-query vectors except the softmax and the ReLU, so the weights are
+// folded once per parameter update (tiger_attn_fold, exact by linearity, accumulated in double):
+//   Wqk_h = scale [Wk_h | bk_h]^T Wq_h   ([C+1, E])   bqk_h = scale [Wk_h | bk_h]^T bq_h
+//       =>  [s-weights qk_h | qb_h] = Wqk_h [c | qt] + bqk_h ,  s_hj = qk_h . kv_j + qb_h
+//   W2f   = [ W1a Wo_1 Wv_1 | W1a Wo_2 Wv_2 | W1b | W1a (Wo bv + bo) ]   (W1 = [W1a | W1b])
+//       =>  hidden = relu(W2f [kvbar_1 | kvbar_2 | c | live] + b1) ,  live = 0 when every slot is padding
+// which needs ~12x fewer flops than projecting all K neighbors of every query and three GEMM
+// launches instead of six.
 //
 // Launch sequence (all queries of the batch at once; workspace provided by the caller):
-//   attn_prepare          gather center rows, query time code, all-padding flags
-//   sgemm_nt              q = scale * (XQ Wq^T + bq)
-//   sgemm_nt (batch = H)  [qk_h | qb_h] = q_h [Wk_h | bk_h]          (pre-folded key pack)
+//   attn_prepare          gather center rows: XQ = [c | qt], KVC[:, c] = c, KVC[:, live]
+//   sgemm_nt (tcgen05)    QKF = XQ Wqk^T + bqk                           [n, H (C+1)]
 //   attn_score_pool       one CTA per query: gather the K key rows once into shared memory
 //                         (memory / GRU-output rows, edge features, time code), scores, masked
-//                         softmax, pooled keys
-//   sgemm_nt (batch = H)  o_h = kvbar_h Wv_h^T + bv_h
-//   sgemm_nt              out = o Wo^T + bo, zeroed for all-padding queries
-//   sgemm_nt              hidden = relu([out | c] W1^T + b1)
-//   sgemm_nt              z = hidden W2^T + b2
-// The projections run as row-batched FFMA GEMMs over all 3B queries, so every weight element fetched
-// from L2 is used for 32-128 rows instead of 4, and the gather kernel keeps >= 32 warps per SM in flight.
+//                         softmax, pooled keys -> KVC[:, kvbar]
+//   sgemm_nt (tcgen05)    HID = relu(KVC W2f^T + b1)                    [n, d]
+//   sgemm_nt (tcgen05)    z = HID W2^T + b2                             [n, d]
 #include "common.cuh"
 
 extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw,
@@ -42,23 +42,25 @@ static inline int ru4(int x) { return (x + 3) & ~3; }
 
 struct AttDims {
   int d, de, K, H, E, C, hd;
-  int ld_xq, ld_q, Cq, ld_qkf, Cp, ld_kvb, ld_oh, ld_mo, ld_hid;
+  int ld_xq, Cq, ld_qkf, Cp, ld_kvc, off_c, off_live, ld_hid;
 };
 
 static AttDims att_dims(int d, int de, int k, int n_head) {
   AttDims a;
   a.d = d; a.de = de; a.K = k; a.H = n_head;
   a.E = 2 * d; a.C = 2 * d + de; a.hd = a.E / n_head;
-  a.ld_xq = ru4(a.E); a.ld_q = ru4(a.E);
+  a.ld_xq = ru4(a.E);
   a.Cq = ru4(a.C + 1); a.ld_qkf = n_head * a.Cq;
-  a.Cp = ru4(a.C); a.ld_kvb = n_head * a.Cp;
-  a.ld_oh = ru4(a.E); a.ld_mo = ru4(a.E + d); a.ld_hid = ru4(d);
+  a.Cp = ru4(a.C);
+  a.off_c = n_head * a.Cp;               // KVC row: [kvbar_0 .. kvbar_{H-1} | c | live | pad]
+  a.off_live = a.off_c + d;
+  a.ld_kvc = ru4(a.off_live + 1);
+  a.ld_hid = ru4(d);
   return a;
 }
 
 struct AttWork {
-  float *xq, *q, *qkf, *kvb, *oh, *mo, *hid;
-  uint8_t* invalid;
+  float *xq, *qkf, *kvc, *hid;
   int64_t total_floats;
 };
 
@@ -67,13 +69,9 @@ static AttWork att_work(const AttDims& a, int64_t n, float* base) {
   int64_t off = 0;
   auto take = [&](int64_t cnt) { float* p = base ? base + off : nullptr; off += (cnt + 3) & ~(int64_t)3; return p; };
   w.xq = take(n * a.ld_xq);
-  w.q = take(n * a.ld_q);
   w.qkf = take(n * a.ld_qkf);
-  w.kvb = take(n * a.ld_kvb);
-  w.oh = take(n * a.ld_oh);
-  w.mo = take(n * a.ld_mo);
+  w.kvc = take(n * a.ld_kvc);
   w.hid = take(n * a.ld_hid);
-  w.invalid = reinterpret_cast<uint8_t*>(take((n + 3) / 4));
   w.total_floats = off;
   return w;
 }
@@ -85,33 +83,86 @@ extern "C" int64_t tiger_temporal_attention_work_bytes(int64_t n_query, int k, i
 }
 
 // ------------------------------------------------------------------------------------------
-// parameter packing: folded key projection [H][Cq][hdp]
-//   row c < C : Wk[h*hd + j][c]     row C : bk[h*hd + j]     (other rows / j >= hd : 0)
+// parameter folding (once per parameter update)
 // ------------------------------------------------------------------------------------------
-__global__ void attn_fold_keys_kernel(const float* __restrict__ wk, const float* __restrict__ bk, int E, int C,
-                                      int H, int hd, int Cq, int hdp, float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)H * Cq * hdp;
-  if (i >= total) return;
-  const int j = (int)(i % hdp);
-  const int c = (int)((i / hdp) % Cq);
-  const int h = (int)(i / ((int64_t)hdp * Cq));
-  float v = 0.f;
-  if (j < hd) {
-    if (c < C) v = wk[(int64_t)(h * hd + j) * C + c];
-    else if (c == C) v = bk[h * hd + j];
-  }
-  out[i] = v;
+struct AttFold {
+  float *wqk, *bqk, *w2f, *wov, *bov;   // wqk [H*Cq][E], bqk [H*Cq], w2f [d][ld_kvc] ; temporaries wov [E][H*Cp], bov [E]
+  int64_t total_floats;
+};
+
+static AttFold att_fold(const AttDims& a, float* base) {
+  AttFold f;
+  int64_t off = 0;
+  auto take = [&](int64_t cnt) { float* p = base ? base + off : nullptr; off += (cnt + 3) & ~(int64_t)3; return p; };
+  f.wqk = take((int64_t)a.H * a.Cq * a.E);
+  f.bqk = take((int64_t)a.H * a.Cq);
+  f.w2f = take((int64_t)a.d * a.ld_kvc);
+  f.wov = take((int64_t)a.E * a.H * a.Cp);
+  f.bov = take(a.E);
+  f.total_floats = off;
+  return f;
 }
 
-extern "C" int tiger_attn_fold_keys(const float* k_proj_weight, const float* k_bias, int d, int de, int n_head,
-                                    float* out, void* stream) {
-  if (d <= 0 || de <= 0 || n_head <= 0 || (2 * d) % n_head != 0) return TIGER_EINVAL;
+extern "C" int64_t tiger_attn_fold_bytes(int d, int de, int n_head) {
+  if (d <= 0 || de <= 0 || n_head <= 0 || (2 * d) % n_head != 0) return -1;
   const AttDims a = att_dims(d, de, 1, n_head);
-  const int hdp = ru4(a.hd);
-  const int64_t total = (int64_t)n_head * a.Cq * hdp;
-  attn_fold_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
-      k_proj_weight, k_bias, a.E, a.C, n_head, a.hd, a.Cq, hdp, out);
+  return att_fold(a, nullptr).total_floats * (int64_t)sizeof(float);
+}
+
+// C[m * scm + n] = alpha * sum_k A[m * sam + k * sak] * B[k * sbk + n * sbn] (+ add[m]) ; double accumulation
+__global__ void attn_fold_mm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B,
+                                    int64_t sbk, int64_t sbn, float* __restrict__ C, int64_t scm, int M, int N, int K,
+                                    float alpha, const float* __restrict__ add) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) acc += (double)A[m * sam + k * sak] * (double)B[k * sbk + n * sbn];
+  acc *= (double)alpha;
+  if (add != nullptr) acc += (double)add[m];
+  C[m * scm + n] = (float)acc;
+}
+
+static void fold_mm(cudaStream_t st, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn,
+                    float* C, int64_t scm, int M, int N, int K, float alpha, const float* add) {
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)M);
+  attn_fold_mm_kernel<<<grid, 128, 0, st>>>(A, sam, sak, B, sbk, sbn, C, scm, M, N, K, alpha, add);
+}
+
+extern "C" int tiger_attn_fold(const tiger_attn_params* p, int d, int de, int n_head, void* stream) {
+  if (p == nullptr || p->folded == nullptr || d <= 0 || de <= 0 || n_head <= 0 || (2 * d) % n_head != 0)
+    return TIGER_EINVAL;
+  const AttDims a = att_dims(d, de, 1, n_head);
+  const AttFold f = att_fold(a, p->folded);
+  cudaStream_t st = as_stream(stream);
+  const int E = a.E, C = a.C, hd = a.hd, H = a.H;
+  const float scale = sqrtf(1.0f / (float)hd);
+  const float* bq = p->in_bias;
+  const float* bk = p->in_bias + E;
+  const float* bv = p->in_bias + 2 * E;
+  if (cudaMemsetAsync(p->folded, 0, (size_t)f.total_floats * sizeof(float), st) != cudaSuccess) return TIGER_ECUDA;
+  for (int h = 0; h < H; ++h) {
+    const float* wk_h = p->wk + (int64_t)h * hd * C;   // [hd][C]
+    const float* wq_h = p->wq + (int64_t)h * hd * E;   // [hd][E]
+    float* wqk_h = f.wqk + (int64_t)h * a.Cq * E;
+    float* bqk_h = f.bqk + (int64_t)h * a.Cq;
+    // rows j < C: scale * Wk_h^T Wq_h ; row C: scale * bk_h^T Wq_h
+    fold_mm(st, wk_h, 1, C, wq_h, E, 1, wqk_h, E, C, E, hd, scale, nullptr);
+    fold_mm(st, bk + h * hd, 0, 1, wq_h, E, 1, wqk_h + (int64_t)C * E, E, 1, E, hd, scale, nullptr);
+    fold_mm(st, wk_h, 1, C, bq + h * hd, 1, 0, bqk_h, 1, C, 1, hd, scale, nullptr);
+    fold_mm(st, bk + h * hd, 0, 1, bq + h * hd, 1, 0, bqk_h + C, 1, 1, 1, hd, scale, nullptr);
+    // Wov_h = Wo[:, h*hd:(h+1)*hd] Wv_h   [E][C]
+    fold_mm(st, p->wo + h * hd, E, 1, p->wv + (int64_t)h * hd * C, C, 1, f.wov + h * a.Cp, (int64_t)H * a.Cp, E, C, hd,
+            1.0f, nullptr);
+  }
+  // bov = Wo bv + bo
+  fold_mm(st, p->wo, E, 1, bv, 1, 0, f.bov, 1, E, 1, E, 1.0f, p->out_bias);
+  // W2f = [ W1a Wov | W1b | W1a bov ]
+  const int64_t ld1 = E + d;
+  fold_mm(st, p->fc1, ld1, 1, f.wov, (int64_t)H * a.Cp, 1, f.w2f, a.ld_kvc, d, H * a.Cp, E, 1.0f, nullptr);
+  if (cudaMemcpy2DAsync(f.w2f + a.off_c, (size_t)a.ld_kvc * sizeof(float), p->fc1 + E, (size_t)ld1 * sizeof(float),
+                        (size_t)d * sizeof(float), (size_t)d, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return TIGER_ECUDA;
+  fold_mm(st, p->fc1, ld1, 1, f.bov, 1, 0, f.w2f + a.off_live, a.ld_kvc, d, 1, E, 1.0f, nullptr);
   return tiger_launch_status();
 }
 
@@ -155,23 +206,23 @@ __device__ __forceinline__ const float* resolve_row(const AttArgs& a, int64_t u)
   return a.rows_a + u * a.dm.d;
 }
 
-// one warp per query: XQ = [c | time code of dt = 0], MO[:, E:E+d] = c, invalid flag
+// one warp per query: XQ = [c | time code of dt = 0], KVC[:, c] = c, KVC[:, live] = any live slot
 __global__ void __launch_bounds__(256) attn_prepare_kernel(const AttArgs a) {
   const int lane = lane_id();
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block();
   if (q >= a.n_query) return;
-  const int d = a.dm.d, K = a.dm.K, E = a.dm.E;
+  const int d = a.dm.d, K = a.dm.K;
   float* xq = a.w.xq + q * a.dm.ld_xq;
-  float* mo = a.w.mo + q * a.dm.ld_mo;
+  float* cc = a.w.kvc + q * a.dm.ld_kvc + a.dm.off_c;
   int any = 0;
   for (int j = lane; j < K; j += 32) any |= a.dense ? (a.pad[q * K + j] == 0) : (a.neigh_nids[q * K + j] != 0);
   any = __any_sync(TIGER_FULL_MASK, any);
-  if (lane == 0) a.w.invalid[q] = !any;
+  if (lane == 0) a.w.kvc[q * a.dm.ld_kvc + a.dm.off_live] = any ? 1.f : 0.f;
   if (a.dense) {
     for (int c = lane; c < d; c += 32) {
       const float v = a.qx[q * d + c];
       xq[c] = v;
-      mo[E + c] = v;
+      cc[c] = v;
       xq[d + c] = a.qt[q * d + c];
     }
   } else {
@@ -181,7 +232,7 @@ __global__ void __launch_bounds__(256) attn_prepare_kernel(const AttArgs a) {
     for (int c = lane; c < d; c += 32) {
       const float v = rp[c] + (nfp != nullptr ? nfp[c] : 0.f);
       xq[c] = v;
-      mo[E + c] = v;
+      cc[c] = v;
       xq[d + c] = time_enc(0.f, a.time_w[c], a.time_b[c]);
     }
   }
@@ -269,12 +320,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   }
   __syncthreads();
   // ---- pooled keys kvbar[h][c] = sum_j p[h][j] kv[j][c] ----
-  float* out = a.w.kvb + q * a.dm.ld_kvb;
-  for (int c = tid; c < C; c += ATT_THREADS) {
+  float* out = a.w.kvc + q * a.dm.ld_kvc;
+  for (int c = tid; c < Cp; c += ATT_THREADS) {   // columns C..Cp-1 are alignment padding: written as zeros
     float acc[ATT_MAXH];
 #pragma unroll
     for (int h = 0; h < ATT_MAXH; ++h) acc[h] = 0.f;
-    for (int j = 0; j < K; ++j) {
+    for (int j = 0; j < (c < C ? K : 0); ++j) {
       const float v = kv[j * Cp + c];        // padding slots hold garbage, but their weights are exactly 0
 #pragma unroll
       for (int h = 0; h < ATT_MAXH; ++h)
@@ -295,18 +346,13 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   void* s = (void*)st;
   a.time_w = p->time_w;
   a.time_b = p->time_b;
+  const AttFold f = att_fold(m, p->folded);
   attn_prepare_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
   if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
-  const float scale = sqrtf(1.0f / (float)m.hd);
-  const int hdp = ru4(m.hd);
   int rc;
-  // q = scale * (XQ Wq^T + bq)
-  rc = tiger_sgemm_nt_batched(a.w.xq, m.ld_xq, 0, p->wq, m.E, 0, p->in_bias, 0, a.w.q, m.ld_q, 0, 1, n, nullptr, 1,
-                              m.E, m.E, scale, 0, nullptr, s);
-  if (rc != TIGER_OK) return rc;
-  // [qk_h | qb_h] = q_h [Wk_h | bk_h]
-  rc = tiger_sgemm_nt_batched(a.w.q, m.ld_q, m.hd, p->wk_fold, hdp, (int64_t)m.Cq * hdp, nullptr, 0, a.w.qkf,
-                              m.ld_qkf, m.Cq, m.H, n, nullptr, 1, m.C + 1, m.hd, 1.0f, 0, nullptr, s);
+  // [qk_h | qb_h] = XQ Wqk^T + bqk
+  rc = tiger_sgemm_nt_batched(a.w.xq, m.ld_xq, 0, f.wqk, m.E, 0, f.bqk, 0, a.w.qkf, m.ld_qkf, 0, 1, n, nullptr, 1,
+                              m.H * m.Cq, m.E, 1.0f, 0, nullptr, s);
   if (rc != TIGER_OK) return rc;
   const size_t smem = ((size_t)m.K * m.Cp + (size_t)m.H * m.K) * sizeof(float);
   if (smem > 200 * 1024) return TIGER_EINVAL;
@@ -319,17 +365,9 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   }
   attn_score_pool_kernel<<<(unsigned)n, ATT_THREADS, smem, st>>>(a);
   if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
-  // o_h = kvbar_h Wv_h^T + bv_h
-  rc = tiger_sgemm_nt_batched(a.w.kvb, m.ld_kvb, m.Cp, p->wv, m.C, (int64_t)m.hd * m.C, p->in_bias + 2 * m.E, m.hd,
-                              a.w.oh, m.ld_oh, m.hd, m.H, n, nullptr, 1, m.hd, m.C, 1.0f, 0, nullptr, s);
-  if (rc != TIGER_OK) return rc;
-  // out = o Wo^T + bo (zero rows for all-padding queries) -> MO[:, :E]
-  rc = tiger_sgemm_nt_batched(a.w.oh, m.ld_oh, 0, p->wo, m.E, 0, p->out_bias, 0, a.w.mo, m.ld_mo, 0, 1, n, nullptr, 1,
-                              m.E, m.E, 1.0f, 0, a.w.invalid, s);
-  if (rc != TIGER_OK) return rc;
-  // hidden = relu([out | c] W1^T + b1) ; z = hidden W2^T + b2
-  rc = tiger_sgemm_nt_batched(a.w.mo, m.ld_mo, 0, p->fc1, m.E + m.d, 0, p->fc1_b, 0, a.w.hid, m.ld_hid, 0, 1, n,
-                              nullptr, 1, m.d, m.E + m.d, 1.0f, 1, nullptr, s);
+  // hidden = relu([kvbar | c | live] W2f^T + b1) ; z = hidden W2^T + b2
+  rc = tiger_sgemm_nt_batched(a.w.kvc, m.ld_kvc, 0, f.w2f, m.ld_kvc, 0, p->fc1_b, 0, a.w.hid, m.ld_hid, 0, 1, n,
+                              nullptr, 1, m.d, m.off_live + 1, 1.0f, 1, nullptr, s);
   if (rc != TIGER_OK) return rc;
   return tiger_sgemm_nt_batched(a.w.hid, m.ld_hid, 0, p->fc2, m.d, 0, p->fc2_b, 0, out, m.d, 0, 1, n, nullptr, 1, m.d,
                                 m.d, 1.0f, 0, nullptr, s);
@@ -337,7 +375,7 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
 
 static int attention_entry(AttArgs& a, int k, int d, int de, int n_head, const tiger_attn_params* params, float* out,
                            void* work, void* stream) {
-  if (params == nullptr || work == nullptr) return TIGER_EINVAL;
+  if (params == nullptr || params->folded == nullptr || work == nullptr) return TIGER_EINVAL;
   if (a.n_query < 0 || k <= 0 || d <= 0 || de <= 0 || n_head <= 0 || n_head > ATT_MAXH) return TIGER_EINVAL;
   if ((2 * d) % n_head != 0 || (((uintptr_t)work) & 15) != 0) return TIGER_EINVAL;
   if (a.n_query == 0) return TIGER_OK;

@@ -3,11 +3,13 @@
 // MergeLayer (basic_modules.py:16-19) on positive and negative pairs -> BCE-with-logits mean.
 //
 // One CTA scores SCORE_GP pairs.  The fc1 weights (k-major, L2 resident) are streamed once per CTA with
-// coalesced loads; the reduction dimension (2d) is split over two thread halves so that 2 * ceil32(d)
-// threads are busy, each keeping SCORE_GP accumulators in registers.
+// coalesced loads; the reduction dimension (2d) is split over SCORE_KS thread groups so that
+// SCORE_KS * ceil32(d) threads are busy, each keeping SCORE_GP accumulators in registers and 8 weight
+// loads in flight (the kernel is bound by the L2 latency of that stream, not by bandwidth or FMAs).
 #include "common.cuh"
 
-#define SCORE_GP 16  // pairs per CTA
+#define SCORE_GP 8   // pairs per CTA
+#define SCORE_KS 4   // split of the reduction dimension over thread groups
 
 __global__ void __launch_bounds__(1024)
 link_score_kernel(const float* __restrict__ h, int64_t batch, int d, int dp, const int64_t* __restrict__ src,
@@ -18,8 +20,8 @@ link_score_kernel(const float* __restrict__ h, int64_t batch, int d, int dp, con
                   float* __restrict__ loss, uint32_t* __restrict__ done_counter) {
   extern __shared__ __align__(16) float sm[];
   float* xin = sm;                             // [2d][GP]
-  float* part = xin + 2 * d * SCORE_GP;        // [dp][GP]  partial sums of the upper K half
-  float* red = part + dp * SCORE_GP;           // [warps][GP]
+  float* part = xin + 2 * d * SCORE_GP;        // [KS-1][dp][GP]  partial sums of the upper K parts
+  float* red = part + (SCORE_KS - 1) * dp * SCORE_GP;   // [warps][GP]
   __shared__ int s_flag[SCORE_GP][2];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
@@ -64,18 +66,20 @@ link_score_kernel(const float* __restrict__ h, int64_t batch, int d, int dp, con
     xin[c * SCORE_GP + g] = v;
   }
   __syncthreads();
-  // hidden layer: thread (half, n) accumulates K range [half*d, (half+1)*d) of output unit n
-  const int half = tid / dp, n = tid % dp;
+  // hidden layer: thread (part, n) accumulates K range [part * kper, (part + 1) * kper) of output unit n
+  const int kpart = tid / dp, n = tid % dp;
+  const int kper = (2 * d + SCORE_KS - 1) / SCORE_KS;
   float acc[SCORE_GP];
 #pragma unroll
   for (int g = 0; g < SCORE_GP; ++g) acc[g] = 0.f;
-  if (n < d && half < 2) {
-    const float* wcol = fc1T + (int64_t)half * d * ld + n;
-    const float* xs = xin + half * d * SCORE_GP;
-#pragma unroll 4
-    for (int c = 0; c < d; ++c) {
+  if (n < d) {
+    const int c0 = kpart * kper;
+    const int c1 = (c0 + kper) < 2 * d ? (c0 + kper) : 2 * d;
+    const float* wcol = fc1T + n;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) {
       const float w = __ldg(wcol + (int64_t)c * ld);
-      const float4* x4 = reinterpret_cast<const float4*>(xs + c * SCORE_GP);
+      const float4* x4 = reinterpret_cast<const float4*>(xin + c * SCORE_GP);
 #pragma unroll
       for (int q = 0; q < SCORE_GP / 4; ++q) {
         const float4 x = x4[q];
@@ -85,20 +89,24 @@ link_score_kernel(const float* __restrict__ h, int64_t batch, int d, int dp, con
         acc[4 * q + 3] = fmaf(w, x.w, acc[4 * q + 3]);
       }
     }
-    if (half == 1) {
+    if (kpart > 0) {
 #pragma unroll
-      for (int g = 0; g < SCORE_GP; ++g) part[n * SCORE_GP + g] = acc[g];
+      for (int g = 0; g < SCORE_GP; ++g) part[((kpart - 1) * dp + n) * SCORE_GP + g] = acc[g];
     }
   }
   __syncthreads();
   float out[SCORE_GP];
 #pragma unroll
   for (int g = 0; g < SCORE_GP; ++g) out[g] = 0.f;
-  if (half == 0 && n < d) {
+  if (kpart == 0 && n < d) {
     const float b = fc1_b[n], w2 = fc2_w[n];
 #pragma unroll
-    for (int g = 0; g < SCORE_GP; ++g)
-      out[g] = fmaxf(acc[g] + part[n * SCORE_GP + g] + b, 0.f) * w2;
+    for (int g = 0; g < SCORE_GP; ++g) {
+      float a = acc[g];
+#pragma unroll
+      for (int q = 1; q < SCORE_KS; ++q) a += part[((q - 1) * dp + n) * SCORE_GP + g];
+      out[g] = fmaxf(a + b, 0.f) * w2;
+    }
   }
 #pragma unroll
   for (int g = 0; g < SCORE_GP; ++g) {
@@ -140,14 +148,15 @@ extern "C" int tiger_link_score(const float* h, int64_t batch, int d, const int6
                                 const int64_t* neg, const int64_t* neigh_nids, int k, const float* hit_emb,
                                 const float* fc1T, const float* fc1_b, const float* fc2_w, const float* fc2_b,
                                 float* scores, float* loss, uint32_t* done_counter, void* stream) {
-  if (batch < 0 || d <= 0 || d > 512 || (hit_emb != nullptr && (neigh_nids == nullptr || k <= 0))) return TIGER_EINVAL;
+  if (batch < 0 || d <= 0 || d > 256 || (hit_emb != nullptr && (neigh_nids == nullptr || k <= 0))) return TIGER_EINVAL;
   if (loss != nullptr && done_counter == nullptr) return TIGER_EINVAL;
   if (batch == 0) return TIGER_OK;
   const int dp = (d + 31) / 32 * 32;
-  const int threads = 2 * dp;
+  const int threads = SCORE_KS * dp;
+  if (threads > 1024) return TIGER_EINVAL;
   const int ld = (d + 3) / 4 * 4;
-  const size_t smem = ((size_t)2 * d * SCORE_GP + (size_t)dp * SCORE_GP + (size_t)(threads / 32) * SCORE_GP + 32) *
-                      sizeof(float);
+  const size_t smem = ((size_t)2 * d * SCORE_GP + (size_t)(SCORE_KS - 1) * dp * SCORE_GP +
+                       (size_t)(threads / 32) * SCORE_GP + 32) * sizeof(float);
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     if (smem > 200 * 1024 ||

@@ -29,7 +29,7 @@ from ._lib import raise_on_err_flags
 from .ops import f32, f64, i32, i64, u8
 
 KERNELS_PER_STEP = {  # launches of our kernels per batch (for the bench `gpu_launches` field)
-    'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 8, 'select_latest': 1,
+    'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 5, 'select_latest': 1,
     'right_writeback': 1, 'store_messages': 2, 'left_writeback': 1, 'link_score': 1,
 }
 

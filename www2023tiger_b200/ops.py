@@ -245,21 +245,21 @@ def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_
 
 class AttnParamsC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
-                ('wq', 'wk_fold', 'wv', 'wo', 'fc1', 'fc2', 'in_bias', 'out_bias', 'fc1_b', 'fc2_b', 'time_w',
-                 'time_b')]
+                ('wq', 'wk', 'wv', 'wo', 'fc1', 'fc2', 'in_bias', 'out_bias', 'fc1_b', 'fc2_b', 'time_w', 'time_b',
+                 'folded')]
 
 
 class AttnPack:
     """TemporalAttention parameters for the kernels: the reference's tensors as stored plus the folded
-    key projection [H][Cq][hdp] (tiger_attn_fold_keys), and a workspace that grows on demand."""
+    weights (tiger_attn_fold: Wqk, bqk, W2f), and a workspace that grows on demand."""
 
     def __init__(self, d: int, de: int, device, n_head: int = 2):
         self.d, self.de, self.n_head = d, de, n_head
-        E, C = 2 * d, 2 * d + de
-        self.E, self.C = E, C
-        self.Cq = round_up(C + 1, 4)
-        self.hdp = round_up(E // n_head, 4)
-        self.wk_fold = torch.zeros(n_head * self.Cq * self.hdp, dtype=f32, device=device)
+        self.E, self.C = 2 * d, 2 * d + de
+        nbytes = _lib.load().tiger_attn_fold_bytes(d, de, n_head)
+        if nbytes <= 0:
+            raise _lib.TigerLibraryError(f'invalid attention dims d={d} de={de} heads={n_head}')
+        self.folded = torch.zeros(nbytes // 4, dtype=f32, device=device)
         self.struct = AttnParamsC()
         self._keep = None
         self._work = None
@@ -268,15 +268,14 @@ class AttnPack:
     def refresh(self, q_w, k_w, v_w, in_bias, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b, time_w, time_b):
         det = lambda t: t.detach().to(f32).contiguous()
         keep = [det(t) for t in (q_w, k_w, v_w, in_bias, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b, time_w, time_b)]
-        q_w, k_w, v_w, in_bias, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b, time_w, time_b = keep
         check_cuda(*keep)
-        call('tiger_attn_fold_keys', ptr(k_w), in_bias[self.E:].data_ptr(), self.d, self.de, self.n_head,
-             ptr(self.wk_fold))
         self._keep = keep
         s = self.struct
-        s.wq, s.wk_fold, s.wv, s.wo, s.fc1, s.fc2 = (t.data_ptr() for t in (q_w, self.wk_fold, v_w, out_w, fc1_w, fc2_w))
-        s.in_bias, s.out_bias, s.fc1_b, s.fc2_b, s.time_w, s.time_b = (t.data_ptr() for t in
-                                                                       (in_bias, out_b, fc1_b, fc2_b, time_w, time_b))
+        for name, t in zip(('wq', 'wk', 'wv', 'in_bias', 'wo', 'out_bias', 'fc1', 'fc1_b', 'fc2', 'fc2_b', 'time_w',
+                            'time_b'), keep):
+            setattr(s, name, t.data_ptr())
+        s.folded = self.folded.data_ptr()
+        call('tiger_attn_fold', self.byref(), self.d, self.de, self.n_head)
 
     def byref(self):
         return ctypes.addressof(self.struct)
@@ -285,7 +284,7 @@ class AttnPack:
         key = (n_query, k)
         if self._work is None or self._work_key is None or self._work_key[0] < n_query or self._work_key[1] != k:
             nbytes = _lib.load().tiger_temporal_attention_work_bytes(n_query, k, self.d, self.de, self.n_head)
-            self._work = torch.empty(nbytes, dtype=u8, device=self.wk_fold.device)
+            self._work = torch.empty(nbytes, dtype=u8, device=self.folded.device)
             self._work_key = key
         return self._work
 

@@ -38,7 +38,7 @@ class TemporalAttention(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in params)
         if self._pack is None or key != self._pack_key:
             dev = params[0].device
-            if self._pack is None or self._pack.wk_fold.device != dev:
+            if self._pack is None or self._pack.folded.device != dev:
                 self._pack = ops.AttnPack(self.nfeat_dim, self.efeat_dim, dev, self.n_head)
             if time_encoder is None:
                 zeros = torch.zeros(self.nfeat_dim, device=dev)
