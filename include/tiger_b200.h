@@ -193,17 +193,23 @@ int tiger_copy_pad(const float* w, int64_t rows, int64_t cols, int64_t ld_in, fl
  * Dense operators
  * ------------------------------------------------------------------------------------- */
 
+/* Gate-weight pack of nn.GRUCell for tiger_gru_update: weight_ih [3d][M] and weight_hh [3d][d] (as stored)
+ * split into tf32 head / tail planes and laid out as the shared-memory image of every pipeline stage
+ * (csrc/gru.cu).  Re-run whenever the weights change. */
+int64_t tiger_gru_pack_bytes(int m_dim, int d);
+int tiger_gru_pack(const float* w_ih, const float* w_hh, int m_dim, int d, float* out, void* stream);
+
 /* a6 + a13  LastMessageAggregatorNoGradLastOnly.forward gather + GRUUpdater.forward
  * (message_modules.py:150-160, update_modules.py:30-37 = nn.GRUCell, gates r,z,n):
  *   h_new[r,:] = GRUCell(x = msg rows, h = state rows)
  * node_ids==NULL: x/h are dense [n,M]/[n,d]; otherwise row r reads x_table[node_ids[r]] and
  * h_table[node_ids[r]].  count (device, may be NULL) overrides n_rows (n_rows stays the grid
- * bound).  w_ih [3d][M], w_hh [3d][d], b_ih, b_hh [3d]: nn.GRUCell's parameters as stored
- * (contiguous rows).  The gate GEMMs run on the tensor cores in tf32x3 (fp32-accurate).  Also
- * checks the message invariants of tiger.py:319-327 when check_mem_ts != NULL. */
+ * bound).  wpack: tiger_gru_pack output; b_ih, b_hh [3d] as stored.  The gate GEMMs run on the
+ * tensor cores in tf32x3 (fp32-accurate).  Also checks the message invariants of tiger.py:319-327
+ * when check_mem_ts != NULL. */
 int tiger_gru_update(const int64_t* node_ids, const int32_t* count, int64_t n_rows,
                      const float* x_table, int64_t x_stride, const float* h_table, int64_t h_stride,
-                     int m_dim, int d, const float* w_ih, const float* w_hh,
+                     int m_dim, int d, const float* wpack,
                      const float* b_ih, const float* b_hh, float* h_new,
                      const float* msg_ts, const float* check_mem_ts, int check_equal,
                      uint32_t* err_flags, void* stream);
@@ -321,6 +327,20 @@ int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t stride_a, const 
                            int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
                            int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
                            const uint8_t* row_zero, void* stream);
+
+/* Pre-split weight packs for the tensor-core GEMM: W [n_rows][k_dim] (row stride ldw) -> tf32 head / tail
+ * planes in the shared-memory image of each (column tile of bn rows, k-block) stage, so the kernel loads
+ * a stage of W with one TMA bulk copy.  row_map (device int32 [n_tiles*bn], may be NULL) selects the
+ * source row of every tile row (-1 = zeros).  bn: multiple of 16, <= 128 (tiger_gemm_pick_bn proposes
+ * one for an expected row count). */
+int tiger_gemm_pick_bn(int64_t m_rows, int n_cols, int batch);
+int64_t tiger_gemm_pack_bytes(int n_tiles, int k_dim, int bn);
+int tiger_gemm_pack_weight(const float* W, int64_t ldw, const int32_t* row_map, int n_rows, int k_dim, int bn,
+                           int n_tiles, float* out, void* stream);
+/* C = act(alpha * (A Wpack^T + bias)) with a pack of ceil(n_cols / bn) tiles */
+int tiger_sgemm_nt_packed(const float* A, int64_t lda, const float* wpack, int bn, const float* bias, float* C,
+                          int64_t ldc, int64_t m_rows, const int32_t* count, int64_t rows_per_count, int n_cols,
+                          int k_dim, float alpha, int relu, void* stream);
 
 /* FFMA (CUDA-core) implementation of the same two operators: the measured baseline the tensor-core
  * kernels are compared with in bench.py --micro and tests; never on the product path. */

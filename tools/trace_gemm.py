@@ -5,7 +5,8 @@ from www2023tiger_b200 import ops
 m, n, k = (int(x) for x in sys.argv[1:4])
 a, w, b = torch.randn(m, k, device='cuda'), torch.randn(n, k, device='cuda'), torch.randn(n, device='cuda')
 c = torch.empty(m, n, device='cuda')
+pk = ops.WeightPack(w, m_rows_hint=m)
 for i in range(3):
     print('--- launch', i, flush=True)
-    ops.sgemm_nt(a, w, b, c)
+    ops.sgemm_nt_packed(a, pk, b, c)
     torch.cuda.synchronize()

@@ -34,7 +34,9 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_left_writeback': 'pllp' + 'pip' + 'ppp' + 'p' + 'p',
     'tiger_transpose_pad': 'plllpll' + 'p',
     'tiger_copy_pad': 'plllpl' + 'p',
-    'tiger_gru_update': 'ppl' + 'plpl' + 'ii' + 'pp' + 'ppp' + 'ppi' + 'p' + 'p',
+    'tiger_gru_pack_bytes': 'ii',
+    'tiger_gru_pack': 'ppiip' + 'p',
+    'tiger_gru_update': 'ppl' + 'plpl' + 'ii' + 'p' + 'ppp' + 'ppi' + 'p' + 'p',
     'tiger_attn_fold_bytes': 'iii',
     'tiger_attn_fold': 'piii' + 'p',
     'tiger_temporal_attention_work_bytes': 'liiii',
@@ -45,6 +47,10 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
     'tiger_sgemm_nt': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
     'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
+    'tiger_gemm_pick_bn': 'lii',
+    'tiger_gemm_pack_bytes': 'iii',
+    'tiger_gemm_pack_weight': 'plpiiiip' + 'p',
+    'tiger_sgemm_nt_packed': 'plpippllpliifi' + 'p',
     'tiger_sgemm_ffma': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
     'tiger_sgemm_ffma_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_seq_attn_pool': 'plpp' + 'pli' + 'iip' + 'p',

@@ -35,8 +35,18 @@ extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t strid
                                       const int32_t* count, int64_t rows_per_count, int n_cols, int k_dim,
                                       float alpha, int relu, const uint8_t* row_zero, void* stream);
 
+extern "C" int64_t tiger_gemm_pack_bytes(int n_tiles, int k_dim, int bn);
+extern "C" int tiger_gemm_pack_weight(const float* W, int64_t ldw, const int32_t* row_map, int n_rows, int k_dim,
+                                      int bn, int n_tiles, float* out, void* stream);
+extern "C" int tiger_sgemm_nt_packed(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
+                                     float* C, int64_t ldc, int64_t m_rows, const int32_t* count,
+                                     int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
+                                     void* stream);
+
 #define ATT_MAXH 8
 #define ATT_THREADS 128
+#define ATT_BN_QK 64   // column tile of the Wqk pack: H (C+1) ~ 1000 columns -> ~17 tiles per 128 queries
+#define ATT_BN_D 32    // column tile of the W2f / W2 packs: d columns -> ~6 tiles per 128 queries
 
 static inline int ru4(int x) { return (x + 3) & ~3; }
 
@@ -87,6 +97,8 @@ extern "C" int64_t tiger_temporal_attention_work_bytes(int64_t n_query, int k, i
 // ------------------------------------------------------------------------------------------
 struct AttFold {
   float *wqk, *bqk, *w2f, *wov, *bov;   // wqk [H*Cq][E], bqk [H*Cq], w2f [d][ld_kvc] ; temporaries wov [E][H*Cp], bov [E]
+  float *pk_wqk, *pk_w2f, *pk_fc2;      // tf32 head / tail packs of wqk, w2f and merger.fc2 for the tensor-core GEMM
+  int t_qk, t_d;                        // column tiles of the packs
   int64_t total_floats;
 };
 
@@ -99,6 +111,11 @@ static AttFold att_fold(const AttDims& a, float* base) {
   f.w2f = take((int64_t)a.d * a.ld_kvc);
   f.wov = take((int64_t)a.E * a.H * a.Cp);
   f.bov = take(a.E);
+  f.t_qk = (a.H * a.Cq + ATT_BN_QK - 1) / ATT_BN_QK;
+  f.t_d = (a.d + ATT_BN_D - 1) / ATT_BN_D;
+  f.pk_wqk = take(tiger_gemm_pack_bytes(f.t_qk, a.E, ATT_BN_QK) / 4);
+  f.pk_w2f = take(tiger_gemm_pack_bytes(f.t_d, a.off_live + 1, ATT_BN_D) / 4);
+  f.pk_fc2 = take(tiger_gemm_pack_bytes(f.t_d, a.d, ATT_BN_D) / 4);
   f.total_floats = off;
   return f;
 }
@@ -163,7 +180,12 @@ extern "C" int tiger_attn_fold(const tiger_attn_params* p, int d, int de, int n_
                         (size_t)d * sizeof(float), (size_t)d, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
     return TIGER_ECUDA;
   fold_mm(st, p->fc1, ld1, 1, f.bov, 1, 0, f.w2f + a.off_live, a.ld_kvc, d, 1, E, 1.0f, nullptr);
-  return tiger_launch_status();
+  if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
+  int rc = tiger_gemm_pack_weight(f.wqk, E, nullptr, H * a.Cq, E, ATT_BN_QK, f.t_qk, f.pk_wqk, stream);
+  if (rc != TIGER_OK) return rc;
+  rc = tiger_gemm_pack_weight(f.w2f, a.ld_kvc, nullptr, d, a.off_live + 1, ATT_BN_D, f.t_d, f.pk_w2f, stream);
+  if (rc != TIGER_OK) return rc;
+  return tiger_gemm_pack_weight(p->fc2, d, nullptr, d, d, ATT_BN_D, f.t_d, f.pk_fc2, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -351,8 +373,8 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
   int rc;
   // [qk_h | qb_h] = XQ Wqk^T + bqk
-  rc = tiger_sgemm_nt_batched(a.w.xq, m.ld_xq, 0, f.wqk, m.E, 0, f.bqk, 0, a.w.qkf, m.ld_qkf, 0, 1, n, nullptr, 1,
-                              m.H * m.Cq, m.E, 1.0f, 0, nullptr, s);
+  rc = tiger_sgemm_nt_packed(a.w.xq, m.ld_xq, f.pk_wqk, ATT_BN_QK, f.bqk, a.w.qkf, m.ld_qkf, n, nullptr, 1, m.H * m.Cq,
+                             m.E, 1.0f, 0, s);
   if (rc != TIGER_OK) return rc;
   const size_t smem = ((size_t)m.K * m.Cp + (size_t)m.H * m.K) * sizeof(float);
   if (smem > 200 * 1024) return TIGER_EINVAL;
@@ -366,11 +388,11 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   attn_score_pool_kernel<<<(unsigned)n, ATT_THREADS, smem, st>>>(a);
   if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
   // hidden = relu([kvbar | c | live] W2f^T + b1) ; z = hidden W2^T + b2
-  rc = tiger_sgemm_nt_batched(a.w.kvc, m.ld_kvc, 0, f.w2f, m.ld_kvc, 0, p->fc1_b, 0, a.w.hid, m.ld_hid, 0, 1, n,
-                              nullptr, 1, m.d, m.off_live + 1, 1.0f, 1, nullptr, s);
+  rc = tiger_sgemm_nt_packed(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, p->fc1_b, a.w.hid, m.ld_hid, n, nullptr, 1, m.d,
+                             m.off_live + 1, 1.0f, 1, s);
   if (rc != TIGER_OK) return rc;
-  return tiger_sgemm_nt_batched(a.w.hid, m.ld_hid, 0, p->fc2, m.d, 0, p->fc2_b, 0, out, m.d, 0, 1, n, nullptr, 1, m.d,
-                                m.d, 1.0f, 0, nullptr, s);
+  return tiger_sgemm_nt_packed(a.w.hid, m.ld_hid, f.pk_fc2, ATT_BN_D, p->fc2_b, out, m.d, n, nullptr, 1, m.d, m.d, 1.0f,
+                               0, s);
 }
 
 static int attention_entry(AttArgs& a, int k, int d, int de, int n_head, const tiger_attn_params* params, float* out,

@@ -38,7 +38,7 @@
 #endif
 
 #define TCG_PRODUCER_WARPS 16
-#define TCG_THREADS ((TCG_PRODUCER_WARPS + UMMA_ISSUERS) * 32)
+#define TCG_THREADS ((TCG_PRODUCER_WARPS + UMMA_ISSUERS + 1) * 32)   // + the TMA warp
 #define TCG_BM 128
 #define TCG_GROUPS 4                                    // producer groups, each fills every 4th stage
 #define TCG_GROUP_WARPS (TCG_PRODUCER_WARPS / TCG_GROUPS)
@@ -51,6 +51,8 @@
 struct GemmArgs {
   const float* A;
   const float* W;
+  const float* wpack;    // pre-split weight pack (tiger_gemm_pack_weight) or NULL: convert W in the kernel
+  int64_t stride_wpack;
   const float* bias;
   float* C;
   const uint8_t* row_zero;
@@ -66,6 +68,7 @@ struct GemmArgs {
   uint32_t tmem_cols;
 };
 
+template <bool PACKED>
 __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmArgs g) {
   extern __shared__ __align__(128) unsigned char tcg_smem[];
   const int BN = g.bn, S = g.stages;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == TCG_PRODUCER_WARPS * 32) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full + s, TCG_GROUP_WARPS);
+      mbar_init(full + s, TCG_GROUP_WARPS + (PACKED ? 1 : 0));
       mbar_init(empty + s, UMMA_ISSUERS);
     }
     mbar_init(done, UMMA_ISSUERS);
@@ -120,8 +123,9 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     // group `grp` fills stages grp, grp + GROUPS, ...: while one group waits for its loads the others
     // convert / publish theirs, so GROUPS stages worth of global loads are always in flight
     const int grp = warp / TCG_GROUP_WARPS, wg = warp % TCG_GROUP_WARPS;
+    constexpr int NW = PACKED ? 1 : TCG_NW;   // the packed variant moves no W chunks (placeholder of 1, never owned)
     UmmaChunks<TCG_NA> ca;
-    UmmaChunks<TCG_NW> cw;
+    UmmaChunks<NW> cw;
 #pragma unroll
     for (int i = 0; i < TCG_NA; ++i) {
       int row, kc;
@@ -133,22 +137,27 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       ca.kq[i] = kc * 4;
     }
 #pragma unroll
-    for (int i = 0; i < TCG_NW; ++i) {
+    for (int i = 0; i < NW; ++i) {
       const int wc = wg + TCG_GROUP_WARPS * i;
       int row, kc;
       umma_chunk_pos(wc, lane, row, kc);
       int n = n0 + row;
       n = n < g.N ? n : g.N - 1;
       cw.ptr[i] = W + (int64_t)n * g.ldw + kc * 4;
-      cw.soff[i] = wc < (BN >> 3) ? (kc * BN + row) * 4 : -1;
+      cw.soff[i] = (wc < (BN >> 3) && !PACKED) ? (kc * BN + row) * 4 : -1;
       cw.kq[i] = kc * 4;
     }
-    float4 va[TCG_NA], vw[TCG_NW];
-    if (grp < n_blocks) {
-      umma_chunks_load(va, ca, grp * UMMA_BK, g.K, g.vec_a != 0);
-      umma_chunks_load(vw, cw, grp * UMMA_BK, g.K, g.vec_w != 0);
-    }
-    for (int blk = grp; blk < n_blocks; blk += TCG_GROUPS) {
+    // two register sets per thread: the loads of this group's next two stages are in flight while the
+    // current one is converted and published (the proxy fence would otherwise wait for a stage's loads
+    // right after they were issued)
+    float4 va0[TCG_NA], vw0[NW], va1[TCG_NA], vw1[NW];
+    auto load = [&](float4 (&va)[TCG_NA], float4 (&vw)[NW], int blk) {
+      if (blk < n_blocks) {
+        umma_chunks_load(va, ca, blk * UMMA_BK, g.K, g.vec_a != 0);
+        if constexpr (!PACKED) umma_chunks_load(vw, cw, blk * UMMA_BK, g.K, g.vec_w != 0);
+      }
+    };
+    auto publish = [&](const float4 (&va)[TCG_NA], const float4 (&vw)[NW], int blk) {
       const int s = blk % S;
       float* a_hi = stage0 + (size_t)s * stage_floats;
       float* a_lo = a_hi + a_plane;
@@ -157,17 +166,22 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       mbar_wait(empty + s, ((blk / S) & 1) ^ 1);
       TRACE_MARK();
       umma_chunks_store(a_hi, a_lo, ca, va);
-      umma_chunks_store(w_hi, w_lo, cw, vw);
+      if constexpr (!PACKED) umma_chunks_store(w_hi, w_lo, cw, vw);
       TRACE_MARK();
-      const int nxt = blk + TCG_GROUPS;
-      if (nxt < n_blocks) {
-        umma_chunks_load(va, ca, nxt * UMMA_BK, g.K, g.vec_a != 0);
-        umma_chunks_load(vw, cw, nxt * UMMA_BK, g.K, g.vec_w != 0);
-      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
       TRACE_MARK();
+    };
+    load(va0, vw0, grp);
+    load(va1, vw1, grp + TCG_GROUPS);
+    for (int blk = grp; blk < n_blocks; blk += 2 * TCG_GROUPS) {
+      publish(va0, vw0, blk);
+      load(va0, vw0, blk + 2 * TCG_GROUPS);
+      if (blk + TCG_GROUPS < n_blocks) {
+        publish(va1, vw1, blk + TCG_GROUPS);
+        load(va1, vw1, blk + 3 * TCG_GROUPS);
+      }
     }
     // ---------------- epilogue ----------------
     mbar_wait(done, 0);
@@ -208,21 +222,41 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
           if (nb + j < g.N) dst[j] = v[j];
       }
     }
-  } else if (lane == 0) {
+  } else if (warp == TCG_PRODUCER_WARPS + UMMA_ISSUERS) {
+    // ---------------- TMA warp: one bulk copy per stage brings both planes of the weight tile ----------------
+    if (lane == 0 && PACKED) {
+      const uint32_t bytes = (uint32_t)UMMA_PACK_STAGE_FLOATS(BN) * 4u;
+      const float* src = g.wpack + b * g.stride_wpack +
+                         (int64_t)(blockIdx.x % g.tiles_n) * n_blocks * UMMA_PACK_STAGE_FLOATS(BN);
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        const int s = blk % S;
+        mbar_wait(empty + s, ((blk / S) & 1) ^ 1);
+        mbar_arrive_expect_tx(full + s, bytes);
+        tma_bulk_load(stage0 + (size_t)s * stage_floats + 2 * a_plane, src + (int64_t)blk * UMMA_PACK_STAGE_FLOATS(BN),
+                      bytes, full + s);
+      }
+    }
+  } else {
     // ---------------- MMA issuers (one elected thread per role, see umma.cuh) ----------------
-    const int role = warp - TCG_PRODUCER_WARPS;
+    // The whole warp runs the loop so that every operand stays warp-uniform; only the tcgen05 instructions
+    // are issued by the elected lane.
+    const int role = uniform_warp_idx() - TCG_PRODUCER_WARPS;
     const UmmaRole r = umma_role(role, smem_addr_u32(stage0), (uint32_t)stage_floats * 4u, TCG_BM, BN, (uint32_t)BN);
     const uint32_t idesc = umma_idesc_tf32(TCG_BM, BN);
-    const uint32_t d_even = taddr + r.acc_even, d_odd = taddr + r.acc_odd;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
+    const uint32_t d_even = tbase + r.acc_even, d_odd = tbase + r.acc_odd;
     int s = 0;
     uint32_t ph = 0, a = r.a_lo, b = r.b_lo;
     for (int blk = 0; blk < n_blocks; ++blk) {
       mbar_wait(full + s, ph);
       tc_fence_after_sync();
       TRACE_MARK();
-      umma_tf32_lo(d_even, a, b, idesc, blk > 0 ? 1u : 0u);
-      umma_tf32_lo(d_odd, a + r.a_kstep, b + r.b_kstep, idesc, (role == 2 && blk == 0) ? 0u : 1u);
-      umma_commit(empty + s);
+      if (elect_one()) {
+        umma_tf32_lo(d_even, a, b, idesc, blk > 0 ? 1u : 0u);
+        umma_tf32_lo(d_odd, a + r.a_kstep, b + r.b_kstep, idesc, (role == 2 && blk == 0) ? 0u : 1u);
+        umma_commit(empty + s);
+      }
+      __syncwarp();
       TRACE_MARK();
       a += r.stage_step;
       b += r.stage_step;
@@ -233,7 +267,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
         b = r.b_lo;
       }
     }
-    umma_commit(done);
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
   }
   TRACE_MARK();
 #ifdef TIGER_TRACE
@@ -246,46 +281,111 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
 
 static int g_gemm_sms = 0;
 
-extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw,
-                                      int64_t stride_w, const float* bias, int64_t stride_bias, float* C,
-                                      int64_t ldc, int64_t stride_c, int batch, int64_t m_rows,
-                                      const int32_t* count, int64_t rows_per_count, int n_cols, int k_dim,
-                                      float alpha, int relu, const uint8_t* row_zero, void* stream) {
-  if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldw < k_dim || ldc < n_cols)
+// pack kernel: one thread per (tile, k-block, kc, row)
+__global__ void gemm_pack_weight_kernel(const float* __restrict__ W, int64_t ldw, const int32_t* __restrict__ row_map,
+                                        int n_rows, int k_dim, int bn, int tiles, int n_kb, int vec_ok,
+                                        float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)tiles * n_kb * UMMA_KCH * bn;
+  if (i >= total) return;
+  const int r = (int)(i % bn);
+  const int kc = (int)((i / bn) % UMMA_KCH);
+  const int kb = (int)((i / ((int64_t)bn * UMMA_KCH)) % n_kb);
+  const int t = (int)(i / ((int64_t)bn * UMMA_KCH * n_kb));
+  const int row = row_map != nullptr ? row_map[(int64_t)t * bn + r] : t * bn + r;
+  const int k = kb * UMMA_BK + kc * 4;
+  const float4 v = umma_load_chunk((row >= 0 && row < n_rows) ? W + (int64_t)row * ldw : nullptr, k, k_dim, vec_ok != 0);
+  float4 h, l;
+  tf32_split(v, h, l);
+  float* stage = out + ((int64_t)t * n_kb + kb) * UMMA_PACK_STAGE_FLOATS(bn);
+  *reinterpret_cast<float4*>(stage + (kc * bn + r) * 4) = h;
+  *reinterpret_cast<float4*>(stage + UMMA_KCH * bn * 4 + (kc * bn + r) * 4) = l;
+}
+
+extern "C" int64_t tiger_gemm_pack_bytes(int n_tiles, int k_dim, int bn) {
+  if (n_tiles <= 0 || k_dim <= 0 || bn < 16 || bn > TCG_MAX_BN || (bn & 15) != 0) return -1;
+  const int64_t n_kb = (k_dim + UMMA_BK - 1) / UMMA_BK;
+  return (int64_t)n_tiles * n_kb * UMMA_PACK_STAGE_FLOATS(bn) * (int64_t)sizeof(float);
+}
+
+extern "C" int tiger_gemm_pack_weight(const float* W, int64_t ldw, const int32_t* row_map, int n_rows, int k_dim,
+                                      int bn, int n_tiles, float* out, void* stream) {
+  if (W == nullptr || out == nullptr || tiger_gemm_pack_bytes(n_tiles, k_dim, bn) < 0 || n_rows <= 0 || ldw < k_dim ||
+      (((uintptr_t)out) & 15) != 0)
     return TIGER_EINVAL;
-  if (m_rows == 0) return TIGER_OK;
+  const int n_kb = (k_dim + UMMA_BK - 1) / UMMA_BK;
+  const int64_t total = (int64_t)n_tiles * n_kb * UMMA_KCH * bn;
+  const int vec_ok = ((((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0) ? 1 : 0;
+  gemm_pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      W, ldw, row_map, n_rows, k_dim, bn, n_tiles, n_kb, vec_ok, out);
+  return tiger_launch_status();
+}
+
+// column tile width the packed entry point expects for a weight of n_cols rows used with about m_rows
+// activation rows: the widest of 128/64/32 that still yields about one CTA per SM, then balanced
+static int gemm_pick_bn(int64_t m_rows, int n_cols, int batch, int sms) {
+  const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
+  int bn = 32;
+  for (int cand = TCG_MAX_BN; cand >= 32; cand >>= 1) {
+    const int64_t tiles = tiles_m * ((n_cols + cand - 1) / cand) * batch;
+    if (tiles >= (3 * (int64_t)sms) / 4 || cand == 32) {
+      bn = cand;
+      break;
+    }
+  }
+  const int tiles_n = (n_cols + bn - 1) / bn;
+  return (((n_cols + tiles_n - 1) / tiles_n) + 15) & ~15;
+}
+
+static int gemm_sms() {
   if (g_gemm_sms == 0) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TCG_SMEM_BUDGET + 256) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TCG_SMEM_BUDGET + 256) != cudaSuccess)
-      return TIGER_ECUDA;
+      return -1;
     g_gemm_sms = sms;
   }
+  return g_gemm_sms;
+}
+
+extern "C" int tiger_gemm_pick_bn(int64_t m_rows, int n_cols, int batch) {
+  const int sms = gemm_sms();
+  if (sms < 0 || m_rows <= 0 || n_cols <= 0 || batch <= 0) return TIGER_EINVAL;
+  return gemm_pick_bn(m_rows, n_cols, batch, sms);
+}
+
+static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw, int64_t stride_w,
+                       const float* wpack, int64_t stride_wpack, int bn_pack, const float* bias, int64_t stride_bias,
+                       float* C, int64_t ldc, int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
+                       int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu, const uint8_t* row_zero,
+                       void* stream) {
+  if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldc < n_cols) return TIGER_EINVAL;
+  if (wpack == nullptr && (W == nullptr || ldw < k_dim)) return TIGER_EINVAL;
+  if (wpack != nullptr && (bn_pack < 16 || bn_pack > TCG_MAX_BN || (bn_pack & 15) != 0 || (((uintptr_t)wpack) & 15) != 0 ||
+                           (stride_wpack & 3) != 0))
+    return TIGER_EINVAL;
+  if (m_rows == 0) return TIGER_OK;
+  const int sms = gemm_sms();
+  if (sms < 0) return TIGER_ECUDA;
   GemmArgs g;
-  g.A = A; g.W = W; g.bias = bias; g.C = C; g.row_zero = row_zero; g.count = count;
+  g.A = A; g.W = W; g.wpack = wpack; g.stride_wpack = stride_wpack;
+  g.bias = bias; g.C = C; g.row_zero = row_zero; g.count = count;
   g.lda = lda; g.ldw = ldw; g.ldc = ldc;
   g.stride_a = stride_a; g.stride_w = stride_w; g.stride_bias = stride_bias; g.stride_c = stride_c;
   g.M = m_rows; g.rows_per_count = rows_per_count > 0 ? rows_per_count : 1;
   g.N = n_cols; g.K = k_dim; g.alpha = alpha; g.relu = relu;
   const bool multi = batch > 1;
   g.vec_a = ((((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && (!multi || (stride_a & 3) == 0)) ? 1 : 0;
-  g.vec_w = ((((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && (!multi || (stride_w & 3) == 0)) ? 1 : 0;
+  g.vec_w = (wpack == nullptr && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && (!multi || (stride_w & 3) == 0)) ? 1 : 0;
   g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0 && (!multi || (stride_c & 3) == 0)) ? 1 : 0;
-  // column tile: the widest of 128/64/32 that still yields about one CTA per SM, then balanced
   const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
-  int bn = 32;
-  for (int cand = TCG_MAX_BN; cand >= 32; cand >>= 1) {
-    const int64_t tiles = tiles_m * ((n_cols + cand - 1) / cand) * batch;
-    if (tiles >= (3 * (int64_t)g_gemm_sms) / 4 || cand == 32) {
-      bn = cand;
-      break;
-    }
-  }
-  g.tiles_n = (n_cols + bn - 1) / bn;
-  g.bn = (((n_cols + g.tiles_n - 1) / g.tiles_n) + 15) & ~15;
+  g.bn = wpack != nullptr ? bn_pack : gemm_pick_bn(m_rows, n_cols, batch, sms);
+  g.tiles_n = (n_cols + g.bn - 1) / g.bn;
   g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn));
   const size_t stage_bytes = (size_t)(2 * UMMA_KCH * TCG_BM * 4 + 2 * UMMA_KCH * g.bn * 4) * sizeof(float);
   int stages = (int)(TCG_SMEM_BUDGET / stage_bytes);
@@ -294,8 +394,29 @@ extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t strid
   g.stages = stages;
   const size_t smem = stages * stage_bytes + 256;
   dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)batch);
-  gemm_tf32x3_kernel<<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
+  if (wpack != nullptr)
+    gemm_tf32x3_kernel<true><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
+  else
+    gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
   return tiger_launch_status();
+}
+
+extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw,
+                                      int64_t stride_w, const float* bias, int64_t stride_bias, float* C,
+                                      int64_t ldc, int64_t stride_c, int batch, int64_t m_rows,
+                                      const int32_t* count, int64_t rows_per_count, int n_cols, int k_dim,
+                                      float alpha, int relu, const uint8_t* row_zero, void* stream) {
+  return gemm_launch(A, lda, stride_a, W, ldw, stride_w, nullptr, 0, 0, bias, stride_bias, C, ldc, stride_c, batch,
+                     m_rows, count, rows_per_count, n_cols, k_dim, alpha, relu, row_zero, stream);
+}
+
+extern "C" int tiger_sgemm_nt_packed(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
+                                     float* C, int64_t ldc, int64_t m_rows, const int32_t* count,
+                                     int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
+                                     void* stream) {
+  if (wpack == nullptr) return TIGER_EINVAL;
+  return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
+                     n_cols, k_dim, alpha, relu, nullptr, stream);
 }
 
 extern "C" int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,

@@ -49,9 +49,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// warp index / elected lane as the compiler can prove them warp-uniform (keeps descriptors in uniform
+// registers: UTCHMMA takes uniform-register operands, per-thread values cost an R2UR each)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- TMEM -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem, uint32_t n_cols) {  // one full warp
@@ -146,6 +171,22 @@ __device__ __forceinline__ void tf32_split(const float4& v, float4& hi, float4& 
   lo.z = tf32_rn(v.z - hi.z); lo.w = tf32_rn(v.w - hi.w);
 }
 
+// four consecutive floats of a row starting at column k, zero beyond k_end / for a missing row
+__device__ __forceinline__ float4 umma_load_chunk(const float* row_ptr, int k, int k_end, bool vec_ok) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row_ptr != nullptr && k < k_end) {
+    if (vec_ok && k + 4 <= k_end) {
+      v = __ldg(reinterpret_cast<const float4*>(row_ptr + k));
+    } else {
+      v.x = __ldg(row_ptr + k);
+      if (k + 1 < k_end) v.y = __ldg(row_ptr + k + 1);
+      if (k + 2 < k_end) v.z = __ldg(row_ptr + k + 2);
+      if (k + 3 < k_end) v.w = __ldg(row_ptr + k + 3);
+    }
+  }
+  return v;
+}
+
 // A tile of `rows` rows x UMMA_BK floats is moved in warp-chunks of 8 rows x 4 kc chunks
 // (lane & 7 -> row, lane >> 3 -> kc): a quarter warp writes 128 contiguous bytes of shared memory
 // (conflict-free) and the warp reads 8 x 64 contiguous bytes of global memory.  Each thread owns the
@@ -201,6 +242,13 @@ __device__ __forceinline__ void umma_chunk_pos(int wc, int lane, int& row, int& 
   row = wc * 8 + (lane & 7);
   kc = lane >> 3;
 }
+
+// ---- pre-split weight packs -------------------------------------------------------------------
+// Parameters are split once per update into the exact shared-memory image of the B operand:
+//     pack[tile][k-block][plane: head, tail][kc][row 0..bn-1][4 floats]
+// so that a pipeline stage of B (both planes, bn * 128 bytes) is ONE contiguous TMA bulk copy and costs
+// the SM no instructions.  Rows / columns beyond the matrix are zero.
+#define UMMA_PACK_STAGE_FLOATS(bn) ((bn) * 2 * UMMA_KCH * 4)
 
 // ---- MMA issue -------------------------------------------------------------------------------
 // tf32x3: per k-step three MMAs  tail*head, head*tail (cross terms) and head*head.  They are issued by

@@ -214,17 +214,21 @@ def copy_pad(w: Tensor, out: Tensor, ld_out: int):
 
 
 class GruPack:
-    """nn.GRUCell parameters as the kernel reads them: the tensors as stored (weight_ih [3d, M],
-    weight_hh [3d, d], contiguous fp32) - no derived copy, so nothing goes stale when they train."""
+    """nn.GRUCell parameters as the kernel reads them: the gate weights pre-split into tf32 head / tail
+    planes in the stage layout of tiger_gru_update (tiger_gru_pack), biases as stored."""
 
     def __init__(self, weight_ih: Tensor, weight_hh: Tensor, bias_ih: Tensor, bias_hh: Tensor):
         self.d = weight_hh.shape[1]
         self.m_dim = weight_ih.shape[1]
+        nbytes = _lib.load().tiger_gru_pack_bytes(self.m_dim, self.d)
+        self.wpack = torch.empty(nbytes // 4, dtype=f32, device=weight_ih.device)
         self.refresh(weight_ih, weight_hh, bias_ih, bias_hh)
 
     def refresh(self, weight_ih, weight_hh, bias_ih, bias_hh):
-        self.w_ih = weight_ih.detach().to(f32).contiguous()
-        self.w_hh = weight_hh.detach().to(f32).contiguous()
+        w_ih = weight_ih.detach().to(f32).contiguous()
+        w_hh = weight_hh.detach().to(f32).contiguous()
+        check_cuda(w_ih, w_hh)
+        call('tiger_gru_pack', ptr(w_ih), ptr(w_hh), self.m_dim, self.d, ptr(self.wpack))
         self.b_ih = bias_ih.detach().to(f32).contiguous()
         self.b_hh = bias_hh.detach().to(f32).contiguous()
 
@@ -238,7 +242,7 @@ def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_
     if out is None:
         out = _empty((n_rows, pack.d), f32, x_table)
     call('tiger_gru_update', ptr(node_ids), ptr(count), n_rows, ptr(x_table), x_table.stride(0), ptr(h_table),
-         h_table.stride(0), pack.m_dim, pack.d, ptr(pack.w_ih), ptr(pack.w_hh), ptr(pack.b_ih),
+         h_table.stride(0), pack.m_dim, pack.d, ptr(pack.wpack), ptr(pack.b_ih),
          ptr(pack.b_hh), ptr(out), ptr(msg_ts), ptr(check_mem_ts), int(check_equal), ptr(err_flags))
     return out
 
@@ -367,6 +371,37 @@ def sgemm_nt(a: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, *, m_row
     k = a.shape[1] if k_dim is None else k_dim
     call('tiger_sgemm_ffma' if ffma_baseline else 'tiger_sgemm_nt', ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), m,
          ptr(count), rows_per_count, w.shape[0], k, int(relu))
+    return out
+
+
+class WeightPack:
+    """tf32 head / tail pack of a weight [N, K] for the tensor-core GEMM (tiger_gemm_pack_weight)."""
+
+    def __init__(self, w: Tensor, bn: Optional[int] = None, m_rows_hint: int = 600):
+        check_cuda_strided(w)
+        self.n, self.k = w.shape
+        lib = _lib.load()
+        self.bn = bn if bn is not None else lib.tiger_gemm_pick_bn(m_rows_hint, self.n, 1)
+        self.tiles = (self.n + self.bn - 1) // self.bn
+        nbytes = lib.tiger_gemm_pack_bytes(self.tiles, self.k, self.bn)
+        if self.bn <= 0 or nbytes <= 0:
+            raise _lib.TigerLibraryError(f'cannot pack a [{self.n}, {self.k}] weight with bn={self.bn}')
+        self.data = torch.empty(nbytes // 4, dtype=f32, device=w.device)
+        self.refresh(w)
+
+    def refresh(self, w: Tensor):
+        w = w.detach()
+        call('tiger_gemm_pack_weight', ptr(w), w.stride(0), None, self.n, self.k, self.bn, self.tiles, ptr(self.data))
+
+
+def sgemm_nt_packed(a: Tensor, pack: WeightPack, bias: Optional[Tensor], out: Tensor, *, m_rows: Optional[int] = None,
+                    relu: bool = False, alpha: float = 1.0, count: Optional[Tensor] = None,
+                    rows_per_count: int = 1) -> Tensor:
+    """out[m, n] = act(alpha * (a[m, :K] @ W.T + bias)) with W pre-packed (one TMA bulk copy per stage)."""
+    check_cuda_strided(a, out)
+    m = a.shape[0] if m_rows is None else m_rows
+    call('tiger_sgemm_nt_packed', ptr(a), a.stride(0), ptr(pack.data), pack.bn, ptr(bias), ptr(out), out.stride(0), m,
+         ptr(count), rows_per_count, pack.n, pack.k, float(alpha), int(relu))
     return out
 
 

@@ -32,7 +32,7 @@ class GRUUpdater(UpdateModule):
         key = tuple((p.data_ptr(), p._version) for p in params)
         if self._pack is None or key != self._pack_key:
             args = [f32c(p) for p in params]
-            if self._pack is None or self._pack.w_ih.device != args[0].device:
+            if self._pack is None or self._pack.wpack.device != args[0].device:
                 self._pack = ops.GruPack(*args)
             else:
                 self._pack.refresh(*args)
