@@ -48,6 +48,9 @@ def parse_args():
     p.add_argument('--cpu-batches', type=int, default=40, help='bounded sample of the cpu_baseline leg (0 = off)')
     p.add_argument('--profile-steps', type=int, default=100, help='eager steps with per-kernel CUDA events')
     p.add_argument('--no-e2e', action='store_true')
+    p.add_argument('--micro', action='store_true',
+                   help='feed each gather/scatter kernel >= 256k rows (tables >> L2) and report HBM GB/s vs peak')
+    p.add_argument('--micro-rows', type=int, default=1 << 18)
     p.add_argument('--seed', type=int, default=0)
     return p.parse_args()
 
@@ -77,6 +80,17 @@ def chunk_bounds(n, rank, world, bs, seed=0):
     shift = int(torch.randint(0, residual + 1, size=(), generator=g))
     length = n // (world * bs) * bs
     return shift + length * rank, shift + length * (rank + 1)
+
+
+def max_over_ranks(value: float, world: int, device=None) -> float:
+    """Timing of a multi-rank run = the slowest rank (all-reduce MAX; identity at world 1)."""
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def batch_window(args, n_events, rank, world):
@@ -322,10 +336,7 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     eng.check_errors()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms, world, dev)
     value = world * K * B / (ms * 1e-3)
 
     # ---- e2e: pinned host buffers -> H2D -> graph -> D2H of scores + loss, every step ----
@@ -354,10 +365,7 @@ def run_b200(args):
             checksum += float(runner.wait(pending.pop(0))[2])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(dt, world, dev)
         eng.check_errors()
         e2e = {'value': world * K * B / dt, 'unit': UNIT, 'h2d_bytes_per_step': runner.h2d_bytes_per_step,
                'd2h_bytes_per_step': runner.d2h_bytes_per_step, 'ms_per_step': dt / K * 1e3,
@@ -462,9 +470,129 @@ def profile_kernels(args, eng, dev_in, avail, csr):
     return kernels, counters
 
 
+# ------------------------------------------------------------------------------------------
+# micro mode: HBM fraction of the gather / scatter / search kernels at sizes that leave the L2
+# ------------------------------------------------------------------------------------------
+def run_micro(args):
+    """At batch 200 the whole path moves ~17 MB per step, so every kernel is launch / latency bound in
+    situ.  What the gather/scatter kernels can do is measured here: each one is fed `--micro-rows` rows out
+    of tables far larger than the 126 MB L2 (scaled-config shapes: 1M-node tables, d = de = 172), timed
+    with CUDA events over 20 launches after 3 warm-ups, against the measured HBM peak."""
+    import torch
+    from www2023tiger_b200 import _lib, ops
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --micro needs a CUDA device')
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    _lib.load()
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+        peak_src = 'measured (MEASURED_PEAKS.json)'
+    except (OSError, KeyError):
+        peak, peak_src = 6650.0, 'fallback'
+    g = torch.Generator(device=dev).manual_seed(args.seed)
+    N, d, de, R, K = 1_000_001, 172, 172, args.micro_rows, K_NEIGH
+    M = 3 * d + de
+    f32, i64 = torch.float32, torch.int64
+    table = torch.randn(N, d, device=dev, generator=g)
+    table2 = torch.randn(N, d, device=dev, generator=g)
+    ts_table = torch.zeros(N, device=dev)
+    active = torch.zeros(N, dtype=torch.uint8, device=dev)
+    perm = torch.randperm(N - 1, device=dev, generator=g)[:2 * R] + 1          # distinct node ids, no padding id
+    ids = perm[:R].contiguous()
+    vals = torch.randn(R, d, device=dev, generator=g)
+    ts_r = torch.rand(R, device=dev, generator=g) * 1e6 + 1.0
+    results = {}
+
+    def timed(name, fn, nbytes, n=20, warm=3, note=''):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / n * 1e3
+        gbs = nbytes / (us * 1e-6) / 1e9
+        results[name] = {'us': us, 'bytes': int(nbytes), 'gbs': gbs, 'frac_of_peak': gbs / peak, 'rows': R, 'note': note}
+
+    # Memory.get / Memory.set (memory.py:36-52): row gather / scatter of d floats (+ update_ts)
+    timed('tiger_gather_rows', lambda: ops.gather_rows(table, ids, ts_table), R * (2 * d * 4 + 8 + 8),
+          note='Memory.get: R random rows of a 688 MB table -> dense [R, d]')
+    timed('tiger_scatter_rows', lambda: ops.scatter_rows(table, ids, vals, ts_table=ts_table, ts=ts_r, active=active),
+          R * (2 * d * 4 + 8 + 9), note='Memory.set: dense [R, d] -> R random rows')
+    # store_events (tiger.py:422-442, memory.py:77-106): 2R message rows of M floats, all positions winners
+    B = R // 2
+    src, dst = perm[:B].contiguous(), perm[B:2 * B].contiguous()
+    n_e = 4_000_000
+    efeats = torch.randn(n_e + 1, de, device=dev, generator=g)
+    eids = torch.randint(1, n_e + 1, (B,), device=dev, generator=g)
+    ev_ts = torch.rand(B, device=dev, generator=g) * 1e6 + 2e6
+    winner = torch.ones(2 * B, dtype=torch.uint8, device=dev)
+    msg_vals = torch.empty(N, M, device=dev)
+    msg_ts = torch.zeros(N, device=dev)
+    has_msg = torch.zeros(N, dtype=torch.uint8, device=dev)
+    time_w = torch.from_numpy((1 / 10 ** np.linspace(0, 9, d)).astype(np.float32)).to(dev)
+    time_b = torch.zeros(d, device=dev)
+
+    def store():
+        has_msg.zero_()
+        ops.store_messages(src, dst, eids, ev_ts, winner, table, ts_table, None, efeats, d, de, time_w, time_b,
+                           msg_vals, msg_ts, has_msg)
+    timed('tiger_store_messages', store, 2 * B * ((2 * d + de) * 4 + M * 4 + 8 + 13) + N,
+          note='2R message rows [mem(self) | mem(other) | efeat | time code] built in the table (incl. the has_msg clear)')
+    # write-backs (tiger.py:396-420)
+    pos = torch.cat([src, dst])
+    gru_row = torch.full((N,), -1, dtype=torch.int32, device=dev)
+    gru_row[pos] = torch.arange(2 * B, dtype=torch.int32, device=dev)
+    h_new = torch.randn(2 * B, d, device=dev, generator=g)
+
+    def right():
+        has_msg.fill_(1)
+        ops.right_writeback(pos, winner, gru_row, h_new, d, table2, ts_table, active, msg_ts, has_msg)
+    timed('tiger_right_writeback', right, 2 * B * (2 * d * 4 + 8 + 4 + 10) + N,
+          note='2R GRU rows persisted into the right memory (incl. the has_msg fill)')
+    h_left = torch.randn(3 * B, d, device=dev, generator=g)
+    left_ts = torch.zeros(N, device=dev)
+    timed('tiger_left_writeback',
+          lambda: ops.left_writeback(pos, B, winner, h_left, d, ev_ts, table, left_ts, active),
+          2 * B * (2 * d * 4 + 8 + 4 + 6), note='2R embedding rows persisted into the left memory')
+    del msg_vals, efeats
+    # neighbor finder (graph.py:44-53,117-127): R queries over a 1M-node / 8M-event CSR
+    from www2023tiger_b200.synthetic import StreamShape, make_stream
+    st = make_stream(StreamShape('micro', 900000, 100000, 8_000_000, 0, d), seed=args.seed, n_events=8_000_000,
+                     with_efeats=False)
+    csr = ops.csr_build(torch.from_numpy(st.src).to(dev), torch.from_numpy(st.dst).to(dev),
+                        torch.from_numpy(st.ts).to(dev), torch.from_numpy(st.eids).to(dev), N)
+    q_n = torch.from_numpy(np.concatenate([st.src[-R // 2:], st.dst[-R // 2:]])).to(dev)
+    q_t = torch.from_numpy(np.concatenate([st.ts[-R // 2:], st.ts[-R // 2:]])).to(dev)
+    out = (torch.empty(R, K, dtype=i64, device=dev), torch.empty(R, K, dtype=i64, device=dev),
+           torch.empty(R, K, dtype=f32, device=dev), None)
+    deg = (csr.indptr[q_n + 1] - csr.indptr[q_n]).double().clamp(min=2)
+    search = float(deg.log2().div(5).ceil().clamp(min=1).mul(32 * 8).mean())     # 32-ary probes of 8 B
+    kk = float(deg.clamp(max=K).mean())
+    timed('tiger_find_recent', lambda: ops.find_recent(csr, q_n, q_t, K, out=out),
+          R * (search + kk * 16 + K * 20 + 32),
+          note=f'R queries, mean degree {float(deg.mean()):.0f}: 32-ary lower bound + gather of the last K entries')
+    src_d, dst_d = torch.from_numpy(st.src).to(dev), torch.from_numpy(st.dst).to(dev)
+    ts_d, eid_d = torch.from_numpy(st.ts).to(dev), torch.from_numpy(st.eids).to(dev)
+    E = st.n_events
+    timed('tiger_csr_build', lambda: ops.csr_build(src_d, dst_d, ts_d, eid_d, N), 2 * E * (4 * 3 * 2 * 2 + 21) + E * 32,
+          n=5, warm=1, note='8M events -> 16M CSR entries: LSD radix sort by owner (3 passes of key+value) + entry fill')
+    line = {'metric': 'HBM GB/s of the gather/scatter/search kernels at >= 256k rows (micro mode)', 'unit': 'GB/s',
+            'peak': peak, 'peak_source': peak_src, 'rows': R,
+            'tables': f'{N} nodes x d={d} (688 MB per memory), message store {N} x {M}, 4M x {de} edge features',
+            'micro': results}
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
-    if args.impl == 'reference':
+    if args.micro:
+        run_micro(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_b200(args)

@@ -16,11 +16,21 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id_in_block() { return threadIdx.x >> 5; }
 
-// cos(t*w + b) with the product and the sum rounded separately, exactly like the
-// reference's CPU TimeEncode (time_encoding.py:26: `ts * basis_freq + phase`, no FMA).
-// cosf (not __cosf): arguments reach 1e6 rad, the fast intrinsic is useless there.
+// cos(t*w + b) with the product and the sum rounded separately, exactly like the reference's CPU
+// TimeEncode (time_encoding.py:26: `ts * basis_freq + phase`, no FMA).  Arguments reach 1e6 rad (seconds
+// since the last update times a basis frequency of 1): __cosf is useless there and cosf takes its
+// Payne-Hanek slow path (local memory, hundreds of instructions, divergent within a warp because only
+// the highest frequencies need it).  Instead the fp32 argument is reduced to [-pi, pi] in double
+// (two-constant Cody-Waite, error < 1e-9 rad for |x| < 1e8) and cosf runs on its fast path.
+__device__ __forceinline__ float cos_reduced(float x) {
+  const double xd = (double)x;
+  const double n = rint(xd * 0.15915494309189535);               // x / (2 pi)
+  double r = fma(-n, 6.283185307179586, xd);                     // 2 pi (head)
+  r = fma(-n, 2.4492935982947064e-16, r);                        // 2 pi (tail)
+  return cosf((float)r);
+}
 __device__ __forceinline__ float time_enc(float t, float w, float b) {
-  return cosf(__fadd_rn(__fmul_rn(t, w), b));
+  return cos_reduced(__fadd_rn(__fmul_rn(t, w), b));
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -63,6 +73,44 @@ __device__ __forceinline__ void warp_copy_row(float* __restrict__ dst, const flo
     for (int i = lane; i < (width >> 2); i += 32) d4[i] = s4[i];
   } else {
     for (int i = lane; i < width; i += 32) dst[i] = src[i];
+  }
+}
+
+// Warp-cooperative copy of NR rows at once (dst[r] == NULL skips row r): all loads of the NR rows are
+// issued before the first store, so a warp keeps up to 2 * NR 16-byte loads per lane in flight - the
+// memory-level parallelism a random-row gather / scatter needs to approach the HBM rate (a 172-float row
+// is 43 vectors: one warp-wide load plus an 11-lane tail).
+#define ROWS_PER_WARP 4
+template <int NR>
+__device__ __forceinline__ void warp_copy_rows(float* const (&dst)[NR], const float* const (&src)[NR], int width,
+                                               int lane) {
+  bool vec = (width & 3) == 0;
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+    if (dst[r] != nullptr) vec = vec && ((((uintptr_t)dst[r] | (uintptr_t)src[r]) & 15) == 0);
+  if (vec) {
+    const int w4 = width >> 2;
+    for (int base = 0; base < w4; base += 64) {
+      const int c0 = base + lane, c1 = base + 32 + lane;
+      float4 a[NR], b[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (dst[r] != nullptr && c0 < w4) a[r] = reinterpret_cast<const float4*>(src[r])[c0];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (dst[r] != nullptr && c1 < w4) b[r] = reinterpret_cast<const float4*>(src[r])[c1];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (dst[r] != nullptr && c0 < w4) reinterpret_cast<float4*>(dst[r])[c0] = a[r];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (dst[r] != nullptr && c1 < w4) reinterpret_cast<float4*>(dst[r])[c1] = b[r];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+      if (dst[r] != nullptr)
+        for (int i = lane; i < width; i += 32) dst[r][i] = src[r][i];
   }
 }
 
@@ -109,3 +157,28 @@ __device__ __forceinline__ int64_t warp_lower_bound(const double* __restrict__ t
   return lo + __popc(__ballot_sync(TIGER_FULL_MASK, less));
 }
 
+// Same search with G lanes per query (G = 8 or 16: 32 / G independent queries per warp, which is what keeps
+// enough dependent-load chains in flight when segments are short).  Every lane of the warp must call it
+// (inactive groups pass lo == hi); lanes of one group pass the same arguments and get the same result.
+template <int G>
+__device__ __forceinline__ int64_t group_lower_bound(const double* __restrict__ ts, int64_t lo, int64_t hi, double t,
+                                                     int lane) {
+  const int l = lane & (G - 1), shift = lane & ~(G - 1);
+  const uint32_t gmask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+  while (__any_sync(TIGER_FULL_MASK, hi - lo > G)) {
+    const bool big = hi - lo > G;
+    const int64_t step = (hi - lo + G - 1) / G;
+    const int64_t p = lo + (int64_t)(l + 1) * step - 1;
+    const bool less = big && p < hi && (__ldg(ts + p) < t);
+    const int c = __popc((__ballot_sync(TIGER_FULL_MASK, less) >> shift) & gmask);
+    if (big) {
+      const int64_t pc = lo + (int64_t)(c + 1) * step - 1;
+      const int64_t new_lo = lo + (int64_t)c * step;
+      if (c < G && pc < hi) hi = pc;
+      lo = new_lo < hi ? new_lo : hi;
+    }
+  }
+  const int64_t p = lo + l;
+  const bool less = (p < hi) && (__ldg(ts + p) < t);
+  return lo + __popc((__ballot_sync(TIGER_FULL_MASK, less) >> shift) & gmask);
+}

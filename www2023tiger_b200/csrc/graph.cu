@@ -5,10 +5,13 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
-// K1  one warp per query: 32-ary cooperative lower-bound search on the float64 timestamps of
-// the node's CSR segment (strict '<', np.searchsorted side='left'), then a coalesced gather of
-// the K entries that precede the cut, right-aligned, zero-padded on the left.
+// K1  FIND_G lanes per query (4 queries per warp): FIND_G-ary cooperative lower-bound search on the
+// float64 timestamps of the node's CSR segment (strict '<', np.searchsorted side='left'), then a gather
+// of the K entries that precede the cut, right-aligned, zero-padded on the left.  The kernel is a chain
+// of dependent loads (node id -> indptr -> probes -> entries); several queries per warp keep enough of
+// those chains in flight to use the memory system.
 // ------------------------------------------------------------------------------------------
+#define FIND_G 8
 __global__ void __launch_bounds__(256)
 find_recent_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ adj_nbr,
                    const int32_t* __restrict__ adj_eid, const double* __restrict__ adj_ts,
@@ -17,17 +20,22 @@ find_recent_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
                    int64_t ts_period, int k, int64_t* __restrict__ out_nids, int64_t* __restrict__ out_eids,
                    float* __restrict__ out_ts, int64_t* __restrict__ out_dirs,
                    float* __restrict__ out_ts32, uint32_t* __restrict__ bitmap) {
-  const int lane = lane_id();
-  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block();
-  if (q >= n_query || (count != nullptr && q >= *count)) return;
-  const int64_t nid = q_nids[q];
-  const double t = q_ts[q % ts_period];
-  if (out_ts32 != nullptr && q < ts_period && lane == 0) out_ts32[q] = (float)t;
-  const int64_t beg = indptr[nid];
-  const int64_t end = indptr[nid + 1];
-  const int64_t cut = warp_lower_bound(adj_ts, beg, end, t, lane);
-  if (bitmap != nullptr && lane == 0) atomicOr(bitmap + (nid >> 5), 1u << (nid & 31));
-  for (int kk = lane; kk < k; kk += 32) {
+  const int lane = lane_id(), l = lane & (FIND_G - 1);
+  const int64_t q = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block()) * (32 / FIND_G) + lane / FIND_G;
+  const bool live = q < n_query && (count == nullptr || q < *count);
+  int64_t nid = 0, beg = 0, end = 0;
+  double t = 0.0;
+  if (live) {
+    nid = q_nids[q];
+    t = q_ts[q % ts_period];
+    if (out_ts32 != nullptr && q < ts_period && l == 0) out_ts32[q] = (float)t;
+    beg = indptr[nid];
+    end = indptr[nid + 1];
+  }
+  const int64_t cut = group_lower_bound<FIND_G>(adj_ts, beg, end, t, lane);
+  if (!live) return;
+  if (bitmap != nullptr && l == 0) atomicOr(bitmap + (nid >> 5), 1u << (nid & 31));
+  for (int kk = l; kk < k; kk += FIND_G) {
     const int64_t s = cut - k + kk;
     int64_t nb = 0, ei = 0, dr = 0;
     float tv = 0.f;
@@ -54,8 +62,8 @@ extern "C" int tiger_find_recent(const int64_t* indptr, const int32_t* adj_nbr, 
   if (n_query < 0 || k <= 0 || ts_period < 0) return TIGER_EINVAL;
   if (n_query == 0) return TIGER_OK;
   if (ts_period == 0) ts_period = n_query;
-  const int warps = 8;
-  const unsigned grid = (unsigned)((n_query + warps - 1) / warps);
+  const int warps = 8, per_cta = warps * (32 / FIND_G);
+  const unsigned grid = (unsigned)((n_query + per_cta - 1) / per_cta);
   find_recent_kernel<<<grid, warps * 32, 0, as_stream(stream)>>>(
       indptr, adj_nbr, adj_eid, adj_ts, adj_flag, q_nids, q_ts, n_query, count, ts_period, k, out_nids, out_eids,
       out_ts, out_dirs, out_ts32, mark_bitmap);

@@ -6,6 +6,11 @@
 
 #define ROW_WARPS 8  // warps (rows) per CTA for the row kernels
 
+static inline unsigned row_grid(int64_t n_rows) {
+  const int64_t per_cta = (int64_t)ROW_WARPS * ROWS_PER_WARP;
+  return (unsigned)((n_rows + per_cta - 1) / per_cta);
+}
+
 __device__ __forceinline__ int64_t effective_count(const int32_t* count, int64_t n) {
   if (count == nullptr) return n;
   const int64_t c = *count;
@@ -16,19 +21,28 @@ __device__ __forceinline__ int64_t effective_count(const int32_t* count, int64_t
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 gather_rows_kernel(const float* __restrict__ table, int64_t width, const int64_t* __restrict__ ids, int64_t n,
                    float* __restrict__ out, const float* __restrict__ ts_table, float* __restrict__ out_ts) {
-  const int64_t r = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
-  if (r >= n) return;
+  const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+  if (r0 >= n) return;
   const int lane = lane_id();
-  const int64_t u = ids[r];
-  if (out != nullptr) warp_copy_row(out + r * width, table + u * width, (int)width, lane);
-  if (out_ts != nullptr && lane == 0) out_ts[r] = ts_table[u];
+  float* dst[ROWS_PER_WARP];
+  const float* src[ROWS_PER_WARP];
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_WARP; ++i) {
+    const int64_t r = r0 + i;
+    const bool live = r < n;
+    const int64_t u = live ? ids[r] : 0;
+    dst[i] = (live && out != nullptr) ? out + r * width : nullptr;
+    src[i] = table + u * width;
+    if (live && out_ts != nullptr && lane == i) out_ts[r] = ts_table[u];
+  }
+  warp_copy_rows<ROWS_PER_WARP>(dst, src, (int)width, lane);
 }
 
 extern "C" int tiger_gather_rows(const float* table, int64_t width, const int64_t* ids, int64_t n, float* out,
                                  const float* ts_table, float* out_ts, void* stream) {
   if (n < 0 || width < 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
-  gather_rows_kernel<<<(unsigned)((n + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+  gather_rows_kernel<<<row_grid(n), ROW_WARPS * 32, 0, as_stream(stream)>>>(
       table, width, ids, n, out, ts_table, out_ts);
   return tiger_launch_status();
 }
@@ -39,18 +53,28 @@ scatter_rows_kernel(float* __restrict__ table, int64_t width, const int64_t* __r
                     const int32_t* __restrict__ count, const float* __restrict__ vals,
                     float* __restrict__ ts_table, const float* __restrict__ ts, uint8_t* __restrict__ active,
                     int check, uint32_t* __restrict__ err_flags) {
-  const int64_t r = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
-  if (r >= effective_count(count, n)) return;
+  const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+  const int64_t n_eff = effective_count(count, n);
+  if (r0 >= n_eff) return;
   const int lane = lane_id();
-  const int64_t u = ids[r];
-  if (lane == 0) {
-    if (ts_table != nullptr) {
-      if (check && err_flags != nullptr && ts_table[u] > ts[r]) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
-      ts_table[u] = ts[r];
+  float* dst[ROWS_PER_WARP];
+  const float* src[ROWS_PER_WARP];
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_WARP; ++i) {
+    const int64_t r = r0 + i;
+    const bool live = r < n_eff;
+    const int64_t u = live ? ids[r] : 0;
+    if (live && lane == i) {               // lane i owns the scalar side of row i: the rows proceed in parallel
+      if (ts_table != nullptr) {
+        if (check && err_flags != nullptr && ts_table[u] > ts[r]) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+        ts_table[u] = ts[r];
+      }
+      if (active != nullptr) active[u] = 1;
     }
-    if (active != nullptr) active[u] = 1;
+    dst[i] = (live && table != nullptr) ? table + u * width : nullptr;
+    src[i] = vals + r * width;
   }
-  if (table != nullptr) warp_copy_row(table + u * width, vals + r * width, (int)width, lane);
+  warp_copy_rows<ROWS_PER_WARP>(dst, src, (int)width, lane);
 }
 
 extern "C" int tiger_scatter_rows(float* table, int64_t width, const int64_t* ids, int64_t n,
@@ -58,7 +82,7 @@ extern "C" int tiger_scatter_rows(float* table, int64_t width, const int64_t* id
                                   uint8_t* active, int check, uint32_t* err_flags, void* stream) {
   if (n < 0 || width < 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
-  scatter_rows_kernel<<<(unsigned)((n + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+  scatter_rows_kernel<<<row_grid(n), ROW_WARPS * 32, 0, as_stream(stream)>>>(
       table, width, ids, n, count, vals, ts_table, ts, active, check, err_flags);
   return tiger_launch_status();
 }
@@ -120,16 +144,57 @@ store_messages_kernel(const int64_t* __restrict__ src, const int64_t* __restrict
   float* row = msg_vals + self * m_dim;
   const float* self_row = in.dense ? (is_src ? in.src_vals : in.dst_vals) + e * d : in.mem_vals + self * d;
   const float* other_row = in.dense ? (is_src ? in.dst_vals : in.src_vals) + e * d : in.mem_vals + other * d;
-  warp_add_row(row, self_row, nfeats ? nfeats + self * d : nullptr, d, lane);
-  warp_add_row(row + d, other_row, nfeats ? nfeats + other * d : nullptr, d, lane);
-  if (efeats != nullptr) {
-    warp_copy_row(row + 2 * d, efeats + eids[e] * de, de, lane);
-  } else {
-    for (int i = lane; i < de; i += 32) row[2 * d + i] = 0.f;
-  }
+  const float* nf_self = nfeats ? nfeats + self * d : nullptr;
+  const float* nf_other = nfeats ? nfeats + other * d : nullptr;
+  const float* ef_row = efeats != nullptr ? efeats + eids[e] * de : nullptr;
   const float dt = t - prev;
   float* trow = row + 2 * d + de;
-  for (int i = lane; i < d; i += 32) trow[i] = time_enc(dt, time_w[i], time_b[i]);
+  const int d4 = d >> 2, de4 = de >> 2;
+  const bool vec = (d & 3) == 0 && (de & 3) == 0 && d4 <= 64 && de4 <= 64 &&
+                   ((((uintptr_t)row | (uintptr_t)self_row | (uintptr_t)other_row | (uintptr_t)nf_self |
+                      (uintptr_t)nf_other | (uintptr_t)ef_row | (uintptr_t)time_w | (uintptr_t)time_b) & 15) == 0);
+  if (vec) {
+    // all gathers of the row are issued before the first store (up to 10 16-byte loads per lane in flight)
+    const int c0 = lane, c1 = lane + 32;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s[2] = {z, z}, o[2] = {z, z}, ns[2] = {z, z}, no[2] = {z, z}, ef[2] = {z, z};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = h == 0 ? c0 : c1;
+      if (c < d4) {
+        s[h] = reinterpret_cast<const float4*>(self_row)[c];
+        o[h] = reinterpret_cast<const float4*>(other_row)[c];
+        if (nf_self != nullptr) {
+          ns[h] = reinterpret_cast<const float4*>(nf_self)[c];
+          no[h] = reinterpret_cast<const float4*>(nf_other)[c];
+        }
+      }
+      if (c < de4 && ef_row != nullptr) ef[h] = reinterpret_cast<const float4*>(ef_row)[c];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = h == 0 ? c0 : c1;
+      if (c < d4) {
+        reinterpret_cast<float4*>(row)[c] = nf_self != nullptr
+            ? make_float4(s[h].x + ns[h].x, s[h].y + ns[h].y, s[h].z + ns[h].z, s[h].w + ns[h].w) : s[h];
+        reinterpret_cast<float4*>(row + d)[c] = nf_self != nullptr
+            ? make_float4(o[h].x + no[h].x, o[h].y + no[h].y, o[h].z + no[h].z, o[h].w + no[h].w) : o[h];
+        const float4 w4 = reinterpret_cast<const float4*>(time_w)[c], b4 = reinterpret_cast<const float4*>(time_b)[c];
+        reinterpret_cast<float4*>(trow)[c] = make_float4(time_enc(dt, w4.x, b4.x), time_enc(dt, w4.y, b4.y),
+                                                        time_enc(dt, w4.z, b4.z), time_enc(dt, w4.w, b4.w));
+      }
+      if (c < de4) reinterpret_cast<float4*>(row + 2 * d)[c] = ef[h];
+    }
+  } else {
+    warp_add_row(row, self_row, nf_self, d, lane);
+    warp_add_row(row + d, other_row, nf_other, d, lane);
+    if (ef_row != nullptr) {
+      warp_copy_row(row + 2 * d, ef_row, de, lane);
+    } else {
+      for (int i = lane; i < de; i += 32) row[2 * d + i] = 0.f;
+    }
+    for (int i = lane; i < d; i += 32) trow[i] = time_enc(dt, time_w[i], time_b[i]);
+  }
   if (lane == 0) msg_ts[self] = t;
 }
 
@@ -186,33 +251,72 @@ right_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, const
                        float* __restrict__ right_vals, float* __restrict__ right_ts,
                        uint8_t* __restrict__ right_active, const float* __restrict__ msg_ts,
                        uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags) {
-  const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
-  if (p >= n_pos || !winner[p]) return;
+  const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+  if (p0 >= n_pos) return;
   const int lane = lane_id();
-  const int64_t u = pos_ids[p];
-  if (has_msg[u] == 0) return;           // positive without a pending message: nothing to persist
-  const int32_t r = gru_row[u];
-  const float t = msg_ts[u];
-  __syncwarp();
-  if (lane == 0) {
-    if (err_flags != nullptr && right_ts[u] > t) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
-    right_ts[u] = t;
-    if (right_active != nullptr) right_active[u] = 1;
-    has_msg[u] = 0;                       // the message is consumed (tiger.py:240)
+  float* dst[ROWS_PER_WARP];
+  const float* src[ROWS_PER_WARP];
+  int64_t node[ROWS_PER_WARP];
+  // index chain of the 4 positions side by side: position -> node -> {pending flag, GRU row, clocks} -> row copy
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_WARP; ++i) {
+    const int64_t p = p0 + i;
+    node[i] = (p < n_pos && winner[p]) ? pos_ids[p] : -1;
   }
-  warp_copy_row(right_vals + u * (int64_t)d, h_new + (int64_t)r * d, d, lane);
+  float t_msg = 0.f, t_mem = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_WARP; ++i) {
+    dst[i] = nullptr;
+    src[i] = h_new;
+    if (node[i] < 0) continue;
+    const int64_t u = node[i];
+    const uint8_t pending = has_msg[u];
+    const int32_t r = gru_row[u];
+    if (lane == i) {                       // lane i owns the scalar side of row i
+      t_msg = msg_ts[u];
+      t_mem = right_ts[u];
+    }
+    if (pending == 0) {                    // positive without a pending message: nothing to persist
+      node[i] = -1;
+      continue;
+    }
+    dst[i] = right_vals + u * (int64_t)d;
+    src[i] = h_new + (int64_t)r * d;
+  }
+  __syncwarp();                            // every lane has read has_msg before its owner lane clears it
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_WARP; ++i) {
+    if (node[i] >= 0 && lane == i) {
+      const int64_t u = node[i];
+      if (err_flags != nullptr && t_mem > t_msg) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+      right_ts[u] = t_msg;
+      if (right_active != nullptr) right_active[u] = 1;
+      has_msg[u] = 0;                      // the message is consumed (tiger.py:240)
+    }
+  }
+  warp_copy_rows<ROWS_PER_WARP>(dst, src, d, lane);
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 hprev_copy_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, int d, const float* __restrict__ left_vals,
                   const float* __restrict__ right_vals, float* __restrict__ hprev_left,
                   float* __restrict__ hprev_right) {
-  const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
-  if (p >= n_pos) return;
+  const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * (ROWS_PER_WARP / 2);
+  if (p0 >= n_pos) return;
   const int lane = lane_id();
-  const int64_t u = pos_ids[p];
-  warp_copy_row(hprev_left + p * d, left_vals + u * d, d, lane);
-  warp_copy_row(hprev_right + p * d, right_vals + u * d, d, lane);
+  float* dst[ROWS_PER_WARP];
+  const float* src[ROWS_PER_WARP];
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_WARP / 2; ++i) {
+    const int64_t p = p0 + i;
+    const bool live = p < n_pos;
+    const int64_t u = live ? pos_ids[p] : 0;
+    dst[2 * i] = live ? hprev_left + p * d : nullptr;
+    src[2 * i] = left_vals + u * d;
+    dst[2 * i + 1] = live ? hprev_right + p * d : nullptr;
+    src[2 * i + 1] = right_vals + u * d;
+  }
+  warp_copy_rows<ROWS_PER_WARP>(dst, src, d, lane);
 }
 
 extern "C" int tiger_right_writeback(const int64_t* pos_ids, int64_t n_pos, const uint8_t* winner,
@@ -223,12 +327,11 @@ extern "C" int tiger_right_writeback(const int64_t* pos_ids, int64_t n_pos, cons
   if (n_pos < 0 || d <= 0) return TIGER_EINVAL;
   if ((hprev_left == nullptr) != (hprev_right == nullptr)) return TIGER_EINVAL;
   if (n_pos == 0) return TIGER_OK;
-  const unsigned grid = (unsigned)((n_pos + ROW_WARPS - 1) / ROW_WARPS);
-  right_writeback_kernel<<<grid, ROW_WARPS * 32, 0, as_stream(stream)>>>(
+  right_writeback_kernel<<<row_grid(n_pos), ROW_WARPS * 32, 0, as_stream(stream)>>>(
       pos_ids, n_pos, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg, err_flags);
   if (hprev_left != nullptr)
-    hprev_copy_kernel<<<grid, ROW_WARPS * 32, 0, as_stream(stream)>>>(pos_ids, n_pos, d, left_vals, right_vals,
-                                                                     hprev_left, hprev_right);
+    hprev_copy_kernel<<<row_grid(2 * n_pos), ROW_WARPS * 32, 0, as_stream(stream)>>>(pos_ids, n_pos, d, left_vals,
+                                                                                    right_vals, hprev_left, hprev_right);
   return tiger_launch_status();
 }
 
@@ -238,17 +341,28 @@ left_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, int64_
                       const uint8_t* __restrict__ winner, const float* __restrict__ h_left, int d,
                       const float* __restrict__ ts, float* __restrict__ left_vals, float* __restrict__ left_ts,
                       uint8_t* __restrict__ left_active, uint32_t* __restrict__ err_flags) {
-  const int64_t p = (int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block();
-  if (p >= n_pos || !winner[p]) return;
+  const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+  if (p0 >= n_pos) return;
   const int lane = lane_id();
-  const int64_t u = pos_ids[p];
-  if (lane == 0) {
-    const float t = ts[p % batch];
-    if (err_flags != nullptr && left_ts[u] > t) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
-    left_ts[u] = t;
-    if (left_active != nullptr) left_active[u] = 1;
+  float* dst[ROWS_PER_WARP];
+  const float* src[ROWS_PER_WARP];
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_WARP; ++i) {
+    const int64_t p = p0 + i;
+    dst[i] = nullptr;
+    src[i] = h_left;
+    if (p >= n_pos || !winner[p]) continue;
+    const int64_t u = pos_ids[p];
+    if (lane == i) {                       // lane i owns the scalar side of row i
+      const float t = ts[p % batch];
+      if (err_flags != nullptr && left_ts[u] > t) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+      left_ts[u] = t;
+      if (left_active != nullptr) left_active[u] = 1;
+    }
+    dst[i] = left_vals + u * (int64_t)d;
+    src[i] = h_left + p * d;
   }
-  warp_copy_row(left_vals + u * (int64_t)d, h_left + p * d, d, lane);
+  warp_copy_rows<ROWS_PER_WARP>(dst, src, d, lane);
 }
 
 extern "C" int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64_t batch, const uint8_t* winner,
@@ -256,7 +370,7 @@ extern "C" int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64
                                     uint8_t* left_active, uint32_t* err_flags, void* stream) {
   if (n_pos < 0 || d <= 0 || batch <= 0) return TIGER_EINVAL;
   if (n_pos == 0) return TIGER_OK;
-  left_writeback_kernel<<<(unsigned)((n_pos + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+  left_writeback_kernel<<<row_grid(n_pos), ROW_WARPS * 32, 0, as_stream(stream)>>>(
       pos_ids, n_pos, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags);
   return tiger_launch_status();
 }
