@@ -260,49 +260,128 @@ __global__ void __launch_bounds__(256) attn_prepare_kernel(const AttArgs a) {
   }
 }
 
-// one CTA per query: stage the K key rows in shared memory, scores, masked softmax, pooled keys
+// one CTA per query: stage the K key rows in shared memory, scores, masked softmax, pooled keys.
+// The gathers of all K slots are issued together (every thread keeps up to 8 independent 16-byte loads in
+// flight) - the kernel's time is the latency of those random-row reads, not their volume; the score
+// weights of the query are staged in shared memory once.
+#define ATT_MAXK 64
 __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttArgs a) {
   extern __shared__ __align__(16) float att_smem[];
   const int d = a.dm.d, de = a.dm.de, K = a.dm.K, H = a.dm.H, C = a.dm.C, Cp = a.dm.Cp, Cq = a.dm.Cq;
   float* kv = att_smem;                 // [K][Cp]
   float* sc = kv + K * Cp;              // [H][K]
+  float* qk = sc + ((H * K + 3) & ~3);  // [H][Cq]   score weights of this query
+  __shared__ const float* s_row[ATT_MAXK];   // node representation row of slot j (NULL = padding slot)
+  __shared__ const float* s_nf[ATT_MAXK];
+  __shared__ const float* s_ef[ATT_MAXK];
+  __shared__ float s_dt[ATT_MAXK];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block(), n_warps = ATT_THREADS / 32;
   const int64_t q = blockIdx.x;
   const float* qkf = a.w.qkf + q * a.dm.ld_qkf;
-  const float tq = a.dense ? 0.f : a.q_ts[q % a.ts_period];
-  // ---- gather + scores: one warp per slot ----
-  for (int j = warp; j < K; j += n_warps) {
-    const int64_t o = q * K + j;
-    float* row = kv + j * Cp;
-    bool live;
+  for (int i = tid; i < H * Cq; i += ATT_THREADS) qk[i] = qkf[i];
+  if (tid < K) {
+    const int64_t o = q * K + tid;
+    const float* rp = nullptr;
+    const float* nf = nullptr;
+    const float* ef = nullptr;
+    float dt = 0.f;
     if (a.dense) {
-      live = a.pad[o] == 0;
-      if (live) {
-        for (int c = lane; c < d; c += 32) row[c] = a.kx[o * d + c];
-        for (int c = lane; c < de; c += 32) row[d + c] = a.ky[o * de + c];
-        for (int c = lane; c < d; c += 32) row[d + de + c] = a.kt[o * d + c];
+      if (a.pad[o] == 0) {
+        rp = a.kx + o * d;
+        ef = a.ky + o * de;
       }
     } else {
       const int64_t u = a.neigh_nids[o];
-      live = u != 0;
-      if (live) {
-        const float* rp = resolve_row(a, u);
-        if (a.nfeats != nullptr) {
-          warp_add_row(row, rp, a.nfeats + u * d, d, lane);
-        } else {
-          for (int c = lane; c < d; c += 32) row[c] = rp[c];
-        }
-        if (a.efeats != nullptr) {
-          const float* ep = a.efeats + a.neigh_eids[o] * de;
-          for (int c = lane; c < de; c += 32) row[d + c] = ep[c];
-        } else {
-          for (int c = lane; c < de; c += 32) row[d + c] = 0.f;
-        }
-        const float dt = tq - a.neigh_ts[o];
-        for (int c = lane; c < d; c += 32) row[d + de + c] = time_enc(dt, a.time_w[c], a.time_b[c]);
+      if (u != 0) {
+        rp = resolve_row(a, u);
+        nf = a.nfeats != nullptr ? a.nfeats + u * d : nullptr;
+        ef = a.efeats != nullptr ? a.efeats + a.neigh_eids[o] * de : nullptr;
+        dt = a.q_ts[q % a.ts_period] - a.neigh_ts[o];
       }
     }
-    __syncwarp();
+    s_row[tid] = rp;
+    s_nf[tid] = nf;
+    s_ef[tid] = ef;
+    s_dt[tid] = dt;
+  }
+  __syncthreads();
+  // ---- gather: node rows (+ node features) and edge-feature rows of all slots ----
+  const bool vec = (d & 3) == 0 && (de & 3) == 0 && (Cp & 3) == 0 &&
+                   ((((uintptr_t)a.rows_a | (uintptr_t)a.rows_b | (uintptr_t)a.nfeats | (uintptr_t)a.efeats |
+                      (uintptr_t)a.kx | (uintptr_t)a.ky) & 15) == 0);
+  if (vec) {
+    const int d4 = d >> 2, de4 = de >> 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int f0 = tid; f0 < K * d4; f0 += 4 * ATT_THREADS) {
+      float4 v[4], n4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = f0 + u * ATT_THREADS;
+        v[u] = z4;
+        n4[u] = z4;
+        if (f < K * d4) {
+          const int j = f / d4, c = f - j * d4;
+          if (s_row[j] != nullptr) {
+            v[u] = reinterpret_cast<const float4*>(s_row[j])[c];
+            if (s_nf[j] != nullptr) n4[u] = reinterpret_cast<const float4*>(s_nf[j])[c];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = f0 + u * ATT_THREADS;
+        if (f < K * d4) {
+          const int j = f / d4, c = f - j * d4;
+          reinterpret_cast<float4*>(kv + j * Cp)[c] =
+              make_float4(v[u].x + n4[u].x, v[u].y + n4[u].y, v[u].z + n4[u].z, v[u].w + n4[u].w);
+        }
+      }
+    }
+    for (int f0 = tid; f0 < K * de4; f0 += 4 * ATT_THREADS) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = f0 + u * ATT_THREADS;
+        v[u] = z4;
+        if (f < K * de4) {
+          const int j = f / de4, c = f - j * de4;
+          if (s_ef[j] != nullptr) v[u] = reinterpret_cast<const float4*>(s_ef[j])[c];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = f0 + u * ATT_THREADS;
+        if (f < K * de4) {
+          const int j = f / de4, c = f - j * de4;
+          reinterpret_cast<float4*>(kv + j * Cp + d)[c] = v[u];
+        }
+      }
+    }
+  } else {
+    for (int f = tid; f < K * d; f += ATT_THREADS) {
+      const int j = f / d, c = f - j * d;
+      float v = 0.f;
+      if (s_row[j] != nullptr) v = s_row[j][c] + (s_nf[j] != nullptr ? s_nf[j][c] : 0.f);
+      kv[j * Cp + c] = v;
+    }
+    for (int f = tid; f < K * de; f += ATT_THREADS) {
+      const int j = f / de, c = f - j * de;
+      kv[j * Cp + d + c] = s_ef[j] != nullptr ? s_ef[j][c] : 0.f;
+    }
+  }
+  // ---- time code of every slot ----
+  for (int f = tid; f < K * d; f += ATT_THREADS) {
+    const int j = f / d, c = f - j * d;
+    float v = 0.f;
+    if (s_row[j] != nullptr)
+      v = a.dense ? a.kt[(q * K + j) * d + c] : time_enc(s_dt[j], a.time_w[c], a.time_b[c]);
+    kv[j * Cp + d + de + c] = v;
+  }
+  __syncthreads();
+  // ---- scores: one warp per slot ----
+  for (int j = warp; j < K; j += n_warps) {
+    const float* row = kv + j * Cp;
+    const bool live = s_row[j] != nullptr;
     float s[ATT_MAXH];
 #pragma unroll
     for (int h = 0; h < ATT_MAXH; ++h) s[h] = 0.f;
@@ -311,14 +390,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
         const float v = row[c];
 #pragma unroll
         for (int h = 0; h < ATT_MAXH; ++h)
-          if (h < H) s[h] = fmaf(qkf[h * Cq + c], v, s[h]);
+          if (h < H) s[h] = fmaf(qk[h * Cq + c], v, s[h]);
       }
     }
 #pragma unroll
     for (int h = 0; h < ATT_MAXH; ++h) {
       if (h < H) {
         const float t = warp_sum(s[h]);
-        if (lane == 0) sc[h * K + j] = live ? t + qkf[h * Cq + C] : -INFINITY;
+        if (lane == 0) sc[h * K + j] = live ? t + qk[h * Cq + C] : -INFINITY;
       }
     }
   }
@@ -376,8 +455,8 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   rc = tiger_sgemm_nt_packed(a.w.xq, m.ld_xq, f.pk_wqk, ATT_BN_QK, f.bqk, a.w.qkf, m.ld_qkf, n, nullptr, 1, m.H * m.Cq,
                              m.E, 1.0f, 0, s);
   if (rc != TIGER_OK) return rc;
-  const size_t smem = ((size_t)m.K * m.Cp + (size_t)m.H * m.K) * sizeof(float);
-  if (smem > 200 * 1024) return TIGER_EINVAL;
+  const size_t smem = ((size_t)m.K * m.Cp + (size_t)((m.H * m.K + 3) & ~3) + (size_t)m.H * m.Cq) * sizeof(float);
+  if (smem > 200 * 1024 || m.K > ATT_MAXK) return TIGER_EINVAL;
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     if (cudaFuncSetAttribute(attn_score_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

@@ -90,6 +90,9 @@ class TigerEngine:
         self.eids = self.inp[3 * B:4 * B]
         self.ts64 = self.inp[4 * B:].view(f64)
         # ---- parameters ----
+        self._side = torch.cuda.Stream(device=dev)
+        self._ev_fork, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork2, self._ev_side2 = torch.cuda.Event(), torch.cuda.Event()
         self.gru_pack = None
         self.attn_pack = ops.AttnPack(self.d, self.de, dev, n_head)
         self.score_pack = ops.ScorePack(self.d, dev)
@@ -188,20 +191,37 @@ class TigerEngine:
         ops.gru_update(self.gru_pack, node_ids=self.outdated, x_table=self.msg_vals, h_table=upd_vals,
                        n_rows=self.cap, out=self.h_new, count=self.counts[1:], msg_ts=self.msg_ts,
                        check_mem_ts=msg_ts_mem, check_equal=(self.msg_src == 'left'), err_flags=self.err_flags)
+        # Fork: the write-back / message branch (argmax-by-timestamp selection -> right write-back -> message
+        # build + store) only needs the GRU output and the batch, and touches rows the attention never reads
+        # (right-memory rows of nodes WITH a pending message are read from h_new, csrc/attention.cu
+        # resolve_row), so it runs on a side stream next to the attention chain.  Captured in a CUDA graph
+        # the two branches become parallel paths of the graph.
+        main = torch.cuda.current_stream()
+        self._ev_fork.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_fork)
+            ops.select_latest(self.pos, self.ts32, want_unique=False, winner=self.winner, want_count=False)
+            ops.right_writeback(self.pos, self.winner, self.gru_row, self.h_new, d, self.right_vals, self.right_ts,
+                                self.right_active, self.msg_ts, self.has_msg, self.left_vals, self.hprev_left,
+                                self.hprev_right, self.err_flags)
+            ops.store_messages(self.src, self.dst, self.eids, self.ts32, self.winner, msg_vals_mem, msg_ts_mem,
+                               self.nfeats, self.efeats, d, self.de, self.time_w, self.time_b, self.msg_vals,
+                               self.msg_ts, self.has_msg, self.err_flags)
+            self._ev_side.record(self._side)
         ops.temporal_attention(self.attn_pack, self.H, self.batch_nids, self.ts32, self.neigh_nids, self.neigh_eids,
                                self.neigh_ts, rows_a=self.right_vals, rows_b=self.h_new, sel=self.gru_row,
                                nfeats=self.nfeats, efeats=self.efeats, out=self.emb)
-        ops.select_latest(self.pos, self.ts32, want_unique=False, winner=self.winner, want_count=False)
-        ops.right_writeback(self.pos, self.winner, self.gru_row, self.h_new, d, self.right_vals, self.right_ts,
-                            self.right_active, self.msg_ts, self.has_msg, self.left_vals, self.hprev_left,
-                            self.hprev_right, self.err_flags)
-        ops.store_messages(self.src, self.dst, self.eids, self.ts32, self.winner, msg_vals_mem, msg_ts_mem,
-                           self.nfeats, self.efeats, d, self.de, self.time_w, self.time_b, self.msg_vals,
-                           self.msg_ts, self.has_msg, self.err_flags)
-        ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
-                           self.left_active, self.err_flags)
+        main.wait_event(self._ev_side)       # join: messages were built from the left memory of h(t'-)
+        # second fork: the left write-back and the link scorer both only read the embeddings
+        self._ev_fork2.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_fork2)
+            ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
+                               self.left_active, self.err_flags)
+            self._ev_side2.record(self._side)
         ops.link_score(self.score_pack, self.emb, self.src, self.dst, self.neg,
                        self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
+        main.wait_event(self._ev_side2)
 
     def launches_per_step(self) -> int:
         n = sum(KERNELS_PER_STEP.values())
