@@ -28,8 +28,8 @@
 
 #ifdef TIGER_TRACE
 #include <cstdio>
-#define TRACE_DECL long long tr_t[24]; int tr_n = 0; const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
-#define TRACE_MARK() do { if (tr_on && tr_n < 24) tr_t[tr_n++] = clock64(); } while (0)
+#define TRACE_DECL long long tr_t[40]; int tr_n = 0; const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+#define TRACE_MARK() do { if (tr_on && tr_n < 40) tr_t[tr_n++] = clock64(); } while (0)
 #define TRACE_DUMP(tag, id) do { if (tr_on) for (int i_ = 0; i_ < tr_n; ++i_) printf("%s %d #%d %lld\n", tag, id, i_, tr_t[i_] - tr_base); } while (0)
 #else
 #define TRACE_DECL
@@ -279,6 +279,226 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
   if (warp == 0) tmem_dealloc(taddr, g.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------
+// Packed-weight variant with the activations in tensor memory ("TS" form).
+//   TMEM columns : [0, 4 BN) the four partial accumulators | [4 BN, 4 BN + 64 S) ring of S activation
+//                  stages, each 32 head + 32 tail columns (TS_BK = 32 floats of K)
+//   shared memory: ring of S weight stages [head plane | tail plane], one TMA bulk copy each
+//   warps 0-15   : 4 groups x 4 warps; warp w of a group owns rows 32 w .. 32 w + 31 (its TMEM lanes),
+//                  thread = row: one 128-byte line of the row per stage -> tf32 split -> tcgen05.st
+//   warps 16-18  : MMA issuers (roles as in umma.cuh), warp 19: TMA
+// No shared-memory traffic, no proxy fence and no operand read for the activations: an MMA of this form
+// reads only its BN x 32-byte weight tile from shared memory and runs at the math floor (tools/umma_bench.cu).
+// ------------------------------------------------------------------------------------------
+#define TS_MAX_BN 64
+#define TS_MAX_STAGES 6
+#define TS_THREADS ((TCG_PRODUCER_WARPS + UMMA_ISSUERS + 1) * 32)
+
+__device__ __forceinline__ void ts_load_row(float4 (&v)[TS_KCH], const float* p, int k0, int k_end, bool vec_ok) {
+  if (vec_ok && k0 + TS_BK <= k_end) {
+#pragma unroll
+    for (int i = 0; i < TS_KCH; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(p + k0) + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < TS_KCH; ++i) v[i] = umma_load_chunk(p, k0 + 4 * i, k_end, false);
+  }
+}
+
+// split TS_BK floats and store them as one activation stage [32 head columns | 32 tail columns] of this
+// thread's TMEM lane
+__device__ __forceinline__ void ts_store_row(uint32_t taddr_stage, const float4 (&v)[TS_KCH]) {
+#pragma unroll
+  for (int half = 0; half < TS_BK / 16; ++half) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 h, l;
+      tf32_split(v[4 * half + i], h, l);
+      hi[4 * i] = h.x; hi[4 * i + 1] = h.y; hi[4 * i + 2] = h.z; hi[4 * i + 3] = h.w;
+      lo[4 * i] = l.x; lo[4 * i + 1] = l.y; lo[4 * i + 2] = l.z; lo[4 * i + 3] = l.w;
+    }
+    tmem_st16(taddr_stage + 16u * half, hi);
+    tmem_st16(taddr_stage + TS_BK + 16u * half, lo);
+  }
+  tmem_wait_st();
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const GemmArgs g) {
+  extern __shared__ __align__(128) unsigned char tcg_smem[];
+  const int BN = g.bn, S = g.stages;
+  const int w_stage_floats = UMMA_PACK_STAGE_FLOATS(BN);
+  float* stage0 = reinterpret_cast<float*>(tcg_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tcg_smem + (size_t)S * w_stage_floats * sizeof(float));
+  uint64_t* empty = full + TS_MAX_STAGES;
+  uint64_t* done = empty + TS_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  int64_t M = g.M;
+  if (g.count != nullptr) {
+    const int64_t c = (int64_t)(*g.count) * g.rows_per_count;
+    M = c < M ? c : M;
+  }
+  const int64_t m0 = (int64_t)(blockIdx.x / g.tiles_n) * TCG_BM;
+  if (m0 >= M) return;
+  const int n_tile = (int)(blockIdx.x % g.tiles_n);
+  const int n0 = n_tile * BN;
+  const float* __restrict__ A = g.A;
+  const float* __restrict__ bias = g.bias;
+  float* __restrict__ C = g.C;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == TCG_PRODUCER_WARPS * 32) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, TCG_GROUP_WARPS + 1);
+      mbar_init(empty + s, UMMA_ISSUERS);
+    }
+    mbar_init(done, UMMA_ISSUERS);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, g.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t taddr = *tmem_slot;
+  const uint32_t a_ring = taddr + (uint32_t)(UMMA_ACCS * BN);
+  const int n_blocks = (g.K + TS_BK - 1) / TS_BK;
+#ifdef TIGER_TRACE
+  __shared__ long long tr_base_s;
+  if (tid == 0) tr_base_s = clock64();
+  __syncthreads();
+  const long long tr_base = tr_base_s;
+#endif
+  TRACE_DECL
+
+  if (warp < TCG_PRODUCER_WARPS) {
+    // ---------------- producers: thread = row ----------------
+    const int grp = warp / TCG_GROUP_WARPS, q = warp & 3;
+    const int row = q * 32 + lane;
+    int64_t m = m0 + row;
+    m = m < M ? m : M - 1;                 // rows beyond the edge only feed accumulator rows nobody stores
+    const float* rowp = A + m * g.lda;
+    const uint32_t tl = a_ring + ((uint32_t)(q * 32) << 16);
+    const bool vec = g.vec_a != 0;
+    float4 v[TS_KCH];
+    if (grp < n_blocks) ts_load_row(v, rowp, grp * TS_BK, g.K, vec);
+    for (int blk = grp; blk < n_blocks; blk += TCG_GROUPS) {
+      const int s = blk % S;
+      TRACE_MARK();
+      mbar_wait(empty + s, ((blk / S) & 1) ^ 1);
+      TRACE_MARK();
+      ts_store_row(tl + (uint32_t)(s * 2 * TS_BK), v);
+      TRACE_MARK();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + s);
+      // this group's next stage is loaded while the other groups' stages are converted / consumed
+      if (blk + TCG_GROUPS < n_blocks) ts_load_row(v, rowp, (blk + TCG_GROUPS) * TS_BK, g.K, vec);
+    }
+    // ---------------- epilogue ----------------
+    mbar_wait(done, 0);
+    tc_fence_after_sync();
+    const int64_t mr = m0 + row;
+    const bool row_ok = mr < M;
+    const uint32_t tacc = taddr + ((uint32_t)(q * 32) << 16);
+    for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += 16 * (TCG_PRODUCER_WARPS / 4)) {
+      float o[16];
+      tmem_ld16(tacc + (uint32_t)c0, o);
+#pragma unroll
+      for (int j = 1; j < UMMA_ACCS; ++j) {
+        float t[16];
+        tmem_ld16(tacc + (uint32_t)(j * BN + c0), t);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] += t[e];
+      }
+      const int nb = n0 + c0;
+      if (!row_ok || nb >= g.N) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = nb + j;
+        float x = (o[j] + ((bias != nullptr && n < g.N) ? __ldg(bias + n) : 0.f)) * g.alpha;
+        if (g.relu) x = fmaxf(x, 0.f);
+        o[j] = x;
+      }
+      float* dst = C + mr * g.ldc + nb;
+      if (g.vec_c && nb + 16 <= g.N) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < g.N) dst[j] = o[j];
+      }
+    }
+  } else if (warp == TCG_PRODUCER_WARPS + UMMA_ISSUERS) {
+    // ---------------- TMA warp ----------------
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)w_stage_floats * 4u;
+      const float* src = g.wpack + (int64_t)n_tile * n_blocks * w_stage_floats;
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        const int s = blk % S;
+        mbar_wait(empty + s, ((blk / S) & 1) ^ 1);
+        TRACE_MARK();
+        mbar_arrive_expect_tx(full + s, bytes);
+        tma_bulk_load(stage0 + (size_t)s * w_stage_floats, src + (int64_t)blk * w_stage_floats, bytes, full + s);
+      }
+    }
+  } else {
+    // ---------------- MMA issuers ----------------
+    const int role = uniform_warp_idx() - TCG_PRODUCER_WARPS;
+    const uint32_t idesc = umma_idesc_tf32(TCG_BM, BN);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
+    const uint32_t d_even = tbase + (uint32_t)(role * BN), d_odd = role == 2 ? tbase + (uint32_t)(3 * BN) : d_even;
+    const uint32_t a_first = tbase + (uint32_t)(UMMA_ACCS * BN) + (role == 0 ? (uint32_t)TS_BK : 0u);   // role 0: tail columns
+    const uint32_t b_first = umma_desc_lo(smem_addr_u32(stage0) + (role == 1 ? (uint32_t)(TS_KCH * BN * 16) : 0u),
+                                          (uint32_t)BN);
+    const uint32_t b_step = (uint32_t)(w_stage_floats * 4) >> 4, b_kstep = 2u * BN;
+    int s = 0;
+    uint32_t ph = 0, a = a_first, b = b_first;
+    bool ready = mbar_test(full, 0);
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      TRACE_MARK();
+      mbar_wait_probed(ready, full + s, ph);
+      tc_fence_after_sync();
+      TRACE_MARK();
+      // probe the next stage now: its latency overlaps the MMA issue below
+      int s1 = s + 1;
+      uint32_t ph1 = ph;
+      if (s1 == S) {
+        s1 = 0;
+        ph1 ^= 1;
+      }
+      ready = blk + 1 < n_blocks ? mbar_test(full + s1, ph1) : true;
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < TS_BK / 8; ++j) {
+          const uint32_t fresh = (blk == 0 && (j == 0 || (role == 2 && j == 1))) ? 0u : 1u;
+          umma_tf32_ts((j & 1) ? d_odd : d_even, a + 8u * j, b + b_kstep * j, idesc, fresh);
+        }
+        umma_commit(empty + s);
+      }
+      __syncwarp();
+      a += 2u * TS_BK;
+      b += b_step;
+      if (s1 == 0) {
+        a = a_first;
+        b = b_first;
+      }
+      s = s1;
+      ph = ph1;
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+  }
+#ifdef TIGER_TRACE
+  TRACE_MARK();
+  if (warp % TCG_GROUP_WARPS == 0 || warp >= TCG_PRODUCER_WARPS) TRACE_DUMP(warp < TCG_PRODUCER_WARPS ? "producer" : "issuer", warp);
+#endif
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(taddr, g.tmem_cols);
+}
+
 static int g_gemm_sms = 0;
 
 // pack kernel: one thread per (tile, k-block, kc, row)
@@ -286,25 +506,25 @@ __global__ void gemm_pack_weight_kernel(const float* __restrict__ W, int64_t ldw
                                         int n_rows, int k_dim, int bn, int tiles, int n_kb, int vec_ok,
                                         float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)tiles * n_kb * UMMA_KCH * bn;
+  const int64_t total = (int64_t)tiles * n_kb * TS_KCH * bn;
   if (i >= total) return;
   const int r = (int)(i % bn);
-  const int kc = (int)((i / bn) % UMMA_KCH);
-  const int kb = (int)((i / ((int64_t)bn * UMMA_KCH)) % n_kb);
-  const int t = (int)(i / ((int64_t)bn * UMMA_KCH * n_kb));
+  const int kc = (int)((i / bn) % TS_KCH);
+  const int kb = (int)((i / ((int64_t)bn * TS_KCH)) % n_kb);
+  const int t = (int)(i / ((int64_t)bn * TS_KCH * n_kb));
   const int row = row_map != nullptr ? row_map[(int64_t)t * bn + r] : t * bn + r;
-  const int k = kb * UMMA_BK + kc * 4;
+  const int k = kb * TS_BK + kc * 4;
   const float4 v = umma_load_chunk((row >= 0 && row < n_rows) ? W + (int64_t)row * ldw : nullptr, k, k_dim, vec_ok != 0);
   float4 h, l;
   tf32_split(v, h, l);
   float* stage = out + ((int64_t)t * n_kb + kb) * UMMA_PACK_STAGE_FLOATS(bn);
   *reinterpret_cast<float4*>(stage + (kc * bn + r) * 4) = h;
-  *reinterpret_cast<float4*>(stage + UMMA_KCH * bn * 4 + (kc * bn + r) * 4) = l;
+  *reinterpret_cast<float4*>(stage + TS_KCH * bn * 4 + (kc * bn + r) * 4) = l;
 }
 
 extern "C" int64_t tiger_gemm_pack_bytes(int n_tiles, int k_dim, int bn) {
-  if (n_tiles <= 0 || k_dim <= 0 || bn < 16 || bn > TCG_MAX_BN || (bn & 15) != 0) return -1;
-  const int64_t n_kb = (k_dim + UMMA_BK - 1) / UMMA_BK;
+  if (n_tiles <= 0 || k_dim <= 0 || bn < 16 || bn > TS_MAX_BN || (bn & 15) != 0) return -1;
+  const int64_t n_kb = (k_dim + TS_BK - 1) / TS_BK;
   return (int64_t)n_tiles * n_kb * UMMA_PACK_STAGE_FLOATS(bn) * (int64_t)sizeof(float);
 }
 
@@ -313,8 +533,8 @@ extern "C" int tiger_gemm_pack_weight(const float* W, int64_t ldw, const int32_t
   if (W == nullptr || out == nullptr || tiger_gemm_pack_bytes(n_tiles, k_dim, bn) < 0 || n_rows <= 0 || ldw < k_dim ||
       (((uintptr_t)out) & 15) != 0)
     return TIGER_EINVAL;
-  const int n_kb = (k_dim + UMMA_BK - 1) / UMMA_BK;
-  const int64_t total = (int64_t)n_tiles * n_kb * UMMA_KCH * bn;
+  const int n_kb = (k_dim + TS_BK - 1) / TS_BK;
+  const int64_t total = (int64_t)n_tiles * n_kb * TS_KCH * bn;
   const int vec_ok = ((((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0) ? 1 : 0;
   gemm_pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
       W, ldw, row_map, n_rows, k_dim, bn, n_tiles, n_kb, vec_ok, out);
@@ -323,10 +543,10 @@ extern "C" int tiger_gemm_pack_weight(const float* W, int64_t ldw, const int32_t
 
 // column tile width the packed entry point expects for a weight of n_cols rows used with about m_rows
 // activation rows: the widest of 128/64/32 that still yields about one CTA per SM, then balanced
-static int gemm_pick_bn(int64_t m_rows, int n_cols, int batch, int sms) {
+static int gemm_pick_bn(int64_t m_rows, int n_cols, int batch, int sms, int max_bn) {
   const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
   int bn = 32;
-  for (int cand = TCG_MAX_BN; cand >= 32; cand >>= 1) {
+  for (int cand = max_bn; cand >= 32; cand >>= 1) {
     const int64_t tiles = tiles_m * ((n_cols + cand - 1) / cand) * batch;
     if (tiles >= (3 * (int64_t)sms) / 4 || cand == 32) {
       bn = cand;
@@ -345,8 +565,8 @@ static int gemm_sms() {
     if (sms <= 0) sms = 148;
     if (cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TCG_SMEM_BUDGET + 256) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TCG_SMEM_BUDGET + 256) != cudaSuccess)
+        cudaFuncSetAttribute(gemm_tf32x3_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TS_MAX_STAGES * UMMA_PACK_STAGE_FLOATS(TS_MAX_BN) * 4 + 256) != cudaSuccess)
       return -1;
     g_gemm_sms = sms;
   }
@@ -356,7 +576,7 @@ static int gemm_sms() {
 extern "C" int tiger_gemm_pick_bn(int64_t m_rows, int n_cols, int batch) {
   const int sms = gemm_sms();
   if (sms < 0 || m_rows <= 0 || n_cols <= 0 || batch <= 0) return TIGER_EINVAL;
-  return gemm_pick_bn(m_rows, n_cols, batch, sms);
+  return gemm_pick_bn(m_rows, n_cols, batch, sms, TS_MAX_BN);
 }
 
 static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw, int64_t stride_w,
@@ -366,8 +586,8 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
                        void* stream) {
   if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldc < n_cols) return TIGER_EINVAL;
   if (wpack == nullptr && (W == nullptr || ldw < k_dim)) return TIGER_EINVAL;
-  if (wpack != nullptr && (bn_pack < 16 || bn_pack > TCG_MAX_BN || (bn_pack & 15) != 0 || (((uintptr_t)wpack) & 15) != 0 ||
-                           (stride_wpack & 3) != 0))
+  if (wpack != nullptr && (bn_pack < 16 || bn_pack > TS_MAX_BN || (bn_pack & 15) != 0 || (((uintptr_t)wpack) & 15) != 0 ||
+                           batch != 1))
     return TIGER_EINVAL;
   if (m_rows == 0) return TIGER_OK;
   const int sms = gemm_sms();
@@ -384,8 +604,19 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   g.vec_w = (wpack == nullptr && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && (!multi || (stride_w & 3) == 0)) ? 1 : 0;
   g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0 && (!multi || (stride_c & 3) == 0)) ? 1 : 0;
   const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
-  g.bn = wpack != nullptr ? bn_pack : gemm_pick_bn(m_rows, n_cols, batch, sms);
+  g.bn = wpack != nullptr ? bn_pack : gemm_pick_bn(m_rows, n_cols, batch, sms, TCG_MAX_BN);
   g.tiles_n = (n_cols + g.bn - 1) / g.bn;
+  if (wpack != nullptr) {
+    // activations in tensor memory: 4 accumulators + a ring of 32-column stages must fit 512 columns
+    int stages = (512 - UMMA_ACCS * g.bn) / (2 * TS_BK);
+    stages = stages > TS_MAX_STAGES ? TS_MAX_STAGES : stages;
+    g.stages = stages;
+    g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn + stages * 2 * TS_BK));
+    const size_t smem = (size_t)stages * UMMA_PACK_STAGE_FLOATS(g.bn) * 4 + 256;
+    dim3 grid((unsigned)(tiles_m * g.tiles_n), 1);
+    gemm_tf32x3_ts_kernel<<<grid, TS_THREADS, smem, as_stream(stream)>>>(g);
+    return tiger_launch_status();
+  }
   g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn));
   const size_t stage_bytes = (size_t)(2 * UMMA_KCH * TCG_BM * 4 + 2 * UMMA_KCH * g.bn * 4) * sizeof(float);
   int stages = (int)(TCG_SMEM_BUDGET / stage_bytes);
@@ -394,10 +625,7 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   g.stages = stages;
   const size_t smem = stages * stage_bytes + 256;
   dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)batch);
-  if (wpack != nullptr)
-    gemm_tf32x3_kernel<true><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
-  else
-    gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
+  gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
   return tiger_launch_status();
 }
 

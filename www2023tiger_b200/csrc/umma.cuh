@@ -40,6 +40,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe.  Any phase check costs the issuing thread ~150 cycles of latency (measured,
+// tools/issue_bench.cu), so the MMA issuers probe the NEXT stage's barrier before they issue the current
+// stage's MMAs: the probe's latency overlaps the issue, and mbar_wait_probed is free when it succeeded.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_addr_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a pipeline that cannot make progress (a malformed descriptor, a lost arrive) traps
 // after ~2 s instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -58,6 +75,9 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_s
                    smem_addr_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_addr_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void mbar_wait_probed(bool probed_ok, uint64_t* bar, uint32_t parity) {
+  if (!probed_ok) mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma operand reads)
@@ -127,6 +147,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers (whole warp; lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE, descriptor version 1 (sm_100):
@@ -248,7 +281,12 @@ __device__ __forceinline__ void umma_chunk_pos(int wc, int lane, int& row, int& 
 //     pack[tile][k-block][plane: head, tail][kc][row 0..bn-1][4 floats]
 // so that a pipeline stage of B (both planes, bn * 128 bytes) is ONE contiguous TMA bulk copy and costs
 // the SM no instructions.  Rows / columns beyond the matrix are zero.
-#define UMMA_PACK_STAGE_FLOATS(bn) ((bn) * 2 * UMMA_KCH * 4)
+// (the packed / tensor-memory kernels move TS_BK = 32 floats of K per stage: per-stage costs - barrier
+// wait, fence, commit - are paid once per 4 k-steps; measured with tools/umma_bench.cu the MMAs
+// themselves run at their math floor of N/2 cycles when issued back to back)
+#define TS_BK 32
+#define TS_KCH (TS_BK / 4)
+#define UMMA_PACK_STAGE_FLOATS(bn) ((bn) * 2 * TS_KCH * 4)
 
 // ---- MMA issue -------------------------------------------------------------------------------
 // tf32x3: per k-step three MMAs  tail*head, head*tail (cross terms) and head*head.  They are issued by
@@ -281,6 +319,24 @@ __device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI)
+      : "memory");
+}
+
+// Same with the A operand in tensor memory (128 lanes = rows, 8 consecutive 32-bit columns = one k-step):
+// the producers write the split activations straight into TMEM (tcgen05.st), so an MMA reads only its
+// B tile from shared memory - at the narrow tiles of this path the A read of the shared-memory form
+// costs more than the math.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI)
       : "memory");
 }
 
