@@ -265,9 +265,16 @@ __global__ void __launch_bounds__(256) attn_prepare_kernel(const AttArgs a) {
 // flight) - the kernel's time is the latency of those random-row reads, not their volume; the score
 // weights of the query are staged in shared memory once.
 #define ATT_MAXK 64
+// exact f / w for 0 <= f < 2^20 with a float reciprocal (the flattened (slot, column) loops below would
+// otherwise spend more instructions on integer division than on their loads)
+__device__ __forceinline__ int fast_div(int f, float inv_w) { return __float2int_rz(((float)f + 0.5f) * inv_w); }
+
+// HT = number of heads as a compile-time constant (0: any number up to ATT_MAXH, predicated loops)
+template <int HT>
 __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttArgs a) {
   extern __shared__ __align__(16) float att_smem[];
-  const int d = a.dm.d, de = a.dm.de, K = a.dm.K, H = a.dm.H, C = a.dm.C, Cp = a.dm.Cp, Cq = a.dm.Cq;
+  const int d = a.dm.d, de = a.dm.de, K = a.dm.K, H = HT > 0 ? HT : a.dm.H, C = a.dm.C, Cp = a.dm.Cp, Cq = a.dm.Cq;
+  constexpr int HL = HT > 0 ? HT : ATT_MAXH;   // unrolled head loops run over HL, predicated by h < H
   float* kv = att_smem;                 // [K][Cp]
   float* sc = kv + K * Cp;              // [H][K]
   float* qk = sc + ((H * K + 3) & ~3);  // [H][Cq]   score weights of this query
@@ -309,8 +316,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   const bool vec = (d & 3) == 0 && (de & 3) == 0 && (Cp & 3) == 0 &&
                    ((((uintptr_t)a.rows_a | (uintptr_t)a.rows_b | (uintptr_t)a.nfeats | (uintptr_t)a.efeats |
                       (uintptr_t)a.kx | (uintptr_t)a.ky) & 15) == 0);
+  const float inv_d = 1.0f / (float)d, inv_de = 1.0f / (float)de;
   if (vec) {
     const int d4 = d >> 2, de4 = de >> 2;
+    const float inv_d4 = 1.0f / (float)d4, inv_de4 = 1.0f / (float)de4;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int f0 = tid; f0 < K * d4; f0 += 4 * ATT_THREADS) {
       float4 v[4], n4[4];
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
         v[u] = z4;
         n4[u] = z4;
         if (f < K * d4) {
-          const int j = f / d4, c = f - j * d4;
+          const int j = fast_div(f, inv_d4), c = f - j * d4;
           if (s_row[j] != nullptr) {
             v[u] = reinterpret_cast<const float4*>(s_row[j])[c];
             if (s_nf[j] != nullptr) n4[u] = reinterpret_cast<const float4*>(s_nf[j])[c];
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
       for (int u = 0; u < 4; ++u) {
         const int f = f0 + u * ATT_THREADS;
         if (f < K * d4) {
-          const int j = f / d4, c = f - j * d4;
+          const int j = fast_div(f, inv_d4), c = f - j * d4;
           reinterpret_cast<float4*>(kv + j * Cp)[c] =
               make_float4(v[u].x + n4[u].x, v[u].y + n4[u].y, v[u].z + n4[u].z, v[u].w + n4[u].w);
         }
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
         const int f = f0 + u * ATT_THREADS;
         v[u] = z4;
         if (f < K * de4) {
-          const int j = f / de4, c = f - j * de4;
+          const int j = fast_div(f, inv_de4), c = f - j * de4;
           if (s_ef[j] != nullptr) v[u] = reinterpret_cast<const float4*>(s_ef[j])[c];
         }
       }
@@ -352,26 +361,26 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
       for (int u = 0; u < 4; ++u) {
         const int f = f0 + u * ATT_THREADS;
         if (f < K * de4) {
-          const int j = f / de4, c = f - j * de4;
+          const int j = fast_div(f, inv_de4), c = f - j * de4;
           reinterpret_cast<float4*>(kv + j * Cp + d)[c] = v[u];
         }
       }
     }
   } else {
     for (int f = tid; f < K * d; f += ATT_THREADS) {
-      const int j = f / d, c = f - j * d;
+      const int j = fast_div(f, inv_d), c = f - j * d;
       float v = 0.f;
       if (s_row[j] != nullptr) v = s_row[j][c] + (s_nf[j] != nullptr ? s_nf[j][c] : 0.f);
       kv[j * Cp + c] = v;
     }
     for (int f = tid; f < K * de; f += ATT_THREADS) {
-      const int j = f / de, c = f - j * de;
+      const int j = fast_div(f, inv_de), c = f - j * de;
       kv[j * Cp + d + c] = s_ef[j] != nullptr ? s_ef[j][c] : 0.f;
     }
   }
   // ---- time code of every slot ----
   for (int f = tid; f < K * d; f += ATT_THREADS) {
-    const int j = f / d, c = f - j * d;
+    const int j = fast_div(f, inv_d), c = f - j * d;
     float v = 0.f;
     if (s_row[j] != nullptr)
       v = a.dense ? a.kt[(q * K + j) * d + c] : time_enc(s_dt[j], a.time_w[c], a.time_b[c]);
@@ -382,20 +391,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   for (int j = warp; j < K; j += n_warps) {
     const float* row = kv + j * Cp;
     const bool live = s_row[j] != nullptr;
-    float s[ATT_MAXH];
+    float s[HL];
 #pragma unroll
-    for (int h = 0; h < ATT_MAXH; ++h) s[h] = 0.f;
+    for (int h = 0; h < HL; ++h) s[h] = 0.f;
     if (live) {
       for (int c = lane; c < C; c += 32) {
         const float v = row[c];
 #pragma unroll
-        for (int h = 0; h < ATT_MAXH; ++h)
-          if (h < H) s[h] = fmaf(qk[h * Cq + c], v, s[h]);
+        for (int h = 0; h < HL; ++h)
+          if (HT > 0 || h < H) s[h] = fmaf(qk[h * Cq + c], v, s[h]);
       }
     }
 #pragma unroll
-    for (int h = 0; h < ATT_MAXH; ++h) {
-      if (h < H) {
+    for (int h = 0; h < HL; ++h) {
+      if (HT > 0 || h < H) {
         const float t = warp_sum(s[h]);
         if (lane == 0) sc[h * K + j] = live ? t + qk[h * Cq + C] : -INFINITY;
       }
@@ -423,22 +432,32 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   // ---- pooled keys kvbar[h][c] = sum_j p[h][j] kv[j][c] ----
   float* out = a.w.kvc + q * a.dm.ld_kvc;
   for (int c = tid; c < Cp; c += ATT_THREADS) {   // columns C..Cp-1 are alignment padding: written as zeros
-    float acc[ATT_MAXH];
+    float acc[HL];
 #pragma unroll
-    for (int h = 0; h < ATT_MAXH; ++h) acc[h] = 0.f;
+    for (int h = 0; h < HL; ++h) acc[h] = 0.f;
     for (int j = 0; j < (c < C ? K : 0); ++j) {
-      const float v = kv[j * Cp + c];        // padding slots hold garbage, but their weights are exactly 0
+      const float v = kv[j * Cp + c];        // padding slots hold zeros and their weights are exactly 0
 #pragma unroll
-      for (int h = 0; h < ATT_MAXH; ++h)
-        if (h < H) {
-          const float p = sc[h * K + j];
-          if (p != 0.f) acc[h] = fmaf(p, v, acc[h]);
-        }
+      for (int h = 0; h < HL; ++h)
+        if (HT > 0 || h < H) acc[h] = fmaf(sc[h * K + j], v, acc[h]);
     }
 #pragma unroll
-    for (int h = 0; h < ATT_MAXH; ++h)
-      if (h < H) out[h * Cp + c] = acc[h];
+    for (int h = 0; h < HL; ++h)
+      if (HT > 0 || h < H) out[h * Cp + c] = acc[h];
   }
+}
+
+template <int HT>
+static int launch_score_pool(const AttArgs& a, size_t smem, cudaStream_t st) {
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(attn_score_pool_kernel<HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return TIGER_ECUDA;
+    configured = smem;
+  }
+  attn_score_pool_kernel<HT><<<(unsigned)a.n_query, ATT_THREADS, smem, st>>>(a);
+  return tiger_launch_status();
 }
 
 static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cudaStream_t st) {
@@ -457,15 +476,11 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   if (rc != TIGER_OK) return rc;
   const size_t smem = ((size_t)m.K * m.Cp + (size_t)((m.H * m.K + 3) & ~3) + (size_t)m.H * m.Cq) * sizeof(float);
   if (smem > 200 * 1024 || m.K > ATT_MAXK) return TIGER_EINVAL;
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(attn_score_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
-      return TIGER_ECUDA;
-    configured = smem;
-  }
-  attn_score_pool_kernel<<<(unsigned)n, ATT_THREADS, smem, st>>>(a);
-  if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
+  rc = m.H == 2 ? launch_score_pool<2>(a, smem, st)
+       : m.H == 1 ? launch_score_pool<1>(a, smem, st)
+       : m.H == 4 ? launch_score_pool<4>(a, smem, st)
+                  : launch_score_pool<0>(a, smem, st);
+  if (rc != TIGER_OK) return rc;
   // hidden = relu([kvbar | c | live] W2f^T + b1) ; z = hidden W2^T + b2
   rc = tiger_sgemm_nt_packed(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, p->fc1_b, a.w.hid, m.ld_hid, n, nullptr, 1, m.d,
                              m.off_live + 1, 1.0f, 1, s);
