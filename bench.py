@@ -45,7 +45,7 @@ def parse_args():
     p.add_argument('--workload', default='reddit', choices=['wikipedia', 'reddit', 'mooc', 'lastfm', 'scaled'])
     p.add_argument('--events', type=int, default=0, help='override the number of events of the stream')
     p.add_argument('--skip-batches', type=int, default=1000, help='batches skipped so that histories are populated')
-    p.add_argument('--cpu-batches', type=int, default=40, help='bounded sample of the cpu_baseline leg (0 = off)')
+    p.add_argument('--cpu-batches', type=int, default=1000, help='bounded sample of the cpu_baseline leg (0 = off)')
     p.add_argument('--profile-steps', type=int, default=100, help='eager steps with per-kernel CUDA events')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--micro', action='store_true',
@@ -394,7 +394,18 @@ def run_b200(args):
                     'frac': kernels[top]['gbs'] / peak, 'traffic': traffic,
                     'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback',
                     'launch_us': kernels[top]['us'], 'bytes_per_launch': kernels[top]['bytes'],
-                    'counters': counters}
+                    'counters': counters,
+                    'note': 'entry-point granularity (CUDA events around the C-ABI call, eager launches); at batch 200 '
+                            'every kernel is latency bound - see bench.py --micro for the HBM fractions at 256k rows'}
+        # the dense kernel of the path: GRU gate GEMM on the tensor cores (tf32x3: 3 MMAs per useful product)
+        g = kernels.get('tiger_gru_update')
+        if g:
+            flops = 2.0 * counters['O'] * (eng.M + d) * 3 * d
+            tf32_peak = float(peaks.get('bf16_tflops', 1590.0)) / 2.0
+            g['tensor'] = {'bound': 'tensor', 'useful_tflops': flops / (g['us'] * 1e-6) / 1e12,
+                           'issued_tflops': 3.0 * flops / (g['us'] * 1e-6) / 1e12, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                           'frac': 3.0 * flops / (g['us'] * 1e-6) / 1e12 / tf32_peak,
+                           'peak_source': 'half of the measured bf16 GEMM peak (tf32 runs at half the bf16 rate)'}
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N=1 ----
     cpu = None
