@@ -581,12 +581,15 @@ def run_micro(args):
     q_t = torch.from_numpy(np.concatenate([st.ts[-R // 2:], st.ts[-R // 2:]])).to(dev)
     out = (torch.empty(R, K, dtype=i64, device=dev), torch.empty(R, K, dtype=i64, device=dev),
            torch.empty(R, K, dtype=f32, device=dev), None)
-    deg = (csr.indptr[q_n + 1] - csr.indptr[q_n]).double().clamp(min=2)
-    search = float(deg.log2().div(5).ceil().clamp(min=1).mul(32 * 8).mean())     # 32-ary probes of 8 B
+    deg = (csr.indptr[q_n + 1] - csr.indptr[q_n]).double().clamp(min=1)
+    # timestamps probed by the 8-ary lower bound: 8 per round, never more than the segment itself
+    rounds = (deg / 8).clamp(min=1).log2().div(3).ceil() + 1
+    search = float(torch.minimum(deg, rounds * 8).mul(8).mean())
     kk = float(deg.clamp(max=K).mean())
     timed('tiger_find_recent', lambda: ops.find_recent(csr, q_n, q_t, K, out=out),
-          R * (search + kk * 16 + K * 20 + 32),
-          note=f'R queries, mean degree {float(deg.mean()):.0f}: 32-ary lower bound + gather of the last K entries')
+          R * (16 + 16 + search + kk * 17 + K * 20),
+          note=f'R queries, mean degree {float(deg.mean()):.0f}: query + indptr + 8-ary lower bound + gather of the last K '
+               f'entries (4+4+8+1 B) + [K] outputs (8+8+4 B)')
     src_d, dst_d = torch.from_numpy(st.src).to(dev), torch.from_numpy(st.dst).to(dev)
     ts_d, eid_d = torch.from_numpy(st.ts).to(dev), torch.from_numpy(st.eids).to(dev)
     E = st.n_events

@@ -18,8 +18,9 @@ class UpdateModule(nn.Module):
 
 
 class GRUUpdater(UpdateModule):
-    """h' = GRUCell(msg, mem); the kernel reads k-major packs of the four parameters, re-packed
-    whenever a parameter's version counter moves (optimizer steps, load_state_dict)."""
+    """h' = GRUCell(msg, mem); the tensor-core kernel reads the gate weights pre-split into tf32 head / tail
+    planes (ops.GruPack), re-packed whenever a parameter's version counter moves (optimizer steps,
+    load_state_dict)."""
 
     def __init__(self, msg_dim, memory_dim):
         super().__init__(msg_dim, memory_dim)
