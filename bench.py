@@ -98,7 +98,7 @@ def batch_window(args, n_events, rank, world):
     if world > 1:
         lo, hi = chunk_bounds(n_events, rank, world, BATCH, args.seed)
     else:
-        lo = min(args.skip_batches, max(0, n_events // BATCH - 2)) * BATCH
+        lo = min(args.skip_batches, (n_events // BATCH) // 2) * BATCH   # histories populated, at least half the stream left
         hi = n_events
     return lo, (hi - lo) // BATCH
 

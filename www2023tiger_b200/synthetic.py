@@ -67,6 +67,8 @@ class Stream:
             return self.shape.dim
         if self.efeats is not None:
             return self.efeats.shape[1]
+        if self.shape.efeat_dim > 0:      # edge table generated on the device (with_efeats=False)
+            return self.shape.efeat_dim
         raise ValueError('dim undefined')
 
 
