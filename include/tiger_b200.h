@@ -231,6 +231,8 @@ typedef struct {
   const float* time_w;   /* [d] time_encoder.basis_freq                                     */
   const float* time_b;   /* [d] time_encoder.phase                                          */
   float* folded;         /* tiger_attn_fold_bytes() bytes, 16-byte aligned, filled by tiger_attn_fold */
+  float* score_folded;   /* optional: tiger_score_fold blob - the last GEMM then also emits the scorer terms  */
+  float* pq_out;         /* optional per-call output [n_query][2d]: P = W1a z | Q = W1b z (with score_folded) */
 } tiger_attn_params;
 
 /* Folds the projections that are linear in the per-query vectors (exact by linearity, accumulated in
@@ -238,6 +240,16 @@ typedef struct {
  * W2f = [W1a Wo_h Wv_h .. | W1b | W1a (Wo bv + bo)].  Re-run whenever one of the tensors above changes. */
 int64_t tiger_attn_fold_bytes(int d, int de, int n_head);
 int tiger_attn_fold(const tiger_attn_params* params, int d, int de, int n_head, void* stream);
+
+/* Link-scorer fold (tiger.py:259-288): the scorer's first layer is linear in the two embeddings, and the
+ * embeddings are the output of the merger's last layer, so that layer's GEMM can also emit P = W1a z and
+ * Q = W1b z (split output); scoring a pair is then relu(P[s] + Q[t] + c_ab) . w2 + b2 (tiger_link_score_folded).
+ * score_fc1 [d][2d], score_fc1_b [d]: score_fn.fc1.*; merger_fc2 [d][d], merger_fc2_b: the embedding
+ * module's merger.fc2.*; hit_emb [2][d] or NULL (hit_type 'none').  blob: tiger_score_fold_bytes(d) bytes. */
+int64_t tiger_score_fold_bytes(int d);
+int64_t tiger_score_fold_cab_offset(int d);   /* float offset of the c_ab table [4][d] inside the blob */
+int tiger_score_fold(const float* score_fc1, const float* score_fc1_b, const float* merger_fc2,
+                     const float* merger_fc2_b, const float* hit_emb, int d, float* blob, void* stream);
 
 /* bytes of caller-provided, 16-byte aligned workspace for n_query queries */
 int64_t tiger_temporal_attention_work_bytes(int64_t n_query, int k, int d, int de, int n_head);
@@ -275,6 +287,13 @@ int tiger_link_score(const float* h, int64_t batch, int d, const int64_t* src, c
                      const int64_t* neg, const int64_t* neigh_nids, int k, const float* hit_emb,
                      const float* fc1T, const float* fc1_b, const float* fc2_w, const float* fc2_b,
                      float* scores, float* loss, uint32_t* done_counter, void* stream);
+
+/* Folded form of the same step (see tiger_score_fold): pq [3B][2d] = [W1a z | W1b z] rows of [src ; dst ; neg]
+ * from tiger_temporal_attention, cab = blob + tiger_score_fold_cab_offset(d); neigh_nids NULL = hit_type 'none'. */
+int tiger_link_score_folded(const float* pq, int64_t batch, int d, const int64_t* src, const int64_t* dst,
+                            const int64_t* neg, const int64_t* neigh_nids, int k, const float* cab,
+                            const float* fc2_w, const float* fc2_b, float* scores, float* loss,
+                            uint32_t* done_counter, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Restarters (tiger/model/restarters.py, tiger.py:594-609)
@@ -341,6 +360,14 @@ int tiger_gemm_pack_weight(const float* W, int64_t ldw, const int32_t* row_map, 
 int tiger_sgemm_nt_packed(const float* A, int64_t lda, const float* wpack, int bn, const float* bias, float* C,
                           int64_t ldc, int64_t m_rows, const int32_t* count, int64_t rows_per_count, int n_cols,
                           int k_dim, float alpha, int relu, void* stream);
+
+/* Same with a split output: the pack has ceil((n_split + n_cols1) / bn) tiles; result columns [0, n_cols0)
+ * go to C, columns [n_split, n_split + n_cols1) to C2 (n_split a multiple of 16 >= n_cols0; bias is indexed
+ * in the padded column space). */
+int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
+                                float* C, int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split,
+                                int n_cols1, int64_t m_rows, const int32_t* count, int64_t rows_per_count,
+                                int k_dim, float alpha, int relu, void* stream);
 
 /* FFMA (CUDA-core) implementation of the same two operators: the measured baseline the tensor-core
  * kernels are compared with in bench.py --micro and tests; never on the product path. */

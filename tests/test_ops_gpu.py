@@ -355,3 +355,19 @@ def test_seq_restarter_matches_oracle(gu, d, de, L, with_nf):
     assert_close(gu.cpu(hl[:n]), ref_l.numpy(), TOL, 'h_left')
     assert_close(gu.cpu(hr[:n]), ref_r.numpy(), TOL, 'h_right')
     assert np.array_equal(gu.cpu(pt[:n]), ref_pt.numpy())
+
+
+# ------------------------------------------------------------------ packed-weight tensor-core GEMM
+@pytest.mark.parametrize('m,n,k', [(1, 7, 5), (54, 172, 860), (600, 1040, 344), (600, 172, 1205), (2200, 130, 54)])
+def test_sgemm_nt_packed_matches_torch(gu, m, n, k):
+    g = torch.Generator().manual_seed(m * 1000 + n)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k ** 0.5
+    b = torch.randn(n, generator=g)
+    pack = ops.WeightPack(gu.dev(w), m_rows_hint=m)
+    for relu in (False, True):
+        ref = a.double() @ w.double().t() + b.double()
+        ref = torch.relu(ref) if relu else ref
+        out = torch.full((m, n), float('nan'), device='cuda')
+        ops.sgemm_nt_packed(gu.dev(a), pack, gu.dev(b), out, relu=relu)
+        assert_close(gu.cpu(out), ref.numpy(), 2e-6, f'packed gemm {m}x{n}x{k}')

@@ -42,6 +42,11 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_temporal_attention_work_bytes': 'liiii',
     'tiger_temporal_attention': 'ppll' + 'pppi' + 'pppi' + 'pp' + 'iii' + 'ppp' + 'p',
     'tiger_temporal_attention_dense': 'pppppp' + 'li' + 'iii' + 'ppp' + 'p',
+    'tiger_score_fold_bytes': 'i',
+    'tiger_score_fold_cab_offset': 'i',
+    'tiger_score_fold': 'pppppip' + 'p',
+    'tiger_link_score_folded': 'pli' + 'pppp' + 'i' + 'ppp' + 'ppp' + 'p',
+    'tiger_sgemm_nt_packed_split': 'plpippli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
     'tiger_min_time': 'plp' + 'p',
     'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
@@ -95,7 +100,7 @@ def load() -> ctypes.CDLL:
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = [_KIND[c] for c in sig]
-        fn.restype = L if name.endswith('_bytes') else I
+        fn.restype = L if (name.endswith('_bytes') or name.endswith('_offset')) else I
     _lib = lib
     return lib
 

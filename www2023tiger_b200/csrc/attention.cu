@@ -43,6 +43,11 @@ extern "C" int tiger_sgemm_nt_packed(const float* A, int64_t lda, const float* w
                                      int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
                                      void* stream);
 
+extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
+                                           float* C, int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split,
+                                           int n_cols1, int64_t m_rows, const int32_t* count,
+                                           int64_t rows_per_count, int k_dim, float alpha, int relu, void* stream);
+
 #define ATT_MAXH 8
 #define ATT_THREADS 128
 #define ATT_BN_QK 64   // column tile of the Wqk pack: H (C+1) ~ 1000 columns -> ~17 tiles per 128 queries
@@ -128,8 +133,8 @@ extern "C" int64_t tiger_attn_fold_bytes(int d, int de, int n_head) {
 
 // C[m * scm + n] = alpha * sum_k A[m * sam + k * sak] * B[k * sbk + n * sbn] (+ add[m]) ; double accumulation
 __global__ void attn_fold_mm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B,
-                                    int64_t sbk, int64_t sbn, float* __restrict__ C, int64_t scm, int M, int N, int K,
-                                    float alpha, const float* __restrict__ add) {
+                                    int64_t sbk, int64_t sbn, float* C, int64_t scm, int M, int N, int K,
+                                    float alpha, const float* add) {   // add may alias C (in-place accumulate)
   const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
   if (n >= N || m >= M) return;
   double acc = 0.0;
@@ -186,6 +191,84 @@ extern "C" int tiger_attn_fold(const tiger_attn_params* p, int d, int de, int n_
   rc = tiger_gemm_pack_weight(f.w2f, a.ld_kvc, nullptr, d, a.off_live + 1, ATT_BN_D, f.t_d, f.pk_w2f, stream);
   if (rc != TIGER_OK) return rc;
   return tiger_gemm_pack_weight(p->fc2, d, nullptr, d, d, ATT_BN_D, f.t_d, f.pk_fc2, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Link-scorer fold (tiger.py:259-288, basic_modules.py:16-19).  The scorer's first layer is linear in the
+// two embeddings it concatenates: fc1([x + he_a | y + he_b]) = W1a x + W1b y + (W1a he_a + W1b he_b + b1), and
+// the embeddings are themselves z = W2 hid + b2 (the merger's last layer).  So the LAST attention GEMM also
+// emits P = W1a z and Q = W1b z for every query row (rows [W2 ; pad ; W1a W2 ; W1b W2] of one packed weight,
+// split output), and scoring a pair is an elementwise relu(P[s] + Q[t] + c_ab) . w2 - the 17 us weight-
+// streaming scorer kernel becomes a 2 x 688-byte row read per pair.
+//   blob: w3 [n_split + 2d][d] | b3 [n_split + 2d] | cab [4][d] (c_ab, index 2a + b) | tf32 pack of w3
+// ------------------------------------------------------------------------------------------
+struct ScoreFold {
+  float *w3, *b3, *cab, *pack;
+  int n_split, tiles;
+  int64_t total_floats;
+};
+
+static ScoreFold score_fold(int d, float* base) {
+  ScoreFold f;
+  int64_t off = 0;
+  auto take = [&](int64_t cnt) { float* p = base ? base + off : nullptr; off += (cnt + 3) & ~(int64_t)3; return p; };
+  f.n_split = (d + 15) & ~15;
+  const int rows = f.n_split + 2 * d;
+  f.tiles = (rows + ATT_BN_D - 1) / ATT_BN_D;
+  f.w3 = take((int64_t)rows * d);
+  f.b3 = take(rows);
+  f.cab = take(4 * d);
+  f.pack = take(tiger_gemm_pack_bytes(f.tiles, d, ATT_BN_D) / 4);
+  f.total_floats = off;
+  return f;
+}
+
+extern "C" int64_t tiger_score_fold_bytes(int d) {
+  if (d <= 0) return -1;
+  return score_fold(d, nullptr).total_floats * (int64_t)sizeof(float);
+}
+
+// float offset of the c_ab table [4][d] inside the blob (argument of tiger_link_score_folded)
+extern "C" int64_t tiger_score_fold_cab_offset(int d) {
+  if (d <= 0) return -1;
+  float dummy;
+  const ScoreFold f = score_fold(d, &dummy);
+  return (int64_t)(f.cab - &dummy);
+}
+
+extern "C" int tiger_score_fold(const float* score_fc1, const float* score_fc1_b, const float* merger_fc2,
+                                const float* merger_fc2_b, const float* hit_emb, int d, float* blob, void* stream) {
+  if (score_fc1 == nullptr || score_fc1_b == nullptr || merger_fc2 == nullptr || merger_fc2_b == nullptr ||
+      blob == nullptr || d <= 0 || (((uintptr_t)blob) & 15) != 0)
+    return TIGER_EINVAL;
+  const ScoreFold f = score_fold(d, blob);
+  cudaStream_t st = as_stream(stream);
+  const int64_t ld1 = 2 * d;
+  if (cudaMemsetAsync(blob, 0, (size_t)f.total_floats * sizeof(float), st) != cudaSuccess) return TIGER_ECUDA;
+  // rows [0, d): W2 (copy) ; rows [n_split, n_split + d): W1a W2 ; rows [n_split + d, n_split + 2d): W1b W2
+  if (cudaMemcpyAsync(f.w3, merger_fc2, (size_t)d * d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(f.b3, merger_fc2_b, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return TIGER_ECUDA;
+  for (int half = 0; half < 2; ++half) {
+    const float* w1 = score_fc1 + half * d;   // W1a / W1b: columns [half*d, half*d + d) of fc1 [d][2d]
+    fold_mm(st, w1, ld1, 1, merger_fc2, d, 1, f.w3 + (int64_t)(f.n_split + half * d) * d, d, d, d, d, 1.0f, nullptr);
+    fold_mm(st, w1, ld1, 1, merger_fc2_b, 1, 0, f.b3 + f.n_split + half * d, 1, d, 1, d, 1.0f, nullptr);
+  }
+  // c_ab = b1 + W1a he_a + W1b he_b
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      float* c = f.cab + (2 * a + b) * d;
+      if (hit_emb == nullptr) {
+        if (cudaMemcpyAsync(c, score_fc1_b, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+          return TIGER_ECUDA;
+      } else {
+        fold_mm(st, score_fc1, ld1, 1, hit_emb + a * d, 1, 0, c, 1, d, 1, d, 1.0f, score_fc1_b);
+        // second half accumulates onto the first: add = c itself
+        fold_mm(st, score_fc1 + d, ld1, 1, hit_emb + b * d, 1, 0, c, 1, d, 1, d, 1.0f, c);
+      }
+    }
+  if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
+  return tiger_gemm_pack_weight(f.w3, d, nullptr, f.n_split + 2 * d, d, ATT_BN_D, f.tiles, f.pack, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -485,6 +568,12 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   rc = tiger_sgemm_nt_packed(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, p->fc1_b, a.w.hid, m.ld_hid, n, nullptr, 1, m.d,
                              m.off_live + 1, 1.0f, 1, s);
   if (rc != TIGER_OK) return rc;
+  if (p->score_folded != nullptr && p->pq_out != nullptr) {
+    // last GEMM with the link-scorer fold: z -> out, [W1a z | W1b z] -> pq_out
+    const ScoreFold sf = score_fold(m.d, p->score_folded);
+    return tiger_sgemm_nt_packed_split(a.w.hid, m.ld_hid, sf.pack, ATT_BN_D, sf.b3, out, m.d, m.d, p->pq_out, 2 * m.d,
+                                       sf.n_split, 2 * m.d, n, nullptr, 1, m.d, 1.0f, 0, s);
+  }
   return tiger_sgemm_nt_packed(a.w.hid, m.ld_hid, f.pk_fc2, ATT_BN_D, p->fc2_b, out, m.d, n, nullptr, 1, m.d, m.d, 1.0f,
                                0, s);
 }

@@ -66,6 +66,10 @@ struct GemmArgs {
   int vec_a, vec_w, vec_c;  // 16-byte alignment of the rows of A / W / C
   int bn, tiles_n, stages;
   uint32_t tmem_cols;
+  // optional split output (packed variant): columns [0, n_lim0) go to C, columns [n_split, n_split + n_lim1) to C2
+  float* C2;
+  int64_t ldc2;
+  int n_split, n_lim0, n_lim1, vec_c2;
 };
 
 template <bool PACKED>
@@ -419,15 +423,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
         if (g.relu) x = fmaxf(x, 0.f);
         o[j] = x;
       }
-      float* dst = C + mr * g.ldc + nb;
-      if (g.vec_c && nb + 16 <= g.N) {
+      // destination of this 16-column chunk (n_split is a multiple of 16, so a chunk never straddles it)
+      const bool second = g.C2 != nullptr && nb >= g.n_split;
+      const int col = second ? nb - g.n_split : nb, lim = second ? g.n_lim1 : g.n_lim0;
+      float* dst = second ? g.C2 + mr * g.ldc2 + col : C + mr * g.ldc + col;
+      if ((second ? g.vec_c2 : g.vec_c) && col + 16 <= lim) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (nb + j < g.N) dst[j] = o[j];
+          if (col + j < lim) dst[j] = o[j];
       }
     }
   } else if (warp == TCG_PRODUCER_WARPS + UMMA_ISSUERS) {
@@ -583,9 +590,11 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
                        const float* wpack, int64_t stride_wpack, int bn_pack, const float* bias, int64_t stride_bias,
                        float* C, int64_t ldc, int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
                        int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu, const uint8_t* row_zero,
-                       void* stream) {
+                       void* stream, float* C2 = nullptr, int64_t ldc2 = 0, int n_split = 0, int n_cols1 = 0) {
   if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldc < n_cols) return TIGER_EINVAL;
   if (wpack == nullptr && (W == nullptr || ldw < k_dim)) return TIGER_EINVAL;
+  if (C2 != nullptr && (wpack == nullptr || (n_split & 15) != 0 || n_split < n_cols || n_cols1 <= 0 || ldc2 < n_cols1))
+    return TIGER_EINVAL;
   if (wpack != nullptr && (bn_pack < 16 || bn_pack > TS_MAX_BN || (bn_pack & 15) != 0 || (((uintptr_t)wpack) & 15) != 0 ||
                            batch != 1))
     return TIGER_EINVAL;
@@ -598,7 +607,11 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   g.lda = lda; g.ldw = ldw; g.ldc = ldc;
   g.stride_a = stride_a; g.stride_w = stride_w; g.stride_bias = stride_bias; g.stride_c = stride_c;
   g.M = m_rows; g.rows_per_count = rows_per_count > 0 ? rows_per_count : 1;
-  g.N = n_cols; g.K = k_dim; g.alpha = alpha; g.relu = relu;
+  g.N = C2 != nullptr ? n_split + n_cols1 : n_cols;   // columns of the (padded) weight / bias space
+  g.K = k_dim; g.alpha = alpha; g.relu = relu;
+  g.C2 = C2; g.ldc2 = ldc2; g.n_split = n_split; g.n_lim0 = n_cols; g.n_lim1 = n_cols1;
+  g.vec_c2 = (C2 != nullptr && (((uintptr_t)C2) & 15) == 0 && (ldc2 & 3) == 0) ? 1 : 0;
+  n_cols = g.N;
   const bool multi = batch > 1;
   g.vec_a = ((((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && (!multi || (stride_a & 3) == 0)) ? 1 : 0;
   g.vec_w = (wpack == nullptr && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && (!multi || (stride_w & 3) == 0)) ? 1 : 0;
@@ -645,6 +658,15 @@ extern "C" int tiger_sgemm_nt_packed(const float* A, int64_t lda, const float* w
   if (wpack == nullptr) return TIGER_EINVAL;
   return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
                      n_cols, k_dim, alpha, relu, nullptr, stream);
+}
+
+extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
+                                           float* C, int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split,
+                                           int n_cols1, int64_t m_rows, const int32_t* count,
+                                           int64_t rows_per_count, int k_dim, float alpha, int relu, void* stream) {
+  if (wpack == nullptr || C2 == nullptr) return TIGER_EINVAL;
+  return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
+                     n_cols0, k_dim, alpha, relu, nullptr, stream, C2, ldc2, n_split, n_cols1);
 }
 
 extern "C" int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,

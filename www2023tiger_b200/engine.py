@@ -96,6 +96,8 @@ class TigerEngine:
         self.gru_pack = None
         self.attn_pack = ops.AttnPack(self.d, self.de, dev, n_head)
         self.score_pack = ops.ScorePack(self.d, dev)
+        self.score_fold = ops.ScoreFold(self.d, dev)
+        self.pq = torch.zeros(3 * batch_size, 2 * self.d, dtype=f32, device=dev)   # [W1a z | W1b z] per query row
         self.hist_len = hist_len
         self.seq = ops.SeqRestarterOp(self.d, self.de, hist_len, n_head, self.cap, dev) if restarter == 'seq' else None
         self.load_weights(weights)
@@ -120,6 +122,10 @@ class TigerEngine:
         s = 'score_fn.'
         self.score_pack.refresh(g(s + 'fc1.weight'), g(s + 'fc1.bias'), g(s + 'fc2.weight'), g(s + 'fc2.bias'),
                                 g('hit_embedding.weight') if self.hit_type == 'bin' else None)
+        self.score_fold.refresh(g(s + 'fc1.weight'), g(s + 'fc1.bias'), g(s + 'fc2.weight'), g(s + 'fc2.bias'),
+                                g(a + 'merger.fc2.weight'), g(a + 'merger.fc2.bias'),
+                                g('hit_embedding.weight') if self.hit_type == 'bin' else None)
+        self.attn_pack.attach_score_fold(self.score_fold, self.pq)
         if self.restarter == 'static':
             self.left_emb = g('restarter_fn.left_emb.weight')
             self.right_emb = g('restarter_fn.right_emb.weight')
@@ -219,8 +225,8 @@ class TigerEngine:
             ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
                                self.left_active, self.err_flags)
             self._ev_side2.record(self._side)
-        ops.link_score(self.score_pack, self.emb, self.src, self.dst, self.neg,
-                       self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
+        ops.link_score_folded(self.score_fold, self.pq, self.src, self.dst, self.neg,
+                              self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
         main.wait_event(self._ev_side2)
 
     def launches_per_step(self) -> int:

@@ -250,7 +250,7 @@ def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_
 class AttnParamsC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ('wq', 'wk', 'wv', 'wo', 'fc1', 'fc2', 'in_bias', 'out_bias', 'fc1_b', 'fc2_b', 'time_w', 'time_b',
-                 'folded')]
+                 'folded', 'score_folded', 'pq_out')]
 
 
 class AttnPack:
@@ -283,6 +283,13 @@ class AttnPack:
 
     def byref(self):
         return ctypes.addressof(self.struct)
+
+    def attach_score_fold(self, fold: Optional['ScoreFold'], pq_out: Optional[Tensor]):
+        """With a ScoreFold attached the last attention GEMM also emits the link scorer's first layer
+        (pq_out [n_query, 2d]); detach with (None, None)."""
+        self._score_fold, self._pq_out = fold, pq_out
+        self.struct.score_folded = fold.blob.data_ptr() if fold is not None else None
+        self.struct.pq_out = pq_out.data_ptr() if pq_out is not None else None
 
     def work(self, n_query: int, k: int) -> Tensor:
         key = (n_query, k)
@@ -335,6 +342,39 @@ class ScorePack:
         self.fc2_w = fc2_w.detach().reshape(-1).contiguous()
         self.fc2_b = fc2_b.detach().contiguous()
         self.hit_emb = None if hit_emb is None else hit_emb.detach().contiguous()
+
+
+class ScoreFold:
+    """Link scorer folded into the attention's last GEMM (tiger_score_fold): refresh whenever score_fn,
+    the embedding module's merger.fc2 or the hit embedding change."""
+
+    def __init__(self, d: int, device):
+        self.d = d
+        lib = _lib.load()
+        self.blob = torch.zeros(lib.tiger_score_fold_bytes(d) // 4, dtype=f32, device=device)
+        self.cab = self.blob[lib.tiger_score_fold_cab_offset(d):]
+        self.done = torch.zeros(1, dtype=i32, device=device)
+
+    def refresh(self, fc1_w, fc1_b, fc2_w, fc2_b, merger_fc2_w, merger_fc2_b, hit_emb: Optional[Tensor]):
+        det = lambda t: None if t is None else t.detach().to(f32).contiguous()
+        self._keep = [det(t) for t in (fc1_w, fc1_b, merger_fc2_w, merger_fc2_b, hit_emb)]
+        check_cuda(*self._keep)
+        call('tiger_score_fold', *(ptr(t) for t in self._keep), self.d, ptr(self.blob))
+        self.fc2_w = fc2_w.detach().to(f32).reshape(-1).contiguous()
+        self.fc2_b = fc2_b.detach().to(f32).contiguous()
+
+
+def link_score_folded(fold: ScoreFold, pq: Tensor, src: Tensor, dst: Tensor, neg: Tensor,
+                      neigh_nids: Optional[Tensor], scores: Optional[Tensor] = None, loss: Optional[Tensor] = None):
+    B = src.numel()
+    if scores is None:
+        scores = _empty(2 * B, f32, pq)
+    if loss is None:
+        loss = _empty(1, f32, pq)
+    k = neigh_nids.shape[1] if neigh_nids is not None else 0
+    call('tiger_link_score_folded', ptr(pq), B, fold.d, ptr(src), ptr(dst), ptr(neg), ptr(neigh_nids), k, ptr(fold.cab),
+         ptr(fold.fc2_w), ptr(fold.fc2_b), ptr(scores), ptr(loss), ptr(fold.done))
+    return scores, loss
 
 
 def link_score(pack: ScorePack, h: Tensor, src: Tensor, dst: Tensor, neg: Tensor, neigh_nids: Optional[Tensor],
