@@ -47,17 +47,18 @@ csr_hist_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst
   }
 }
 
-// single-CTA exclusive scan of `n` uint32 counters into OutT (uint32 in place, or int64)
-template <typename OutT>
-__global__ void __launch_bounds__(1024) csr_scan_kernel(const uint32_t* in, int64_t n, OutT* out) {
-  __shared__ unsigned long long warp_sums[32];
-  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
-  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
-  const int64_t i0 = (int64_t)tid * per;
-  const int64_t i1 = (i0 + per < n) ? i0 + per : n;
-  unsigned long long s = 0;
-  for (int64_t i = i0; i < i1; ++i) s += in[i];
-  unsigned long long inc = s;
+// Exclusive scan of `n` uint32 counters into OutT (uint32 in place, or int64), three launches:
+// per-chunk sums (one CTA per 8192 counters) -> scan of the chunk sums (one CTA) -> per-chunk scan + offset.
+// (The histogram of one radix pass has 256 x tiles counters - 2 M for 8 M events - and a single-CTA scan
+// of it was 60 % of the build.)
+#define SCAN_THREADS 1024
+#define SCAN_PER_THREAD 8
+#define SCAN_CHUNK (SCAN_THREADS * SCAN_PER_THREAD)
+
+__device__ __forceinline__ unsigned long long block_exscan_u64(unsigned long long v, unsigned long long* total,
+                                                               unsigned long long* warp_sums) {
+  const int lane = lane_id(), warp = warp_id_in_block();
+  unsigned long long inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned long long t = __shfl_up_sync(TIGER_FULL_MASK, inc, o);
@@ -66,22 +67,75 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(const uint32_t* in, int6
   if (lane == 31) warp_sums[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    const unsigned long long v = warp_sums[lane];
-    unsigned long long w = v;
+    const unsigned long long w = warp_sums[lane];
+    unsigned long long s = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(TIGER_FULL_MASK, w, o);
-      if (lane >= o) w += t;
+      const unsigned long long t = __shfl_up_sync(TIGER_FULL_MASK, s, o);
+      if (lane >= o) s += t;
     }
-    warp_sums[lane] = w - v;
+    warp_sums[lane] = s - w;
+    if (lane == 31 && total != nullptr) *total = s;
   }
   __syncthreads();
-  unsigned long long run = inc - s + warp_sums[warp];
+  return inc - v + warp_sums[warp];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) csr_scan_sums_kernel(const uint32_t* __restrict__ in, int64_t n,
+                                                                     unsigned long long* __restrict__ chunk_sums) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long total;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_PER_THREAD; ++i)
+    if (base + i < n) s += in[base + i];
+  block_exscan_u64(s, &total, warp_sums);
+  if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
+}
+
+// exclusive scan of the chunk sums in place (one CTA, any number of chunks)
+__global__ void __launch_bounds__(SCAN_THREADS) csr_scan_chunks_kernel(unsigned long long* chunk_sums, int64_t n_chunks) {
+  __shared__ unsigned long long warp_sums[32];
+  const int64_t per = (n_chunks + SCAN_THREADS - 1) / SCAN_THREADS;
+  const int64_t i0 = (int64_t)threadIdx.x * per, i1 = (i0 + per < n_chunks) ? i0 + per : n_chunks;
+  unsigned long long s = 0;
+  for (int64_t i = i0; i < i1; ++i) s += chunk_sums[i];
+  unsigned long long run = block_exscan_u64(s, nullptr, warp_sums);
   for (int64_t i = i0; i < i1; ++i) {
-    const uint32_t v = in[i];
-    out[i] = (OutT)run;
+    const unsigned long long v = chunk_sums[i];
+    chunk_sums[i] = run;
     run += v;
   }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(SCAN_THREADS) csr_scan_apply_kernel(const uint32_t* in, int64_t n,
+                                                                      const unsigned long long* __restrict__ chunk_offsets,
+                                                                      OutT* out) {
+  __shared__ unsigned long long warp_sums[32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+  uint32_t v[SCAN_PER_THREAD];
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+    v[i] = base + i < n ? in[base + i] : 0u;
+    s += v[i];
+  }
+  unsigned long long run = block_exscan_u64(s, nullptr, warp_sums) + chunk_offsets[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+    if (base + i < n) out[base + i] = (OutT)run;   // in may alias out: every element was read above
+    run += v[i];
+  }
+}
+
+template <typename OutT>
+static void csr_exscan(const uint32_t* in, int64_t n, OutT* out, unsigned long long* chunk_sums, cudaStream_t st) {
+  const int64_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  csr_scan_sums_kernel<<<(unsigned)n_chunks, SCAN_THREADS, 0, st>>>(in, n, chunk_sums);
+  csr_scan_chunks_kernel<<<1, SCAN_THREADS, 0, st>>>(chunk_sums, n_chunks);
+  csr_scan_apply_kernel<OutT><<<(unsigned)n_chunks, SCAN_THREADS, 0, st>>>(in, n, chunk_sums, out);
 }
 
 __global__ void __launch_bounds__(CSR_WARPS * 32)
@@ -132,7 +186,9 @@ static inline int64_t csr_tiles(int64_t n_entries) { return (n_entries + CSR_TIL
 extern "C" int64_t tiger_csr_build_work_bytes(int64_t n_events, int64_t n_nodes) {
   const int64_t n_entries = 2 * n_events;
   const int64_t words = 2 * n_entries + 256 * csr_tiles(n_entries) + (n_nodes + 1);
-  return (words * 4 + 15) / 16 * 16;
+  const int64_t scan_n = 256 * csr_tiles(n_entries) > n_nodes + 1 ? 256 * csr_tiles(n_entries) : n_nodes + 1;
+  const int64_t chunk_words = 2 * ((scan_n + SCAN_CHUNK - 1) / SCAN_CHUNK + 2);   // uint64 chunk sums
+  return ((words + 1 + chunk_words) * 4 + 15) / 16 * 16;
 }
 
 extern "C" int tiger_csr_build(const int64_t* src, const int64_t* dst, const double* ts, const int64_t* eid,
@@ -146,17 +202,19 @@ extern "C" int tiger_csr_build(const int64_t* src, const int64_t* dst, const dou
   uint32_t* perm_b = perm_a + n_entries;
   uint32_t* hist = perm_b + n_entries;
   uint32_t* deg = hist + 256 * n_tiles;
+  unsigned long long* chunk_sums =
+      reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(deg + n_nodes + 1) + 7) & ~(uintptr_t)7);
   cudaMemsetAsync(deg, 0, (size_t)(n_nodes + 1) * sizeof(uint32_t), st);
   if (n_entries > 0)
     csr_iota_degree_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(src, dst, n_entries, perm_a, deg);
-  csr_scan_kernel<int64_t><<<1, 1024, 0, st>>>(deg, n_nodes + 1, indptr);
+  csr_exscan<int64_t>(deg, n_nodes + 1, indptr, chunk_sums, st);
   if (n_entries == 0) return tiger_launch_status();
   int bits = 0;
   while (((int64_t)1 << bits) < n_nodes) ++bits;
   const unsigned tgrid = (unsigned)((n_tiles + CSR_WARPS - 1) / CSR_WARPS);
   for (int shift = 0; shift < bits || shift == 0; shift += 8) {
     csr_hist_kernel<<<tgrid, CSR_WARPS * 32, 0, st>>>(src, dst, perm_a, n_entries, shift, n_tiles, hist);
-    csr_scan_kernel<uint32_t><<<1, 1024, 0, st>>>(hist, 256 * n_tiles, hist);
+    csr_exscan<uint32_t>(hist, 256 * n_tiles, hist, chunk_sums, st);
     csr_scatter_kernel<<<tgrid, CSR_WARPS * 32, 0, st>>>(src, dst, perm_a, perm_b, n_entries, shift, n_tiles, hist);
     uint32_t* t = perm_a;
     perm_a = perm_b;
