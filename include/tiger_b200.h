@@ -369,6 +369,21 @@ int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const float* wpack,
                                 int n_cols1, int64_t m_rows, const int32_t* count, int64_t rows_per_count,
                                 int k_dim, float alpha, int relu, void* stream);
 
+/* Split-K pair for long reductions with few output tiles.  tiger_sgemm_nt_packed_splitk writes
+ * tiger_gemm_splitk_parts(k_dim, k_parts) raw partial products A[:, part] Wpack[:, part]^T to
+ * C_parts + part * part_stride (no bias / activation); tiger_sgemm_nt_packed_sum consumes such partials as its
+ * A operand: A = act(sum_p A_parts[p] + a_bias[k]) is formed while the activations are staged, so no
+ * reduction kernel runs in between.  C2 / n_split / n_cols1 as in tiger_sgemm_nt_packed_split (C2 may be NULL). */
+int tiger_gemm_splitk_parts(int k_dim, int k_parts);
+int tiger_sgemm_nt_packed_splitk(const float* A, int64_t lda, const float* wpack, int bn, float* C_parts, int64_t ldc,
+                                 int64_t part_stride, int k_parts, int64_t m_rows, const int32_t* count,
+                                 int64_t rows_per_count, int n_cols, int k_dim, void* stream);
+int tiger_sgemm_nt_packed_sum(const float* A_parts, int64_t lda, int64_t a_part_stride, int a_parts,
+                              const float* a_bias, int a_relu, const float* wpack, int bn, const float* bias,
+                              float* C, int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split, int n_cols1,
+                              int64_t m_rows, const int32_t* count, int64_t rows_per_count, int k_dim, float alpha,
+                              int relu, void* stream);
+
 /* FFMA (CUDA-core) implementation of the same two operators: the measured baseline the tensor-core
  * kernels are compared with in bench.py --micro and tests; never on the product path. */
 int tiger_sgemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,

@@ -46,6 +46,9 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_score_fold_cab_offset': 'i',
     'tiger_score_fold': 'pppppip' + 'p',
     'tiger_link_score_folded': 'pli' + 'pppp' + 'i' + 'ppp' + 'ppp' + 'p',
+    'tiger_gemm_splitk_parts': 'ii',
+    'tiger_sgemm_nt_packed_splitk': 'plpi' + 'plli' + 'lpl' + 'ii' + 'p',
+    'tiger_sgemm_nt_packed_sum': 'plli' + 'pi' + 'pi' + 'p' + 'pli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_sgemm_nt_packed_split': 'plpippli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
     'tiger_min_time': 'plp' + 'p',

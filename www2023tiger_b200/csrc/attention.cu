@@ -43,6 +43,17 @@ extern "C" int tiger_sgemm_nt_packed(const float* A, int64_t lda, const float* w
                                      int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
                                      void* stream);
 
+extern "C" int tiger_gemm_splitk_parts(int k_dim, int k_parts);
+extern "C" int tiger_sgemm_nt_packed_splitk(const float* A, int64_t lda, const float* wpack, int bn, float* C_parts,
+                                            int64_t ldc, int64_t part_stride, int k_parts, int64_t m_rows,
+                                            const int32_t* count, int64_t rows_per_count, int n_cols, int k_dim,
+                                            void* stream);
+extern "C" int tiger_sgemm_nt_packed_sum(const float* A_parts, int64_t lda, int64_t a_part_stride, int a_parts,
+                                         const float* a_bias, int a_relu, const float* wpack, int bn,
+                                         const float* bias, float* C, int64_t ldc, int n_cols0, float* C2,
+                                         int64_t ldc2, int n_split, int n_cols1, int64_t m_rows,
+                                         const int32_t* count, int64_t rows_per_count, int k_dim, float alpha,
+                                         int relu, void* stream);
 extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
                                            float* C, int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split,
                                            int n_cols1, int64_t m_rows, const int32_t* count,
@@ -52,6 +63,8 @@ extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const fl
 #define ATT_THREADS 128
 #define ATT_BN_QK 64   // column tile of the Wqk pack: H (C+1) ~ 1000 columns -> ~17 tiles per 128 queries
 #define ATT_BN_D 32    // column tile of the W2f / W2 packs: d columns -> ~6 tiles per 128 queries
+#define ATT_KPARTS 4   // split-K of the W2f product (K = H C + d + 1 ~ 1200, only ~30 output tiles): the partial
+                       // sums are added, biased and rectified by the next GEMM while it stages its input
 
 static inline int ru4(int x) { return (x + 3) & ~3; }
 
@@ -86,7 +99,7 @@ static AttWork att_work(const AttDims& a, int64_t n, float* base) {
   w.xq = take(n * a.ld_xq);
   w.qkf = take(n * a.ld_qkf);
   w.kvc = take(n * a.ld_kvc);
-  w.hid = take(n * a.ld_hid);
+  w.hid = take((int64_t)ATT_KPARTS * n * a.ld_hid);   // split-K partial sums of the hidden layer
   w.total_floats = off;
   return w;
 }
@@ -564,18 +577,20 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
        : m.H == 4 ? launch_score_pool<4>(a, smem, st)
                   : launch_score_pool<0>(a, smem, st);
   if (rc != TIGER_OK) return rc;
-  // hidden = relu([kvbar | c | live] W2f^T + b1) ; z = hidden W2^T + b2
-  rc = tiger_sgemm_nt_packed(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, p->fc1_b, a.w.hid, m.ld_hid, n, nullptr, 1, m.d,
-                             m.off_live + 1, 1.0f, 1, s);
+  // hidden = relu([kvbar | c | live] W2f^T + b1) as ATT_KPARTS partial products ; z = hidden W2^T + b2
+  const int kparts = tiger_gemm_splitk_parts(m.off_live + 1, ATT_KPARTS);
+  const int64_t part_stride = n * m.ld_hid;
+  rc = tiger_sgemm_nt_packed_splitk(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, a.w.hid, m.ld_hid, part_stride, kparts, n,
+                                    nullptr, 1, m.d, m.off_live + 1, s);
   if (rc != TIGER_OK) return rc;
   if (p->score_folded != nullptr && p->pq_out != nullptr) {
     // last GEMM with the link-scorer fold: z -> out, [W1a z | W1b z] -> pq_out
     const ScoreFold sf = score_fold(m.d, p->score_folded);
-    return tiger_sgemm_nt_packed_split(a.w.hid, m.ld_hid, sf.pack, ATT_BN_D, sf.b3, out, m.d, m.d, p->pq_out, 2 * m.d,
-                                       sf.n_split, 2 * m.d, n, nullptr, 1, m.d, 1.0f, 0, s);
+    return tiger_sgemm_nt_packed_sum(a.w.hid, m.ld_hid, part_stride, kparts, p->fc1_b, 1, sf.pack, ATT_BN_D, sf.b3, out,
+                                     m.d, m.d, p->pq_out, 2 * m.d, sf.n_split, 2 * m.d, n, nullptr, 1, m.d, 1.0f, 0, s);
   }
-  return tiger_sgemm_nt_packed(a.w.hid, m.ld_hid, f.pk_fc2, ATT_BN_D, p->fc2_b, out, m.d, n, nullptr, 1, m.d, m.d, 1.0f,
-                               0, s);
+  return tiger_sgemm_nt_packed_sum(a.w.hid, m.ld_hid, part_stride, kparts, p->fc1_b, 1, f.pk_fc2, ATT_BN_D, p->fc2_b, out,
+                                   m.d, m.d, nullptr, 0, 0, 0, n, nullptr, 1, m.d, 1.0f, 0, s);
 }
 
 static int attention_entry(AttArgs& a, int k, int d, int de, int n_head, const tiger_attn_params* params, float* out,

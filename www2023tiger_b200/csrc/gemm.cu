@@ -70,6 +70,15 @@ struct GemmArgs {
   float* C2;
   int64_t ldc2;
   int n_split, n_lim0, n_lim1, vec_c2;
+  // optional split-K (packed variant): blockIdx.y = part, every part writes its raw partial sums to
+  // C + part * c_part_stride (no bias / alpha / activation); and its counterpart on the input side: A is
+  // the sum of a_parts partial matrices (+ a_bias[k], ReLU) - the consumer of a split-K product applies the
+  // producer's epilogue while it stages its activations, so no reduction kernel runs in between
+  int k_parts;
+  int64_t c_part_stride;
+  int a_parts, a_relu;
+  int64_t a_part_stride;
+  const float* a_bias;
 };
 
 template <bool PACKED>
@@ -365,7 +374,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
   tc_fence_after_sync();
   const uint32_t taddr = *tmem_slot;
   const uint32_t a_ring = taddr + (uint32_t)(UMMA_ACCS * BN);
-  const int n_blocks = (g.K + TS_BK - 1) / TS_BK;
+  const int n_blocks_all = (g.K + TS_BK - 1) / TS_BK;
+  const int per_part = (n_blocks_all + g.k_parts - 1) / g.k_parts;
+  const int kb0 = (int)blockIdx.y * per_part;                      // first k-block of this part
+  const int n_blocks = (kb0 + per_part < n_blocks_all ? kb0 + per_part : n_blocks_all) - kb0;
 #ifdef TIGER_TRACE
   __shared__ long long tr_base_s;
   if (tid == 0) tr_base_s = clock64();
@@ -384,7 +396,36 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
     const uint32_t tl = a_ring + ((uint32_t)(q * 32) << 16);
     const bool vec = g.vec_a != 0;
     float4 v[TS_KCH];
-    if (grp < n_blocks) ts_load_row(v, rowp, grp * TS_BK, g.K, vec);
+    auto load = [&](int blk) {
+      const int k0 = (kb0 + blk) * TS_BK;
+      ts_load_row(v, rowp, k0, g.K, vec);
+      if (g.a_parts > 1 || g.a_bias != nullptr || g.a_relu) {
+        // A = act(sum of the partial matrices + bias[k]): the epilogue of the split-K product that made it
+        for (int part = 1; part < g.a_parts; ++part) {
+          float4 t[TS_KCH];
+          ts_load_row(t, rowp + part * g.a_part_stride, k0, g.K, vec);
+#pragma unroll
+          for (int i = 0; i < TS_KCH; ++i) {
+            v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < TS_KCH; ++i) {
+          const float4 bb = g.a_bias != nullptr ? umma_load_chunk(g.a_bias, k0 + 4 * i, g.K, false)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
+          if (g.a_relu) {
+            v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f);
+            v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f);
+          }
+          if (k0 + 4 * i + 0 >= g.K) v[i].x = 0.f;   // keep the zero padding of the K tail (bias must not leak in)
+          if (k0 + 4 * i + 1 >= g.K) v[i].y = 0.f;
+          if (k0 + 4 * i + 2 >= g.K) v[i].z = 0.f;
+          if (k0 + 4 * i + 3 >= g.K) v[i].w = 0.f;
+        }
+      }
+    };
+    if (grp < n_blocks) load(grp);
     for (int blk = grp; blk < n_blocks; blk += TCG_GROUPS) {
       const int s = blk % S;
       TRACE_MARK();
@@ -396,7 +437,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
       // this group's next stage is loaded while the other groups' stages are converted / consumed
-      if (blk + TCG_GROUPS < n_blocks) ts_load_row(v, rowp, (blk + TCG_GROUPS) * TS_BK, g.K, vec);
+      if (blk + TCG_GROUPS < n_blocks) load(blk + TCG_GROUPS);
     }
     // ---------------- epilogue ----------------
     mbar_wait(done, 0);
@@ -416,17 +457,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
       }
       const int nb = n0 + c0;
       if (!row_ok || nb >= g.N) continue;
+      if (g.k_parts == 1) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = nb + j;
-        float x = (o[j] + ((bias != nullptr && n < g.N) ? __ldg(bias + n) : 0.f)) * g.alpha;
-        if (g.relu) x = fmaxf(x, 0.f);
-        o[j] = x;
+        for (int j = 0; j < 16; ++j) {
+          const int n = nb + j;
+          float x = (o[j] + ((bias != nullptr && n < g.N) ? __ldg(bias + n) : 0.f)) * g.alpha;
+          if (g.relu) x = fmaxf(x, 0.f);
+          o[j] = x;
+        }
       }
       // destination of this 16-column chunk (n_split is a multiple of 16, so a chunk never straddles it)
       const bool second = g.C2 != nullptr && nb >= g.n_split;
       const int col = second ? nb - g.n_split : nb, lim = second ? g.n_lim1 : g.n_lim0;
-      float* dst = second ? g.C2 + mr * g.ldc2 + col : C + mr * g.ldc + col;
+      float* dst = second ? g.C2 + mr * g.ldc2 + col : C + (int64_t)blockIdx.y * g.c_part_stride + mr * g.ldc + col;
       if ((second ? g.vec_c2 : g.vec_c) && col + 16 <= lim) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
@@ -441,7 +484,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
     // ---------------- TMA warp ----------------
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)w_stage_floats * 4u;
-      const float* src = g.wpack + (int64_t)n_tile * n_blocks * w_stage_floats;
+      const float* src = g.wpack + ((int64_t)n_tile * n_blocks_all + kb0) * w_stage_floats;
       for (int blk = 0; blk < n_blocks; ++blk) {
         const int s = blk % S;
         mbar_wait(empty + s, ((blk / S) & 1) ^ 1);
@@ -590,10 +633,15 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
                        const float* wpack, int64_t stride_wpack, int bn_pack, const float* bias, int64_t stride_bias,
                        float* C, int64_t ldc, int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
                        int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu, const uint8_t* row_zero,
-                       void* stream, float* C2 = nullptr, int64_t ldc2 = 0, int n_split = 0, int n_cols1 = 0) {
+                       void* stream, float* C2 = nullptr, int64_t ldc2 = 0, int n_split = 0, int n_cols1 = 0,
+                       int k_parts = 1, int64_t c_part_stride = 0, int a_parts = 1, int64_t a_part_stride = 0,
+                       const float* a_bias = nullptr, int a_relu = 0) {
   if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldc < n_cols) return TIGER_EINVAL;
   if (wpack == nullptr && (W == nullptr || ldw < k_dim)) return TIGER_EINVAL;
   if (C2 != nullptr && (wpack == nullptr || (n_split & 15) != 0 || n_split < n_cols || n_cols1 <= 0 || ldc2 < n_cols1))
+    return TIGER_EINVAL;
+  if (k_parts < 1 || a_parts < 1 || ((k_parts > 1 || a_parts > 1 || a_bias != nullptr || a_relu) && wpack == nullptr) ||
+      (k_parts > 1 && (C2 != nullptr || c_part_stride < m_rows * ldc)) || (a_parts > 1 && a_part_stride < m_rows * lda))
     return TIGER_EINVAL;
   if (wpack != nullptr && (bn_pack < 16 || bn_pack > TS_MAX_BN || (bn_pack & 15) != 0 || (((uintptr_t)wpack) & 15) != 0 ||
                            batch != 1))
@@ -611,9 +659,15 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   g.K = k_dim; g.alpha = alpha; g.relu = relu;
   g.C2 = C2; g.ldc2 = ldc2; g.n_split = n_split; g.n_lim0 = n_cols; g.n_lim1 = n_cols1;
   g.vec_c2 = (C2 != nullptr && (((uintptr_t)C2) & 15) == 0 && (ldc2 & 3) == 0) ? 1 : 0;
+  const int k_blocks = (k_dim + TS_BK - 1) / TS_BK;
+  g.k_parts = k_parts < k_blocks ? k_parts : k_blocks;              // every part owns at least one k-block
+  g.k_parts = (k_blocks + ((k_blocks + g.k_parts - 1) / g.k_parts) - 1) / ((k_blocks + g.k_parts - 1) / g.k_parts);
+  g.c_part_stride = c_part_stride;
+  g.a_parts = a_parts; g.a_part_stride = a_part_stride; g.a_bias = a_bias; g.a_relu = a_relu;
   n_cols = g.N;
   const bool multi = batch > 1;
-  g.vec_a = ((((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && (!multi || (stride_a & 3) == 0)) ? 1 : 0;
+  g.vec_a = ((((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && (!multi || (stride_a & 3) == 0) &&
+             (a_parts == 1 || (a_part_stride & 3) == 0)) ? 1 : 0;
   g.vec_w = (wpack == nullptr && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && (!multi || (stride_w & 3) == 0)) ? 1 : 0;
   g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0 && (!multi || (stride_c & 3) == 0)) ? 1 : 0;
   const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
@@ -626,7 +680,7 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
     g.stages = stages;
     g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn + stages * 2 * TS_BK));
     const size_t smem = (size_t)stages * UMMA_PACK_STAGE_FLOATS(g.bn) * 4 + 256;
-    dim3 grid((unsigned)(tiles_m * g.tiles_n), 1);
+    dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)g.k_parts);
     gemm_tf32x3_ts_kernel<<<grid, TS_THREADS, smem, as_stream(stream)>>>(g);
     return tiger_launch_status();
   }
@@ -667,6 +721,36 @@ extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const fl
   if (wpack == nullptr || C2 == nullptr) return TIGER_EINVAL;
   return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
                      n_cols0, k_dim, alpha, relu, nullptr, stream, C2, ldc2, n_split, n_cols1);
+}
+
+// number of partial products tiger_sgemm_nt_packed_splitk will actually write for this K (<= k_parts)
+extern "C" int tiger_gemm_splitk_parts(int k_dim, int k_parts) {
+  if (k_dim <= 0 || k_parts < 1) return TIGER_EINVAL;
+  const int k_blocks = (k_dim + TS_BK - 1) / TS_BK;
+  int p = k_parts < k_blocks ? k_parts : k_blocks;
+  const int per = (k_blocks + p - 1) / p;
+  return (k_blocks + per - 1) / per;
+}
+
+extern "C" int tiger_sgemm_nt_packed_splitk(const float* A, int64_t lda, const float* wpack, int bn, float* C_parts,
+                                            int64_t ldc, int64_t part_stride, int k_parts, int64_t m_rows,
+                                            const int32_t* count, int64_t rows_per_count, int n_cols, int k_dim,
+                                            void* stream) {
+  if (wpack == nullptr || C_parts == nullptr) return TIGER_EINVAL;
+  return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, nullptr, 0, C_parts, ldc, 0, 1, m_rows, count,
+                     rows_per_count, n_cols, k_dim, 1.0f, 0, nullptr, stream, nullptr, 0, 0, 0, k_parts, part_stride);
+}
+
+extern "C" int tiger_sgemm_nt_packed_sum(const float* A_parts, int64_t lda, int64_t a_part_stride, int a_parts,
+                                         const float* a_bias, int a_relu, const float* wpack, int bn,
+                                         const float* bias, float* C, int64_t ldc, int n_cols0, float* C2,
+                                         int64_t ldc2, int n_split, int n_cols1, int64_t m_rows,
+                                         const int32_t* count, int64_t rows_per_count, int k_dim, float alpha,
+                                         int relu, void* stream) {
+  if (wpack == nullptr || A_parts == nullptr) return TIGER_EINVAL;
+  return gemm_launch(A_parts, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
+                     n_cols0, k_dim, alpha, relu, nullptr, stream, C2, ldc2, n_split, n_cols1, 1, 0, a_parts,
+                     a_part_stride, a_bias, a_relu);
 }
 
 extern "C" int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
