@@ -369,6 +369,17 @@ int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const float* wpack,
                                 int n_cols1, int64_t m_rows, const int32_t* count, int64_t rows_per_count,
                                 int k_dim, float alpha, int relu, void* stream);
 
+/* Same with a gathered A operand: row m of A is row sel[ids[m]] of rows_b when that index is >= 0 (or rows_a
+ * is NULL), else row ids[m] of rows_a, plus row ids[m] of add_rows when given - the "latest representation of
+ * node u" lookup of compute_embedding_with_computation_graph (temporal_agg_modules.py:210-235: memory row or
+ * the row the GRU just produced, + node features) done by the GEMM's producer warps.  sel is int32 or int64
+ * (sel_is_i64); all three tables have row stride ld_rows. */
+int tiger_sgemm_nt_packed_gather(const int64_t* ids, const void* sel, int sel_is_i64, const float* rows_a,
+                                 const float* rows_b, int64_t ld_rows, const float* add_rows, const float* wpack,
+                                 int bn, const float* bias, float* C, int64_t ldc, int64_t m_rows,
+                                 const int32_t* count, int64_t rows_per_count, int n_cols, int k_dim, float alpha,
+                                 int relu, void* stream);
+
 /* Split-K pair for long reductions with few output tiles.  tiger_sgemm_nt_packed_splitk writes
  * tiger_gemm_splitk_parts(k_dim, k_parts) raw partial products A[:, part] Wpack[:, part]^T to
  * C_parts + part * part_stride (no bias / activation); tiger_sgemm_nt_packed_sum consumes such partials as its

@@ -371,3 +371,31 @@ def test_sgemm_nt_packed_matches_torch(gu, m, n, k):
         out = torch.full((m, n), float('nan'), device='cuda')
         ops.sgemm_nt_packed(gu.dev(a), pack, gu.dev(b), out, relu=relu)
         assert_close(gu.cpu(out), ref.numpy(), 2e-6, f'packed gemm {m}x{n}x{k}')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('m,n,k', [(7, 40, 172), (600, 704, 172), (333, 96, 100)])
+def test_sgemm_nt_packed_gather_matches_torch(gu, m, n, k):
+    """A rows looked up by the producers: rows_b[sel[id]] if sel[id] >= 0 else rows_a[id], + add_rows[id]."""
+    g = torch.Generator().manual_seed(m + n)
+    n_nodes, n_b = 500, 90
+    rows_a = torch.randn(n_nodes, k, generator=g)
+    rows_b = torch.randn(n_b, k, generator=g)
+    add = torch.randn(n_nodes, k, generator=g)
+    sel = torch.full((n_nodes,), -1, dtype=torch.int32)
+    picked = torch.randperm(n_nodes, generator=g)[:n_b]
+    sel[picked] = torch.arange(n_b, dtype=torch.int32)
+    ids = torch.randint(0, n_nodes, (m,), generator=g)
+    w = torch.randn(n, k, generator=g) / k ** 0.5
+    b = torch.randn(n, generator=g)
+    pack = ops.WeightPack(gu.dev(w), m_rows_hint=m)
+    for with_add in (False, True):
+        for sel_dt in (torch.int32, torch.int64):
+            x = torch.where((sel[ids] >= 0)[:, None], rows_b[sel[ids].clamp(min=0).long()], rows_a[ids])
+            if with_add:
+                x = x + add[ids]
+            ref = x.double() @ w.double().t() + b.double()
+            out = torch.full((m, n), float('nan'), device='cuda')
+            ops.sgemm_nt_packed_gather(gu.dev(ids), gu.dev(sel.to(sel_dt)), gu.dev(rows_a), gu.dev(rows_b),
+                                       gu.dev(add) if with_add else None, pack, gu.dev(b), out)
+            assert_close(gu.cpu(out), ref.numpy(), 2e-6, f'gather gemm {m}x{n}x{k} add={with_add}')

@@ -116,6 +116,9 @@ extern "C" int64_t tiger_temporal_attention_work_bytes(int64_t n_query, int k, i
 struct AttFold {
   float *wqk, *bqk, *w2f, *wov, *bov;   // wqk [H*Cq][E], bqk [H*Cq], w2f [d][ld_kvc] ; temporaries wov [E][H*Cp], bov [E]
   float *pk_wqk, *pk_w2f, *pk_fc2;      // tf32 head / tail packs of wqk, w2f and merger.fc2 for the tensor-core GEMM
+  // graph path: the query's time code is the constant cos(time_b) (dt = 0), so its half of Wqk folds into the
+  // bias: bqk_c = bqk + Wqk[:, d:] tq ; pk_wqk_c = pack of Wqk[:, :d] (K = d instead of 2d)
+  float *tq, *bqk_c, *pk_wqk_c;
   int t_qk, t_d;                        // column tiles of the packs
   int64_t total_floats;
 };
@@ -134,8 +137,17 @@ static AttFold att_fold(const AttDims& a, float* base) {
   f.pk_wqk = take(tiger_gemm_pack_bytes(f.t_qk, a.E, ATT_BN_QK) / 4);
   f.pk_w2f = take(tiger_gemm_pack_bytes(f.t_d, a.off_live + 1, ATT_BN_D) / 4);
   f.pk_fc2 = take(tiger_gemm_pack_bytes(f.t_d, a.d, ATT_BN_D) / 4);
+  f.tq = take(a.E - a.d);
+  f.bqk_c = take((int64_t)a.H * a.Cq);
+  f.pk_wqk_c = take(tiger_gemm_pack_bytes(f.t_qk, a.d, ATT_BN_QK) / 4);
   f.total_floats = off;
   return f;
+}
+
+__global__ void attn_fold_time0_kernel(const float* __restrict__ w, const float* __restrict__ b, int n,
+                                       float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) out[c] = time_enc(0.f, w[c], b[c]);
 }
 
 extern "C" int64_t tiger_attn_fold_bytes(int d, int de, int n_head) {
@@ -203,7 +215,15 @@ extern "C" int tiger_attn_fold(const tiger_attn_params* p, int d, int de, int n_
   if (rc != TIGER_OK) return rc;
   rc = tiger_gemm_pack_weight(f.w2f, a.ld_kvc, nullptr, d, a.off_live + 1, ATT_BN_D, f.t_d, f.pk_w2f, stream);
   if (rc != TIGER_OK) return rc;
-  return tiger_gemm_pack_weight(p->fc2, d, nullptr, d, d, ATT_BN_D, f.t_d, f.pk_fc2, stream);
+  rc = tiger_gemm_pack_weight(p->fc2, d, nullptr, d, d, ATT_BN_D, f.t_d, f.pk_fc2, stream);
+  if (rc != TIGER_OK) return rc;
+  if (p->time_w == nullptr || p->time_b == nullptr) return TIGER_EINVAL;
+  // constant query time code folded into the bias (graph path)
+  const int dt = E - d;
+  attn_fold_time0_kernel<<<(dt + 127) / 128, 128, 0, st>>>(p->time_w, p->time_b, dt, f.tq);
+  fold_mm(st, f.wqk + d, E, 1, f.tq, 1, 0, f.bqk_c, 1, H * a.Cq, 1, dt, 1.0f, f.bqk);
+  if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
+  return tiger_gemm_pack_weight(f.wqk, E, nullptr, H * a.Cq, d, ATT_BN_QK, f.t_qk, f.pk_wqk_c, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -374,8 +394,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   float* kv = att_smem;                 // [K][Cp]
   float* sc = kv + K * Cp;              // [H][K]
   float* qk = sc + ((H * K + 3) & ~3);  // [H][Cq]   score weights of this query
-  __shared__ const float* s_row[ATT_MAXK];   // node representation row of slot j (NULL = padding slot)
-  __shared__ const float* s_nf[ATT_MAXK];
+  __shared__ const float* s_row[ATT_MAXK + 1];   // node representation row of slot j (NULL = padding slot)
+  __shared__ const float* s_nf[ATT_MAXK + 1];    // entry K: the query's own (center) row, graph path only
   __shared__ const float* s_ef[ATT_MAXK];
   __shared__ float s_dt[ATT_MAXK];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block(), n_warps = ATT_THREADS / 32;
@@ -406,8 +426,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
     s_nf[tid] = nf;
     s_ef[tid] = ef;
     s_dt[tid] = dt;
+  } else if (tid == K && !a.dense) {
+    const int64_t u = a.center_nids[q];
+    s_row[K] = resolve_row(a, u);
+    s_nf[K] = a.nfeats != nullptr ? a.nfeats + u * d : nullptr;
   }
   __syncthreads();
+  float* out = a.w.kvc + q * a.dm.ld_kvc;
   // ---- gather: node rows (+ node features) and edge-feature rows of all slots ----
   const bool vec = (d & 3) == 0 && (de & 3) == 0 && (Cp & 3) == 0 &&
                    ((((uintptr_t)a.rows_a | (uintptr_t)a.rows_b | (uintptr_t)a.nfeats | (uintptr_t)a.efeats |
@@ -417,6 +442,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
     const int d4 = d >> 2, de4 = de >> 2;
     const float inv_d4 = 1.0f / (float)d4, inv_de4 = 1.0f / (float)de4;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!a.dense) {
+      // the query's own representation: the `c` columns of the second-stage operand (attn_prepare does this on
+      // the dense path); the loads fly with the slot gathers below
+      for (int c = tid; c < d4; c += ATT_THREADS) {
+        float4 v = reinterpret_cast<const float4*>(s_row[K])[c];
+        if (s_nf[K] != nullptr) {
+          const float4 n4 = reinterpret_cast<const float4*>(s_nf[K])[c];
+          v = make_float4(v.x + n4.x, v.y + n4.y, v.z + n4.z, v.w + n4.w);
+        }
+        reinterpret_cast<float4*>(out + a.dm.off_c)[c] = v;
+      }
+    }
     for (int f0 = tid; f0 < K * d4; f0 += 4 * ATT_THREADS) {
       float4 v[4], n4[4];
 #pragma unroll
@@ -463,6 +500,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
       }
     }
   } else {
+    if (!a.dense)
+      for (int c = tid; c < d; c += ATT_THREADS)
+        out[a.dm.off_c + c] = s_row[K][c] + (s_nf[K] != nullptr ? s_nf[K][c] : 0.f);
     for (int f = tid; f < K * d; f += ATT_THREADS) {
       const int j = fast_div(f, inv_d), c = f - j * d;
       float v = 0.f;
@@ -512,6 +552,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
     float* row = sc + tid * K;
     float m = -INFINITY;
     for (int j = 0; j < K; ++j) m = fmaxf(m, row[j]);
+    if (tid == 0 && !a.dense) out[a.dm.off_live] = m == -INFINITY ? 0.f : 1.f;
     if (m == -INFINITY) {
       for (int j = 0; j < K; ++j) row[j] = 0.f;   // every slot is padding: the output row is zero-filled later
     } else {
@@ -526,7 +567,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   }
   __syncthreads();
   // ---- pooled keys kvbar[h][c] = sum_j p[h][j] kv[j][c] ----
-  float* out = a.w.kvc + q * a.dm.ld_kvc;
   for (int c = tid; c < Cp; c += ATT_THREADS) {   // columns C..Cp-1 are alignment padding: written as zeros
     float acc[HL];
 #pragma unroll
@@ -563,12 +603,20 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   a.time_w = p->time_w;
   a.time_b = p->time_b;
   const AttFold f = att_fold(m, p->folded);
-  attn_prepare_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
-  if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
   int rc;
-  // [qk_h | qb_h] = XQ Wqk^T + bqk
-  rc = tiger_sgemm_nt_packed(a.w.xq, m.ld_xq, f.pk_wqk, ATT_BN_QK, f.bqk, a.w.qkf, m.ld_qkf, n, nullptr, 1, m.H * m.Cq,
-                             m.E, 1.0f, 0, s);
+  if (a.dense) {
+    attn_prepare_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a);
+    if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
+    // [qk_h | qb_h] = XQ Wqk^T + bqk
+    rc = tiger_sgemm_nt_packed(a.w.xq, m.ld_xq, f.pk_wqk, ATT_BN_QK, f.bqk, a.w.qkf, m.ld_qkf, n, nullptr, 1,
+                               m.H * m.Cq, m.E, 1.0f, 0, s);
+  } else {
+    // graph path: no gather kernel - the GEMM's producers look the center rows up themselves, and the constant
+    // time code of the query sits in the bias (K = d instead of 2d); attn_score_pool fills the c / live columns
+    rc = tiger_sgemm_nt_packed_gather(a.center_nids, a.sel, a.sel_is_i64, a.rows_a, a.rows_b, m.d, a.nfeats, f.pk_wqk_c,
+                                      ATT_BN_QK, f.bqk_c, a.w.qkf, m.ld_qkf, n, nullptr, 1, m.H * m.Cq, m.d, 1.0f, 0,
+                                      s);
+  }
   if (rc != TIGER_OK) return rc;
   const size_t smem = ((size_t)m.K * m.Cp + (size_t)((m.H * m.K + 3) & ~3) + (size_t)m.H * m.Cq) * sizeof(float);
   if (smem > 200 * 1024 || m.K > ATT_MAXK) return TIGER_EINVAL;

@@ -79,6 +79,22 @@ struct GemmArgs {
   int a_parts, a_relu;
   int64_t a_part_stride;
   const float* a_bias;
+  // optional gathered input (packed variant): row m of A is row sel[ids[m]] of a_alt when that is >= 0 (or A is
+  // NULL), else row ids[m] of A, plus row ids[m] of a_add - the representation lookup of the embedding module
+  // (csrc/attention.cu resolve_row) done by the producer warps instead of a gather kernel in front of the GEMM
+  const int64_t* a_ids;
+  const void* a_sel;
+  int a_sel_i64;
+  const float* a_alt;
+  const float* a_add;
+};
+
+struct GemmGather {
+  const int64_t* ids;
+  const void* sel;
+  int sel_is_i64;
+  const float* alt;
+  const float* add;
 };
 
 template <bool PACKED>
@@ -393,12 +409,28 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
     int64_t m = m0 + row;
     m = m < M ? m : M - 1;                 // rows beyond the edge only feed accumulator rows nobody stores
     const float* rowp = A + m * g.lda;
+    const float* addp = nullptr;
+    if (g.a_ids != nullptr) {
+      const int64_t u = g.a_ids[m];
+      const int64_t r = g.a_sel_i64 ? reinterpret_cast<const int64_t*>(g.a_sel)[u]
+                                    : (int64_t) reinterpret_cast<const int32_t*>(g.a_sel)[u];
+      rowp = (A == nullptr || r >= 0) ? g.a_alt + r * g.lda : A + u * g.lda;
+      if (g.a_add != nullptr) addp = g.a_add + u * g.lda;
+    }
     const uint32_t tl = a_ring + ((uint32_t)(q * 32) << 16);
     const bool vec = g.vec_a != 0;
     float4 v[TS_KCH];
     auto load = [&](int blk) {
       const int k0 = (kb0 + blk) * TS_BK;
       ts_load_row(v, rowp, k0, g.K, vec);
+      if (addp != nullptr) {
+        float4 t[TS_KCH];
+        ts_load_row(t, addp, k0, g.K, vec);
+#pragma unroll
+        for (int i = 0; i < TS_KCH; ++i) {
+          v[i].x += t[i].x; v[i].y += t[i].y; v[i].z += t[i].z; v[i].w += t[i].w;
+        }
+      }
       if (g.a_parts > 1 || g.a_bias != nullptr || g.a_relu) {
         // A = act(sum of the partial matrices + bias[k]): the epilogue of the split-K product that made it
         for (int part = 1; part < g.a_parts; ++part) {
@@ -635,8 +667,11 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
                        int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu, const uint8_t* row_zero,
                        void* stream, float* C2 = nullptr, int64_t ldc2 = 0, int n_split = 0, int n_cols1 = 0,
                        int k_parts = 1, int64_t c_part_stride = 0, int a_parts = 1, int64_t a_part_stride = 0,
-                       const float* a_bias = nullptr, int a_relu = 0) {
+                       const float* a_bias = nullptr, int a_relu = 0, const GemmGather* gather = nullptr) {
   if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldc < n_cols) return TIGER_EINVAL;
+  if (gather != nullptr && (wpack == nullptr || gather->ids == nullptr || gather->sel == nullptr ||
+                            gather->alt == nullptr || a_parts > 1))
+    return TIGER_EINVAL;
   if (wpack == nullptr && (W == nullptr || ldw < k_dim)) return TIGER_EINVAL;
   if (C2 != nullptr && (wpack == nullptr || (n_split & 15) != 0 || n_split < n_cols || n_cols1 <= 0 || ldc2 < n_cols1))
     return TIGER_EINVAL;
@@ -664,10 +699,16 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   g.k_parts = (k_blocks + ((k_blocks + g.k_parts - 1) / g.k_parts) - 1) / ((k_blocks + g.k_parts - 1) / g.k_parts);
   g.c_part_stride = c_part_stride;
   g.a_parts = a_parts; g.a_part_stride = a_part_stride; g.a_bias = a_bias; g.a_relu = a_relu;
+  g.a_ids = nullptr; g.a_sel = nullptr; g.a_sel_i64 = 0; g.a_alt = nullptr; g.a_add = nullptr;
+  if (gather != nullptr) {
+    g.a_ids = gather->ids; g.a_sel = gather->sel; g.a_sel_i64 = gather->sel_is_i64;
+    g.a_alt = gather->alt; g.a_add = gather->add;
+  }
   n_cols = g.N;
   const bool multi = batch > 1;
   g.vec_a = ((((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && (!multi || (stride_a & 3) == 0) &&
-             (a_parts == 1 || (a_part_stride & 3) == 0)) ? 1 : 0;
+             (a_parts == 1 || (a_part_stride & 3) == 0) &&
+             (gather == nullptr || ((((uintptr_t)gather->alt) | ((uintptr_t)gather->add)) & 15) == 0)) ? 1 : 0;
   g.vec_w = (wpack == nullptr && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && (!multi || (stride_w & 3) == 0)) ? 1 : 0;
   g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0 && (!multi || (stride_c & 3) == 0)) ? 1 : 0;
   const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
@@ -751,6 +792,18 @@ extern "C" int tiger_sgemm_nt_packed_sum(const float* A_parts, int64_t lda, int6
   return gemm_launch(A_parts, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
                      n_cols0, k_dim, alpha, relu, nullptr, stream, C2, ldc2, n_split, n_cols1, 1, 0, a_parts,
                      a_part_stride, a_bias, a_relu);
+}
+
+extern "C" int tiger_sgemm_nt_packed_gather(const int64_t* ids, const void* sel, int sel_is_i64, const float* rows_a,
+                                            const float* rows_b, int64_t ld_rows, const float* add_rows,
+                                            const float* wpack, int bn, const float* bias, float* C, int64_t ldc,
+                                            int64_t m_rows, const int32_t* count, int64_t rows_per_count,
+                                            int n_cols, int k_dim, float alpha, int relu, void* stream) {
+  if (wpack == nullptr) return TIGER_EINVAL;
+  const GemmGather gg = {ids, sel, sel_is_i64, rows_b, add_rows};
+  return gemm_launch(rows_a, ld_rows, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count,
+                     rows_per_count, n_cols, k_dim, alpha, relu, nullptr, stream, nullptr, 0, 0, 0, 1, 0, 1, 0, nullptr,
+                     0, &gg);
 }
 
 extern "C" int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,

@@ -219,14 +219,18 @@ compact_involved_fast_kernel(uint32_t* __restrict__ bitmap, int n_words, int64_t
   __shared__ int sm[3][32];
   __shared__ int total[3];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
-  // ---- phase 1: flags of every member node, 4 words per warp in flight ----
-  for (int w0 = warp * 4; w0 < n_words; w0 += 32 * 4) {
-    uint32_t bits[4];
-    uint8_t up[4], hm[4];
+  // ---- phase 0: the bitmap itself (one load per thread), so the flag loads below depend on shared memory only ----
+  for (int w = tid; w < n_words; w += 1024) m_mem[w] = bitmap[w];
+  __syncthreads();
+  // ---- phase 1: flags of every member node, CW words per warp in flight ----
+  constexpr int CW = 8;
+  for (int w0 = warp * CW; w0 < n_words; w0 += 32 * CW) {
+    uint32_t bits[CW];
+    uint8_t up[CW], hm[CW];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CW; ++i) {
       const int w = w0 + i;
-      bits[i] = w < n_words ? bitmap[w] : 0u;
+      bits[i] = w < n_words ? m_mem[w] : 0u;
       up[i] = 1;
       hm[i] = 0;
       const int64_t u = (int64_t)w * 32 + lane;
@@ -236,14 +240,13 @@ compact_involved_fast_kernel(uint32_t* __restrict__ bitmap, int n_words, int64_t
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CW; ++i) {
       const int w = w0 + i;
       const bool member = (bits[i] >> lane) & 1u;
       const bool rst = member && uptodate != nullptr && up[i] == 0;
       const bool pend = member && hm[i] != 0 && !rst;
       const uint32_t br = __ballot_sync(TIGER_FULL_MASK, rst), bp = __ballot_sync(TIGER_FULL_MASK, pend);
       if (lane == 0 && w < n_words) {
-        m_mem[w] = bits[i];
         m_rst[w] = br;
         m_out[w] = bp;
       }

@@ -29,7 +29,7 @@ from ._lib import raise_on_err_flags
 from .ops import f32, f64, i32, i64, u8
 
 KERNELS_PER_STEP = {  # launches of our kernels per batch (for the bench `gpu_launches` field)
-    'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 5, 'select_latest': 1,
+    'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 4, 'select_latest': 1,
     'right_writeback': 1, 'store_messages': 2, 'left_writeback': 1, 'link_score': 1,
 }
 
@@ -93,6 +93,7 @@ class TigerEngine:
         self._side = torch.cuda.Stream(device=dev)
         self._ev_fork, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
         self._ev_fork2, self._ev_side2 = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork0, self._ev_rst = torch.cuda.Event(), torch.cuda.Event()
         self.gru_pack = None
         self.attn_pack = ops.AttnPack(self.d, self.de, dev, n_head)
         self.score_pack = ops.ScorePack(self.d, dev)
@@ -177,23 +178,33 @@ class TigerEngine:
                              uptodate=self.uptodate if self.lazy_restart else None, outdated=self.outdated,
                              gru_row=self.gru_row, restart_nodes=self.restart_nodes if self.lazy_restart else None,
                              err_flags=self.err_flags)
-        if self.lazy_restart and self.restarter == 'static':
-            ops.static_restart(self.restart_nodes, self.cap, self.csr, self.left_emb, self.right_emb, d,
-                               count=self.counts[2:], batch_ts=self.ts32, left_vals=self.left_vals,
-                               left_ts=self.left_ts, left_active=self.left_active, right_vals=self.right_vals,
-                               right_ts=self.right_ts, right_active=self.right_active, has_msg=self.has_msg)
-        elif self.lazy_restart:
-            # TIGER.restart with the seq restarter (tiger.py:594-609, restarters.py:51-114): history at
-            # ts.min() of the batch, surrogate h(t'-) / h(t'+), both memories overwritten without checks
-            # (compact_involved has already dropped the pending-message flags of these nodes)
-            R = self.counts[2:]
-            ops.min_time(self.ts32, self.seq.tmin)
-            self.seq.history(self.csr, self.restart_nodes, self.seq.tmin, self.cap, ts_period=1, count=R)
-            hl, hr, pt = self.seq.forward(self.restart_nodes, self.cap, self.nfeats, self.efeats, count=R)
-            ops.scatter_rows(self.left_vals, self.restart_nodes, hl, ts_table=self.left_ts, ts=pt,
-                             active=self.left_active, count=R)
-            ops.scatter_rows(self.right_vals, self.restart_nodes, hr, ts_table=self.right_ts, ts=pt,
-                             active=self.right_active, count=R)
+        # Fork 0: the restart only writes rows of nodes compact_involved put on the restart list, which it also
+        # removed from the outdated list (csrc/graph.cu: pend = member && has_msg && !rst), i.e. rows the GRU
+        # neither reads nor writes - the restarter runs next to the GRU on the side stream; the attention and
+        # the message builder (same side stream, later) read restarted rows and wait for it.
+        main = torch.cuda.current_stream()
+        if self.lazy_restart:
+            self._ev_fork0.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev_fork0)
+                if self.restarter == 'static':
+                    ops.static_restart(self.restart_nodes, self.cap, self.csr, self.left_emb, self.right_emb, d,
+                                       count=self.counts[2:], batch_ts=self.ts32, left_vals=self.left_vals,
+                                       left_ts=self.left_ts, left_active=self.left_active, right_vals=self.right_vals,
+                                       right_ts=self.right_ts, right_active=self.right_active, has_msg=self.has_msg)
+                else:
+                    # TIGER.restart with the seq restarter (tiger.py:594-609, restarters.py:51-114): history at
+                    # ts.min() of the batch, surrogate h(t'-) / h(t'+), both memories overwritten without checks
+                    # (compact_involved has already dropped the pending-message flags of these nodes)
+                    R = self.counts[2:]
+                    ops.min_time(self.ts32, self.seq.tmin)
+                    self.seq.history(self.csr, self.restart_nodes, self.seq.tmin, self.cap, ts_period=1, count=R)
+                    hl, hr, pt = self.seq.forward(self.restart_nodes, self.cap, self.nfeats, self.efeats, count=R)
+                    ops.scatter_rows(self.left_vals, self.restart_nodes, hl, ts_table=self.left_ts, ts=pt,
+                                     active=self.left_active, count=R)
+                    ops.scatter_rows(self.right_vals, self.restart_nodes, hr, ts_table=self.right_ts, ts=pt,
+                                     active=self.right_active, count=R)
+                self._ev_rst.record(self._side)
         ops.gru_update(self.gru_pack, node_ids=self.outdated, x_table=self.msg_vals, h_table=upd_vals,
                        n_rows=self.cap, out=self.h_new, count=self.counts[1:], msg_ts=self.msg_ts,
                        check_mem_ts=msg_ts_mem, check_equal=(self.msg_src == 'left'), err_flags=self.err_flags)
@@ -202,7 +213,6 @@ class TigerEngine:
         # (right-memory rows of nodes WITH a pending message are read from h_new, csrc/attention.cu
         # resolve_row), so it runs on a side stream next to the attention chain.  Captured in a CUDA graph
         # the two branches become parallel paths of the graph.
-        main = torch.cuda.current_stream()
         self._ev_fork.record(main)
         with torch.cuda.stream(self._side):
             self._side.wait_event(self._ev_fork)
@@ -214,6 +224,8 @@ class TigerEngine:
                                self.nfeats, self.efeats, d, self.de, self.time_w, self.time_b, self.msg_vals,
                                self.msg_ts, self.has_msg, self.err_flags)
             self._ev_side.record(self._side)
+        if self.lazy_restart:
+            main.wait_event(self._ev_rst)
         ops.temporal_attention(self.attn_pack, self.H, self.batch_nids, self.ts32, self.neigh_nids, self.neigh_eids,
                                self.neigh_ts, rows_a=self.right_vals, rows_b=self.h_new, sel=self.gru_row,
                                nfeats=self.nfeats, efeats=self.efeats, out=self.emb)

@@ -445,6 +445,19 @@ def sgemm_nt_packed(a: Tensor, pack: WeightPack, bias: Optional[Tensor], out: Te
     return out
 
 
+def sgemm_nt_packed_gather(ids: Tensor, sel: Tensor, rows_a: Optional[Tensor], rows_b: Tensor, add_rows: Optional[Tensor],
+                           pack: WeightPack, bias: Optional[Tensor], out: Tensor, *, relu: bool = False) -> Tensor:
+    """out[m] = act(W @ x_m + bias) with x_m the latest representation of node ids[m]: rows_b[sel[ids[m]]] when
+    that index is >= 0 (or rows_a is None), else rows_a[ids[m]]; plus add_rows[ids[m]] (node features).  The
+    lookup of compute_embedding_with_computation_graph (temporal_agg_modules.py:210-235) inside the GEMM."""
+    check_cuda(ids, sel, rows_a, rows_b, add_rows, bias, out)
+    assert sel.dtype in (i32, i64) and ids.dtype == i64 and rows_b.stride(0) == pack.k
+    call('tiger_sgemm_nt_packed_gather', ptr(ids), ptr(sel), int(sel.dtype == i64), ptr(rows_a), ptr(rows_b),
+         rows_b.stride(0), ptr(add_rows), ptr(pack.data), pack.bn, ptr(bias), ptr(out), out.stride(0), ids.numel(),
+         None, 1, pack.n, pack.k, 1.0, int(relu))
+    return out
+
+
 def check_cuda_strided(*tensors):
     for t in tensors:
         if not t.is_cuda or t.dtype != f32 or t.dim() != 2 or t.stride(1) != 1:
