@@ -389,6 +389,13 @@ int tiger_gemm_splitk_parts(int k_dim, int k_parts);
 int tiger_sgemm_nt_packed_splitk(const float* A, int64_t lda, const float* wpack, int bn, float* C_parts, int64_t ldc,
                                  int64_t part_stride, int k_parts, int64_t m_rows, const int32_t* count,
                                  int64_t rows_per_count, int n_cols, int k_dim, void* stream);
+/* Split-K with the reduction inside the launch: the k_parts (<= 8) CTAs of an output tile form a thread-block
+ * cluster, exchange their partial tiles through distributed shared memory, sum them in part order
+ * (deterministic) and write act(alpha * (A W^T + bias)) once. */
+int tiger_sgemm_nt_packed_splitk_fused(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
+                                       float* C, int64_t ldc, int k_parts, int64_t m_rows, const int32_t* count,
+                                       int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
+                                       void* stream);
 int tiger_sgemm_nt_packed_sum(const float* A_parts, int64_t lda, int64_t a_part_stride, int a_parts,
                               const float* a_bias, int a_relu, const float* wpack, int bn, const float* bias,
                               float* C, int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split, int n_cols1,

@@ -50,6 +50,7 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_sgemm_nt_packed_splitk': 'plpi' + 'plli' + 'lpl' + 'ii' + 'p',
     'tiger_sgemm_nt_packed_sum': 'plli' + 'pi' + 'pi' + 'p' + 'pli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_sgemm_nt_packed_gather': 'ppi' + 'pplp' + 'pi' + 'ppl' + 'lpl' + 'iifi' + 'p',
+    'tiger_sgemm_nt_packed_splitk_fused': 'plpi' + 'ppl' + 'i' + 'lpl' + 'iifi' + 'p',
     'tiger_sgemm_nt_packed_split': 'plpippli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
     'tiger_min_time': 'plp' + 'p',

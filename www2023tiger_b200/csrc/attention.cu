@@ -60,11 +60,16 @@ extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const fl
                                            int64_t rows_per_count, int k_dim, float alpha, int relu, void* stream);
 
 #define ATT_MAXH 8
-#define ATT_THREADS 128
+#ifndef ATT_THREADS
+#define ATT_THREADS 256
+#endif
 #define ATT_BN_QK 64   // column tile of the Wqk pack: H (C+1) ~ 1000 columns -> ~17 tiles per 128 queries
 #define ATT_BN_D 32    // column tile of the W2f / W2 packs: d columns -> ~6 tiles per 128 queries
-#define ATT_KPARTS 4   // split-K of the W2f product (K = H C + d + 1 ~ 1200, only ~30 output tiles): the partial
-                       // sums are added, biased and rectified by the next GEMM while it stages its input
+#ifndef ATT_BN_F3
+#define ATT_BN_F3 32   // column tile of the last product (fc2, with the scorer fold 3d columns)
+#endif
+#define ATT_KPARTS 4   // split-K of the W2f product (K = H C + d + 1 ~ 1200, only ~30 output tiles): the parts of a
+                       // tile run as one thread-block cluster and sum their partial tiles through DSMEM
 
 static inline int ru4(int x) { return (x + 3) & ~3; }
 
@@ -99,7 +104,7 @@ static AttWork att_work(const AttDims& a, int64_t n, float* base) {
   w.xq = take(n * a.ld_xq);
   w.qkf = take(n * a.ld_qkf);
   w.kvc = take(n * a.ld_kvc);
-  w.hid = take((int64_t)ATT_KPARTS * n * a.ld_hid);   // split-K partial sums of the hidden layer
+  w.hid = take((int64_t)n * a.ld_hid);                // hidden layer of the merger
   w.total_floats = off;
   return w;
 }
@@ -136,7 +141,7 @@ static AttFold att_fold(const AttDims& a, float* base) {
   f.t_d = (a.d + ATT_BN_D - 1) / ATT_BN_D;
   f.pk_wqk = take(tiger_gemm_pack_bytes(f.t_qk, a.E, ATT_BN_QK) / 4);
   f.pk_w2f = take(tiger_gemm_pack_bytes(f.t_d, a.off_live + 1, ATT_BN_D) / 4);
-  f.pk_fc2 = take(tiger_gemm_pack_bytes(f.t_d, a.d, ATT_BN_D) / 4);
+  f.pk_fc2 = take(tiger_gemm_pack_bytes((a.d + ATT_BN_F3 - 1) / ATT_BN_F3, a.d, ATT_BN_F3) / 4);
   f.tq = take(a.E - a.d);
   f.bqk_c = take((int64_t)a.H * a.Cq);
   f.pk_wqk_c = take(tiger_gemm_pack_bytes(f.t_qk, a.d, ATT_BN_QK) / 4);
@@ -215,7 +220,7 @@ extern "C" int tiger_attn_fold(const tiger_attn_params* p, int d, int de, int n_
   if (rc != TIGER_OK) return rc;
   rc = tiger_gemm_pack_weight(f.w2f, a.ld_kvc, nullptr, d, a.off_live + 1, ATT_BN_D, f.t_d, f.pk_w2f, stream);
   if (rc != TIGER_OK) return rc;
-  rc = tiger_gemm_pack_weight(p->fc2, d, nullptr, d, d, ATT_BN_D, f.t_d, f.pk_fc2, stream);
+  rc = tiger_gemm_pack_weight(p->fc2, d, nullptr, d, d, ATT_BN_F3, (d + ATT_BN_F3 - 1) / ATT_BN_F3, f.pk_fc2, stream);
   if (rc != TIGER_OK) return rc;
   if (p->time_w == nullptr || p->time_b == nullptr) return TIGER_EINVAL;
   // constant query time code folded into the bias (graph path)
@@ -247,11 +252,11 @@ static ScoreFold score_fold(int d, float* base) {
   auto take = [&](int64_t cnt) { float* p = base ? base + off : nullptr; off += (cnt + 3) & ~(int64_t)3; return p; };
   f.n_split = (d + 15) & ~15;
   const int rows = f.n_split + 2 * d;
-  f.tiles = (rows + ATT_BN_D - 1) / ATT_BN_D;
+  f.tiles = (rows + ATT_BN_F3 - 1) / ATT_BN_F3;
   f.w3 = take((int64_t)rows * d);
   f.b3 = take(rows);
   f.cab = take(4 * d);
-  f.pack = take(tiger_gemm_pack_bytes(f.tiles, d, ATT_BN_D) / 4);
+  f.pack = take(tiger_gemm_pack_bytes(f.tiles, d, ATT_BN_F3) / 4);
   f.total_floats = off;
   return f;
 }
@@ -301,7 +306,7 @@ extern "C" int tiger_score_fold(const float* score_fc1, const float* score_fc1_b
       }
     }
   if (tiger_launch_status() != TIGER_OK) return TIGER_ECUDA;
-  return tiger_gemm_pack_weight(f.w3, d, nullptr, f.n_split + 2 * d, d, ATT_BN_D, f.tiles, f.pack, stream);
+  return tiger_gemm_pack_weight(f.w3, d, nullptr, f.n_split + 2 * d, d, ATT_BN_F3, f.tiles, f.pack, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -625,20 +630,20 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
        : m.H == 4 ? launch_score_pool<4>(a, smem, st)
                   : launch_score_pool<0>(a, smem, st);
   if (rc != TIGER_OK) return rc;
-  // hidden = relu([kvbar | c | live] W2f^T + b1) as ATT_KPARTS partial products ; z = hidden W2^T + b2
+  // hidden = relu([kvbar | c | live] W2f^T + b1): the long K is split over a cluster of ATT_KPARTS CTAs per tile whose
+  // partial tiles are summed through distributed shared memory ; z = hidden W2^T + b2
   const int kparts = tiger_gemm_splitk_parts(m.off_live + 1, ATT_KPARTS);
-  const int64_t part_stride = n * m.ld_hid;
-  rc = tiger_sgemm_nt_packed_splitk(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, a.w.hid, m.ld_hid, part_stride, kparts, n,
-                                    nullptr, 1, m.d, m.off_live + 1, s);
+  rc = tiger_sgemm_nt_packed_splitk_fused(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, p->fc1_b, a.w.hid, m.ld_hid, kparts, n,
+                                          nullptr, 1, m.d, m.off_live + 1, 1.0f, 1, s);
   if (rc != TIGER_OK) return rc;
   if (p->score_folded != nullptr && p->pq_out != nullptr) {
     // last GEMM with the link-scorer fold: z -> out, [W1a z | W1b z] -> pq_out
     const ScoreFold sf = score_fold(m.d, p->score_folded);
-    return tiger_sgemm_nt_packed_sum(a.w.hid, m.ld_hid, part_stride, kparts, p->fc1_b, 1, sf.pack, ATT_BN_D, sf.b3, out,
-                                     m.d, m.d, p->pq_out, 2 * m.d, sf.n_split, 2 * m.d, n, nullptr, 1, m.d, 1.0f, 0, s);
+    return tiger_sgemm_nt_packed_split(a.w.hid, m.ld_hid, sf.pack, ATT_BN_F3, sf.b3, out, m.d, m.d, p->pq_out, 2 * m.d,
+                                       sf.n_split, 2 * m.d, n, nullptr, 1, m.d, 1.0f, 0, s);
   }
-  return tiger_sgemm_nt_packed_sum(a.w.hid, m.ld_hid, part_stride, kparts, p->fc1_b, 1, f.pk_fc2, ATT_BN_D, p->fc2_b, out,
-                                   m.d, m.d, nullptr, 0, 0, 0, n, nullptr, 1, m.d, 1.0f, 0, s);
+  return tiger_sgemm_nt_packed(a.w.hid, m.ld_hid, f.pk_fc2, ATT_BN_F3, p->fc2_b, out, m.d, n, nullptr, 1, m.d, m.d, 1.0f,
+                               0, s);
 }
 
 static int attention_entry(AttArgs& a, int k, int d, int de, int n_head, const tiger_attn_params* params, float* out,

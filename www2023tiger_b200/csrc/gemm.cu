@@ -76,6 +76,9 @@ struct GemmArgs {
   // producer's epilogue while it stages its activations, so no reduction kernel runs in between
   int k_parts;
   int64_t c_part_stride;
+  // cluster_reduce: the k_parts CTAs of a tile form a thread-block cluster; partial tiles are exchanged through
+  // distributed shared memory, summed in part order (deterministic), biased / activated and written once
+  int cluster_reduce;
   int a_parts, a_relu;
   int64_t a_part_stride;
   const float* a_bias;
@@ -487,6 +490,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
 #pragma unroll
         for (int e = 0; e < 16; ++e) o[e] += t[e];
       }
+      if (g.cluster_reduce) {
+        float* dst = stage0 + row * (BN + 4) + c0;       // the weight ring is idle once `done` has fired
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        continue;
+      }
       const int nb = n0 + c0;
       if (!row_ok || nb >= g.N) continue;
       if (g.k_parts == 1) {
@@ -576,6 +586,42 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
   TRACE_MARK();
   if (warp % TCG_GROUP_WARPS == 0 || warp >= TCG_PRODUCER_WARPS) TRACE_DUMP(warp < TCG_PRODUCER_WARPS ? "producer" : "issuer", warp);
 #endif
+  if (g.cluster_reduce) {
+    __syncwarp();
+    cluster_sync_all();                       // every part's tile sits in its CTA's shared memory
+    const int kp = g.k_parts, rank = (int)cluster_cta_rank();
+    const int rb = (TCG_BM + kp - 1) / kp;    // rows this CTA finishes
+    const int r0 = rank * rb, r1 = r0 + rb < TCG_BM ? r0 + rb : TCG_BM;
+    const int c4n = BN >> 2;
+    const uint32_t red = smem_addr_u32(stage0);
+    for (int i = tid; i < (r1 - r0) * c4n; i += TS_THREADS) {
+      const int row = r0 + i / c4n, c = (i % c4n) * 4;
+      const int64_t mr = m0 + row;
+      const int n = n0 + c;
+      if (mr >= M || n >= g.N) continue;
+      const uint32_t off = (uint32_t)(row * (BN + 4) + c) * 4u;
+      float4 acc = cluster_ld_f4(cluster_map_shared(red + off, 0));
+      for (int part = 1; part < kp; ++part) {
+        const float4 t = cluster_ld_f4(cluster_map_shared(red + off, (uint32_t)part));
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = (o[j] + ((bias != nullptr && n + j < g.N) ? __ldg(bias + n + j) : 0.f)) * g.alpha;
+        o[j] = g.relu ? fmaxf(x, 0.f) : x;
+      }
+      float* dst = C + mr * g.ldc + n;
+      if (g.vec_c && n + 4 <= g.n_lim0) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < g.n_lim0) dst[j] = o[j];
+      }
+    }
+    cluster_sync_all();                       // nobody leaves while a peer still reads its tile
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(taddr, g.tmem_cols);
@@ -667,7 +713,8 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
                        int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu, const uint8_t* row_zero,
                        void* stream, float* C2 = nullptr, int64_t ldc2 = 0, int n_split = 0, int n_cols1 = 0,
                        int k_parts = 1, int64_t c_part_stride = 0, int a_parts = 1, int64_t a_part_stride = 0,
-                       const float* a_bias = nullptr, int a_relu = 0, const GemmGather* gather = nullptr) {
+                       const float* a_bias = nullptr, int a_relu = 0, const GemmGather* gather = nullptr,
+                       int cluster_reduce = 0) {
   if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldc < n_cols) return TIGER_EINVAL;
   if (gather != nullptr && (wpack == nullptr || gather->ids == nullptr || gather->sel == nullptr ||
                             gather->alt == nullptr || a_parts > 1))
@@ -676,7 +723,8 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   if (C2 != nullptr && (wpack == nullptr || (n_split & 15) != 0 || n_split < n_cols || n_cols1 <= 0 || ldc2 < n_cols1))
     return TIGER_EINVAL;
   if (k_parts < 1 || a_parts < 1 || ((k_parts > 1 || a_parts > 1 || a_bias != nullptr || a_relu) && wpack == nullptr) ||
-      (k_parts > 1 && (C2 != nullptr || c_part_stride < m_rows * ldc)) || (a_parts > 1 && a_part_stride < m_rows * lda))
+      (k_parts > 1 && !cluster_reduce && (C2 != nullptr || c_part_stride < m_rows * ldc)) ||
+      (a_parts > 1 && a_part_stride < m_rows * lda) || (cluster_reduce && (C2 != nullptr || k_parts > 8)))
     return TIGER_EINVAL;
   if (wpack != nullptr && (bn_pack < 16 || bn_pack > TS_MAX_BN || (bn_pack & 15) != 0 || (((uintptr_t)wpack) & 15) != 0 ||
                            batch != 1))
@@ -697,7 +745,8 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   const int k_blocks = (k_dim + TS_BK - 1) / TS_BK;
   g.k_parts = k_parts < k_blocks ? k_parts : k_blocks;              // every part owns at least one k-block
   g.k_parts = (k_blocks + ((k_blocks + g.k_parts - 1) / g.k_parts) - 1) / ((k_blocks + g.k_parts - 1) / g.k_parts);
-  g.c_part_stride = c_part_stride;
+  g.c_part_stride = cluster_reduce ? 0 : c_part_stride;
+  g.cluster_reduce = (cluster_reduce && g.k_parts > 1) ? 1 : 0;
   g.a_parts = a_parts; g.a_part_stride = a_part_stride; g.a_bias = a_bias; g.a_relu = a_relu;
   g.a_ids = nullptr; g.a_sel = nullptr; g.a_sel_i64 = 0; g.a_alt = nullptr; g.a_add = nullptr;
   if (gather != nullptr) {
@@ -722,6 +771,23 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
     g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn + stages * 2 * TS_BK));
     const size_t smem = (size_t)stages * UMMA_PACK_STAGE_FLOATS(g.bn) * 4 + 256;
     dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)g.k_parts);
+    if (g.cluster_reduce) {
+      if ((size_t)TCG_BM * (g.bn + 4) * 4 > (size_t)stages * UMMA_PACK_STAGE_FLOATS(g.bn) * 4) return TIGER_EINVAL;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(TS_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = as_stream(stream);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = (unsigned)g.k_parts;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaLaunchKernelEx(&cfg, gemm_tf32x3_ts_kernel, g) != cudaSuccess) return TIGER_ECUDA;
+      return tiger_launch_status();
+    }
     gemm_tf32x3_ts_kernel<<<grid, TS_THREADS, smem, as_stream(stream)>>>(g);
     return tiger_launch_status();
   }
@@ -780,6 +846,16 @@ extern "C" int tiger_sgemm_nt_packed_splitk(const float* A, int64_t lda, const f
   if (wpack == nullptr || C_parts == nullptr) return TIGER_EINVAL;
   return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, nullptr, 0, C_parts, ldc, 0, 1, m_rows, count,
                      rows_per_count, n_cols, k_dim, 1.0f, 0, nullptr, stream, nullptr, 0, 0, 0, k_parts, part_stride);
+}
+
+extern "C" int tiger_sgemm_nt_packed_splitk_fused(const float* A, int64_t lda, const float* wpack, int bn,
+                                                  const float* bias, float* C, int64_t ldc, int k_parts,
+                                                  int64_t m_rows, const int32_t* count, int64_t rows_per_count,
+                                                  int n_cols, int k_dim, float alpha, int relu, void* stream) {
+  if (wpack == nullptr || C == nullptr || k_parts < 1 || k_parts > 8) return TIGER_EINVAL;
+  return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
+                     n_cols, k_dim, alpha, relu, nullptr, stream, nullptr, 0, 0, 0, k_parts, 0, 1, 0, nullptr, 0,
+                     nullptr, 1);
 }
 
 extern "C" int tiger_sgemm_nt_packed_sum(const float* A_parts, int64_t lda, int64_t a_part_stride, int a_parts,

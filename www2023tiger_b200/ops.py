@@ -445,6 +445,15 @@ def sgemm_nt_packed(a: Tensor, pack: WeightPack, bias: Optional[Tensor], out: Te
     return out
 
 
+def sgemm_nt_packed_splitk_fused(a: Tensor, pack: WeightPack, bias: Optional[Tensor], out: Tensor, k_parts: int, *,
+                                 relu: bool = False, alpha: float = 1.0) -> Tensor:
+    """As sgemm_nt_packed with K split over a thread-block cluster of k_parts CTAs per tile (DSMEM reduction)."""
+    check_cuda_strided(a, out)
+    call('tiger_sgemm_nt_packed_splitk_fused', ptr(a), a.stride(0), ptr(pack.data), pack.bn, ptr(bias), ptr(out),
+         out.stride(0), k_parts, a.shape[0], None, 1, pack.n, pack.k, float(alpha), int(relu))
+    return out
+
+
 def sgemm_nt_packed_gather(ids: Tensor, sel: Tensor, rows_a: Optional[Tensor], rows_b: Tensor, add_rows: Optional[Tensor],
                            pack: WeightPack, bias: Optional[Tensor], out: Tensor, *, relu: bool = False) -> Tensor:
     """out[m] = act(W @ x_m + bias) with x_m the latest representation of node ids[m]: rows_b[sel[ids[m]]] when
