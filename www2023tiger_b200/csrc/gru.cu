@@ -5,11 +5,15 @@
 //   r = s(Wir x + bir + Whr h + bhr)   z = s(Wiz x + biz + Whz h + bhz)
 //   n = tanh(Win x + bin + r*(Whn h + bhn))   h' = (h - n)*z + n
 //
-// One CTA = 128 gathered rows x U = 32 hidden units.  Accumulator set in TMEM: [128 x 4U] fp32 with the
-// column groups [ Win x | r | z | Whn h ].  The K loop runs over the message columns first (x phase: one
-// MMA of N = 3U per k-step into [Win x | r | z], weight tile rows [n | r | z] of weight_ih) and then over
-// the state columns (h phase: N = 2U accumulating into [r | z] and N = U into [Whn h], weight tile rows
-// [r | z | n] of weight_hh), in tf32x3 (umma.cuh) so the result keeps fp32 accuracy.
+// One output tile = 128 gathered rows x U = 48 hidden units, computed by a CLUSTER OF TWO CTAs that split the
+// K loop in halves (at O ~ 1,900 rows there are only 15 x 4 tiles for 148 SMs, and a CTA's time is its number
+// of K stages).  Accumulator set in TMEM: [128 x 4U] fp32 with the column groups [ Win x | r | z | Whn h ].
+// The K loop runs over the message columns first (x phase: one MMA of N = 3U per k-step into
+// [Win x | r | z], weight tile rows [n | r | z] of weight_ih) and then over the state columns (h phase:
+// N = 2U accumulating into [r | z] and N = U into [Whn h], weight tile rows [r | z | n] of weight_hh), in
+// tf32x3 (umma.cuh) so the result keeps fp32 accuracy.  Each CTA leaves its partial tile in shared memory;
+// after a cluster barrier CTA r adds both partials of rows [64r, 64r + 64) through distributed shared
+// memory (fixed order: deterministic) and applies the gates.
 //
 // Data movement (everything the tensor core reads is produced without shared-memory traffic from the SM):
 //   activations  the 16 producer warps (2 groups x 8 warps; two threads per row, 64 bytes each) gather
@@ -22,10 +26,10 @@
 //   weights      pre-split once per parameter update (tiger_gru_pack) into the shared-memory image of
 //                every stage; one TMA bulk copy per stage into a 6-stage ring
 //   MMA issue    two warps (one elected thread each): X issues the cross terms tail*head + head*tail
-//                into accumulator set 0, Y the head*head terms alternating between sets 1 and 2 (the
-//                tensor core truncates when it accumulates; spreading the large products over two
-//                accumulators halves that bias); 3 sets x 128 + 2 x 64 activation columns = 512 TMEM columns
-//   epilogue     the producer warps add the three partial sets and apply the gates out of TMEM
+//                into accumulator set 0, Y the head*head terms into set 1 (the tensor core truncates when
+//                it accumulates, a bias that grows with the number of accumulation steps: the K split
+//                halves the steps per accumulator); 2 sets x 192 + 2 x 64 activation columns = 512 TMEM columns
+//   epilogue     the producer warps add the two sets out of TMEM into the shared-memory partial tile
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -35,16 +39,20 @@
 #define GRU_ISSUERS 2
 #define GRU_THREADS ((GRU_PRODUCER_WARPS + GRU_ISSUERS + 1) * 32)   // + the TMA warp
 #define GRU_BM 128
-#define GRU_U 32                       // hidden units per CTA (multiple of 16)
+#define GRU_U 48                       // hidden units per tile (multiple of 16)
+#define GRU_KPARTS 2                   // CTAs per tile (cluster size): each runs half of the K stages
 #define GRU_WROWS (3 * GRU_U)          // weight rows per stage
 #define GRU_ACC_COLS (4 * GRU_U)       // one accumulator set: [ Win x | r | z | Whn h ]
-#define GRU_SETS 3
+#define GRU_SETS 2
 #define GRU_A_STAGES 2
 #define GRU_W_STAGES 6
 #define GRU_A_RING (GRU_SETS * GRU_ACC_COLS)                          // first TMEM column of the activation ring
 #define GRU_TMEM_COLS 512
 #define GRU_W_STAGE_FLOATS UMMA_PACK_STAGE_FLOATS(GRU_WROWS)
 #define GRU_SMEM_BYTES (GRU_W_STAGES * GRU_W_STAGE_FLOATS * 4 + 4 * GRU_U * 4 + 256)
+#define GRU_RED_LD (GRU_ACC_COLS + 4)   // row stride of the partial tile parked in the (idle) weight ring
+static_assert(GRU_BM * GRU_RED_LD <= GRU_W_STAGES * GRU_W_STAGE_FLOATS, "partial tile must fit the weight ring");
+static_assert(GRU_SETS * GRU_ACC_COLS + GRU_A_STAGES * 2 * TS_BK <= GRU_TMEM_COLS, "TMEM budget");
 
 struct GruArgs {
   const int64_t* node_ids;
@@ -115,6 +123,13 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
   const uint32_t taddr = *tmem_slot;
   const int nbx = (m_dim + TS_BK - 1) / TS_BK, nbh = (d + TS_BK - 1) / TS_BK;
   const int n_blocks = nbx + nbh;
+  // this CTA's share of the K stages: [b0, b1)
+  const int part = (int)blockIdx.z;
+  const int per_part = (n_blocks + GRU_KPARTS - 1) / GRU_KPARTS;
+  const int b0 = part * per_part < n_blocks ? part * per_part : n_blocks;
+  const int b1 = b0 + per_part < n_blocks ? b0 + per_part : n_blocks;
+  const int n_loc = b1 - b0;
+  const bool has_x = n_loc > 0 && b0 < nbx, has_h = n_loc > 0 && b1 > nbx;
 
   if (warp < GRU_PRODUCER_WARPS) {
     // ---------------- producers: two threads per row ----------------
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
     const int64_t u = g.node_ids != nullptr ? g.node_ids[r] : r;
     const float* xp = g.x_table + u * g.x_stride;
     const float* hp = g.h_table + u * g.h_stride;
-    if (live && warp < 4 && g.check_mem_ts != nullptr && blockIdx.x == 0 && g.err_flags != nullptr) {
+    if (live && warp < 4 && g.check_mem_ts != nullptr && blockIdx.x == 0 && part == 0 && g.err_flags != nullptr) {
       const float mt = g.msg_ts[u], pt = g.check_mem_ts[u];
       if (pt > mt) atomicOr(g.err_flags, TIGER_ERR_MSG_BEFORE_MEM);                    // message_modules.py:157-159
       if (g.check_equal && mt != pt) atomicOr(g.err_flags, TIGER_ERR_MSG_TS_MISMATCH);  // tiger.py:324-327
@@ -147,10 +162,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
         for (int i = 0; i < 4; ++i) v[i] = umma_load_chunk(p, k0 + 4 * i, kdim, false);
       }
     };
-    if (grp < n_blocks) load(grp);
-    for (int blk = grp; blk < n_blocks; blk += GRU_GROUPS) {
-      const int s = blk % GRU_A_STAGES;
-      mbar_wait(a_empty + s, ((blk / GRU_A_STAGES) & 1) ^ 1);
+    if (grp < n_loc) load(b0 + grp);
+    for (int lb = grp; lb < n_loc; lb += GRU_GROUPS) {
+      const int s = lb % GRU_A_STAGES;
+      mbar_wait(a_empty + s, ((lb / GRU_A_STAGES) & 1) ^ 1);
       float hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -167,55 +182,31 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + s);
       // this group's next line is in flight while the other group's stage is written / consumed
-      if (blk + GRU_GROUPS < n_blocks) load(blk + GRU_GROUPS);
+      if (lb + GRU_GROUPS < n_loc) load(b0 + lb + GRU_GROUPS);
     }
-    // ---------------- gate epilogue ----------------
+    // ---------------- partial tile: TMEM -> shared memory ----------------
     mbar_wait(done, 0);
     tc_fence_after_sync();
     const uint32_t tacc = taddr + ((uint32_t)(q * 32) << 16);   // q == warp & 3: same rows as in the producer role
-    for (int c0 = (warp >> 2) * 16; c0 < GRU_U; c0 += 16 * (GRU_PRODUCER_WARPS / 4)) {
-      float an[16], ar[16], az[16], ah[16];
-      tmem_ld16(tacc + (uint32_t)c0, an);
-      tmem_ld16(tacc + (uint32_t)(GRU_U + c0), ar);
-      tmem_ld16(tacc + (uint32_t)(2 * GRU_U + c0), az);
-      tmem_ld16(tacc + (uint32_t)(3 * GRU_U + c0), ah);
+    float* red = wstage0 + rl * GRU_RED_LD;                       // the weight ring is idle once `done` has fired
+    for (int c0 = (warp >> 2) * 16; c0 < GRU_ACC_COLS; c0 += 16 * (GRU_PRODUCER_WARPS / 4)) {
+      float a[16], t[16];
+      tmem_ld16(tacc + (uint32_t)c0, a);
+      tmem_ld16(tacc + (uint32_t)(GRU_ACC_COLS + c0), t);
+      // column groups this CTA's stages never touched hold no sum (U is a multiple of 16: a chunk lies in one group)
+      const bool valid = c0 < GRU_U ? has_x : (c0 < 3 * GRU_U ? (has_x || has_h) : has_h);
 #pragma unroll
-      for (int jb = 1; jb < GRU_SETS; ++jb) {
-        float t[16];
-        const uint32_t tb = tacc + (uint32_t)(jb * GRU_ACC_COLS + c0);
-        tmem_ld16(tb, t);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) an[e] += t[e];
-        tmem_ld16(tb + GRU_U, t);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) ar[e] += t[e];
-        tmem_ld16(tb + 2 * GRU_U, t);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) az[e] += t[e];
-        tmem_ld16(tb + 3 * GRU_U, t);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) ah[e] += t[e];
-      }
-      if (!live) continue;
-      float* dst = g.h_new + (row0 + rl) * d;
-#pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        const int j = j0 + c0 + jj;
-        if (j < d) {
-          const float rg = sigmoidf_acc(ar[jj] + bias_s[c0 + jj]);
-          const float zg = sigmoidf_acc(az[jj] + bias_s[GRU_U + c0 + jj]);
-          const float nn = tanhf((an[jj] + bias_s[2 * GRU_U + c0 + jj]) + rg * (ah[jj] + bias_s[3 * GRU_U + c0 + jj]));
-          const float h = hp[j];
-          dst[j] = (h - nn) * zg + nn;
-        }
-      }
+      for (int e = 0; e < 16; e += 4)
+        *reinterpret_cast<float4*>(red + c0 + e) =
+            valid ? make_float4(a[e] + t[e], a[e + 1] + t[e + 1], a[e + 2] + t[e + 2], a[e + 3] + t[e + 3])
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (warp == GRU_PRODUCER_WARPS + GRU_ISSUERS) {
     // ---------------- TMA warp: one bulk copy per stage brings both planes of the weight tile ----------------
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)GRU_W_STAGE_FLOATS * 4u;
-      const float* src = g.wpack + (int64_t)blockIdx.x * n_blocks * GRU_W_STAGE_FLOATS;
-      for (int blk = 0; blk < n_blocks; ++blk) {
+      const float* src = g.wpack + ((int64_t)blockIdx.x * n_blocks + b0) * GRU_W_STAGE_FLOATS;
+      for (int blk = 0; blk < n_loc; ++blk) {
         const int s = blk % GRU_W_STAGES;
         mbar_wait(w_empty + s, ((blk / GRU_W_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(w_full + s, bytes);
@@ -236,44 +227,47 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
     const uint32_t b_plane = (uint32_t)(TS_KCH * GRU_WROWS * 16) >> 4;      // head plane -> tail plane, 16-byte units
     const uint32_t b_stage = (uint32_t)(GRU_W_STAGE_FLOATS * 4) >> 4, b_kstep = 2u * GRU_WROWS;
     bool ready_a = mbar_test(a_full, 0), ready_w = mbar_test(w_full, 0);
-    for (int blk = 0; blk < n_blocks; ++blk) {
-      const int sa = blk % GRU_A_STAGES, sw = blk % GRU_W_STAGES;
-      mbar_wait_probed(ready_a, a_full + sa, (blk / GRU_A_STAGES) & 1);
-      mbar_wait_probed(ready_w, w_full + sw, (blk / GRU_W_STAGES) & 1);
+    const int first_h = b0 > nbx ? b0 : nbx;      // first h-phase block of this part (if it has one)
+    for (int lb = 0; lb < n_loc; ++lb) {
+      const int blk = b0 + lb;
+      const int sa = lb % GRU_A_STAGES, sw = lb % GRU_W_STAGES;
+      mbar_wait_probed(ready_a, a_full + sa, (lb / GRU_A_STAGES) & 1);
+      mbar_wait_probed(ready_w, w_full + sw, (lb / GRU_W_STAGES) & 1);
       tc_fence_after_sync();
       // probe the next stage now: the probes' latency overlaps the MMA issue below
-      const int nb = blk + 1;
-      ready_a = nb < n_blocks ? mbar_test(a_full + nb % GRU_A_STAGES, (nb / GRU_A_STAGES) & 1) : true;
-      ready_w = nb < n_blocks ? mbar_test(w_full + nb % GRU_W_STAGES, (nb / GRU_W_STAGES) & 1) : true;
+      const int nb = lb + 1;
+      ready_a = nb < n_loc ? mbar_test(a_full + nb % GRU_A_STAGES, (nb / GRU_A_STAGES) & 1) : true;
+      ready_w = nb < n_loc ? mbar_test(w_full + nb % GRU_W_STAGES, (nb / GRU_W_STAGES) & 1) : true;
       if (elect_one()) {
         const uint32_t a_hi = a_ring + (uint32_t)(sa * 2 * TS_BK), a_lo = a_hi + TS_BK;
         const uint32_t b_hi = b_hi0 + (uint32_t)sw * b_stage, b_lo = b_hi + b_plane;
         const bool xph = blk < nbx;
-        const bool first = xph ? blk == 0 : blk == nbx;
+        // the first MMA into a column group overwrites it: [Win x] and (with x stages) [r | z] at the first x
+        // block, [Whn h] (and [r | z] of a part without x stages) at the first h block
+        const bool first = xph ? blk == b0 : blk == first_h;
+        const uint32_t acc = tbase + (is_x ? 0u : (uint32_t)GRU_ACC_COLS);   // set 0: cross terms, set 1: head*head
 #pragma unroll
         for (int j = 0; j < TS_BK / 8; ++j) {
           const uint32_t ah = a_hi + 8u * j, al = a_lo + 8u * j, bh = b_hi + b_kstep * j, bl = b_lo + b_kstep * j;
+          const uint32_t fresh = (first && j == 0) ? 0u : 1u;
+          const uint32_t fresh_rz = (first && j == 0 && !has_x) ? 0u : 1u;
           if (is_x) {
-            const uint32_t acc = tbase;                                  // set 0
-            const uint32_t fresh = (first && j == 0) ? 0u : 1u;
             if (xph) {
               // weight tile rows [n | r | z] -> columns [0, 3U)
               umma_tf32_ts(acc, al, bh, id3, fresh);
               umma_tf32_ts(acc, ah, bl, id3, 1u);
             } else {
               // weight tile rows [r | z | n] -> [r | z] accumulate at column U, Whn h starts at column 3U
-              umma_tf32_ts(acc + GRU_U, al, bh, id2, 1u);
+              umma_tf32_ts(acc + GRU_U, al, bh, id2, fresh_rz);
               umma_tf32_ts(acc + GRU_U, ah, bl, id2, 1u);
               umma_tf32_ts(acc + 3 * GRU_U, al, bh + 2 * GRU_U, id1, fresh);
               umma_tf32_ts(acc + 3 * GRU_U, ah, bl + 2 * GRU_U, id1, 1u);
             }
           } else {
-            const uint32_t acc = tbase + (uint32_t)((1 + (j & 1)) * GRU_ACC_COLS);   // sets 1 / 2
-            const uint32_t fresh = (first && j < 2) ? 0u : 1u;
             if (xph) {
               umma_tf32_ts(acc, ah, bh, id3, fresh);
             } else {
-              umma_tf32_ts(acc + GRU_U, ah, bh, id2, 1u);
+              umma_tf32_ts(acc + GRU_U, ah, bh, id2, fresh_rz);
               umma_tf32_ts(acc + 3 * GRU_U, ah, bh + 2 * GRU_U, id1, fresh);
             }
           }
@@ -283,16 +277,72 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
       }
       __syncwarp();
     }
-    if (elect_one()) umma_commit(done);
+    if (elect_one()) {
+      if (n_loc > 0)
+        umma_commit(done);
+      else
+        mbar_arrive(done);
+    }
     __syncwarp();
   }
+  // ---------------- cluster reduction + gates ----------------
+  __syncwarp();
+  cluster_sync_all();                         // both partial tiles are in place
+  {
+    constexpr int RB = GRU_BM / GRU_KPARTS, Q = GRU_U / 4;
+    const int r_first = (int)cluster_cta_rank() * RB;
+    const uint32_t red0 = smem_addr_u32(wstage0);
+    const bool vec_out = (d & 3) == 0 && ((((uintptr_t)g.h_new) & 15) == 0);
+    for (int i = tid; i < RB * Q; i += GRU_THREADS) {
+      const int rl = r_first + i / Q, c = (i % Q) * 4;
+      const int64_t r = row0 + rl;
+      const int j = j0 + c;
+      if (r >= n || j >= d) continue;
+      float4 acc[4];                            // Win x, r, z, Whn h
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        const uint32_t off = red0 + (uint32_t)(rl * GRU_RED_LD + gi * GRU_U + c) * 4u;
+        acc[gi] = cluster_ld_f4(cluster_map_shared(off, 0));
+#pragma unroll
+        for (int pp = 1; pp < GRU_KPARTS; ++pp) {
+          const float4 t = cluster_ld_f4(cluster_map_shared(off, (uint32_t)pp));
+          acc[gi].x += t.x; acc[gi].y += t.y; acc[gi].z += t.z; acc[gi].w += t.w;
+        }
+      }
+      const int64_t u = g.node_ids != nullptr ? g.node_ids[r] : r;
+      const float* hp = g.h_table + u * g.h_stride;
+      const float an[4] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w}, ar[4] = {acc[1].x, acc[1].y, acc[1].z, acc[1].w};
+      const float az[4] = {acc[2].x, acc[2].y, acc[2].z, acc[2].w}, ah[4] = {acc[3].x, acc[3].y, acc[3].z, acc[3].w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[e] = 0.f;
+        if (j + e < d) {
+          const float rg = sigmoidf_acc(ar[e] + bias_s[c + e]);
+          const float zg = sigmoidf_acc(az[e] + bias_s[GRU_U + c + e]);
+          const float nn = tanhf((an[e] + bias_s[2 * GRU_U + c + e]) + rg * (ah[e] + bias_s[3 * GRU_U + c + e]));
+          const float h = hp[j + e];
+          o[e] = (h - nn) * zg + nn;
+        }
+      }
+      float* dst = g.h_new + r * d + j;
+      if (vec_out && j + 4 <= d) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e < d) dst[e] = o[e];
+      }
+    }
+  }
+  cluster_sync_all();                         // nobody leaves while its partner still reads its tile
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(taddr, GRU_TMEM_COLS);
 }
 
 // Gate-weight pack: for unit tile t and k-block kb (x phase: kb < nbx over weight_ih, rows [n | r | z]; h phase over
-// weight_hh, rows [r | z | n]) the stage image [head plane | tail plane][kc][96 rows][4 floats].
+// weight_hh, rows [r | z | n]) the stage image [head plane | tail plane][kc][3U rows][4 floats].
 __global__ void gru_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, int m_dim, int d,
                                 int tiles, int nbx, int nbh, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,7 +407,18 @@ extern "C" int tiger_gru_update(const int64_t* node_ids, const int32_t* count, i
   g.msg_ts = msg_ts; g.check_mem_ts = check_mem_ts; g.check_equal = check_equal; g.err_flags = err_flags;
   g.vec_x = ((((uintptr_t)x_table) & 15) == 0 && (x_stride & 3) == 0) ? 1 : 0;
   g.vec_h = ((((uintptr_t)h_table) & 15) == 0 && (h_stride & 3) == 0) ? 1 : 0;
-  dim3 grid((unsigned)((d + GRU_U - 1) / GRU_U), (unsigned)((n_rows + GRU_BM - 1) / GRU_BM));
-  gru_update_kernel<<<grid, GRU_THREADS, GRU_SMEM_BYTES, as_stream(stream)>>>(g);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((d + GRU_U - 1) / GRU_U), (unsigned)((n_rows + GRU_BM - 1) / GRU_BM), GRU_KPARTS);
+  cfg.blockDim = dim3(GRU_THREADS);
+  cfg.dynamicSmemBytes = GRU_SMEM_BYTES;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = GRU_KPARTS;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, gru_update_kernel, g) != cudaSuccess) return TIGER_ECUDA;
   return tiger_launch_status();
 }
