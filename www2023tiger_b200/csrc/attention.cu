@@ -405,6 +405,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   __shared__ float s_dt[ATT_MAXK];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block(), n_warps = ATT_THREADS / 32;
   const int64_t q = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();      // qkf comes from the Wqk product
   const float* qkf = a.w.qkf + q * a.dm.ld_qkf;
   for (int i = tid; i < H * Cq; i += ATT_THREADS) qk[i] = qkf[i];
   if (tid < K) {
@@ -597,8 +599,8 @@ static int launch_score_pool(const AttArgs& a, size_t smem, cudaStream_t st) {
       return TIGER_ECUDA;
     configured = smem;
   }
-  attn_score_pool_kernel<HT><<<(unsigned)a.n_query, ATT_THREADS, smem, st>>>(a);
-  return tiger_launch_status();
+  return tiger_launch_chain(attn_score_pool_kernel<HT>, dim3((unsigned)a.n_query), dim3(ATT_THREADS), smem, st,
+                            dim3(1, 1, 1), a);
 }
 
 static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cudaStream_t st) {

@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "tiger_b200.h"
 
@@ -12,6 +15,52 @@ static inline int tiger_launch_status() {
 }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch.  The kernels of the per-batch chain run back to back on one stream, each a
+// few microseconds long: with the launch attribute below a kernel's CTAs may be scheduled while its
+// predecessor still runs (as soon as every CTA of the predecessor has called pdl_trigger or exited), set up
+// what does not depend on it (barriers, tensor-memory allocation, weight tiles) and block in pdl_wait until
+// the predecessor has completed and its writes are visible.  pdl_wait is a no-op for a normal launch.
+// TIGER_NO_PDL=1 in the environment turns the attribute off (plain stream order).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool tiger_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TIGER_NO_PDL");
+    on = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+template <typename... KP, typename... Args>
+static inline int tiger_launch_chain(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     dim3 cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n_attr = 0;
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = cluster.x;
+    attr[n_attr].val.clusterDim.y = cluster.y;
+    attr[n_attr].val.clusterDim.z = cluster.z;
+    ++n_attr;
+  }
+  if (tiger_pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  if (cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...) != cudaSuccess) return TIGER_ECUDA;
+  return tiger_launch_status();
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id_in_block() { return threadIdx.x >> 5; }

@@ -365,6 +365,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
   uint64_t* done = empty + TS_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
+  pdl_trigger();
+  // With a host-side row count the set-up and the weight stream (parameters: nothing the previous kernel
+  // writes) run ahead of the previous kernel's completion; only the producers wait, before their first
+  // activation load.  A device-side count is itself produced upstream: everybody waits first.
+  const bool early = g.count == nullptr;
+  if (!early) pdl_wait();
   int64_t M = g.M;
   if (g.count != nullptr) {
     const int64_t c = (int64_t)(*g.count) * g.rows_per_count;
@@ -411,6 +417,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
     const int row = q * 32 + lane;
     int64_t m = m0 + row;
     m = m < M ? m : M - 1;                 // rows beyond the edge only feed accumulator rows nobody stores
+    if (early) pdl_wait();
     const float* rowp = A + m * g.lda;
     const float* addp = nullptr;
     if (g.a_ids != nullptr) {
@@ -588,6 +595,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
 #endif
   if (g.cluster_reduce) {
     __syncwarp();
+    if (early && warp >= TCG_PRODUCER_WARPS) pdl_wait();   // these warps store results below
     cluster_sync_all();                       // every part's tile sits in its CTA's shared memory
     const int kp = g.k_parts, rank = (int)cluster_cta_rank();
     const int rb = (TCG_BM + kp - 1) / kp;    // rows this CTA finishes
@@ -771,25 +779,10 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
     g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn + stages * 2 * TS_BK));
     const size_t smem = (size_t)stages * UMMA_PACK_STAGE_FLOATS(g.bn) * 4 + 256;
     dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)g.k_parts);
-    if (g.cluster_reduce) {
-      if ((size_t)TCG_BM * (g.bn + 4) * 4 > (size_t)stages * UMMA_PACK_STAGE_FLOATS(g.bn) * 4) return TIGER_EINVAL;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = grid;
-      cfg.blockDim = dim3(TS_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = as_stream(stream);
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 1;
-      attr[0].val.clusterDim.y = (unsigned)g.k_parts;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      if (cudaLaunchKernelEx(&cfg, gemm_tf32x3_ts_kernel, g) != cudaSuccess) return TIGER_ECUDA;
-      return tiger_launch_status();
-    }
-    gemm_tf32x3_ts_kernel<<<grid, TS_THREADS, smem, as_stream(stream)>>>(g);
-    return tiger_launch_status();
+    if (g.cluster_reduce && (size_t)TCG_BM * (g.bn + 4) * 4 > (size_t)stages * UMMA_PACK_STAGE_FLOATS(g.bn) * 4)
+      return TIGER_EINVAL;
+    return tiger_launch_chain(gemm_tf32x3_ts_kernel, grid, dim3(TS_THREADS), smem, as_stream(stream),
+                              dim3(1, g.cluster_reduce ? (unsigned)g.k_parts : 1u, 1), g);
   }
   g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn));
   const size_t stage_bytes = (size_t)(2 * UMMA_KCH * TCG_BM * 4 + 2 * UMMA_KCH * g.bn * 4) * sizeof(float);

@@ -219,6 +219,8 @@ compact_involved_fast_kernel(uint32_t* __restrict__ bitmap, int n_words, int64_t
   __shared__ int sm[3][32];
   __shared__ int total[3];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
+  pdl_trigger();
+  pdl_wait();      // the finder marks the bitmap
   // ---- phase 0: the bitmap itself (one load per thread), so the flag loads below depend on shared memory only ----
   for (int w = tid; w < n_words; w += 1024) m_mem[w] = bitmap[w];
   __syncthreads();
@@ -320,10 +322,9 @@ extern "C" int tiger_compact_involved(uint32_t* bitmap, int64_t n_nodes, uint8_t
         return TIGER_ECUDA;
       configured = true;
     }
-    compact_involved_fast_kernel<<<1, 1024, (size_t)n_words * 6 * sizeof(uint32_t), as_stream(stream)>>>(
-        bitmap, (int)n_words, n_nodes, has_msg, uptodate, involved, cap_involved, local_index, outdated, gru_row,
-        restart_nodes, counts, err_flags);
-    return tiger_launch_status();
+    return tiger_launch_chain(compact_involved_fast_kernel, dim3(1), dim3(1024), (size_t)n_words * 6 * sizeof(uint32_t),
+                              as_stream(stream), dim3(1, 1, 1), bitmap, (int)n_words, n_nodes, has_msg, uptodate, involved,
+                              cap_involved, local_index, outdated, gru_row, restart_nodes, counts, err_flags);
   }
   compact_involved_kernel<<<1, 1024, 0, as_stream(stream)>>>(bitmap, n_words, has_msg, uptodate, involved,
                                                             cap_involved, local_index, outdated, gru_row,

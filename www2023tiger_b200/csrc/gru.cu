@@ -33,6 +33,17 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+#ifdef TIGER_TRACE
+#include <cstdio>
+#define GTRACE_DECL long long tr_t[48]; int tr_n = 0; const bool tr_on = blockIdx.x == 0 && (blockIdx.y == 0 || blockIdx.y == 7) && lane == 0;
+#define GTRACE_MARK() do { if (tr_on && tr_n < 48) tr_t[tr_n++] = clock64(); } while (0)
+#define GTRACE_DUMP(tag, id) do { if (tr_on) for (int i_ = 0; i_ < tr_n; ++i_) printf("%s y%d z%d w%d #%d %lld\n", tag, blockIdx.y, blockIdx.z, id, i_, tr_t[i_] - tr_base); } while (0)
+#else
+#define GTRACE_DECL
+#define GTRACE_MARK() do { } while (0)
+#define GTRACE_DUMP(tag, id) do { } while (0)
+#endif
+
 #define GRU_PRODUCER_WARPS 16
 #define GRU_GROUPS 2                   // producer groups: group g fills activation stage g (GROUPS <= A_STAGES, see below)
 #define GRU_GROUP_WARPS (GRU_PRODUCER_WARPS / GRU_GROUPS)
@@ -85,6 +96,11 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
   uint64_t* done = w_empty + GRU_W_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
+#ifdef TIGER_TRACE
+  const long long tr_base = clock64();
+#endif
+  pdl_trigger();
+  pdl_wait();      // the row count and the row list come from the compaction kernel
   int64_t n = g.n_rows;
   if (g.count != nullptr) {
     const int64_t c = *g.count;
@@ -96,6 +112,13 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
   const int d = g.d, m_dim = g.m_dim;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  // producers: the id of this thread's row is in flight while the barriers / TMEM allocation are set up
+  int64_t prod_u = 0;
+  if (warp < GRU_PRODUCER_WARPS) {
+    int64_t r = row0 + (warp & 3) * 32 + lane;
+    r = r < n ? r : n - 1;
+    prod_u = g.node_ids != nullptr ? g.node_ids[r] : r;
+  }
   if (tid < GRU_U) {
     const int j = j0 + tid;
     const bool ok = j < d;
@@ -121,6 +144,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t taddr = *tmem_slot;
+  GTRACE_DECL
+  GTRACE_MARK();   // #0 setup done
   const int nbx = (m_dim + TS_BK - 1) / TS_BK, nbh = (d + TS_BK - 1) / TS_BK;
   const int n_blocks = nbx + nbh;
   // this CTA's share of the K stages: [b0, b1)
@@ -130,6 +155,27 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
   const int b1 = b0 + per_part < n_blocks ? b0 + per_part : n_blocks;
   const int n_loc = b1 - b0;
   const bool has_x = n_loc > 0 && b0 < nbx, has_h = n_loc > 0 && b1 > nbx;
+  // gate stage (after the cluster barrier): this CTA finishes rows [RB * rank, RB * (rank + 1)) of the tile, one item =
+  // one row x 4 units; a thread owns items tid and tid + GRU_THREADS.  The previous state h of an item is fetched
+  // before the barrier (gate_prefetch) so that only shared-memory traffic and math remain behind it.
+  constexpr int GATE_RB = GRU_BM / GRU_KPARTS, GATE_Q = GRU_U / 4, GATE_ITEMS = 2;
+  static_assert(GATE_RB * GATE_Q <= GATE_ITEMS * GRU_THREADS, "gate items per thread");
+  const int gate_r0 = (int)cluster_cta_rank() * GATE_RB;
+  float4 gate_h[GATE_ITEMS];
+  auto gate_prefetch = [&]() {
+#pragma unroll
+    for (int it = 0; it < GATE_ITEMS; ++it) {
+      const int i = tid + it * GRU_THREADS;
+      const int rl = gate_r0 + i / GATE_Q, c = (i % GATE_Q) * 4;
+      const int64_t r = row0 + rl;
+      const int j = j0 + c;
+      gate_h[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < GATE_RB * GATE_Q && r < n && j < d) {
+        const int64_t u = g.node_ids != nullptr ? g.node_ids[r] : r;
+        gate_h[it] = umma_load_chunk(g.h_table + u * g.h_stride, j, d, g.vec_h != 0);
+      }
+    }
+  };
 
   if (warp < GRU_PRODUCER_WARPS) {
     // ---------------- producers: two threads per row ----------------
@@ -140,7 +186,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
     int64_t r = row0 + rl;
     const bool live = r < n;
     r = live ? r : n - 1;
-    const int64_t u = g.node_ids != nullptr ? g.node_ids[r] : r;
+    const int64_t u = prod_u;
     const float* xp = g.x_table + u * g.x_stride;
     const float* hp = g.h_table + u * g.h_stride;
     if (live && warp < 4 && g.check_mem_ts != nullptr && blockIdx.x == 0 && part == 0 && g.err_flags != nullptr) {
@@ -162,6 +208,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
         for (int i = 0; i < 4; ++i) v[i] = umma_load_chunk(p, k0 + 4 * i, kdim, false);
       }
     };
+    GTRACE_MARK();   // #1 pointers resolved
     if (grp < n_loc) load(b0 + grp);
     for (int lb = grp; lb < n_loc; lb += GRU_GROUPS) {
       const int s = lb % GRU_A_STAGES;
@@ -181,11 +228,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + s);
+      GTRACE_MARK();   // stage published
       // this group's next line is in flight while the other group's stage is written / consumed
       if (lb + GRU_GROUPS < n_loc) load(b0 + lb + GRU_GROUPS);
     }
     // ---------------- partial tile: TMEM -> shared memory ----------------
+    GTRACE_MARK();   // producer loop done
+    gate_prefetch();
     mbar_wait(done, 0);
+    GTRACE_MARK();   // MMAs done
     tc_fence_after_sync();
     const uint32_t tacc = taddr + ((uint32_t)(q * 32) << 16);   // q == warp & 3: same rows as in the producer role
     float* red = wstage0 + rl * GRU_RED_LD;                       // the weight ring is idle once `done` has fired
@@ -214,6 +265,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
                       w_full + s);
       }
     }
+    __syncwarp();
+    gate_prefetch();
   } else {
     // ---------------- MMA issuers: X (cross terms) and Y (head*head) ----------------
     // The whole warp runs the loop so that every operand stays warp-uniform; only the tcgen05 instructions
@@ -233,6 +286,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
       const int sa = lb % GRU_A_STAGES, sw = lb % GRU_W_STAGES;
       mbar_wait_probed(ready_a, a_full + sa, (lb / GRU_A_STAGES) & 1);
       mbar_wait_probed(ready_w, w_full + sw, (lb / GRU_W_STAGES) & 1);
+      GTRACE_MARK();   // stage ready
       tc_fence_after_sync();
       // probe the next stage now: the probes' latency overlaps the MMA issue below
       const int nb = lb + 1;
@@ -284,46 +338,55 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
         mbar_arrive(done);
     }
     __syncwarp();
+    gate_prefetch();
   }
   // ---------------- cluster reduction + gates ----------------
   __syncwarp();
+  GTRACE_MARK();   // role done
   cluster_sync_all();                         // both partial tiles are in place
+  GTRACE_MARK();   // cluster sync 1
   {
-    constexpr int RB = GRU_BM / GRU_KPARTS, Q = GRU_U / 4;
-    const int r_first = (int)cluster_cta_rank() * RB;
     const uint32_t red0 = smem_addr_u32(wstage0);
     const bool vec_out = (d & 3) == 0 && ((((uintptr_t)g.h_new) & 15) == 0);
-    for (int i = tid; i < RB * Q; i += GRU_THREADS) {
-      const int rl = r_first + i / Q, c = (i % Q) * 4;
-      const int64_t r = row0 + rl;
-      const int j = j0 + c;
-      if (r >= n || j >= d) continue;
-      float4 acc[4];                            // Win x, r, z, Whn h
+    float4 acc[GATE_ITEMS][4];                  // Win x, r, z, Whn h
+#pragma unroll
+    for (int it = 0; it < GATE_ITEMS; ++it) {   // all partial-tile reads of both items are issued before any math
+      const int i = tid + it * GRU_THREADS;
+      const int rl = gate_r0 + i / GATE_Q, c = (i % GATE_Q) * 4;
+      const bool on = i < GATE_RB * GATE_Q && row0 + rl < n && j0 + c < d;
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) {
-        const uint32_t off = red0 + (uint32_t)(rl * GRU_RED_LD + gi * GRU_U + c) * 4u;
-        acc[gi] = cluster_ld_f4(cluster_map_shared(off, 0));
+        acc[it][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+          const uint32_t off = red0 + (uint32_t)(rl * GRU_RED_LD + gi * GRU_U + c) * 4u;
+          acc[it][gi] = cluster_ld_f4(cluster_map_shared(off, 0));
 #pragma unroll
-        for (int pp = 1; pp < GRU_KPARTS; ++pp) {
-          const float4 t = cluster_ld_f4(cluster_map_shared(off, (uint32_t)pp));
-          acc[gi].x += t.x; acc[gi].y += t.y; acc[gi].z += t.z; acc[gi].w += t.w;
+          for (int pp = 1; pp < GRU_KPARTS; ++pp) {
+            const float4 t = cluster_ld_f4(cluster_map_shared(off, (uint32_t)pp));
+            acc[it][gi].x += t.x; acc[it][gi].y += t.y; acc[it][gi].z += t.z; acc[it][gi].w += t.w;
+          }
         }
       }
-      const int64_t u = g.node_ids != nullptr ? g.node_ids[r] : r;
-      const float* hp = g.h_table + u * g.h_stride;
-      const float an[4] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w}, ar[4] = {acc[1].x, acc[1].y, acc[1].z, acc[1].w};
-      const float az[4] = {acc[2].x, acc[2].y, acc[2].z, acc[2].w}, ah[4] = {acc[3].x, acc[3].y, acc[3].z, acc[3].w};
+    }
+#pragma unroll
+    for (int it = 0; it < GATE_ITEMS; ++it) {
+      const int i = tid + it * GRU_THREADS;
+      const int rl = gate_r0 + i / GATE_Q, c = (i % GATE_Q) * 4;
+      const int64_t r = row0 + rl;
+      const int j = j0 + c;
+      if (i >= GATE_RB * GATE_Q || r >= n || j >= d) continue;
+      const float an[4] = {acc[it][0].x, acc[it][0].y, acc[it][0].z, acc[it][0].w};
+      const float ar[4] = {acc[it][1].x, acc[it][1].y, acc[it][1].z, acc[it][1].w};
+      const float az[4] = {acc[it][2].x, acc[it][2].y, acc[it][2].z, acc[it][2].w};
+      const float ah[4] = {acc[it][3].x, acc[it][3].y, acc[it][3].z, acc[it][3].w};
+      const float hv[4] = {gate_h[it].x, gate_h[it].y, gate_h[it].z, gate_h[it].w};
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        o[e] = 0.f;
-        if (j + e < d) {
-          const float rg = sigmoidf_acc(ar[e] + bias_s[c + e]);
-          const float zg = sigmoidf_acc(az[e] + bias_s[GRU_U + c + e]);
-          const float nn = tanhf((an[e] + bias_s[2 * GRU_U + c + e]) + rg * (ah[e] + bias_s[3 * GRU_U + c + e]));
-          const float h = hp[j + e];
-          o[e] = (h - nn) * zg + nn;
-        }
+        const float rg = sigmoidf_acc(ar[e] + bias_s[c + e]);
+        const float zg = sigmoidf_acc(az[e] + bias_s[GRU_U + c + e]);
+        const float nn = tanhf((an[e] + bias_s[2 * GRU_U + c + e]) + rg * (ah[e] + bias_s[3 * GRU_U + c + e]));
+        o[e] = (hv[e] - nn) * zg + nn;
       }
       float* dst = g.h_new + r * d + j;
       if (vec_out && j + 4 <= d) {
@@ -335,7 +398,12 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_update_kernel(const GruArg
       }
     }
   }
+  GTRACE_MARK();   // gates done
   cluster_sync_all();                         // nobody leaves while its partner still reads its tile
+  GTRACE_MARK();   // cluster sync 2
+#ifdef TIGER_TRACE
+  if (warp == 0 || warp == 8 || warp >= GRU_PRODUCER_WARPS) GTRACE_DUMP(warp < GRU_PRODUCER_WARPS ? "producer" : (warp == GRU_PRODUCER_WARPS + GRU_ISSUERS ? "tma" : "issuer"), warp);
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(taddr, GRU_TMEM_COLS);
@@ -407,18 +475,7 @@ extern "C" int tiger_gru_update(const int64_t* node_ids, const int32_t* count, i
   g.msg_ts = msg_ts; g.check_mem_ts = check_mem_ts; g.check_equal = check_equal; g.err_flags = err_flags;
   g.vec_x = ((((uintptr_t)x_table) & 15) == 0 && (x_stride & 3) == 0) ? 1 : 0;
   g.vec_h = ((((uintptr_t)h_table) & 15) == 0 && (h_stride & 3) == 0) ? 1 : 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((d + GRU_U - 1) / GRU_U), (unsigned)((n_rows + GRU_BM - 1) / GRU_BM), GRU_KPARTS);
-  cfg.blockDim = dim3(GRU_THREADS);
-  cfg.dynamicSmemBytes = GRU_SMEM_BYTES;
-  cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = GRU_KPARTS;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, gru_update_kernel, g) != cudaSuccess) return TIGER_ECUDA;
-  return tiger_launch_status();
+  return tiger_launch_chain(gru_update_kernel,
+                            dim3((unsigned)((d + GRU_U - 1) / GRU_U), (unsigned)((n_rows + GRU_BM - 1) / GRU_BM), GRU_KPARTS),
+                            dim3(GRU_THREADS), GRU_SMEM_BYTES, as_stream(stream), dim3(1, 1, GRU_KPARTS), g);
 }

@@ -189,6 +189,8 @@ link_score_folded_kernel(const float* __restrict__ pq, int64_t batch, int d, con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_pairs = 2 * batch;
   const int64_t p = (int64_t)blockIdx.x * SCOREF_WARPS + warp;
+  pdl_trigger();
+  pdl_wait();      // PQ comes from the last attention product
   if (p < n_pairs) {
     const bool is_neg = p >= batch;
     const int64_t e = is_neg ? p - batch : p;
@@ -244,8 +246,7 @@ extern "C" int tiger_link_score_folded(const float* pq, int64_t batch, int d, co
   if (loss != nullptr && done_counter == nullptr) return TIGER_EINVAL;
   if (batch == 0) return TIGER_OK;
   const unsigned grid = (unsigned)((2 * batch + SCOREF_WARPS - 1) / SCOREF_WARPS);
-  link_score_folded_kernel<<<grid, SCOREF_WARPS * 32, 0, as_stream(stream)>>>(pq, batch, d, src, dst, neg, neigh_nids, k,
-                                                                             cab, fc2_w, fc2_b, scores, loss,
-                                                                             done_counter);
-  return tiger_launch_status();
+  return tiger_launch_chain(link_score_folded_kernel, dim3(grid), dim3(SCOREF_WARPS * 32), 0, as_stream(stream),
+                            dim3(1, 1, 1), pq, batch, d, src, dst, neg, neigh_nids, k, cab, fc2_w, fc2_b, scores, loss,
+                            done_counter);
 }
