@@ -163,6 +163,24 @@ __device__ __forceinline__ void warp_copy_rows(float* const (&dst)[NR], const fl
   }
 }
 
+// Lane l of the warp holds the (dst, src) pair of row l (l < rows; dst NULL = skip): the rows are copied four at
+// a time.  A kernel resolves the index chain of up to 32 rows once, in parallel across the lanes, and then
+// streams rows back to back - with 4 rows per warp the chain's latency was most of a warp's life and the
+// kernels idled at half the bandwidth their loads in flight could have carried.
+__device__ __forceinline__ void warp_copy_lane_rows(float* my_dst, const float* my_src, int rows, int width, int lane) {
+  for (int g = 0; g < rows; g += ROWS_PER_WARP) {
+    float* dst[ROWS_PER_WARP];
+    const float* src[ROWS_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_WARP; ++i) {
+      dst[i] = reinterpret_cast<float*>(__shfl_sync(TIGER_FULL_MASK, reinterpret_cast<unsigned long long>(my_dst), g + i));
+      src[i] = reinterpret_cast<const float*>(
+          __shfl_sync(TIGER_FULL_MASK, reinterpret_cast<unsigned long long>(my_src), g + i));
+    }
+    warp_copy_rows<ROWS_PER_WARP>(dst, src, width, lane);
+  }
+}
+
 // dst = a + b (b may be NULL => copy), same vector/scalar policy.
 __device__ __forceinline__ void warp_add_row(float* __restrict__ dst, const float* __restrict__ a,
                                              const float* __restrict__ b, int width, int lane) {

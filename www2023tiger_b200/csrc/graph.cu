@@ -3,6 +3,10 @@
 // (tiger/data/graph.py:44-53,117-127,150-155; tiger/data/data_loader.py:61-67,105-131;
 // tiger/data/data_classes.py:163-165; tiger/model/memory.py:108-126).
 #include "common.cuh"
+#include "umma.cuh"
+#ifdef TIGER_TRACE
+#include <cstdio>
+#endif
 
 // ------------------------------------------------------------------------------------------
 // K1  FIND_G lanes per query (4 queries per warp): FIND_G-ary cooperative lower-bound search on the
@@ -197,45 +201,52 @@ compact_involved_kernel(uint32_t* __restrict__ bitmap, int64_t n_words, uint8_t*
   }
 }
 
-// Same operator for graphs of up to COMPACT_FAST_WORDS * 32 nodes (every BASELINE stream except the scaled
-// one): one warp per bitmap word, lane = bit.  The per-node flag reads (uptodate, has_msg) of a word are 32
-// parallel loads instead of a serial walk over its set bits, four words are in flight per warp, the flag
-// ballots are kept in shared memory so the write pass re-reads nothing, and the ordered output positions
-// come from per-word popcounts + one block scan.  The kernel was a chain of dependent loads before
-// (~10 us at 11 k nodes); now it is three short phases.
+// Same operator as a thread-block cluster: COMPACT_CTAS CTAs, each owns a contiguous slice of the bitmap (up to
+// COMPACT_FAST_WORDS words, i.e. graphs of up to COMPACT_CTAS * COMPACT_FAST_WORDS * 32 ~ 1 M nodes), one warp per
+// bitmap word / lane per bit.  The per-node flag reads (uptodate, has_msg) of a word are 32 parallel loads
+// instead of a serial walk over its set bits, the flag ballots are kept in shared memory so the write pass
+// re-reads nothing, and the ordered output positions come from per-word popcounts + one block scan + the slice
+// totals of the lower-ranked CTAs read through distributed shared memory.  On one SM the kernel spent ~19 k
+// cycles (in-kernel trace: 5-7 k in the flag loads, 7 k in the output stores - one SM's load/store path
+// serving the whole graph); spread over the cluster each SM handles an eighth of both.
 #define COMPACT_FAST_WORDS 4096
+#define COMPACT_CTAS 8
 __global__ void __launch_bounds__(1024)
-compact_involved_fast_kernel(uint32_t* __restrict__ bitmap, int n_words, int64_t n_nodes,
-                             uint8_t* __restrict__ has_msg, uint8_t* __restrict__ uptodate,
-                             int64_t* __restrict__ involved, int64_t cap, int64_t* __restrict__ local_index,
-                             int64_t* __restrict__ outdated, int32_t* __restrict__ gru_row,
-                             int64_t* __restrict__ restart_nodes, int32_t* __restrict__ counts,
-                             uint32_t* __restrict__ err_flags) {
-  extern __shared__ uint32_t cw[];           // [3][n_words] masks (member, restart, pending) then [3][n_words] offsets
+compact_involved_cluster_kernel(uint32_t* __restrict__ bitmap, int n_words, int chunk, int64_t n_nodes,
+                                uint8_t* __restrict__ has_msg, uint8_t* __restrict__ uptodate,
+                                int64_t* __restrict__ involved, int64_t cap, int64_t* __restrict__ local_index,
+                                int64_t* __restrict__ outdated, int32_t* __restrict__ gru_row,
+                                int64_t* __restrict__ restart_nodes, int32_t* __restrict__ counts,
+                                uint32_t* __restrict__ err_flags) {
+  extern __shared__ uint32_t cw[];           // [3][chunk] masks (member, restart, pending) then [3][chunk] offsets
   uint32_t* m_mem = cw;
-  uint32_t* m_rst = cw + n_words;
-  uint32_t* m_out = cw + 2 * n_words;
-  int* off = reinterpret_cast<int*>(cw + 3 * n_words);   // [3][n_words]
+  uint32_t* m_rst = cw + chunk;
+  uint32_t* m_out = cw + 2 * chunk;
+  int* off = reinterpret_cast<int*>(cw + 3 * chunk);   // [3][chunk]
   __shared__ int sm[3][32];
-  __shared__ int total[3];
+  __shared__ int total[3];                   // this slice's totals (involved, outdated, restart): read by the peers
+  __shared__ int peer[COMPACT_CTAS][3];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
+  const int rank = (int)cluster_cta_rank();
+  const int w_begin = rank * chunk < n_words ? rank * chunk : n_words;
+  const int nw = (w_begin + chunk < n_words ? w_begin + chunk : n_words) - w_begin;
   pdl_trigger();
   pdl_wait();      // the finder marks the bitmap
-  // ---- phase 0: the bitmap itself (one load per thread), so the flag loads below depend on shared memory only ----
-  for (int w = tid; w < n_words; w += 1024) m_mem[w] = bitmap[w];
+  // ---- phase 0: the bitmap slice (one load per thread), so the flag loads below depend on shared memory only ----
+  for (int w = tid; w < nw; w += 1024) m_mem[w] = bitmap[w_begin + w];
   __syncthreads();
   // ---- phase 1: flags of every member node, CW words per warp in flight ----
-  constexpr int CW = 8;
-  for (int w0 = warp * CW; w0 < n_words; w0 += 32 * CW) {
+  constexpr int CW = 4;
+  for (int w0 = warp * CW; w0 < nw; w0 += 32 * CW) {
     uint32_t bits[CW];
     uint8_t up[CW], hm[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
       const int w = w0 + i;
-      bits[i] = w < n_words ? m_mem[w] : 0u;
+      bits[i] = w < nw ? m_mem[w] : 0u;
       up[i] = 1;
       hm[i] = 0;
-      const int64_t u = (int64_t)w * 32 + lane;
+      const int64_t u = (int64_t)(w_begin + w) * 32 + lane;
       if ((bits[i] >> lane) & 1u) {
         if (uptodate != nullptr) up[i] = uptodate[u];
         if (has_msg != nullptr) hm[i] = has_msg[u];
@@ -248,16 +259,16 @@ compact_involved_fast_kernel(uint32_t* __restrict__ bitmap, int n_words, int64_t
       const bool rst = member && uptodate != nullptr && up[i] == 0;
       const bool pend = member && hm[i] != 0 && !rst;
       const uint32_t br = __ballot_sync(TIGER_FULL_MASK, rst), bp = __ballot_sync(TIGER_FULL_MASK, pend);
-      if (lane == 0 && w < n_words) {
+      if (lane == 0 && w < nw) {
         m_rst[w] = br;
         m_out[w] = bp;
       }
     }
   }
   __syncthreads();
-  // ---- phase 2: ordered output offsets of every word ----
-  const int wpt = (n_words + 1023) / 1024;
-  const int a0 = tid * wpt, a1 = (a0 + wpt < n_words) ? a0 + wpt : n_words;
+  // ---- phase 2: ordered output offsets of every word (slice-relative), then the cluster-wide bases ----
+  const int wpt = (nw + 1023) / 1024;
+  const int a0 = tid * wpt < nw ? tid * wpt : nw, a1 = (a0 + wpt < nw) ? a0 + wpt : nw;
   int c_inv = 0, c_out = 0, c_rst = 0;
   for (int w = a0; w < a1; ++w) {
     c_inv += __popc(m_mem[w]);
@@ -268,41 +279,57 @@ compact_involved_fast_kernel(uint32_t* __restrict__ bitmap, int n_words, int64_t
   block_exscan3(o_inv, o_out, o_rst, total, sm);
   for (int w = a0; w < a1; ++w) {
     off[w] = o_inv;
-    off[n_words + w] = o_rst;
-    off[2 * n_words + w] = o_out;
+    off[chunk + w] = o_rst;
+    off[2 * chunk + w] = o_out;
     o_inv += __popc(m_mem[w]);
     o_rst += __popc(m_rst[w]);
     o_out += __popc(m_out[w]);
   }
-  __syncthreads();
+  cluster_sync_all();                        // every slice's totals are published (and this CTA's offsets complete)
+  if (tid < COMPACT_CTAS * 3) {
+    const uint32_t addr = cluster_map_shared(smem_addr_u32(total) + (uint32_t)(tid % 3) * 4u, (uint32_t)(tid / 3));
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    peer[tid / 3][tid % 3] = v;
+  }
+  cluster_sync_all();                        // nobody reads a peer's shared memory after this point
+  int base[3] = {0, 0, 0}, grand[3] = {0, 0, 0};   // order of total[]: involved, outdated, restart
+#pragma unroll
+  for (int r = 0; r < COMPACT_CTAS; ++r)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int v = peer[r][k];
+      grand[k] += v;
+      if (r < rank) base[k] += v;
+    }
   // ---- phase 3: independent stores, lane = bit ----
   const uint32_t lt = (1u << lane) - 1u;
-  for (int w = warp; w < n_words; w += 32) {
+  for (int w = warp; w < nw; w += 32) {
     const uint32_t bits = m_mem[w];
     if (bits == 0u) continue;
     const uint32_t br = m_rst[w], bp = m_out[w];
-    if (lane == 0) bitmap[w] = 0u;
+    if (lane == 0) bitmap[w_begin + w] = 0u;
     if (!((bits >> lane) & 1u)) continue;
-    const int64_t u = (int64_t)w * 32 + lane;
-    const int r_inv = off[w] + __popc(bits & lt);
+    const int64_t u = (int64_t)(w_begin + w) * 32 + lane;
+    const int r_inv = base[0] + off[w] + __popc(bits & lt);
     if (r_inv < cap) involved[r_inv] = u;
     if (local_index != nullptr) local_index[u] = r_inv;
     const bool rst = (br >> lane) & 1u, pend = (bp >> lane) & 1u;
     if (rst) {
-      const int r = off[n_words + w] + __popc(br & lt);
+      const int r = base[2] + off[chunk + w] + __popc(br & lt);
       if (r < cap) restart_nodes[r] = u;
       uptodate[u] = 1;
       if (has_msg != nullptr) has_msg[u] = 0;  // msg_store.clear(nids): memory.py:136
     }
-    const int r_out = off[2 * n_words + w] + __popc(bp & lt);
+    const int r_out = base[1] + off[2 * chunk + w] + __popc(bp & lt);
     if (gru_row != nullptr) gru_row[u] = pend ? r_out : -1;
     if (pend && r_out < cap) outdated[r_out] = u;
   }
-  if (tid == 0) {
-    counts[0] = total[0] < cap ? total[0] : (int)cap;
-    counts[1] = total[1] < cap ? total[1] : (int)cap;
-    counts[2] = total[2] < cap ? total[2] : (int)cap;
-    if (total[0] > cap && err_flags != nullptr) atomicOr(err_flags, TIGER_ERR_CAPACITY);
+  if (rank == 0 && tid == 0) {
+    counts[0] = grand[0] < cap ? grand[0] : (int)cap;
+    counts[1] = grand[1] < cap ? grand[1] : (int)cap;
+    counts[2] = grand[2] < cap ? grand[2] : (int)cap;
+    if (grand[0] > cap && err_flags != nullptr) atomicOr(err_flags, TIGER_ERR_CAPACITY);
   }
 }
 
@@ -314,17 +341,19 @@ extern "C" int tiger_compact_involved(uint32_t* bitmap, int64_t n_nodes, uint8_t
   if (has_msg != nullptr && outdated == nullptr) return TIGER_EINVAL;
   if (uptodate != nullptr && restart_nodes == nullptr) return TIGER_EINVAL;
   const int64_t n_words = (n_nodes + 31) / 32;
-  if (n_words <= COMPACT_FAST_WORDS) {
+  if (n_words <= (int64_t)COMPACT_CTAS * COMPACT_FAST_WORDS) {
     static bool configured = false;
     if (!configured) {
-      if (cudaFuncSetAttribute(compact_involved_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      if (cudaFuncSetAttribute(compact_involved_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                COMPACT_FAST_WORDS * 6 * (int)sizeof(uint32_t)) != cudaSuccess)
         return TIGER_ECUDA;
       configured = true;
     }
-    return tiger_launch_chain(compact_involved_fast_kernel, dim3(1), dim3(1024), (size_t)n_words * 6 * sizeof(uint32_t),
-                              as_stream(stream), dim3(1, 1, 1), bitmap, (int)n_words, n_nodes, has_msg, uptodate, involved,
-                              cap_involved, local_index, outdated, gru_row, restart_nodes, counts, err_flags);
+    const int chunk = (int)((n_words + COMPACT_CTAS - 1) / COMPACT_CTAS);
+    return tiger_launch_chain(compact_involved_cluster_kernel, dim3(COMPACT_CTAS), dim3(1024),
+                              (size_t)chunk * 6 * sizeof(uint32_t), as_stream(stream), dim3(COMPACT_CTAS, 1, 1), bitmap,
+                              (int)n_words, chunk, n_nodes, has_msg, uptodate, involved, cap_involved, local_index, outdated,
+                              gru_row, restart_nodes, counts, err_flags);
   }
   compact_involved_kernel<<<1, 1024, 0, as_stream(stream)>>>(bitmap, n_words, has_msg, uptodate, involved,
                                                             cap_involved, local_index, outdated, gru_row,

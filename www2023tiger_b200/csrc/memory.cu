@@ -11,6 +11,17 @@ static inline unsigned row_grid(int64_t n_rows) {
   return (unsigned)((n_rows + per_cta - 1) / per_cta);
 }
 
+// rows one warp resolves and copies (lane-per-row index chain, warp_copy_lane_rows): few rows (a batch of 200
+// events) -> 4, so that the rows spread over many warps; many rows -> up to 32, so that the chain of dependent
+// index loads is paid once per 32 rows and the warp spends its life streaming
+static inline int rows_per_warp(int64_t n_rows) {
+  return n_rows >= (1 << 16) ? 32 : n_rows >= (1 << 14) ? 16 : n_rows >= (1 << 12) ? 8 : ROWS_PER_WARP;
+}
+static inline unsigned row_grid(int64_t n_rows, int rpw) {
+  const int64_t per_cta = (int64_t)ROW_WARPS * rpw;
+  return (unsigned)((n_rows + per_cta - 1) / per_cta);
+}
+
 __device__ __forceinline__ int64_t effective_count(const int32_t* count, int64_t n) {
   if (count == nullptr) return n;
   const int64_t c = *count;
@@ -18,63 +29,58 @@ __device__ __forceinline__ int64_t effective_count(const int32_t* count, int64_t
 }
 
 // ---------------------------------------------------------------- a11 Memory.get
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 gather_rows_kernel(const float* __restrict__ table, int64_t width, const int64_t* __restrict__ ids, int64_t n,
-                   float* __restrict__ out, const float* __restrict__ ts_table, float* __restrict__ out_ts) {
-  const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+                   float* __restrict__ out, const float* __restrict__ ts_table, float* __restrict__ out_ts, int rpw) {
+  const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   if (r0 >= n) return;
   const int lane = lane_id();
-  float* dst[ROWS_PER_WARP];
-  const float* src[ROWS_PER_WARP];
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_WARP; ++i) {
-    const int64_t r = r0 + i;
-    const bool live = r < n;
-    const int64_t u = live ? ids[r] : 0;
-    dst[i] = (live && out != nullptr) ? out + r * width : nullptr;
-    src[i] = table + u * width;
-    if (live && out_ts != nullptr && lane == i) out_ts[r] = ts_table[u];
+  const int64_t r = r0 + lane;
+  float* dst = nullptr;
+  const float* src = table;
+  if (lane < rpw && r < n) {               // lane l owns row l: index and scalar side
+    const int64_t u = ids[r];
+    if (out != nullptr) dst = out + r * width;
+    src = table + u * width;
+    if (out_ts != nullptr) out_ts[r] = ts_table[u];
   }
-  warp_copy_rows<ROWS_PER_WARP>(dst, src, (int)width, lane);
+  warp_copy_lane_rows(dst, src, rpw, (int)width, lane);
 }
 
 extern "C" int tiger_gather_rows(const float* table, int64_t width, const int64_t* ids, int64_t n, float* out,
                                  const float* ts_table, float* out_ts, void* stream) {
   if (n < 0 || width < 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
-  gather_rows_kernel<<<row_grid(n), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      table, width, ids, n, out, ts_table, out_ts);
+  const int rpw = rows_per_warp(n);
+  gather_rows_kernel<<<row_grid(n, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      table, width, ids, n, out, ts_table, out_ts, rpw);
   return tiger_launch_status();
 }
 
 // ---------------------------------------------------------------- a11 Memory.set
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 scatter_rows_kernel(float* __restrict__ table, int64_t width, const int64_t* __restrict__ ids, int64_t n,
                     const int32_t* __restrict__ count, const float* __restrict__ vals,
                     float* __restrict__ ts_table, const float* __restrict__ ts, uint8_t* __restrict__ active,
-                    int check, uint32_t* __restrict__ err_flags) {
-  const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+                    int check, uint32_t* __restrict__ err_flags, int rpw) {
+  const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   const int64_t n_eff = effective_count(count, n);
   if (r0 >= n_eff) return;
   const int lane = lane_id();
-  float* dst[ROWS_PER_WARP];
-  const float* src[ROWS_PER_WARP];
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_WARP; ++i) {
-    const int64_t r = r0 + i;
-    const bool live = r < n_eff;
-    const int64_t u = live ? ids[r] : 0;
-    if (live && lane == i) {               // lane i owns the scalar side of row i: the rows proceed in parallel
-      if (ts_table != nullptr) {
-        if (check && err_flags != nullptr && ts_table[u] > ts[r]) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
-        ts_table[u] = ts[r];
-      }
-      if (active != nullptr) active[u] = 1;
+  const int64_t r = r0 + lane;
+  float* dst = nullptr;
+  const float* src = vals;
+  if (lane < rpw && r < n_eff) {           // lane l owns row l: index and scalar side
+    const int64_t u = ids[r];
+    if (ts_table != nullptr) {
+      if (check && err_flags != nullptr && ts_table[u] > ts[r]) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+      ts_table[u] = ts[r];
     }
-    dst[i] = (live && table != nullptr) ? table + u * width : nullptr;
-    src[i] = vals + r * width;
+    if (active != nullptr) active[u] = 1;
+    if (table != nullptr) dst = table + u * width;
+    src = vals + r * width;
   }
-  warp_copy_rows<ROWS_PER_WARP>(dst, src, (int)width, lane);
+  warp_copy_lane_rows(dst, src, rpw, (int)width, lane);
 }
 
 extern "C" int tiger_scatter_rows(float* table, int64_t width, const int64_t* ids, int64_t n,
@@ -82,8 +88,9 @@ extern "C" int tiger_scatter_rows(float* table, int64_t width, const int64_t* id
                                   uint8_t* active, int check, uint32_t* err_flags, void* stream) {
   if (n < 0 || width < 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
-  scatter_rows_kernel<<<row_grid(n), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      table, width, ids, n, count, vals, ts_table, ts, active, check, err_flags);
+  const int rpw = rows_per_warp(n);
+  scatter_rows_kernel<<<row_grid(n, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      table, width, ids, n, count, vals, ts_table, ts, active, check, err_flags, rpw);
   return tiger_launch_status();
 }
 
@@ -245,56 +252,35 @@ extern "C" int tiger_store_messages_dense(const int64_t* src, const int64_t* dst
 }
 
 // ---------------------------------------------------------------- a17 right write-back (+ a19)
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 right_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, const uint8_t* __restrict__ winner,
                        const int32_t* __restrict__ gru_row, const float* __restrict__ h_new, int d,
                        float* __restrict__ right_vals, float* __restrict__ right_ts,
                        uint8_t* __restrict__ right_active, const float* __restrict__ msg_ts,
-                       uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags) {
-  const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+                       uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags, int rpw) {
+  const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   if (p0 >= n_pos) return;
   const int lane = lane_id();
-  float* dst[ROWS_PER_WARP];
-  const float* src[ROWS_PER_WARP];
-  int64_t node[ROWS_PER_WARP];
-  // index chain of the 4 positions side by side: position -> node -> {pending flag, GRU row, clocks} -> row copy
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_WARP; ++i) {
-    const int64_t p = p0 + i;
-    node[i] = (p < n_pos && winner[p]) ? pos_ids[p] : -1;
-  }
-  float t_msg = 0.f, t_mem = 0.f;
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_WARP; ++i) {
-    dst[i] = nullptr;
-    src[i] = h_new;
-    if (node[i] < 0) continue;
-    const int64_t u = node[i];
+  const int64_t p = p0 + lane;
+  // lane l resolves position l: position -> node -> {pending flag, GRU row, clocks}; every selected node occurs at
+  // one position only (tiger_select_latest), so no two lanes touch the same node
+  float* dst = nullptr;
+  const float* src = h_new;
+  if (lane < rpw && p < n_pos && winner[p]) {
+    const int64_t u = pos_ids[p];
     const uint8_t pending = has_msg[u];
     const int32_t r = gru_row[u];
-    if (lane == i) {                       // lane i owns the scalar side of row i
-      t_msg = msg_ts[u];
-      t_mem = right_ts[u];
-    }
-    if (pending == 0) {                    // positive without a pending message: nothing to persist
-      node[i] = -1;
-      continue;
-    }
-    dst[i] = right_vals + u * (int64_t)d;
-    src[i] = h_new + (int64_t)r * d;
-  }
-  __syncwarp();                            // every lane has read has_msg before its owner lane clears it
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_WARP; ++i) {
-    if (node[i] >= 0 && lane == i) {
-      const int64_t u = node[i];
+    const float t_msg = msg_ts[u], t_mem = right_ts[u];
+    if (pending != 0) {                    // a positive without a pending message has nothing to persist
       if (err_flags != nullptr && t_mem > t_msg) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
       right_ts[u] = t_msg;
       if (right_active != nullptr) right_active[u] = 1;
       has_msg[u] = 0;                      // the message is consumed (tiger.py:240)
+      dst = right_vals + u * (int64_t)d;
+      src = h_new + (int64_t)r * d;
     }
   }
-  warp_copy_rows<ROWS_PER_WARP>(dst, src, d, lane);
+  warp_copy_lane_rows(dst, src, rpw, d, lane);
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
@@ -327,8 +313,9 @@ extern "C" int tiger_right_writeback(const int64_t* pos_ids, int64_t n_pos, cons
   if (n_pos < 0 || d <= 0) return TIGER_EINVAL;
   if ((hprev_left == nullptr) != (hprev_right == nullptr)) return TIGER_EINVAL;
   if (n_pos == 0) return TIGER_OK;
-  right_writeback_kernel<<<row_grid(n_pos), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      pos_ids, n_pos, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg, err_flags);
+  const int rpw = rows_per_warp(n_pos);
+  right_writeback_kernel<<<row_grid(n_pos, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      pos_ids, n_pos, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg, err_flags, rpw);
   if (hprev_left != nullptr)
     hprev_copy_kernel<<<row_grid(2 * n_pos), ROW_WARPS * 32, 0, as_stream(stream)>>>(pos_ids, n_pos, d, left_vals,
                                                                                     right_vals, hprev_left, hprev_right);
@@ -336,33 +323,27 @@ extern "C" int tiger_right_writeback(const int64_t* pos_ids, int64_t n_pos, cons
 }
 
 // ---------------------------------------------------------------- a18 left write-back
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 left_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, int64_t batch,
                       const uint8_t* __restrict__ winner, const float* __restrict__ h_left, int d,
                       const float* __restrict__ ts, float* __restrict__ left_vals, float* __restrict__ left_ts,
-                      uint8_t* __restrict__ left_active, uint32_t* __restrict__ err_flags) {
-  const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * ROWS_PER_WARP;
+                      uint8_t* __restrict__ left_active, uint32_t* __restrict__ err_flags, int rpw) {
+  const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   if (p0 >= n_pos) return;
   const int lane = lane_id();
-  float* dst[ROWS_PER_WARP];
-  const float* src[ROWS_PER_WARP];
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_WARP; ++i) {
-    const int64_t p = p0 + i;
-    dst[i] = nullptr;
-    src[i] = h_left;
-    if (p >= n_pos || !winner[p]) continue;
+  const int64_t p = p0 + lane;
+  float* dst = nullptr;
+  const float* src = h_left;
+  if (lane < rpw && p < n_pos && winner[p]) {   // lane l owns position l: index and scalar side
     const int64_t u = pos_ids[p];
-    if (lane == i) {                       // lane i owns the scalar side of row i
-      const float t = ts[p % batch];
-      if (err_flags != nullptr && left_ts[u] > t) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
-      left_ts[u] = t;
-      if (left_active != nullptr) left_active[u] = 1;
-    }
-    dst[i] = left_vals + u * (int64_t)d;
-    src[i] = h_left + p * d;
+    const float t = ts[p % batch];
+    if (err_flags != nullptr && left_ts[u] > t) atomicOr(err_flags, TIGER_ERR_PAST_MEMORY);
+    left_ts[u] = t;
+    if (left_active != nullptr) left_active[u] = 1;
+    dst = left_vals + u * (int64_t)d;
+    src = h_left + p * d;
   }
-  warp_copy_rows<ROWS_PER_WARP>(dst, src, d, lane);
+  warp_copy_lane_rows(dst, src, rpw, d, lane);
 }
 
 extern "C" int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64_t batch, const uint8_t* winner,
@@ -370,8 +351,9 @@ extern "C" int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64
                                     uint8_t* left_active, uint32_t* err_flags, void* stream) {
   if (n_pos < 0 || d <= 0 || batch <= 0) return TIGER_EINVAL;
   if (n_pos == 0) return TIGER_OK;
-  left_writeback_kernel<<<row_grid(n_pos), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      pos_ids, n_pos, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags);
+  const int rpw = rows_per_warp(n_pos);
+  left_writeback_kernel<<<row_grid(n_pos, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
+      pos_ids, n_pos, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags, rpw);
   return tiger_launch_status();
 }
 
