@@ -28,6 +28,9 @@
 //   sgemm_nt (tcgen05)    HID = relu(KVC W2f^T + b1)                    [n, d]
 //   sgemm_nt (tcgen05)    z = HID W2^T + b2                             [n, d]
 #include "common.cuh"
+#ifdef TIGER_TRACE
+#include <cstdio>
+#endif
 
 extern "C" int tiger_sgemm_nt_batched(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw,
                                       int64_t stride_w, const float* bias, int64_t stride_bias, float* C,
@@ -392,7 +395,7 @@ __device__ __forceinline__ int fast_div(int f, float inv_w) { return __float2int
 
 // HT = number of heads as a compile-time constant (0: any number up to ATT_MAXH, predicated loops)
 template <int HT>
-__global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, 5) attn_score_pool_kernel(const AttArgs a) {
   extern __shared__ __align__(16) float att_smem[];
   const int d = a.dm.d, de = a.dm.de, K = a.dm.K, H = HT > 0 ? HT : a.dm.H, C = a.dm.C, Cp = a.dm.Cp, Cq = a.dm.Cq;
   constexpr int HL = HT > 0 ? HT : ATT_MAXH;   // unrolled head loops run over HL, predicated by h < H
@@ -405,6 +408,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
   __shared__ float s_dt[ATT_MAXK];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block(), n_warps = ATT_THREADS / 32;
   const int64_t q = blockIdx.x;
+#ifdef TIGER_TRACE
+  long long tr[10]; int trn = 0;
+#define SP_MARK() tr[trn++] = clock64()
+#else
+#define SP_MARK() do { } while (0)
+#endif
+  SP_MARK();
   pdl_trigger();
   pdl_wait();      // qkf comes from the Wqk product
   const float* qkf = a.w.qkf + q * a.dm.ld_qkf;
@@ -439,6 +449,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
     s_nf[K] = a.nfeats != nullptr ? a.nfeats + u * d : nullptr;
   }
   __syncthreads();
+  SP_MARK();   // metadata
   float* out = a.w.kvc + q * a.dm.ld_kvc;
   // ---- gather: node rows (+ node features) and edge-feature rows of all slots ----
   const bool vec = (d & 3) == 0 && (de & 3) == 0 && (Cp & 3) == 0 &&
@@ -461,7 +472,49 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
         reinterpret_cast<float4*>(out + a.dm.off_c)[c] = v;
       }
     }
-    for (int f0 = tid; f0 < K * d4; f0 += 4 * ATT_THREADS) {
+    // first pass: the first 2 * ATT_THREADS node-row vectors and edge-feature vectors (everything at K <= 11,
+    // d = 172) are loaded into registers here and stored only after the time codes below have been computed:
+    // the cosines (a few thousand instructions per CTA) run while the random-row reads are in flight
+    float4 pv[2], pn[2], pe[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int f = tid + u * ATT_THREADS;
+      pv[u] = z4; pn[u] = z4; pe[u] = z4;
+      if (f < K * d4) {
+        const int j = fast_div(f, inv_d4), c = f - j * d4;
+        if (s_row[j] != nullptr) {
+          pv[u] = reinterpret_cast<const float4*>(s_row[j])[c];
+          if (s_nf[j] != nullptr) pn[u] = reinterpret_cast<const float4*>(s_nf[j])[c];
+        }
+      }
+      if (f < K * de4) {
+        const int j = fast_div(f, inv_de4), c = f - j * de4;
+        if (s_ef[j] != nullptr) pe[u] = reinterpret_cast<const float4*>(s_ef[j])[c];
+      }
+    }
+    // ---- time code of every slot ----
+    for (int f = tid; f < K * d; f += ATT_THREADS) {
+      const int j = fast_div(f, inv_d), c = f - j * d;
+      float v = 0.f;
+      if (s_row[j] != nullptr)
+        v = a.dense ? a.kt[(q * K + j) * d + c] : time_enc(s_dt[j], a.time_w[c], a.time_b[c]);
+      kv[j * Cp + d + de + c] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int f = tid + u * ATT_THREADS;
+      if (f < K * d4) {
+        const int j = fast_div(f, inv_d4), c = f - j * d4;
+        reinterpret_cast<float4*>(kv + j * Cp)[c] =
+            make_float4(pv[u].x + pn[u].x, pv[u].y + pn[u].y, pv[u].z + pn[u].z, pv[u].w + pn[u].w);
+      }
+      if (f < K * de4) {
+        const int j = fast_div(f, inv_de4), c = f - j * de4;
+        reinterpret_cast<float4*>(kv + j * Cp + d)[c] = pe[u];
+      }
+    }
+    // remaining vectors (large K): four loads in flight per thread
+    for (int f0 = tid + 2 * ATT_THREADS; f0 < K * d4; f0 += 4 * ATT_THREADS) {
       float4 v[4], n4[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -486,7 +539,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
         }
       }
     }
-    for (int f0 = tid; f0 < K * de4; f0 += 4 * ATT_THREADS) {
+    for (int f0 = tid + 2 * ATT_THREADS; f0 < K * de4; f0 += 4 * ATT_THREADS) {
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -520,16 +573,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
       const int j = fast_div(f, inv_de), c = f - j * de;
       kv[j * Cp + d + c] = s_ef[j] != nullptr ? s_ef[j][c] : 0.f;
     }
+    for (int f = tid; f < K * d; f += ATT_THREADS) {   // time code of every slot
+      const int j = fast_div(f, inv_d), c = f - j * d;
+      float v = 0.f;
+      if (s_row[j] != nullptr)
+        v = a.dense ? a.kt[(q * K + j) * d + c] : time_enc(s_dt[j], a.time_w[c], a.time_b[c]);
+      kv[j * Cp + d + de + c] = v;
+    }
   }
-  // ---- time code of every slot ----
-  for (int f = tid; f < K * d; f += ATT_THREADS) {
-    const int j = fast_div(f, inv_d), c = f - j * d;
-    float v = 0.f;
-    if (s_row[j] != nullptr)
-      v = a.dense ? a.kt[(q * K + j) * d + c] : time_enc(s_dt[j], a.time_w[c], a.time_b[c]);
-    kv[j * Cp + d + de + c] = v;
-  }
+  SP_MARK();   // gathers + time code
+  SP_MARK();
   __syncthreads();
+  SP_MARK();   // time code
   // ---- scores: one warp per slot ----
   for (int j = warp; j < K; j += n_warps) {
     const float* row = kv + j * Cp;
@@ -554,25 +609,26 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
     }
   }
   __syncthreads();
-  // ---- masked softmax over the K slots, one thread per head ----
-  if (tid < H) {
-    float* row = sc + tid * K;
-    float m = -INFINITY;
-    for (int j = 0; j < K; ++j) m = fmaxf(m, row[j]);
-    if (tid == 0 && !a.dense) out[a.dm.off_live] = m == -INFINITY ? 0.f : 1.f;
-    if (m == -INFINITY) {
-      for (int j = 0; j < K; ++j) row[j] = 0.f;   // every slot is padding: the output row is zero-filled later
-    } else {
-      float sum = 0.f;
-      for (int j = 0; j < K; ++j) {
-        const float e = expf(row[j] - m);
-        row[j] = e;
-        sum += e;
-      }
-      for (int j = 0; j < K; ++j) row[j] = row[j] / sum;
+  SP_MARK();   // scores
+  // ---- masked softmax over the K slots, one warp per head (K <= ATT_MAXK = 64: two values per lane) ----
+  for (int h = warp; h < H; h += n_warps) {
+    float* row = sc + h * K;
+    const float x0 = lane < K ? row[lane] : -INFINITY, x1 = lane + 32 < K ? row[lane + 32] : -INFINITY;
+    const float m = warp_max(fmaxf(x0, x1));
+    if (h == 0 && lane == 0 && !a.dense) out[a.dm.off_live] = m == -INFINITY ? 0.f : 1.f;
+    float e0 = 0.f, e1 = 0.f;                 // every slot padding: the weights stay 0 and the pooled row is zero
+    if (m != -INFINITY) {
+      e0 = lane < K ? expf(x0 - m) : 0.f;
+      e1 = lane + 32 < K ? expf(x1 - m) : 0.f;
+      const float sum = warp_sum(e0 + e1);
+      e0 = e0 / sum;
+      e1 = e1 / sum;
     }
+    if (lane < K) row[lane] = e0;
+    if (lane + 32 < K) row[lane + 32] = e1;
   }
   __syncthreads();
+  SP_MARK();   // softmax
   // ---- pooled keys kvbar[h][c] = sum_j p[h][j] kv[j][c] ----
   for (int c = tid; c < Cp; c += ATT_THREADS) {   // columns C..Cp-1 are alignment padding: written as zeros
     float acc[HL];
@@ -588,6 +644,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_score_pool_kernel(const AttA
     for (int h = 0; h < HL; ++h)
       if (HT > 0 || h < H) out[h * Cp + c] = acc[h];
   }
+#ifdef TIGER_TRACE
+  SP_MARK();
+  if ((q == 0 || q == 300) && (tid == 0 || tid == 128))
+    printf("pool q%d t%d: meta %lld gather %lld tcode %lld scores %lld softmax %lld pooled %lld\n", (int)q, tid, tr[1] - tr[0],
+           tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5]);
+#endif
 }
 
 template <int HT>
