@@ -315,8 +315,7 @@ def run_b200(args):
         j = i % avail
         if j == 0 and i > 0:
             eng.reset()           # epoch boundary (train_self_supervised.py:127-128): the window wraps
-        eng.inp.copy_(dev_in[j], non_blocking=True)
-        runner.run_device()
+        runner.submit_device(dev_in[j])
 
     def barrier():
         if world > 1:

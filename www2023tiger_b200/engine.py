@@ -79,16 +79,11 @@ class TigerEngine:
         self.winner = z(2 * B, dt=u8)
         self.sel_count = z(1, dt=i32)
         self.out_buf = z(2 * B + 1)                    # [pos scores | neg scores | loss]
-        self.scores, self.loss = self.out_buf[:2 * B], self.out_buf[2 * B:]
         self.hprev_left = z(2 * B, d) if want_restarter_targets else None
         self.hprev_right = z(2 * B, d) if want_restarter_targets else None
         # ---- batch inputs: [src | dst | neg | eids] int64 and ts float64, one contiguous buffer ----
         self.inp = z(5 * B, dt=i64)
-        self.batch_nids = self.inp[:3 * B]
-        self.src, self.dst, self.neg = self.inp[:B], self.inp[B:2 * B], self.inp[2 * B:3 * B]
-        self.pos = self.inp[:2 * B]
-        self.eids = self.inp[3 * B:4 * B]
-        self.ts64 = self.inp[4 * B:].view(f64)
+        self.bind_io(self.inp, self.out_buf)
         # ---- parameters ----
         self._side = torch.cuda.Stream(device=dev)
         self._ev_fork, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
@@ -241,6 +236,21 @@ class TigerEngine:
                               self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
         main.wait_event(self._ev_side2)
 
+    def bind_io(self, inp: Tensor, out_buf: Tensor):
+        """Points the batch-input views ([src | dst | neg | eids | ts as f64 bits], int64 [5B]) and the result
+        views ([pos scores | neg scores | loss], f32 [2B + 1]) at the given device buffers.  Launches issued (or
+        captured into a CUDA graph) afterwards read / write them: the host path keeps one buffer pair per
+        staging slot so that uploads and downloads of neighbouring batches overlap the kernels."""
+        B = self.B
+        assert inp.numel() == 5 * B and inp.dtype == i64 and out_buf.numel() == 2 * B + 1 and out_buf.dtype == f32
+        self.inp, self.out_buf = inp, out_buf
+        self.batch_nids = inp[:3 * B]
+        self.src, self.dst, self.neg = inp[:B], inp[B:2 * B], inp[2 * B:3 * B]
+        self.pos = inp[:2 * B]
+        self.eids = inp[3 * B:4 * B]
+        self.ts64 = inp[4 * B:].view(f64)
+        self.scores, self.loss = out_buf[:2 * B], out_buf[2 * B:]
+
     def launches_per_step(self) -> int:
         n = sum(KERNELS_PER_STEP.values())
         if self.lazy_restart:
@@ -262,12 +272,20 @@ class StreamRunner:
     def __init__(self, engine: TigerEngine, n_slots: int = 4):
         self.e = engine
         self.graph = None
+        self.host_graphs = None
         B = engine.B
         self.n_slots = n_slots
         self.h_in = [torch.empty(5 * B, dtype=i64).pin_memory() for _ in range(n_slots)]
         self.h_out = [torch.empty(2 * B + 1, dtype=f32).pin_memory() for _ in range(n_slots)]
+        dev = engine.inp.device
+        self.d_in = [torch.zeros(5 * B, dtype=i64, device=dev) for _ in range(n_slots)]
+        self.d_out = [torch.zeros(2 * B + 1, dtype=f32, device=dev) for _ in range(n_slots)]
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(n_slots)]
+        self.ev_done = [torch.cuda.Event() for _ in range(n_slots)]
         self.events = [torch.cuda.Event() for _ in range(n_slots)]
         self.slot_busy = [False] * n_slots
+        self.slot_used = [False] * n_slots
         self.slot = 0
 
     def capture(self, warmup: int = 2):
@@ -284,6 +302,19 @@ class StreamRunner:
         with torch.cuda.graph(self.graph):
             e.step()
         torch.cuda.synchronize()
+        # host-buffer path: one graph per staging slot, bound to that slot's device input / result buffers.  The
+        # upload of batch i+1 (copy-in stream) and the download of batch i-1 (copy-out stream) then run beside
+        # the kernels of batch i; the kernels themselves still replay strictly in batch order on one stream.
+        self.host_graphs = []
+        inp0, out0 = e.inp, e.out_buf
+        for slot in range(self.n_slots):
+            e.bind_io(self.d_in[slot], self.d_out[slot])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                e.step()
+            self.host_graphs.append(g)
+        e.bind_io(inp0, out0)
+        torch.cuda.synchronize()
 
     def run_device(self):
         """Inputs already resident in engine.inp."""
@@ -291,6 +322,28 @@ class StreamRunner:
             self.graph.replay()
         else:
             self.e.step()
+
+    def submit_device(self, batch: Tensor):
+        """One step on a batch that is already resident in HBM (int64 [5B], layout of engine.inp): staged into the
+        next slot's input buffer on the copy-in stream (beside the previous batch's kernels), then that slot's
+        graph.  Results stay in d_out[slot]; returns the slot."""
+        if self.host_graphs is None:
+            self.e.inp.copy_(batch, non_blocking=True)
+            self.run_device()
+            return 0
+        slot = self.slot
+        self.slot = (slot + 1) % self.n_slots
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.s_in):
+            if self.slot_used[slot]:
+                self.s_in.wait_event(self.ev_done[slot])      # the slot's previous batch has been consumed
+            self.d_in[slot].copy_(batch, non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+        main.wait_event(self.ev_in[slot])
+        self.host_graphs[slot].replay()
+        self.ev_done[slot].record(main)
+        self.slot_used[slot] = True
+        return slot
 
     def fill_host(self, slot: int, src, dst, neg, ts, eids):
         B = self.e.B
@@ -307,10 +360,26 @@ class StreamRunner:
             self.events[slot].synchronize()
         self.fill_host(slot, src, dst, neg, ts, eids)
         e = self.e
-        e.inp.copy_(self.h_in[slot], non_blocking=True)
-        self.run_device()
-        self.h_out[slot].copy_(e.out_buf, non_blocking=True)
-        self.events[slot].record()
+        if self.host_graphs is not None:
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(self.s_in):
+                if self.slot_used[slot]:
+                    self.s_in.wait_event(self.ev_done[slot])  # the slot's previous batch has been consumed
+                self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
+                self.ev_in[slot].record(self.s_in)
+            main.wait_event(self.ev_in[slot])
+            self.host_graphs[slot].replay()
+            self.ev_done[slot].record(main)
+            self.slot_used[slot] = True
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_done[slot])
+                self.h_out[slot].copy_(self.d_out[slot], non_blocking=True)
+                self.events[slot].record(self.s_out)
+        else:
+            e.inp.copy_(self.h_in[slot], non_blocking=True)
+            self.run_device()
+            self.h_out[slot].copy_(e.out_buf, non_blocking=True)
+            self.events[slot].record()
         self.slot_busy[slot] = True
         return slot
 
