@@ -251,6 +251,18 @@ class TigerEngine:
         self.ts64 = inp[4 * B:].view(f64)
         self.scores, self.loss = out_buf[:2 * B], out_buf[2 * B:]
 
+    def finder_buffers(self, fresh: bool = False):
+        """The finder's outputs (neighbor tables, float32 batch times, involved-node bitmap).  They depend on the
+        static graph and the batch only, not on the memory state, so the finder of batch i+1 may run while batch
+        i is still in its model kernels - provided it writes its own set (`fresh=True` allocates one)."""
+        if not fresh:
+            return self.neigh_nids, self.neigh_eids, self.neigh_ts, self.ts32, self.bitmap
+        return tuple(torch.zeros_like(t) for t in
+                     (self.neigh_nids, self.neigh_eids, self.neigh_ts, self.ts32, self.bitmap))
+
+    def bind_finder(self, bufs):
+        self.neigh_nids, self.neigh_eids, self.neigh_ts, self.ts32, self.bitmap = bufs
+
     def launches_per_step(self) -> int:
         n = sum(KERNELS_PER_STEP.values())
         if self.lazy_restart:
@@ -283,6 +295,8 @@ class StreamRunner:
         self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         self.ev_in = [torch.cuda.Event() for _ in range(n_slots)]
         self.ev_done = [torch.cuda.Event() for _ in range(n_slots)]
+        self.finder_bufs = [engine.finder_buffers(fresh=True) for _ in range(n_slots)]
+        self.finder_graphs = None
         self.events = [torch.cuda.Event() for _ in range(n_slots)]
         self.slot_busy = [False] * n_slots
         self.slot_used = [False] * n_slots
@@ -305,15 +319,24 @@ class StreamRunner:
         # host-buffer path: one graph per staging slot, bound to that slot's device input / result buffers.  The
         # upload of batch i+1 (copy-in stream) and the download of batch i-1 (copy-out stream) then run beside
         # the kernels of batch i; the kernels themselves still replay strictly in batch order on one stream.
-        self.host_graphs = []
-        inp0, out0 = e.inp, e.out_buf
+        # The finder (a function of the static graph and the batch only) is captured separately per slot and
+        # replayed on the copy-in stream right behind the slot's upload, i.e. beside the model kernels of the
+        # previous batch; it writes the slot's own neighbor tables / bitmap, which that slot's model graph reads.
+        self.host_graphs, self.finder_graphs = [], []
+        inp0, out0, find0 = e.inp, e.out_buf, e.finder_buffers()
         for slot in range(self.n_slots):
             e.bind_io(self.d_in[slot], self.d_out[slot])
+            e.bind_finder(self.finder_bufs[slot])
+            gf = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf):
+                e.launch_finder()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                e.step()
+                e.launch_model()
+            self.finder_graphs.append(gf)
             self.host_graphs.append(g)
         e.bind_io(inp0, out0)
+        e.bind_finder(find0)
         torch.cuda.synchronize()
 
     def run_device(self):
@@ -338,6 +361,7 @@ class StreamRunner:
             if self.slot_used[slot]:
                 self.s_in.wait_event(self.ev_done[slot])      # the slot's previous batch has been consumed
             self.d_in[slot].copy_(batch, non_blocking=True)
+            self.finder_graphs[slot].replay()
             self.ev_in[slot].record(self.s_in)
         main.wait_event(self.ev_in[slot])
         self.host_graphs[slot].replay()
@@ -366,6 +390,7 @@ class StreamRunner:
                 if self.slot_used[slot]:
                     self.s_in.wait_event(self.ev_done[slot])  # the slot's previous batch has been consumed
                 self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
+                self.finder_graphs[slot].replay()
                 self.ev_in[slot].record(self.s_in)
             main.wait_event(self.ev_in[slot])
             self.host_graphs[slot].replay()
