@@ -192,3 +192,65 @@ def test_full_size_stream_properties(gu, name):
         finals.append([t.clone() for t in (e.left_vals, e.right_vals, e.msg_vals, e.left_ts, e.right_ts, e.out_buf)])
     for a, b in zip(*finals):
         assert torch.equal(a, b)
+
+
+def test_pipelined_host_and_device_paths_match_eager_steps(gu):
+    """StreamRunner keeps n_slots batches in flight (upload + finder of batch i+1 and download of batch i-1 beside
+    the model kernels of batch i, per-slot buffers): the results must be bit-identical to eager, strictly
+    sequential steps."""
+    shape = StreamShape('p', 700, 90, 12000, 16, None)
+    st = make_stream(shape, seed=5)
+    B, K, H, n_batches, start = 200, 10, 2, 26, 3000
+    neg = NegativeSampler(st.src, st.dst, seed=0).pre_sample_neg_dsts(st.n_events)
+    N, d = st.n_nodes, st.dim
+    W = perturb_biases(random_weights(d, st.efeats.shape[1], n_nodes=N, restarter='static', nonzero_static=True, seed=3))
+    csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
+    e = gu.engine_from(W, csr, N=N, dim=d, efeats=st.efeats, nfeats=None, K=K, H=H, B=B, msg_src='left',
+                       upd_src='right', restarter='static', lazy_restart=True)
+    cols = lambda ib: tuple(a[start + ib * B:start + (ib + 1) * B] for a in (st.src, st.dst, neg, st.ts, st.eids))
+    # eager reference run
+    ref = []
+    e.reset()
+    for ib in range(n_batches):
+        e.set_batch(*cols(ib))
+        e.step()
+        ref.append(e.out_buf.clone())
+    final_ref = [t.clone() for t in (e.left_vals, e.right_vals, e.msg_vals, e.left_ts, e.right_ts, e.has_msg)]
+    e.check_errors()
+    runner = StreamRunner(e)
+    e.set_batch(*cols(0))
+    runner.capture(warmup=1)
+    # host path, n_slots deep
+    e.reset()
+    pending, got = [], []
+    for ib in range(n_batches):
+        pending.append(runner.submit_host(*cols(ib)))
+        if len(pending) >= runner.n_slots:
+            ps, ns, loss = runner.wait(pending.pop(0))
+            got.append(torch.cat([ps, ns, loss.reshape(1)]).clone())
+    while pending:
+        ps, ns, loss = runner.wait(pending.pop(0))
+        got.append(torch.cat([ps, ns, loss.reshape(1)]).clone())
+    torch.cuda.synchronize()
+    e.check_errors()
+    for ib in range(n_batches):
+        assert torch.equal(got[ib], ref[ib].cpu()), f'host path batch {ib}'
+    for a, b in zip(final_ref, (e.left_vals, e.right_vals, e.msg_vals, e.left_ts, e.right_ts, e.has_msg)):
+        assert torch.equal(a, b)
+    # device-resident path
+    e.reset()
+    dev_batches = []
+    for ib in range(n_batches):
+        h = torch.empty(5 * B, dtype=torch.int64)
+        runner.fill_host(0, *cols(ib))
+        dev_batches.append(runner.h_in[0].clone().cuda())
+    outs = []
+    for ib in range(n_batches):
+        slot = runner.submit_device(dev_batches[ib])
+        if ib >= n_batches - runner.n_slots:
+            outs.append((ib, slot))
+    torch.cuda.synchronize()
+    for ib, slot in outs:
+        assert torch.equal(runner.d_out[slot], ref[ib]), f'device path batch {ib}'
+    for a, b in zip(final_ref, (e.left_vals, e.right_vals, e.msg_vals, e.left_ts, e.right_ts, e.has_msg)):
+        assert torch.equal(a, b)

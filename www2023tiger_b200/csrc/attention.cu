@@ -415,10 +415,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 5) attn_score_pool_kernel(const A
 #define SP_MARK() do { } while (0)
 #endif
   SP_MARK();
+  // Everything up to the scores reads what kernels BEFORE the Wqk product wrote (finder tables, GRU rows,
+  // memories) - the Wqk product (graph path) releases its dependents only after its own dependency wait, so
+  // those writes are complete when this CTA starts, and the gathers / time codes below overlap that product.
+  // The dense path's Wqk product triggers at its start: there the wait comes first.
   pdl_trigger();
-  pdl_wait();      // qkf comes from the Wqk product
+  if (a.dense) pdl_wait();
   const float* qkf = a.w.qkf + q * a.dm.ld_qkf;
-  for (int i = tid; i < H * Cq; i += ATT_THREADS) qk[i] = qkf[i];
   if (tid < K) {
     const int64_t o = q * K + tid;
     const float* rp = nullptr;
@@ -582,6 +585,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 5) attn_score_pool_kernel(const A
     }
   }
   SP_MARK();   // gathers + time code
+  if (!a.dense) pdl_wait();      // qkf comes from the Wqk product
+  for (int i = tid; i < H * Cq; i += ATT_THREADS) qk[i] = qkf[i];
   SP_MARK();
   __syncthreads();
   SP_MARK();   // time code

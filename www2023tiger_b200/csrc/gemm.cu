@@ -79,6 +79,7 @@ struct GemmArgs {
   // cluster_reduce: the k_parts CTAs of a tile form a thread-block cluster; partial tiles are exchanged through
   // distributed shared memory, summed in part order (deterministic), biased / activated and written once
   int cluster_reduce;
+  int late_trigger;      // programmatic-launch trigger only after this kernel's own dependency wait
   int a_parts, a_relu;
   int64_t a_part_stride;
   const float* a_bias;
@@ -365,12 +366,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
   uint64_t* done = empty + TS_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-  pdl_trigger();
+  // late_trigger: the kernel behind this one reads, before its own wait, data written upstream of this kernel; it
+  // may therefore only be scheduled once this kernel's producers have passed THEIR wait (see below)
+  if (!g.late_trigger) pdl_trigger();
   // With a host-side row count the set-up and the weight stream (parameters: nothing the previous kernel
   // writes) run ahead of the previous kernel's completion; only the producers wait, before their first
   // activation load.  A device-side count is itself produced upstream: everybody waits first.
   const bool early = g.count == nullptr;
-  if (!early) pdl_wait();
+  if (!early) {
+    pdl_wait();
+    if (g.late_trigger) pdl_trigger();
+  }
   int64_t M = g.M;
   if (g.count != nullptr) {
     const int64_t c = (int64_t)(*g.count) * g.rows_per_count;
@@ -417,7 +423,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
     const int row = q * 32 + lane;
     int64_t m = m0 + row;
     m = m < M ? m : M - 1;                 // rows beyond the edge only feed accumulator rows nobody stores
-    if (early) pdl_wait();
+    if (early) {
+      pdl_wait();
+      if (g.late_trigger) pdl_trigger();
+    }
     const float* rowp = A + m * g.lda;
     const float* addp = nullptr;
     if (g.a_ids != nullptr) {
@@ -755,6 +764,7 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   g.k_parts = (k_blocks + ((k_blocks + g.k_parts - 1) / g.k_parts) - 1) / ((k_blocks + g.k_parts - 1) / g.k_parts);
   g.c_part_stride = cluster_reduce ? 0 : c_part_stride;
   g.cluster_reduce = (cluster_reduce && g.k_parts > 1) ? 1 : 0;
+  g.late_trigger = gather != nullptr ? 1 : 0;
   g.a_parts = a_parts; g.a_part_stride = a_part_stride; g.a_bias = a_bias; g.a_relu = a_relu;
   g.a_ids = nullptr; g.a_sel = nullptr; g.a_sel_i64 = 0; g.a_alt = nullptr; g.a_add = nullptr;
   if (gather != nullptr) {
