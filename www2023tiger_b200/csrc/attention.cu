@@ -67,11 +67,11 @@ extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const fl
 #define ATT_THREADS 256
 #endif
 #define ATT_BN_QK 64   // column tile of the Wqk pack: H (C+1) ~ 1000 columns -> ~17 tiles per 128 queries
-#define ATT_BN_D 32    // column tile of the W2f / W2 packs: d columns -> ~6 tiles per 128 queries
+#define ATT_BN_D 64    // column tile of the W2f pack: d columns -> 3 tiles per 128 queries
 #ifndef ATT_BN_F3
 #define ATT_BN_F3 32   // column tile of the last product (fc2, with the scorer fold 3d columns)
 #endif
-#define ATT_KPARTS 4   // split-K of the W2f product (K = H C + d + 1 ~ 1200, only ~30 output tiles): the parts of a
+#define ATT_KPARTS 8   // split-K of the W2f product (K = H C + d + 1 ~ 1200, only ~15 output tiles): the parts of a
                        // tile run as one thread-block cluster and sum their partial tiles through DSMEM
 
 static inline int ru4(int x) { return (x + 3) & ~3; }
