@@ -418,3 +418,56 @@ def test_sgemm_nt_packed_splitk_fused_matches_torch(gu, m, n, k, parts):
         out2 = torch.full((m, n), float('nan'), device='cuda')
         ops.sgemm_nt_packed_splitk_fused(gu.dev(a), pack, gu.dev(b), out2, parts, relu=relu)
         assert torch.equal(out, out2)       # part order is fixed: bit-identical from run to run
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('d', [172, 100, 37])
+def test_large_row_sets_take_the_bulk_copy_path(gu, d):
+    """>= 64 k rows: gather / scatter / write-backs move rows with one bulk copy per row through shared memory
+    (16-byte aligned rows; d = 37 falls back to the register path) - same results as torch indexing."""
+    g = torch.Generator().manual_seed(d)
+    N, n = 90000, 70001
+    table = torch.randn(N, d, generator=g).cuda()
+    ts_table = torch.rand(N, generator=g).cuda()
+    ids = torch.randperm(N, generator=g)[:n].cuda()
+    out, out_ts = ops.gather_rows(table, ids, ts_table)
+    assert torch.equal(out, table[ids]) and torch.equal(out_ts, ts_table[ids])
+    # scatter (unique ids: a permutation prefix)
+    vals = torch.randn(n, d, generator=g).cuda()
+    ts = (torch.rand(n, generator=g) + 2).cuda()
+    t2, tt2 = table.clone(), ts_table.clone()
+    active = torch.zeros(N, dtype=torch.uint8, device='cuda')
+    ops.scatter_rows(t2, ids, vals, ts_table=tt2, ts=ts, active=active)
+    ref = table.clone(); ref[ids] = vals
+    reft = ts_table.clone(); reft[ids] = ts
+    assert torch.equal(t2, ref) and torch.equal(tt2, reft) and int(active.sum()) == n
+    # left write-back: positions [src ; dst] of a batch, winners only
+    B = n // 2
+    pos = ids[:2 * B].contiguous()
+    winner = (torch.rand(2 * B, generator=g) < 0.7).to(torch.uint8).cuda()
+    h_left = torch.randn(2 * B, d, generator=g).cuda()
+    bts = (torch.rand(B, generator=g) + 5).cuda()
+    lv, lt = table.clone(), ts_table.clone()
+    la = torch.zeros(N, dtype=torch.uint8, device='cuda')
+    ops.left_writeback(pos, B, winner, h_left, d, bts, lv, lt, la)
+    w = winner.bool()
+    ref = table.clone(); ref[pos[w]] = h_left[w]
+    reft = ts_table.clone(); reft[pos[w]] = bts.repeat(2)[w]
+    assert torch.equal(lv, ref) and torch.equal(lt, reft) and torch.equal(la.bool(), torch.zeros(N, dtype=torch.bool, device='cuda').index_fill_(0, pos[w], True))
+    # right write-back: winners with a pending message take their GRU row
+    has_msg = (torch.rand(N, generator=g) < 0.8).to(torch.uint8).cuda()
+    gru_row = torch.full((N,), -1, dtype=torch.int32, device='cuda')
+    pend_nodes = torch.nonzero(has_msg).flatten()
+    gru_row[pend_nodes] = torch.arange(pend_nodes.numel(), dtype=torch.int32, device='cuda')
+    h_new = torch.randn(pend_nodes.numel(), d, generator=g).cuda()
+    msg_ts = (ts_table + 1).contiguous()
+    rv, rt = table.clone(), ts_table.clone()
+    ra = torch.zeros(N, dtype=torch.uint8, device='cuda')
+    hm = has_msg.clone()
+    ops.right_writeback(pos, winner, gru_row, h_new, d, rv, rt, ra, msg_ts, hm)
+    sel = w & has_msg[pos].bool()
+    nodes = pos[sel]
+    ref = table.clone(); ref[nodes] = h_new[gru_row[nodes].long()]
+    reft = ts_table.clone(); reft[nodes] = msg_ts[nodes]
+    refm = has_msg.clone(); refm[nodes] = 0
+    assert torch.equal(rv, ref) and torch.equal(rt, reft) and torch.equal(hm, refm)

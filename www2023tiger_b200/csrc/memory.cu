@@ -3,6 +3,7 @@
 // Reference: tiger/model/memory.py:12-138, tiger/model/time_encoding.py,
 // tiger/model/tiger.py:230-255,396-442.
 #include "common.cuh"
+#include "umma.cuh"
 
 #define ROW_WARPS 8  // warps (rows) per CTA for the row kernels
 
@@ -28,10 +29,56 @@ __device__ __forceinline__ int64_t effective_count(const int32_t* count, int64_t
   return c < n ? c : n;
 }
 
+// Large row sets (>= 64 k rows): the rows move through shared memory with the bulk-copy engine instead of through
+// registers.  Lane l of a warp owns row l of a batch of 32: after the (lane-parallel) index chain every lane issues
+// ONE bulk load of its whole row (cp.async.bulk, completion on the warp's mbarrier) - 32 rows = 22 KB per warp and
+// 176 KB per SM are in flight at once, far more than the register path can hold - and, once the barrier fires, one
+// bulk store of the row to its destination.  No thread touches the payload.  Needs 16-byte aligned rows.
+#define ROWS_TMA_MIN (1 << 16)
+__device__ __forceinline__ void warp_tma_move_rows(float* my_dst, const float* my_src, uint32_t row_bytes,
+                                                   unsigned char* smem_base, int lane) {
+  // layout per warp: [32 rows][row_bytes] then one mbarrier (row_bytes is a multiple of 16)
+  const int warp = warp_id_in_block();
+  unsigned char* rows = smem_base + (size_t)warp * (32u * row_bytes + 16u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(rows + 32u * row_bytes);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const bool active = my_dst != nullptr;
+  const unsigned n_act = __popc(__ballot_sync(TIGER_FULL_MASK, active));
+  if (n_act == 0) return;
+  if (lane == 0) mbar_arrive_expect_tx(bar, n_act * row_bytes);
+  __syncwarp();
+  unsigned char* mine = rows + (size_t)lane * row_bytes;
+  if (active) tma_bulk_load(mine, my_src, row_bytes, bar);
+  mbar_wait(bar, 0);
+  if (active) {
+    tma_bulk_store(my_dst, mine, row_bytes);
+    tma_store_commit();
+    tma_store_wait_read();      // shared memory is released when the CTA exits
+  }
+}
+
+static inline size_t rows_tma_smem(int64_t width) { return (size_t)ROW_WARPS * (32u * (size_t)width * 4u + 16u); }
+
+// the bulk path applies to a launch when there are many rows, the rows are 16-byte multiples, every base pointer is
+// 16-byte aligned and a CTA's staging area fits the shared memory of an SM
+template <typename Kernel>
+static inline bool rows_tma_ok(Kernel kernel, int64_t n_rows, int64_t width, const void* a, const void* b) {
+  if (n_rows < ROWS_TMA_MIN || width <= 0 || (width & 3) != 0 || ((((uintptr_t)a) | ((uintptr_t)b)) & 15) != 0) return false;
+  const size_t smem = rows_tma_smem(width);
+  if (smem > 200 * 1024) return false;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+}
+
 // ---------------------------------------------------------------- a11 Memory.get
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 gather_rows_kernel(const float* __restrict__ table, int64_t width, const int64_t* __restrict__ ids, int64_t n,
-                   float* __restrict__ out, const float* __restrict__ ts_table, float* __restrict__ out_ts, int rpw) {
+                   float* __restrict__ out, const float* __restrict__ ts_table, float* __restrict__ out_ts, int rpw,
+                   int tma) {
+  extern __shared__ __align__(128) unsigned char row_smem[];
   const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   if (r0 >= n) return;
   const int lane = lane_id();
@@ -44,7 +91,10 @@ gather_rows_kernel(const float* __restrict__ table, int64_t width, const int64_t
     src = table + u * width;
     if (out_ts != nullptr) out_ts[r] = ts_table[u];
   }
-  warp_copy_lane_rows(dst, src, rpw, (int)width, lane);
+  if (tma)
+    warp_tma_move_rows(dst, src, (uint32_t)width * 4u, row_smem, lane);
+  else
+    warp_copy_lane_rows(dst, src, rpw, (int)width, lane);
 }
 
 extern "C" int tiger_gather_rows(const float* table, int64_t width, const int64_t* ids, int64_t n, float* out,
@@ -52,8 +102,11 @@ extern "C" int tiger_gather_rows(const float* table, int64_t width, const int64_
   if (n < 0 || width < 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
   const int rpw = rows_per_warp(n);
-  gather_rows_kernel<<<row_grid(n, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      table, width, ids, n, out, ts_table, out_ts, rpw);
+  // measured (bench.py --micro, 262,144 rows): the register path is the faster one for the gather direction (0.80 vs
+  // 0.785 of the copy peak), the bulk path for the scatter direction (0.69 vs 0.66)
+  const bool tma = false;
+  gather_rows_kernel<<<row_grid(n, rpw), ROW_WARPS * 32, tma ? rows_tma_smem(width) : 0, as_stream(stream)>>>(
+      table, width, ids, n, out, ts_table, out_ts, rpw, tma ? 1 : 0);
   return tiger_launch_status();
 }
 
@@ -62,7 +115,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 scatter_rows_kernel(float* __restrict__ table, int64_t width, const int64_t* __restrict__ ids, int64_t n,
                     const int32_t* __restrict__ count, const float* __restrict__ vals,
                     float* __restrict__ ts_table, const float* __restrict__ ts, uint8_t* __restrict__ active,
-                    int check, uint32_t* __restrict__ err_flags, int rpw) {
+                    int check, uint32_t* __restrict__ err_flags, int rpw, int tma) {
+  extern __shared__ __align__(128) unsigned char row_smem[];
   const int64_t r0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   const int64_t n_eff = effective_count(count, n);
   if (r0 >= n_eff) return;
@@ -80,7 +134,10 @@ scatter_rows_kernel(float* __restrict__ table, int64_t width, const int64_t* __r
     if (table != nullptr) dst = table + u * width;
     src = vals + r * width;
   }
-  warp_copy_lane_rows(dst, src, rpw, (int)width, lane);
+  if (tma)
+    warp_tma_move_rows(dst, src, (uint32_t)width * 4u, row_smem, lane);
+  else
+    warp_copy_lane_rows(dst, src, rpw, (int)width, lane);
 }
 
 extern "C" int tiger_scatter_rows(float* table, int64_t width, const int64_t* ids, int64_t n,
@@ -89,8 +146,9 @@ extern "C" int tiger_scatter_rows(float* table, int64_t width, const int64_t* id
   if (n < 0 || width < 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
   const int rpw = rows_per_warp(n);
-  scatter_rows_kernel<<<row_grid(n, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      table, width, ids, n, count, vals, ts_table, ts, active, check, err_flags, rpw);
+  const bool tma = table != nullptr && rows_tma_ok(scatter_rows_kernel, n, width, table, vals);
+  scatter_rows_kernel<<<row_grid(n, rpw), ROW_WARPS * 32, tma ? rows_tma_smem(width) : 0, as_stream(stream)>>>(
+      table, width, ids, n, count, vals, ts_table, ts, active, check, err_flags, rpw, tma ? 1 : 0);
   return tiger_launch_status();
 }
 
@@ -257,7 +315,8 @@ right_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, const
                        const int32_t* __restrict__ gru_row, const float* __restrict__ h_new, int d,
                        float* __restrict__ right_vals, float* __restrict__ right_ts,
                        uint8_t* __restrict__ right_active, const float* __restrict__ msg_ts,
-                       uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags, int rpw) {
+                       uint8_t* __restrict__ has_msg, uint32_t* __restrict__ err_flags, int rpw, int tma) {
+  extern __shared__ __align__(128) unsigned char row_smem[];
   const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   if (p0 >= n_pos) return;
   const int lane = lane_id();
@@ -280,7 +339,10 @@ right_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, const
       src = h_new + (int64_t)r * d;
     }
   }
-  warp_copy_lane_rows(dst, src, rpw, d, lane);
+  if (tma)
+    warp_tma_move_rows(dst, src, (uint32_t)d * 4u, row_smem, lane);
+  else
+    warp_copy_lane_rows(dst, src, rpw, d, lane);
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
@@ -314,8 +376,10 @@ extern "C" int tiger_right_writeback(const int64_t* pos_ids, int64_t n_pos, cons
   if ((hprev_left == nullptr) != (hprev_right == nullptr)) return TIGER_EINVAL;
   if (n_pos == 0) return TIGER_OK;
   const int rpw = rows_per_warp(n_pos);
-  right_writeback_kernel<<<row_grid(n_pos, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      pos_ids, n_pos, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg, err_flags, rpw);
+  const bool tma = rows_tma_ok(right_writeback_kernel, n_pos, d, right_vals, h_new);
+  right_writeback_kernel<<<row_grid(n_pos, rpw), ROW_WARPS * 32, tma ? rows_tma_smem(d) : 0, as_stream(stream)>>>(
+      pos_ids, n_pos, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg, err_flags, rpw,
+      tma ? 1 : 0);
   if (hprev_left != nullptr)
     hprev_copy_kernel<<<row_grid(2 * n_pos), ROW_WARPS * 32, 0, as_stream(stream)>>>(pos_ids, n_pos, d, left_vals,
                                                                                     right_vals, hprev_left, hprev_right);
@@ -327,7 +391,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4)
 left_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, int64_t batch,
                       const uint8_t* __restrict__ winner, const float* __restrict__ h_left, int d,
                       const float* __restrict__ ts, float* __restrict__ left_vals, float* __restrict__ left_ts,
-                      uint8_t* __restrict__ left_active, uint32_t* __restrict__ err_flags, int rpw) {
+                      uint8_t* __restrict__ left_active, uint32_t* __restrict__ err_flags, int rpw, int tma) {
+  extern __shared__ __align__(128) unsigned char row_smem[];
   const int64_t p0 = ((int64_t)blockIdx.x * ROW_WARPS + warp_id_in_block()) * rpw;
   if (p0 >= n_pos) return;
   const int lane = lane_id();
@@ -343,7 +408,10 @@ left_writeback_kernel(const int64_t* __restrict__ pos_ids, int64_t n_pos, int64_
     dst = left_vals + u * (int64_t)d;
     src = h_left + p * d;
   }
-  warp_copy_lane_rows(dst, src, rpw, d, lane);
+  if (tma)
+    warp_tma_move_rows(dst, src, (uint32_t)d * 4u, row_smem, lane);
+  else
+    warp_copy_lane_rows(dst, src, rpw, d, lane);
 }
 
 extern "C" int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64_t batch, const uint8_t* winner,
@@ -352,8 +420,9 @@ extern "C" int tiger_left_writeback(const int64_t* pos_ids, int64_t n_pos, int64
   if (n_pos < 0 || d <= 0 || batch <= 0) return TIGER_EINVAL;
   if (n_pos == 0) return TIGER_OK;
   const int rpw = rows_per_warp(n_pos);
-  left_writeback_kernel<<<row_grid(n_pos, rpw), ROW_WARPS * 32, 0, as_stream(stream)>>>(
-      pos_ids, n_pos, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags, rpw);
+  const bool tma = rows_tma_ok(left_writeback_kernel, n_pos, d, left_vals, h_left);
+  left_writeback_kernel<<<row_grid(n_pos, rpw), ROW_WARPS * 32, tma ? rows_tma_smem(d) : 0, as_stream(stream)>>>(
+      pos_ids, n_pos, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags, rpw, tma ? 1 : 0);
   return tiger_launch_status();
 }
 

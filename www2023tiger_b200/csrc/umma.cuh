@@ -76,6 +76,14 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_s
                "l"(gmem_src), "r"(bytes), "r"(smem_addr_u32(bar))
                : "memory");
 }
+// bulk store shared -> global (bulk-group completion); the source must stay valid until tma_store_wait_read
+__device__ __forceinline__ void tma_bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_addr_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait_probed(bool probed_ok, uint64_t* bar, uint32_t parity) {
   if (!probed_ok) mbar_wait(bar, parity);
 }
