@@ -422,6 +422,22 @@ int tiger_seq_attn_pool(const float* qk, int64_t ld_qk, const float* x, const ui
                         const int32_t* count, int64_t n, int len, int d_model, int n_head, float* xbar,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-side batch pipeline (csrc/pipe.cu; no device code).  Replaces the synchronous per-batch `.to(device)` /
+ * `.item()` traffic of the reference's loop (train_self_supervised.py:140-175): per staging slot a captured
+ * finder graph and a captured model graph; tiger_pipe_submit uploads the batch and replays the finder on a
+ * copy-in stream (beside the previous batch's model kernels), replays the model graph on main_stream (batch
+ * order = call order) and downloads the results on a copy-out stream.  Capture: tiger_pipe_capture_begin(stream),
+ * launch the kernels on that stream, tiger_pipe_capture_end(pipe, stream, slot, kind) with kind 0 = finder,
+ * 1 = model.  src may be pinned host or device memory. */
+void* tiger_pipe_create(int n_slots);
+void tiger_pipe_destroy(void* pipe);
+int tiger_pipe_capture_begin(void* stream);
+int tiger_pipe_capture_end(void* pipe, void* stream, int slot, int kind);
+int tiger_pipe_submit(void* pipe, int slot, const void* src, void* d_in, int64_t in_bytes, const void* d_out, void* h_out,
+                      int64_t out_bytes, void* main_stream);
+int tiger_pipe_wait(void* pipe, int slot, int host_results);
+
 #ifdef __cplusplus
 }
 #endif

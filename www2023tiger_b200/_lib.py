@@ -51,6 +51,10 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_sgemm_nt_packed_sum': 'plli' + 'pi' + 'pi' + 'p' + 'pli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_sgemm_nt_packed_gather': 'ppi' + 'pplp' + 'pi' + 'ppl' + 'lpl' + 'iifi' + 'p',
     'tiger_sgemm_nt_packed_splitk_fused': 'plpi' + 'ppl' + 'i' + 'lpl' + 'iifi' + 'p',
+    'tiger_pipe_capture_begin': 'p',
+    'tiger_pipe_capture_end': 'ppii',
+    'tiger_pipe_submit': 'pipplpplp',
+    'tiger_pipe_wait': 'pii',
     'tiger_sgemm_nt_packed_split': 'plpippli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
     'tiger_min_time': 'plp' + 'p',
@@ -106,6 +110,9 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = [_KIND[c] for c in sig]
         fn.restype = L if (name.endswith('_bytes') or name.endswith('_offset')) else I
+    # the two entry points that do not return a status / size
+    lib.tiger_pipe_create.argtypes, lib.tiger_pipe_create.restype = [I], ctypes.c_void_p
+    lib.tiger_pipe_destroy.argtypes, lib.tiger_pipe_destroy.restype = [ctypes.c_void_p], None
     _lib = lib
     return lib
 

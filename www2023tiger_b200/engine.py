@@ -24,7 +24,7 @@ import numpy as np
 import torch
 from torch import Tensor
 
-from . import ops
+from . import _lib, ops
 from ._lib import raise_on_err_flags
 from .ops import f32, f64, i32, i64, u8
 
@@ -278,29 +278,39 @@ class TigerEngine:
 
 
 class StreamRunner:
-    """Replays an event stream through a TigerEngine: CUDA-graph capture of the whole batch,
-    pinned host staging for the host-buffer (e2e) path."""
+    """Replays an event stream through a TigerEngine.
+
+    `capture()` records the whole batch as one CUDA graph (`run_device`, inputs in engine.inp) and, per staging
+    slot, a finder graph and a model graph bound to the slot's own device input / result buffers and finder
+    outputs.  `submit_host` / `submit_device` hand a batch to the native pipeline (csrc/pipe.cu): upload + finder
+    on a copy-in stream beside the previous batch's model kernels, model graphs in batch order on the current
+    stream, download on a copy-out stream - seven CUDA calls per batch, issued from C."""
 
     def __init__(self, engine: TigerEngine, n_slots: int = 4):
         self.e = engine
         self.graph = None
-        self.host_graphs = None
+        self.pipe = None
         B = engine.B
         self.n_slots = n_slots
         self.h_in = [torch.empty(5 * B, dtype=i64).pin_memory() for _ in range(n_slots)]
         self.h_out = [torch.empty(2 * B + 1, dtype=f32).pin_memory() for _ in range(n_slots)]
+        self._h_in_np = [t.numpy() for t in self.h_in]
         dev = engine.inp.device
         self.d_in = [torch.zeros(5 * B, dtype=i64, device=dev) for _ in range(n_slots)]
         self.d_out = [torch.zeros(2 * B + 1, dtype=f32, device=dev) for _ in range(n_slots)]
-        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        self.ev_in = [torch.cuda.Event() for _ in range(n_slots)]
-        self.ev_done = [torch.cuda.Event() for _ in range(n_slots)]
         self.finder_bufs = [engine.finder_buffers(fresh=True) for _ in range(n_slots)]
-        self.finder_graphs = None
-        self.events = [torch.cuda.Event() for _ in range(n_slots)]
         self.slot_busy = [False] * n_slots
-        self.slot_used = [False] * n_slots
         self.slot = 0
+        self._lib = _lib.load()
+
+    def __del__(self):
+        if getattr(self, 'pipe', None):
+            self._lib.tiger_pipe_destroy(self.pipe)
+            self.pipe = None
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise _lib.TigerLibraryError(f'{what} failed with code {rc}')
 
     def capture(self, warmup: int = 2):
         """Warm up (eagerly, state restored afterwards is the caller's business) and capture."""
@@ -316,25 +326,28 @@ class StreamRunner:
         with torch.cuda.graph(self.graph):
             e.step()
         torch.cuda.synchronize()
-        # host-buffer path: one graph per staging slot, bound to that slot's device input / result buffers.  The
-        # upload of batch i+1 (copy-in stream) and the download of batch i-1 (copy-out stream) then run beside
-        # the kernels of batch i; the kernels themselves still replay strictly in batch order on one stream.
-        # The finder (a function of the static graph and the batch only) is captured separately per slot and
-        # replayed on the copy-in stream right behind the slot's upload, i.e. beside the model kernels of the
-        # previous batch; it writes the slot's own neighbor tables / bitmap, which that slot's model graph reads.
-        self.host_graphs, self.finder_graphs = [], []
+        # Per-slot graphs for the pipeline.  The finder (a function of the static graph and the batch only) is
+        # captured separately and replayed on the copy-in stream right behind the slot's upload, i.e. beside the
+        # model kernels of the previous batch; it writes the slot's own neighbor tables / bitmap, which that
+        # slot's model graph reads.
+        if self.pipe:
+            self._lib.tiger_pipe_destroy(self.pipe)
+        self.pipe = self._lib.tiger_pipe_create(self.n_slots)
+        if not self.pipe:
+            raise _lib.TigerLibraryError('tiger_pipe_create failed')
         inp0, out0, find0 = e.inp, e.out_buf, e.finder_buffers()
-        for slot in range(self.n_slots):
-            e.bind_io(self.d_in[slot], self.d_out[slot])
-            e.bind_finder(self.finder_bufs[slot])
-            gf = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gf):
-                e.launch_finder()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                e.launch_model()
-            self.finder_graphs.append(gf)
-            self.host_graphs.append(g)
+        cap = torch.cuda.Stream()
+        with torch.cuda.stream(cap):
+            for slot in range(self.n_slots):
+                e.bind_io(self.d_in[slot], self.d_out[slot])
+                e.bind_finder(self.finder_bufs[slot])
+                for kind, launch in ((0, e.launch_finder), (1, e.launch_model)):
+                    self._check(self._lib.tiger_pipe_capture_begin(cap.cuda_stream), 'capture_begin')
+                    try:
+                        launch()
+                    finally:
+                        rc = self._lib.tiger_pipe_capture_end(self.pipe, cap.cuda_stream, slot, kind)
+                    self._check(rc, 'capture_end')
         e.bind_io(inp0, out0)
         e.bind_finder(find0)
         torch.cuda.synchronize()
@@ -346,70 +359,54 @@ class StreamRunner:
         else:
             self.e.step()
 
-    def submit_device(self, batch: Tensor):
+    def _next_slot(self) -> int:
+        slot = self.slot
+        self.slot = (slot + 1) % self.n_slots
+        return slot
+
+    def submit_device(self, batch: Tensor) -> int:
         """One step on a batch that is already resident in HBM (int64 [5B], layout of engine.inp): staged into the
         next slot's input buffer on the copy-in stream (beside the previous batch's kernels), then that slot's
-        graph.  Results stay in d_out[slot]; returns the slot."""
-        if self.host_graphs is None:
+        graphs.  Results stay in d_out[slot]; returns the slot."""
+        if not self.pipe:
             self.e.inp.copy_(batch, non_blocking=True)
             self.run_device()
             return 0
-        slot = self.slot
-        self.slot = (slot + 1) % self.n_slots
-        main = torch.cuda.current_stream()
-        with torch.cuda.stream(self.s_in):
-            if self.slot_used[slot]:
-                self.s_in.wait_event(self.ev_done[slot])      # the slot's previous batch has been consumed
-            self.d_in[slot].copy_(batch, non_blocking=True)
-            self.finder_graphs[slot].replay()
-            self.ev_in[slot].record(self.s_in)
-        main.wait_event(self.ev_in[slot])
-        self.host_graphs[slot].replay()
-        self.ev_done[slot].record(main)
-        self.slot_used[slot] = True
+        slot = self._next_slot()
+        self._check(self._lib.tiger_pipe_submit(self.pipe, slot, batch.data_ptr(), self.d_in[slot].data_ptr(),
+                                                batch.numel() * 8, None, None, 0, _lib.stream_ptr()), 'pipe_submit')
         return slot
 
     def fill_host(self, slot: int, src, dst, neg, ts, eids):
         B = self.e.B
-        h = self.h_in[slot].numpy()
+        h = self._h_in_np[slot]
         h[:B], h[B:2 * B], h[2 * B:3 * B], h[3 * B:4 * B] = src, dst, neg, eids
         h[4 * B:].view(np.float64)[:] = ts
 
     def submit_host(self, src, dst, neg, ts, eids) -> int:
-        """Host-buffer step: H2D of the batch, the graph, D2H of scores + loss.  Returns the slot whose
+        """Host-buffer step: H2D of the batch, the graphs, D2H of scores + loss.  Returns the slot whose
         results become readable after `wait(slot)`."""
-        slot = self.slot
-        self.slot = (slot + 1) % self.n_slots
+        slot = self._next_slot()
         if self.slot_busy[slot]:
-            self.events[slot].synchronize()
+            self.wait(slot)
         self.fill_host(slot, src, dst, neg, ts, eids)
-        e = self.e
-        if self.host_graphs is not None:
-            main = torch.cuda.current_stream()
-            with torch.cuda.stream(self.s_in):
-                if self.slot_used[slot]:
-                    self.s_in.wait_event(self.ev_done[slot])  # the slot's previous batch has been consumed
-                self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
-                self.finder_graphs[slot].replay()
-                self.ev_in[slot].record(self.s_in)
-            main.wait_event(self.ev_in[slot])
-            self.host_graphs[slot].replay()
-            self.ev_done[slot].record(main)
-            self.slot_used[slot] = True
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_done[slot])
-                self.h_out[slot].copy_(self.d_out[slot], non_blocking=True)
-                self.events[slot].record(self.s_out)
-        else:
+        if not self.pipe:
+            e = self.e
             e.inp.copy_(self.h_in[slot], non_blocking=True)
             self.run_device()
             self.h_out[slot].copy_(e.out_buf, non_blocking=True)
-            self.events[slot].record()
+            torch.cuda.current_stream().synchronize()
+        else:
+            self._check(self._lib.tiger_pipe_submit(self.pipe, slot, self.h_in[slot].data_ptr(),
+                                                    self.d_in[slot].data_ptr(), self.h_in[slot].numel() * 8,
+                                                    self.d_out[slot].data_ptr(), self.h_out[slot].data_ptr(),
+                                                    self.h_out[slot].numel() * 4, _lib.stream_ptr()), 'pipe_submit')
         self.slot_busy[slot] = True
         return slot
 
     def wait(self, slot: int):
-        self.events[slot].synchronize()
+        if self.pipe and self.slot_busy[slot]:
+            self._check(self._lib.tiger_pipe_wait(self.pipe, slot, 1), 'pipe_wait')
         self.slot_busy[slot] = False
         out = self.h_out[slot]
         B = self.e.B
