@@ -254,3 +254,38 @@ def test_pipelined_host_and_device_paths_match_eager_steps(gu):
         assert torch.equal(runner.d_out[slot], ref[ib]), f'device path batch {ib}'
     for a, b in zip(final_ref, (e.left_vals, e.right_vals, e.msg_vals, e.left_ts, e.right_ts, e.has_msg)):
         assert torch.equal(a, b)
+
+
+def test_first_batch_after_reset_is_bit_stable_under_graph_replay(gu):
+    """The first batch after a reset restarts EVERY involved node while the GRU has no rows: the restarter (a
+    parallel branch of the graph) is then far slower than the GRU, the worst case for the join in front of the
+    attention chain.  300 resets + replays must reproduce the eager single-stream result bit for bit."""
+    shape = StreamShape('r', 300, 40, 4000, 16, None, horizon=4000.)
+    st = make_stream(shape, seed=0)
+    B, K = 100, 10
+    neg = NegativeSampler(st.src, st.dst, seed=0).pre_sample_neg_dsts(st.n_events)
+    N, d = st.n_nodes, st.dim
+    W = perturb_biases(random_weights(d, d, n_nodes=N, restarter='static', nonzero_static=True, seed=0))
+    csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
+    e = gu.engine_from(W, csr, N=N, dim=d, efeats=st.efeats, nfeats=None, K=K, H=2, B=B, msg_src='left',
+                       upd_src='right', restarter='static', lazy_restart=True, want_targets=False)
+    cols = lambda ib: tuple(a[ib * B:(ib + 1) * B] for a in (st.src, st.dst, neg, st.ts, st.eids))
+    e.reset()
+    e.set_batch(*cols(10))
+    e.step()
+    ref_out, ref_emb, ref_right = e.out_buf.clone(), e.emb.clone(), e.right_vals.clone()
+    runner = StreamRunner(e)
+    runner.capture(warmup=1)
+    for it in range(300):
+        e.reset()
+        slot = runner.submit_host(*cols(10))
+        ps, ns, loss = runner.wait(slot)
+        got = torch.cat([ps, ns, loss.reshape(1)])
+        assert torch.equal(got, ref_out.cpu()), f'iteration {it}: scores differ'
+        assert torch.equal(e.emb, ref_emb) and torch.equal(e.right_vals, ref_right), f'iteration {it}'
+        # single whole-step graph as well
+        e.reset()
+        e.set_batch(*cols(10))
+        runner.run_device()
+        torch.cuda.synchronize()
+        assert torch.equal(e.emb, ref_emb) and torch.equal(e.out_buf, ref_out), f'iteration {it} (single graph)'

@@ -51,7 +51,13 @@ static inline int tiger_launch_chain(void (*kernel)(KP...), dim3 grid, dim3 bloc
     attr[n_attr].val.clusterDim.z = cluster.z;
     ++n_attr;
   }
-  if (tiger_pdl_enabled()) {
+  // The relaxed (programmatic) ordering is requested only while the stream is being captured into a CUDA graph: there
+  // every dependency of the launch - including event joins from other branches - is an explicit edge.  Eager
+  // launches keep plain stream order, so library calls compose with arbitrary caller code.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+  static const bool eager_pdl = getenv("TIGER_EAGER_PDL") != nullptr;   // debug aid
+  if ((capturing || eager_pdl) && tiger_pdl_enabled()) {
     attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
     ++n_attr;

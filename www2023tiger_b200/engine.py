@@ -20,6 +20,8 @@ Launch sequence of one batch (B events, K neighbors):
 """
 from typing import Dict, Optional
 
+import os
+
 import numpy as np
 import torch
 from torch import Tensor
@@ -86,6 +88,7 @@ class TigerEngine:
         self.bind_io(self.inp, self.out_buf)
         # ---- parameters ----
         self._side = torch.cuda.Stream(device=dev)
+        self._serial = int(os.environ.get('TIGER_SERIAL', '0'))   # debug aid, bit mask: branches kept on the main stream
         self._ev_fork, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
         self._ev_fork2, self._ev_side2 = torch.cuda.Event(), torch.cuda.Event()
         self._ev_fork0, self._ev_rst = torch.cuda.Event(), torch.cuda.Event()
@@ -167,6 +170,15 @@ class TigerEngine:
 
     def launch_model(self):
         d, B = self.d, self.B
+        # Branches (restarter beside the GRU, write-back / message store beside the attention chain, left write-back
+        # beside the link scorer) exist only under graph capture, where they become parallel paths of the graph
+        # with explicit edges; eager launches (tests, smoke, debugging) stay on one stream.  TIGER_SERIAL is a
+        # debug bit mask that keeps individual branches on the main stream under capture as well.
+        cur = torch.cuda.current_stream()
+        serial = self._serial if (torch.cuda.is_current_stream_capturing() or os.environ.get('TIGER_EAGER_BRANCHES') == '1') else 7
+        side0 = cur if serial & 1 else self._side
+        side1 = cur if serial & 2 else self._side
+        side2 = cur if serial & 4 else self._side
         msg_vals_mem, msg_ts_mem = self._mem(self.msg_src)
         upd_vals, _ = self._mem(self.upd_src)
         ops.compact_involved(self.bitmap, self.N, self.involved, self.counts, has_msg=self.has_msg,
@@ -180,8 +192,8 @@ class TigerEngine:
         main = torch.cuda.current_stream()
         if self.lazy_restart:
             self._ev_fork0.record(main)
-            with torch.cuda.stream(self._side):
-                self._side.wait_event(self._ev_fork0)
+            with torch.cuda.stream(side0):
+                side0.wait_event(self._ev_fork0)
                 if self.restarter == 'static':
                     ops.static_restart(self.restart_nodes, self.cap, self.csr, self.left_emb, self.right_emb, d,
                                        count=self.counts[2:], batch_ts=self.ts32, left_vals=self.left_vals,
@@ -199,7 +211,7 @@ class TigerEngine:
                                      active=self.left_active, count=R)
                     ops.scatter_rows(self.right_vals, self.restart_nodes, hr, ts_table=self.right_ts, ts=pt,
                                      active=self.right_active, count=R)
-                self._ev_rst.record(self._side)
+                self._ev_rst.record(side0)
         ops.gru_update(self.gru_pack, node_ids=self.outdated, x_table=self.msg_vals, h_table=upd_vals,
                        n_rows=self.cap, out=self.h_new, count=self.counts[1:], msg_ts=self.msg_ts,
                        check_mem_ts=msg_ts_mem, check_equal=(self.msg_src == 'left'), err_flags=self.err_flags)
@@ -208,9 +220,11 @@ class TigerEngine:
         # (right-memory rows of nodes WITH a pending message are read from h_new, csrc/attention.cu
         # resolve_row), so it runs on a side stream next to the attention chain.  Captured in a CUDA graph
         # the two branches become parallel paths of the graph.
+        if self.lazy_restart and (serial & 2):
+            main.wait_event(self._ev_rst)
         self._ev_fork.record(main)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ev_fork)
+        with torch.cuda.stream(side1):
+            side1.wait_event(self._ev_fork)
             ops.select_latest(self.pos, self.ts32, want_unique=False, winner=self.winner, want_count=False)
             ops.right_writeback(self.pos, self.winner, self.gru_row, self.h_new, d, self.right_vals, self.right_ts,
                                 self.right_active, self.msg_ts, self.has_msg, self.left_vals, self.hprev_left,
@@ -218,7 +232,7 @@ class TigerEngine:
             ops.store_messages(self.src, self.dst, self.eids, self.ts32, self.winner, msg_vals_mem, msg_ts_mem,
                                self.nfeats, self.efeats, d, self.de, self.time_w, self.time_b, self.msg_vals,
                                self.msg_ts, self.has_msg, self.err_flags)
-            self._ev_side.record(self._side)
+            self._ev_side.record(side1)
         if self.lazy_restart:
             main.wait_event(self._ev_rst)
         ops.temporal_attention(self.attn_pack, self.H, self.batch_nids, self.ts32, self.neigh_nids, self.neigh_eids,
@@ -227,11 +241,11 @@ class TigerEngine:
         main.wait_event(self._ev_side)       # join: messages were built from the left memory of h(t'-)
         # second fork: the left write-back and the link scorer both only read the embeddings
         self._ev_fork2.record(main)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ev_fork2)
+        with torch.cuda.stream(side2):
+            side2.wait_event(self._ev_fork2)
             ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
                                self.left_active, self.err_flags)
-            self._ev_side2.record(self._side)
+            self._ev_side2.record(side2)
         ops.link_score_folded(self.score_fold, self.pq, self.src, self.dst, self.neg,
                               self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
         main.wait_event(self._ev_side2)
