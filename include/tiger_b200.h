@@ -429,7 +429,9 @@ int tiger_seq_attn_pool(const float* qk, int64_t ld_qk, const float* x, const ui
  * copy-in stream (beside the previous batch's model kernels), replays the model graph on main_stream (batch
  * order = call order) and downloads the results on a copy-out stream.  Capture: tiger_pipe_capture_begin(stream),
  * launch the kernels on that stream, tiger_pipe_capture_end(pipe, stream, slot, kind) with kind 0 = finder,
- * 1 = model.  src may be pinned host or device memory. */
+ * 1 = model, 2 = tail (optional: result-only kernels such as the link scorer, replayed on the copy-out stream in
+ * front of the download, beside the next batch's model kernels).  src may be pinned host or device memory.
+ * tiger_pipe_join makes a stream wait for the copy-out stream's work of the latest submit. */
 void* tiger_pipe_create(int n_slots);
 void tiger_pipe_destroy(void* pipe);
 int tiger_pipe_capture_begin(void* stream);
@@ -437,6 +439,7 @@ int tiger_pipe_capture_end(void* pipe, void* stream, int slot, int kind);
 int tiger_pipe_submit(void* pipe, int slot, const void* src, void* d_in, int64_t in_bytes, const void* d_out, void* h_out,
                       int64_t out_bytes, void* main_stream);
 int tiger_pipe_wait(void* pipe, int slot, int host_results);
+int tiger_pipe_join(void* pipe, void* stream);
 
 #ifdef __cplusplus
 }

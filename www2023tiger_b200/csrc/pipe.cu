@@ -11,9 +11,10 @@
 struct TigerPipe {
   int n_slots;
   cudaStream_t s_in, s_out;
-  std::vector<cudaGraphExec_t> finder, model;
+  std::vector<cudaGraphExec_t> finder, model, tail;
   std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
-  std::vector<char> used;
+  std::vector<char> used, has_out;
+  int last_slot;
 };
 
 extern "C" void* tiger_pipe_create(int n_slots) {
@@ -27,6 +28,9 @@ extern "C" void* tiger_pipe_create(int n_slots) {
   }
   p->finder.assign(n_slots, nullptr);
   p->model.assign(n_slots, nullptr);
+  p->tail.assign(n_slots, nullptr);
+  p->has_out.assign(n_slots, 0);
+  p->last_slot = -1;
   p->ev_in.resize(n_slots);
   p->ev_done.resize(n_slots);
   p->ev_out.resize(n_slots);
@@ -45,6 +49,7 @@ extern "C" void tiger_pipe_destroy(void* pipe) {
   for (int i = 0; i < p->n_slots; ++i) {
     if (p->finder[i] != nullptr) cudaGraphExecDestroy(p->finder[i]);
     if (p->model[i] != nullptr) cudaGraphExecDestroy(p->model[i]);
+    if (p->tail[i] != nullptr) cudaGraphExecDestroy(p->tail[i]);
     cudaEventDestroy(p->ev_in[i]);
     cudaEventDestroy(p->ev_done[i]);
     cudaEventDestroy(p->ev_out[i]);
@@ -55,7 +60,9 @@ extern "C" void tiger_pipe_destroy(void* pipe) {
 }
 
 // Everything launched on `stream` (and on streams that join it through events) between begin and end becomes the
-// slot's finder (kind 0) or model (kind 1) graph.
+// slot's finder (kind 0), model (kind 1) or tail (kind 2, optional) graph.  The tail graph holds kernels that only
+// produce the batch's results and change no state (the link scorer): it is replayed on the copy-out stream in front
+// of the download, i.e. beside the next batch's model kernels.
 extern "C" int tiger_pipe_capture_begin(void* stream) {
   return cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed) == cudaSuccess ? TIGER_OK : TIGER_ECUDA;
 }
@@ -64,7 +71,7 @@ extern "C" int tiger_pipe_capture_end(void* pipe, void* stream, int slot, int ki
   TigerPipe* p = reinterpret_cast<TigerPipe*>(pipe);
   cudaGraph_t graph = nullptr;
   if (cudaStreamEndCapture(as_stream(stream), &graph) != cudaSuccess || graph == nullptr) return TIGER_ECUDA;
-  if (p == nullptr || slot < 0 || slot >= p->n_slots || (kind != 0 && kind != 1)) {
+  if (p == nullptr || slot < 0 || slot >= p->n_slots || kind < 0 || kind > 2) {
     cudaGraphDestroy(graph);
     return TIGER_EINVAL;
   }
@@ -72,7 +79,7 @@ extern "C" int tiger_pipe_capture_end(void* pipe, void* stream, int slot, int ki
   const cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
   if (err != cudaSuccess) return TIGER_ECUDA;
-  cudaGraphExec_t& dst = kind == 0 ? p->finder[slot] : p->model[slot];
+  cudaGraphExec_t& dst = kind == 0 ? p->finder[slot] : (kind == 1 ? p->model[slot] : p->tail[slot]);
   if (dst != nullptr) cudaGraphExecDestroy(dst);
   dst = exec;
   return TIGER_OK;
@@ -90,7 +97,10 @@ extern "C" int tiger_pipe_submit(void* pipe, int slot, const void* src, void* d_
     return TIGER_EINVAL;
   cudaStream_t main = as_stream(main_stream);
   bool ok = true;
-  if (p->used[slot]) ok = ok && cudaStreamWaitEvent(p->s_in, p->ev_done[slot], 0) == cudaSuccess;
+  // the slot's buffers are free once its previous batch has been consumed: by the model graph, or - when a tail
+  // graph / download followed - by those
+  if (p->used[slot])
+    ok = ok && cudaStreamWaitEvent(p->s_in, p->has_out[slot] ? p->ev_out[slot] : p->ev_done[slot], 0) == cudaSuccess;
   ok = ok && cudaMemcpyAsync(d_in, src, (size_t)in_bytes, cudaMemcpyDefault, p->s_in) == cudaSuccess;
   ok = ok && cudaGraphLaunch(p->finder[slot], p->s_in) == cudaSuccess;
   ok = ok && cudaEventRecord(p->ev_in[slot], p->s_in) == cudaSuccess;
@@ -98,9 +108,13 @@ extern "C" int tiger_pipe_submit(void* pipe, int slot, const void* src, void* d_
   ok = ok && cudaGraphLaunch(p->model[slot], main) == cudaSuccess;
   ok = ok && cudaEventRecord(p->ev_done[slot], main) == cudaSuccess;
   p->used[slot] = 1;
-  if (h_out != nullptr && out_bytes > 0) {
+  p->last_slot = slot;
+  const bool download = h_out != nullptr && out_bytes > 0;
+  p->has_out[slot] = (p->tail[slot] != nullptr || download) ? 1 : 0;
+  if (p->has_out[slot]) {
     ok = ok && cudaStreamWaitEvent(p->s_out, p->ev_done[slot], 0) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(h_out, d_out, (size_t)out_bytes, cudaMemcpyDefault, p->s_out) == cudaSuccess;
+    if (p->tail[slot] != nullptr) ok = ok && cudaGraphLaunch(p->tail[slot], p->s_out) == cudaSuccess;
+    if (download) ok = ok && cudaMemcpyAsync(h_out, d_out, (size_t)out_bytes, cudaMemcpyDefault, p->s_out) == cudaSuccess;
     ok = ok && cudaEventRecord(p->ev_out[slot], p->s_out) == cudaSuccess;
   }
   return ok ? TIGER_OK : TIGER_ECUDA;
@@ -110,5 +124,14 @@ extern "C" int tiger_pipe_submit(void* pipe, int slot, const void* src, void* d_
 extern "C" int tiger_pipe_wait(void* pipe, int slot, int host_results) {
   TigerPipe* p = reinterpret_cast<TigerPipe*>(pipe);
   if (p == nullptr || slot < 0 || slot >= p->n_slots) return TIGER_EINVAL;
-  return cudaEventSynchronize(host_results ? p->ev_out[slot] : p->ev_done[slot]) == cudaSuccess ? TIGER_OK : TIGER_ECUDA;
+  const bool out = host_results && p->has_out[slot];
+  return cudaEventSynchronize(out ? p->ev_out[slot] : p->ev_done[slot]) == cudaSuccess ? TIGER_OK : TIGER_ECUDA;
+}
+
+// Makes `stream` wait for everything the most recent submit put on the copy-out stream (tail graph, download).
+extern "C" int tiger_pipe_join(void* pipe, void* stream) {
+  TigerPipe* p = reinterpret_cast<TigerPipe*>(pipe);
+  if (p == nullptr) return TIGER_EINVAL;
+  if (p->last_slot < 0 || !p->has_out[p->last_slot]) return TIGER_OK;
+  return cudaStreamWaitEvent(as_stream(stream), p->ev_out[p->last_slot], 0) == cudaSuccess ? TIGER_OK : TIGER_ECUDA;
 }

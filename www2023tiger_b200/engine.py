@@ -168,7 +168,7 @@ class TigerEngine:
                         ts32_out=self.ts32, bitmap=self.bitmap,
                         out=(self.neigh_nids, self.neigh_eids, self.neigh_ts, None))
 
-    def launch_model(self):
+    def launch_model(self, with_scorer: bool = True):
         d, B = self.d, self.B
         # Branches (restarter beside the GRU, write-back / message store beside the attention chain, left write-back
         # beside the link scorer) exist only under graph capture, where they become parallel paths of the graph
@@ -239,6 +239,12 @@ class TigerEngine:
                                self.neigh_ts, rows_a=self.right_vals, rows_b=self.h_new, sel=self.gru_row,
                                nfeats=self.nfeats, efeats=self.efeats, out=self.emb)
         main.wait_event(self._ev_side)       # join: messages were built from the left memory of h(t'-)
+        if not with_scorer:
+            # pipelined replay: the link scorer (reads the embeddings' projections, changes no state) is a separate
+            # graph on the copy-out stream (launch_scorer); the state-changing left write-back ends the model graph
+            ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
+                               self.left_active, self.err_flags)
+            return
         # second fork: the left write-back and the link scorer both only read the embeddings
         self._ev_fork2.record(main)
         with torch.cuda.stream(side2):
@@ -249,6 +255,17 @@ class TigerEngine:
         ops.link_score_folded(self.score_fold, self.pq, self.src, self.dst, self.neg,
                               self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
         main.wait_event(self._ev_side2)
+
+    def launch_scorer(self):
+        ops.link_score_folded(self.score_fold, self.pq, self.src, self.dst, self.neg,
+                              self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
+
+    def bind_pq(self, pq: Tensor):
+        """The [3B, 2d] first-layer projections of the link scorer, written by the last attention product and read
+        by the scorer: one buffer per pipeline slot, because the scorer of batch i runs beside batch i+1."""
+        assert pq.shape == self.pq.shape and pq.dtype == f32
+        self.pq = pq
+        self.attn_pack.attach_score_fold(self.score_fold, pq)
 
     def bind_io(self, inp: Tensor, out_buf: Tensor):
         """Points the batch-input views ([src | dst | neg | eids | ts as f64 bits], int64 [5B]) and the result
@@ -313,6 +330,7 @@ class StreamRunner:
         self.d_in = [torch.zeros(5 * B, dtype=i64, device=dev) for _ in range(n_slots)]
         self.d_out = [torch.zeros(2 * B + 1, dtype=f32, device=dev) for _ in range(n_slots)]
         self.finder_bufs = [engine.finder_buffers(fresh=True) for _ in range(n_slots)]
+        self.pq_bufs = [torch.zeros_like(engine.pq) for _ in range(n_slots)]
         self.slot_busy = [False] * n_slots
         self.slot = 0
         self._lib = _lib.load()
@@ -349,13 +367,15 @@ class StreamRunner:
         self.pipe = self._lib.tiger_pipe_create(self.n_slots)
         if not self.pipe:
             raise _lib.TigerLibraryError('tiger_pipe_create failed')
-        inp0, out0, find0 = e.inp, e.out_buf, e.finder_buffers()
+        inp0, out0, find0, pq0 = e.inp, e.out_buf, e.finder_buffers(), e.pq
         cap = torch.cuda.Stream()
         with torch.cuda.stream(cap):
             for slot in range(self.n_slots):
                 e.bind_io(self.d_in[slot], self.d_out[slot])
                 e.bind_finder(self.finder_bufs[slot])
-                for kind, launch in ((0, e.launch_finder), (1, e.launch_model)):
+                e.bind_pq(self.pq_bufs[slot])
+                for kind, launch in ((0, e.launch_finder), (1, lambda: e.launch_model(with_scorer=False)),
+                                     (2, e.launch_scorer)):
                     self._check(self._lib.tiger_pipe_capture_begin(cap.cuda_stream), 'capture_begin')
                     try:
                         launch()
@@ -364,7 +384,13 @@ class StreamRunner:
                     self._check(rc, 'capture_end')
         e.bind_io(inp0, out0)
         e.bind_finder(find0)
+        e.bind_pq(pq0)
         torch.cuda.synchronize()
+
+    def join(self):
+        """Makes the current stream wait for the copy-out stream's work (link scorer, download) of the latest batch."""
+        if self.pipe:
+            self._check(self._lib.tiger_pipe_join(self.pipe, _lib.stream_ptr()), 'pipe_join')
 
     def run_device(self):
         """Inputs already resident in engine.inp."""
