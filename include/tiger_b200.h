@@ -217,6 +217,25 @@ int tiger_gru_update(const int64_t* node_ids, const int32_t* count, int64_t n_ro
 /* temporal-attention parameters (device pointers): the reference's tensors as stored
  * (temporal_embedding_fn.fns.0.*), plus one caller-allocated buffer for the folded weights.
  * E = 2d, C = 2d + de, hd = E / n_head. */
+/* Optional fusion of update_left_memory (tiger.py:408-420, tiger_left_writeback below) into the last product of
+ * tiger_temporal_attention: the rows p < n_pos of the result whose winner[p] != 0 are also written to
+ * left_vals[pos_ids[p]], with left_ts[...] = ts[p % batch] (error flag if the stored clock is later) and
+ * left_active[...] = 1 - the embeddings are persisted by the kernel that produces them.  ready_event (a
+ * cudaEvent_t, may be NULL) is waited for on the stream in front of that product: it must cover the producer of
+ * `winner` and every reader of the old left-memory rows (the message builder). */
+typedef struct {
+  const int64_t* pos_ids;
+  const uint8_t* winner;
+  int64_t n_pos;
+  const float* ts;
+  int64_t batch;
+  float* left_vals;       /* [N][d] */
+  float* left_ts;         /* [N] */
+  uint8_t* left_active;   /* [N] or NULL */
+  uint32_t* err_flags;    /* or NULL */
+  void* ready_event;
+} tiger_left_writeback_fused;
+
 typedef struct {
   const float* wq;       /* [E][E]    mha_fn.q_proj_weight                                  */
   const float* wk;       /* [E][C]    mha_fn.k_proj_weight                                  */
@@ -233,6 +252,7 @@ typedef struct {
   float* folded;         /* tiger_attn_fold_bytes() bytes, 16-byte aligned, filled by tiger_attn_fold */
   float* score_folded;   /* optional: tiger_score_fold blob - the last GEMM then also emits the scorer terms  */
   float* pq_out;         /* optional per-call output [n_query][2d]: P = W1a z | Q = W1b z (with score_folded) */
+  const tiger_left_writeback_fused* left_wb;   /* optional, see above (gather form only) */
 } tiger_attn_params;
 
 /* Folds the projections that are linear in the per-query vectors (exact by linearity, accumulated in
@@ -379,6 +399,12 @@ int tiger_sgemm_nt_packed_gather(const int64_t* ids, const void* sel, int sel_is
                                  int bn, const float* bias, float* C, int64_t ldc, int64_t m_rows,
                                  const int32_t* count, int64_t rows_per_count, int n_cols, int k_dim, float alpha,
                                  int relu, void* stream);
+
+/* tiger_sgemm_nt_packed / _packed_split (C2 may be NULL here) with the fused row scatter described at
+ * tiger_left_writeback_fused: result rows are additionally stored into a node-indexed table. */
+int tiger_sgemm_nt_packed_scatter(const float* A, int64_t lda, const float* wpack, int bn, const float* bias, float* C,
+                                  int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split, int n_cols1,
+                                  int64_t m_rows, int k_dim, const tiger_left_writeback_fused* wb, void* stream);
 
 /* Split-K pair for long reductions with few output tiles.  tiger_sgemm_nt_packed_splitk writes
  * tiger_gemm_splitk_parts(k_dim, k_parts) raw partial products A[:, part] Wpack[:, part]^T to

@@ -56,6 +56,7 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_pipe_submit': 'pipplpplp',
     'tiger_pipe_wait': 'pii',
     'tiger_pipe_join': 'pp',
+    'tiger_sgemm_nt_packed_scatter': 'plpippli' + 'pliil' + 'ip' + 'p',
     'tiger_sgemm_nt_packed_split': 'plpippli' + 'pliil' + 'pl' + 'ifi' + 'p',
     'tiger_link_score': 'pli' + 'pppp' + 'i' + 'ppppp' + 'ppp' + 'p',
     'tiger_min_time': 'plp' + 'p',

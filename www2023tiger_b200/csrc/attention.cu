@@ -705,7 +705,18 @@ static int attention_run(AttArgs& a, const tiger_attn_params* p, float* out, cud
   rc = tiger_sgemm_nt_packed_splitk_fused(a.w.kvc, m.ld_kvc, f.pk_w2f, ATT_BN_D, p->fc1_b, a.w.hid, m.ld_hid, kparts, n,
                                           nullptr, 1, m.d, m.off_live + 1, 1.0f, 1, s);
   if (rc != TIGER_OK) return rc;
-  if (p->score_folded != nullptr && p->pq_out != nullptr) {
+  const bool fold_scorer = p->score_folded != nullptr && p->pq_out != nullptr;
+  if (p->left_wb != nullptr && !a.dense) {
+    // last GEMM also persists the winners' embeddings into the left memory (waits for left_wb->ready_event first)
+    if (fold_scorer) {
+      const ScoreFold sf = score_fold(m.d, p->score_folded);
+      return tiger_sgemm_nt_packed_scatter(a.w.hid, m.ld_hid, sf.pack, ATT_BN_F3, sf.b3, out, m.d, m.d, p->pq_out, 2 * m.d,
+                                           sf.n_split, 2 * m.d, n, m.d, p->left_wb, s);
+    }
+    return tiger_sgemm_nt_packed_scatter(a.w.hid, m.ld_hid, f.pk_fc2, ATT_BN_F3, p->fc2_b, out, m.d, m.d, nullptr, 0, 0, 0, n,
+                                         m.d, p->left_wb, s);
+  }
+  if (fold_scorer) {
     // last GEMM with the link-scorer fold: z -> out, [W1a z | W1b z] -> pq_out
     const ScoreFold sf = score_fold(m.d, p->score_folded);
     return tiger_sgemm_nt_packed_split(a.w.hid, m.ld_hid, sf.pack, ATT_BN_F3, sf.b3, out, m.d, m.d, p->pq_out, 2 * m.d,

@@ -80,6 +80,17 @@ struct GemmArgs {
   // distributed shared memory, summed in part order (deterministic), biased / activated and written once
   int cluster_reduce;
   int late_trigger;      // programmatic-launch trigger only after this kernel's own dependency wait
+  // optional fused row scatter (tiger_left_writeback_fused): rows m < sc_rows with sc_mask[m] also go to
+  // sc_table[sc_ids[m]] (columns of the first output), with the row's clock / activity flag
+  const int64_t* sc_ids;
+  const uint8_t* sc_mask;
+  int64_t sc_rows, sc_period, sc_ld;
+  const float* sc_ts;
+  float* sc_table;
+  float* sc_ts_table;
+  uint8_t* sc_active;
+  uint32_t* sc_err;
+  int vec_sc;
   int a_parts, a_relu;
   int64_t a_part_stride;
   const float* a_bias;
@@ -495,6 +506,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
     tc_fence_after_sync();
     const int64_t mr = m0 + row;
     const bool row_ok = mr < M;
+    const bool sc_row = g.sc_table != nullptr && row_ok && mr < g.sc_rows && g.sc_mask[mr] != 0;
+    const int64_t sc_u = sc_row ? g.sc_ids[mr] : 0;
     const uint32_t tacc = taddr + ((uint32_t)(q * 32) << 16);
     for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += 16 * (TCG_PRODUCER_WARPS / 4)) {
       float o[16];
@@ -536,6 +549,25 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gemm_tf32x3_ts_kernel(const Gem
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (col + j < lim) dst[j] = o[j];
+      }
+      if (sc_row && !second) {
+        // the same values into the node's row of the table (update_left_memory fused into the producing kernel)
+        float* d3 = g.sc_table + sc_u * g.sc_ld + col;
+        if (g.vec_sc && col + 16 <= lim) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(d3 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col + j < lim) d3[j] = o[j];
+        }
+        if (nb == 0) {                         // one thread per row owns the scalar side
+          const float t = g.sc_ts[mr % g.sc_period];
+          if (g.sc_err != nullptr && g.sc_ts_table[sc_u] > t) atomicOr(g.sc_err, TIGER_ERR_PAST_MEMORY);
+          g.sc_ts_table[sc_u] = t;
+          if (g.sc_active != nullptr) g.sc_active[sc_u] = 1;
+        }
       }
     }
   } else if (warp == TCG_PRODUCER_WARPS + UMMA_ISSUERS) {
@@ -731,7 +763,7 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
                        void* stream, float* C2 = nullptr, int64_t ldc2 = 0, int n_split = 0, int n_cols1 = 0,
                        int k_parts = 1, int64_t c_part_stride = 0, int a_parts = 1, int64_t a_part_stride = 0,
                        const float* a_bias = nullptr, int a_relu = 0, const GemmGather* gather = nullptr,
-                       int cluster_reduce = 0) {
+                       int cluster_reduce = 0, const tiger_left_writeback_fused* wb = nullptr) {
   if (m_rows < 0 || batch <= 0 || n_cols <= 0 || k_dim <= 0 || lda < k_dim || ldc < n_cols) return TIGER_EINVAL;
   if (gather != nullptr && (wpack == nullptr || gather->ids == nullptr || gather->sel == nullptr ||
                             gather->alt == nullptr || a_parts > 1))
@@ -765,6 +797,17 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   g.c_part_stride = cluster_reduce ? 0 : c_part_stride;
   g.cluster_reduce = (cluster_reduce && g.k_parts > 1) ? 1 : 0;
   g.late_trigger = gather != nullptr ? 1 : 0;
+  g.sc_table = nullptr; g.sc_ids = nullptr; g.sc_mask = nullptr; g.sc_rows = 0; g.sc_period = 1; g.sc_ld = 0;
+  g.sc_ts = nullptr; g.sc_ts_table = nullptr; g.sc_active = nullptr; g.sc_err = nullptr; g.vec_sc = 0;
+  if (wb != nullptr) {
+    if (wpack == nullptr || k_parts != 1 || wb->pos_ids == nullptr || wb->winner == nullptr || wb->ts == nullptr ||
+        wb->left_vals == nullptr || wb->left_ts == nullptr || wb->n_pos < 0 || wb->n_pos > m_rows || wb->batch <= 0)
+      return TIGER_EINVAL;
+    g.sc_table = wb->left_vals; g.sc_ids = wb->pos_ids; g.sc_mask = wb->winner; g.sc_rows = wb->n_pos;
+    g.sc_period = wb->batch; g.sc_ld = ldc; g.sc_ts = wb->ts; g.sc_ts_table = wb->left_ts;
+    g.sc_active = wb->left_active; g.sc_err = wb->err_flags;
+    g.vec_sc = ((((uintptr_t)wb->left_vals) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
+  }
   g.a_parts = a_parts; g.a_part_stride = a_part_stride; g.a_bias = a_bias; g.a_relu = a_relu;
   g.a_ids = nullptr; g.a_sel = nullptr; g.a_sel_i64 = 0; g.a_alt = nullptr; g.a_add = nullptr;
   if (gather != nullptr) {
@@ -831,6 +874,19 @@ extern "C" int tiger_sgemm_nt_packed_split(const float* A, int64_t lda, const fl
   if (wpack == nullptr || C2 == nullptr) return TIGER_EINVAL;
   return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count,
                      n_cols0, k_dim, alpha, relu, nullptr, stream, C2, ldc2, n_split, n_cols1);
+}
+
+extern "C" int tiger_sgemm_nt_packed_scatter(const float* A, int64_t lda, const float* wpack, int bn, const float* bias,
+                                             float* C, int64_t ldc, int n_cols0, float* C2, int64_t ldc2, int n_split,
+                                             int n_cols1, int64_t m_rows, int k_dim, const tiger_left_writeback_fused* wb,
+                                             void* stream) {
+  if (wpack == nullptr || wb == nullptr) return TIGER_EINVAL;
+  if (wb->ready_event != nullptr &&
+      cudaStreamWaitEvent(as_stream(stream), reinterpret_cast<cudaEvent_t>(wb->ready_event), 0) != cudaSuccess)
+    return TIGER_ECUDA;
+  return gemm_launch(A, lda, 0, nullptr, 0, 0, wpack, 0, bn, bias, 0, C, ldc, 0, 1, m_rows, nullptr, 1, n_cols0, k_dim, 1.0f,
+                     0, nullptr, stream, C2, ldc2, C2 != nullptr ? n_split : 0, C2 != nullptr ? n_cols1 : 0, 1, 0, 1, 0,
+                     nullptr, 0, nullptr, 0, wb);
 }
 
 // number of partial products tiger_sgemm_nt_packed_splitk will actually write for this K (<= k_parts)

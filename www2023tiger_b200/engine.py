@@ -32,7 +32,7 @@ from .ops import f32, f64, i32, i64, u8
 
 KERNELS_PER_STEP = {  # launches of our kernels per batch (for the bench `gpu_launches` field)
     'find_recent': 1, 'compact_involved': 1, 'gru_update': 1, 'temporal_attention': 4, 'select_latest': 1,
-    'right_writeback': 1, 'store_messages': 2, 'left_writeback': 1, 'link_score': 1,
+    'right_writeback': 1, 'store_messages': 2, 'left_writeback': 0, 'link_score': 1,
 }
 
 
@@ -235,26 +235,17 @@ class TigerEngine:
             self._ev_side.record(side1)
         if self.lazy_restart:
             main.wait_event(self._ev_rst)
+        # update_left_memory is fused into the last attention product, which first waits for the side branch (the
+        # message builder reads the OLD left-memory rows, and `winner` comes from the selection kernel)
+        self.attn_pack.attach_left_writeback(self.pos, self.winner, self.ts32, self.left_vals, self.left_ts,
+                                             self.left_active, self.err_flags, ready_event=self._ev_side)
         ops.temporal_attention(self.attn_pack, self.H, self.batch_nids, self.ts32, self.neigh_nids, self.neigh_eids,
                                self.neigh_ts, rows_a=self.right_vals, rows_b=self.h_new, sel=self.gru_row,
                                nfeats=self.nfeats, efeats=self.efeats, out=self.emb)
-        main.wait_event(self._ev_side)       # join: messages were built from the left memory of h(t'-)
-        if not with_scorer:
-            # pipelined replay: the link scorer (reads the embeddings' projections, changes no state) is a separate
-            # graph on the copy-out stream (launch_scorer); the state-changing left write-back ends the model graph
-            ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
-                               self.left_active, self.err_flags)
-            return
-        # second fork: the left write-back and the link scorer both only read the embeddings
-        self._ev_fork2.record(main)
-        with torch.cuda.stream(side2):
-            side2.wait_event(self._ev_fork2)
-            ops.left_writeback(self.pos, B, self.winner, self.emb, d, self.ts32, self.left_vals, self.left_ts,
-                               self.left_active, self.err_flags)
-            self._ev_side2.record(side2)
-        ops.link_score_folded(self.score_fold, self.pq, self.src, self.dst, self.neg,
-                              self.neigh_nids if self.hit_type == 'bin' else None, self.scores, self.loss)
-        main.wait_event(self._ev_side2)
+        # the link scorer reads the projections `pq` of the embeddings and changes no state: in the pipelined replay
+        # it is a separate graph on the copy-out stream (launch_scorer), beside the next batch's model kernels
+        if with_scorer:
+            self.launch_scorer()
 
     def launch_scorer(self):
         ops.link_score_folded(self.score_fold, self.pq, self.src, self.dst, self.neg,

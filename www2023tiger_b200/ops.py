@@ -250,7 +250,15 @@ def gru_update(pack: GruPack, *, node_ids: Optional[Tensor], x_table: Tensor, h_
 class AttnParamsC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ('wq', 'wk', 'wv', 'wo', 'fc1', 'fc2', 'in_bias', 'out_bias', 'fc1_b', 'fc2_b', 'time_w', 'time_b',
-                 'folded', 'score_folded', 'pq_out')]
+                 'folded', 'score_folded', 'pq_out', 'left_wb')]
+
+
+class LeftWritebackFusedC(ctypes.Structure):
+    """tiger_left_writeback_fused (include/tiger_b200.h)."""
+    _fields_ = [('pos_ids', ctypes.c_void_p), ('winner', ctypes.c_void_p), ('n_pos', ctypes.c_int64),
+                ('ts', ctypes.c_void_p), ('batch', ctypes.c_int64), ('left_vals', ctypes.c_void_p),
+                ('left_ts', ctypes.c_void_p), ('left_active', ctypes.c_void_p), ('err_flags', ctypes.c_void_p),
+                ('ready_event', ctypes.c_void_p)]
 
 
 class AttnPack:
@@ -290,6 +298,28 @@ class AttnPack:
         self._score_fold, self._pq_out = fold, pq_out
         self.struct.score_folded = fold.blob.data_ptr() if fold is not None else None
         self.struct.pq_out = pq_out.data_ptr() if pq_out is not None else None
+
+    def attach_left_writeback(self, pos_ids: Optional[Tensor], winner: Optional[Tensor] = None, ts: Optional[Tensor] = None,
+                              left_vals: Optional[Tensor] = None, left_ts: Optional[Tensor] = None,
+                              left_active: Optional[Tensor] = None, err_flags: Optional[Tensor] = None,
+                              ready_event: Optional[torch.cuda.Event] = None):
+        """update_left_memory (tiger.py:408-420) fused into the last attention product: result rows p < len(pos_ids)
+        with winner[p] are also stored into left_vals[pos_ids[p]] (+ clock, activity flag).  `ready_event` must
+        cover the producer of `winner` and the readers of the old left-memory rows.  None detaches."""
+        if pos_ids is None:
+            self._left_wb = None
+            self.struct.left_wb = None
+            return
+        check_cuda(pos_ids, winner, ts, left_vals, left_ts, left_active, err_flags)
+        w = LeftWritebackFusedC()
+        w.pos_ids, w.winner, w.n_pos = pos_ids.data_ptr(), winner.data_ptr(), pos_ids.numel()
+        w.ts, w.batch = ts.data_ptr(), ts.numel()
+        w.left_vals, w.left_ts = left_vals.data_ptr(), left_ts.data_ptr()
+        w.left_active = left_active.data_ptr() if left_active is not None else None
+        w.err_flags = err_flags.data_ptr() if err_flags is not None else None
+        w.ready_event = ready_event.cuda_event if ready_event is not None else None
+        self._left_wb = (w, pos_ids, winner, ts, left_vals, left_ts, left_active, err_flags, ready_event)
+        self.struct.left_wb = ctypes.addressof(w)
 
     def work(self, n_query: int, k: int) -> Tensor:
         key = (n_query, k)
