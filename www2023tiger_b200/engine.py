@@ -90,7 +90,6 @@ class TigerEngine:
         self._side = torch.cuda.Stream(device=dev)
         self._serial = int(os.environ.get('TIGER_SERIAL', '0'))   # debug aid, bit mask: branches kept on the main stream
         self._ev_fork, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
-        self._ev_fork2, self._ev_side2 = torch.cuda.Event(), torch.cuda.Event()
         self._ev_fork0, self._ev_rst = torch.cuda.Event(), torch.cuda.Event()
         self.gru_pack = None
         self.attn_pack = ops.AttnPack(self.d, self.de, dev, n_head)
@@ -170,15 +169,15 @@ class TigerEngine:
 
     def launch_model(self, with_scorer: bool = True):
         d, B = self.d, self.B
-        # Branches (restarter beside the GRU, write-back / message store beside the attention chain, left write-back
-        # beside the link scorer) exist only under graph capture, where they become parallel paths of the graph
-        # with explicit edges; eager launches (tests, smoke, debugging) stay on one stream.  TIGER_SERIAL is a
-        # debug bit mask that keeps individual branches on the main stream under capture as well.
+        # Branches (restarter beside the GRU, write-back / message store beside the attention chain) exist only under
+        # graph capture, where they become parallel paths of the graph with explicit edges; eager launches (tests,
+        # smoke, debugging) stay on one stream.  TIGER_SERIAL is a debug bit mask (1: restarter, 2: write-back /
+        # message branch) that keeps a branch on the main stream under capture as well; TIGER_EAGER_BRANCHES=1
+        # re-enables the branches for eager launches (tools/eager_race.py).
         cur = torch.cuda.current_stream()
         serial = self._serial if (torch.cuda.is_current_stream_capturing() or os.environ.get('TIGER_EAGER_BRANCHES') == '1') else 7
         side0 = cur if serial & 1 else self._side
         side1 = cur if serial & 2 else self._side
-        side2 = cur if serial & 4 else self._side
         msg_vals_mem, msg_ts_mem = self._mem(self.msg_src)
         upd_vals, _ = self._mem(self.upd_src)
         ops.compact_involved(self.bitmap, self.N, self.involved, self.counts, has_msg=self.has_msg,
