@@ -7,9 +7,13 @@
 One step = one batch of 200 events through the whole fused path: temporal neighbor finder ->
 involved/outdated compaction -> lazy restart -> pending-message gather + GRU -> temporal
 attention embedding -> argmax-by-timestamp selection -> right write-back -> message build +
-store -> left write-back -> link scorer + loss.  `value` is measured with the batch inputs already
-resident in HBM (CUDA-graph replay, CUDA events); `e2e` goes through pinned HOST buffers (H2D of the
-batch, the graph, D2H of scores + loss inside the timed region).
+store -> left write-back (fused into the last attention product) -> link scorer + loss.  `value` is
+measured with the batch inputs already resident in HBM (CUDA-graph replay, CUDA events); `e2e` goes
+through pinned HOST buffers (H2D of the batch, the graphs, D2H of scores + loss inside the timed region).
+Both use the batch pipeline of www2023tiger_b200/engine.py:StreamRunner (csrc/pipe.cu): the model kernels of
+consecutive batches run strictly in order on one stream (the memory is state), while the upload + neighbor
+finder of batch i+1 and the link scorer + download of batch i-1 run beside them on copy streams; every
+batch still pays its own H2D and D2H, and every result is read on the host before the clock stops.
 
 Only the `cpu_baseline` leg and `--impl reference` import oracle/ (the CPU checker); the product
 path never does.
