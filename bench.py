@@ -34,7 +34,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = 'events/sec (memory update + embedding, batch 200)'
+METRIC_TRAIN = 'events/sec (full training step: memory update + embedding + restarter + backward + Adam, batch 200)'
 UNIT = 'events/s'
+HIST_LEN = 40
 BATCH = 200
 K_NEIGH = 10
 N_HEAD = 2
@@ -46,17 +48,29 @@ def parse_args():
     p.add_argument('--steps', type=int, default=1000)
     p.add_argument('--warmup', type=int, default=20)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    p.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                   help='infer: the no-grad memory path (BASELINE metric); train: the full training step')
     p.add_argument('--workload', default='reddit', choices=['wikipedia', 'reddit', 'mooc', 'lastfm', 'scaled'])
     p.add_argument('--events', type=int, default=0, help='override the number of events of the stream')
     p.add_argument('--skip-batches', type=int, default=1000, help='batches skipped so that histories are populated')
-    p.add_argument('--cpu-batches', type=int, default=1000, help='bounded sample of the cpu_baseline leg (0 = off)')
+    p.add_argument('--cpu-batches', type=int, default=400, help='bounded sample of the cpu_baseline leg (0 = off)')
     p.add_argument('--profile-steps', type=int, default=100, help='eager steps with per-kernel CUDA events')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--micro', action='store_true',
                    help='feed each gather/scatter kernel >= 256k rows (tables >> L2) and report HBM GB/s vs peak')
     p.add_argument('--micro-rows', type=int, default=1 << 18)
     p.add_argument('--seed', type=int, default=0)
+    p.add_argument('--restarter', default='auto', choices=['auto', 'seq', 'static'],
+                   help="auto = the restarter BASELINE.json's config line names for the workload")
+    p.add_argument('--cpu-seconds', type=float, default=25.0, help='time budget of the cpu_baseline leg')
+    p.add_argument('--parity-batches', type=int, default=3,
+                   help='batches replayed after a reset and compared with the CPU arm (0 = off)')
+    p.add_argument('--cpu-kind', default='auto', choices=['auto', 'reference', 'port'])
     return p.parse_args()
+
+
+def pick_restarter(args, shape):
+    return shape.restarter if args.restarter == 'auto' else args.restarter
 
 
 def dist_env():
@@ -66,10 +80,12 @@ def dist_env():
 # ------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------
-def load_workload(args, with_efeats=True):
+def load_workload(args, with_efeats=True, cpu_only=False):
     from www2023tiger_b200.synthetic import SHAPES, NegativeSampler, make_stream
     shape = SHAPES[args.workload]
     n_events = args.events or shape.n_events
+    if cpu_only:
+        with_efeats = with_efeats and st_fits_host(args)    # scaled: CpuArm draws the rows of its event prefix
     st = make_stream(shape, seed=args.seed, n_events=n_events, with_efeats=with_efeats)
     neg = NegativeSampler(st.src, st.dst, seed=args.seed).pre_sample_neg_dsts(st.n_events, BATCH)
     return shape, st, neg
@@ -108,128 +124,222 @@ def batch_window(args, n_events, rank, world):
 
 
 class ClockSampler:
-    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-              'clocks_event_reasons.sw_power_cap')
+    """SM clock + throttle reasons sampled through NVML from a thread of this process while the timed regions
+    run (a timed region of the driver's default 20 steps lasts ~2 ms: a `nvidia-smi -lms 100` child never sees
+    it).  Samples are taken every ~0.5 ms between start() and stop()."""
 
     def __init__(self, gpu_index=0):
-        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-        self.p = None
+        import threading
+        self.samples, self.reasons_seen = [], 0
+        self.max_mhz, self.h, self.nv = None, None, None
+        self._stop = threading.Event()
+        self._t = None
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), f'--query-gpu={self.FIELDS}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                try:
+                    idx = int(vis.split(',')[gpu_index])
+                except (ValueError, IndexError):
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+        if self.h is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons_seen |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        if self.p is None:
+        out = {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': []}
+        if self._t is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(', ') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, names, reasons = [], ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], set()
-        for r in rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0]))
-                out['sm_max_mhz'] = float(r[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.strip().lower().startswith('active'):
-                    reasons.add(n)
-        if sm:
-            out['sm_mhz'] = float(np.median(sm))
-            out['samples'] = len(sm)
-        out['reasons'] = sorted(reasons)
+        self._stop.set()
+        self._t.join(timeout=2)
+        nv = self.nv
+        names = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown,
+                 'hw_thermal_slowdown': nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 'sw_power_cap': nv.nvmlClocksEventReasonSwPowerCap}
+        out['reasons'] = sorted(n for n, bit in names.items() if self.reasons_seen & bit)
+        if self.samples:
+            out['sm_mhz'] = float(np.median(self.samples))
+            out['samples'] = len(self.samples)
         return out
 
 
 # ------------------------------------------------------------------------------------------
-# CPU leg: the oracle restatement of the reference path on the host cores
+# CPU arm: the reference itself (oracle/_ref, vendored by tools/vendor_ref.py) on the host cores; the oracle
+# restatement (oracle/tiger_oracle.py) as the second reported number and as the fallback
 # ------------------------------------------------------------------------------------------
-def oracle_runner(args, shape, st, neg, lo):
-    """Returns step(i) running batch i (collate + lazy restart + contrast step) on the CPU."""
-    import torch
-    from oracle import tiger_oracle as O
-    from www2023tiger_b200.init import random_weights
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    N, d = st.n_nodes, st.dim
-    de = st.efeats.shape[1] if st.efeats is not None else d
-    W = random_weights(d, de, n_nodes=N, restarter='static', seed=args.seed)
-    graph = O.OracleGraph(st.src, st.dst, st.ts, st.eids, n_nodes=N)
-    model = O.OracleTIGER(W, graph, N, d, st.efeats, None, n_neighbors=K_NEIGH, n_head=N_HEAD,
-                          msg_src=shape.msg_src, upd_src=shape.upd_src, restarter='static')
-    uptodate = np.zeros(N, dtype=bool)
+class CpuArm:
+    """step(i) runs batch i of the window that starts at event `lo` (collate + lazy restart + contrast step; in
+    train mode the whole training step: + restarter targets, backward, Adam) on the CPU."""
 
-    def step(i):
-        s = slice(lo + i * BATCH, lo + (i + 1) * BATCH)
-        b = O.collate(graph, st.src[s], st.dst[s], neg[s], st.ts[s], st.eids[s], K_NEIGH)
-        rn = O.lazy_restart_nodes(b.involved, uptodate)
-        model.restart(rn, np.full(len(rn), b.ts.min(), dtype=np.float32))
+    def __init__(self, args, shape, st, neg, lo, n_batches, *, kind='auto', mode='infer', efeats_prefix=None):
+        import torch
+        self.kind, self.mode, self.lo, self.args = None, mode, lo, args
+        self.restarter = pick_restarter(args, shape)
+        self.cores = os.cpu_count() or 1
+        n_graph = min(st.n_events, lo + (n_batches + 2) * BATCH)
+        if st.efeats is None and shape.efeat_dim > 0:
+            # scaled stream: the 34 GB edge table lives on the device only; the CPU arm replays a window of an event
+            # prefix and needs the rows of that prefix (efeats_prefix: the device rows when parity is checked)
+            if efeats_prefix is None:
+                efeats_prefix = np.random.RandomState(args.seed).standard_normal(
+                    (n_graph + 1, shape.efeat_dim)).astype(np.float32)
+                efeats_prefix[0] = 0
+            import copy
+            st = copy.copy(st)
+            st.efeats = efeats_prefix
+        if kind in ('auto', 'reference'):
+            from oracle import ref_harness
+            why = ref_harness.available()
+            if why is None:
+                self.ref = ref_harness.ReferenceRunner(
+                    st, neg, restarter=self.restarter, msg_src=shape.msg_src, upd_src=shape.upd_src,
+                    n_graph_events=n_graph, n_neighbors=K_NEIGH, n_heads=N_HEAD, hist_len=HIST_LEN, batch=BATCH,
+                    seed=args.seed, threads=self.cores)
+                self.ref.reset(train=(mode == 'train'))
+                self.kind = 'reference'
+                self.what = ('the unmodified reference (oracle/_ref: GraphCollator + TIGER.restart + '
+                             + ('contrast_and_mutual_learning + backward + Adam' if mode == 'train'
+                                else 'contrast_learning') + f'), torch {torch.__version__} CPU')
+            elif kind == 'reference':
+                raise SystemExit(f'--cpu-kind reference: {why}')
+        if self.kind is None:
+            if mode == 'train':
+                raise SystemExit('the training step has no oracle port; vendor the reference (tools/vendor_ref.py)')
+            from oracle import tiger_oracle as O
+            from www2023tiger_b200.init import random_weights
+            torch.set_num_threads(self.cores)
+            N, d = st.n_nodes, st.dim
+            de = st.efeats.shape[1] if st.efeats is not None else d
+            self.W = random_weights(d, de, n_nodes=N, restarter=self.restarter, hist_len=HIST_LEN, seed=args.seed)
+            self.O, self.st, self.neg = O, st, neg
+            E = n_graph
+            self.graph = O.OracleGraph(st.src[:E], st.dst[:E], st.ts[:E], st.eids[:E], n_nodes=N)
+            self.model = O.OracleTIGER(self.W, self.graph, N, d, st.efeats, None, n_neighbors=K_NEIGH, n_head=N_HEAD,
+                                       msg_src=shape.msg_src, upd_src=shape.upd_src, restarter=self.restarter,
+                                       hist_len=HIST_LEN)
+            self.uptodate = np.zeros(N, dtype=bool)
+            self.kind = 'port'
+            self.what = 'oracle/tiger_oracle.py (collate + lazy restart + contrast step), ' \
+                        f'torch {torch.__version__} CPU'
+
+    def weights(self):
+        return self.ref.state_dict() if self.kind == 'reference' else self.W
+
+    def step(self, i):
+        """-> dict(neigh_nids, winner_index, pos_scores, neg_scores, loss) as numpy (eval mode)."""
+        lo = self.lo + i * BATCH
+        if self.kind == 'reference':
+            if self.mode == 'train':
+                return self.ref.train_step(lo)
+            (loss, _, ps, ns, _, _), cg = self.ref.eval_step(lo)
+            return {'neigh_nids': cg.layers[1][0].numpy(), 'winner_index': cg.restart_data.index.numpy(),
+                    'pos_scores': ps.numpy(), 'neg_scores': ns.numpy(), 'loss': float(loss)}
+        import torch
+        O, st, neg = self.O, self.st, self.neg
+        s = slice(lo, lo + BATCH)
+        b = O.collate(self.graph, st.src[s], st.dst[s], neg[s], st.ts[s], st.eids[s], K_NEIGH)
+        rn = O.lazy_restart_nodes(b.involved, self.uptodate)
         with torch.no_grad():
-            model.contrast_step(b)
-    return step, cores
+            self.model.restart(rn, np.full(len(rn), b.ts.min(), dtype=np.float32))
+            r = self.model.contrast_step(b)
+        _, idx = O.select_latest(np.concatenate([b.src, b.dst]), np.tile(b.ts64, 2))
+        return {'neigh_nids': b.neigh_nids, 'winner_index': idx, 'pos_scores': r['pos_scores'].numpy(),
+                'neg_scores': r['neg_scores'].numpy(), 'loss': float(r['loss'])}
 
+    def time(self, first, max_batches, budget_s, warmup=2):
+        """Times consecutive batches first+warmup .. until `max_batches` or the time budget; -> (n, seconds)."""
+        for i in range(first, first + warmup):
+            self.step(i)
+        n, t0 = 0, time.perf_counter()
+        while n < max_batches:
+            self.step(first + warmup + n)
+            n += 1
+            if time.perf_counter() - t0 > budget_s and n >= 3:
+                break
+        return n, time.perf_counter() - t0
 
-def time_oracle(step, n_batches, warmup=2):
-    for i in range(warmup):
-        step(i)
-    t0 = time.perf_counter()
-    for i in range(warmup, warmup + n_batches):
-        step(i)
-    return time.perf_counter() - t0
+    def describe(self, n, lo_batch):
+        return (f'{n} consecutive batches of {BATCH} events from event {self.lo + lo_batch * BATCH} of the '
+                f'{self.args.workload}-shaped stream: {self.what}, {self.cores} threads')
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    shape, st, neg = load_workload(args)
+    shape, st, neg = load_workload(args, with_efeats=True, cpu_only=True)
     lo, avail = batch_window(args, st.n_events, 0, max(world, 1))
-    step, cores = oracle_runner(args, shape, st, neg, lo)
-    budget_s = 240.0
-    W = min(args.warmup, max(avail - 1, 0))
+    budget_s = 200.0
+    W = min(args.warmup, max(avail - 1, 0), 5)
+    K = min(args.steps, avail - W)
+    arm = CpuArm(args, shape, st, neg, lo, W + K, kind=args.cpu_kind, mode=args.mode)
     t0 = time.perf_counter()
     for i in range(W):
-        step(i)
+        arm.step(i)
     per = (time.perf_counter() - t0) / max(W, 1)
-    K = min(args.steps, avail - W)
     if per > 0 and K * per > budget_s:
         K = max(3, int(budget_s / per))
     t0 = time.perf_counter()
     for i in range(W, W + K):
-        step(i)
+        arm.step(i)
     dt = time.perf_counter() - t0
     value = K * BATCH / dt
-    sample = f'{K} consecutive batches of {BATCH} events of the {args.workload}-shaped stream from event {lo}'
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': K,
+        'impl': 'reference', 'metric': metric_name(args), 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': K,
         'warmup': W, 'ms_per_step': dt / K * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, shape, st, world),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind,
+                         'sample': arm.describe(K, W)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
 
 
+def metric_name(args):
+    return METRIC_TRAIN if args.mode == 'train' else METRIC
+
+
+CONFIG_LINES = {   # BASELINE.json:configs, verbatim
+    'wikipedia': 'TIGER seq restarter on synthetic Wikipedia-shaped stream (9,227 nodes, 157,474 events, 172-d edge '
+                 'feats, dim 172, batch 200)',
+    'reddit': 'Synthetic Reddit-shaped stream (10,984 nodes, 672,447 events, 172-d feats), static restarter, 1xB200',
+    'mooc': 'Synthetic MOOC-shaped stream (7,144 nodes, 411,749 events, 4-d feats, --dim 100), msg_src/upd_src right',
+    'lastfm': 'Synthetic LastFM-shaped stream (1,980 nodes, 1,293,103 events, no edge feats, --dim 100), restart_prob '
+              '0.001',
+    'scaled': 'Scaled synthetic stream (1M nodes, 50M events, 172-d feats) via train_self_supervised_ddp at 2/4/8xB200',
+}
+
+
 def workload_config(args, shape, st, world):
-    return {'workload': f'{args.workload}-shaped synthetic stream ({st.n_nodes - 1} nodes, {st.n_events} events, '
-                        f'd={st.dim}, de={shape.efeat_dim or st.dim}), static restarter, lazy restart, '
+    rst = pick_restarter(args, shape)
+    return {'workload': f'{CONFIG_LINES[args.workload]} :: {st.n_nodes - 1} nodes, {st.n_events} events, '
+                        f'd={st.dim}, de={shape.efeat_dim or st.dim}, {rst} restarter'
+                        f'{" (hist_len %d)" % HIST_LEN if rst == "seq" else ""}, lazy restart, '
                         f'msg_src={shape.msg_src}, upd_src={shape.upd_src}',
+            'mode': args.mode, 'restarter': rst,
             'batch': BATCH, 'n_neighbors': K_NEIGH, 'n_heads': N_HEAD, 'n_layers': 1,
-            'partition': 'ChunkSampler time chunks, rank-local memory replicas, no data-path collective'
-            if world > 1 else 'single stream',
+            'partition': 'ChunkSampler time chunks, rank-local memory replicas'
+                         + (', gradient all-reduce (NCCL) every step' if args.mode == 'train' else
+                            ', no data-path collective') if world > 1 else 'single stream',
             'l2': 'tables read per step (edge features + message store + memories) exceed the 126 MB L2 for '
                   'reddit/scaled; no flush between steps: consecutive batches are state-dependent and run '
                   'back to back exactly as in the real workload'}
@@ -291,14 +401,26 @@ def run_b200(args):
     to = lambda x, dt: torch.as_tensor(x).to(dt).to(dev).contiguous()
     csr = ops.csr_build(to(st.src, torch.int64), to(st.dst, torch.int64), to(st.ts, torch.float64),
                         to(st.eids, torch.int64), N)
-    W = random_weights(d, de, n_nodes=N, restarter='static', seed=args.seed)
-    eng = TigerEngine(W, csr, n_nodes=N, dim=d, efeats=efeats, n_neighbors=K_NEIGH, n_head=N_HEAD,
-                      batch_size=BATCH, msg_src=shape.msg_src, upd_src=shape.upd_src, restarter='static',
-                      lazy_restart=True, device=dev)
+    rst = pick_restarter(args, shape)
     lo, avail = batch_window(args, st.n_events, rank, world)
     if avail < 8:
         raise SystemExit('stream too short for this rank')
     B = BATCH
+    # CPU arm (rank 0 at N = 1): built first because the engine runs with ITS parameters - the reference's own
+    # init_model under torch.manual_seed(seed) - so that the two can be compared batch by batch below
+    arm = None
+    if rank == 0 and world == 1 and args.cpu_batches > 0:
+        n_cpu = min(args.cpu_batches + args.parity_batches + 4, avail - 2)
+        prefix = None
+        if st.efeats is None and efeats is not None:
+            prefix = efeats[:min(st.n_events, lo + (n_cpu + 2) * B) + 1].cpu().numpy()
+        arm = CpuArm(args, shape, st, neg, lo, n_cpu, kind=args.cpu_kind, efeats_prefix=prefix)
+        W = arm.weights()
+    else:
+        W = random_weights(d, de, n_nodes=N, restarter=rst, hist_len=HIST_LEN, seed=args.seed)
+    eng = TigerEngine(W, csr, n_nodes=N, dim=d, efeats=efeats, n_neighbors=K_NEIGH, n_head=N_HEAD,
+                      batch_size=BATCH, msg_src=shape.msg_src, upd_src=shape.upd_src, restarter=rst,
+                      hist_len=HIST_LEN, lazy_restart=True, device=dev)
 
     # all batch inputs of this rank's window, resident in HBM: [avail, 5B] int64 (ts as float64 bits)
     host_in = np.empty((avail, 5 * B), dtype=np.int64)
@@ -411,28 +533,67 @@ def run_b200(args):
                            'frac': 3.0 * flops / (g['us'] * 1e-6) / 1e12 / tf32_peak,
                            'peak_source': 'half of the measured bf16 GEMM peak (tf32 runs at half the bf16 rate)'}
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N=1 ----
+    # ---- parity inside the bench: the first batches after a reset, engine vs the CPU arm on the same inputs ----
+    parity = None
+    if arm is not None and args.parity_batches > 0:
+        parity = check_parity(eng, arm, dev_in, args.parity_batches)
+
+    # ---- CPU baseline: the reference on the host cores, bounded sample, rank 0 at N=1 (+ the oracle port) ----
     cpu = None
-    if rank == 0 and world == 1 and args.cpu_batches > 0 and (st.efeats is not None or shape.efeat_dim == 0):
-        step, cores = oracle_runner(args, shape, st, neg, lo)
-        n = min(args.cpu_batches, avail - 2)
-        dt = time_oracle(step, n)
-        cpu = {'value': n * B / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': f'{n} consecutive batches of {B} events from event {lo} (oracle/tiger_oracle.py: collate + '
-                         f'lazy restart + contrast step), torch {torch.__version__} CPU, {cores} threads',
-               'ms_per_step': dt / n * 1e3}
+    if arm is not None:
+        first = args.parity_batches if parity is not None else 0
+        n, dt = arm.time(first, min(args.cpu_batches, avail - first - 4), args.cpu_seconds)
+        cpu = {'value': n * B / dt, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind,
+               'sample': arm.describe(n, first + 2), 'ms_per_step': dt / n * 1e3}
+        if arm.kind == 'reference' and st.efeats is not None:
+            port = CpuArm(args, shape, st, neg, lo, first + n + 4, kind='port')
+            n2, dt2 = port.time(first, n, args.cpu_seconds)
+            cpu['port'] = {'value': n2 * B / dt2, 'unit': UNIT, 'cores': port.cores, 'kind': 'port',
+                           'sample': port.describe(n2, first + 2), 'ms_per_step': dt2 / n2 * 1e3}
 
     if rank == 0:
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+            'metric': metric_name(args), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, shape, st, world),
             'e2e': e2e, 'gpu_launches': eng.launches_per_step() * K, 'clocks': clk, 'roofline': roofline,
-            'cpu_baseline': cpu, 'kernels': kernels,
+            'cpu_baseline': cpu, 'parity_checked': bool(parity), 'parity': parity, 'kernels': kernels,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def check_parity(eng, arm, dev_in, n_batches):
+    """Replays the first `n_batches` batches of the window from a reset state through the engine (eager launches)
+    and through the CPU arm, which runs with the same parameters: neighbor tables and argmax-by-timestamp winners
+    must be bit-identical, scores and loss within 1e-5 (max-norm, the tolerance BASELINE.json states).  Raises on
+    a mismatch - a fast wrong kernel must not produce a bench line."""
+    import torch
+    eng.reset()
+    B = eng.B
+    worst = {'scores': 0.0, 'loss': 0.0}
+    for j in range(n_batches):
+        eng.inp.copy_(dev_in[j])
+        eng.step()
+        torch.cuda.synchronize()
+        eng.check_errors()
+        ref = arm.step(j)
+        if not np.array_equal(eng.neigh_nids.cpu().numpy(), ref['neigh_nids']):
+            raise SystemExit(f'parity: neighbor table of batch {j} differs from the {arm.kind}')
+        got = np.flatnonzero(eng.winner.cpu().numpy())
+        if not np.array_equal(got, np.sort(ref['winner_index'])):
+            raise SystemExit(f'parity: argmax-by-timestamp winners of batch {j} differ from the {arm.kind}')
+        out = eng.out_buf.cpu().numpy()
+        want = np.concatenate([ref['pos_scores'], ref['neg_scores']])
+        e_s = float(np.abs(out[:2 * B] - want).max() / max(np.abs(want).max(), 1e-30))
+        e_l = abs(float(out[2 * B]) - ref['loss']) / max(abs(ref['loss']), 1e-30)
+        worst['scores'], worst['loss'] = max(worst['scores'], e_s), max(worst['loss'], e_l)
+        if e_s > 1e-5 or e_l > 1e-5:
+            raise SystemExit(f'parity: batch {j} scores {e_s:.2e} / loss {e_l:.2e} exceed 1e-5 vs the {arm.kind}')
+    eng.reset()
+    return {'against': arm.kind, 'batches': n_batches, 'neighbor_tables': 'bit-identical',
+            'winners': 'bit-identical', 'scores_max_rel': worst['scores'], 'loss_rel': worst['loss'], 'tol': 1e-5}
 
 
 def st_fits_host(args):

@@ -201,3 +201,140 @@ def test_eval_edge_prediction_ap_matches_oracle():
         aps.append(average_precision_score(label, score))
     assert abs(ap - float(np.mean(aps))) <= 0.002
     assert 0.0 <= auc <= 1.0
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE dimensions (tests/golden/make_golden_full.py): the class surface driven like eval_edge_prediction
+# ------------------------------------------------------------------------------------------
+from golden_utils import FULL_CASES, FullGolden, check_full_batch   # noqa: E402
+
+
+@pytest.mark.parametrize('name', FULL_CASES)
+def test_dropin_replays_reference_at_baseline_dimensions(name):
+    g = FullGolden(name)
+    src_, dst_, ts_, eids_ = g.stream_prefix()
+    full = InteractionData(src_, dst_, ts_, eids_, np.zeros_like(src_), seed=0, eval=True, neg_dst=g.neg[:g.E])
+    graph = Graph.from_data(full, strategy='recent_edges', seed=0, max_node_id=g.N - 1)
+    coll = GraphCollator(graph, g.K, 1, restarter=g.restarter, hist_len=g.hist_len)
+    model = D.init_model(None, g.efeats, graph, g.N, g.st.n_events, DEV, dim=g.shape.dim, n_layers=1,
+                         n_heads=g.n_heads, n_neighbors=g.K, hit_type='bin', dropout=0.1, restarter_type=g.restarter,
+                         hist_len=g.hist_len, msg_src=g.msg_src, upd_src=g.upd_src)
+    res = model.load_state_dict(g.W, strict=False)
+    assert not res.unexpected_keys
+    model.eval()
+    model.reset()
+    uptodate = set()
+    with torch.no_grad():
+        for ib in range(g.warm + g.rec):
+            lo = g.start + ib * g.bs
+            src, dst, neg, ts, eids, cg = to_dev(coll([full[i] for i in range(lo, lo + g.bs)]))
+            fresh = sorted(set(cg.np_computation_graph_nodes.tolist()) - uptodate)
+            r_nids = torch.tensor(fresh, dtype=torch.long, device=DEV)
+            r_ts = torch.full((len(r_nids),), ts.min().item(), device=DEV)
+            got = {}
+            if ib >= g.warm and len(r_nids):
+                hl, hr, pt = model.restarter_fn(r_nids, r_ts)
+                got.update(restart_hl=cpu(hl), restart_hr=cpu(hr), restart_pt=cpu(pt))
+            model.restart(r_nids, r_ts)
+            uptodate.update(fresh)
+            pending_before = np.array(sorted(model.msg_store.nodes_with_messages), dtype=np.int64)
+            loss, h_left, ps, ns, hpl, hpr = model.contrast_learning(src, dst, neg, ts, eids, cg)
+            if ib < g.warm:
+                continue
+            rd = cg.restart_data
+            sl, sr, _ = model.restarter_fn(torch.cat([src, dst])[rd.index], ts.repeat(2)[rd.index], cg)
+            targets = torch.cat([hpl[rd.index], hpr[rd.index]], 0)
+            preds = torch.cat([sl, sr], 0)
+            valid = torch.where(~(targets == 0).all(1))[0]
+            ml = model.mutual_loss_fn(preds[valid], targets[valid]) if len(valid) else torch.tensor(0.)
+            w = np.zeros(2 * g.bs, dtype=np.uint8)
+            w[cpu(rd.index)] = 1
+            got.update(neigh_nids=cpu(cg.layers[1][0]), neigh_eids=cpu(cg.layers[1][1]), neigh_ts=cpu(cg.layers[1][2]),
+                       involved=cg.np_computation_graph_nodes, restart_nids=np.array(fresh),
+                       outdated=np.intersect1d(pending_before, cg.np_computation_graph_nodes), winner=w,
+                       h_left=cpu(h_left), pos_scores=cpu(ps), neg_scores=cpu(ns), loss=cpu(loss), mutual_loss=cpu(ml),
+                       h_prev_left=cpu(hpl), h_prev_right=cpu(hpr), surrogate_left=cpu(sl), surrogate_right=cpu(sr),
+                       left_vals=cpu(model.left_memory.vals), right_vals=cpu(model.right_memory.vals),
+                       msg_vals=cpu(model.msg_store.node_msg_vals), left_ts=cpu(model.left_memory.update_ts),
+                       right_ts=cpu(model.right_memory.update_ts), msg_ts=cpu(model.msg_store.node_msg_ts),
+                       pending_after=np.array(sorted(model.msg_store.nodes_with_messages)))
+            check_full_batch(g, ib - g.warm, got, TOL, 'dropin ')
+
+
+# ------------------------------------------------------------------------------------------
+# a27: the snapshot API the drivers call around every validation pass (train_self_supervised.py:193-202)
+# ------------------------------------------------------------------------------------------
+from tiger.eval_utils import warmup   # noqa: E402
+
+
+def test_save_and_load_memory_state_round_trip():
+    """save_memory_state / load_memory_state (tiger.py:465-484): the snapshot restores both memories and the
+    message store exactly, later steps run on the restored objects (every buffer on the device - the clone used to
+    leave `active_mask` on the host), and Memory.clone drops the activity flags like the reference (Q2)."""
+    g = Golden('seq_restart_mode')
+    full, graph, coll, dl, model = setup(g)
+    batches = [to_dev(b) for _, b in zip(range(8), dl)]
+    model.eval()
+    model.reset()
+    with torch.no_grad():
+        for b in batches[:4]:
+            model.contrast_learning(*b)
+        snap = model.save_memory_state()
+        assert all(t.is_cuda for m in snap[:2] for t in (m.vals, m.update_ts, m.active_mask))
+        assert int(snap[0].active_mask.sum()) == 0 and int(model.left_memory.active_mask.sum()) > 0     # Q2
+        want = [cpu(t).copy() for t in (model.left_memory.vals, model.right_memory.vals, model.left_memory.update_ts,
+                                        model.right_memory.update_ts, model.msg_store.node_msg_vals,
+                                        model.msg_store.node_msg_ts)]
+        pending = sorted(model.msg_store.nodes_with_messages)
+        first = [cpu(t) for t in model.contrast_learning(*batches[4])]
+        for b in batches[5:]:
+            model.contrast_learning(*b)                           # memory modified by "validation"
+        model.load_memory_state(snap)
+        got = [cpu(t) for t in (model.left_memory.vals, model.right_memory.vals, model.left_memory.update_ts,
+                                model.right_memory.update_ts, model.msg_store.node_msg_vals,
+                                model.msg_store.node_msg_ts)]
+        for a, b_ in zip(got, want):
+            assert np.array_equal(a, b_)
+        assert sorted(model.msg_store.nodes_with_messages) == pending
+        assert model.msg_memory is (model.left_memory if g.msg_src == 'left' else model.right_memory)
+        again = [cpu(t) for t in model.contrast_learning(*batches[4])]    # kernels store through the restored buffers
+        for a, b_ in zip(again, first):
+            assert np.array_equal(a, b_)
+        # the snapshot was handed over, not copied: a second restore needs a second snapshot (reference semantics)
+        model.flush_msg()
+        assert len(model.msg_store.nodes_with_messages) == 0
+
+
+def test_warmup_equals_eval_loop_without_scoring():
+    """warmup (eval_utils.py:102-129) = the lazy-restart loop of eval_edge_prediction without the scores."""
+    g = Golden('seq_restart_mode')
+    full, graph, coll, dl, model = setup(g)
+    model.reset()
+    seen = warmup(model, dl, DEV)
+    a = [cpu(t).copy() for t in (model.left_memory.vals, model.right_memory.vals, model.msg_store.node_msg_vals)]
+    model.reset()
+    seen2 = set()
+    eval_edge_prediction(model, dl, DEV, restart_mode=True, uptodate_nodes=seen2, mean_over_n_samples=g.bs)
+    b = [cpu(t) for t in (model.left_memory.vals, model.right_memory.vals, model.msg_store.node_msg_vals)]
+    assert seen == seen2 and len(seen) > 0
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_memory_set_and_flush_with_more_than_2048_ids():
+    """Memory.set's duplicate check takes the large-n path of tiger_select_latest in flags-only mode, whose count
+    used to stay unwritten; flush_msg hits it after an epoch."""
+    from tiger.model.memory import Memory
+    n, d = 6000, 12
+    mem = Memory(n, d).to(DEV)
+    ids = torch.randperm(n, device=DEV)[:5000]
+    vals = torch.randn(5000, d, device=DEV)
+    ts = torch.rand(5000, device=DEV) + 1
+    mem.set(ids, vals, ts)
+    assert torch.equal(mem.vals[ids], vals) and torch.equal(mem.update_ts[ids], ts)
+    dup = ids.clone()
+    dup[4000] = dup[17]
+    with pytest.raises(ValueError, match='Duplicate'):
+        mem.set(dup, vals, ts + 1)
+    with pytest.raises(ValueError, match='past memory'):
+        mem.set(ids, vals, ts - 1)

@@ -289,3 +289,56 @@ def test_first_batch_after_reset_is_bit_stable_under_graph_replay(gu):
         runner.run_device()
         torch.cuda.synchronize()
         assert torch.equal(e.emb, ref_emb) and torch.equal(e.out_buf, ref_out), f'iteration {it} (single graph)'
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE dimensions, fixtures of the unmodified reference (tests/golden/make_golden_full.py)
+# ------------------------------------------------------------------------------------------
+from golden_utils import FULL_CASES, FullGolden, check_full_batch   # noqa: E402
+
+
+def engine_results(gu, e, B):
+    U, Oc, R = (int(x) for x in e.counts[:3])
+    got = dict(neigh_nids=gu.cpu(e.neigh_nids), neigh_eids=gu.cpu(e.neigh_eids), neigh_ts=gu.cpu(e.neigh_ts),
+               involved=gu.cpu(e.involved[:U]), outdated=gu.cpu(e.outdated[:Oc]), restart_nids=gu.cpu(e.restart_nodes[:R]),
+               winner=gu.cpu(e.winner), h_left=gu.cpu(e.emb[:2 * B]), pos_scores=gu.cpu(e.scores[:B]),
+               neg_scores=gu.cpu(e.scores[B:]), loss=gu.cpu(e.loss), h_prev_left=gu.cpu(e.hprev_left),
+               h_prev_right=gu.cpu(e.hprev_right), left_vals=gu.cpu(e.left_vals), right_vals=gu.cpu(e.right_vals),
+               msg_vals=gu.cpu(e.msg_vals), left_ts=gu.cpu(e.left_ts), right_ts=gu.cpu(e.right_ts),
+               msg_ts=gu.cpu(e.msg_ts), pending_after=np.nonzero(gu.cpu(e.has_msg))[0])
+    if e.restarter == 'seq' and R:
+        got.update(restart_hl=gu.cpu(e.seq.h_left[:R]), restart_hr=gu.cpu(e.seq.h_right[:R]),
+                   restart_pt=gu.cpu(e.seq.prev_ts[:R]))
+    return got
+
+
+@pytest.mark.parametrize('replay', ['eager', 'graph'])
+@pytest.mark.parametrize('name', FULL_CASES)
+def test_engine_replays_reference_at_baseline_dimensions(gu, name, replay):
+    """d / d_e / K / hist_len / batch of the BASELINE configs, on the BASELINE-shaped streams, lazy-restart mode:
+    eager launches and the captured-graph pipeline (the benchmarked path) against the unmodified reference."""
+    g = FullGolden(name)
+    csr = gu.device_csr(*g.stream_prefix(), g.N)
+    e = gu.engine_from(g.W, csr, N=g.N, dim=g.dim, efeats=g.efeats, nfeats=None, K=g.K, H=g.n_heads, B=g.bs,
+                       msg_src=g.msg_src, upd_src=g.upd_src, restarter=g.restarter, lazy_restart=True,
+                       hist_len=g.hist_len)
+    runner = None
+    if replay == 'graph':
+        runner = StreamRunner(e)
+        e.set_batch(*g.batch(0))
+        runner.capture(warmup=1)
+        e.reset()
+    for ib in range(g.warm + g.rec):
+        if runner is None:
+            e.set_batch(*g.batch(ib))
+            e.step()
+        else:
+            slot = runner.submit_host(*g.batch(ib))
+            runner.wait(slot)
+            torch.cuda.synchronize()
+            # the pipeline's slot owns the finder outputs and the result buffer of this batch
+            e.bind_finder(runner.finder_bufs[slot])
+            e.bind_io(runner.d_in[slot], runner.d_out[slot])
+        e.check_errors()
+        if ib >= g.warm:
+            check_full_batch(g, ib - g.warm, engine_results(gu, e, g.bs), TOL, replay + ' ')

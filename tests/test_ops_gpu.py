@@ -471,3 +471,21 @@ def test_large_row_sets_take_the_bulk_copy_path(gu, d):
     reft = ts_table.clone(); reft[nodes] = msg_ts[nodes]
     refm = has_msg.clone(); refm[nodes] = 0
     assert torch.equal(rv, ref) and torch.equal(rt, reft) and torch.equal(hm, refm)
+
+
+@pytest.mark.parametrize('n', [2049, 5000, 70000])
+def test_select_latest_large_flags_only_count(n):
+    """flags-only mode (no ordered output) of the large-n path must still report the number of distinct ids."""
+    rng = np.random.RandomState(n)
+    n_nodes = 3000
+    ids = rng.randint(1, n_nodes, n)
+    ts = np.floor(rng.uniform(0, 50, n))
+    scratch = ops.SelectScratch(n_nodes, 'cuda')
+    winner, _, _, count = ops.select_latest(torch.from_numpy(ids).cuda(), torch.from_numpy(ts).cuda(), scratch,
+                                            want_unique=False)
+    u, ix = O.select_latest(ids, ts)
+    assert int(count) == len(u)
+    w = np.zeros(n, dtype=np.uint8)
+    w[ix] = 1
+    assert np.array_equal(winner.cpu().numpy(), w)
+    assert int(scratch.slot_ts.abs().sum()) == 0 and int(scratch.slot_pos.abs().sum()) == 0

@@ -128,3 +128,56 @@ def test_chunk_range_partitions_like_chunk_sampler():
         for r, (lo, hi) in enumerate(ranges):
             assert hi - lo == L and lo == ranges[0][0] + r * L
         assert 0 <= ranges[0][0] <= n % (W * bs) and ranges[-1][1] <= n
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE dimensions: d / d_e / K / hist_len / batch of the BASELINE.json configs, on the BASELINE-shaped
+# streams (tests/golden/make_golden_full.py)
+# ------------------------------------------------------------------------------------------
+from golden_utils import FULL_CASES, FullGolden, check_full_batch   # noqa: E402
+
+
+def replay_full_on_oracle(g: FullGolden):
+    """Yields (recorded-batch index, dict of results in the fixture's names) for the oracle port."""
+    src, dst, ts, eids = g.stream_prefix()
+    graph = O.OracleGraph(src, dst, ts, eids, n_nodes=g.N)
+    model = O.OracleTIGER(g.W, graph, g.N, g.dim, g.efeats, None, n_neighbors=g.K, n_head=g.n_heads,
+                          msg_src=g.msg_src, upd_src=g.upd_src, restarter=g.restarter, hist_len=g.hist_len)
+    uptodate = np.zeros(g.N, dtype=bool)
+    with torch.no_grad():
+        for ib in range(g.warm + g.rec):
+            b = O.collate(graph, *g.batch(ib), g.K, restarter=g.restarter, hist_len=g.hist_len)
+            rn = O.lazy_restart_nodes(b.involved, uptodate)
+            r_ts = np.full(len(rn), b.ts.min(), dtype=np.float32)
+            got = {}
+            if ib >= g.warm and len(rn):
+                hl, hr, pt = model.restarter_forward(rn, r_ts)
+                got.update(restart_hl=hl.numpy(), restart_hr=hr.numpy(), restart_pt=pt.numpy())
+            model.restart(rn, r_ts)
+            out = model.contrast_step(b)
+            if ib < g.warm:
+                continue
+            sl, sr, _ = model.restarter_on_batch(b)
+            w = np.zeros(2 * g.bs, dtype=np.uint8)
+            w[b.restart.index] = 1
+            got.update(neigh_nids=b.neigh_nids, neigh_eids=b.neigh_eids, neigh_ts=b.neigh_ts, involved=b.involved,
+                       restart_nids=rn, outdated=out['outdated'], winner=w, h_left=out['h_left'].numpy(),
+                       pos_scores=out['pos_scores'].numpy(), neg_scores=out['neg_scores'].numpy(),
+                       loss=out['loss'].numpy(), mutual_loss=model.mutual_loss(b, out).numpy(),
+                       h_prev_left=out['h_prev_left'].numpy(), h_prev_right=out['h_prev_right'].numpy(),
+                       surrogate_left=sl.numpy(), surrogate_right=sr.numpy(),
+                       left_vals=model.left_vals.numpy(), right_vals=model.right_vals.numpy(),
+                       msg_vals=model.msg_vals.numpy(), left_ts=model.left_ts.numpy(),
+                       right_ts=model.right_ts.numpy(), msg_ts=model.msg_ts.numpy(),
+                       pending_after=np.nonzero(model.has_msg)[0])
+            yield ib - g.warm, got
+
+
+@pytest.mark.parametrize('name', FULL_CASES)
+def test_oracle_matches_reference_at_baseline_dimensions(name):
+    g = FullGolden(name)
+    n = 0
+    for ir, got in replay_full_on_oracle(g):
+        check_full_batch(g, ir, got, tol=5e-6, what='oracle ')
+        n += 1
+    assert n == g.rec

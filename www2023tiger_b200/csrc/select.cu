@@ -87,13 +87,20 @@ __global__ void select_min_pos_kernel(const int64_t* __restrict__ nids, const vo
 
 __global__ void select_flag_kernel(const int64_t* __restrict__ nids, int64_t n,
                                    const uint32_t* __restrict__ slot_pos, uint8_t* __restrict__ winner,
-                                   uint32_t* __restrict__ bitmap) {
+                                   uint32_t* __restrict__ bitmap, int32_t* __restrict__ count) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const int64_t id = nids[p];
-  const bool win = slot_pos[id] == 0xffffffffu - (uint32_t)p;
-  if (winner != nullptr) winner[p] = win;
-  if (win && bitmap != nullptr) atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+  bool win = false;
+  if (p < n) {
+    const int64_t id = nids[p];
+    win = slot_pos[id] == 0xffffffffu - (uint32_t)p;
+    if (winner != nullptr) winner[p] = win;
+    if (win && bitmap != nullptr) atomicOr(bitmap + (id >> 5), 1u << (id & 31));
+  }
+  // flags-only mode: the number of winners (= distinct ids) is an integer sum, order-independent
+  if (count != nullptr) {
+    const unsigned votes = __ballot_sync(TIGER_FULL_MASK, win);
+    if (lane_id() == 0 && votes) atomicAdd(count, __popc(votes));
+  }
 }
 
 // scratch reset when no ordered output was requested (idempotent writes)
@@ -177,7 +184,11 @@ extern "C" int tiger_select_latest(const int64_t* nids, const void* ts, int ts_i
   const unsigned grid = (unsigned)((n + 255) / 256);
   select_max_ts_kernel<<<grid, 256, 0, st>>>(nids, ts, ts_is_f64, n, ts_period, slot_ts);
   select_min_pos_kernel<<<grid, 256, 0, st>>>(nids, ts, ts_is_f64, n, ts_period, slot_ts, slot_pos);
-  select_flag_kernel<<<grid, 256, 0, st>>>(nids, n, slot_pos, winner, unique_ids != nullptr ? bitmap : nullptr);
+  // without the ordered output nothing else writes *count (select_compact_kernel does when it runs)
+  const bool count_in_flags = unique_ids == nullptr && count != nullptr;
+  if (count_in_flags) cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+  select_flag_kernel<<<grid, 256, 0, st>>>(nids, n, slot_pos, winner, unique_ids != nullptr ? bitmap : nullptr,
+                                           count_in_flags ? count : nullptr);
   if (unique_ids != nullptr) {
     select_compact_kernel<<<1, 1024, 0, st>>>(bitmap, (n_nodes + 31) / 32, slot_ts, slot_pos, unique_ids, index,
                                               count);

@@ -159,7 +159,7 @@ def gather_rows(table: Tensor, ids: Tensor, ts_table: Optional[Tensor] = None):
 
 def scatter_rows(table: Optional[Tensor], ids: Tensor, vals: Optional[Tensor], *, ts_table=None, ts=None,
                  active=None, check: bool = False, err_flags=None, count=None, width: Optional[int] = None):
-    check_cuda(table, ids, vals, ts_table, ts)
+    check_cuda(table, ids, vals, ts_table, ts, active, err_flags, count)
     w = width if width is not None else (table.shape[1] if table is not None else 0)
     call('tiger_scatter_rows', ptr(table), w, ptr(ids), ids.numel(), ptr(count), ptr(vals), ptr(ts_table), ptr(ts),
          ptr(active), int(check), ptr(err_flags))
@@ -182,12 +182,15 @@ def store_messages(src, dst, eids, ts, winner, mem_vals, mem_ts, nfeats, efeats,
 
 def right_writeback(pos_ids, winner, gru_row, h_new, d, right_vals, right_ts, right_active, msg_ts, has_msg,
                     left_vals=None, hprev_left=None, hprev_right=None, err_flags=None):
+    check_cuda(pos_ids, winner, gru_row, h_new, right_vals, right_ts, right_active, msg_ts, has_msg, left_vals,
+               hprev_left, hprev_right, err_flags)
     call('tiger_right_writeback', ptr(pos_ids), pos_ids.numel(), ptr(winner), ptr(gru_row), ptr(h_new), d,
          ptr(right_vals), ptr(right_ts), ptr(right_active), ptr(msg_ts), ptr(has_msg), ptr(left_vals),
          ptr(hprev_left), ptr(hprev_right), ptr(err_flags))
 
 
 def left_writeback(pos_ids, batch, winner, h_left, d, ts, left_vals, left_ts, left_active, err_flags=None):
+    check_cuda(pos_ids, winner, h_left, ts, left_vals, left_ts, left_active, err_flags)
     call('tiger_left_writeback', ptr(pos_ids), pos_ids.numel(), batch, ptr(winner), ptr(h_left), d, ptr(ts),
          ptr(left_vals), ptr(left_ts), ptr(left_active), ptr(err_flags))
 

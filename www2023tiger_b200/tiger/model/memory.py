@@ -24,7 +24,9 @@ class Memory(nn.Module):
         self._err = ErrFlags()
 
     def clone(self):
-        other = Memory(self.n, self.dim)           # like the reference, active_mask is not carried over
+        # like the reference (memory.py:21-25) the activity flags are not carried over (they start at zero); unlike
+        # it, every buffer of the copy lives on the source's device - the kernels store through all three
+        other = Memory(self.n, self.dim).to(self.vals.device)
         other.vals.data = self.vals.data.clone()
         other.update_ts.data = self.update_ts.data.clone()
         return other
