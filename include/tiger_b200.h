@@ -357,6 +357,19 @@ int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, con
                    int64_t ldc, int64_t m_rows, const int32_t* count, int64_t rows_per_count, int n_cols,
                    int k_dim, int relu, void* stream);
 
+/* General product for the training step (same tensor-core kernel):
+ *   C[m,n] (+)= act(alpha * (sum_k opA[m,k] * opW[n,k] + bias[n]))
+ * opA[m,k] = A[m*lda + k] (trans_a = 0) or A[k*lda + m] (trans_a = 1), opW likewise, so that the three products of
+ * a linear layer use the tensors as stored: y = x W^T (0,0), dx = dy W (0,1), dW = dy^T x (1,1) - what autograd
+ * runs for nn.Linear / nn.GRUCell / nn.MultiheadAttention under loss.backward() (train_self_supervised.py:169).
+ * accumulate != 0 adds the tile into C with atomic adds (the gradient of a parameter with several uses; bias and
+ * relu must be off) and splits K over k_parts CTAs per tile.  m_count / k_count (device, may be NULL) bound the
+ * row count / the reduction length by *count * rows_per_count. */
+int tiger_sgemm_ex(const float* A, int64_t lda, int trans_a, const float* W, int64_t ldw, int trans_w,
+                   const float* bias, float* C, int64_t ldc, int64_t m_rows, int n_cols, int64_t k_dim,
+                   const int32_t* m_count, const int32_t* k_count, int64_t rows_per_count, float alpha, int relu,
+                   int accumulate, int k_parts, void* stream);
+
 /* Batched / extended form: problem b uses A + b*stride_a, W + b*stride_w, bias + b*stride_bias,
  * C + b*stride_c (strides in floats); the result is act(alpha * (A W^T + bias)); rows with
  * row_zero[m] != 0 (may be NULL; shared by all problems) are written as zeros - the

@@ -489,3 +489,51 @@ def test_select_latest_large_flags_only_count(n):
     w[ix] = 1
     assert np.array_equal(winner.cpu().numpy(), w)
     assert int(scratch.slot_ts.abs().sum()) == 0 and int(scratch.slot_pos.abs().sum()) == 0
+
+
+# ------------------------------------------------------------------ general tensor-core product (training step)
+@pytest.mark.parametrize('m,n,k', [(600, 172, 344), (37, 5, 19), (1900, 516, 688), (128, 128, 16), (1, 1, 1)])
+@pytest.mark.parametrize('ta,tw', [(False, False), (False, True), (True, True), (True, False)])
+def test_sgemm_ex_all_operand_layouts(m, n, k, ta, tw):
+    g = torch.Generator(device='cuda').manual_seed(m * 7 + n)
+    A = torch.randn((k, m) if ta else (m, k), device='cuda', generator=g)
+    W = torch.randn((k, n) if tw else (n, k), device='cuda', generator=g)
+    bias = torch.randn(n, device='cuda', generator=g)
+    out = torch.empty(m, n, device='cuda')
+    ops.sgemm_ex(A, W, out, m=m, n=n, k=k, trans_a=ta, trans_w=tw, bias=bias, relu=True, alpha=0.5)
+    opA = (A.t() if ta else A).double()
+    opW = (W.t() if tw else W).double()
+    want = torch.relu(0.5 * (opA @ opW.t() + bias.double()))
+    assert_close(out.cpu().numpy(), want.cpu().numpy(), 2e-6, f'sgemm_ex {m}x{n}x{k} {ta}{tw}')
+
+
+@pytest.mark.parametrize('rows,count', [(6600, 1900), (6600, 0), (300, 300), (70000, 11200)])
+def test_sgemm_ex_weight_gradient_accumulates_with_device_count(rows, count):
+    """dW += dY[:count]^T X[:count]: transposed operands, reduction length from device memory, split K, atomic
+    accumulation on top of what the buffer already holds."""
+    g = torch.Generator(device='cuda').manual_seed(rows + count)
+    n_out, n_in = 516, 172
+    dY = torch.randn(rows, n_out, device='cuda', generator=g)
+    X = torch.randn(rows, n_in, device='cuda', generator=g)
+    dW = torch.randn(n_out, n_in, device='cuda', generator=g)
+    base = dW.clone()
+    cnt = torch.tensor([count], dtype=torch.int32, device='cuda')
+    ops.sgemm_ex(dY, X, dW, m=n_out, n=n_in, k=rows, trans_a=True, trans_w=True, accumulate=True, k_parts=16,
+                 k_count=cnt)
+    want = base.double() + dY[:count].double().t() @ X[:count].double()
+    assert_close(dW.cpu().numpy(), want.cpu().numpy(), 2e-6, f'wgrad rows={rows} count={count}')
+
+
+def test_sgemm_nt_capacity_launch_is_persistent_and_exact():
+    """A launch sized for a large row capacity with a small device-side row count (the seq restarter's case)."""
+    g = torch.Generator(device='cuda').manual_seed(3)
+    cap, rows, k, n = 264000, 920, 860, 1720
+    A = torch.randn(cap, k, device='cuda', generator=g)
+    W = torch.randn(n, k, device='cuda', generator=g)
+    b = torch.randn(n, device='cuda', generator=g)
+    out = torch.zeros(cap, n, device='cuda')
+    cnt = torch.tensor([rows // 40], dtype=torch.int32, device='cuda')
+    ops.sgemm_nt(A, W, b, out, m_rows=cap, count=cnt, rows_per_count=40)
+    want = A[:rows].double() @ W.double().t() + b.double()
+    assert_close(out[:rows].cpu().numpy(), want.cpu().numpy(), 2e-6, 'capacity launch')
+    assert float(out[rows:rows + 4096].abs().max()) == 0.0

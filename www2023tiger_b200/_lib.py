@@ -62,6 +62,7 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_min_time': 'plp' + 'p',
     'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
     'tiger_sgemm_nt': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
+    'tiger_sgemm_ex': 'pli' + 'pli' + 'ppl' + 'lil' + 'ppl' + 'fiii' + 'p',
     'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_gemm_pick_bn': 'lii',
     'tiger_gemm_pack_bytes': 'iii',

@@ -25,6 +25,7 @@
 // host syncs: CTAs whose row block starts beyond it exit before touching TMEM.
 #include "common.cuh"
 #include "umma.cuh"
+#include <cstring>
 
 #ifdef TIGER_TRACE
 #include <cstdio>
@@ -102,6 +103,14 @@ struct GemmArgs {
   int a_sel_i64;
   const float* a_alt;
   const float* a_add;
+  // general form (tiger_sgemm_ex, unpacked kernel): either operand may be read transposed (element (row, k) at
+  // base[k * ld + row]) - the dgrad / wgrad products of the training step use the tensors as stored; the
+  // reduction length may live on the device (k_count * k_rows_per_count); blockIdx.y splits K into parts of
+  // kblk_per_part stages whose partial tiles are accumulated into C with atomic adds (gradient accumulation)
+  int trans_a, trans_w, accumulate;
+  const int32_t* k_count;
+  int64_t k_rows_per_count;
+  int kblk_per_part;
 };
 
 struct GemmGather {
@@ -130,30 +139,61 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     const int64_t c = (int64_t)(*g.count) * g.rows_per_count;
     M = c < M ? c : M;
   }
-  const int64_t m0 = (int64_t)(blockIdx.x / g.tiles_n) * TCG_BM;
-  if (m0 >= M) return;
-  const int n0 = (int)(blockIdx.x % g.tiles_n) * BN;
-  const int b = blockIdx.y;
+  // persistent over output tiles: CTA c owns tiles c, c + gridDim.x, ... (row-block major), so a launch sized for
+  // a row CAPACITY whose actual row count lives on the device costs at most gridDim.x (<= #SMs) CTAs instead of
+  // one (immediately exiting) CTA per capacity tile - at the seq restarter's capacity that was 29k CTAs = 57 us
+  const int64_t n_tiles_total = ((g.M + TCG_BM - 1) / TCG_BM) * g.tiles_n;
+  if ((int64_t)(blockIdx.x / g.tiles_n) * TCG_BM >= M) return;
+  const int b = g.kblk_per_part > 0 ? 0 : blockIdx.y;
+  int K_eff = g.K;
+  if (g.k_count != nullptr) {
+    const int64_t c = (int64_t)(*g.k_count) * g.k_rows_per_count;
+    K_eff = c < K_eff ? (int)c : K_eff;
+  }
+  const int kblk0 = g.kblk_per_part > 0 ? (int)blockIdx.y * g.kblk_per_part : 0;   // first stage of this K part
+  {
+    const int all_blocks = (K_eff + UMMA_BK - 1) / UMMA_BK;
+    if (g.kblk_per_part > 0 && kblk0 >= all_blocks) return;     // nothing to add (also K_eff == 0)
+  }
   const float* __restrict__ A = g.A + b * g.stride_a;
   const float* __restrict__ W = g.W + b * g.stride_w;
   const float* __restrict__ bias = g.bias != nullptr ? g.bias + b * g.stride_bias : nullptr;
   float* __restrict__ C = g.C + b * g.stride_c;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == TCG_PRODUCER_WARPS * 32) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full + s, TCG_GROUP_WARPS + (PACKED ? 1 : 0));
-      mbar_init(empty + s, UMMA_ISSUERS);
+  auto init_barriers = [&](bool again) {
+    if (tid == TCG_PRODUCER_WARPS * 32) {
+      for (int s = 0; s < S; ++s) {
+        if (again) { mbar_inval(full + s); mbar_inval(empty + s); }
+        mbar_init(full + s, TCG_GROUP_WARPS + (PACKED ? 1 : 0));
+        mbar_init(empty + s, UMMA_ISSUERS);
+      }
+      if (again) mbar_inval(done);
+      mbar_init(done, UMMA_ISSUERS);
+      fence_mbar_init();
     }
-    mbar_init(done, UMMA_ISSUERS);
-    fence_mbar_init();
-  }
+  };
+  init_barriers(false);
   if (warp == 0) tmem_alloc(tmem_slot, g.tmem_cols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t taddr = *tmem_slot;
-  const int n_blocks = (g.K + UMMA_BK - 1) / UMMA_BK;
+  for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+  const int64_t m0 = (tile / g.tiles_n) * TCG_BM;
+  if (m0 >= M) break;
+  const int n0 = (int)(tile % g.tiles_n) * BN;
+  if (tile != (int64_t)blockIdx.x) {
+    // every barrier of the previous tile has completed its last phase (the epilogue waited for `done`, which the
+    // issuers commit after all MMAs, and the block synchronised): start the next tile from fresh barriers
+    init_barriers(true);
+    __syncthreads();
+  }
+  int n_blocks = (K_eff + UMMA_BK - 1) / UMMA_BK;
+  if (g.kblk_per_part > 0) {
+    n_blocks -= kblk0;
+    n_blocks = n_blocks < g.kblk_per_part ? n_blocks : g.kblk_per_part;
+  }
 #ifdef TIGER_TRACE
   __shared__ long long tr_base_s;
   if (tid == 0) tr_base_s = clock64();
@@ -176,7 +216,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       umma_chunk_pos(wg + TCG_GROUP_WARPS * i, lane, row, kc);
       int64_t m = m0 + row;
       m = m < M ? m : M - 1;
-      ca.ptr[i] = A + m * g.lda + kc * 4;
+      ca.ptr[i] = g.trans_a ? A + m + (int64_t)(kc * 4) * g.lda : A + m * g.lda + kc * 4;
       ca.soff[i] = (kc * TCG_BM + row) * 4;
       ca.kq[i] = kc * 4;
     }
@@ -187,7 +227,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       umma_chunk_pos(wc, lane, row, kc);
       int n = n0 + row;
       n = n < g.N ? n : g.N - 1;
-      cw.ptr[i] = W + (int64_t)n * g.ldw + kc * 4;
+      cw.ptr[i] = g.trans_w ? W + n + (int64_t)(kc * 4) * g.ldw : W + (int64_t)n * g.ldw + kc * 4;
       cw.soff[i] = (wc < (BN >> 3) && !PACKED) ? (kc * BN + row) * 4 : -1;
       cw.kq[i] = kc * 4;
     }
@@ -197,8 +237,13 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     float4 va0[TCG_NA], vw0[NW], va1[TCG_NA], vw1[NW];
     auto load = [&](float4 (&va)[TCG_NA], float4 (&vw)[NW], int blk) {
       if (blk < n_blocks) {
-        umma_chunks_load(va, ca, blk * UMMA_BK, g.K, g.vec_a != 0);
-        if constexpr (!PACKED) umma_chunks_load(vw, cw, blk * UMMA_BK, g.K, g.vec_w != 0);
+        const int k0 = (kblk0 + blk) * UMMA_BK;
+        if (g.trans_a) umma_chunks_load_t(va, ca, k0, K_eff, g.lda);
+        else umma_chunks_load(va, ca, k0, K_eff, g.vec_a != 0);
+        if constexpr (!PACKED) {
+          if (g.trans_w) umma_chunks_load_t(vw, cw, k0, K_eff, g.ldw);
+          else umma_chunks_load(vw, cw, k0, K_eff, g.vec_w != 0);
+        }
       }
     };
     auto publish = [&](const float4 (&va)[TCG_NA], const float4 (&vw)[NW], int blk) {
@@ -256,7 +301,11 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
         v[j] = zero ? 0.f : x;
       }
       float* dst = C + m * g.ldc + nb;
-      if (g.vec_c && nb + 16 <= g.N) {
+      if (g.accumulate) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < g.N) atomicAdd(dst + j, v[j]);
+      } else if (g.vec_c && nb + 16 <= g.N) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -271,7 +320,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     if (lane == 0 && PACKED) {
       const uint32_t bytes = (uint32_t)UMMA_PACK_STAGE_FLOATS(BN) * 4u;
       const float* src = g.wpack + b * g.stride_wpack +
-                         (int64_t)(blockIdx.x % g.tiles_n) * n_blocks * UMMA_PACK_STAGE_FLOATS(BN);
+                         (int64_t)(tile % g.tiles_n) * n_blocks * UMMA_PACK_STAGE_FLOATS(BN);
       for (int blk = 0; blk < n_blocks; ++blk) {
         const int s = blk % S;
         mbar_wait(empty + s, ((blk / S) & 1) ^ 1);
@@ -320,6 +369,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
 #endif
   tc_fence_before_sync();
   __syncthreads();
+  tc_fence_after_sync();
+  }  // tile loop
   if (warp == 0) tmem_dealloc(taddr, g.tmem_cols);
 }
 
@@ -809,6 +860,7 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
     g.vec_sc = ((((uintptr_t)wb->left_vals) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
   }
   g.a_parts = a_parts; g.a_part_stride = a_part_stride; g.a_bias = a_bias; g.a_relu = a_relu;
+  g.trans_a = 0; g.trans_w = 0; g.accumulate = 0; g.k_count = nullptr; g.k_rows_per_count = 1; g.kblk_per_part = 0;
   g.a_ids = nullptr; g.a_sel = nullptr; g.a_sel_i64 = 0; g.a_alt = nullptr; g.a_add = nullptr;
   if (gather != nullptr) {
     g.a_ids = gather->ids; g.a_sel = gather->sel; g.a_sel_i64 = gather->sel_is_i64;
@@ -844,7 +896,8 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   if (stages < 2) return TIGER_EINVAL;
   g.stages = stages;
   const size_t smem = stages * stage_bytes + 256;
-  dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)batch);
+  const int64_t tiles = tiles_m * g.tiles_n;
+  dim3 grid((unsigned)(tiles < sms ? tiles : sms), (unsigned)batch);      // persistent over tiles
   gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
   return tiger_launch_status();
 }
@@ -946,4 +999,56 @@ extern "C" int tiger_sgemm_nt(const float* A, int64_t lda, const float* W, int64
                               int n_cols, int k_dim, int relu, void* stream) {
   return tiger_sgemm_nt_batched(A, lda, 0, W, ldw, 0, bias, 0, C, ldc, 0, 1, m_rows, count, rows_per_count, n_cols,
                                 k_dim, 1.0f, relu, nullptr, stream);
+}
+
+// General product on the unpacked tensor-core kernel:
+//   C[m, n] (+)= act(alpha * (sum_k opA[m, k] * opW[n, k] + bias[n]))
+// opA[m, k] = A[m * lda + k] (trans_a = 0) or A[k * lda + m] (trans_a = 1), opW likewise.  With the three
+// combinations the training step needs no transposed copies: forward y = x W^T (0, 0), input gradient
+// dx = dy W (0, 1), weight gradient dW = dy^T x (1, 1).  `accumulate` adds the tile into C with atomic adds
+// (gradients of a parameter used more than once sum up; bias / relu are not allowed then) and lets the launch
+// split K over `k_parts` CTAs per tile; m_count / k_count bound the row count / the reduction length from
+// device memory (times rows_per_count).
+extern "C" int tiger_sgemm_ex(const float* A, int64_t lda, int trans_a, const float* W, int64_t ldw, int trans_w,
+                              const float* bias, float* C, int64_t ldc, int64_t m_rows, int n_cols, int64_t k_dim,
+                              const int32_t* m_count, const int32_t* k_count, int64_t rows_per_count, float alpha,
+                              int relu, int accumulate, int k_parts, void* stream) {
+  if (A == nullptr || W == nullptr || C == nullptr || m_rows < 0 || n_cols <= 0 || k_dim <= 0 || k_dim > 0x7fffffffll ||
+      ldc < n_cols || (!trans_a && lda < k_dim) || (trans_a && lda < m_rows) || (!trans_w && ldw < k_dim) ||
+      (trans_w && ldw < n_cols) || k_parts < 1 || (accumulate && (bias != nullptr || relu)) ||
+      (!accumulate && (k_parts > 1 || k_count != nullptr)))
+    return TIGER_EINVAL;
+  if (m_rows == 0) return TIGER_OK;
+  const int sms = gemm_sms();
+  if (sms < 0) return TIGER_ECUDA;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.W = W; g.bias = bias; g.C = C; g.count = m_count; g.k_count = k_count;
+  g.lda = lda; g.ldw = ldw; g.ldc = ldc;
+  g.M = m_rows; g.rows_per_count = rows_per_count > 0 ? rows_per_count : 1;
+  g.k_rows_per_count = g.rows_per_count;
+  g.N = n_cols; g.K = (int)k_dim; g.alpha = alpha; g.relu = relu;
+  g.trans_a = trans_a ? 1 : 0; g.trans_w = trans_w ? 1 : 0; g.accumulate = accumulate ? 1 : 0;
+  g.k_parts = 1; g.a_parts = 1; g.sc_period = 1;
+  g.vec_a = (!trans_a && (((uintptr_t)A) & 15) == 0 && (lda & 3) == 0) ? 1 : 0;
+  g.vec_w = (!trans_w && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0) ? 1 : 0;
+  g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
+  const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
+  g.bn = gemm_pick_bn(m_rows, n_cols, accumulate ? k_parts : 1, sms, TCG_MAX_BN);
+  g.tiles_n = (n_cols + g.bn - 1) / g.bn;
+  g.tmem_cols = tmem_cols_pow2((uint32_t)(UMMA_ACCS * g.bn));
+  const size_t stage_bytes = (size_t)(2 * UMMA_KCH * TCG_BM * 4 + 2 * UMMA_KCH * g.bn * 4) * sizeof(float);
+  int stages = (int)(TCG_SMEM_BUDGET / stage_bytes);
+  stages = stages > TCG_MAX_STAGES ? TCG_MAX_STAGES : stages;
+  if (stages < 2) return TIGER_EINVAL;
+  g.stages = stages;
+  const int k_blocks = (int)((k_dim + UMMA_BK - 1) / UMMA_BK);
+  int parts = accumulate ? (k_parts < k_blocks ? k_parts : k_blocks) : 1;
+  g.kblk_per_part = accumulate ? (k_blocks + parts - 1) / parts : 0;
+  if (accumulate) parts = (k_blocks + g.kblk_per_part - 1) / g.kblk_per_part;
+  const int64_t tiles = tiles_m * g.tiles_n;
+  const int64_t per_part = (sms + parts - 1) / parts > 0 ? (sms + parts - 1) / parts : 1;
+  dim3 grid((unsigned)(tiles < per_part ? tiles : per_part), (unsigned)parts);
+  gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, stages * stage_bytes + 256, as_stream(stream)>>>(g);
+  return tiger_launch_status();
 }

@@ -24,6 +24,9 @@ __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint3
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
 }
@@ -284,6 +287,26 @@ __device__ __forceinline__ void umma_chunks_load(float4 (&v)[N], const UmmaChunk
       }
       v[i] = t;
     }
+  }
+}
+
+// transposed operand: the chunk (row, k .. k+3) is read from base[(k + j) * ld + row]; c.ptr holds
+// base + row + kq * ld.  Eight lanes (rows) share a 32-byte sector per k, so the reads stay sector-efficient.
+template <int N>
+__device__ __forceinline__ void umma_chunks_load_t(float4 (&v)[N], const UmmaChunks<N>& c, int k0, int k_end,
+                                                   int64_t ld) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.soff[i] >= 0) {
+      const int k = k0 + c.kq[i];
+      const float* p = c.ptr[i] + (int64_t)k0 * ld;
+      if (k < k_end) t.x = __ldg(p);
+      if (k + 1 < k_end) t.y = __ldg(p + ld);
+      if (k + 2 < k_end) t.z = __ldg(p + 2 * ld);
+      if (k + 3 < k_end) t.w = __ldg(p + 3 * ld);
+    }
+    v[i] = t;
   }
 }
 

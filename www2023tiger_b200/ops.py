@@ -447,6 +447,20 @@ def sgemm_nt(a: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, *, m_row
     return out
 
 
+def sgemm_ex(a: Tensor, w: Tensor, out: Tensor, *, m: int, n: int, k: int, trans_a: bool = False,
+             trans_w: bool = False, bias: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0,
+             accumulate: bool = False, k_parts: int = 1, m_count: Optional[Tensor] = None,
+             k_count: Optional[Tensor] = None, rows_per_count: int = 1) -> Tensor:
+    """out[m, n] (+)= act(alpha * (opA @ opW.T + bias)); opA = a[:m, :k] or a[:k, :m].T (trans_a), opW = w[:n, :k] or
+    w[:k, :n].T (trans_w).  forward y = x W^T: (False, False); input gradient dx = dy W: (False, True); weight
+    gradient dW = dy^T x: (True, True).  `accumulate` adds into `out` (atomic adds; K split over k_parts CTAs)."""
+    check_cuda_strided(a, w, out)
+    call('tiger_sgemm_ex', ptr(a), a.stride(0), int(trans_a), ptr(w), w.stride(0), int(trans_w), ptr(bias), ptr(out),
+         out.stride(0), m, n, k, ptr(m_count), ptr(k_count), rows_per_count, float(alpha), int(relu), int(accumulate),
+         k_parts)
+    return out
+
+
 class WeightPack:
     """tf32 head / tail pack of a weight [N, K] for the tensor-core GEMM (tiger_gemm_pack_weight)."""
 
