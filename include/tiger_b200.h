@@ -480,6 +480,51 @@ int tiger_pipe_submit(void* pipe, int slot, const void* src, void* d_in, int64_t
 int tiger_pipe_wait(void* pipe, int slot, int host_results);
 int tiger_pipe_join(void* pipe, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Training step (csrc/train.cu): forward pieces that keep what backward needs and the hand-written backward of
+ * TIGER.contrast_and_mutual_learning (tiger/model/tiger.py:547-592) - what loss.backward() / optimizer.step() of
+ * train_self_supervised.py:165-171 and train_self_supervised_ddp.py:203-208 run through autograd.  Dense products
+ * go through tiger_sgemm_ex; gradients accumulate into caller-owned buffers that tiger_train_adam zeroes.
+ *   gather_pending / gru_gates[_bwd]   compute_messages + GRUUpdater (tiger.py:292-356, update_modules.py:30-37)
+ *   attn_build[_bwd] / attn_core[_bwd] compute_embedding_with_computation_graph + TemporalAttention with dropout
+ *                                      (temporal_agg_modules.py:29-83,210-235), TimeEncode gradients
+ *   score_build[_bwd] / score_head[_bwd] hit embedding + score_fn + BCE (tiger.py:259-288)
+ *   mse                                 mutual loss over valid rows (tiger.py:583-590)
+ *   colsum / relu_bwd / zero_rows / scatter_add_rows   bias gradients, ReLU, masked rows, nn.Embedding gradients
+ *   adam                                torch.optim.Adam defaults (train_self_supervised.py:116) on a flat buffer
+ * --------------------------------------------------------------------------------------------------------- */
+int tiger_train_gather_pending(const int64_t* ids, const int32_t* count, int64_t cap, const float* msg_vals, int m_dim, const float* msg_ts, const float* upd_vals, int d, const float* check_mem_ts, int check_equal, float* X, float* H, float* dh_zero, uint32_t* err_flags, void* stream);
+int tiger_train_gru_gates(const float* Gi, const float* Gh, const float* H, const int32_t* count, int64_t cap, int d, float* h_new, float* r_out, float* z_out, float* n_out, void* stream);
+int tiger_train_gru_gates_bwd(const float* dh, const float* r_in, const float* z_in, const float* n_in, const float* Gh, const float* H, const int32_t* count, int64_t cap, int d, float* dGi, float* dGh, void* stream);
+int tiger_train_attn_build(const int64_t* center, int64_t n_q, const float* ts, int64_t batch, const int64_t* neigh_nids, const int64_t* neigh_eids, const float* neigh_ts, int k, const float* rows_a, const float* rows_b, const int32_t* sel, const float* nfeats, const float* efeats, int d, int de, const float* time_w, const float* time_b, float* q_in, float* kv_in, float* cat, int64_t ld_cat, int cat_off, void* stream);
+int tiger_train_attn_core(const float* Q, int64_t ldq, const float* Kp, const float* Vp, int64_t ldkv, const int64_t* neigh_nids, int64_t n_q, int k, int n_head, int head_dim, float p_drop, int seed, float* attn, int64_t ld_attn, float* P, uint32_t* keep_bits, uint8_t* empty, void* stream);
+int tiger_train_attn_core_bwd(const float* dattn, int64_t ld_attn, const float* Q, int64_t ldq, const float* Kp, const float* Vp, int64_t ldkv, const float* P, const uint32_t* keep_bits, int64_t n_q, int k, int n_head, int head_dim, float p_drop, float* dQ, float* dKp, float* dVp, void* stream);
+int tiger_train_attn_build_bwd(const float* dkv_in, const float* dq_in, const float* dcat, int64_t ld_cat, int cat_off, const int64_t* center, int64_t n_q, const float* ts, int64_t batch, const int64_t* neigh_nids, const float* neigh_ts, int k, const int32_t* sel, int d, int de, const float* time_w, const float* time_b, float* dh_new, float* g_time_w, float* g_time_b, void* stream);
+int tiger_train_zero_rows(float* buf, int64_t ld, int cols, int64_t n_rows, const uint8_t* flag, void* stream);
+int tiger_train_relu_bwd(float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int cols, int64_t n_rows, const int32_t* count, int64_t rows_per_count, float scale, void* stream);
+int tiger_train_colsum(const float* X, int64_t ld, int64_t n_rows, const int32_t* count, int64_t rows_per_count, int cols, float scale, float* out, void* stream);
+int tiger_train_scatter_add_rows(float* table, const int64_t* ids, int64_t n, const int32_t* count, int64_t rows_per_count, const float* src, int64_t ld_src, int width, float scale, void* stream);
+int tiger_train_score_build(const float* z, const float* hits, int k, const float* hit_emb, int64_t batch, int d, float* pair, uint8_t* codes, void* stream);
+int tiger_train_score_head(float* hid, const float* fc2_w, const float* fc2_b, int64_t batch, int d, float p_drop, int seed, float* scores, float* loss, float* dscore, void* stream);
+int tiger_train_score_head_bwd(const float* dscore, float g, const float* hid, const float* fc2_w, int64_t batch, int d, float p_drop, float* dhid, float* g_fc2_w, float* g_fc2_b, void* stream);
+int tiger_train_score_build_bwd(const float* dpair, const uint8_t* codes, int64_t batch, int d, float* dz, float* g_hit_emb, void* stream);
+int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev_left, const float* hprev_right, const int64_t* index, const int32_t* count, int64_t n, int d, float* loss, float* dpred_l, float* dpred_r, void* stream);
+int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale, int zero_grad, void* stream);
+
+
+/* Seq-restarter training step (csrc/train_seq.cu): SeqRestarter.forward under autograd (restarters.py:51-114 as
+ * called from tiger.py:574-590) - L x L self-attention per (node, head) with dropout, folded through the mean over
+ * positions (exact by linearity), forward and backward; value-bias term, token gradients (anony_emb, TimeEncode),
+ * dropout, axpy. */
+int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* P, float* pbar, float* psum, float* xbar, void* stream);
+int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, const float* x, const float* qk, int64_t ld_qk, const float* P, const float* pbar, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* dX, float* dqk, void* stream);
+int tiger_train_seq_vbias(float* att, const float* psum, const float* bv, int64_t n, int d_model, int n_head, void* stream);
+int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, const float* bv, int64_t n, int d_model, int n_head, float* g_bv, float* dpsum, void* stream);
+int tiger_train_seq_tokens_bwd(const float* dX, int64_t n, int len, const int64_t* anony_ids, const float* hist_ts, int d, int de, const float* time_w, const float* time_b, float* g_anony_emb, float* g_time_w, float* g_time_b, void* stream);
+int tiger_train_dropout(float* x, int64_t n, float p_drop, int seed, int stream_id, void* stream);
+int tiger_train_axpy(float* y, const float* x, int64_t n, float alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

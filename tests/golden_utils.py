@@ -7,7 +7,8 @@ import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 _ALL = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-CASES = [c for c in _ALL if not c.startswith('full_')]          # toy-size fixtures (make_golden.py)
+CASES = [c for c in _ALL if not c.startswith(('full_', 'train_'))]   # toy-size fixtures (make_golden.py)
+TRAIN_CASES = [c for c in _ALL if c.startswith('train_')]       # training-step fixtures (make_golden_train.py)
 FULL_CASES = [c for c in _ALL if c.startswith('full_')]         # BASELINE-dimension fixtures (make_golden_full.py)
 
 

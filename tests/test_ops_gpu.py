@@ -518,8 +518,8 @@ def test_sgemm_ex_weight_gradient_accumulates_with_device_count(rows, count):
     dW = torch.randn(n_out, n_in, device='cuda', generator=g)
     base = dW.clone()
     cnt = torch.tensor([count], dtype=torch.int32, device='cuda')
-    ops.sgemm_ex(dY, X, dW, m=n_out, n=n_in, k=rows, trans_a=True, trans_w=True, accumulate=True, k_parts=16,
-                 k_count=cnt)
+    ops.sgemm_ex(dY, X, dW, m=n_out, n=n_in, k=rows, trans_a=True, trans_w=True, accumulate=True,
+                 k_parts=max(1, min(64, (rows + 511) // 512)), k_count=cnt)
     want = base.double() + dY[:count].double().t() @ X[:count].double()
     assert_close(dW.cpu().numpy(), want.cpu().numpy(), 2e-6, f'wgrad rows={rows} count={count}')
 

@@ -62,6 +62,30 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_min_time': 'plp' + 'p',
     'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
     'tiger_sgemm_nt': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
+    'tiger_train_gather_pending': 'pplpippipippppp',
+    'tiger_train_gru_gates': 'pppplippppp',
+    'tiger_train_gru_gates_bwd': 'ppppppplippp',
+    'tiger_train_attn_build': 'plplpppipppppiippppplip',
+    'tiger_train_attn_core': 'plpplpliiifiplpppp',
+    'tiger_train_attn_core_bwd': 'plplpplppliiifpppp',
+    'tiger_train_attn_build_bwd': 'pppliplplppipiipppppp',
+    'tiger_train_zero_rows': 'plilpp',
+    'tiger_train_relu_bwd': 'plplilplfp',
+    'tiger_train_colsum': 'pllplifpp',
+    'tiger_train_scatter_add_rows': 'pplplplifp',
+    'tiger_train_score_build': 'ppiplippp',
+    'tiger_train_score_head': 'ppplifipppp',
+    'tiger_train_score_head_bwd': 'pfpplifpppp',
+    'tiger_train_score_build_bwd': 'pplippp',
+    'tiger_train_mse': 'pppppplipppp',
+    'tiger_train_adam': 'pppplfffflfip',
+    'tiger_train_seq_pool': 'plppliiifippppp',
+    'tiger_train_seq_pool_bwd': 'pppplppliiifippp',
+    'tiger_train_seq_vbias': 'pppliip',
+    'tiger_train_seq_vbias_bwd': 'pppliippp',
+    'tiger_train_seq_tokens_bwd': 'plippiipppppp',
+    'tiger_train_dropout': 'plfiip',
+    'tiger_train_axpy': 'pplfp',
     'tiger_sgemm_ex': 'pli' + 'pli' + 'ppl' + 'lil' + 'ppl' + 'fiii' + 'p',
     'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_gemm_pick_bn': 'lii',

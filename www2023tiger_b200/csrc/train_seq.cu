@@ -1,0 +1,415 @@
+// Training step of the seq restarter (SeqRestarter.forward, tiger/model/restarters.py:51-114, under autograd in
+// TIGER.contrast_and_mutual_learning, tiger/model/tiger.py:574-590): the attention pieces between the tensor-core
+// products, forward with dropout and backward.
+//
+// The forward keeps the folding of csrc/restart_seq.cu, which stays exact under dropout because everything between
+// the attention probabilities and the first non-linearity is linear:
+//   mean_i out_i = W_o [ concat_h ( W_v,h xbar_h + b_v,h psum_h ) ] + b_o,
+//   xbar_h = sum_j pbar_hj x_j,   pbar_hj = mean_i P'_h,ij  (P' = dropout(softmax)),   psum_h = sum_j pbar_hj
+// (psum_h = 1 without dropout).  Only the q / k in-projection runs on all n * L tokens.
+#include "common.cuh"
+
+__device__ __forceinline__ uint32_t seq_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool seq_keep(uint32_t seed, uint32_t stream, uint32_t idx, float p) {
+  if (p <= 0.f) return true;
+  const uint32_t h = seq_mix32(idx ^ seq_mix32(seed + 0x9E3779B9u * (stream + 1u)));
+  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p;
+}
+__device__ __forceinline__ float seq_sin_reduced(float x) {
+  const double xd = (double)x;
+  const double n = rint(xd * 0.15915494309189535);
+  double r = fma(-n, 6.283185307179586, xd);
+  r = fma(-n, 2.4492935982947064e-16, r);
+  return sinf((float)r);
+}
+
+#define SP_THREADS 256
+#define SP_CW 32
+#define SP_MAXL 64
+#define SP_MAXP ((SP_MAXL * SP_MAXL + SP_THREADS - 1) / SP_THREADS)
+
+// ------------------------------------------------------------------------------------------
+// forward: per (node, head) L x L scores, key-padding mask, softmax, dropout, mean over the query positions,
+// pooled tokens.  Keeps P (softmax output) [n, H, L, L], pbar [n, H, L], psum [n, H].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SP_THREADS)
+train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ x,
+                      const uint8_t* __restrict__ mask, int64_t n, int len, int dm, int n_head, float p_drop,
+                      uint32_t seed, float* __restrict__ P, float* __restrict__ pbar_out, float* __restrict__ psum_out,
+                      float* __restrict__ xbar) {
+  __shared__ float qs[SP_MAXL][SP_CW + 1];
+  __shared__ float ks[SP_MAXL][SP_CW + 1];
+  __shared__ float sc[SP_MAXL][SP_MAXL + 1];
+  __shared__ float pbar[SP_MAXL];
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
+  const int hd = dm / n_head;
+  const float scale = sqrtf(1.0f / (float)hd);
+  const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const int n_pairs = len * len;
+  const int64_t total = n * n_head;
+  for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const int64_t i = item / n_head;
+    const int h = (int)(item % n_head);
+    const float* qbase = qk + i * len * ld_qk + h * hd;
+    const float* kbase = qbase + dm;
+    float acc[SP_MAXP];
+#pragma unroll
+    for (int r = 0; r < SP_MAXP; ++r) acc[r] = 0.f;
+    for (int c0 = 0; c0 < hd; c0 += SP_CW) {
+      const int cw = (hd - c0) < SP_CW ? (hd - c0) : SP_CW;
+      __syncthreads();
+      for (int e = tid; e < len * SP_CW; e += SP_THREADS) {
+        const int j = e / SP_CW, c = e % SP_CW;
+        float qv = 0.f, kv = 0.f;
+        if (c < cw) {
+          qv = qbase[(int64_t)j * ld_qk + c0 + c] * scale;
+          kv = kbase[(int64_t)j * ld_qk + c0 + c];
+        }
+        qs[j][c] = qv;
+        ks[j][c] = kv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < SP_MAXP; ++r) {
+        const int p = tid + r * SP_THREADS;
+        if (p < n_pairs) {
+          const int j = p / len, i2 = p % len;
+          float s = acc[r];
+#pragma unroll 8
+          for (int c = 0; c < SP_CW; ++c) s = fmaf(qs[j][c], ks[i2][c], s);
+          acc[r] = s;
+        }
+      }
+    }
+    const uint8_t* mrow = mask + i * len;
+#pragma unroll
+    for (int r = 0; r < SP_MAXP; ++r) {
+      const int p = tid + r * SP_THREADS;
+      if (p < n_pairs) {
+        const int j = p / len, i2 = p % len;
+        sc[j][i2] = mrow[i2] ? -INFINITY : acc[r];
+      }
+    }
+    __syncthreads();
+    float* Pout = P + item * n_pairs;
+    for (int j = warp; j < len; j += SP_THREADS / 32) {
+      float m = -INFINITY;
+      for (int c = lane; c < len; c += 32) m = fmaxf(m, sc[j][c]);
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int c = lane; c < len; c += 32) {
+        const float e = expf(sc[j][c] - m);
+        sc[j][c] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      for (int c = lane; c < len; c += 32) {
+        const float p = sc[j][c] / sum;
+        Pout[j * len + c] = p;
+        sc[j][c] = seq_keep(seed, 3u, (uint32_t)(item * n_pairs + j * len + c), p_drop) ? p * inv_keep : 0.f;
+      }
+    }
+    __syncthreads();
+    if (tid < len) {
+      float s = 0.f;
+      for (int j = 0; j < len; ++j) s += sc[j][tid];
+      s = s / (float)len;
+      pbar[tid] = s;
+      pbar_out[item * len + tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int j = 0; j < len; ++j) s += pbar[j];
+      psum_out[item] = s;
+    }
+    const float* xrow = x + i * len * (int64_t)dm;
+    float* orow = xbar + (i * n_head + h) * (int64_t)dm;
+    for (int c = tid; c < dm; c += SP_THREADS) {
+      float s = 0.f;
+      for (int j = 0; j < len; ++j) s = fmaf(pbar[j], xrow[(int64_t)j * dm + c], s);
+      orow[c] = s;
+    }
+  }
+}
+
+extern "C" int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask, int64_t n,
+                                    int len, int d_model, int n_head, float p_drop, int seed, float* P, float* pbar,
+                                    float* psum, float* xbar, void* stream) {
+  if (qk == nullptr || x == nullptr || mask == nullptr || P == nullptr || pbar == nullptr || psum == nullptr ||
+      xbar == nullptr || n < 0 || len <= 0 || len > SP_MAXL || d_model <= 0 || n_head <= 0 || d_model % n_head != 0 ||
+      ld_qk < 2 * (int64_t)d_model || p_drop < 0.f || p_drop >= 1.f)
+    return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  int64_t grid = n * n_head;
+  if (grid > 148 * 4) grid = 148 * 4;
+  train_seq_pool_kernel<<<(unsigned)grid, SP_THREADS, 0, as_stream(stream)>>>(qk, ld_qk, x, mask, n, len, d_model, n_head,
+                                                                             p_drop, (uint32_t)seed, P, pbar, psum, xbar);
+  return tiger_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: one CTA per node (both heads in turn, so that the token gradient of the value path is written once).
+//   dpbar_j = dxbar_h . x_j + dpsum_h          dX_j  = sum_h pbar_hj dxbar_h        (value path)
+//   dP'_ij  = dpbar_j / L,  dP_ij = dP'_ij keep_ij / (1 - p),  dS_ij = P_ij (dP_ij - sum_l P_il dP_il)
+//   dQ_i = scale sum_j dS_ij K_j,   dK_j = scale sum_i dS_ij Q_i
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SP_THREADS)
+train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restrict__ dpsum, const float* __restrict__ x,
+                          const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ P,
+                          const float* __restrict__ pbar, int64_t n, int len, int dm, int n_head, float p_drop,
+                          uint32_t seed, float* __restrict__ dX, float* __restrict__ dqk) {
+  __shared__ float ds[SP_MAXL][SP_MAXL + 1];
+  __shared__ float dpb[SP_MAXL];
+  __shared__ float pb[4][SP_MAXL];          // pbar of up to 4 heads
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
+  const int hd = dm / n_head;
+  const float scale = sqrtf(1.0f / (float)hd);
+  const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const int n_pairs = len * len;
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const float* xrow = x + i * len * (int64_t)dm;
+    __syncthreads();
+    for (int e = tid; e < n_head * len; e += SP_THREADS) pb[e / len][e % len] = pbar[(i * n_head) * len + e];
+    __syncthreads();
+    // value path: dX_j = sum_h pbar_hj dxbar_h
+    for (int c = tid; c < dm; c += SP_THREADS) {
+      float g[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) g[h] = h < n_head ? dxbar[(i * n_head + h) * (int64_t)dm + c] : 0.f;
+      for (int j = 0; j < len; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          if (h < n_head) s = fmaf(pb[h][j], g[h], s);
+        dX[(i * len + j) * (int64_t)dm + c] = s;
+      }
+    }
+    for (int h = 0; h < n_head; ++h) {
+      const int64_t item = i * n_head + h;
+      const float* gx = dxbar + item * (int64_t)dm;
+      __syncthreads();
+      for (int j = warp; j < len; j += SP_THREADS / 32) {
+        float s = 0.f;
+        for (int c = lane; c < dm; c += 32) s = fmaf(gx[c], xrow[(int64_t)j * dm + c], s);
+        s = warp_sum(s);
+        if (lane == 0) dpb[j] = (s + dpsum[item]) / (float)len;
+      }
+      __syncthreads();
+      const float* Pin = P + item * n_pairs;
+      for (int q = warp; q < len; q += SP_THREADS / 32) {          // one warp per query row
+        float dot = 0.f;
+        for (int c = lane; c < len; c += 32) {
+          const bool keep = seq_keep(seed, 3u, (uint32_t)(item * n_pairs + q * len + c), p_drop);
+          const float dp = keep ? dpb[c] * inv_keep : 0.f;
+          const float p = Pin[q * len + c];
+          ds[q][c] = dp;
+          dot = fmaf(p, dp, dot);
+        }
+        dot = warp_sum(dot);
+        for (int c = lane; c < len; c += 32) ds[q][c] = Pin[q * len + c] * (ds[q][c] - dot) * scale;
+      }
+      __syncthreads();
+      const float* qbase = qk + i * len * ld_qk + h * hd;
+      const float* kbase = qbase + dm;
+      float* dqbase = dqk + i * len * ld_qk + h * hd;
+      float* dkbase = dqbase + dm;
+      for (int c = tid; c < hd; c += SP_THREADS) {
+        float qc[SP_MAXL], kc[SP_MAXL];
+#pragma unroll
+        for (int j = 0; j < SP_MAXL; ++j)
+          if (j < len) {
+            qc[j] = qbase[(int64_t)j * ld_qk + c];
+            kc[j] = kbase[(int64_t)j * ld_qk + c];
+          }
+#pragma unroll 1
+        for (int q = 0; q < len; ++q) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < SP_MAXL; ++j)
+            if (j < len) s = fmaf(ds[q][j], kc[j], s);
+          dqbase[(int64_t)q * ld_qk + c] = s;
+        }
+#pragma unroll 1
+        for (int j = 0; j < len; ++j) {
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < SP_MAXL; ++q)
+            if (q < len) s = fmaf(ds[q][j], qc[q], s);
+          dkbase[(int64_t)j * ld_qk + c] = s;
+        }
+      }
+    }
+  }
+}
+
+extern "C" int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, const float* x, const float* qk,
+                                        int64_t ld_qk, const float* P, const float* pbar, int64_t n, int len,
+                                        int d_model, int n_head, float p_drop, int seed, float* dX, float* dqk,
+                                        void* stream) {
+  if (dxbar == nullptr || dpsum == nullptr || x == nullptr || qk == nullptr || P == nullptr || pbar == nullptr ||
+      dX == nullptr || dqk == nullptr || n < 0 || len <= 0 || len > SP_MAXL || d_model <= 0 || n_head <= 0 ||
+      n_head > 4 || d_model % n_head != 0 || ld_qk < 2 * (int64_t)d_model)
+    return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  int64_t grid = n < 148 * 4 ? n : 148 * 4;
+  train_seq_pool_bwd_kernel<<<(unsigned)grid, SP_THREADS, 0, as_stream(stream)>>>(
+      dxbar, dpsum, x, qk, ld_qk, P, pbar, n, len, d_model, n_head, p_drop, (uint32_t)seed, dX, dqk);
+  return tiger_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// value-projection bias under dropout: att[r, h*hd + c] += psum[r, h] * b_v[h*hd + c]; backward:
+// g_bv[h*hd + c] += sum_r psum[r, h] datt[r, h*hd + c],  dpsum[r, h] = sum_c datt[r, h*hd + c] b_v[h*hd + c]
+// ------------------------------------------------------------------------------------------
+__global__ void train_seq_vbias_kernel(float* __restrict__ att, const float* __restrict__ psum,
+                                       const float* __restrict__ bv, int64_t n, int dm, int n_head) {
+  const int hd = dm / n_head;
+  const int64_t total = n * dm;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dm;
+    const int c = (int)(i % dm);
+    att[i] += psum[r * n_head + c / hd] * bv[c];
+  }
+}
+
+extern "C" int tiger_train_seq_vbias(float* att, const float* psum, const float* bv, int64_t n, int d_model, int n_head,
+                                     void* stream) {
+  if (att == nullptr || psum == nullptr || bv == nullptr || n < 0 || d_model <= 0 || n_head <= 0) return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  int64_t grid = (n * d_model + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  train_seq_vbias_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(att, psum, bv, n, d_model, n_head);
+  return tiger_launch_status();
+}
+
+__global__ void __launch_bounds__(256)
+train_seq_vbias_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ psum, const float* __restrict__ bv,
+                           int64_t n, int dm, int n_head, float* __restrict__ g_bv, float* __restrict__ dpsum) {
+  // one warp per (row, head) for dpsum; the bias gradient is accumulated by a second pass of column owners
+  const int hd = dm / n_head;
+  const int lane = lane_id();
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block(); item < n * n_head; item += n_warps) {
+    const int64_t r = item / n_head;
+    const int h = (int)(item % n_head);
+    const float* g = datt + r * dm + h * hd;
+    const float* b = bv + h * hd;
+    float s = 0.f;
+    for (int c = lane; c < hd; c += 32) s = fmaf(g[c], b[c], s);
+    s = warp_sum(s);
+    if (lane == 0) dpsum[item] = s;
+  }
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < dm; c += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(c / hd);
+    float s = 0.f;
+    for (int64_t r = 0; r < n; ++r) s = fmaf(psum[r * n_head + h], datt[r * dm + c], s);
+    atomicAdd(g_bv + c, s);
+  }
+}
+
+extern "C" int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, const float* bv, int64_t n, int d_model,
+                                         int n_head, float* g_bv, float* dpsum, void* stream) {
+  if (datt == nullptr || psum == nullptr || bv == nullptr || g_bv == nullptr || dpsum == nullptr || n < 0 ||
+      d_model <= 0 || n_head <= 0)
+    return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  int64_t grid = (n * n_head + 7) / 8;
+  const int64_t need = (d_model + 255) / 256;
+  if (grid < need) grid = need;
+  if (grid > 148 * 4) grid = 148 * 4;
+  train_seq_vbias_bwd_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(datt, psum, bv, n, d_model, n_head, g_bv,
+                                                                           dpsum);
+  return tiger_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// token gradients (restarters.py:96-104): columns [2d, 3d) are rows of anony_emb, columns [3d + de, 4d + de) the
+// time code cos((t_last - t_j) w + b); the last position keeps only its time code.  One warp per token.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+train_seq_tokens_bwd_kernel(const float* __restrict__ dX, int64_t n, int len, const int64_t* __restrict__ anony_ids,
+                            const float* __restrict__ hist_ts, int d, int de, const float* __restrict__ time_w,
+                            const float* __restrict__ time_b, float* __restrict__ g_anony, float* __restrict__ g_w,
+                            float* __restrict__ g_b) {
+  extern __shared__ float acc_smem[];          // [2][d]
+  float* s_w = acc_smem;
+  float* s_b = acc_smem + d;
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) acc_smem[c] = 0.f;
+  __syncthreads();
+  const int lane = lane_id();
+  const int64_t dm = 4 * (int64_t)d + de;
+  const int64_t total = n * len;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block(); r < total; r += n_warps) {
+    const int64_t i = r / len;
+    const int j = (int)(r % len);
+    const float* g = dX + r * dm;
+    if (j != len - 1) {
+      float* ga = g_anony + anony_ids[r] * d;
+      for (int c = lane; c < d; c += 32) {
+        const float v = g[2 * d + c];
+        if (v != 0.f) atomicAdd(ga + c, v);
+      }
+    }
+    const float dt = hist_ts[i * len + len - 1] - hist_ts[r];
+    for (int c = lane; c < d; c += 32) {
+      const float v = -seq_sin_reduced(__fadd_rn(__fmul_rn(dt, time_w[c]), time_b[c])) * g[3 * d + de + c];
+      atomicAdd(s_w + c, v * dt);
+      atomicAdd(s_b + c, v);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    if (s_w[c] != 0.f) atomicAdd(g_w + c, s_w[c]);
+    if (s_b[c] != 0.f) atomicAdd(g_b + c, s_b[c]);
+  }
+}
+
+extern "C" int tiger_train_seq_tokens_bwd(const float* dX, int64_t n, int len, const int64_t* anony_ids,
+                                          const float* hist_ts, int d, int de, const float* time_w, const float* time_b,
+                                          float* g_anony_emb, float* g_time_w, float* g_time_b, void* stream) {
+  if (dX == nullptr || anony_ids == nullptr || hist_ts == nullptr || time_w == nullptr || time_b == nullptr ||
+      g_anony_emb == nullptr || g_time_w == nullptr || g_time_b == nullptr || n < 0 || len <= 0 || d <= 0 || de <= 0)
+    return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  int64_t grid = (n * len + 7) / 8;
+  if (grid > 148 * 2) grid = 148 * 2;
+  train_seq_tokens_bwd_kernel<<<(unsigned)grid, 256, 2 * d * sizeof(float), as_stream(stream)>>>(
+      dX, n, len, anony_ids, hist_ts, d, de, time_w, time_b, g_anony_emb, g_time_w, g_time_b);
+  return tiger_launch_status();
+}
+
+// x[i] = keep(i) ? x[i] / (1 - p) : 0 in place (nn.Dropout in training mode; MergeLayer, basic_modules.py:16-19)
+__global__ void train_dropout_kernel(float* __restrict__ x, int64_t n, float p, uint32_t seed, uint32_t stream_id) {
+  const float inv_keep = 1.0f / (1.0f - p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = seq_keep(seed, stream_id, (uint32_t)i, p) ? x[i] * inv_keep : 0.f;
+}
+
+extern "C" int tiger_train_dropout(float* x, int64_t n, float p_drop, int seed, int stream_id, void* stream) {
+  if (x == nullptr || n < 0 || p_drop < 0.f || p_drop >= 1.f) return TIGER_EINVAL;
+  if (n == 0 || p_drop == 0.f) return TIGER_OK;
+  int64_t grid = (n + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  train_dropout_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(x, n, p_drop, (uint32_t)seed, (uint32_t)stream_id);
+  return tiger_launch_status();
+}
+
+// y[i] += alpha * x[i]
+__global__ void train_axpy_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n, float alpha) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(alpha, x[i], y[i]);
+}
+
+extern "C" int tiger_train_axpy(float* y, const float* x, int64_t n, float alpha, void* stream) {
+  if (y == nullptr || x == nullptr || n < 0) return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  int64_t grid = (n + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  train_axpy_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(y, x, n, alpha);
+  return tiger_launch_status();
+}

@@ -18,7 +18,7 @@ class MergeLayer(nn.Module):
 
     def forward(self, x1, x2):
         x = torch.cat([x1, x2], dim=-1)
-        if use_kernel() and x.is_cuda and x.dim() == 2:
+        if use_kernel(self) and x.is_cuda and x.dim() == 2:
             x = f32c(x)
             hid = torch.empty(x.shape[0], self.fc1.out_features, device=x.device)
             out = torch.empty(x.shape[0], self.fc2.out_features, device=x.device)

@@ -38,6 +38,7 @@ class SeqRestarter(Restarter):
         super().__init__(raw_feat_getter, graph)
         self.hist_len = hist_len
         self.n_head = n_head
+        self.dropout = dropout
         self.anony_emb = nn.Embedding(hist_len + 1, self.nfeat_dim)
         self.d_model = self.nfeat_dim * 3 + self.efeat_dim + self.tfeat_dim
         self.mha_fn = nn.MultiheadAttention(self.d_model, n_head, dropout)
@@ -70,7 +71,7 @@ class SeqRestarter(Restarter):
             r = computation_graph.restart_data
             hn, he, ht, hd, an = r.hist_nids, r.hist_eids, r.hist_ts, r.hist_dirs, r.anonymized_ids
         n = nids.numel()
-        if use_kernel() and hn.is_cuda:
+        if use_kernel(self) and hn.is_cuda:
             op = self._operator(n, hn.device)
             fg = self.raw_feat_getter
             hl, hr, pt = op.forward(nids.contiguous(), n, fg.nfeats, fg.efeats,

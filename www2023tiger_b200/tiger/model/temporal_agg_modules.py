@@ -49,7 +49,7 @@ class TemporalAttention(nn.Module):
 
     def forward(self, qx: Tensor, qt: Tensor, kx: Tensor, ky: Tensor, kt: Tensor, padding_mask: Tensor) -> Tensor:
         """qx [n,d] qt [n,d] kx [n,len,d] ky [n,len,de] kt [n,len,d]; padding_mask [n,len], True = padding."""
-        if use_kernel() and qx.is_cuda:
+        if use_kernel(self) and qx.is_cuda:
             return ops.temporal_attention_dense(self.packed(), self.n_head, f32c(qx), f32c(qt), f32c(kx), f32c(ky),
                                                 f32c(kt), padding_mask)
         query = torch.cat([qx, qt], 1).unsqueeze(0)
@@ -82,7 +82,7 @@ class GraphEmbedding(nn.Module):
         (`involved_node_reprs[computation_graph.local_index[u]]`)."""
         depth = self.n_layers if depth is None else depth
         cg = computation_graph
-        if depth == 1 and use_kernel() and involved_node_reprs.is_cuda and hasattr(self, 'fns'):
+        if depth == 1 and use_kernel(self) and involved_node_reprs.is_cuda and hasattr(self, 'fns'):
             nn_, ne_, nt_ = cg.layers[1]
             fn = self.fns[self.n_layers - 1]
             return ops.temporal_attention(fn.packed(self.time_encoder), fn.n_head, center_nids.contiguous(), f32c(ts),

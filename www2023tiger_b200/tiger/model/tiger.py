@@ -29,6 +29,26 @@ from .update_modules import GRUUpdater, MergeUpdater
 from .utils import select_latest_nids
 
 
+class _NativeStep(torch.autograd.Function):
+    """TIGER.contrast_and_mutual_learning as ONE autograd node: forward and backward are the hand-written training
+    step of www2023tiger_b200/train.py (no torch autograd graph in between), the parameters are its differentiable
+    inputs, so `loss.backward()`, torch optimizers and DistributedDataParallel (which hooks the parameters' gradient
+    accumulation) work unchanged on top of it."""
+
+    @staticmethod
+    def forward(ctx, trainer, batch, contrast_only, *params):
+        closs, mloss = trainer.forward(*batch, contrast_only=contrast_only, train=True)
+        ctx.trainer = trainer
+        return closs[0].clone(), mloss[0].clone()
+
+    @staticmethod
+    def backward(ctx, g_contrast, g_mutual):
+        tr = ctx.trainer
+        tr.fp.grad.zero_()                      # autograd accumulates what this node returns into p.grad itself
+        tr.backward(float(g_contrast), float(g_mutual))
+        return (None, None, None) + tuple(tr.fp.g[n].clone() for n in tr.fp.names)
+
+
 class _Workspace:
     """Per-batch device scratch of the fused route (sized for batch B, K neighbors)."""
 
@@ -60,6 +80,7 @@ class TIGE(nn.Module):
         self.memory_dim = self.nfeat_dim
         self.raw_msg_dim = self.memory_dim * 2 + self.efeat_dim + self.tfeat_dim
         self.n_neighbors, self.n_layers = n_neighbors, n_layers
+        self.dropout = dropout
         self.msg_src, self.upd_src = msg_src, upd_src
         if not msg_last_only:
             raise NotImplementedError('only msg_last_only=True (the reference CLI default) is implemented')
@@ -191,7 +212,7 @@ class TIGE(nn.Module):
                           computation_graph) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
         """-> (contrast_loss, h_left [2B,d], pos_scores [B], neg_scores [B], h_prev_left, h_prev_right)."""
         cg = computation_graph
-        if use_kernel() and self._fusable():
+        if use_kernel(self) and self._fusable():
             return self._contrast_learning_fused(src_ids, dst_ids, neg_dst_ids, ts, eids, cg)
         bs = len(src_ids)
         pos_ids = torch.cat([src_ids, dst_ids])
@@ -326,6 +347,10 @@ class TIGER(TIGE):
     def contrast_and_mutual_learning(self, src_ids: Tensor, dst_ids: Tensor, neg_dst_ids: Tensor, ts: Tensor,
                                      eids: Tensor, computation_graph, contrast_only: bool = False
                                      ) -> Tuple[Tensor, Tensor]:
+        if self._native_training():
+            tr = self.native_trainer(len(src_ids))
+            return _NativeStep.apply(tr, (src_ids, dst_ids, neg_dst_ids, ts, eids, computation_graph), contrast_only,
+                                     *tr.fp.params)
         contrast_loss, *_, h_prev_left, h_prev_right = self.contrast_learning(
             src_ids, dst_ids, neg_dst_ids, ts, eids, computation_graph)
         if contrast_only:
@@ -339,6 +364,24 @@ class TIGER(TIGE):
         if len(valid):
             return contrast_loss, self.mutual_loss_fn(preds[valid], targets[valid].detach())
         return contrast_loss, torch.tensor(0, device=contrast_loss.device)
+
+    # ---- native training step (www2023tiger_b200/train.py) ----
+    def _native_training(self) -> bool:
+        """The hand-written training step covers the reference's default operator variants; anything else (and
+        TIGER_AUTOGRAD_ROUTE=1, the comparison route of the tests) trains through the torch-op route below."""
+        import os
+        from .restarters import SeqRestarter, StaticRestarter
+        return (torch.is_grad_enabled() and self.training and self._fusable()
+                and isinstance(self.restarter_fn, (SeqRestarter, StaticRestarter))
+                and os.environ.get('TIGER_AUTOGRAD_ROUTE') != '1')
+
+    def native_trainer(self, batch_size: int, **kw):
+        from www2023tiger_b200.train import NativeTrainer
+        tr = getattr(self, '_trainer', None)
+        if tr is None or tr.B < batch_size or tr.device != self.device:
+            tr = NativeTrainer(self, batch_size, **kw)
+            object.__setattr__(self, '_trainer', tr)
+        return tr
 
     @torch.no_grad()
     def restart(self, nids: Tensor, ts: Tensor, mix: float = 0.):

@@ -1,0 +1,341 @@
+"""The training step of the drop-in TIGER model on hand-written kernels: forward that keeps what backward needs,
+hand-written backward, Adam - what `loss.backward(); optimizer.step()` of the reference's loops runs through autograd
+(train_self_supervised.py:165-171, train_self_supervised_ddp.py:203-208; model function
+TIGER.contrast_and_mutual_learning, tiger/model/tiger.py:547-592).
+
+`NativeTrainer` adopts the parameters of a `tiger.model.tiger.TIGER` (this package's mirror of the reference class):
+they are re-pointed into ONE flat fp32 buffer (with a flat gradient buffer and flat Adam moments beside it), so the
+optimizer is one kernel and the DDP gradient all-reduce is one NCCL call over one bucket.  The module keeps working
+as an nn.Module (state_dict, eval route, torch optimizers): only the storage of `p.data` moved.
+
+Step (B events, K neighbors; all data-dependent counts stay on the device):
+  forward   compaction of the involved / pending sets -> gather of the pending messages -> GRU (2 tensor-core
+            products + gates) -> attention (row builder, q / k / v products, single-query core with dropout,
+            out-projection, merger) -> argmax-by-timestamp + right write-back (+ restarter targets) -> link scorer
+            (pair rows, first layer, dropout + second layer + BCE) -> restarter on the collated batch + mutual loss
+            -> message build + store, left write-back
+  backward  scorer -> merger -> out-projection -> attention core -> q / k / v products -> scatter onto the GRU rows
+            and TimeEncode gradients -> GRU gates -> GRU weight gradients; restarter backward
+  update    [gradient all-reduce] -> Adam (zeroes the gradient buffer for the next step)
+Dense products: ops.sgemm_ex (tcgen05, tf32x3): y = x W^T, dx = dy W, dW += dy^T x on the tensors as stored.
+"""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+from ._lib import call, ptr, raise_on_err_flags
+
+f32, i32, i64, u8 = torch.float32, torch.int32, torch.int64, torch.uint8
+
+
+class FlatParams:
+    """Parameters of a module re-pointed into one flat buffer (+ gradient and Adam moment buffers of the same
+    layout).  Shared parameters (the time encoder is registered under three names, tiger.py:71-72) appear once."""
+
+    ALIGN = 4     # floats: every tensor starts on a 16-byte boundary
+
+    def __init__(self, module: torch.nn.Module):
+        seen, self.names, self.params = set(), [], []
+        for name, p in module.named_parameters():
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            self.names.append(name)
+            self.params.append(p)
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=f32, device=dev)
+        self.grad = torch.zeros(off, dtype=f32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=f32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=f32, device=dev)
+        self.g: Dict[str, Tensor] = {}
+        self.p: Dict[str, Tensor] = {}
+        for name, p, o in zip(self.names, self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self.p[name] = view
+            self.g[name] = self.grad[o:o + p.numel()].view(p.shape)
+        self.step = 0
+
+    def publish_grads(self):
+        """Make the gradients visible as `p.grad` (views of the flat gradient buffer)."""
+        for name, p in zip(self.names, self.params):
+            p.grad = self.g[name]
+
+    def adam(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0, zero_grad: bool = True):
+        self.step += 1
+        call('tiger_train_adam', ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.numel,
+             float(lr), float(betas[0]), float(betas[1]), float(eps), self.step, float(grad_scale), int(zero_grad))
+
+
+def _linear_fwd(x, w, b, out, *, m, relu=False, m_count=None, per=1):
+    ops.sgemm_ex(x, w, out, m=m, n=w.shape[0], k=w.shape[1], bias=b, relu=relu, m_count=m_count, rows_per_count=per)
+
+
+def _linear_bwd(dy, x, w, gw, gb, dx, *, m, k_parts=None, count=None, per=1, accumulate_dx=False):
+    """dy [m, n], x [m, k], w [n, k]: gw += dy^T x, gb += colsum(dy), dx (=|+=) dy w.  `count` bounds m on the device."""
+    n, k = w.shape
+    # K split of the weight gradient: <= ~512 reduction steps per CTA (accumulator truncation grows with the length)
+    k_parts = max(1, min(64, (m + 511) // 512))
+    if gw is not None:
+        ops.sgemm_ex(dy, x, gw, m=n, n=k, k=m, trans_a=True, trans_w=True, accumulate=True, k_parts=k_parts,
+                     k_count=count, rows_per_count=per)
+    if gb is not None:
+        call('tiger_train_colsum', ptr(dy), dy.stride(0), m, ptr(count), per, n, 1.0, ptr(gb))
+    if dx is not None:
+        ops.sgemm_ex(dy, w, dx, m=m, n=k, k=n, trans_w=True, m_count=count, rows_per_count=per,
+                     accumulate=accumulate_dx)
+
+
+class NativeTrainer:
+    def __init__(self, model, batch_size: int, *, lr: float = 1e-4, seed: int = 0):
+        from .tiger.model.message_modules import IdentityMessageFunction
+        from .tiger.model.restarters import SeqRestarter, StaticRestarter
+        from .tiger.model.update_modules import GRUUpdater
+        if not (isinstance(model.msg_transform_fn, IdentityMessageFunction)
+                and isinstance(model.right_mem_updater, GRUUpdater) and model.n_layers == 1
+                and model.hit_type in ('bin', 'none')):
+            raise NotImplementedError('native training covers the default operator variants '
+                                      '(tsfm_fn id, upd_fn gru, n_layers 1, hit_type bin|none)')
+        self.model = model
+        self.fp = FlatParams(model)
+        self.lr, self.seed, self.n_steps = lr, seed, 0
+        dev = self.fp.flat.device
+        self.device = dev
+        fn = model.temporal_embedding_fn.fns[0]
+        self.B, self.K, self.H = batch_size, model.n_neighbors, fn.n_head
+        self.d, self.de = model.nfeat_dim, model.efeat_dim
+        self.M, self.E, self.C = model.raw_msg_dim, 2 * model.nfeat_dim, 2 * model.nfeat_dim + model.efeat_dim
+        self.p_attn = float(fn.dropout)
+        self.p_score = float(model.score_fn.dropout.p)
+        B, K, d, E, C, M = self.B, self.K, self.d, self.E, self.C, self.M
+        self.cap = cap = 3 * B * (K + 1)
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        N = model.n_nodes
+        # --- compaction scratch
+        self.bitmap = z(ops.bitmap_words(N), dt=i32)
+        self.involved, self.outdated = z(cap, dt=i64), z(cap, dt=i64)
+        self.gru_row = torch.full((N,), -1, dtype=i32, device=dev)
+        self.counts = z(4, dt=i32)
+        self.err = z(1, dt=i32)
+        # --- GRU
+        self.X, self.Hs = z(cap, M), z(cap, d)
+        self.Gi, self.Gh, self.dGi, self.dGh = z(cap, 3 * d), z(cap, 3 * d), z(cap, 3 * d), z(cap, 3 * d)
+        self.h_new, self.dh_new = z(cap, d), z(cap, d)
+        self.r, self.zg, self.n = z(cap, d), z(cap, d), z(cap, d)
+        # --- attention
+        nq = 3 * B
+        self.q_in, self.kv_in, self.cat = z(nq, E), z(nq * K, C), z(nq, E + d)
+        self.Qp, self.KV, self.attn = z(nq, E), z(nq * K, 2 * E), z(nq, E)
+        self.P, self.keep, self.empty = z(nq * self.H * K), z(nq * self.H, dt=i32), z(nq, dt=u8)
+        self.hid, self.z = z(nq, d), z(nq, d)
+        self.dz, self.dhid, self.dcat, self.dattn = z(nq, d), z(nq, d), z(nq, E + d), z(nq, E)
+        self.dQ, self.dKV, self.dkv_in, self.dq_in = z(nq, E), z(nq * K, 2 * E), z(nq * K, C), z(nq, E)
+        # --- steps 4-6
+        self.winner = z(2 * B, dt=u8)
+        self.hprev_left, self.hprev_right = z(2 * B, d), z(2 * B, d)
+        # --- scorer
+        self.pair, self.codes, self.hid_s = z(2 * B, 2 * d), z(4 * B, dt=u8), z(2 * B, d)
+        self.scores, self.closs, self.dscore = z(2 * B), z(1), z(2 * B)
+        self.dhid_s, self.dpair = z(2 * B, d), z(2 * B, 2 * d)
+        # --- restarter / mutual loss
+        self.mloss = z(1)
+        self.pred_l, self.pred_r = z(2 * B, d), z(2 * B, d)
+        self.dpred_l, self.dpred_r = z(2 * B, d), z(2 * B, d)
+        self.restarter = model.restarter_fn
+        if isinstance(self.restarter, StaticRestarter):
+            self.rkind = 'static'
+        elif isinstance(self.restarter, SeqRestarter):
+            self.rkind = 'seq'
+            from .train_seq import SeqRestarterTrainer
+            self.seq = SeqRestarterTrainer(self.restarter, self.fp, 2 * B, dev)
+        else:
+            raise NotImplementedError(type(self.restarter).__name__)
+        self._ctx = None
+
+    # ------------------------------------------------------------------ parameter handles
+    def P_(self, name: str) -> Tensor:
+        return self.fp.p[name]
+
+    def G_(self, name: str) -> Tensor:
+        return self.fp.g[name]
+
+    def check_errors(self):
+        v = int(self.err.item()) & 0xffffffff
+        if v:
+            self.err.zero_()
+            raise_on_err_flags(v)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, src: Tensor, dst: Tensor, neg: Tensor, ts: Tensor, eids: Tensor, cg, *, contrast_only: bool = False,
+                train: bool = True) -> Tuple[Tensor, Tensor]:
+        """-> (contrast_loss [1], mutual_loss [1]) device tensors; memory state advanced like the reference's
+        contrast_and_mutual_learning.  `train=False` switches dropout off (eval-mode forward of the same program)."""
+        m = self.model
+        B, K, H, d, de, E, C, M, cap = len(src), self.K, self.H, self.d, self.de, self.E, self.C, self.M, self.cap
+        assert B <= self.B
+        nq = 3 * B
+        P, G = self.fp.p, self.fp.g
+        self.n_steps += 1
+        seed = (self.seed * 1000003 + self.n_steps) & 0x7fffffff
+        p_attn = self.p_attn if train else 0.0
+        p_score = self.p_score if train else 0.0
+        nn_, ne_, nt_ = cg.layers[1]
+        batch_nids = torch.cat([src, dst, neg]).contiguous()
+        pos = batch_nids[:2 * B]
+        ts = ts.to(f32).contiguous()
+        eids = eids.contiguous()
+        left, right, store = m.left_memory, m.right_memory, m.msg_store
+        msg_mem, upd_mem = m.msg_memory, m.upd_memory
+        fg = m.raw_feat_getter
+        cnt_o = self.counts[1:]
+        # ---- steps 1-2: pending set, gather, GRU (tiger.py:206-221)
+        ops.mark_nodes(cg.computation_graph_nodes.contiguous(), self.bitmap, m.n_nodes)
+        ops.compact_involved(self.bitmap, m.n_nodes, self.involved, self.counts, has_msg=store.has_msg,
+                             outdated=self.outdated, gru_row=self.gru_row, err_flags=self.err)
+        call('tiger_train_gather_pending', ptr(self.outdated), ptr(cnt_o), cap, ptr(store.node_msg_vals), M,
+             ptr(store.node_msg_ts), ptr(upd_mem.vals), d, ptr(msg_mem.update_ts), int(m.msg_src == 'left'),
+             ptr(self.X), ptr(self.Hs), ptr(self.dh_new), ptr(self.err))
+        c = 'right_mem_updater.cell.'
+        _linear_fwd(self.X, P[c + 'weight_ih'], P[c + 'bias_ih'], self.Gi, m=cap, m_count=cnt_o)
+        _linear_fwd(self.Hs, P[c + 'weight_hh'], P[c + 'bias_hh'], self.Gh, m=cap, m_count=cnt_o)
+        call('tiger_train_gru_gates', ptr(self.Gi), ptr(self.Gh), ptr(self.Hs), ptr(cnt_o), cap, d, ptr(self.h_new),
+             ptr(self.r), ptr(self.zg), ptr(self.n))
+        # ---- step 3: temporal attention (temporal_agg_modules.py:29-83,210-235)
+        a = 'temporal_embedding_fn.fns.0.'
+        tw, tb = P['time_encoder.basis_freq'], P['time_encoder.phase']
+        call('tiger_train_attn_build', ptr(batch_nids), nq, ptr(ts), B, ptr(nn_), ptr(ne_), ptr(nt_), K, ptr(right.vals),
+             ptr(self.h_new), ptr(self.gru_row), ptr(fg.nfeats), ptr(fg.efeats), d, de, ptr(tw), ptr(tb), ptr(self.q_in),
+             ptr(self.kv_in), ptr(self.cat), E + d, E)
+        in_b = P[a + 'mha_fn.in_proj_bias']
+        _linear_fwd(self.q_in, P[a + 'mha_fn.q_proj_weight'], in_b[:E], self.Qp, m=nq)
+        _linear_fwd(self.kv_in, P[a + 'mha_fn.k_proj_weight'], in_b[E:2 * E], self.KV[:, :E], m=nq * K)
+        _linear_fwd(self.kv_in, P[a + 'mha_fn.v_proj_weight'], in_b[2 * E:], self.KV[:, E:], m=nq * K)
+        hd = E // H
+        call('tiger_train_attn_core', ptr(self.Qp), E, ptr(self.KV), ptr(self.KV[:, E:]), 2 * E, ptr(nn_), nq, K, H, hd,
+             p_attn, seed, ptr(self.attn), E, ptr(self.P), ptr(self.keep), ptr(self.empty))
+        _linear_fwd(self.attn, P[a + 'mha_fn.out_proj.weight'], P[a + 'mha_fn.out_proj.bias'], self.cat[:, :E], m=nq)
+        call('tiger_train_zero_rows', ptr(self.cat), E + d, E, nq, ptr(self.empty))
+        _linear_fwd(self.cat, P[a + 'merger.fc1.weight'], P[a + 'merger.fc1.bias'], self.hid, m=nq, relu=True)
+        _linear_fwd(self.hid, P[a + 'merger.fc2.weight'], P[a + 'merger.fc2.bias'], self.z, m=nq)
+        # ---- step 4 + restarter targets (tiger.py:230-251), no grad
+        winner = self.winner[:2 * B]
+        ops.select_latest(pos, ts, want_unique=False, winner=winner, want_count=False)
+        ops.right_writeback(pos, winner, self.gru_row, self.h_new, d, right.vals, right.update_ts, right.active_mask,
+                            store.node_msg_ts, store.has_msg, left.vals, self.hprev_left, self.hprev_right, self.err)
+        # ---- step 7: link scorer (tiger.py:259-288)
+        hits = None
+        if m.hit_type == 'bin':
+            hits = torch.stack(list(cg.hit_data)).to(f32).contiguous()          # [4, B, K]
+        call('tiger_train_score_build', ptr(self.z), ptr(hits), K, ptr(P['hit_embedding.weight']) if hits is not None
+             else None, B, d, ptr(self.pair), ptr(self.codes) if hits is not None else None)
+        s = 'score_fn.'
+        _linear_fwd(self.pair, P[s + 'fc1.weight'], P[s + 'fc1.bias'], self.hid_s, m=2 * B, relu=True)
+        call('tiger_train_score_head', ptr(self.hid_s), ptr(P[s + 'fc2.weight']), ptr(P[s + 'fc2.bias']), B, d, p_score,
+             seed, ptr(self.scores), ptr(self.closs), ptr(self.dscore))
+        # ---- restarter on the collated batch + mutual loss (tiger.py:574-590)
+        n_pos = 0
+        rd = cg.restart_data
+        if not contrast_only:
+            n_pos = rd.nids.numel()
+            nids = rd.nids.contiguous()
+            if self.rkind == 'static':
+                call('tiger_gather_rows', ptr(P['restarter_fn.left_emb.weight']), d, ptr(nids), n_pos, ptr(self.pred_l),
+                     None, None)
+                call('tiger_gather_rows', ptr(P['restarter_fn.right_emb.weight']), d, ptr(nids), n_pos, ptr(self.pred_r),
+                     None, None)
+            else:
+                self.seq.forward(nids, rd, fg, self.pred_l, self.pred_r, seed, train)
+            call('tiger_train_mse', ptr(self.pred_l), ptr(self.pred_r), ptr(self.hprev_left), ptr(self.hprev_right),
+                 ptr(rd.index.contiguous()), None, n_pos, d, ptr(self.mloss), ptr(self.dpred_l), ptr(self.dpred_r))
+        else:
+            self.mloss.zero_()
+        # ---- steps 5-6 (tiger.py:244-255), no grad
+        ops.store_messages(batch_nids[:B], batch_nids[B:2 * B], eids, ts, winner, msg_mem.vals, msg_mem.update_ts,
+                           fg.nfeats, fg.efeats, d, de, tw, tb, store.node_msg_vals, store.node_msg_ts, store.has_msg,
+                           self.err)
+        ops.left_writeback(pos, B, winner, self.z, d, ts, left.vals, left.update_ts, left.active_mask, self.err)
+        self._ctx = dict(B=B, batch_nids=batch_nids, ts=ts, nn=nn_, nt=nt_, hits=hits is not None, n_pos=n_pos,
+                         nids=rd.nids if not contrast_only else None, p_attn=p_attn, p_score=p_score, seed=seed,
+                         keepalive=(ne_, hits, rd))
+        return self.closs, self.mloss
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, g_contrast: float = 1.0, g_mutual: float = 1.0):
+        """Accumulates d(g_contrast * contrast_loss + g_mutual * mutual_loss)/d(parameters) into the flat gradient
+        buffer (call once per forward)."""
+        ctx = self._ctx
+        assert ctx is not None, 'backward() needs a forward()'
+        self._ctx = None
+        B, K, H, d, de, E, C, M, cap = ctx['B'], self.K, self.H, self.d, self.de, self.E, self.C, self.M, self.cap
+        nq = 3 * B
+        P, G = self.fp.p, self.fp.g
+        cnt_o = self.counts[1:]
+        s, a, c = 'score_fn.', 'temporal_embedding_fn.fns.0.', 'right_mem_updater.cell.'
+        # ---- scorer
+        call('tiger_train_score_head_bwd', ptr(self.dscore), float(g_contrast), ptr(self.hid_s), ptr(P[s + 'fc2.weight']),
+             B, d, ctx['p_score'], ptr(self.dhid_s), ptr(G[s + 'fc2.weight']), ptr(G[s + 'fc2.bias']))
+        _linear_bwd(self.dhid_s, self.pair, P[s + 'fc1.weight'], G[s + 'fc1.weight'], G[s + 'fc1.bias'], self.dpair,
+                    m=2 * B, k_parts=4)
+        call('tiger_train_score_build_bwd', ptr(self.dpair), ptr(self.codes) if ctx['hits'] else None, B, d, ptr(self.dz),
+             ptr(G['hit_embedding.weight']) if ctx['hits'] else None)
+        # ---- merger (MergeLayer: fc2(relu(fc1([out | c]))))
+        _linear_bwd(self.dz, self.hid, P[a + 'merger.fc2.weight'], G[a + 'merger.fc2.weight'], G[a + 'merger.fc2.bias'],
+                    self.dhid, m=nq, k_parts=4)
+        call('tiger_train_relu_bwd', ptr(self.dhid), d, ptr(self.hid), d, d, nq, None, 1, 1.0)
+        _linear_bwd(self.dhid, self.cat, P[a + 'merger.fc1.weight'], G[a + 'merger.fc1.weight'],
+                    G[a + 'merger.fc1.bias'], self.dcat, m=nq, k_parts=4)
+        call('tiger_train_zero_rows', ptr(self.dcat), E + d, E, nq, ptr(self.empty))
+        # ---- out-projection, attention core
+        dout = self.dcat[:, :E]
+        _linear_bwd(dout, self.attn, P[a + 'mha_fn.out_proj.weight'], G[a + 'mha_fn.out_proj.weight'],
+                    G[a + 'mha_fn.out_proj.bias'], self.dattn, m=nq, k_parts=4)
+        hd = E // H
+        call('tiger_train_attn_core_bwd', ptr(self.dattn), E, ptr(self.Qp), E, ptr(self.KV), ptr(self.KV[:, E:]), 2 * E,
+             ptr(self.P), ptr(self.keep), nq, K, H, hd, ctx['p_attn'], ptr(self.dQ), ptr(self.dKV), ptr(self.dKV[:, E:]))
+        g_in_b = G[a + 'mha_fn.in_proj_bias']
+        _linear_bwd(self.dQ, self.q_in, P[a + 'mha_fn.q_proj_weight'], G[a + 'mha_fn.q_proj_weight'], g_in_b[:E],
+                    self.dq_in, m=nq, k_parts=4)
+        _linear_bwd(self.dKV[:, :E], self.kv_in, P[a + 'mha_fn.k_proj_weight'], G[a + 'mha_fn.k_proj_weight'],
+                    g_in_b[E:2 * E], self.dkv_in, m=nq * K, k_parts=16)
+        _linear_bwd(self.dKV[:, E:], self.kv_in, P[a + 'mha_fn.v_proj_weight'], G[a + 'mha_fn.v_proj_weight'],
+                    g_in_b[2 * E:], self.dkv_in, m=nq * K, k_parts=16, accumulate_dx=True)
+        # ---- representation gradients back onto the GRU rows, TimeEncode gradients
+        call('tiger_train_attn_build_bwd', ptr(self.dkv_in), ptr(self.dq_in), ptr(self.dcat), E + d, E,
+             ptr(ctx['batch_nids']), nq, ptr(ctx['ts']), B, ptr(ctx['nn']), ptr(ctx['nt']), K, ptr(self.gru_row), d, de,
+             ptr(P['time_encoder.basis_freq']), ptr(P['time_encoder.phase']), ptr(self.dh_new),
+             ptr(G['time_encoder.basis_freq']), ptr(G['time_encoder.phase']))
+        # ---- GRU (inputs are detached messages / memory buffers: weight gradients only)
+        call('tiger_train_gru_gates_bwd', ptr(self.dh_new), ptr(self.r), ptr(self.zg), ptr(self.n), ptr(self.Gh),
+             ptr(self.Hs), ptr(cnt_o), cap, d, ptr(self.dGi), ptr(self.dGh))
+        _linear_bwd(self.dGi, self.X, P[c + 'weight_ih'], G[c + 'weight_ih'], G[c + 'bias_ih'], None, m=cap, k_parts=16,
+                    count=cnt_o)
+        _linear_bwd(self.dGh, self.Hs, P[c + 'weight_hh'], G[c + 'weight_hh'], G[c + 'bias_hh'], None, m=cap, k_parts=16,
+                    count=cnt_o)
+        # ---- restarter
+        if ctx['n_pos'] and g_mutual != 0.0:
+            n_pos, nids = ctx['n_pos'], ctx['nids'].contiguous()
+            if self.rkind == 'static':
+                for side, dp in (('left', self.dpred_l), ('right', self.dpred_r)):
+                    call('tiger_train_scatter_add_rows', ptr(G[f'restarter_fn.{side}_emb.weight']), ptr(nids), n_pos, None,
+                         1, ptr(dp), d, d, float(g_mutual))
+            else:
+                self.seq.backward(self.dpred_l, self.dpred_r, float(g_mutual))
+
+    # ------------------------------------------------------------------ whole step
+    def step(self, src, dst, neg, ts, eids, cg, *, mutual_coef: float = 1.0, contrast_only: bool = False,
+             grad_scale: float = 1.0, allreduce=None):
+        """forward + backward + [allreduce(flat gradient)] + Adam.  Returns the two loss tensors (device)."""
+        closs, mloss = self.forward(src, dst, neg, ts, eids, cg, contrast_only=contrast_only)
+        self.backward(1.0, 0.0 if contrast_only else mutual_coef)
+        if allreduce is not None:
+            allreduce(self.fp.grad)
+        self.fp.adam(self.lr, grad_scale=grad_scale)
+        return closs, mloss
