@@ -96,12 +96,11 @@ def _linear_bwd(dy, x, w, gw, gb, dx, *, m, k_parts=None, count=None, per=1, acc
 
 class NativeTrainer:
     def __init__(self, model, batch_size: int, *, lr: float = 1e-4, seed: int = 0):
-        from .tiger.model.message_modules import IdentityMessageFunction
-        from .tiger.model.restarters import SeqRestarter, StaticRestarter
-        from .tiger.model.update_modules import GRUUpdater
-        if not (isinstance(model.msg_transform_fn, IdentityMessageFunction)
-                and isinstance(model.right_mem_updater, GRUUpdater) and model.n_layers == 1
-                and model.hit_type in ('bin', 'none')):
+        # class names, not isinstance: the drop-in package is importable both as `tiger` (PYTHONPATH, the way the
+        # reference's drivers see it) and as `www2023tiger_b200.tiger`
+        kind = lambda o: type(o).__name__
+        if not (kind(model.msg_transform_fn) == 'IdentityMessageFunction' and kind(model.right_mem_updater) == 'GRUUpdater'
+                and model.n_layers == 1 and model.hit_type in ('bin', 'none')):
             raise NotImplementedError('native training covers the default operator variants '
                                       '(tsfm_fn id, upd_fn gru, n_layers 1, hit_type bin|none)')
         self.model = model
@@ -150,14 +149,14 @@ class NativeTrainer:
         self.pred_l, self.pred_r = z(2 * B, d), z(2 * B, d)
         self.dpred_l, self.dpred_r = z(2 * B, d), z(2 * B, d)
         self.restarter = model.restarter_fn
-        if isinstance(self.restarter, StaticRestarter):
+        if kind(self.restarter) == 'StaticRestarter':
             self.rkind = 'static'
-        elif isinstance(self.restarter, SeqRestarter):
+        elif kind(self.restarter) == 'SeqRestarter':
             self.rkind = 'seq'
             from .train_seq import SeqRestarterTrainer
             self.seq = SeqRestarterTrainer(self.restarter, self.fp, 2 * B, dev)
         else:
-            raise NotImplementedError(type(self.restarter).__name__)
+            raise NotImplementedError(kind(self.restarter))
         self._ctx = None
 
     # ------------------------------------------------------------------ parameter handles
