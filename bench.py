@@ -366,71 +366,96 @@ def algorithmic_bytes(kernel, c, d, de, M, B, K):
     }.get(kernel, 0)
 
 
+class DeviceWorkload:
+    """Stream, features, device CSR, the rank's window of batch records resident in HBM, and (rank 0 at N = 1) the CPU
+    arm, whose parameters - the reference's own init_model under torch.manual_seed(seed) - the B200 arm runs with so
+    that the two can be compared batch by batch."""
+
+    def __init__(self, args, mode='infer'):
+        import torch
+        import torch.distributed as dist
+        from www2023tiger_b200 import _lib, ops
+        rank, local_rank, world = dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py needs a CUDA device: the TIGER B200 path has no CPU fallback')
+        torch.cuda.set_device(local_rank)
+        dev = torch.device('cuda', local_rank)
+        if world > 1:
+            dist.init_process_group('nccl', device_id=dev)
+        _lib.load()
+        self.rank, self.local_rank, self.world, self.dev = rank, local_rank, world, dev
+        shape, st, neg = load_workload(args, with_efeats=st_fits_host(args))
+        self.shape, self.st, self.neg = shape, st, neg
+        self.N, self.d = st.n_nodes, st.dim
+        self.de = shape.efeat_dim or self.d
+        if shape.efeat_dim > 0:
+            if st.efeats is not None:
+                efeats = torch.from_numpy(st.efeats).to(dev)
+            else:
+                efeats = torch.empty(st.n_events + 1, self.de, device=dev)
+                g = torch.Generator(device=dev).manual_seed(args.seed)
+                chunk = 1 << 22
+                for i in range(0, st.n_events + 1, chunk):
+                    efeats[i:i + chunk].normal_(generator=g)
+                efeats[0] = 0
+        else:
+            efeats = None
+        self.efeats = efeats
+        to = lambda x, dt: torch.as_tensor(x).to(dt).to(dev).contiguous()
+        self.csr = ops.csr_build(to(st.src, torch.int64), to(st.dst, torch.int64), to(st.ts, torch.float64),
+                                 to(st.eids, torch.int64), self.N)
+        self.rst = pick_restarter(args, shape)
+        lo, avail = batch_window(args, st.n_events, rank, world)
+        if avail < 8:
+            raise SystemExit('stream too short for this rank')
+        avail = min(avail, max(args.warmup + args.steps + args.profile_steps + 8, 64))   # records actually replayed
+        self.lo, self.avail = lo, avail
+        B = BATCH
+        self.arm = None
+        if rank == 0 and world == 1 and args.cpu_batches > 0:
+            n_cpu = min(args.cpu_batches + args.parity_batches + 4, avail - 2)
+            prefix = None
+            if st.efeats is None and efeats is not None:
+                prefix = efeats[:min(st.n_events, lo + (n_cpu + 2) * B) + 1].cpu().numpy()
+            self.arm = CpuArm(args, shape, st, neg, lo, n_cpu, kind=args.cpu_kind, efeats_prefix=prefix, mode=mode)
+        # all batch inputs of this rank's window, resident in HBM: [avail, 5B] int64 (ts as float64 bits)
+        host_in = np.empty((avail, 5 * B), dtype=np.int64)
+        s = slice(lo, lo + avail * B)
+        host_in[:, :B] = st.src[s].reshape(avail, B)
+        host_in[:, B:2 * B] = st.dst[s].reshape(avail, B)
+        host_in[:, 2 * B:3 * B] = neg[s].reshape(avail, B)
+        host_in[:, 3 * B:4 * B] = st.eids[s].reshape(avail, B)
+        host_in[:, 4 * B:] = st.ts[s].reshape(avail, B).view(np.int64)
+        self.host_in = host_in
+        self.dev_in = torch.from_numpy(host_in).to(dev)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from www2023tiger_b200 import _lib, ops
     from www2023tiger_b200.engine import StreamRunner, TigerEngine
     from www2023tiger_b200.init import random_weights
 
-    rank, local_rank, world = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device: the TIGER B200 path has no CPU fallback')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    _lib.load()
-
-    # ---- workload: stream, features, CSR, weights, engine ----
-    shape, st, neg = load_workload(args, with_efeats=st_fits_host(args))
-    N, d = st.n_nodes, st.dim
-    de = shape.efeat_dim or d
-    if shape.efeat_dim > 0:
-        if st.efeats is not None:
-            efeats = torch.from_numpy(st.efeats).to(dev)
-        else:
-            efeats = torch.empty(st.n_events + 1, de, device=dev)
-            g = torch.Generator(device=dev).manual_seed(args.seed)
-            chunk = 1 << 22
-            for i in range(0, st.n_events + 1, chunk):
-                efeats[i:i + chunk].normal_(generator=g)
-            efeats[0] = 0
-    else:
-        efeats = None
-    to = lambda x, dt: torch.as_tensor(x).to(dt).to(dev).contiguous()
-    csr = ops.csr_build(to(st.src, torch.int64), to(st.dst, torch.int64), to(st.ts, torch.float64),
-                        to(st.eids, torch.int64), N)
-    rst = pick_restarter(args, shape)
-    lo, avail = batch_window(args, st.n_events, rank, world)
-    if avail < 8:
-        raise SystemExit('stream too short for this rank')
+    wl = DeviceWorkload(args)
+    rank, local_rank, world, dev = wl.rank, wl.local_rank, wl.world, wl.dev
+    shape, st, neg, efeats, csr, rst = wl.shape, wl.st, wl.neg, wl.efeats, wl.csr, wl.rst
+    N, d, de, lo, avail, arm = wl.N, wl.d, wl.de, wl.lo, wl.avail, wl.arm
+    host_in, dev_in = wl.host_in, wl.dev_in
     B = BATCH
-    # CPU arm (rank 0 at N = 1): built first because the engine runs with ITS parameters - the reference's own
-    # init_model under torch.manual_seed(seed) - so that the two can be compared batch by batch below
-    arm = None
-    if rank == 0 and world == 1 and args.cpu_batches > 0:
-        n_cpu = min(args.cpu_batches + args.parity_batches + 4, avail - 2)
-        prefix = None
-        if st.efeats is None and efeats is not None:
-            prefix = efeats[:min(st.n_events, lo + (n_cpu + 2) * B) + 1].cpu().numpy()
-        arm = CpuArm(args, shape, st, neg, lo, n_cpu, kind=args.cpu_kind, efeats_prefix=prefix)
+    if arm is not None:
         W = arm.weights()
     else:
         W = random_weights(d, de, n_nodes=N, restarter=rst, hist_len=HIST_LEN, seed=args.seed)
     eng = TigerEngine(W, csr, n_nodes=N, dim=d, efeats=efeats, n_neighbors=K_NEIGH, n_head=N_HEAD,
                       batch_size=BATCH, msg_src=shape.msg_src, upd_src=shape.upd_src, restarter=rst,
                       hist_len=HIST_LEN, lazy_restart=True, device=dev)
-
-    # all batch inputs of this rank's window, resident in HBM: [avail, 5B] int64 (ts as float64 bits)
-    host_in = np.empty((avail, 5 * B), dtype=np.int64)
-    s = slice(lo, lo + avail * B)
-    host_in[:, :B] = st.src[s].reshape(avail, B)
-    host_in[:, B:2 * B] = st.dst[s].reshape(avail, B)
-    host_in[:, 2 * B:3 * B] = neg[s].reshape(avail, B)
-    host_in[:, 3 * B:4 * B] = st.eids[s].reshape(avail, B)
-    host_in[:, 4 * B:] = st.ts[s].reshape(avail, B).view(np.int64)
-    dev_in = torch.from_numpy(host_in).to(dev)
 
     runner = StreamRunner(eng)
     eng.inp.copy_(dev_in[0])
@@ -443,11 +468,7 @@ def run_b200(args):
             eng.reset()           # epoch boundary (train_self_supervised.py:127-128): the window wraps
         runner.submit_device(dev_in[j])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    barrier = wl.barrier
     Wm, K = args.warmup, args.steps
     for i in range(Wm):
         device_step(i)
@@ -562,6 +583,248 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm, training step (--mode train): forward + hand-written backward + [gradient all-reduce] + Adam
+# ------------------------------------------------------------------------------------------
+def train_flops(c, d, de, B, K, L, seq):
+    """Algorithmic flops of the dense products of one training step (forward; backward = 2x for layers whose input
+    needs a gradient, 1x for the GRU whose inputs are buffers); c = mean device counters."""
+    M, E, C, dm = 3 * d + de, 2 * d, 2 * d + de, 4 * d + de
+    gru = 2.0 * c['O'] * 3 * d * (M + d)
+    attn = 2.0 * 3 * B * (E * E + K * C * 2 * E + E * E + (E + d) * d + d * d)
+    score = 2.0 * 2 * B * (2 * d * d)
+    fwd_bwd = 2 * gru + 3 * attn + 3 * score
+    if seq:
+        per_node = 2.0 * (L * dm * 2 * dm + 2 * dm * dm + dm * d + 2 * d * d)
+        fwd_bwd += 3 * c['P'] * per_node + c['R'] * per_node
+    return fwd_bwd
+
+
+def run_train(args):
+    """One step = the loop body of train_self_supervised_ddp.py:186-214 for one batch of 200 events: neighbor finder,
+    lazy restart of not-yet-seen nodes, contrast_and_mutual_learning forward, backward, gradient all-reduce over NCCL
+    (N > 1; one bucket = the flat gradient buffer, 1/N folded into the optimizer), Adam.  lr = 1e-4 * sqrt(N) (:146)."""
+    import torch
+    import torch.distributed as dist
+    from www2023tiger_b200 import train as T, train_seq as TS, ops
+    from www2023tiger_b200.init import build_model
+    from www2023tiger_b200.tiger.data.graph import Graph
+
+    wl = DeviceWorkload(args, mode='train')
+    rank, world, dev = wl.rank, wl.world, wl.dev
+    shape, st, rst, arm, dev_in, host_in, avail, lo = wl.shape, wl.st, wl.rst, wl.arm, wl.dev_in, wl.host_in, wl.avail, wl.lo
+    B, d, de = BATCH, wl.d, wl.de
+    torch.manual_seed(args.seed)
+    graph = Graph.from_csr(wl.csr)
+    model = build_model(None, wl.efeats, graph, wl.N, st.n_events, dev, dim=shape.dim, n_layers=1, n_heads=N_HEAD,
+                        n_neighbors=K_NEIGH, hit_type='bin', dropout=0.1, restarter_type=rst, hist_len=HIST_LEN,
+                        msg_src=shape.msg_src, upd_src=shape.upd_src)
+    if arm is not None:
+        res = model.load_state_dict(arm.weights(), strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+    if world > 1:                                  # DDP broadcasts rank 0's parameters at construction (:145)
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    model.train()
+    lr = 1e-4 * math.sqrt(world)
+    tr = model.native_trainer(B, lr=lr, seed=args.seed)
+    tr.attach_stream(wl.csr, HIST_LEN)
+    losses = torch.zeros(2, device=dev)
+    comm = {'bytes': tr.fp.numel * 4 if world > 1 else 0}
+
+    def allreduce(t):
+        return dist.all_reduce(t, async_op=True) if world > 1 else None
+
+    def device_step(i, inp=None):
+        j = i % avail
+        if j == 0 and i > 0:
+            tr.reset_stream()                      # epoch boundary: the window wraps (model.reset(), :176)
+        closs, mloss = tr.step_stream(dev_in[j] if inp is None else inp, mutual_coef=1.0, grad_scale=1.0 / world,
+                                      allreduce=allreduce)
+        losses[0:1].add_(closs)
+        losses[1:2].add_(mloss)
+
+    # ---- parity: the first training steps from a reset, dropout off on both sides, against the reference's loop body
+    parity = None
+    if arm is not None and args.parity_batches > 0 and arm.kind == 'reference':
+        parity = check_train_parity(args, wl, model, tr)
+    tr.reset_stream()
+    Wm, K = args.warmup, args.steps
+    for i in range(Wm):
+        device_step(i)
+    wl.barrier()
+    clocks = ClockSampler(wl.local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    losses.zero_()
+    ev0.record()
+    for i in range(Wm, Wm + K):
+        device_step(i)
+    ev1.record()
+    wl.barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1), world, dev)
+    tr.check_errors()
+    value = world * K * B / (ms * 1e-3)
+    if world > 1:
+        dist.all_reduce(losses)                    # the reference all-reduces its loss scalars (:209-211)
+    mean_losses = (losses / (K * world)).cpu().tolist()
+
+    # ---- e2e: the batch record comes from pinned host memory every step, the two losses go back to the host ----
+    e2e = None
+    if not args.no_e2e:
+        tr.reset_stream()
+        pin = [torch.empty(5 * B, dtype=torch.int64).pin_memory() for _ in range(4)]
+        d_in = [torch.empty(5 * B, dtype=torch.int64, device=dev) for _ in range(4)]
+        h_out = torch.empty(K + Wm, 2).pin_memory()
+        copied = [None] * 4
+        wl.barrier()
+        t0 = None
+        for i in range(Wm + K):
+            if i == Wm:
+                wl.barrier()
+                t0 = time.perf_counter()
+            sl = i % 4
+            if copied[sl] is not None:
+                copied[sl].synchronize()            # the slot's previous upload has left the pinned buffer
+            pin[sl].numpy()[:] = host_in[i % avail]
+            d_in[sl].copy_(pin[sl], non_blocking=True)
+            copied[sl] = torch.cuda.Event()
+            copied[sl].record()
+            j = i % avail
+            if j == 0 and i > 0:
+                tr.reset_stream()
+            closs, mloss = tr.step_stream(d_in[sl], mutual_coef=1.0, grad_scale=1.0 / world, allreduce=allreduce)
+            h_out[i, 0:1].copy_(closs, non_blocking=True)
+            h_out[i, 1:2].copy_(mloss, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0, world, dev)
+        tr.check_errors()
+        e2e = {'value': world * K * B / dt, 'unit': UNIT, 'h2d_bytes_per_step': 5 * B * 8, 'd2h_bytes_per_step': 8,
+               'ms_per_step': dt / K * 1e3, 'mean_loss': float(h_out[Wm:].sum(1).mean())}
+    clk = clocks.stop() if clocks is not None else None
+
+    # ---- per-entry-point CUDA-event breakdown + launch count ----
+    kernels, roofline, launches = None, None, None
+    if rank == 0 and args.profile_steps > 0:
+        from www2023tiger_b200 import _lib
+        tr.reset_stream()
+        records = []
+        orig = _lib.call
+
+        def timed_call(name, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig(name, *a)
+            e1.record()
+            records.append((name, e0, e1))
+        n_steps = min(args.profile_steps, avail)
+        warm = min(10, n_steps // 2)
+        counts = []
+        ops.call = T.call = TS.call = timed_call
+        try:
+            for i in range(n_steps):
+                if i == warm:
+                    torch.cuda.synchronize()
+                    records.clear()
+                    counts.clear()
+                tr.step_stream(dev_in[i], mutual_coef=1.0, grad_scale=1.0 / world, allreduce=allreduce)
+                counts.append(torch.cat([tr.counts[:3].long(), tr.t_count.long()]))
+        finally:
+            ops.call = T.call = TS.call = orig
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1 in records:
+            agg.setdefault(name, []).append(e0.elapsed_time(e1) * 1e3)
+        n = n_steps - warm
+        kernels = {k: {'us': float(np.sum(v)) / n, 'launches_per_step': len(v) / n} for k, v in agg.items()}
+        launches = sum(v['launches_per_step'] for v in kernels.values())
+        U, O_, R, P = (float(x) for x in torch.stack(counts).double().mean(0).cpu())
+        counters = {'U': U, 'O': O_, 'R': R, 'P': P}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except OSError:
+            pass
+        flops = train_flops(counters, d, de, B, K_NEIGH, HIST_LEN, rst == 'seq')
+        g = kernels.get('tiger_sgemm_ex')
+        tf32_peak = float(peaks.get('bf16_tflops', 1590.0)) / 2.0
+        if g:
+            ach = 3.0 * flops / (g['us'] * 1e-6) / 1e12
+            roofline = {'bound': 'tensor', 'kernel': 'tiger_sgemm_ex', 'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                        'frac': ach / tf32_peak, 'traffic': None, 'useful_tflops': ach / 3.0, 'launch_us': g['us'],
+                        'launches_per_step': g['launches_per_step'], 'flops_per_step': flops, 'counters': counters,
+                        'peak_source': 'half of the measured bf16 GEMM peak (tf32 runs at half the bf16 rate)'
+                        if peaks else 'fallback',
+                        'note': 'all tensor-core products of the step (forward, input and weight gradients) together: '
+                                'issued = 3 x useful flops (tf32x3); eager launches timed with CUDA events per entry point'}
+
+    # ---- CPU baseline: the reference's training loop body on the host cores ----
+    cpu = None
+    if arm is not None:
+        first = 0
+        arm.ref.reset(train=True) if arm.kind == 'reference' else None
+        n, dt = arm.time(first, min(args.cpu_batches, avail - 4), args.cpu_seconds, warmup=1)
+        cpu = {'value': n * B / dt, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind, 'sample': arm.describe(n, 1),
+               'ms_per_step': dt / n * 1e3}
+
+    if rank == 0:
+        line = {
+            'metric': metric_name(args), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, shape, st, world),
+            'e2e': e2e, 'gpu_launches': int(round((launches or 0) * K)), 'clocks': clk, 'roofline': roofline,
+            'cpu_baseline': cpu, 'parity_checked': bool(parity), 'parity': parity,
+            'train': {'lr': lr, 'optimizer': 'Adam (flat buffer, one kernel)', 'params': tr.fp.numel,
+                      'allreduce_bytes_per_step': comm['bytes'], 'mean_contrast_loss': mean_losses[0],
+                      'mean_mutual_loss': mean_losses[1], 'dropout': 0.1},
+            'kernels': kernels,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def check_train_parity(args, wl, model, tr):
+    """First training steps after a reset, dropout off on both sides (masks are not reproducible across
+    implementations): losses of every step must agree with the reference's loop body within 1e-5 / 2e-5, and because
+    step k + 1 runs on the parameters Adam produced from step k's gradients, backward and optimizer are covered too."""
+    import torch
+    from oracle import ref_harness
+    n = args.parity_batches
+    ref = ref_harness.ReferenceRunner(wl.st if wl.st.efeats is not None else wl.arm.ref.st, wl.neg,
+                                      restarter=wl.rst, msg_src=wl.shape.msg_src, upd_src=wl.shape.upd_src,
+                                      n_graph_events=wl.lo + (n + 1) * BATCH, n_neighbors=K_NEIGH, n_heads=N_HEAD,
+                                      hist_len=HIST_LEN, batch=BATCH, seed=args.seed, dropout=0.0)
+    ref.reset(train=True)
+    saved = {k: v.clone() for k, v in tr.fp.p.items()}
+    keep = (tr.p_attn, tr.p_score, tr.fp.step)
+    tr.p_attn = tr.p_score = 0.0
+    if tr.rkind == 'seq':
+        p_seq, tr.seq.p = tr.seq.p, 0.0
+    tr.reset_stream()
+    worst = [0.0, 0.0]
+    for j in range(n):
+        c, m = tr.step_stream(wl.dev_in[j], mutual_coef=1.0)
+        rc, rm = ref.train_step(wl.lo + j * BATCH, lr=tr.lr)
+        torch.cuda.synchronize()
+        tr.check_errors()
+        e_c = abs(float(c) - rc) / max(abs(rc), 1e-30)
+        e_m = abs(float(m) - rm) / max(abs(rm), 1e-30)
+        worst = [max(worst[0], e_c), max(worst[1], e_m)]
+        if e_c > 1e-5 or e_m > 5e-5:
+            raise SystemExit(f'train parity: step {j} contrast {float(c):.7f} vs {rc:.7f} ({e_c:.1e}), '
+                             f'mutual {float(m):.7f} vs {rm:.7f} ({e_m:.1e})')
+    # back to the initial parameters / optimizer state for the timed run
+    for k, v in saved.items():
+        tr.fp.p[k].copy_(v)
+    tr.fp.exp_avg.zero_(), tr.fp.exp_avg_sq.zero_(), tr.fp.grad.zero_()
+    tr.p_attn, tr.p_score, tr.fp.step = keep
+    if tr.rkind == 'seq':
+        tr.seq.p = p_seq
+    return {'against': 'reference', 'steps': n, 'what': 'contrast and mutual loss of consecutive optimisation steps '
+            '(forward + backward + Adam), dropout 0 on both sides', 'contrast_rel': worst[0], 'mutual_rel': worst[1],
+            'tol': [1e-5, 5e-5]}
 
 
 def check_parity(eng, arm, dev_in, n_batches):
@@ -773,6 +1036,8 @@ def main():
         run_micro(args)
     elif args.impl == 'reference':
         run_reference(args)
+    elif args.mode == 'train':
+        run_train(args)
     else:
         run_b200(args)
 

@@ -505,7 +505,7 @@ int tiger_train_zero_rows(float* buf, int64_t ld, int cols, int64_t n_rows, cons
 int tiger_train_relu_bwd(float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int cols, int64_t n_rows, const int32_t* count, int64_t rows_per_count, float scale, void* stream);
 int tiger_train_colsum(const float* X, int64_t ld, int64_t n_rows, const int32_t* count, int64_t rows_per_count, int cols, float scale, float* out, void* stream);
 int tiger_train_scatter_add_rows(float* table, const int64_t* ids, int64_t n, const int32_t* count, int64_t rows_per_count, const float* src, int64_t ld_src, int width, float scale, void* stream);
-int tiger_train_score_build(const float* z, const float* hits, int k, const float* hit_emb, int64_t batch, int d, float* pair, uint8_t* codes, void* stream);
+int tiger_train_score_build(const float* z, const float* hits, const int64_t* neigh_nids, const int64_t* batch_nids, int k, const float* hit_emb, int64_t batch, int d, float* pair, uint8_t* codes, void* stream);
 int tiger_train_score_head(float* hid, const float* fc2_w, const float* fc2_b, int64_t batch, int d, float p_drop, int seed, float* scores, float* loss, float* dscore, void* stream);
 int tiger_train_score_head_bwd(const float* dscore, float g, const float* hid, const float* fc2_w, int64_t batch, int d, float p_drop, float* dhid, float* g_fc2_w, float* g_fc2_b, void* stream);
 int tiger_train_score_build_bwd(const float* dpair, const uint8_t* codes, int64_t batch, int d, float* dz, float* g_hit_emb, void* stream);
@@ -517,13 +517,13 @@ int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg
  * called from tiger.py:574-590) - L x L self-attention per (node, head) with dropout, folded through the mean over
  * positions (exact by linearity), forward and backward; value-bias term, token gradients (anony_emb, TimeEncode),
  * dropout, axpy. */
-int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* P, float* pbar, float* psum, float* xbar, void* stream);
-int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, const float* x, const float* qk, int64_t ld_qk, const float* P, const float* pbar, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* dX, float* dqk, void* stream);
-int tiger_train_seq_vbias(float* att, const float* psum, const float* bv, int64_t n, int d_model, int n_head, void* stream);
-int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, const float* bv, int64_t n, int d_model, int n_head, float* g_bv, float* dpsum, void* stream);
-int tiger_train_seq_tokens_bwd(const float* dX, int64_t n, int len, const int64_t* anony_ids, const float* hist_ts, int d, int de, const float* time_w, const float* time_b, float* g_anony_emb, float* g_time_w, float* g_time_b, void* stream);
-int tiger_train_dropout(float* x, int64_t n, float p_drop, int seed, int stream_id, void* stream);
-int tiger_train_axpy(float* y, const float* x, int64_t n, float alpha, void* stream);
+int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask, const int32_t* count, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* P, float* pbar, float* psum, float* xbar, void* stream);
+int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, const float* x, const float* qk, int64_t ld_qk, const float* P, const float* pbar, const int32_t* count, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* dX, float* dqk, void* stream);
+int tiger_train_seq_vbias(float* att, const float* psum, const float* bv, const int32_t* count, int64_t n, int d_model, int n_head, void* stream);
+int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, const float* bv, const int32_t* count, int64_t n, int d_model, int n_head, float* g_bv, float* dpsum, void* stream);
+int tiger_train_seq_tokens_bwd(const float* dX, const int32_t* count, int64_t n, int len, const int64_t* anony_ids, const float* hist_ts, int d, int de, const float* time_w, const float* time_b, float* g_anony_emb, float* g_time_w, float* g_time_b, void* stream);
+int tiger_train_dropout(float* x, const int32_t* count, int64_t per_count, int64_t n, float p_drop, int seed, int stream_id, void* stream);
+int tiger_train_axpy(float* y, const float* x, const int32_t* count, int64_t per_count, int64_t n, float alpha, void* stream);
 
 #ifdef __cplusplus
 }

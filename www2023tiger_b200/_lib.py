@@ -73,19 +73,19 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_train_relu_bwd': 'plplilplfp',
     'tiger_train_colsum': 'pllplifpp',
     'tiger_train_scatter_add_rows': 'pplplplifp',
-    'tiger_train_score_build': 'ppiplippp',
+    'tiger_train_score_build': 'ppppiplippp',
     'tiger_train_score_head': 'ppplifipppp',
     'tiger_train_score_head_bwd': 'pfpplifpppp',
     'tiger_train_score_build_bwd': 'pplippp',
     'tiger_train_mse': 'pppppplipppp',
     'tiger_train_adam': 'pppplfffflfip',
-    'tiger_train_seq_pool': 'plppliiifippppp',
-    'tiger_train_seq_pool_bwd': 'pppplppliiifippp',
-    'tiger_train_seq_vbias': 'pppliip',
-    'tiger_train_seq_vbias_bwd': 'pppliippp',
-    'tiger_train_seq_tokens_bwd': 'plippiipppppp',
-    'tiger_train_dropout': 'plfiip',
-    'tiger_train_axpy': 'pplfp',
+    'tiger_train_seq_pool': 'plpppliiifippppp',
+    'tiger_train_seq_pool_bwd': 'pppplpppliiifippp',
+    'tiger_train_seq_vbias': 'ppppliip',
+    'tiger_train_seq_vbias_bwd': 'ppppliippp',
+    'tiger_train_seq_tokens_bwd': 'pplippiipppppp',
+    'tiger_train_dropout': 'ppllfiip',
+    'tiger_train_axpy': 'pppllfp',
     'tiger_sgemm_ex': 'pli' + 'pli' + 'ppl' + 'lil' + 'ppl' + 'fiii' + 'p',
     'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_gemm_pick_bn': 'lii',

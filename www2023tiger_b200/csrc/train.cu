@@ -592,13 +592,17 @@ extern "C" int tiger_train_scatter_add_rows(float* table, const int64_t* ids, in
 // ------------------------------------------------------------------------------------------
 // pair[i]     = [x_i + he(src_hit_i)     | y_i  + he(dst_hit_i)]        i <  B  (positive pairs)
 // pair[B + i] = [x_i + he(neg_src_hit_i) | ny_i + he(neg_dst_hit_i)]           (negative pairs)
-// hits: the four [B, K] 0/1 tables of HitData in the order (src, dst, neg_src, neg_dst); code = max over K ('bin')
+// hit codes ('bin': max over the K slots), either from the four [B, K] 0/1 tables of HitData in the order
+// (src, dst, neg_src, neg_dst), or straight from the neighbor table of the batch [3B, K] (rows: N(src) | N(dst) |
+// N(neg)) with check_in_window's rule (data_loader.py:61-75): src_hit = src in N(dst), dst_hit = dst in N(src),
+// neg_src_hit = src in N(neg), neg_dst_hit = neg in N(src)
 __global__ void __launch_bounds__(256)
-train_score_build_kernel(const float* __restrict__ z, const float* __restrict__ hits, int K,
-                         const float* __restrict__ hit_emb, int64_t B, int d, float* __restrict__ pair,
-                         uint8_t* __restrict__ codes) {
+train_score_build_kernel(const float* __restrict__ z, const float* __restrict__ hits, const int64_t* __restrict__ nn,
+                         const int64_t* __restrict__ batch_nids, int K, const float* __restrict__ hit_emb, int64_t B,
+                         int d, float* __restrict__ pair, uint8_t* __restrict__ codes) {
   const int lane = lane_id();
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool use_hits = hits != nullptr || nn != nullptr;
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block(); r < 2 * B; r += n_warps) {
     const int64_t i = r % B;
     const bool negp = r >= B;
@@ -613,27 +617,43 @@ train_score_build_kernel(const float* __restrict__ z, const float* __restrict__ 
       }
       code_a = warp_max(ma) > 0.5f ? 1 : 0;
       code_b = warp_max(mb) > 0.5f ? 1 : 0;
-      if (lane == 0) {
-        codes[(negp ? 2 : 0) * B + i] = (uint8_t)code_a;
-        codes[(negp ? 3 : 1) * B + i] = (uint8_t)code_b;
+    } else if (nn != nullptr) {
+      const int64_t src = batch_nids[i];
+      const int64_t other = batch_nids[(negp ? 2 : 1) * B + i];      // dst or neg
+      const int64_t* n_other = nn + ((negp ? 2 : 1) * B + i) * K;     // N(dst) or N(neg)
+      const int64_t* n_src = nn + i * K;
+      bool a = false, b = false;
+      for (int k = lane; k < K; k += 32) {
+        a |= n_other[k] == src;
+        b |= n_src[k] == other;
       }
+      code_a = __any_sync(TIGER_FULL_MASK, a) ? 1 : 0;
+      code_b = __any_sync(TIGER_FULL_MASK, b) ? 1 : 0;
+    }
+    if (use_hits && lane == 0) {
+      codes[(negp ? 2 : 0) * B + i] = (uint8_t)code_a;
+      codes[(negp ? 3 : 1) * B + i] = (uint8_t)code_b;
     }
     const float* xa = z + i * d;
     const float* xb = z + ((negp ? 2 : 1) * B + i) * d;
     float* row = pair + r * 2 * d;
     for (int c = lane; c < d; c += 32) {
-      row[c] = xa[c] + (hits != nullptr ? hit_emb[code_a * d + c] : 0.f);
-      row[d + c] = xb[c] + (hits != nullptr ? hit_emb[code_b * d + c] : 0.f);
+      row[c] = xa[c] + (use_hits ? hit_emb[code_a * d + c] : 0.f);
+      row[d + c] = xb[c] + (use_hits ? hit_emb[code_b * d + c] : 0.f);
     }
   }
 }
 
-extern "C" int tiger_train_score_build(const float* z, const float* hits, int k, const float* hit_emb, int64_t batch,
-                                       int d, float* pair, uint8_t* codes, void* stream) {
-  if (z == nullptr || pair == nullptr || batch <= 0 || d <= 0 || (hits != nullptr && (hit_emb == nullptr || codes == nullptr || k <= 0)))
+extern "C" int tiger_train_score_build(const float* z, const float* hits, const int64_t* neigh_nids,
+                                       const int64_t* batch_nids, int k, const float* hit_emb, int64_t batch, int d,
+                                       float* pair, uint8_t* codes, void* stream) {
+  const bool use_hits = hits != nullptr || neigh_nids != nullptr;
+  if (z == nullptr || pair == nullptr || batch <= 0 || d <= 0 ||
+      (use_hits && (hit_emb == nullptr || codes == nullptr || k <= 0)) || (neigh_nids != nullptr && batch_nids == nullptr))
     return TIGER_EINVAL;
   int64_t grid = (2 * batch + 7) / 8;
-  train_score_build_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(z, hits, k, hit_emb, batch, d, pair, codes);
+  train_score_build_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(z, hits, neigh_nids, batch_nids, k, hit_emb,
+                                                                         batch, d, pair, codes);
   return tiger_launch_status();
 }
 

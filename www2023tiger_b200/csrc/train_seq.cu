@@ -26,6 +26,12 @@ __device__ __forceinline__ float seq_sin_reduced(float x) {
   return sinf((float)r);
 }
 
+__device__ __forceinline__ int64_t seq_rows(const int32_t* count, int64_t n, int64_t per = 1) {
+  if (count == nullptr) return n;
+  const int64_t c = (int64_t)(*count) * per;
+  return c < n ? c : n;
+}
+
 #define SP_THREADS 256
 #define SP_CW 32
 #define SP_MAXL 64
@@ -37,8 +43,8 @@ __device__ __forceinline__ float seq_sin_reduced(float x) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SP_THREADS)
 train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ x,
-                      const uint8_t* __restrict__ mask, int64_t n, int len, int dm, int n_head, float p_drop,
-                      uint32_t seed, float* __restrict__ P, float* __restrict__ pbar_out, float* __restrict__ psum_out,
+                      const uint8_t* __restrict__ mask, const int32_t* __restrict__ count, int64_t n, int len, int dm,
+                      int n_head, float p_drop, uint32_t seed, float* __restrict__ P, float* __restrict__ pbar_out, float* __restrict__ psum_out,
                       float* __restrict__ xbar) {
   __shared__ float qs[SP_MAXL][SP_CW + 1];
   __shared__ float ks[SP_MAXL][SP_CW + 1];
@@ -49,7 +55,7 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
   const float scale = sqrtf(1.0f / (float)hd);
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int n_pairs = len * len;
-  const int64_t total = n * n_head;
+  const int64_t total = seq_rows(count, n) * n_head;
   for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
     const int64_t i = item / n_head;
     const int h = (int)(item % n_head);
@@ -136,8 +142,8 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
   }
 }
 
-extern "C" int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask, int64_t n,
-                                    int len, int d_model, int n_head, float p_drop, int seed, float* P, float* pbar,
+extern "C" int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask,
+                                    const int32_t* count, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* P, float* pbar,
                                     float* psum, float* xbar, void* stream) {
   if (qk == nullptr || x == nullptr || mask == nullptr || P == nullptr || pbar == nullptr || psum == nullptr ||
       xbar == nullptr || n < 0 || len <= 0 || len > SP_MAXL || d_model <= 0 || n_head <= 0 || d_model % n_head != 0 ||
@@ -146,8 +152,8 @@ extern "C" int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float*
   if (n == 0) return TIGER_OK;
   int64_t grid = n * n_head;
   if (grid > 148 * 4) grid = 148 * 4;
-  train_seq_pool_kernel<<<(unsigned)grid, SP_THREADS, 0, as_stream(stream)>>>(qk, ld_qk, x, mask, n, len, d_model, n_head,
-                                                                             p_drop, (uint32_t)seed, P, pbar, psum, xbar);
+  train_seq_pool_kernel<<<(unsigned)grid, SP_THREADS, 0, as_stream(stream)>>>(
+      qk, ld_qk, x, mask, count, n, len, d_model, n_head, p_drop, (uint32_t)seed, P, pbar, psum, xbar);
   return tiger_launch_status();
 }
 
@@ -160,8 +166,9 @@ extern "C" int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float*
 __global__ void __launch_bounds__(SP_THREADS)
 train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restrict__ dpsum, const float* __restrict__ x,
                           const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ P,
-                          const float* __restrict__ pbar, int64_t n, int len, int dm, int n_head, float p_drop,
-                          uint32_t seed, float* __restrict__ dX, float* __restrict__ dqk) {
+                          const float* __restrict__ pbar, const int32_t* __restrict__ count, int64_t n_cap, int len,
+                          int dm, int n_head, float p_drop, uint32_t seed, float* __restrict__ dX,
+                          float* __restrict__ dqk) {
   __shared__ float ds[SP_MAXL][SP_MAXL + 1];
   __shared__ float dpb[SP_MAXL];
   __shared__ float pb[4][SP_MAXL];          // pbar of up to 4 heads
@@ -170,6 +177,7 @@ train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restri
   const float scale = sqrtf(1.0f / (float)hd);
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int n_pairs = len * len;
+  const int64_t n = seq_rows(count, n_cap);
   for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
     const float* xrow = x + i * len * (int64_t)dm;
     __syncthreads();
@@ -247,8 +255,8 @@ train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restri
 }
 
 extern "C" int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, const float* x, const float* qk,
-                                        int64_t ld_qk, const float* P, const float* pbar, int64_t n, int len,
-                                        int d_model, int n_head, float p_drop, int seed, float* dX, float* dqk,
+                                        int64_t ld_qk, const float* P, const float* pbar, const int32_t* count,
+                                        int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* dX, float* dqk,
                                         void* stream) {
   if (dxbar == nullptr || dpsum == nullptr || x == nullptr || qk == nullptr || P == nullptr || pbar == nullptr ||
       dX == nullptr || dqk == nullptr || n < 0 || len <= 0 || len > SP_MAXL || d_model <= 0 || n_head <= 0 ||
@@ -257,7 +265,7 @@ extern "C" int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, 
   if (n == 0) return TIGER_OK;
   int64_t grid = n < 148 * 4 ? n : 148 * 4;
   train_seq_pool_bwd_kernel<<<(unsigned)grid, SP_THREADS, 0, as_stream(stream)>>>(
-      dxbar, dpsum, x, qk, ld_qk, P, pbar, n, len, d_model, n_head, p_drop, (uint32_t)seed, dX, dqk);
+      dxbar, dpsum, x, qk, ld_qk, P, pbar, count, n, len, d_model, n_head, p_drop, (uint32_t)seed, dX, dqk);
   return tiger_launch_status();
 }
 
@@ -266,9 +274,10 @@ extern "C" int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, 
 // g_bv[h*hd + c] += sum_r psum[r, h] datt[r, h*hd + c],  dpsum[r, h] = sum_c datt[r, h*hd + c] b_v[h*hd + c]
 // ------------------------------------------------------------------------------------------
 __global__ void train_seq_vbias_kernel(float* __restrict__ att, const float* __restrict__ psum,
-                                       const float* __restrict__ bv, int64_t n, int dm, int n_head) {
+                                       const float* __restrict__ bv, const int32_t* __restrict__ count, int64_t n,
+                                       int dm, int n_head) {
   const int hd = dm / n_head;
-  const int64_t total = n * dm;
+  const int64_t total = seq_rows(count, n) * dm;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / dm;
     const int c = (int)(i % dm);
@@ -276,19 +285,21 @@ __global__ void train_seq_vbias_kernel(float* __restrict__ att, const float* __r
   }
 }
 
-extern "C" int tiger_train_seq_vbias(float* att, const float* psum, const float* bv, int64_t n, int d_model, int n_head,
-                                     void* stream) {
+extern "C" int tiger_train_seq_vbias(float* att, const float* psum, const float* bv, const int32_t* count, int64_t n,
+                                     int d_model, int n_head, void* stream) {
   if (att == nullptr || psum == nullptr || bv == nullptr || n < 0 || d_model <= 0 || n_head <= 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
   int64_t grid = (n * d_model + 255) / 256;
   if (grid > 148 * 8) grid = 148 * 8;
-  train_seq_vbias_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(att, psum, bv, n, d_model, n_head);
+  train_seq_vbias_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(att, psum, bv, count, n, d_model, n_head);
   return tiger_launch_status();
 }
 
 __global__ void __launch_bounds__(256)
 train_seq_vbias_bwd_kernel(const float* __restrict__ datt, const float* __restrict__ psum, const float* __restrict__ bv,
-                           int64_t n, int dm, int n_head, float* __restrict__ g_bv, float* __restrict__ dpsum) {
+                           const int32_t* __restrict__ count, int64_t n_cap, int dm, int n_head,
+                           float* __restrict__ g_bv, float* __restrict__ dpsum) {
+  const int64_t n = seq_rows(count, n_cap);
   // one warp per (row, head) for dpsum; the bias gradient is accumulated by a second pass of column owners
   const int hd = dm / n_head;
   const int lane = lane_id();
@@ -311,8 +322,8 @@ train_seq_vbias_bwd_kernel(const float* __restrict__ datt, const float* __restri
   }
 }
 
-extern "C" int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, const float* bv, int64_t n, int d_model,
-                                         int n_head, float* g_bv, float* dpsum, void* stream) {
+extern "C" int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, const float* bv, const int32_t* count,
+                                         int64_t n, int d_model, int n_head, float* g_bv, float* dpsum, void* stream) {
   if (datt == nullptr || psum == nullptr || bv == nullptr || g_bv == nullptr || dpsum == nullptr || n < 0 ||
       d_model <= 0 || n_head <= 0)
     return TIGER_EINVAL;
@@ -321,8 +332,8 @@ extern "C" int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, c
   const int64_t need = (d_model + 255) / 256;
   if (grid < need) grid = need;
   if (grid > 148 * 4) grid = 148 * 4;
-  train_seq_vbias_bwd_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(datt, psum, bv, n, d_model, n_head, g_bv,
-                                                                           dpsum);
+  train_seq_vbias_bwd_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(datt, psum, bv, count, n, d_model, n_head,
+                                                                           g_bv, dpsum);
   return tiger_launch_status();
 }
 
@@ -331,7 +342,8 @@ extern "C" int tiger_train_seq_vbias_bwd(const float* datt, const float* psum, c
 // time code cos((t_last - t_j) w + b); the last position keeps only its time code.  One warp per token.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-train_seq_tokens_bwd_kernel(const float* __restrict__ dX, int64_t n, int len, const int64_t* __restrict__ anony_ids,
+train_seq_tokens_bwd_kernel(const float* __restrict__ dX, const int32_t* __restrict__ count, int64_t n, int len,
+                            const int64_t* __restrict__ anony_ids,
                             const float* __restrict__ hist_ts, int d, int de, const float* __restrict__ time_w,
                             const float* __restrict__ time_b, float* __restrict__ g_anony, float* __restrict__ g_w,
                             float* __restrict__ g_b) {
@@ -342,7 +354,7 @@ train_seq_tokens_bwd_kernel(const float* __restrict__ dX, int64_t n, int len, co
   __syncthreads();
   const int lane = lane_id();
   const int64_t dm = 4 * (int64_t)d + de;
-  const int64_t total = n * len;
+  const int64_t total = seq_rows(count, n) * len;
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block(); r < total; r += n_warps) {
     const int64_t i = r / len;
@@ -369,7 +381,8 @@ train_seq_tokens_bwd_kernel(const float* __restrict__ dX, int64_t n, int len, co
   }
 }
 
-extern "C" int tiger_train_seq_tokens_bwd(const float* dX, int64_t n, int len, const int64_t* anony_ids,
+extern "C" int tiger_train_seq_tokens_bwd(const float* dX, const int32_t* count, int64_t n, int len,
+                                          const int64_t* anony_ids,
                                           const float* hist_ts, int d, int de, const float* time_w, const float* time_b,
                                           float* g_anony_emb, float* g_time_w, float* g_time_b, void* stream) {
   if (dX == nullptr || anony_ids == nullptr || hist_ts == nullptr || time_w == nullptr || time_b == nullptr ||
@@ -379,37 +392,44 @@ extern "C" int tiger_train_seq_tokens_bwd(const float* dX, int64_t n, int len, c
   int64_t grid = (n * len + 7) / 8;
   if (grid > 148 * 2) grid = 148 * 2;
   train_seq_tokens_bwd_kernel<<<(unsigned)grid, 256, 2 * d * sizeof(float), as_stream(stream)>>>(
-      dX, n, len, anony_ids, hist_ts, d, de, time_w, time_b, g_anony_emb, g_time_w, g_time_b);
+      dX, count, n, len, anony_ids, hist_ts, d, de, time_w, time_b, g_anony_emb, g_time_w, g_time_b);
   return tiger_launch_status();
 }
 
 // x[i] = keep(i) ? x[i] / (1 - p) : 0 in place (nn.Dropout in training mode; MergeLayer, basic_modules.py:16-19)
-__global__ void train_dropout_kernel(float* __restrict__ x, int64_t n, float p, uint32_t seed, uint32_t stream_id) {
+__global__ void train_dropout_kernel(float* __restrict__ x, const int32_t* __restrict__ count, int64_t per,
+                                     int64_t n_cap, float p, uint32_t seed, uint32_t stream_id) {
   const float inv_keep = 1.0f / (1.0f - p);
+  const int64_t n = seq_rows(count, n_cap, per);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     x[i] = seq_keep(seed, stream_id, (uint32_t)i, p) ? x[i] * inv_keep : 0.f;
 }
 
-extern "C" int tiger_train_dropout(float* x, int64_t n, float p_drop, int seed, int stream_id, void* stream) {
+extern "C" int tiger_train_dropout(float* x, const int32_t* count, int64_t per_count, int64_t n, float p_drop, int seed,
+                                   int stream_id, void* stream) {
   if (x == nullptr || n < 0 || p_drop < 0.f || p_drop >= 1.f) return TIGER_EINVAL;
   if (n == 0 || p_drop == 0.f) return TIGER_OK;
   int64_t grid = (n + 255) / 256;
   if (grid > 148 * 8) grid = 148 * 8;
-  train_dropout_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(x, n, p_drop, (uint32_t)seed, (uint32_t)stream_id);
+  train_dropout_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(x, count, per_count > 0 ? per_count : 1, n, p_drop,
+                                                                     (uint32_t)seed, (uint32_t)stream_id);
   return tiger_launch_status();
 }
 
 // y[i] += alpha * x[i]
-__global__ void train_axpy_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n, float alpha) {
+__global__ void train_axpy_kernel(float* __restrict__ y, const float* __restrict__ x, const int32_t* __restrict__ count,
+                                  int64_t per, int64_t n_cap, float alpha) {
+  const int64_t n = seq_rows(count, n_cap, per);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = fmaf(alpha, x[i], y[i]);
 }
 
-extern "C" int tiger_train_axpy(float* y, const float* x, int64_t n, float alpha, void* stream) {
+extern "C" int tiger_train_axpy(float* y, const float* x, const int32_t* count, int64_t per_count, int64_t n, float alpha,
+                                void* stream) {
   if (y == nullptr || x == nullptr || n < 0) return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
   int64_t grid = (n + 255) / 256;
   if (grid > 148 * 8) grid = 148 * 8;
-  train_axpy_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(y, x, n, alpha);
+  train_axpy_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(y, x, count, per_count > 0 ? per_count : 1, n, alpha);
   return tiger_launch_status();
 }

@@ -82,3 +82,31 @@ def perturb_biases(W: Dict[str, torch.Tensor], seed: int = 1, scale: float = 0.2
         if (k.endswith('bias') or k.endswith('phase')) and float(v.abs().max()) == 0.0:
             out[k] = torch.randn(v.shape, generator=g) * scale
     return out
+
+
+def build_model(nfeats, efeats, graph, n_nodes: int, n_edges: int, device, *, dim, n_layers=1, n_heads=2, n_neighbors=10,
+                hit_type='bin', dropout=0.1, restarter_type='seq', hist_len=40, msg_src='left', upd_src='right',
+                msg_tsfm_type='id', mem_update_type='gru'):
+    """The drop-in TIGER model wired exactly like the reference's init_utils.init_model (init_utils.py:126-168), from
+    this package's classes; `efeats` / `nfeats` may already be device tensors (large tables are generated in HBM)."""
+    from .tiger.model.feature_getter import NumericalFeature
+    from .tiger.model.restarters import SeqRestarter, StaticRestarter
+    from .tiger.model.tiger import TIGER
+    as_t = lambda x: None if x is None else torch.as_tensor(x).float()
+    nfeats, efeats = as_t(nfeats), as_t(efeats)
+    if nfeats is not None:
+        dim = nfeats.shape[1] if dim is None else dim
+    if efeats is not None:
+        dim = efeats.shape[1] if dim is None else dim
+    getter = NumericalFeature(nfeats, efeats, dim=dim, register_buffer=True, device=device)
+    getter.n_nodes, getter.n_edges = n_nodes, n_edges
+    if restarter_type == 'seq':
+        restarter = SeqRestarter(raw_feat_getter=getter, graph=graph, hist_len=hist_len, n_head=n_heads, dropout=dropout)
+    elif restarter_type == 'static':
+        restarter = StaticRestarter(raw_feat_getter=getter, graph=graph)
+    else:
+        raise NotImplementedError(restarter_type)
+    model = TIGER(raw_feat_getter=getter, graph=graph, restarter=restarter, n_neighbors=n_neighbors, hit_type=hit_type,
+                  n_layers=n_layers, n_head=n_heads, dropout=dropout, msg_src=msg_src, upd_src=upd_src,
+                  msg_tsfm_type=msg_tsfm_type, mem_update_type=mem_update_type, tgn_mode=True, msg_last_only=True)
+    return model.to(device)

@@ -69,6 +69,15 @@ class Graph:
         self.csr = ops.csr_build(src, dst, ts, eids, self.num_node)
         return self
 
+    @classmethod
+    def from_csr(cls, csr: 'ops.DeviceCSR', strategy='recent_edges', seed=None):
+        """Wrap a device CSR that already exists (ops.csr_build over a stream resident in HBM)."""
+        self = cls.__new__(cls)
+        self.strategy, self.seed, self.alpha = strategy, seed, 0.0
+        self.num_node = csr.n_nodes
+        self.csr = csr
+        return self
+
     @property
     def device(self) -> torch.device:
         return self.csr.device

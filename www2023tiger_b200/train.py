@@ -175,30 +175,47 @@ class NativeTrainer:
     # ------------------------------------------------------------------ forward
     def forward(self, src: Tensor, dst: Tensor, neg: Tensor, ts: Tensor, eids: Tensor, cg, *, contrast_only: bool = False,
                 train: bool = True) -> Tuple[Tensor, Tensor]:
-        """-> (contrast_loss [1], mutual_loss [1]) device tensors; memory state advanced like the reference's
-        contrast_and_mutual_learning.  `train=False` switches dropout off (eval-mode forward of the same program)."""
+        """The drop-in entry (batch + ComputationGraph from GraphCollator) -> (contrast_loss [1], mutual_loss [1])
+        device tensors; memory state advanced like the reference's contrast_and_mutual_learning.  `train=False`
+        switches dropout off (eval-mode forward of the same program)."""
         m = self.model
-        B, K, H, d, de, E, C, M, cap = len(src), self.K, self.H, self.d, self.de, self.E, self.C, self.M, self.cap
+        B = len(src)
         assert B <= self.B
-        nq = 3 * B
-        P, G = self.fp.p, self.fp.g
-        self.n_steps += 1
-        seed = (self.seed * 1000003 + self.n_steps) & 0x7fffffff
-        p_attn = self.p_attn if train else 0.0
-        p_score = self.p_score if train else 0.0
         nn_, ne_, nt_ = cg.layers[1]
         batch_nids = torch.cat([src, dst, neg]).contiguous()
-        pos = batch_nids[:2 * B]
         ts = ts.to(f32).contiguous()
-        eids = eids.contiguous()
+        # pending set of the involved nodes (tiger.py:206-209)
+        ops.mark_nodes(cg.computation_graph_nodes.contiguous(), self.bitmap, m.n_nodes)
+        ops.compact_involved(self.bitmap, m.n_nodes, self.involved, self.counts, has_msg=m.msg_store.has_msg,
+                             outdated=self.outdated, gru_row=self.gru_row, err_flags=self.err)
+        hits = torch.stack(list(cg.hit_data)).to(f32).contiguous() if m.hit_type == 'bin' else None     # [4, B, K]
+        rd = cg.restart_data
+        targets = None
+        if not contrast_only:
+            hist = None
+            if self.rkind == 'seq':
+                hist = tuple(t.contiguous() for t in (rd.hist_nids, rd.hist_eids, rd.hist_ts, rd.hist_dirs,
+                                                      rd.anonymized_ids))
+            targets = dict(nids=rd.nids.contiguous(), index=rd.index.contiguous(), n=rd.nids.numel(), count=None, hist=hist)
+        return self._core(B, batch_nids, ts, eids.contiguous(), nn_, ne_, nt_, hits=hits, hits_from_table=False,
+                          targets=targets, train=train)
+
+    def _core(self, B, batch_nids, ts, eids, nn_, ne_, nt_, *, hits, hits_from_table, targets, train):
+        """Steps 1-7 of TIGE.contrast_learning + the restarter targets, after the involved / pending compaction."""
+        m = self.model
+        K, H, d, de, E, C, M, cap = self.K, self.H, self.d, self.de, self.E, self.C, self.M, self.cap
+        nq = 3 * B
+        P = self.fp.p
+        self.n_steps += 1
+        seed = (self.seed * 1000003 + self.n_steps * 101) & 0x7fffffff
+        p_attn = self.p_attn if train else 0.0
+        p_score = self.p_score if train else 0.0
+        pos = batch_nids[:2 * B]
         left, right, store = m.left_memory, m.right_memory, m.msg_store
         msg_mem, upd_mem = m.msg_memory, m.upd_memory
         fg = m.raw_feat_getter
         cnt_o = self.counts[1:]
-        # ---- steps 1-2: pending set, gather, GRU (tiger.py:206-221)
-        ops.mark_nodes(cg.computation_graph_nodes.contiguous(), self.bitmap, m.n_nodes)
-        ops.compact_involved(self.bitmap, m.n_nodes, self.involved, self.counts, has_msg=store.has_msg,
-                             outdated=self.outdated, gru_row=self.gru_row, err_flags=self.err)
+        # ---- steps 1-2: gather of the pending messages, GRU (tiger.py:206-221)
         call('tiger_train_gather_pending', ptr(self.outdated), ptr(cnt_o), cap, ptr(store.node_msg_vals), M,
              ptr(store.node_msg_ts), ptr(upd_mem.vals), d, ptr(msg_mem.update_ts), int(m.msg_src == 'left'),
              ptr(self.X), ptr(self.Hs), ptr(self.dh_new), ptr(self.err))
@@ -230,30 +247,25 @@ class NativeTrainer:
         ops.right_writeback(pos, winner, self.gru_row, self.h_new, d, right.vals, right.update_ts, right.active_mask,
                             store.node_msg_ts, store.has_msg, left.vals, self.hprev_left, self.hprev_right, self.err)
         # ---- step 7: link scorer (tiger.py:259-288)
-        hits = None
-        if m.hit_type == 'bin':
-            hits = torch.stack(list(cg.hit_data)).to(f32).contiguous()          # [4, B, K]
-        call('tiger_train_score_build', ptr(self.z), ptr(hits), K, ptr(P['hit_embedding.weight']) if hits is not None
-             else None, B, d, ptr(self.pair), ptr(self.codes) if hits is not None else None)
+        use_hits = hits is not None or hits_from_table
+        call('tiger_train_score_build', ptr(self.z), ptr(hits), ptr(nn_) if hits_from_table else None,
+             ptr(batch_nids) if hits_from_table else None, K, ptr(P['hit_embedding.weight']) if use_hits else None, B, d,
+             ptr(self.pair), ptr(self.codes) if use_hits else None)
         s = 'score_fn.'
         _linear_fwd(self.pair, P[s + 'fc1.weight'], P[s + 'fc1.bias'], self.hid_s, m=2 * B, relu=True)
         call('tiger_train_score_head', ptr(self.hid_s), ptr(P[s + 'fc2.weight']), ptr(P[s + 'fc2.bias']), B, d, p_score,
              seed, ptr(self.scores), ptr(self.closs), ptr(self.dscore))
         # ---- restarter on the collated batch + mutual loss (tiger.py:574-590)
-        n_pos = 0
-        rd = cg.restart_data
-        if not contrast_only:
-            n_pos = rd.nids.numel()
-            nids = rd.nids.contiguous()
+        if targets is not None:
+            n_pos, nids, cnt = targets['n'], targets['nids'], targets['count']
             if self.rkind == 'static':
-                call('tiger_gather_rows', ptr(P['restarter_fn.left_emb.weight']), d, ptr(nids), n_pos, ptr(self.pred_l),
-                     None, None)
-                call('tiger_gather_rows', ptr(P['restarter_fn.right_emb.weight']), d, ptr(nids), n_pos, ptr(self.pred_r),
-                     None, None)
+                for side, out in (('left', self.pred_l), ('right', self.pred_r)):
+                    call('tiger_gather_rows', ptr(P[f'restarter_fn.{side}_emb.weight']), d, ptr(nids), n_pos, ptr(out),
+                         None, None)
             else:
-                self.seq.forward(nids, rd, fg, self.pred_l, self.pred_r, seed, train)
+                self.seq.forward(nids, targets['hist'], fg, self.pred_l, self.pred_r, seed, train, n=n_pos, count=cnt)
             call('tiger_train_mse', ptr(self.pred_l), ptr(self.pred_r), ptr(self.hprev_left), ptr(self.hprev_right),
-                 ptr(rd.index.contiguous()), None, n_pos, d, ptr(self.mloss), ptr(self.dpred_l), ptr(self.dpred_r))
+                 ptr(targets['index']), ptr(cnt), n_pos, d, ptr(self.mloss), ptr(self.dpred_l), ptr(self.dpred_r))
         else:
             self.mloss.zero_()
         # ---- steps 5-6 (tiger.py:244-255), no grad
@@ -261,10 +273,101 @@ class NativeTrainer:
                            fg.nfeats, fg.efeats, d, de, tw, tb, store.node_msg_vals, store.node_msg_ts, store.has_msg,
                            self.err)
         ops.left_writeback(pos, B, winner, self.z, d, ts, left.vals, left.update_ts, left.active_mask, self.err)
-        self._ctx = dict(B=B, batch_nids=batch_nids, ts=ts, nn=nn_, nt=nt_, hits=hits is not None, n_pos=n_pos,
-                         nids=rd.nids if not contrast_only else None, p_attn=p_attn, p_score=p_score, seed=seed,
-                         keepalive=(ne_, hits, rd))
+        self._ctx = dict(B=B, batch_nids=batch_nids, ts=ts, nn=nn_, nt=nt_, hits=use_hits, targets=targets,
+                         p_attn=p_attn, p_score=p_score, seed=seed, keepalive=(ne_, hits, eids))
         return self.closs, self.mloss
+
+    # ------------------------------------------------------------------ device-resident stream (bench / DDP loop)
+    def attach_stream(self, csr: ops.DeviceCSR, hist_len: int = 40):
+        """Buffers of the sync-free loop: the temporal neighbor finder, the lazy restart of not-yet-seen nodes and the
+        collation of the restarter targets all run on the device from one [5B] int64 batch record (layout of
+        TigerEngine.inp: src | dst | neg | eids | ts as float64 bits) - what GraphCollator + the driver's restart
+        bookkeeping (train_self_supervised_ddp.py:186-199) do on the host in the reference."""
+        m, dev, B, K, cap = self.model, self.device, self.B, self.K, self.cap
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)
+        self.csr, self.L = csr, hist_len
+        self.nn_, self.ne_, self.nt_ = z(3 * B, K, dt=i64), z(3 * B, K, dt=i64), z(3 * B, K)
+        self.ts32 = z(B)
+        self.uptodate = z(m.n_nodes, dt=u8)
+        self.restart_nodes = z(cap, dt=i64)
+        self.t_uniq, self.t_index, self.t_count = z(2 * B, dt=i64), z(2 * B, dt=i64), z(1, dt=i32)
+        self.t_winner = z(2 * B, dt=u8)
+        if self.rkind == 'seq':
+            L = hist_len
+            from .train_seq import SeqRestarterTrainer
+            self.seq = SeqRestarterTrainer(self.restarter, self.fp, 2 * B, dev, cap_fwd=cap)
+            self.tmin = z(1, dt=torch.float64)
+            mk = lambda n: (z(n, L, dt=i64), z(n, L, dt=i64), z(n, L), z(n, L, dt=i64), z(n, L, dt=i64))
+            self.r_hist, self.t_hist = mk(cap), mk(2 * B)
+            self.r_left, self.r_right = z(cap, self.d), z(cap, self.d)
+
+    def reset_stream(self):
+        self.model.reset()
+        self.model.msg_store.has_msg.zero_()
+        self.uptodate.zero_()
+
+    def forward_stream(self, inp: Tensor, *, lazy_restart: bool = True, train: bool = True):
+        m, B, K, d, cap = self.model, self.B, self.K, self.d, self.cap
+        assert inp.numel() == 5 * B and inp.dtype == i64
+        batch_nids, pos, eids = inp[:3 * B], inp[:2 * B], inp[3 * B:4 * B]
+        ts64 = inp[4 * B:].view(torch.float64)
+        left, right, store, fg = m.left_memory, m.right_memory, m.msg_store, m.raw_feat_getter
+        # ---- neighbor finder + involved / pending / restart lists (GraphCollator.collate_memory_nodes, the drivers'
+        #      restart sets) ----
+        ops.find_recent(self.csr, batch_nids, ts64, K, ts_period=B, want_dirs=False, ts32_out=self.ts32,
+                        bitmap=self.bitmap, out=(self.nn_, self.ne_, self.nt_, None))
+        ops.compact_involved(self.bitmap, m.n_nodes, self.involved, self.counts, has_msg=store.has_msg,
+                             uptodate=self.uptodate if lazy_restart else None, outdated=self.outdated,
+                             gru_row=self.gru_row, restart_nodes=self.restart_nodes if lazy_restart else None,
+                             err_flags=self.err)
+        seed0 = (self.seed * 1000003 + (self.n_steps + 1) * 101) & 0x7fffffff
+        if lazy_restart:                                            # TIGER.restart (tiger.py:594-609)
+            R = self.counts[2:]
+            if self.rkind == 'static':
+                P = self.fp.p
+                ops.static_restart(self.restart_nodes, cap, self.csr, P['restarter_fn.left_emb.weight'],
+                                   P['restarter_fn.right_emb.weight'], d, count=R, batch_ts=self.ts32,
+                                   left_vals=left.vals, left_ts=left.update_ts, left_active=left.active_mask,
+                                   right_vals=right.vals, right_ts=right.update_ts, right_active=right.active_mask,
+                                   has_msg=store.has_msg)
+            else:
+                ops.min_time(self.ts32, self.tmin)
+                hn, he, ht, hd, an = self.r_hist
+                ops.find_recent(self.csr, self.restart_nodes, self.tmin, self.L, ts_period=1, count=R,
+                                out=(hn, he, ht, hd))
+                ops.anonymized_reindex(hn, out=an, count=R)
+                # train() mode: the reference's restart applies the restarter's dropout (the call sits inside the
+                # training loop, train_self_supervised_ddp.py:193-199)
+                self.seq.forward(self.restart_nodes, self.r_hist, fg, self.r_left, self.r_right, seed0, train, n=cap,
+                                 count=R, seed_stream=1)
+                ops.scatter_rows(left.vals, self.restart_nodes, self.r_left, ts_table=left.update_ts, ts=self.seq.prev_ts,
+                                 active=left.active_mask, count=R)
+                ops.scatter_rows(right.vals, self.restart_nodes, self.r_right, ts_table=right.update_ts,
+                                 ts=self.seq.prev_ts, active=right.active_mask, count=R)
+        # ---- restarter targets: collate_restart_data (data_loader.py:95-168) on the device: unique positives by
+        #      float64 time, their histories at those times ----
+        call('tiger_select_latest', ptr(pos), ptr(ts64), 1, 2 * B, B, 0, None, None, None, ptr(self.t_winner),
+             ptr(self.t_uniq), ptr(self.t_index), ptr(self.t_count))
+        hist = None
+        if self.rkind == 'seq':
+            sel_ts = ts64[self.t_index % B]
+            hn, he, ht, hd, an = self.t_hist
+            ops.find_recent(self.csr, self.t_uniq, sel_ts, self.L, count=self.t_count, out=(hn, he, ht, hd))
+            ops.anonymized_reindex(hn, out=an, count=self.t_count)
+            hist = self.t_hist
+        targets = dict(nids=self.t_uniq, index=self.t_index, n=2 * B, count=self.t_count, hist=hist)
+        return self._core(B, batch_nids, self.ts32, eids, self.nn_, self.ne_, self.nt_, hits=None,
+                          hits_from_table=(m.hit_type == 'bin'), targets=targets, train=train)
+
+    def step_stream(self, inp: Tensor, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, allreduce=None,
+                    lr: Optional[float] = None):
+        closs, mloss = self.forward_stream(inp)
+        self.backward(1.0, mutual_coef)
+        work = allreduce(self.fp.grad) if allreduce is not None else None
+        if work is not None:
+            work.wait()
+        self.fp.adam(self.lr if lr is None else lr, grad_scale=grad_scale)
+        return closs, mloss
 
     # ------------------------------------------------------------------ backward
     def backward(self, g_contrast: float = 1.0, g_mutual: float = 1.0):
@@ -319,12 +422,12 @@ class NativeTrainer:
         _linear_bwd(self.dGh, self.Hs, P[c + 'weight_hh'], G[c + 'weight_hh'], G[c + 'bias_hh'], None, m=cap, k_parts=16,
                     count=cnt_o)
         # ---- restarter
-        if ctx['n_pos'] and g_mutual != 0.0:
-            n_pos, nids = ctx['n_pos'], ctx['nids'].contiguous()
+        tg = ctx['targets']
+        if tg is not None and g_mutual != 0.0:
             if self.rkind == 'static':
                 for side, dp in (('left', self.dpred_l), ('right', self.dpred_r)):
-                    call('tiger_train_scatter_add_rows', ptr(G[f'restarter_fn.{side}_emb.weight']), ptr(nids), n_pos, None,
-                         1, ptr(dp), d, d, float(g_mutual))
+                    call('tiger_train_scatter_add_rows', ptr(G[f'restarter_fn.{side}_emb.weight']), ptr(tg['nids']),
+                         tg['n'], ptr(tg['count']), 1, ptr(dp), d, d, float(g_mutual))
             else:
                 self.seq.backward(self.dpred_l, self.dpred_r, float(g_mutual))
 
