@@ -811,6 +811,17 @@ def check_train_parity(args, wl, model, tr):
         tr.check_errors()
         e_c = abs(float(c) - rc) / max(abs(rc), 1e-30)
         e_m = abs(float(m) - rm) / max(abs(rm), 1e-30)
+        if os.environ.get('TIGER_DEBUG_PARITY') == '1':
+            sd = ref.model.state_dict()
+            rows = []
+            for k, v in tr.fp.p.items():
+                dv = (v.detach().cpu() - sd[k]).abs()
+                rows.append((float(dv.max()) / tr.lr, k, float(dv.mean()) / tr.lr))
+            rows.sort(reverse=True)
+            print(f'[parity debug] step {j}: contrast {float(c):.7f} vs {rc:.7f}, mutual {float(m):.7f} vs {rm:.7f}; '
+                  f'parameter deviation in units of lr (max, mean):', file=sys.stderr)
+            for r in rows[:8]:
+                print(f'    {r[1]:60s} {r[0]:10.4f} {r[2]:10.6f}', file=sys.stderr)
         worst = [max(worst[0], e_c), max(worst[1], e_m)]
         if e_c > 1e-5 or e_m > 5e-5:
             raise SystemExit(f'train parity: step {j} contrast {float(c):.7f} vs {rc:.7f} ({e_c:.1e}), '

@@ -160,12 +160,14 @@ def test_training_through_torch_optimizer_and_native_adam_agree():
     assert la[-1] < la[0] or lb[-1] < lb[0] or True
 
 
+@pytest.mark.parametrize('dropout', [0.0, 0.1])
 @pytest.mark.parametrize('name', ['seq_left_right', 'static_right_right_dim10'])
-def test_dropout_step_is_seeded_and_consistent_with_finite_differences(name):
-    """With dropout on, forward and backward must use the same masks: the analytic gradient of a few scalar
-    parameters is compared with central differences of the (seeded, hence repeatable) forward."""
+def test_dropout_step_is_seeded_and_consistent_with_finite_differences(name, dropout):
+    """With dropout on, forward and backward must use the same masks: the analytic directional derivative along
+    random parameter directions is compared with central differences of the (seeded, hence repeatable) forward;
+    dropout 0 is the control (those gradients are pinned against the reference above)."""
     g = Golden(name)
-    dl, model = setup(g, dropout=0.1)
+    dl, model = setup(g, dropout=dropout)
     model.train()
     model.reset()
     batches = [to_dev(b) for _, b in zip(range(5), dl)]
@@ -182,19 +184,21 @@ def test_dropout_step_is_seeded_and_consistent_with_finite_differences(name):
 
     base = loss_at(100)
     assert loss_at(100) == base                      # same seed -> same masks -> bit-identical loss
-    assert loss_at(101) != base                      # another step, other masks
+    assert (loss_at(101) != base) == (dropout > 0)   # another step, other masks
     model.load_memory_state(tuple(s.clone() for s in snap))
     tr.n_steps = 100
     tr.fp.grad.zero_()
     tr.forward(*batches[4])
     tr.backward(1.0, 1.0)
-    grads = {k: cpu(v).copy() for k, v in tr.fp.g.items()}
-    # directional derivatives along random directions over ALL parameters: single ReLU kinks average out
+    grads = {k: v.clone() for k, v in tr.fp.g.items()}
+    # random directions over all parameters except the time-encoder frequencies (a frequency step of 1e-4 times a
+    # time difference of 1e3 s is far outside the linear regime)
     gen = torch.Generator(device='cuda').manual_seed(5)
     for trial in range(3):
-        direction = {k: torch.randn(v.shape, device='cuda', generator=gen) for k, v in tr.fp.p.items()}
-        an = sum(float((torch.from_numpy(grads[k]).cuda() * direction[k]).sum()) for k in direction)
-        eps = 1e-3
+        direction = {k: (torch.zeros_like(v) if k.endswith('basis_freq') else
+                         torch.randn(v.shape, device='cuda', generator=gen)) for k, v in tr.fp.p.items()}
+        an = sum(float((grads[k].double() * direction[k].double()).sum()) for k in direction)
+        eps = 2e-4
         for k, v in tr.fp.p.items():
             v.add_(direction[k], alpha=eps)
         up = loss_at(100)
@@ -204,7 +208,8 @@ def test_dropout_step_is_seeded_and_consistent_with_finite_differences(name):
         for k, v in tr.fp.p.items():
             v.add_(direction[k], alpha=eps)
         fd = (up - dn) / (2 * eps)
-        assert abs(fd - an) <= 0.03 * max(abs(fd), abs(an)) + 1e-3, f'{name} trial {trial}: fd {fd:.5f} vs analytic {an:.5f}'
+        assert abs(fd - an) <= 0.02 * max(abs(fd), abs(an)) + 2e-3, \
+            f'{name} p={dropout} trial {trial}: fd {fd:.5f} vs analytic {an:.5f}'
 
 
 # ------------------------------------------------------------------------------------------
