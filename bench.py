@@ -632,7 +632,7 @@ def run_train(args):
     tr = model.native_trainer(B, lr=lr, seed=args.seed)
     tr.attach_stream(wl.csr, HIST_LEN)
     losses = torch.zeros(2, device=dev)
-    comm = {'bytes': tr.fp.numel * 4 if world > 1 else 0}
+    comm = {'bytes': tr.fp.grad_all.numel() * 4 if world > 1 else 0}
 
     def allreduce(t):
         return dist.all_reduce(t, async_op=True) if world > 1 else None
@@ -798,7 +798,7 @@ def check_train_parity(args, wl, model, tr):
                                       hist_len=HIST_LEN, batch=BATCH, seed=args.seed, dropout=0.0)
     ref.reset(train=True)
     saved = {k: v.clone() for k, v in tr.fp.p.items()}
-    keep = (tr.p_attn, tr.p_score, tr.fp.step)
+    keep = (tr.p_attn, tr.p_score)
     tr.p_attn = tr.p_score = 0.0
     if tr.rkind == 'seq':
         p_seq, tr.seq.p = tr.seq.p, 0.0
@@ -829,8 +829,8 @@ def check_train_parity(args, wl, model, tr):
     # back to the initial parameters / optimizer state for the timed run
     for k, v in saved.items():
         tr.fp.p[k].copy_(v)
-    tr.fp.exp_avg.zero_(), tr.fp.exp_avg_sq.zero_(), tr.fp.grad.zero_()
-    tr.p_attn, tr.p_score, tr.fp.step = keep
+    tr.fp.reset_optimizer()
+    tr.p_attn, tr.p_score = keep
     if tr.rkind == 'seq':
         tr.seq.p = p_seq
     return {'against': 'reference', 'steps': n, 'what': 'contrast and mutual loss of consecutive optimisation steps '

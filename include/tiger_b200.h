@@ -494,7 +494,7 @@ int tiger_pipe_join(void* pipe, void* stream);
  *   colsum / relu_bwd / zero_rows / scatter_add_rows   bias gradients, ReLU, masked rows, nn.Embedding gradients
  *   adam                                torch.optim.Adam defaults (train_self_supervised.py:116) on a flat buffer
  * --------------------------------------------------------------------------------------------------------- */
-int tiger_train_gather_pending(const int64_t* ids, const int32_t* count, int64_t cap, const float* msg_vals, int m_dim, const float* msg_ts, const float* upd_vals, int d, const float* check_mem_ts, int check_equal, float* X, float* H, float* dh_zero, uint32_t* err_flags, void* stream);
+int tiger_train_gather_pending(const int64_t* ids, const int32_t* count, int64_t cap, const float* msg_vals, int m_dim, const float* msg_ts, const float* upd_vals, int d, const float* check_mem_ts, int check_equal, float* X, float* H, float* dh_zero, uint32_t* err_flags, float* n_rows_out, void* stream);
 int tiger_train_gru_gates(const float* Gi, const float* Gh, const float* H, const int32_t* count, int64_t cap, int d, float* h_new, float* r_out, float* z_out, float* n_out, void* stream);
 int tiger_train_gru_gates_bwd(const float* dh, const float* r_in, const float* z_in, const float* n_in, const float* Gh, const float* H, const int32_t* count, int64_t cap, int d, float* dGi, float* dGh, void* stream);
 int tiger_train_attn_build(const int64_t* center, int64_t n_q, const float* ts, int64_t batch, const int64_t* neigh_nids, const int64_t* neigh_eids, const float* neigh_ts, int k, const float* rows_a, const float* rows_b, const int32_t* sel, const float* nfeats, const float* efeats, int d, int de, const float* time_w, const float* time_b, float* q_in, float* kv_in, float* cat, int64_t ld_cat, int cat_off, void* stream);
@@ -509,8 +509,8 @@ int tiger_train_score_build(const float* z, const float* hits, const int64_t* ne
 int tiger_train_score_head(float* hid, const float* fc2_w, const float* fc2_b, int64_t batch, int d, float p_drop, int seed, float* scores, float* loss, float* dscore, void* stream);
 int tiger_train_score_head_bwd(const float* dscore, float g, const float* hid, const float* fc2_w, int64_t batch, int d, float p_drop, float* dhid, float* g_fc2_w, float* g_fc2_b, void* stream);
 int tiger_train_score_build_bwd(const float* dpair, const uint8_t* codes, int64_t batch, int d, float* dz, float* g_hit_emb, void* stream);
-int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev_left, const float* hprev_right, const int64_t* index, const int32_t* count, int64_t n, int d, float* loss, float* dpred_l, float* dpred_r, void* stream);
-int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale, int zero_grad, void* stream);
+int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev_left, const float* hprev_right, const int64_t* index, const int32_t* count, int64_t n, int d, float* loss, float* dpred_l, float* dpred_r, float* n_valid_out, void* stream);
+int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_start, const int32_t* seg_group, int32_t* seg_step, float* seg_bc, int n_seg, float* gates, int64_t max_seg, float lr, float beta1, float beta2, float eps, float grad_scale, int zero_grad, void* stream);
 
 
 /* Seq-restarter training step (csrc/train_seq.cu): SeqRestarter.forward under autograd (restarters.py:51-114 as

@@ -47,6 +47,10 @@ def unique_named_params(model):
     return out
 
 
+def grad_of(p):
+    return cpu(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+
+
 def check_grads(got: dict, want: dict, what: str, tol=GRAD_TOL):
     assert set(got) == set(want), set(got) ^ set(want)
     for k in want:
@@ -79,7 +83,7 @@ def test_native_step_matches_reference_gradients(name):
         assert_close(cpu(contrast).reshape(1), g.b(ib, 'contrast').reshape(1), 1e-5, what + ' contrast')
         assert_close(cpu(mutual).reshape(1), g.b(ib, 'mutual').reshape(1), 2e-5, what + ' mutual')
         if g.has(ib, 'g_' + params[0][0]):
-            got = {k: cpu(p.grad) for k, p in params}
+            got = {k: grad_of(p) for k, p in params}
             want = {k: g.b(ib, 'g_' + k) for k, _ in params}
             check_grads(got, want, what)
     model._trainer.check_errors()
@@ -109,29 +113,47 @@ def test_native_step_matches_autograd_route(name, monkeypatch):
         what = f'{name} b{ib}'
         assert_close(cpu(c1).reshape(1), cpu(c2).reshape(1), 1e-5, what + ' contrast')
         assert_close(cpu(m1).reshape(1), cpu(m2).reshape(1), 2e-5, what + ' mutual')
-        got = {k: cpu(p.grad) for k, p in unique_named_params(native)}
-        want = {k: (cpu(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
-                for k, p in unique_named_params(ref)}
+        got = {k: grad_of(p) for k, p in unique_named_params(native)}
+        want = {k: grad_of(p) for k, p in unique_named_params(ref)}
+        # tensors without a gradient are the same on both routes (torch optimizers skip them)
+        assert [p.grad is None for _, p in unique_named_params(native)] == \
+            [p.grad is None for _, p in unique_named_params(ref)], what
         check_grads(got, want, what)
         assert_close(cpu(native.right_memory.vals), cpu(ref.right_memory.vals), 1e-5, what + ' right memory')
         assert_close(cpu(native.left_memory.vals), cpu(ref.left_memory.vals), 1e-5, what + ' left memory')
 
 
 def test_adam_kernel_equals_torch_adam():
+    """Flat segmented Adam vs torch.optim.Adam, including torch's per-tensor step counters: a tensor whose gradient
+    is None in a step (here: the gated tensor in steps 1-2) is skipped and its bias correction starts later."""
     gen = torch.Generator(device='cuda').manual_seed(0)
-    n = 100_003
-    p0 = torch.randn(n, device='cuda', generator=gen)
-    p_ref = torch.nn.Parameter(p0.clone())
-    opt = torch.optim.Adam([p_ref], lr=1e-3)
-    p, m, v = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
-    for step in range(1, 6):
-        grad = torch.randn(n, device='cuda', generator=gen) * 10 ** float(step - 3)
-        p_ref.grad = grad.clone()
+    sizes = [100_003, 517, 4096]
+    offs = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])])
+    total = int(offs[-1])
+    flat = torch.randn(total, device='cuda', generator=gen)
+    refs = [torch.nn.Parameter(flat[offs[i]:offs[i] + n].clone()) for i, n in enumerate(sizes)]
+    opt = torch.optim.Adam(refs, lr=1e-3)
+    gbuf = torch.zeros(total + 4, device='cuda')
+    m, v = torch.zeros(total, device='cuda'), torch.zeros(total, device='cuda')
+    seg_start = torch.tensor(offs, dtype=torch.int64, device='cuda')
+    seg_group = torch.tensor([0, 1, 0], dtype=torch.int32, device='cuda')
+    seg_step = torch.zeros(3, dtype=torch.int32, device='cuda')
+    seg_bc = torch.zeros(6, device='cuda')
+    for step in range(1, 7):
+        gate_on = step >= 3
+        for i, n in enumerate(sizes):
+            grad = torch.randn(n, device='cuda', generator=gen) * 10 ** float(step - 3)
+            used = i != 1 or gate_on
+            refs[i].grad = grad.clone() if used else None
+            gbuf[offs[i]:offs[i] + n] = grad * 4 if used else 0.0     # grad_scale folds the 1 / world_size
+        gbuf[total] = 5.0 if gate_on else 0.0
         opt.step()
-        gbuf = (grad * 4).clone()                       # grad_scale folds the 1 / world_size of the all-reduce
-        call('tiger_train_adam', ptr(p), ptr(gbuf), ptr(m), ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, step, 0.25, 1)
-        assert float(gbuf.abs().max()) == 0.0           # zero_grad
-        assert_close(cpu(p), cpu(p_ref), 1e-6, f'adam step {step}')
+        call('tiger_train_adam', ptr(flat), ptr(gbuf), ptr(m), ptr(v), ptr(seg_start), ptr(seg_group), ptr(seg_step),
+             ptr(seg_bc), 3, ptr(gbuf[total:]), max(sizes), 1e-3, 0.9, 0.999, 1e-8, 0.25, 1)
+        assert float(gbuf.abs().max()) == 0.0           # zero_grad (gradients and gates)
+        for i, n in enumerate(sizes):
+            assert_close(cpu(flat[offs[i]:offs[i] + n]), cpu(refs[i]), 1e-6, f'adam step {step} tensor {i}')
+    assert seg_step.tolist() == [6, 4, 6]
 
 
 def test_training_through_torch_optimizer_and_native_adam_agree():
@@ -156,8 +178,7 @@ def test_training_through_torch_optimizer_and_native_adam_agree():
     tr.check_errors()
     # same algorithm, same data; Adam normalises gradients, so round-off in near-zero gradients may move single
     # weights differently - the loss trajectories must still agree closely
-    assert np.allclose(la, lb, rtol=2e-3), (la, lb)
-    assert la[-1] < la[0] or lb[-1] < lb[0] or True
+    assert np.allclose(la, lb, rtol=1e-4), (la, lb)
 
 
 @pytest.mark.parametrize('dropout', [0.0, 0.1])
@@ -180,36 +201,40 @@ def test_dropout_step_is_seeded_and_consistent_with_finite_differences(name, dro
         model.load_memory_state(tuple(s.clone() for s in snap))
         tr.n_steps = step_id
         c, m = tr.forward(*batches[4])
-        return float(c) + float(m)
+        return float(c), float(m)
 
     base = loss_at(100)
-    assert loss_at(100) == base                      # same seed -> same masks -> bit-identical loss
+    assert loss_at(100) == base                      # same seed -> same masks -> bit-identical losses
     assert (loss_at(101) != base) == (dropout > 0)   # another step, other masks
-    model.load_memory_state(tuple(s.clone() for s in snap))
-    tr.n_steps = 100
-    tr.fp.grad.zero_()
-    tr.forward(*batches[4])
-    tr.backward(1.0, 1.0)
-    grads = {k: v.clone() for k, v in tr.fp.g.items()}
-    # random directions over all parameters except the time-encoder frequencies (a frequency step of 1e-4 times a
-    # time difference of 1e3 s is far outside the linear regime)
-    gen = torch.Generator(device='cuda').manual_seed(5)
-    for trial in range(3):
-        direction = {k: (torch.zeros_like(v) if k.endswith('basis_freq') else
-                         torch.randn(v.shape, device='cuda', generator=gen)) for k, v in tr.fp.p.items()}
-        an = sum(float((grads[k].double() * direction[k].double()).sum()) for k in direction)
-        eps = 2e-4
-        for k, v in tr.fp.p.items():
-            v.add_(direction[k], alpha=eps)
-        up = loss_at(100)
-        for k, v in tr.fp.p.items():
-            v.add_(direction[k], alpha=-2 * eps)
-        dn = loss_at(100)
-        for k, v in tr.fp.p.items():
-            v.add_(direction[k], alpha=eps)
-        fd = (up - dn) / (2 * eps)
-        assert abs(fd - an) <= 0.02 * max(abs(fd), abs(an)) + 2e-3, \
-            f'{name} p={dropout} trial {trial}: fd {fd:.5f} vs analytic {an:.5f}'
+    # the two losses are checked separately: the restarter's targets depend on the other parameters but are detached
+    # (tiger.py:590), so the mutual loss is differentiated w.r.t. the restarter only, the contrast loss w.r.t. the rest;
+    # the time-encoder frequencies are left out (a frequency step times a time difference of 1e3 s is far outside
+    # the linear regime)
+    for which, own, (gc, gm) in ((0, lambda k: not k.startswith('restarter_fn.'), (1.0, 0.0)),
+                                 (1, lambda k: k.startswith('restarter_fn.'), (0.0, 1.0))):
+        model.load_memory_state(tuple(s.clone() for s in snap))
+        tr.n_steps = 100
+        tr.fp.grad_all.zero_()
+        tr.forward(*batches[4])
+        tr.backward(gc, gm)
+        grads = {k: v.clone() for k, v in tr.fp.g.items()}
+        gen = torch.Generator(device='cuda').manual_seed(5)
+        for trial in range(3):
+            direction = {k: (torch.randn(v.shape, device='cuda', generator=gen) if own(k) and not k.endswith('basis_freq')
+                             else torch.zeros_like(v)) for k, v in tr.fp.p.items()}
+            an = sum(float((grads[k].double() * direction[k].double()).sum()) for k in direction)
+            eps = 2e-4
+            for k, v in tr.fp.p.items():
+                v.add_(direction[k], alpha=eps)
+            up = loss_at(100)[which]
+            for k, v in tr.fp.p.items():
+                v.add_(direction[k], alpha=-2 * eps)
+            dn = loss_at(100)[which]
+            for k, v in tr.fp.p.items():
+                v.add_(direction[k], alpha=eps)
+            fd = (up - dn) / (2 * eps)
+            assert abs(fd - an) <= 0.02 * max(abs(fd), abs(an)) + 2e-3, \
+                f'{name} p={dropout} loss {which} trial {trial}: fd {fd:.5f} vs analytic {an:.5f}'
 
 
 # ------------------------------------------------------------------------------------------
@@ -249,8 +274,10 @@ def test_native_step_matches_autograd_route_at_baseline_dimensions(name, monkeyp
         what = f'{name} b{ib}'
         assert_close(cpu(c1).reshape(1), cpu(c2).reshape(1), 1e-5, what + ' contrast')
         assert_close(cpu(m1).reshape(1), cpu(m2).reshape(1), 2e-5, what + ' mutual')
-        got = {k: cpu(p.grad) for k, p in unique_named_params(native)}
-        want = {k: (cpu(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
-                for k, p in unique_named_params(ref)}
+        got = {k: grad_of(p) for k, p in unique_named_params(native)}
+        want = {k: grad_of(p) for k, p in unique_named_params(ref)}
+        # tensors without a gradient are the same on both routes (torch optimizers skip them)
+        assert [p.grad is None for _, p in unique_named_params(native)] == \
+            [p.grad is None for _, p in unique_named_params(ref)], what
         check_grads(got, want, what)
     native._trainer.check_errors()

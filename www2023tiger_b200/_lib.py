@@ -62,7 +62,7 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_min_time': 'plp' + 'p',
     'tiger_seq_tokens': 'ppli' + 'ppppp' + 'ppii' + 'ppp' + 'ppp' + 'p',
     'tiger_sgemm_nt': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
-    'tiger_train_gather_pending': 'pplpippipippppp',
+    'tiger_train_gather_pending': 'pplpippipipppppp',
     'tiger_train_gru_gates': 'pppplippppp',
     'tiger_train_gru_gates_bwd': 'ppppppplippp',
     'tiger_train_attn_build': 'plplpppipppppiippppplip',
@@ -77,8 +77,8 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_train_score_head': 'ppplifipppp',
     'tiger_train_score_head_bwd': 'pfpplifpppp',
     'tiger_train_score_build_bwd': 'pplippp',
-    'tiger_train_mse': 'pppppplipppp',
-    'tiger_train_adam': 'pppplfffflfip',
+    'tiger_train_mse': 'pppppplippppp',
+    'tiger_train_adam': 'ppppppppiplfffffip',
     'tiger_train_seq_pool': 'plpppliiifippppp',
     'tiger_train_seq_pool_bwd': 'pppplpppliiifippp',
     'tiger_train_seq_vbias': 'ppppliip',

@@ -53,8 +53,9 @@ train_gather_pending_kernel(const int64_t* __restrict__ ids, const int32_t* __re
                             const float* __restrict__ msg_vals, int m_dim, const float* __restrict__ msg_ts,
                             const float* __restrict__ upd_vals, int d, const float* __restrict__ check_mem_ts,
                             int check_equal, float* __restrict__ X, float* __restrict__ H, float* __restrict__ dh_zero,
-                            uint32_t* __restrict__ err_flags) {
+                            uint32_t* __restrict__ err_flags, float* __restrict__ n_rows_out) {
   const int64_t n = bounded_rows(count, cap);
+  if (n_rows_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) n_rows_out[0] = (float)n;
   const int lane = lane_id();
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block(); r < n; r += n_warps) {
@@ -74,7 +75,7 @@ train_gather_pending_kernel(const int64_t* __restrict__ ids, const int32_t* __re
 extern "C" int tiger_train_gather_pending(const int64_t* ids, const int32_t* count, int64_t cap, const float* msg_vals,
                                           int m_dim, const float* msg_ts, const float* upd_vals, int d,
                                           const float* check_mem_ts, int check_equal, float* X, float* H,
-                                          float* dh_zero, uint32_t* err_flags, void* stream) {
+                                          float* dh_zero, uint32_t* err_flags, float* n_rows_out, void* stream) {
   if (ids == nullptr || msg_vals == nullptr || upd_vals == nullptr || X == nullptr || H == nullptr || cap < 0 ||
       m_dim <= 0 || d <= 0)
     return TIGER_EINVAL;
@@ -82,7 +83,8 @@ extern "C" int tiger_train_gather_pending(const int64_t* ids, const int32_t* cou
   int64_t grid = (cap + 7) / 8;
   if (grid > 148 * 4) grid = 148 * 4;
   train_gather_pending_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(
-      ids, count, cap, msg_vals, m_dim, msg_ts, upd_vals, d, check_mem_ts, check_equal, X, H, dh_zero, err_flags);
+      ids, count, cap, msg_vals, m_dim, msg_ts, upd_vals, d, check_mem_ts, check_equal, X, H, dh_zero, err_flags,
+      n_rows_out);
   return tiger_launch_status();
 }
 
@@ -806,7 +808,8 @@ extern "C" int tiger_train_score_build_bwd(const float* dpair, const uint8_t* co
 __global__ void __launch_bounds__(1024)
 train_mse_kernel(const float* __restrict__ pred_l, const float* __restrict__ pred_r, const float* __restrict__ hpl,
                  const float* __restrict__ hpr, const int64_t* __restrict__ index, const int32_t* __restrict__ count,
-                 int64_t P, int d, float* __restrict__ loss, float* __restrict__ dpred_l, float* __restrict__ dpred_r) {
+                 int64_t P, int d, float* __restrict__ loss, float* __restrict__ dpred_l, float* __restrict__ dpred_r,
+                 float* __restrict__ n_valid_out) {
   __shared__ float red[32];
   __shared__ int red_n[32];
   __shared__ uint8_t valid[2 * 2048];
@@ -849,51 +852,86 @@ train_mse_kernel(const float* __restrict__ pred_l, const float* __restrict__ pre
     float s = 0.f;
     for (int k = 0; k < n_warps; ++k) s += red[k];
     loss[0] = s * inv;
+    if (n_valid_out != nullptr) n_valid_out[0] = (float)n_valid;
   }
 }
 
 extern "C" int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev_left,
                                const float* hprev_right, const int64_t* index, const int32_t* count, int64_t n, int d,
-                               float* loss, float* dpred_l, float* dpred_r, void* stream) {
+                               float* loss, float* dpred_l, float* dpred_r, float* n_valid_out, void* stream) {
   if (pred_l == nullptr || pred_r == nullptr || hprev_left == nullptr || hprev_right == nullptr || index == nullptr ||
       loss == nullptr || n < 0 || n > 2048 || d <= 0 || (dpred_l == nullptr) != (dpred_r == nullptr))
     return TIGER_EINVAL;
   train_mse_kernel<<<1, 1024, 0, as_stream(stream)>>>(pred_l, pred_r, hprev_left, hprev_right, index, count, n, d, loss,
-                                                     dpred_l, dpred_r);
+                                                     dpred_l, dpred_r, n_valid_out);
   return tiger_launch_status();
 }
 
 // ------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam defaults of the reference: train_self_supervised.py:116; no weight decay, no amsgrad) over a
-// flat parameter buffer; gscale folds the 1/world_size of the gradient all-reduce; the gradient is zeroed for the
-// next step (optimizer.zero_grad()).
+// flat parameter buffer cut into the model's tensors.  torch keeps one step counter PER TENSOR and skips a tensor
+// whose gradient is None in a step - the GRU cell when no involved node holds a pending message (tiger.py:215), the
+// restarter when contrast_only or no target row is valid (tiger.py:571,586-592) - so every tensor carries a group:
+//   0 always stepped | 1 stepped iff gates[0] > 0 | 2 stepped iff gates[1] > 0
+// with the gates (#GRU rows, #valid target rows) read from device memory - they live at the tail of the flat gradient
+// buffer and so take part in the DDP all-reduce: a tensor used on any rank is stepped on every rank.
+// gscale folds the 1/world_size of the all-reduce; the gradient (and the gates) are zeroed for the next step
+// (optimizer.zero_grad()).
 // ------------------------------------------------------------------------------------------
+__global__ void train_adam_prepare_kernel(const int32_t* __restrict__ seg_group, int32_t* __restrict__ seg_step,
+                                          float* __restrict__ seg_bc, int n_seg, const float* __restrict__ gates,
+                                          float b1, float b2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_seg) return;
+  const int grp = seg_group[t];
+  const bool active = grp == 0 || (gates != nullptr && gates[grp - 1] > 0.f);
+  int step = seg_step[t];
+  if (active) seg_step[t] = ++step;
+  seg_bc[2 * t] = active ? 1.0f - powf(b1, (float)step) : 0.f;          // 0 marks "skip this tensor"
+  seg_bc[2 * t + 1] = active ? sqrtf(1.0f - powf(b2, (float)step)) : 0.f;
+}
+
 __global__ void train_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                  float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                  float bc1, float bc2_sqrt, float gscale, int zero_grad) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * b2 + gi * gi * (1.0f - b2);         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - (lr / bc1) * (mi / denom);
+                                  float* __restrict__ v, const int64_t* __restrict__ seg_start,
+                                  const float* __restrict__ seg_bc, float lr, float b1, float b2, float eps,
+                                  float gscale, int zero_grad) {
+  const int t = blockIdx.y;
+  const int64_t lo = seg_start[t], hi = seg_start[t + 1];
+  const float bc1 = seg_bc[2 * t], bc2_sqrt = seg_bc[2 * t + 1];
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    if (bc1 > 0.f) {
+      const float gi = g[i] * gscale;
+      const float mi = m[i] + (gi - m[i]) * (1.0f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
+      const float vi = v[i] * b2 + gi * gi * (1.0f - b2);         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      m[i] = mi;
+      v[i] = vi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      p[i] = p[i] - (lr / bc1) * (mi / denom);
+    }
     if (zero_grad) g[i] = 0.f;
   }
 }
 
-extern "C" int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                                float beta1, float beta2, float eps, int64_t step, float grad_scale, int zero_grad,
-                                void* stream) {
-  if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || n < 0 || step < 1)
+__global__ void train_zero_gates_kernel(float* gates, int n) {
+  if (threadIdx.x < n) gates[threadIdx.x] = 0.f;
+}
+
+extern "C" int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_start,
+                                const int32_t* seg_group, int32_t* seg_step, float* seg_bc, int n_seg, float* gates,
+                                int64_t max_seg, float lr, float beta1, float beta2, float eps, float grad_scale,
+                                int zero_grad, void* stream) {
+  if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || seg_start == nullptr ||
+      seg_group == nullptr || seg_step == nullptr || seg_bc == nullptr || n_seg <= 0 || max_seg < 0)
     return TIGER_EINVAL;
-  if (n == 0) return TIGER_OK;
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-  int64_t grid = (n + 255) / 256;
-  if (grid > 148 * 16) grid = 148 * 16;
-  train_adam_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                  eps, bc1, bc2_sqrt, grad_scale, zero_grad);
+  cudaStream_t st = as_stream(stream);
+  train_adam_prepare_kernel<<<(unsigned)((n_seg + 127) / 128), 128, 0, st>>>(seg_group, seg_step, seg_bc, n_seg, gates,
+                                                                            beta1, beta2);
+  int64_t gx = (max_seg + 255) / 256;
+  if (gx < 1) gx = 1;
+  if (gx > 512) gx = 512;
+  dim3 grid((unsigned)gx, (unsigned)n_seg);
+  train_adam_kernel<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, seg_start, seg_bc, lr, beta1, beta2, eps,
+                                          grad_scale, zero_grad);
+  if (zero_grad && gates != nullptr) train_zero_gates_kernel<<<1, 32, 0, st>>>(gates, 2);
   return tiger_launch_status();
 }

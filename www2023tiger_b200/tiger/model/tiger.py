@@ -44,9 +44,16 @@ class _NativeStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_contrast, g_mutual):
         tr = ctx.trainer
-        tr.fp.grad.zero_()                      # autograd accumulates what this node returns into p.grad itself
+        tr.fp.grad_all[:tr.fp.numel].zero_()    # autograd accumulates what this node returns into p.grad itself
         tr.backward(float(g_contrast), float(g_mutual))
-        return (None, None, None) + tuple(tr.fp.g[n].clone() for n in tr.fp.names)
+        # like autograd in the reference, parameters that took no part in this step get no gradient (None): the GRU
+        # cell when no involved node held a pending message, the restarter without a valid target row - torch
+        # optimizers skip such tensors (and do not advance their step counters)
+        gates = tr.fp.gates.tolist()
+        tr.fp.gates.zero_()
+        live = (True, gates[0] > 0, gates[1] > 0 and float(g_mutual) != 0.0)
+        return (None, None, None) + tuple(tr.fp.g[n].clone() if live[grp] else None
+                                          for n, grp in zip(tr.fp.names, tr.fp.groups))
 
 
 class _Workspace:

@@ -32,11 +32,18 @@ f32, i32, i64, u8 = torch.float32, torch.int32, torch.int64, torch.uint8
 
 class FlatParams:
     """Parameters of a module re-pointed into one flat buffer (+ gradient and Adam moment buffers of the same
-    layout).  Shared parameters (the time encoder is registered under three names, tiger.py:71-72) appear once."""
+    layout).  Shared parameters (the time encoder is registered under three names, tiger.py:71-72) appear once.
+
+    torch.optim.Adam keeps one step counter per tensor and skips tensors whose gradient is None; which tensors those
+    are in a given step is data dependent (no pending message -> the GRU cell is not used, no valid target row -> the
+    restarter gets no gradient).  `group_of(name)` puts every tensor into group 0 (always), 1 (GRU cell) or 2
+    (restarter); the two gate values sit behind the last tensor of the flat GRADIENT buffer (so they take part in the
+    gradient all-reduce) and are written by the step's kernels."""
 
     ALIGN = 4     # floats: every tensor starts on a 16-byte boundary
+    N_GATES = 4
 
-    def __init__(self, module: torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, group_of=lambda name: 0):
         seen, self.names, self.params = set(), [], []
         for name, p in module.named_parameters():
             if id(p) in seen:
@@ -51,7 +58,9 @@ class FlatParams:
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
         self.flat = torch.zeros(off, dtype=f32, device=dev)
-        self.grad = torch.zeros(off, dtype=f32, device=dev)
+        self.grad_all = torch.zeros(off + self.N_GATES, dtype=f32, device=dev)     # [gradients | gates]
+        self.grad = self.grad_all[:off]
+        self.gates = self.grad_all[off:]
         self.exp_avg = torch.zeros(off, dtype=f32, device=dev)
         self.exp_avg_sq = torch.zeros(off, dtype=f32, device=dev)
         self.g: Dict[str, Tensor] = {}
@@ -62,17 +71,29 @@ class FlatParams:
             p.data = view
             self.p[name] = view
             self.g[name] = self.grad[o:o + p.numel()].view(p.shape)
-        self.step = 0
+        self.groups = [int(group_of(n)) for n in self.names]
+        self.seg_start = torch.tensor(self.offsets + [off], dtype=i64, device=dev)
+        self.seg_group = torch.tensor(self.groups, dtype=i32, device=dev)
+        self.seg_step = torch.zeros(len(self.names), dtype=i32, device=dev)
+        self.seg_bc = torch.zeros(2 * len(self.names), dtype=f32, device=dev)
+        self.max_seg = max(p.numel() for p in self.params)
 
-    def publish_grads(self):
-        """Make the gradients visible as `p.grad` (views of the flat gradient buffer)."""
-        for name, p in zip(self.names, self.params):
-            p.grad = self.g[name]
+    def reset_optimizer(self):
+        self.exp_avg.zero_(), self.exp_avg_sq.zero_(), self.grad_all.zero_(), self.seg_step.zero_()
 
     def adam(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0, zero_grad: bool = True):
-        self.step += 1
-        call('tiger_train_adam', ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.numel,
-             float(lr), float(betas[0]), float(betas[1]), float(eps), self.step, float(grad_scale), int(zero_grad))
+        call('tiger_train_adam', ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+             ptr(self.seg_start), ptr(self.seg_group), ptr(self.seg_step), ptr(self.seg_bc), len(self.names),
+             ptr(self.gates), self.max_seg, float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale),
+             int(zero_grad))
+
+
+def _param_group(name: str) -> int:
+    if name.startswith('right_mem_updater.'):
+        return 1
+    if name.startswith('restarter_fn.'):
+        return 2
+    return 0
 
 
 def _linear_fwd(x, w, b, out, *, m, relu=False, m_count=None, per=1):
@@ -104,7 +125,7 @@ class NativeTrainer:
             raise NotImplementedError('native training covers the default operator variants '
                                       '(tsfm_fn id, upd_fn gru, n_layers 1, hit_type bin|none)')
         self.model = model
-        self.fp = FlatParams(model)
+        self.fp = FlatParams(model, _param_group)
         self.lr, self.seed, self.n_steps = lr, seed, 0
         dev = self.fp.flat.device
         self.device = dev
@@ -218,7 +239,7 @@ class NativeTrainer:
         # ---- steps 1-2: gather of the pending messages, GRU (tiger.py:206-221)
         call('tiger_train_gather_pending', ptr(self.outdated), ptr(cnt_o), cap, ptr(store.node_msg_vals), M,
              ptr(store.node_msg_ts), ptr(upd_mem.vals), d, ptr(msg_mem.update_ts), int(m.msg_src == 'left'),
-             ptr(self.X), ptr(self.Hs), ptr(self.dh_new), ptr(self.err))
+             ptr(self.X), ptr(self.Hs), ptr(self.dh_new), ptr(self.err), ptr(self.fp.gates))
         c = 'right_mem_updater.cell.'
         _linear_fwd(self.X, P[c + 'weight_ih'], P[c + 'bias_ih'], self.Gi, m=cap, m_count=cnt_o)
         _linear_fwd(self.Hs, P[c + 'weight_hh'], P[c + 'bias_hh'], self.Gh, m=cap, m_count=cnt_o)
@@ -265,7 +286,8 @@ class NativeTrainer:
             else:
                 self.seq.forward(nids, targets['hist'], fg, self.pred_l, self.pred_r, seed, train, n=n_pos, count=cnt)
             call('tiger_train_mse', ptr(self.pred_l), ptr(self.pred_r), ptr(self.hprev_left), ptr(self.hprev_right),
-                 ptr(targets['index']), ptr(cnt), n_pos, d, ptr(self.mloss), ptr(self.dpred_l), ptr(self.dpred_r))
+                 ptr(targets['index']), ptr(cnt), n_pos, d, ptr(self.mloss), ptr(self.dpred_l), ptr(self.dpred_r),
+                 ptr(self.fp.gates[1:]))
         else:
             self.mloss.zero_()
         # ---- steps 5-6 (tiger.py:244-255), no grad
@@ -363,7 +385,7 @@ class NativeTrainer:
                     lr: Optional[float] = None):
         closs, mloss = self.forward_stream(inp)
         self.backward(1.0, mutual_coef)
-        work = allreduce(self.fp.grad) if allreduce is not None else None
+        work = allreduce(self.fp.grad_all) if allreduce is not None else None
         if work is not None:
             work.wait()
         self.fp.adam(self.lr if lr is None else lr, grad_scale=grad_scale)
@@ -438,6 +460,6 @@ class NativeTrainer:
         closs, mloss = self.forward(src, dst, neg, ts, eids, cg, contrast_only=contrast_only)
         self.backward(1.0, 0.0 if contrast_only else mutual_coef)
         if allreduce is not None:
-            allreduce(self.fp.grad)
+            allreduce(self.fp.grad_all)
         self.fp.adam(self.lr, grad_scale=grad_scale)
         return closs, mloss
