@@ -872,7 +872,7 @@ extern "C" int tiger_train_mse(const float* pred_l, const float* pred_r, const f
 // flat parameter buffer cut into the model's tensors.  torch keeps one step counter PER TENSOR and skips a tensor
 // whose gradient is None in a step - the GRU cell when no involved node holds a pending message (tiger.py:215), the
 // restarter when contrast_only or no target row is valid (tiger.py:571,586-592) - so every tensor carries a group:
-//   0 always stepped | 1 stepped iff gates[0] > 0 | 2 stepped iff gates[1] > 0
+//   0 always stepped | 1 stepped iff gates[0] > 0 | 2 stepped iff gates[1] > 0 | 3 never (gates[2] stays 0)
 // with the gates (#GRU rows, #valid target rows) read from device memory - they live at the tail of the flat gradient
 // buffer and so take part in the DDP all-reduce: a tensor used on any rank is stepped on every rank.
 // gscale folds the 1/world_size of the all-reduce; the gradient (and the gates) are zeroed for the next step

@@ -51,7 +51,7 @@ class _NativeStep(torch.autograd.Function):
         # optimizers skip such tensors (and do not advance their step counters)
         gates = tr.fp.gates.tolist()
         tr.fp.gates.zero_()
-        live = (True, gates[0] > 0, gates[1] > 0 and float(g_mutual) != 0.0)
+        live = (True, gates[0] > 0, gates[1] > 0 and float(g_mutual) != 0.0, False)
         return (None, None, None) + tuple(tr.fp.g[n].clone() if live[grp] else None
                                           for n, grp in zip(tr.fp.names, tr.fp.groups))
 

@@ -125,7 +125,10 @@ class NativeTrainer:
             raise NotImplementedError('native training covers the default operator variants '
                                       '(tsfm_fn id, upd_fn gru, n_layers 1, hit_type bin|none)')
         self.model = model
-        self.fp = FlatParams(model, _param_group)
+        # a static restarter owns a time encoder it never uses (restarters.py:17-33,254-277): never stepped (group 3)
+        static = type(model.restarter_fn).__name__ == 'StaticRestarter'
+        self.fp = FlatParams(model, lambda n: 3 if (static and n.startswith('restarter_fn.time_encoder.'))
+                             else _param_group(n))
         self.lr, self.seed, self.n_steps = lr, seed, 0
         dev = self.fp.flat.device
         self.device = dev
