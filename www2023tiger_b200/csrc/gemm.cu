@@ -108,6 +108,7 @@ struct GemmArgs {
   // reduction length may live on the device (k_count * k_rows_per_count); blockIdx.y splits K into parts of
   // kblk_per_part stages whose partial tiles are accumulated into C with atomic adds (gradient accumulation)
   int trans_a, trans_w, accumulate;
+  int mn_a, mn_w;        // the transposed operand is 16-byte aligned: staged MN-major with vector loads
   const int32_t* k_count;
   int64_t k_rows_per_count;
   int kblk_per_part;
@@ -219,6 +220,16 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       ca.ptr[i] = g.trans_a ? A + m + (int64_t)(kc * 4) * g.lda : A + m * g.lda + kc * 4;
       ca.soff[i] = (kc * TCG_BM + row) * 4;
       ca.kq[i] = kc * 4;
+      ca.nv[i] = 4;
+      if (g.mn_a) {          // chunk = (k_local, rows 4 lane .. 4 lane + 3)
+        const int kl = wg + TCG_GROUP_WARPS * i;
+        const int64_t r0 = m0 + 4 * lane;
+        const int64_t left = M - r0;
+        ca.nv[i] = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
+        ca.ptr[i] = A + (int64_t)kl * g.lda + (left > 0 ? r0 : 0);
+        ca.soff[i] = (kl >> 3) * (TCG_BM * 8) + lane * 32 + (kl & 7) * 4;
+        ca.kq[i] = kl;
+      }
     }
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
@@ -230,6 +241,16 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       cw.ptr[i] = g.trans_w ? W + n + (int64_t)(kc * 4) * g.ldw : W + (int64_t)n * g.ldw + kc * 4;
       cw.soff[i] = (wc < (BN >> 3) && !PACKED) ? (kc * BN + row) * 4 : -1;
       cw.kq[i] = kc * 4;
+      cw.nv[i] = 4;
+      if (g.mn_w && !PACKED) {
+        const int kl = wg + TCG_GROUP_WARPS * i;
+        const int r0 = n0 + 4 * lane;
+        const int left = g.N - r0;
+        cw.nv[i] = left >= 4 ? 4 : (left > 0 ? left : 0);
+        cw.ptr[i] = W + (int64_t)kl * g.ldw + (left > 0 ? r0 : 0);
+        cw.soff[i] = (4 * lane < BN) ? (kl >> 3) * (BN * 8) + lane * 32 + (kl & 7) * 4 : -1;
+        cw.kq[i] = kl;
+      }
     }
     // two register sets per thread: the loads of this group's next two stages are in flight while the
     // current one is converted and published (the proxy fence would otherwise wait for a stage's loads
@@ -238,10 +259,12 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     auto load = [&](float4 (&va)[TCG_NA], float4 (&vw)[NW], int blk) {
       if (blk < n_blocks) {
         const int k0 = (kblk0 + blk) * UMMA_BK;
-        if (g.trans_a) umma_chunks_load_t(va, ca, k0, K_eff, g.lda);
+        if (g.mn_a) umma_chunks_load_mn(va, ca, k0, K_eff, g.lda);
+        else if (g.trans_a) umma_chunks_load_t(va, ca, k0, K_eff, g.lda);
         else umma_chunks_load(va, ca, k0, K_eff, g.vec_a != 0);
         if constexpr (!PACKED) {
-          if (g.trans_w) umma_chunks_load_t(vw, cw, k0, K_eff, g.ldw);
+          if (g.mn_w) umma_chunks_load_mn(vw, cw, k0, K_eff, g.ldw);
+          else if (g.trans_w) umma_chunks_load_t(vw, cw, k0, K_eff, g.ldw);
           else umma_chunks_load(vw, cw, k0, K_eff, g.vec_w != 0);
         }
       }
@@ -334,8 +357,9 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     // The whole warp runs the loop so that every operand stays warp-uniform; only the tcgen05 instructions
     // are issued by the elected lane.
     const int role = uniform_warp_idx() - TCG_PRODUCER_WARPS;
-    const UmmaRole r = umma_role(role, smem_addr_u32(stage0), (uint32_t)stage_floats * 4u, TCG_BM, BN, (uint32_t)BN);
-    const uint32_t idesc = umma_idesc_tf32(TCG_BM, BN);
+    const UmmaRole r = umma_role(role, smem_addr_u32(stage0), (uint32_t)stage_floats * 4u, TCG_BM, BN, (uint32_t)BN,
+                                 g.mn_a, g.mn_w);
+    const uint32_t idesc = umma_idesc_tf32(TCG_BM, BN, g.mn_a, g.mn_w);
     const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
     const uint32_t d_even = tbase + r.acc_even, d_odd = tbase + r.acc_odd;
     int s = 0;
@@ -861,6 +885,7 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   }
   g.a_parts = a_parts; g.a_part_stride = a_part_stride; g.a_bias = a_bias; g.a_relu = a_relu;
   g.trans_a = 0; g.trans_w = 0; g.accumulate = 0; g.k_count = nullptr; g.k_rows_per_count = 1; g.kblk_per_part = 0;
+  g.mn_a = 0; g.mn_w = 0;
   g.a_ids = nullptr; g.a_sel = nullptr; g.a_sel_i64 = 0; g.a_alt = nullptr; g.a_add = nullptr;
   if (gather != nullptr) {
     g.a_ids = gather->ids; g.a_sel = gather->sel; g.a_sel_i64 = gather->sel_is_i64;
@@ -1033,6 +1058,8 @@ extern "C" int tiger_sgemm_ex(const float* A, int64_t lda, int trans_a, const fl
   g.vec_a = (!trans_a && (((uintptr_t)A) & 15) == 0 && (lda & 3) == 0) ? 1 : 0;
   g.vec_w = (!trans_w && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0) ? 1 : 0;
   g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
+  g.mn_a = (trans_a && (((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && getenv("TIGER_NO_MN_MAJOR") == nullptr) ? 1 : 0;
+  g.mn_w = (trans_w && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && getenv("TIGER_NO_MN_MAJOR") == nullptr) ? 1 : 0;
   const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
   g.bn = gemm_pick_bn(m_rows, n_cols, accumulate ? k_parts : 1, sms, TCG_MAX_BN);
   g.tiles_n = (n_cols + g.bn - 1) / g.bn;
@@ -1047,8 +1074,9 @@ extern "C" int tiger_sgemm_ex(const float* A, int64_t lda, int trans_a, const fl
   g.kblk_per_part = accumulate ? (k_blocks + parts - 1) / parts : 0;
   if (accumulate) parts = (k_blocks + g.kblk_per_part - 1) / g.kblk_per_part;
   const int64_t tiles = tiles_m * g.tiles_n;
-  const int64_t per_part = (sms + parts - 1) / parts > 0 ? (sms + parts - 1) / parts : 1;
-  dim3 grid((unsigned)(tiles < per_part ? tiles : per_part), (unsigned)parts);
+  // every (tile, K part) gets its own CTA up to one wave per part: with a device-side reduction length most parts of a
+  // capacity-sized launch exit at once, the live ones must not queue behind each other
+  dim3 grid((unsigned)(tiles < sms ? tiles : sms), (unsigned)parts);
   gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, stages * stage_bytes + 256, as_stream(stream)>>>(g);
   return tiger_launch_status();
 }

@@ -103,8 +103,8 @@ def _linear_fwd(x, w, b, out, *, m, relu=False, m_count=None, per=1):
 def _linear_bwd(dy, x, w, gw, gb, dx, *, m, k_parts=None, count=None, per=1, accumulate_dx=False):
     """dy [m, n], x [m, k], w [n, k]: gw += dy^T x, gb += colsum(dy), dx (=|+=) dy w.  `count` bounds m on the device."""
     n, k = w.shape
-    # K split of the weight gradient: <= ~512 reduction steps per CTA (accumulator truncation grows with the length)
-    k_parts = max(1, min(64, (m + 511) // 512))
+    # K split of the weight gradient: <= 256 reduction steps per CTA (accumulator truncation grows with the length)
+    k_parts = max(1, min(128, (m + 255) // 256))
     if gw is not None:
         ops.sgemm_ex(dy, x, gw, m=n, n=k, k=m, trans_a=True, trans_w=True, accumulate=True, k_parts=k_parts,
                      k_count=count, rows_per_count=per)

@@ -11,9 +11,9 @@ f32, i64, u8 = torch.float32, torch.int64, torch.uint8
 
 
 def _parts(k: int) -> int:
-    """K split of a weight-gradient product: at most ~512 reduction steps per CTA (the tensor core truncates when it
+    """K split of a weight-gradient product: at most 256 reduction steps per CTA (the tensor core truncates when it
     adds into its fp32 accumulator, an error that grows with the accumulation length: DESIGN.md, Tensor cores)."""
-    return max(1, min(64, (k + 511) // 512))
+    return max(1, min(128, (k + 255) // 256))
 
 
 class SeqRestarterTrainer:
