@@ -108,7 +108,7 @@ struct GemmArgs {
   // reduction length may live on the device (k_count * k_rows_per_count); blockIdx.y splits K into parts of
   // kblk_per_part stages whose partial tiles are accumulated into C with atomic adds (gradient accumulation)
   int trans_a, trans_w, accumulate;
-  int mn_a, mn_w;        // the transposed operand is 16-byte aligned: staged MN-major with vector loads
+  int mn_a, mn_w;        // the transposed operand is 16-byte aligned: vector loads along its rows + quad transposes
   const int32_t* k_count;
   int64_t k_rows_per_count;
   int kblk_per_part;
@@ -221,14 +221,11 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       ca.soff[i] = (kc * TCG_BM + row) * 4;
       ca.kq[i] = kc * 4;
       ca.nv[i] = 4;
-      if (g.mn_a) {          // chunk = (k_local, rows 4 lane .. 4 lane + 3)
-        const int kl = wg + TCG_GROUP_WARPS * i;
-        const int64_t r0 = m0 + 4 * lane;
+      if (g.mn_a) {          // load (k = 4 kc + q, rows of this lane's quad), see umma_chunks_load_tv
+        const int64_t r0 = m0 + (row & ~3);
         const int64_t left = M - r0;
         ca.nv[i] = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
-        ca.ptr[i] = A + (int64_t)kl * g.lda + (left > 0 ? r0 : 0);
-        ca.soff[i] = (kl >> 3) * (TCG_BM * 8) + lane * 32 + (kl & 7) * 4;
-        ca.kq[i] = kl;
+        ca.ptr[i] = A + (int64_t)(kc * 4 + (lane & 3)) * g.lda + (left > 0 ? r0 : 0);
       }
     }
 #pragma unroll
@@ -243,13 +240,10 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
       cw.kq[i] = kc * 4;
       cw.nv[i] = 4;
       if (g.mn_w && !PACKED) {
-        const int kl = wg + TCG_GROUP_WARPS * i;
-        const int r0 = n0 + 4 * lane;
+        const int r0 = n0 + (row & ~3);
         const int left = g.N - r0;
         cw.nv[i] = left >= 4 ? 4 : (left > 0 ? left : 0);
-        cw.ptr[i] = W + (int64_t)kl * g.ldw + (left > 0 ? r0 : 0);
-        cw.soff[i] = (4 * lane < BN) ? (kl >> 3) * (BN * 8) + lane * 32 + (kl & 7) * 4 : -1;
-        cw.kq[i] = kl;
+        cw.ptr[i] = W + (int64_t)(kc * 4 + (lane & 3)) * g.ldw + (left > 0 ? r0 : 0);
       }
     }
     // two register sets per thread: the loads of this group's next two stages are in flight while the
@@ -259,11 +253,11 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     auto load = [&](float4 (&va)[TCG_NA], float4 (&vw)[NW], int blk) {
       if (blk < n_blocks) {
         const int k0 = (kblk0 + blk) * UMMA_BK;
-        if (g.mn_a) umma_chunks_load_mn(va, ca, k0, K_eff, g.lda);
+        if (g.mn_a) umma_chunks_load_tv(va, ca, k0, K_eff, g.lda, lane);
         else if (g.trans_a) umma_chunks_load_t(va, ca, k0, K_eff, g.lda);
         else umma_chunks_load(va, ca, k0, K_eff, g.vec_a != 0);
         if constexpr (!PACKED) {
-          if (g.mn_w) umma_chunks_load_mn(vw, cw, k0, K_eff, g.ldw);
+          if (g.mn_w) umma_chunks_load_tv(vw, cw, k0, K_eff, g.ldw, lane);
           else if (g.trans_w) umma_chunks_load_t(vw, cw, k0, K_eff, g.ldw);
           else umma_chunks_load(vw, cw, k0, K_eff, g.vec_w != 0);
         }
@@ -357,9 +351,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     // The whole warp runs the loop so that every operand stays warp-uniform; only the tcgen05 instructions
     // are issued by the elected lane.
     const int role = uniform_warp_idx() - TCG_PRODUCER_WARPS;
-    const UmmaRole r = umma_role(role, smem_addr_u32(stage0), (uint32_t)stage_floats * 4u, TCG_BM, BN, (uint32_t)BN,
-                                 g.mn_a, g.mn_w);
-    const uint32_t idesc = umma_idesc_tf32(TCG_BM, BN, g.mn_a, g.mn_w);
+    const UmmaRole r = umma_role(role, smem_addr_u32(stage0), (uint32_t)stage_floats * 4u, TCG_BM, BN, (uint32_t)BN);
+    const uint32_t idesc = umma_idesc_tf32(TCG_BM, BN);
     const uint32_t tbase = __shfl_sync(0xffffffffu, taddr, 0);
     const uint32_t d_even = tbase + r.acc_even, d_odd = tbase + r.acc_odd;
     int s = 0;

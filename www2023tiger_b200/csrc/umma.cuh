@@ -205,10 +205,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major, M = 128:
 //   [4,6) D format = 1 (f32) | [7,10) A format = 2 (tf32) | [10,13) B format = 2 | [17,23) N >> 3 | [24,29) M >> 4
-//   [15] A is MN-major | [16] B is MN-major
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n, int a_mn = 0, int b_mn = 0) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -266,7 +264,7 @@ struct UmmaChunks {
   const float* ptr[N];   // row base + kq, clamped to a valid row (rows beyond the edge only feed unused outputs)
   int soff[N];           // float offset inside a plane: (kc * rows + row) * 4 ; < 0 = chunk not owned
   int kq[N];             // kc * 4
-  int nv[N];             // MN-major chunks only: how many of the chunk's 4 rows exist (0..4)
+  int nv[N];             // vector-transposed chunks only: how many of the quad's 4 rows exist (0..4)
 };
 
 template <int N>
@@ -313,19 +311,20 @@ __device__ __forceinline__ void umma_chunks_load_t(float4 (&v)[N], const UmmaChu
   }
 }
 
-// MN-major operand (tcgen05 instruction-descriptor bits 15 / 16): the tile is stored as it lies in a matrix whose
-// CONTIGUOUS dimension is the tile's row (M / N) dimension - element (row, k) at base[k * ld + row], i.e. the
-// transposed operands of the input- and weight-gradient products.  Canonical no-swizzle layout per k-step of 8:
-//     plane[k-step][row / 4][k % 8][4 rows]        (core matrix = 8 k x 16 bytes, SBO = 128 B between row groups)
-// so a chunk is the 16-byte vector (k, rows r..r+3): one coalesced LDG.128 along the contiguous dimension and one
-// STS.128, no transposition anywhere.  c.ptr = base + k_local * ld + row; c.kq = k_local.
+// Transposed operand, 16-byte aligned (element (row, k) at base[k * ld + row], ld % 4 == 0): the chunk geometry of
+// the K-major tile stays (lane & 7 -> row, lane >> 3 -> kc), but the data is fetched with vector loads ALONG THE
+// ROWS and transposed inside quads of lanes: lane (rq = (lane >> 2) & 1, q = lane & 3, kc) loads the float4
+// (k = 4 kc + q, rows 4 rq .. 4 rq + 3), then the four lanes of a quad exchange components with four shuffles so
+// that lane q ends up with (row 4 rq + q, k = 4 kc .. 4 kc + 3) - exactly the K-major chunk it has to store.
+// c.ptr = base + (4 kc + q) * ld + first row of the quad; c.nv = rows of the quad that exist (0..4).
 template <int N>
-__device__ __forceinline__ void umma_chunks_load_mn(float4 (&v)[N], const UmmaChunks<N>& c, int k0, int k_end,
-                                                    int64_t ld) {
+__device__ __forceinline__ void umma_chunks_load_tv(float4 (&v)[N], const UmmaChunks<N>& c, int k0, int k_end,
+                                                    int64_t ld, int lane) {
+  const int q = lane & 3;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c.soff[i] >= 0 && k0 + c.kq[i] < k_end && c.nv[i] > 0) {
+    if (c.soff[i] >= 0 && k0 + c.kq[i] + q < k_end && c.nv[i] > 0) {
       const float* p = c.ptr[i] + (int64_t)k0 * ld;
       if (c.nv[i] == 4) {
         t = __ldg(reinterpret_cast<const float4*>(p));
@@ -335,7 +334,20 @@ __device__ __forceinline__ void umma_chunks_load_mn(float4 (&v)[N], const UmmaCh
         if (c.nv[i] > 2) t.z = __ldg(p + 2);
       }
     }
-    v[i] = t;
+    // 4 x 4 transpose inside the quad: in round j lane q sends its component (q ^ j) to lane q ^ j and receives
+    // that lane's component q = element (row q, k-offset q ^ j)
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int comp = q ^ j;
+      const float send = comp == 0 ? t.x : (comp == 1 ? t.y : (comp == 2 ? t.z : t.w));
+      const float got = __shfl_xor_sync(0xffffffffu, send, j);
+      if (comp == 0) o[0] = got;
+      else if (comp == 1) o[1] = got;
+      else if (comp == 2) o[2] = got;
+      else o[3] = got;
+    }
+    v[i] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -432,12 +444,11 @@ struct UmmaRole {
   uint32_t acc_even, acc_odd;  // TMEM column offsets of this role's accumulator for even / odd k-steps
 };
 __device__ __forceinline__ UmmaRole umma_role(int role, uint32_t stage0_addr, uint32_t stage_bytes, int a_rows,
-                                              int b_rows, uint32_t acc_stride, int a_mn = 0, int b_mn = 0) {
+                                              int b_rows, uint32_t acc_stride) {
   const uint32_t a_plane = (uint32_t)UMMA_KCH * a_rows * 16u, b_plane = (uint32_t)UMMA_KCH * b_rows * 16u;
   UmmaRole r;
-  // leading byte offset = distance between K groups: rows * 16 B (K-major chunks) or rows * 32 B (MN-major k-steps)
-  r.a_lo = umma_desc_lo(stage0_addr + (role == 0 ? a_plane : 0u), (uint32_t)(a_mn ? 2 * a_rows : a_rows));
-  r.b_lo = umma_desc_lo(stage0_addr + 2u * a_plane + (role == 1 ? b_plane : 0u), (uint32_t)(b_mn ? 2 * b_rows : b_rows));
+  r.a_lo = umma_desc_lo(stage0_addr + (role == 0 ? a_plane : 0u), (uint32_t)a_rows);
+  r.b_lo = umma_desc_lo(stage0_addr + 2u * a_plane + (role == 1 ? b_plane : 0u), (uint32_t)b_rows);
   r.a_kstep = 2u * a_rows;
   r.b_kstep = 2u * b_rows;
   r.stage_step = stage_bytes >> 4;
