@@ -122,7 +122,10 @@ struct GemmGather {
   const float* add;
 };
 
-template <bool PACKED>
+// MODE_A / MODE_W: how the operand is fetched - 0 row-major [rows, K] (vector loads along K), 1 transposed with
+// scalar loads, 2 transposed and 16-byte aligned (vector loads along the rows + in-quad transposes).  Template
+// parameters, not runtime switches: with all three loaders in one body the kernel spilled 1.5 KB per thread.
+template <bool PACKED, int MODE_A, int MODE_W>
 __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmArgs g) {
   extern __shared__ __align__(128) unsigned char tcg_smem[];
   const int BN = g.bn, S = g.stages;
@@ -211,39 +214,41 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     constexpr int NW = PACKED ? 1 : TCG_NW;   // the packed variant moves no W chunks (placeholder of 1, never owned)
     UmmaChunks<TCG_NA> ca;
     UmmaChunks<NW> cw;
-#pragma unroll
-    for (int i = 0; i < TCG_NA; ++i) {
+    {
       int row, kc;
-      umma_chunk_pos(wg + TCG_GROUP_WARPS * i, lane, row, kc);
-      int64_t m = m0 + row;
-      m = m < M ? m : M - 1;
-      ca.ptr[i] = g.trans_a ? A + m + (int64_t)(kc * 4) * g.lda : A + m * g.lda + kc * 4;
-      ca.soff[i] = (kc * TCG_BM + row) * 4;
-      ca.kq[i] = kc * 4;
-      ca.nv[i] = 4;
-      if (g.mn_a) {          // load (k = 4 kc + q, rows of this lane's quad), see umma_chunks_load_tv
-        const int64_t r0 = m0 + (row & ~3);
-        const int64_t left = M - r0;
-        ca.nv[i] = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
-        ca.ptr[i] = A + (int64_t)(kc * 4 + (lane & 3)) * g.lda + (left > 0 ? r0 : 0);
+      umma_chunk_pos(wg, lane, row, kc);          // chunk 0 = warp-chunk wg; chunk i = warp-chunk wg + 4 i
+      const int64_t rows_a = M - m0;
+      ca.rows_valid = rows_a < TCG_BM ? (int)rows_a : TCG_BM;
+      ca.n_own = TCG_NA;
+      ca.row0 = row;
+      ca.kq = kc * 4;
+      ca.soff0 = (kc * TCG_BM + row) * 4;
+      if constexpr (MODE_A == 0) {
+        ca.ptr0 = A + (m0 + row) * g.lda + kc * 4;
+        ca.step = 32 * g.lda;
+      } else if constexpr (MODE_A == 1) {
+        ca.ptr0 = A + (int64_t)(kc * 4) * g.lda + m0 + row;
+        ca.step = 32;
+      } else {
+        ca.ptr0 = A + (int64_t)(kc * 4 + (lane & 3)) * g.lda + m0 + (row & ~3);
+        ca.step = 32;
       }
-    }
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      const int wc = wg + TCG_GROUP_WARPS * i;
-      int row, kc;
-      umma_chunk_pos(wc, lane, row, kc);
-      int n = n0 + row;
-      n = n < g.N ? n : g.N - 1;
-      cw.ptr[i] = g.trans_w ? W + n + (int64_t)(kc * 4) * g.ldw : W + (int64_t)n * g.ldw + kc * 4;
-      cw.soff[i] = (wc < (BN >> 3) && !PACKED) ? (kc * BN + row) * 4 : -1;
-      cw.kq[i] = kc * 4;
-      cw.nv[i] = 4;
-      if (g.mn_w && !PACKED) {
-        const int r0 = n0 + (row & ~3);
-        const int left = g.N - r0;
-        cw.nv[i] = left >= 4 ? 4 : (left > 0 ? left : 0);
-        cw.ptr[i] = W + (int64_t)(kc * 4 + (lane & 3)) * g.ldw + (left > 0 ? r0 : 0);
+      const int rows_w = g.N - n0;
+      cw.rows_valid = rows_w < BN ? rows_w : BN;
+      const int wchunks = BN >> 3;                // warp-chunks of the W tile
+      cw.n_own = PACKED ? 0 : (wchunks > wg ? (wchunks - wg + TCG_GROUP_WARPS - 1) / TCG_GROUP_WARPS : 0);
+      cw.row0 = row;
+      cw.kq = kc * 4;
+      cw.soff0 = (kc * BN + row) * 4;
+      if constexpr (MODE_W == 0) {
+        cw.ptr0 = W + (int64_t)(n0 + row) * g.ldw + kc * 4;
+        cw.step = 32 * g.ldw;
+      } else if constexpr (MODE_W == 1) {
+        cw.ptr0 = W + (int64_t)(kc * 4) * g.ldw + n0 + row;
+        cw.step = 32;
+      } else {
+        cw.ptr0 = W + (int64_t)(kc * 4 + (lane & 3)) * g.ldw + n0 + (row & ~3);
+        cw.step = 32;
       }
     }
     // two register sets per thread: the loads of this group's next two stages are in flight while the
@@ -253,12 +258,12 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) gemm_tf32x3_kernel(const GemmA
     auto load = [&](float4 (&va)[TCG_NA], float4 (&vw)[NW], int blk) {
       if (blk < n_blocks) {
         const int k0 = (kblk0 + blk) * UMMA_BK;
-        if (g.mn_a) umma_chunks_load_tv(va, ca, k0, K_eff, g.lda, lane);
-        else if (g.trans_a) umma_chunks_load_t(va, ca, k0, K_eff, g.lda);
+        if constexpr (MODE_A == 2) umma_chunks_load_tv(va, ca, k0, K_eff, g.lda, lane);
+        else if constexpr (MODE_A == 1) umma_chunks_load_t(va, ca, k0, K_eff, g.lda);
         else umma_chunks_load(va, ca, k0, K_eff, g.vec_a != 0);
         if constexpr (!PACKED) {
-          if (g.mn_w) umma_chunks_load_tv(vw, cw, k0, K_eff, g.ldw, lane);
-          else if (g.trans_w) umma_chunks_load_t(vw, cw, k0, K_eff, g.ldw);
+          if constexpr (MODE_W == 2) umma_chunks_load_tv(vw, cw, k0, K_eff, g.ldw, lane);
+          else if constexpr (MODE_W == 1) umma_chunks_load_t(vw, cw, k0, K_eff, g.ldw);
           else umma_chunks_load(vw, cw, k0, K_eff, g.vec_w != 0);
         }
       }
@@ -808,8 +813,19 @@ static int gemm_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    if (cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TCG_SMEM_BUDGET + 256) != cudaSuccess ||
+    bool ok = true;
+    auto set_smem = [&](auto kernel) {
+      ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCG_SMEM_BUDGET + 256) ==
+                     cudaSuccess;
+    };
+    set_smem(gemm_tf32x3_kernel<false, 0, 0>);
+    set_smem(gemm_tf32x3_kernel<false, 0, 1>);
+    set_smem(gemm_tf32x3_kernel<false, 0, 2>);
+    set_smem(gemm_tf32x3_kernel<false, 1, 0>);
+    set_smem(gemm_tf32x3_kernel<false, 1, 1>);
+    set_smem(gemm_tf32x3_kernel<false, 2, 0>);
+    set_smem(gemm_tf32x3_kernel<false, 2, 2>);
+    if (!ok ||
         cudaFuncSetAttribute(gemm_tf32x3_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TS_MAX_STAGES * UMMA_PACK_STAGE_FLOATS(TS_MAX_BN) * 4 + 256) != cudaSuccess)
       return -1;
@@ -916,7 +932,7 @@ static int gemm_launch(const float* A, int64_t lda, int64_t stride_a, const floa
   const size_t smem = stages * stage_bytes + 256;
   const int64_t tiles = tiles_m * g.tiles_n;
   dim3 grid((unsigned)(tiles < sms ? tiles : sms), (unsigned)batch);      // persistent over tiles
-  gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
+  gemm_tf32x3_kernel<false, 0, 0><<<grid, TCG_THREADS, smem, as_stream(stream)>>>(g);
   return tiger_launch_status();
 }
 
@@ -1070,6 +1086,23 @@ extern "C" int tiger_sgemm_ex(const float* A, int64_t lda, int trans_a, const fl
   // every (tile, K part) gets its own CTA up to one wave per part: with a device-side reduction length most parts of a
   // capacity-sized launch exit at once, the live ones must not queue behind each other
   dim3 grid((unsigned)(tiles < sms ? tiles : sms), (unsigned)parts);
-  gemm_tf32x3_kernel<false><<<grid, TCG_THREADS, stages * stage_bytes + 256, as_stream(stream)>>>(g);
+  const size_t smem = stages * stage_bytes + 256;
+  cudaStream_t st = as_stream(stream);
+  // an operand pair mixes the scalar and the vector transposed loader only if exactly one of them is misaligned:
+  // then both take the scalar one (fewer instantiations of a large kernel)
+  int ma = trans_a ? (g.mn_a ? 2 : 1) : 0, mw = trans_w ? (g.mn_w ? 2 : 1) : 0;
+  if (ma == 2 && mw == 1) ma = 1;
+  if (ma == 1 && mw == 2) mw = 1;
+  const int mode = ma * 3 + mw;
+  switch (mode) {
+    case 0: gemm_tf32x3_kernel<false, 0, 0><<<grid, TCG_THREADS, smem, st>>>(g); break;
+    case 1: gemm_tf32x3_kernel<false, 0, 1><<<grid, TCG_THREADS, smem, st>>>(g); break;
+    case 2: gemm_tf32x3_kernel<false, 0, 2><<<grid, TCG_THREADS, smem, st>>>(g); break;
+    case 3: gemm_tf32x3_kernel<false, 1, 0><<<grid, TCG_THREADS, smem, st>>>(g); break;
+    case 4: gemm_tf32x3_kernel<false, 1, 1><<<grid, TCG_THREADS, smem, st>>>(g); break;
+    case 6: gemm_tf32x3_kernel<false, 2, 0><<<grid, TCG_THREADS, smem, st>>>(g); break;
+    case 8: gemm_tf32x3_kernel<false, 2, 2><<<grid, TCG_THREADS, smem, st>>>(g); break;
+    default: return TIGER_EINVAL;
+  }
   return tiger_launch_status();
 }

@@ -256,52 +256,56 @@ __device__ __forceinline__ float4 umma_load_chunk(const float* row_ptr, int k, i
 
 // A tile of `rows` rows x UMMA_BK floats is moved in warp-chunks of 8 rows x 4 kc chunks
 // (lane & 7 -> row, lane >> 3 -> kc): a quarter warp writes 128 contiguous bytes of shared memory
-// (conflict-free) and the warp reads 8 x 64 contiguous bytes of global memory.  Each thread owns the
-// same N (row, kc) positions of every stage it fills, so its global pointers (row base + kc * 4) and
-// shared offsets are computed once; per stage the pointer only advances by k0.
+// (conflict-free) and the warp reads 8 x 64 contiguous bytes of global memory.  A thread owns the same N
+// (row, kc) positions of every stage it fills - warp-chunks wc0, wc0 + 4, ... , i.e. rows 32 apart - so everything
+// about chunk i follows from chunk 0 (kept as scalars, not arrays: the producers also hold two stages of
+// operand data in registers):  pointer = ptr0 + i * step,  plane offset = soff0 + 128 i floats,
+// tile-relative row = row0 + 32 i.  Rows at or beyond rows_valid (tile edge / device-side row count) read as zero.
 template <int N>
 struct UmmaChunks {
-  const float* ptr[N];   // row base + kq, clamped to a valid row (rows beyond the edge only feed unused outputs)
-  int soff[N];           // float offset inside a plane: (kc * rows + row) * 4 ; < 0 = chunk not owned
-  int kq[N];             // kc * 4
-  int nv[N];             // vector-transposed chunks only: how many of the quad's 4 rows exist (0..4)
+  const float* ptr0;   // row-major: &A[row, kq];  transposed: &A[kq (+ q), row (quad start)]
+  int64_t step;        // row-major: 32 * ld;  transposed: 32
+  int soff0;           // (kc * rows + row0) * 4
+  int n_own;           // chunks [0, n_own) exist in this tile (narrow W tiles own fewer)
+  int row0;            // lane's row inside the tile for chunk 0
+  int rows_valid;      // rows of the tile backed by data
+  int kq;              // kc * 4
 };
 
 template <int N>
 __device__ __forceinline__ void umma_chunks_load(float4 (&v)[N], const UmmaChunks<N>& c, int k0, int k_end,
                                                  bool vec_ok) {
-  if (vec_ok && k0 + UMMA_BK <= k_end) {
+  const bool full = vec_ok && k0 + UMMA_BK <= k_end;
 #pragma unroll
-    for (int i = 0; i < N; ++i)
-      if (c.soff[i] >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(c.ptr[i] + k0));
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c.soff[i] >= 0) {
-        const int k = k0 + c.kq[i];
-        const float* p = c.ptr[i] + k0;
+  for (int i = 0; i < N; ++i) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < c.n_own && c.row0 + 32 * i < c.rows_valid) {
+      const float* p = c.ptr0 + i * c.step + k0;
+      if (full) {
+        t = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        const int k = k0 + c.kq;
         if (k < k_end) t.x = __ldg(p);
         if (k + 1 < k_end) t.y = __ldg(p + 1);
         if (k + 2 < k_end) t.z = __ldg(p + 2);
         if (k + 3 < k_end) t.w = __ldg(p + 3);
       }
-      v[i] = t;
     }
+    v[i] = t;
   }
 }
 
-// transposed operand: the chunk (row, k .. k+3) is read from base[(k + j) * ld + row]; c.ptr holds
-// base + row + kq * ld.  Eight lanes (rows) share a 32-byte sector per k, so the reads stay sector-efficient.
+// transposed operand: the chunk (row, k .. k+3) is read from base[(k + j) * ld + row] with scalar loads.  Eight
+// lanes (rows) share a 32-byte sector per k, so the reads stay sector-efficient.
 template <int N>
 __device__ __forceinline__ void umma_chunks_load_t(float4 (&v)[N], const UmmaChunks<N>& c, int k0, int k_end,
                                                    int64_t ld) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c.soff[i] >= 0) {
-      const int k = k0 + c.kq[i];
-      const float* p = c.ptr[i] + (int64_t)k0 * ld;
+    if (i < c.n_own && c.row0 + 32 * i < c.rows_valid) {
+      const int k = k0 + c.kq;
+      const float* p = c.ptr0 + i * c.step + (int64_t)k0 * ld;
       if (k < k_end) t.x = __ldg(p);
       if (k + 1 < k_end) t.y = __ldg(p + ld);
       if (k + 2 < k_end) t.z = __ldg(p + 2 * ld);
@@ -316,22 +320,24 @@ __device__ __forceinline__ void umma_chunks_load_t(float4 (&v)[N], const UmmaChu
 // ROWS and transposed inside quads of lanes: lane (rq = (lane >> 2) & 1, q = lane & 3, kc) loads the float4
 // (k = 4 kc + q, rows 4 rq .. 4 rq + 3), then the four lanes of a quad exchange components with four shuffles so
 // that lane q ends up with (row 4 rq + q, k = 4 kc .. 4 kc + 3) - exactly the K-major chunk it has to store.
-// c.ptr = base + (4 kc + q) * ld + first row of the quad; c.nv = rows of the quad that exist (0..4).
+// c.ptr0 = base + (4 kc + q) * ld + first row of the quad.
 template <int N>
 __device__ __forceinline__ void umma_chunks_load_tv(float4 (&v)[N], const UmmaChunks<N>& c, int k0, int k_end,
                                                     int64_t ld, int lane) {
   const int q = lane & 3;
+  const bool k_ok = k0 + c.kq + q < k_end;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c.soff[i] >= 0 && k0 + c.kq[i] + q < k_end && c.nv[i] > 0) {
-      const float* p = c.ptr[i] + (int64_t)k0 * ld;
-      if (c.nv[i] == 4) {
+    const int left = c.rows_valid - ((c.row0 + 32 * i) & ~3);     // rows of this quad that exist
+    if (i < c.n_own && k_ok && left > 0) {
+      const float* p = c.ptr0 + i * c.step + (int64_t)k0 * ld;
+      if (left >= 4) {
         t = __ldg(reinterpret_cast<const float4*>(p));
       } else {
         t.x = __ldg(p);
-        if (c.nv[i] > 1) t.y = __ldg(p + 1);
-        if (c.nv[i] > 2) t.z = __ldg(p + 2);
+        if (left > 1) t.y = __ldg(p + 1);
+        if (left > 2) t.z = __ldg(p + 2);
       }
     }
     // 4 x 4 transpose inside the quad: in round j lane q sends its component (q ^ j) to lane q ^ j and receives
@@ -356,11 +362,11 @@ __device__ __forceinline__ void umma_chunks_store(float* hi_plane, float* lo_pla
                                                   const float4 (&v)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    if (c.soff[i] >= 0) {
+    if (i < c.n_own) {
       float4 h, l;
       tf32_split(v[i], h, l);
-      *reinterpret_cast<float4*>(hi_plane + c.soff[i]) = h;
-      *reinterpret_cast<float4*>(lo_plane + c.soff[i]) = l;
+      *reinterpret_cast<float4*>(hi_plane + c.soff0 + 128 * i) = h;
+      *reinterpret_cast<float4*>(lo_plane + c.soff0 + 128 * i) = l;
     }
   }
 }
