@@ -1067,8 +1067,12 @@ extern "C" int tiger_sgemm_ex(const float* A, int64_t lda, int trans_a, const fl
   g.vec_a = (!trans_a && (((uintptr_t)A) & 15) == 0 && (lda & 3) == 0) ? 1 : 0;
   g.vec_w = (!trans_w && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0) ? 1 : 0;
   g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
-  g.mn_a = (trans_a && (((uintptr_t)A) & 15) == 0 && (lda & 3) == 0 && getenv("TIGER_NO_MN_MAJOR") == nullptr) ? 1 : 0;
-  g.mn_w = (trans_w && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0 && getenv("TIGER_NO_MN_MAJOR") == nullptr) ? 1 : 0;
+  // vector loads along the rows + in-quad transposes (mode 2) measured SLOWER than the scalar transposed loader
+  // (mode 1) on B200 (ncu, weight gradient 344 x 516 x 6000: 185 us vs 93 us - the producers are instruction-bound and
+  // the 4 shuffles + selects per chunk cost more than the 3 extra load instructions), so it is opt-in (TIGER_TV=1)
+  const bool tv = getenv("TIGER_TV") != nullptr;
+  g.mn_a = (tv && trans_a && (((uintptr_t)A) & 15) == 0 && (lda & 3) == 0) ? 1 : 0;
+  g.mn_w = (tv && trans_w && (((uintptr_t)W) & 15) == 0 && (ldw & 3) == 0) ? 1 : 0;
   const int64_t tiles_m = (m_rows + TCG_BM - 1) / TCG_BM;
   g.bn = gemm_pick_bn(m_rows, n_cols, accumulate ? k_parts : 1, sms, TCG_MAX_BN);
   g.tiles_n = (n_cols + g.bn - 1) / g.bn;
