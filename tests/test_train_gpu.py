@@ -181,60 +181,79 @@ def test_training_through_torch_optimizer_and_native_adam_agree():
     assert np.allclose(la, lb, rtol=1e-4), (la, lb)
 
 
-@pytest.mark.parametrize('dropout', [0.0, 0.1])
-@pytest.mark.parametrize('name', ['seq_left_right', 'static_right_right_dim10'])
-def test_dropout_step_is_seeded_and_consistent_with_finite_differences(name, dropout):
-    """With dropout on, forward and backward must use the same masks: the analytic directional derivative along
-    random parameter directions is compared with central differences of the (seeded, hence repeatable) forward;
-    dropout 0 is the control (those gradients are pinned against the reference above)."""
+def _mix32(x):
+    x = x & 0xffffffff
+    x ^= x >> 16
+    x = (x * 0x7feb352d) & 0xffffffff
+    x ^= x >> 15
+    x = (x * 0x846ca68b) & 0xffffffff
+    x ^= x >> 16
+    return x
+
+
+def keep_mask(seed: int, stream: int, n: int, p: float) -> np.ndarray:
+    """The counter-based dropout decisions of csrc/train.cu (dropout_keep), restated with numpy."""
+    idx = np.arange(n, dtype=np.uint64)
+    h = _mix32(idx ^ _mix32(np.uint64((seed + 0x9E3779B9 * (stream + 1)) & 0xffffffff)))
+    return ((h >> 8).astype(np.float32) * np.float32(1.0 / 16777216.0)) >= np.float32(p)
+
+
+@pytest.mark.parametrize('name', ['seq_left_right', 'static_right_right_dim10', 'seq_nfeats_left_left'])
+def test_dropout_step_matches_autograd_route_with_the_same_masks(name, monkeypatch):
+    """Dropout 0.1: the native step (seeded counter-based masks) vs the torch-op autograd route with
+    torch.nn.functional.dropout replaced by the SAME masks - losses and every gradient must agree, i.e. forward
+    and backward of every dropout site (attention weights, scorer, restarter attention, restarter merger) use one
+    consistent mask."""
+    import torch.nn.functional as F
     g = Golden(name)
-    dl, model = setup(g, dropout=dropout)
-    model.train()
-    model.reset()
-    batches = [to_dev(b) for _, b in zip(range(5), dl)]
-    tr = model.native_trainer(g.bs)
-    for b in batches[:4]:
-        tr.forward(*b)
-    snap = model.save_memory_state()
+    p = 0.1
+    dl, native = setup(g, dropout=p)
+    _, ref = setup(g, dropout=p)
+    native.train(), ref.train()
+    native.reset(), ref.reset()
+    tr = native.native_trainer(g.bs)
+    H, K, L = g.n_heads, g.K, g.hist_len
+    for ib, batch in zip(range(6), dl):
+        b = to_dev(batch)
+        B = len(b[0])
+        d = native.nfeat_dim
+        native.zero_grad(set_to_none=True)
+        c1, m1 = native.contrast_and_mutual_learning(*b)
+        seed = tr.n_steps * 101 & 0x7fffffff                      # NativeTrainer._core with trainer seed 0
+        (c1 + m1).backward()
+        n_pos = b[5].restart_data.nids.numel()
+        queue = [torch.from_numpy(keep_mask(seed, 1, 3 * B * H * K, p)).reshape(3 * B * H, 1, K)]
+        score = torch.from_numpy(keep_mask(seed, 2, 2 * B * d, p)).reshape(2 * B, d)
+        queue += [score[:B], score[B:]]
+        if g.restarter == 'seq':
+            queue.append(torch.from_numpy(keep_mask(seed, 3, n_pos * H * L * L, p)).reshape(n_pos * H, L, L))
+            queue.append(torch.from_numpy(keep_mask(seed, 4, n_pos * d, p)).reshape(n_pos, d))
+        queue = [q.to(DEV) for q in queue]
 
-    def loss_at(step_id):
-        model.load_memory_state(tuple(s.clone() for s in snap))
-        tr.n_steps = step_id
-        c, m = tr.forward(*batches[4])
-        return float(c), float(m)
+        def fake_dropout(x, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return x
+            mask = queue.pop(0)
+            assert mask.shape == x.shape, (mask.shape, x.shape)
+            return x * mask.to(x.dtype) / (1.0 - p)
 
-    base = loss_at(100)
-    assert loss_at(100) == base                      # same seed -> same masks -> bit-identical losses
-    assert (loss_at(101) != base) == (dropout > 0)   # another step, other masks
-    # the two losses are checked separately: the restarter's targets depend on the other parameters but are detached
-    # (tiger.py:590), so the mutual loss is differentiated w.r.t. the restarter only, the contrast loss w.r.t. the rest;
-    # the time-encoder frequencies are left out (a frequency step times a time difference of 1e3 s is far outside
-    # the linear regime)
-    for which, own, (gc, gm) in ((0, lambda k: not k.startswith('restarter_fn.'), (1.0, 0.0)),
-                                 (1, lambda k: k.startswith('restarter_fn.'), (0.0, 1.0))):
-        model.load_memory_state(tuple(s.clone() for s in snap))
-        tr.n_steps = 100
-        tr.fp.grad_all.zero_()
-        tr.forward(*batches[4])
-        tr.backward(gc, gm)
-        grads = {k: v.clone() for k, v in tr.fp.g.items()}
-        gen = torch.Generator(device='cuda').manual_seed(5)
-        for trial in range(3):
-            direction = {k: (torch.randn(v.shape, device='cuda', generator=gen) if own(k) and not k.endswith('basis_freq')
-                             else torch.zeros_like(v)) for k, v in tr.fp.p.items()}
-            an = sum(float((grads[k].double() * direction[k].double()).sum()) for k in direction)
-            eps = 2e-4
-            for k, v in tr.fp.p.items():
-                v.add_(direction[k], alpha=eps)
-            up = loss_at(100)[which]
-            for k, v in tr.fp.p.items():
-                v.add_(direction[k], alpha=-2 * eps)
-            dn = loss_at(100)[which]
-            for k, v in tr.fp.p.items():
-                v.add_(direction[k], alpha=eps)
-            fd = (up - dn) / (2 * eps)
-            assert abs(fd - an) <= 0.02 * max(abs(fd), abs(an)) + 2e-3, \
-                f'{name} p={dropout} loss {which} trial {trial}: fd {fd:.5f} vs analytic {an:.5f}'
+        monkeypatch.setenv('TIGER_AUTOGRAD_ROUTE', '1')
+        monkeypatch.setattr(F, 'dropout', fake_dropout)
+        ref.zero_grad(set_to_none=True)
+        c2, m2 = ref.contrast_and_mutual_learning(*b)
+        (c2 + m2).backward()
+        monkeypatch.undo()
+        assert not queue, f'{len(queue)} dropout sites of the autograd route were not reached'
+        what = f'{name} b{ib}'
+        assert_close(cpu(c1).reshape(1), cpu(c2).reshape(1), 1e-5, what + ' contrast')
+        assert_close(cpu(m1).reshape(1), cpu(m2).reshape(1), 2e-5, what + ' mutual')
+        got = {k: grad_of(pp) for k, pp in unique_named_params(native)}
+        want = {k: grad_of(pp) for k, pp in unique_named_params(ref)}
+        check_grads(got, want, what)
+        assert_close(cpu(native.left_memory.vals), cpu(ref.left_memory.vals), 1e-5, what + ' left memory')
+    # seeded: the same step number reproduces the same masks, another one does not
+    assert np.array_equal(keep_mask(7, 1, 64, p), keep_mask(7, 1, 64, p))
+    assert not np.array_equal(keep_mask(7, 1, 64, p), keep_mask(8, 1, 64, p))
 
 
 # ------------------------------------------------------------------------------------------
