@@ -66,6 +66,9 @@ def parse_args():
     p.add_argument('--parity-batches', type=int, default=3,
                    help='batches replayed after a reset and compared with the CPU arm (0 = off)')
     p.add_argument('--cpu-kind', default='auto', choices=['auto', 'reference', 'port'])
+    p.add_argument('--train-steps', type=int, default=100,
+                   help='infer mode: also time this many training steps (fwd + bwd + all-reduce + Adam) of the same '
+                        'configuration and report them under "train_step" (0 = off)')
     return p.parse_args()
 
 
@@ -572,13 +575,22 @@ def run_b200(args):
             cpu['port'] = {'value': n2 * B / dt2, 'unit': UNIT, 'cores': port.cores, 'kind': 'port',
                            'sample': port.describe(n2, first + 2), 'ms_per_step': dt2 / n2 * 1e3}
 
+    # ---- the training step of the same configuration (DDP at N > 1: gradient all-reduce inside the timed region) ----
+    train_step = None
+    if args.train_steps > 0:
+        del runner
+        t = measure_train(args, wl, args.train_steps, min(Wm, 10), parity=False, cpu=False, e2e=False, profile_steps=0)
+        train_step = {'metric': METRIC_TRAIN, 'value': t['value'], 'unit': UNIT, 'ms_per_step': t['ms_per_step'],
+                      'n_gpus': world, **t['train']}
+
     if rank == 0:
         line = {
             'metric': metric_name(args), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, shape, st, world),
             'e2e': e2e, 'gpu_launches': eng.launches_per_step() * K, 'clocks': clk, 'roofline': roofline,
-            'cpu_baseline': cpu, 'parity_checked': bool(parity), 'parity': parity, 'kernels': kernels,
+            'cpu_baseline': cpu, 'parity_checked': bool(parity), 'parity': parity, 'train_step': train_step,
+            'kernels': kernels,
         }
         print(json.dumps(line))
     if world > 1:
@@ -606,13 +618,32 @@ def run_train(args):
     """One step = the loop body of train_self_supervised_ddp.py:186-214 for one batch of 200 events: neighbor finder,
     lazy restart of not-yet-seen nodes, contrast_and_mutual_learning forward, backward, gradient all-reduce over NCCL
     (N > 1; one bucket = the flat gradient buffer, 1/N folded into the optimizer), Adam.  lr = 1e-4 * sqrt(N) (:146)."""
+    import torch.distributed as dist
+    wl = DeviceWorkload(args, mode='train')
+    r = measure_train(args, wl, args.steps, args.warmup, parity=True, cpu=True, e2e=not args.no_e2e,
+                      profile_steps=args.profile_steps)
+    if wl.rank == 0:
+        line = {
+            'metric': metric_name(args), 'value': r['value'], 'unit': UNIT, 'n_gpus': wl.world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, wl.shape, wl.st, wl.world),
+            'e2e': r['e2e'], 'gpu_launches': r['gpu_launches'], 'clocks': r['clocks'], 'roofline': r['roofline'],
+            'cpu_baseline': r['cpu_baseline'], 'parity_checked': bool(r['parity']), 'parity': r['parity'],
+            'train': r['train'], 'kernels': r['kernels'],
+        }
+        print(json.dumps(line))
+    if wl.world > 1:
+        dist.destroy_process_group()
+
+
+def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     import torch
     import torch.distributed as dist
     from www2023tiger_b200 import train as T, train_seq as TS, ops
     from www2023tiger_b200.init import build_model
     from www2023tiger_b200.tiger.data.graph import Graph
 
-    wl = DeviceWorkload(args, mode='train')
     rank, world, dev = wl.rank, wl.world, wl.dev
     shape, st, rst, arm, dev_in, host_in, avail, lo = wl.shape, wl.st, wl.rst, wl.arm, wl.dev_in, wl.host_in, wl.avail, wl.lo
     B, d, de = BATCH, wl.d, wl.de
@@ -621,7 +652,7 @@ def run_train(args):
     model = build_model(None, wl.efeats, graph, wl.N, st.n_events, dev, dim=shape.dim, n_layers=1, n_heads=N_HEAD,
                         n_neighbors=K_NEIGH, hit_type='bin', dropout=0.1, restarter_type=rst, hist_len=HIST_LEN,
                         msg_src=shape.msg_src, upd_src=shape.upd_src)
-    if arm is not None:
+    if arm is not None and arm.kind == 'reference':
         res = model.load_state_dict(arm.weights(), strict=False)
         assert not res.unexpected_keys, res.unexpected_keys
     if world > 1:                                  # DDP broadcasts rank 0's parameters at construction (:145)
@@ -632,26 +663,25 @@ def run_train(args):
     tr = model.native_trainer(B, lr=lr, seed=args.seed)
     tr.attach_stream(wl.csr, HIST_LEN)
     losses = torch.zeros(2, device=dev)
-    comm = {'bytes': tr.fp.grad_all.numel() * 4 if world > 1 else 0}
+    comm_bytes = tr.fp.grad_all.numel() * 4 if world > 1 else 0
 
     def allreduce(t):
         return dist.all_reduce(t, async_op=True) if world > 1 else None
 
-    def device_step(i, inp=None):
+    def device_step(i):
         j = i % avail
         if j == 0 and i > 0:
             tr.reset_stream()                      # epoch boundary: the window wraps (model.reset(), :176)
-        closs, mloss = tr.step_stream(dev_in[j] if inp is None else inp, mutual_coef=1.0, grad_scale=1.0 / world,
-                                      allreduce=allreduce)
+        closs, mloss = tr.step_stream(dev_in[j], mutual_coef=1.0, grad_scale=1.0 / world, allreduce=allreduce)
         losses[0:1].add_(closs)
         losses[1:2].add_(mloss)
 
     # ---- parity: the first training steps from a reset, dropout off on both sides, against the reference's loop body
-    parity = None
-    if arm is not None and args.parity_batches > 0 and arm.kind == 'reference':
-        parity = check_train_parity(args, wl, model, tr)
+    par = None
+    if parity and arm is not None and args.parity_batches > 0 and arm.kind == 'reference':
+        par = check_train_parity(args, wl, model, tr)
     tr.reset_stream()
-    Wm, K = args.warmup, args.steps
+    Wm, K = warmup, steps
     for i in range(Wm):
         device_step(i)
     wl.barrier()
@@ -671,8 +701,8 @@ def run_train(args):
     mean_losses = (losses / (K * world)).cpu().tolist()
 
     # ---- e2e: the batch record comes from pinned host memory every step, the two losses go back to the host ----
-    e2e = None
-    if not args.no_e2e:
+    e2e_out = None
+    if e2e:
         tr.reset_stream()
         pin = [torch.empty(5 * B, dtype=torch.int64).pin_memory() for _ in range(4)]
         d_in = [torch.empty(5 * B, dtype=torch.int64, device=dev) for _ in range(4)]
@@ -700,13 +730,13 @@ def run_train(args):
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0, world, dev)
         tr.check_errors()
-        e2e = {'value': world * K * B / dt, 'unit': UNIT, 'h2d_bytes_per_step': 5 * B * 8, 'd2h_bytes_per_step': 8,
-               'ms_per_step': dt / K * 1e3, 'mean_loss': float(h_out[Wm:].sum(1).mean())}
+        e2e_out = {'value': world * K * B / dt, 'unit': UNIT, 'h2d_bytes_per_step': 5 * B * 8, 'd2h_bytes_per_step': 8,
+                   'ms_per_step': dt / K * 1e3, 'mean_loss': float(h_out[Wm:].sum(1).mean())}
     clk = clocks.stop() if clocks is not None else None
 
     # ---- per-entry-point CUDA-event breakdown + launch count ----
     kernels, roofline, launches = None, None, None
-    if rank == 0 and args.profile_steps > 0:
+    if rank == 0 and profile_steps > 0:
         from www2023tiger_b200 import _lib
         tr.reset_stream()
         records = []
@@ -718,7 +748,7 @@ def run_train(args):
             orig(name, *a)
             e1.record()
             records.append((name, e0, e1))
-        n_steps = min(args.profile_steps, avail)
+        n_steps = min(profile_steps, avail)
         warm = min(10, n_steps // 2)
         counts = []
         ops.call = T.call = TS.call = timed_call
@@ -757,32 +787,23 @@ def run_train(args):
                         'peak_source': 'half of the measured bf16 GEMM peak (tf32 runs at half the bf16 rate)'
                         if peaks else 'fallback',
                         'note': 'all tensor-core products of the step (forward, input and weight gradients) together: '
-                                'issued = 3 x useful flops (tf32x3); eager launches timed with CUDA events per entry point'}
+                                'issued = 3 x useful flops (tf32x3); entry-point granularity: CUDA events around the '
+                                'eager C-ABI calls include the launch gaps between them - profiles/ holds the ncu launch '
+                                'list with the kernel durations'}
 
     # ---- CPU baseline: the reference's training loop body on the host cores ----
-    cpu = None
-    if arm is not None:
-        first = 0
-        arm.ref.reset(train=True) if arm.kind == 'reference' else None
-        n, dt = arm.time(first, min(args.cpu_batches, avail - 4), args.cpu_seconds, warmup=1)
-        cpu = {'value': n * B / dt, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind, 'sample': arm.describe(n, 1),
-               'ms_per_step': dt / n * 1e3}
-
-    if rank == 0:
-        line = {
-            'metric': metric_name(args), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, shape, st, world),
-            'e2e': e2e, 'gpu_launches': int(round((launches or 0) * K)), 'clocks': clk, 'roofline': roofline,
-            'cpu_baseline': cpu, 'parity_checked': bool(parity), 'parity': parity,
-            'train': {'lr': lr, 'optimizer': 'Adam (flat buffer, one kernel)', 'params': tr.fp.numel,
-                      'allreduce_bytes_per_step': comm['bytes'], 'mean_contrast_loss': mean_losses[0],
-                      'mean_mutual_loss': mean_losses[1], 'dropout': 0.1},
-            'kernels': kernels,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    cpu_out = None
+    if cpu and arm is not None:
+        if arm.kind == 'reference':
+            arm.ref.reset(train=True)
+        n, dt = arm.time(0, min(args.cpu_batches, avail - 4), args.cpu_seconds, warmup=1)
+        cpu_out = {'value': n * B / dt, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind, 'sample': arm.describe(n, 1),
+                   'ms_per_step': dt / n * 1e3}
+    return {'value': value, 'ms_per_step': ms / K, 'e2e': e2e_out, 'gpu_launches': int(round((launches or 0) * K)),
+            'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu_out, 'parity': par, 'kernels': kernels,
+            'train': {'lr': lr, 'optimizer': 'Adam (flat buffer, per-tensor step counters)', 'params': tr.fp.numel,
+                      'allreduce_bytes_per_step': comm_bytes, 'mean_contrast_loss': mean_losses[0],
+                      'mean_mutual_loss': mean_losses[1], 'dropout': 0.1, 'steps': K}}
 
 
 def check_train_parity(args, wl, model, tr):
