@@ -78,6 +78,20 @@ class FlatParams:
         self.seg_bc = torch.zeros(2 * len(self.names), dtype=f32, device=dev)
         self.max_seg = max(p.numel() for p in self.params)
 
+    def comm_ranges(self):
+        """Three contiguous slices of the flat gradient buffer, in the order the backward pass completes them:
+        restarter (+ the gates), attention / hit embedding / scorer, time encoder + GRU - so that each can be
+        all-reduced while the rest of the backward pass still runs.  None when the parameter order differs."""
+        first = lambda prefix: next((o for n, o in zip(self.names, self.offsets) if n.startswith(prefix)), None)
+        a, r = first('temporal_embedding_fn.'), first('restarter_fn.')
+        order_ok = a is not None and r is not None and a < r and all(
+            (o < a) == n.startswith(('time_encoder.', 'right_mem_updater.')) and (o >= r) == n.startswith('restarter_fn.')
+            for n, o in zip(self.names, self.offsets))
+        if not order_ok:
+            return None
+        total = self.grad_all.numel()
+        return {'restarter': (r, total), 'attention': (a, r), 'gru': (0, a)}
+
     def reset_optimizer(self):
         self.exp_avg.zero_(), self.exp_avg_sq.zero_(), self.grad_all.zero_(), self.seg_step.zero_()
 
@@ -387,17 +401,30 @@ class NativeTrainer:
     def step_stream(self, inp: Tensor, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, allreduce=None,
                     lr: Optional[float] = None):
         closs, mloss = self.forward_stream(inp)
-        self.backward(1.0, mutual_coef)
-        work = allreduce(self.fp.grad_all) if allreduce is not None else None
-        if work is not None:
-            work.wait()
+        if allreduce is None:
+            self.backward(1.0, mutual_coef)
+        else:
+            # one bucket per slice of the flat gradient buffer, started as soon as the backward pass has completed it
+            ranges = self.fp.comm_ranges()
+            works = []
+            if ranges is None:
+                self.backward(1.0, mutual_coef)
+                works.append(allreduce(self.fp.grad_all))
+            else:
+                self.backward(1.0, mutual_coef,
+                              comm=lambda name: works.append(allreduce(self.fp.grad_all[ranges[name][0]:ranges[name][1]])))
+            for w in works:
+                if w is not None:
+                    w.wait()
         self.fp.adam(self.lr if lr is None else lr, grad_scale=grad_scale)
         return closs, mloss
 
     # ------------------------------------------------------------------ backward
-    def backward(self, g_contrast: float = 1.0, g_mutual: float = 1.0):
+    def backward(self, g_contrast: float = 1.0, g_mutual: float = 1.0, comm=None):
         """Accumulates d(g_contrast * contrast_loss + g_mutual * mutual_loss)/d(parameters) into the flat gradient
-        buffer (call once per forward)."""
+        buffer (call once per forward).  `comm(slice_name)` is called as soon as a slice of the gradient buffer
+        (FlatParams.comm_ranges) is complete: the DDP loop starts that slice's all-reduce there, beside the rest of
+        the backward pass - the restarter runs first because it is the longest part and depends on nothing else."""
         ctx = self._ctx
         assert ctx is not None, 'backward() needs a forward()'
         self._ctx = None
@@ -406,6 +433,17 @@ class NativeTrainer:
         P, G = self.fp.p, self.fp.g
         cnt_o = self.counts[1:]
         s, a, c = 'score_fn.', 'temporal_embedding_fn.fns.0.', 'right_mem_updater.cell.'
+        # ---- restarter
+        tg = ctx['targets']
+        if tg is not None and g_mutual != 0.0:
+            if self.rkind == 'static':
+                for side, dp in (('left', self.dpred_l), ('right', self.dpred_r)):
+                    call('tiger_train_scatter_add_rows', ptr(G[f'restarter_fn.{side}_emb.weight']), ptr(tg['nids']),
+                         tg['n'], ptr(tg['count']), 1, ptr(dp), d, d, float(g_mutual))
+            else:
+                self.seq.backward(self.dpred_l, self.dpred_r, float(g_mutual))
+        if comm is not None:
+            comm('restarter')
         # ---- scorer
         call('tiger_train_score_head_bwd', ptr(self.dscore), float(g_contrast), ptr(self.hid_s), ptr(P[s + 'fc2.weight']),
              B, d, ctx['p_score'], ptr(self.dhid_s), ptr(G[s + 'fc2.weight']), ptr(G[s + 'fc2.bias']))
@@ -434,6 +472,8 @@ class NativeTrainer:
                     g_in_b[E:2 * E], self.dkv_in, m=nq * K, k_parts=16)
         _linear_bwd(self.dKV[:, E:], self.kv_in, P[a + 'mha_fn.v_proj_weight'], G[a + 'mha_fn.v_proj_weight'],
                     g_in_b[2 * E:], self.dkv_in, m=nq * K, k_parts=16, accumulate_dx=True)
+        if comm is not None:
+            comm('attention')
         # ---- representation gradients back onto the GRU rows, TimeEncode gradients
         call('tiger_train_attn_build_bwd', ptr(self.dkv_in), ptr(self.dq_in), ptr(self.dcat), E + d, E,
              ptr(ctx['batch_nids']), nq, ptr(ctx['ts']), B, ptr(ctx['nn']), ptr(ctx['nt']), K, ptr(self.gru_row), d, de,
@@ -446,15 +486,8 @@ class NativeTrainer:
                     count=cnt_o)
         _linear_bwd(self.dGh, self.Hs, P[c + 'weight_hh'], G[c + 'weight_hh'], G[c + 'bias_hh'], None, m=cap, k_parts=16,
                     count=cnt_o)
-        # ---- restarter
-        tg = ctx['targets']
-        if tg is not None and g_mutual != 0.0:
-            if self.rkind == 'static':
-                for side, dp in (('left', self.dpred_l), ('right', self.dpred_r)):
-                    call('tiger_train_scatter_add_rows', ptr(G[f'restarter_fn.{side}_emb.weight']), ptr(tg['nids']),
-                         tg['n'], ptr(tg['count']), 1, ptr(dp), d, d, float(g_mutual))
-            else:
-                self.seq.backward(self.dpred_l, self.dpred_r, float(g_mutual))
+        if comm is not None:
+            comm('gru')
 
     # ------------------------------------------------------------------ whole step
     def step(self, src, dst, neg, ts, eids, cg, *, mutual_coef: float = 1.0, contrast_only: bool = False,
