@@ -43,8 +43,9 @@ def init_model(nfeats, efeats, train_graph, full_graph_num_node, n_edges, device
 
 def model_from_golden(g, graph, device, dropout=0.1):
     m = init_model(g.nfeats, g.efeats, graph, g.N, len(g.src), device, dim=g.dim,
-                   n_layers=1, n_heads=g.n_heads, n_neighbors=g.K, hit_type='bin', dropout=dropout,
-                   restarter_type=g.restarter, hist_len=g.hist_len, msg_src=g.msg_src, upd_src=g.upd_src)
+                   n_layers=g.n_layers, n_heads=g.n_heads, n_neighbors=g.K, hit_type=g.hit_type, dropout=dropout,
+                   restarter_type=g.restarter, hist_len=g.hist_len, msg_src=g.msg_src, upd_src=g.upd_src,
+                   msg_tsfm_type=g.tsfm, mem_update_type=g.upd)
     return m
 
 

@@ -42,6 +42,17 @@ CASES = {
     'seq_nfeats_left_left': (StreamShape('g5', 30, 10, 600, 6, None, horizon=4000.), 12,
                              dict(dim=None, restarter_type='seq', msg_src='left', upd_src='left', hist_len=4), 20, 12, False),
 }
+# non-default operator variants: n_layers = 2 (collator recursion with float32 re-query times,
+# data_loader.py:124-131; temporal_agg_modules.py:59-65), hit_type vec | count (tiger.py:261-275), upd_fn merge
+# (update_modules.py:40-47), tsfm_fn linear | mlp (message_modules.py:29-55).  Written as var_<name>.npz.
+VARIANTS = {
+    'var_two_layers': ('seq_left_right', dict(n_layers=2)),
+    'var_hit_vec': ('static_right_right_dim10', dict(hit_type='vec')),
+    'var_hit_count': ('seq_left_right', dict(hit_type='count')),
+    'var_upd_merge': ('seq_left_right', dict(mem_update_type='merge')),
+    'var_tsfm_linear': ('static_right_right_dim10', dict(msg_tsfm_type='linear')),
+    'var_tsfm_mlp': ('seq_nfeats_left_left', dict(msg_tsfm_type='mlp')),
+}
 N_NEIGHBORS = 5
 N_HEADS = 2
 
@@ -50,18 +61,21 @@ def t2n(x):
     return x.detach().cpu().numpy().copy()   # copy: state tensors are mutated in place later
 
 
-def run_case(name, shape, nfeat_dim, mk, bs, n_batches, lazy_restart):
+def run_case(name, shape, nfeat_dim, mk, bs, n_batches, lazy_restart, variant=None):
+    variant = {**dict(n_layers=1, hit_type='bin', msg_tsfm_type='id', mem_update_type='gru'), **(variant or {})}
+    n_layers = variant['n_layers']
     torch.manual_seed(0)
     np.random.seed(0)
     st = make_stream(shape, seed=1, nfeat_dim=nfeat_dim)
     full = InteractionData(st.src, st.dst, st.ts, st.eids, st.labels, seed=0, eval=True)
     g = Graph.from_data(full, strategy='recent_edges', seed=0, max_node_id=st.n_nodes - 1)
-    coll = GraphCollator(g, N_NEIGHBORS, 1, restarter=mk['restarter_type'], hist_len=mk['hist_len'])
+    coll = GraphCollator(g, N_NEIGHBORS, n_layers, restarter=mk['restarter_type'], hist_len=mk['hist_len'])
     model = init_model(st.nfeats, st.efeats, g, g, full, torch.device('cpu'),
-                       feature_as_buffer=True, dim=mk['dim'], n_layers=1, n_heads=N_HEADS,
-                       n_neighbors=N_NEIGHBORS, hit_type='bin', dropout=0.1,
+                       feature_as_buffer=True, dim=mk['dim'], n_layers=n_layers, n_heads=N_HEADS,
+                       n_neighbors=N_NEIGHBORS, hit_type=variant['hit_type'], dropout=0.1,
                        restarter_type=mk['restarter_type'], hist_len=mk['hist_len'],
-                       msg_src=mk['msg_src'], upd_src=mk['upd_src'], msg_tsfm_type='id', mem_update_type='gru')
+                       msg_src=mk['msg_src'], upd_src=mk['upd_src'], msg_tsfm_type=variant['msg_tsfm_type'],
+                       mem_update_type=variant['mem_update_type'])
     # non-trivial values for parameters the reference initialises to zero / constants
     with torch.no_grad():
         model.time_encoder.phase.normal_(0, 0.3)
@@ -76,6 +90,8 @@ def run_case(name, shape, nfeat_dim, mk, bs, n_batches, lazy_restart):
            'meta_n_neighbors': N_NEIGHBORS, 'meta_n_heads': N_HEADS, 'meta_hist_len': mk['hist_len'],
            'meta_n_nodes': st.n_nodes, 'meta_dim': model.nfeat_dim, 'meta_restarter': mk['restarter_type'],
            'meta_msg_src': mk['msg_src'], 'meta_upd_src': mk['upd_src'],
+           'meta_n_layers': n_layers, 'meta_hit_type': variant['hit_type'], 'meta_tsfm': variant['msg_tsfm_type'],
+           'meta_upd': variant['mem_update_type'],
            'stream_src': st.src, 'stream_dst': st.dst, 'stream_ts': st.ts, 'stream_eids': st.eids,
            'stream_neg': full.neg_dst}
     if st.efeats is not None:
@@ -101,6 +117,9 @@ def run_case(name, shape, nfeat_dim, mk, bs, n_batches, lazy_restart):
             src, dst, neg, ts, eids, _, cg = coll(batch)
             p = f'b{ib}_'
             out[p + 'neigh_nids'], out[p + 'neigh_eids'], out[p + 'neigh_ts'] = (t2n(x) for x in cg.layers[1])
+            for depth in range(2, n_layers + 1):
+                for x, nm in zip(cg.layers[depth], ('neigh_nids', 'neigh_eids', 'neigh_ts')):
+                    out[p + f'l{depth}_' + nm] = t2n(x)
             out[p + 'involved'] = cg.np_computation_graph_nodes
             out[p + 'local_index'] = t2n(cg.local_index)
             for hn, hv in zip(('src_hits', 'dst_hits', 'neg_src_hits', 'neg_dst_hits'), cg.hit_data):
@@ -165,5 +184,10 @@ def run_case(name, shape, nfeat_dim, mk, bs, n_batches, lazy_restart):
 
 
 if __name__ == '__main__':
+    only = sys.argv[1:]
     for name, args in CASES.items():
-        run_case(name, *args)
+        if not only or name in only:
+            run_case(name, *args)
+    for name, (base, variant) in VARIANTS.items():
+        if not only or name in only or 'variants' in only:
+            run_case(name, *CASES[base], variant=variant)

@@ -7,7 +7,8 @@ import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 _ALL = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-CASES = [c for c in _ALL if not c.startswith(('full_', 'train_'))]   # toy-size fixtures (make_golden.py)
+CASES = [c for c in _ALL if not c.startswith(('full_', 'train_', 'var_'))]   # toy-size fixtures (make_golden.py)
+VAR_CASES = [c for c in _ALL if c.startswith('var_')]           # non-default operator variants (make_golden.py)
 TRAIN_CASES = [c for c in _ALL if c.startswith('train_')]       # training-step fixtures (make_golden_train.py)
 FULL_CASES = [c for c in _ALL if c.startswith('full_')]         # BASELINE-dimension fixtures (make_golden_full.py)
 
@@ -28,6 +29,9 @@ class Golden:
         self.restarter = str(m('restarter'))
         self.msg_src = str(m('msg_src'))
         self.upd_src = str(m('upd_src'))
+        opt = lambda k, default: type(default)(self.z['meta_' + k]) if 'meta_' + k in self.z else default
+        self.n_layers, self.hit_type = opt('n_layers', 1), opt('hit_type', 'bin')
+        self.tsfm, self.upd = opt('tsfm', 'id'), opt('upd', 'gru')
         self.src, self.dst, self.ts = self.z['stream_src'], self.z['stream_dst'], self.z['stream_ts']
         self.eids, self.neg = self.z['stream_eids'], self.z['stream_neg']
         self.efeats = self.z.get('stream_efeats')

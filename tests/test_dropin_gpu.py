@@ -6,7 +6,7 @@ import pytest
 import torch
 from torch.utils.data import DataLoader
 
-from golden_utils import CASES, Golden, assert_close
+from golden_utils import CASES, VAR_CASES, Golden, assert_close
 import dropin_utils as D
 from tiger.data.data_loader import GraphCollator, InteractionData
 from tiger.data.graph import Graph
@@ -23,7 +23,7 @@ cpu = lambda t: t.detach().cpu().numpy()
 def setup(g, dropout=0.1):
     full = InteractionData(g.src, g.dst, g.ts, g.eids, np.zeros_like(g.src), seed=0, eval=True, neg_dst=g.neg)
     graph = Graph.from_data(full, strategy='recent_edges', seed=0, max_node_id=g.N - 1)
-    coll = GraphCollator(graph, g.K, 1, restarter=g.restarter, hist_len=g.hist_len)
+    coll = GraphCollator(graph, g.K, g.n_layers, restarter=g.restarter, hist_len=g.hist_len)
     dl = DataLoader(full, batch_size=g.bs, collate_fn=coll, pin_memory=True)
     model = D.load_golden_weights(D.model_from_golden(g, graph, DEV, dropout=dropout), g)
     return full, graph, coll, dl, model
@@ -64,8 +64,11 @@ def test_graph_from_adjacency_list_equals_from_data():
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES + VAR_CASES)
 def test_dropin_replays_reference_golden(name):
+    """CASES: the default operators (fused kernel route).  VAR_CASES: the non-default variants of SURVEY.md §8(f)3 -
+    n_layers = 2, hit_type vec | count, upd_fn merge, tsfm_fn linear | mlp - whose index / memory operators run the
+    same kernels while the variant-specific dense pieces go through the operator modules."""
     g = Golden(name)
     full, graph, coll, dl, model = setup(g)
     model.eval()
@@ -81,6 +84,9 @@ def test_dropin_replays_reference_golden(name):
             assert np.array_equal(cpu(cg.layers[1][0]), g.b(ib, 'neigh_nids')), what
             assert np.array_equal(cpu(cg.layers[1][1]), g.b(ib, 'neigh_eids')), what
             assert np.array_equal(cpu(cg.layers[1][2]), g.b(ib, 'neigh_ts')), what
+            for depth in range(2, g.n_layers + 1):
+                for j, nm in enumerate(('neigh_nids', 'neigh_eids', 'neigh_ts')):
+                    assert np.array_equal(cpu(cg.layers[depth][j]), g.b(ib, f'l{depth}_{nm}')), what + f'layer {depth} {nm}'
             assert np.array_equal(cg.np_computation_graph_nodes, g.b(ib, 'involved')), what
             assert np.array_equal(cpu(cg.local_index), g.b(ib, 'local_index')), what
             for got, key in zip(cg.hit_data, ('src_hits', 'dst_hits', 'neg_src_hits', 'neg_dst_hits')):

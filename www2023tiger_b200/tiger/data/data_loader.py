@@ -51,8 +51,8 @@ class GraphCollator:
     def __init__(self, graph: Graph, n_neighbors: int, n_layers: int, *, restarter: str = 'seq',
                  hist_len: Optional[int] = None, n_walks: Optional[int] = None,
                  walk_length: Optional[int] = None, alpha: float = 0.0):
-        if n_layers != 1:
-            raise NotImplementedError('the device collator implements n_layers=1 (the reference default)')
+        if n_layers < 1:
+            raise ValueError('n_layers must be >= 1')
         if restarter not in ('seq', 'static'):
             raise NotImplementedError(f"restarter '{restarter}'")
         self.graph = graph
@@ -65,22 +65,31 @@ class GraphCollator:
 
     # the pieces of the reference collator, each usable on its own -------------------------------
     def collate_memory_nodes(self, nids: torch.Tensor, ts64: torch.Tensor, ts_period: int = 0):
-        """data_loader.py:105-131 for n_layers=1.  Device tensors in; returns
-        (layers, (np involved ids, device involved ids), local_index)."""
+        """data_loader.py:105-131.  Device tensors in; returns (layers, (np involved ids, device involved ids),
+        local_index).  layers[n_layers] holds the neighbors of the batch nodes, layers[l - 1] the neighbors of
+        layers[l]'s neighbors queried at THEIR (float32) event times (the reference recurses with the float32 table it
+        just produced, :124-131); every layer marks the involved-node bitmap."""
         dev = self.graph.device
         if self._bitmap is None or self._bitmap.device != dev:
             self._bitmap = torch.zeros(ops.bitmap_words(self.n_nodes), dtype=torch.int32, device=dev)
-        n, k = nids.numel(), self.n_neighbors
-        nn_, ne_, nt_, _ = ops.find_recent(self.graph.csr, nids, ts64, k, ts_period=ts_period, want_dirs=False,
-                                           bitmap=self._bitmap)
-        cap = n * (k + 1)
+        k = self.n_neighbors
+        layers = [None] * (self.n_layers + 1)
+        layers[0] = (nids, None, None)
+        q_n, q_t, period = nids, ts64, ts_period
+        n_queries = 0
+        for depth in range(self.n_layers, 0, -1):
+            nn_, ne_, nt_, _ = ops.find_recent(self.graph.csr, q_n, q_t, k, ts_period=period, want_dirs=False,
+                                               bitmap=self._bitmap)
+            layers[depth] = (nn_, ne_, nt_)
+            n_queries += q_n.numel()
+            q_n, q_t, period = nn_.reshape(-1), nt_.reshape(-1).double(), 0
+        cap = n_queries * (k + 1)
         involved = torch.empty(cap, dtype=torch.int64, device=dev)
         counts = torch.zeros(4, dtype=torch.int32, device=dev)
         local_index = torch.zeros(self.n_nodes, dtype=torch.int64, device=dev)
         ops.compact_involved(self._bitmap, self.n_nodes, involved, counts, local_index=local_index)
         u = int(counts[0])                                   # host sync: the drivers need the ids on the host
         involved = involved[:u]
-        layers = [(nids, None, None), (nn_, ne_, nt_)]
         return layers, (involved.cpu().numpy(), involved), local_index
 
     def collate_restart_data(self, nids: torch.Tensor, ts64: torch.Tensor, ts_period: int = 0):
@@ -119,7 +128,7 @@ class GraphCollator:
         restart_data = self.collate_restart_data(batch_nids[:2 * B], ts64, ts_period=B)
         # hit windows reuse the neighbor rows just computed: rows [0,B) = N(src), [B,2B) = N(dst),
         # [2B,3B) = N(neg), all at the events' times (data_loader.py:69-75)
-        neigh = layers[1][0]
+        neigh = layers[self.n_layers][0]
         n_src, n_dst, n_neg = neigh[:B], neigh[B:2 * B], neigh[2 * B:]
         hit_data = HitData(self.check_in_window(d_src, n_dst), self.check_in_window(d_dst, n_src),
                            self.check_in_window(d_src, n_neg), self.check_in_window(d_neg, n_src))
