@@ -58,7 +58,7 @@ int tiger_csr_build(const int64_t* src, const int64_t* dst, const double* ts, co
                     int32_t* adj_eid, double* adj_ts, uint8_t* adj_flag, void* work, void* stream);
 
 /* a2  Graph.find_before + sample_temporal_neighbor['recent_edges'] + get_history
- * (graph.py:44-53,117-127,150-155).  One warp per query, 32-ary cooperative search for the
+ * (graph.py:44-53,117-127,150-155).  Eight lanes per query (4 queries per warp), 8-ary cooperative search for the
  * strict-'<' cut, right-aligned zero-padded K most recent entries.
  * q_ts has ts_period entries, query i uses q_ts[i % ts_period] (np.tile of the collator).
  * out_dirs, out_ts32 and mark_bitmap may be NULL.  mark_bitmap (ceil(n_nodes/32) words)

@@ -2,7 +2,7 @@
 
 `TigerEngine` owns the device state of TIGE/TIGER (both memories, the last-message store, the
 pending / up-to-date flags) and runs TIGE.contrast_learning (reference tiger/model/tiger.py:174-290)
-as ten kernel launches whose data-dependent sizes (involved U, outdated O, restarted R) stay on
+as a fixed sequence of kernel launches (13 per batch) whose data-dependent sizes (involved U, outdated O, restarted R) stay on
 the device.  `StreamRunner` adds the device neighbor finder in front, captures the sequence in a
 CUDA graph and feeds it from pinned host buffers.
 
@@ -322,6 +322,7 @@ class StreamRunner:
         self.finder_bufs = [engine.finder_buffers(fresh=True) for _ in range(n_slots)]
         self.pq_bufs = [torch.zeros_like(engine.pq) for _ in range(n_slots)]
         self.slot_busy = [False] * n_slots
+        self.check_on_wait = False     # True: wait() also polls the device error word (one more host sync per batch)
         self.slot = 0
         self._lib = _lib.load()
 
@@ -418,7 +419,8 @@ class StreamRunner:
         results become readable after `wait(slot)`."""
         slot = self._next_slot()
         if self.slot_busy[slot]:
-            self.wait(slot)
+            raise RuntimeError(f'staging slot {slot} still holds unread results: call wait(slot) on every slot returned '
+                               f'by submit_host before more than {self.n_slots} batches are in flight')
         self.fill_host(slot, src, dst, neg, ts, eids)
         if not self.pipe:
             e = self.e
@@ -438,6 +440,8 @@ class StreamRunner:
         if self.pipe and self.slot_busy[slot]:
             self._check(self._lib.tiger_pipe_wait(self.pipe, slot, 1), 'pipe_wait')
         self.slot_busy[slot] = False
+        if self.check_on_wait:
+            self.e.check_errors()          # attribute an invariant violation to (at most n_slots batches around) this one
         out = self.h_out[slot]
         B = self.e.B
         return out[:B], out[B:2 * B], out[2 * B]

@@ -22,10 +22,20 @@ def _device(device=None) -> torch.device:
     return torch.device('cuda', torch.cuda.current_device())
 
 
+def _check_strategy(strategy):
+    """The keyword default stays the reference's ('recent_nodes', graph.py:11) so that positional call sites keep
+    working, but only 'recent_edges' - what init_utils passes (init_utils.py:40-42,77-78) - exists on the device:
+    anything else fails here, at construction, not at the first collate call."""
+    if strategy != 'recent_edges':
+        raise NotImplementedError(f"neighbor strategy '{strategy}': only 'recent_edges' is implemented "
+                                  "(pass strategy='recent_edges', the reference CLI default)")
+
+
 class Graph:
     def __init__(self, adj_list, strategy='recent_nodes', seed=None, alpha=0.0, device=None):
         """adj_list[n] = list of (neighbor, eid, ts, flag) of node n, as data2adjlist builds it
         (graph.py:226-241).  The per-node stable sort by time (graph.py:30-36) runs on the device."""
+        _check_strategy(strategy)
         self.strategy = strategy
         self.seed = seed
         self.alpha = alpha
@@ -52,6 +62,7 @@ class Graph:
     @classmethod
     def from_data(cls, data, strategy='recent_nodes', seed=None, max_node_id=None, device=None):
         """Build straight from the interaction stream (reference: data2adjlist + Graph.__init__)."""
+        _check_strategy(strategy)
         self = cls.__new__(cls)
         self.strategy, self.seed, self.alpha = strategy, seed, 0.0
         dev = _device(device)
