@@ -243,11 +243,16 @@ extern "C" int tiger_train_attn_build(const int64_t* center, int64_t n_q, const 
 // One warp per (query, head).  s_j = (q_h * scale) . k_jh, padding (neighbor id 0) -> -inf, rows without any
 // neighbor keep their last slot (and are flagged `empty`: their output is zero-filled downstream), softmax,
 // dropout on the probabilities, o_h = sum_j p'_j v_jh.  P keeps the softmax output, keep_bits the dropout decisions.
+template <int KT>
 __global__ void __launch_bounds__(256)
 train_attn_core_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ Kp, const float* __restrict__ Vp,
                        int64_t ldkv, const int64_t* __restrict__ nn, int64_t n_q, int K, int n_head, int hd,
                        float p_drop, uint32_t seed, float* __restrict__ attn, int64_t ld_attn, float* __restrict__ P,
                        uint32_t* __restrict__ keep_bits, uint8_t* __restrict__ empty) {
+  // KT > 0: K is a compile-time constant, so the per-neighbor loops below unroll without branches and the K dot
+  // products / reductions of one (query, head) overlap instead of forming one dependent chain each
+  constexpr int KU = KT > 0 ? KT : ATT_MAXK;
+  if (KT > 0) K = KT;
   const int lane = lane_id();
   const float scale = sqrtf(1.0f / (float)hd);
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
@@ -257,10 +262,10 @@ train_attn_core_kernel(const float* __restrict__ Q, int64_t ldq, const float* __
     const int64_t i = item / n_head;
     const int h = (int)(item % n_head);
     const float* q = Q + i * ldq + h * hd;
-    float s[ATT_MAXK];
+    float s[KU];
     bool any = false;
 #pragma unroll
-    for (int j = 0; j < ATT_MAXK; ++j) {
+    for (int j = 0; j < KU; ++j) {
       if (j < K) {
         const float* kr = Kp + (i * K + j) * ldkv + h * hd;
         float acc = 0.f;
@@ -278,23 +283,23 @@ train_attn_core_kernel(const float* __restrict__ Q, int64_t ldq, const float* __
       for (int c = lane; c < hd; c += 32) acc = fmaf(q[c] * scale, kr[c], acc);
       acc = warp_sum(acc);
 #pragma unroll
-      for (int j = 0; j < ATT_MAXK; ++j)
+      for (int j = 0; j < KU; ++j)
         if (j == K - 1) s[j] = acc;
     }
     float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < ATT_MAXK; ++j)
+    for (int j = 0; j < KU; ++j)
       if (j < K) m = fmaxf(m, s[j]);
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < ATT_MAXK; ++j)
+    for (int j = 0; j < KU; ++j)
       if (j < K) {
         s[j] = expf(s[j] - m);
         sum += s[j];
       }
     uint32_t bits = 0;
 #pragma unroll
-    for (int j = 0; j < ATT_MAXK; ++j)
+    for (int j = 0; j < KU; ++j)
       if (j < K) {
         s[j] = s[j] / sum;
         if (lane == 0) P[item * K + j] = s[j];
@@ -310,7 +315,7 @@ train_attn_core_kernel(const float* __restrict__ Q, int64_t ldq, const float* __
     for (int c = lane; c < hd; c += 32) {
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < ATT_MAXK; ++j)
+      for (int j = 0; j < KU; ++j)
         if (j < K) acc = fmaf(s[j], Vp[(i * K + j) * ldkv + h * hd + c], acc);
       o[c] = acc;
     }
@@ -328,20 +333,28 @@ extern "C" int tiger_train_attn_core(const float* Q, int64_t ldq, const float* K
   if (n_q == 0) return TIGER_OK;
   int64_t grid = (n_q * n_head + 7) / 8;
   if (grid > 148 * 8) grid = 148 * 8;
-  train_attn_core_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(Q, ldq, Kp, Vp, ldkv, neigh_nids, n_q, k, n_head,
-                                                                       head_dim, p_drop, (uint32_t)seed, attn, ld_attn,
-                                                                       P, keep_bits, empty);
+  auto launch = [&](auto kernel) {
+    kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(Q, ldq, Kp, Vp, ldkv, neigh_nids, n_q, k, n_head, head_dim,
+                                                          p_drop, (uint32_t)seed, attn, ld_attn, P, keep_bits, empty);
+  };
+  if (k == 10) launch(train_attn_core_kernel<10>);
+  else if (k == 5) launch(train_attn_core_kernel<5>);
+  else if (k == 20) launch(train_attn_core_kernel<20>);
+  else launch(train_attn_core_kernel<0>);
   return tiger_launch_status();
 }
 
 // backward of the core: dV_j = p'_j do, dp'_j = do . v_j, dp_j = dp'_j * keep / (1 - p_drop),
 // ds_j = p_j (dp_j - sum_l p_l dp_l), dq = scale * sum_j ds_j k_j, dk_j = scale * ds_j q.
+template <int KT>
 __global__ void __launch_bounds__(256)
 train_attn_core_bwd_kernel(const float* __restrict__ dattn, int64_t ld_attn, const float* __restrict__ Q, int64_t ldq,
                            const float* __restrict__ Kp, const float* __restrict__ Vp, int64_t ldkv,
                            const float* __restrict__ P, const uint32_t* __restrict__ keep_bits, int64_t n_q, int K,
                            int n_head, int hd, float p_drop, float* __restrict__ dQ, float* __restrict__ dKp,
                            float* __restrict__ dVp) {
+  constexpr int KU = KT > 0 ? KT : ATT_MAXK;
+  if (KT > 0) K = KT;
   const int lane = lane_id();
   const float scale = sqrtf(1.0f / (float)hd);
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
@@ -353,10 +366,10 @@ train_attn_core_bwd_kernel(const float* __restrict__ dattn, int64_t ld_attn, con
     const float* go = dattn + i * ld_attn + h * hd;
     const float* q = Q + i * ldq + h * hd;
     const uint32_t bits = keep_bits[item];
-    float p[ATT_MAXK], ds[ATT_MAXK];
+    float p[KU], ds[KU];
     float dot = 0.f;
 #pragma unroll
-    for (int j = 0; j < ATT_MAXK; ++j)
+    for (int j = 0; j < KU; ++j)
       if (j < K) {
         p[j] = P[item * K + j];
         const float m = ((bits >> j) & 1u) ? inv_keep : 0.f;
@@ -374,14 +387,14 @@ train_attn_core_bwd_kernel(const float* __restrict__ dattn, int64_t ld_attn, con
         dot = fmaf(p[j], acc, dot);
       }
 #pragma unroll
-    for (int j = 0; j < ATT_MAXK; ++j)
+    for (int j = 0; j < KU; ++j)
       if (j < K) ds[j] = p[j] * (ds[j] - dot) * scale;
     float* dq = dQ + i * ldq + h * hd;
     for (int c = lane; c < hd; c += 32) {
       float acc = 0.f;
       const float qc = q[c];
 #pragma unroll
-      for (int j = 0; j < ATT_MAXK; ++j)
+      for (int j = 0; j < KU; ++j)
         if (j < K) {
           acc = fmaf(ds[j], Kp[(i * K + j) * ldkv + h * hd + c], acc);
           dKp[(i * K + j) * ldkv + h * hd + c] = ds[j] * qc;
@@ -402,9 +415,14 @@ extern "C" int tiger_train_attn_core_bwd(const float* dattn, int64_t ld_attn, co
   if (n_q == 0) return TIGER_OK;
   int64_t grid = (n_q * n_head + 7) / 8;
   if (grid > 148 * 8) grid = 148 * 8;
-  train_attn_core_bwd_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(dattn, ld_attn, Q, ldq, Kp, Vp, ldkv, P,
-                                                                           keep_bits, n_q, k, n_head, head_dim, p_drop,
-                                                                           dQ, dKp, dVp);
+  auto launch = [&](auto kernel) {
+    kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(dattn, ld_attn, Q, ldq, Kp, Vp, ldkv, P, keep_bits, n_q, k,
+                                                          n_head, head_dim, p_drop, dQ, dKp, dVp);
+  };
+  if (k == 10) launch(train_attn_core_bwd_kernel<10>);
+  else if (k == 5) launch(train_attn_core_bwd_kernel<5>);
+  else if (k == 20) launch(train_attn_core_bwd_kernel<20>);
+  else launch(train_attn_core_bwd_kernel<0>);
   return tiger_launch_status();
 }
 

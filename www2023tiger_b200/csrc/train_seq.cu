@@ -158,97 +158,97 @@ extern "C" int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float*
 }
 
 // ------------------------------------------------------------------------------------------
-// backward: one CTA per node (both heads in turn, so that the token gradient of the value path is written once).
-//   dpbar_j = dxbar_h . x_j + dpsum_h          dX_j  = sum_h pbar_hj dxbar_h        (value path)
-//   dP'_ij  = dpbar_j / L,  dP_ij = dP'_ij keep_ij / (1 - p),  dS_ij = P_ij (dP_ij - sum_l P_il dP_il)
-//   dQ_i = scale sum_j dS_ij K_j,   dK_j = scale sum_i dS_ij Q_i
+// backward, two kernels.
+//   value path (element-wise, one pass over the token gradients):   dX_j = sum_h pbar_hj dxbar_h
+//   score path, one CTA per (node, head):
+//     dpbar_j = dxbar_h . x_j + dpsum_h,  dP'_ij = dpbar_j / L,  dP_ij = dP'_ij keep_ij / (1 - p),
+//     dS_ij = P_ij (dP_ij - sum_l P_il dP_il),  dQ_i = scale sum_j dS_ij K_j,  dK_j = scale sum_i dS_ij Q_i
+//   the two L x L x head_dim products run out of shared memory in column chunks of SPB_CW (Q / K columns staged once,
+//   dS broadcast), so nothing is indexed dynamically in registers (the first version kept 2 x 64 floats per thread
+//   in local memory and ran at 12 % occupancy: 756 us for 281 nodes; profiles/r02_train_kernels.md)
 // ------------------------------------------------------------------------------------------
+__global__ void train_seq_pool_bwd_value_kernel(const float* __restrict__ dxbar, const float* __restrict__ pbar,
+                                                const int32_t* __restrict__ count, int64_t n_cap, int len, int dm,
+                                                int n_head, float* __restrict__ dX) {
+  const int64_t n = seq_rows(count, n_cap);
+  const int64_t total = n * len * dm;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % dm);
+    const int64_t r = e / dm;
+    const int64_t i = r / len;
+    const int j = (int)(r % len);
+    float s = 0.f;
+    for (int h = 0; h < n_head; ++h)
+      s = fmaf(pbar[(i * n_head + h) * len + j], dxbar[(i * n_head + h) * (int64_t)dm + c], s);
+    dX[e] = s;
+  }
+}
+
+#define SPB_CW 32
 __global__ void __launch_bounds__(SP_THREADS)
 train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restrict__ dpsum, const float* __restrict__ x,
                           const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ P,
-                          const float* __restrict__ pbar, const int32_t* __restrict__ count, int64_t n_cap, int len,
-                          int dm, int n_head, float p_drop, uint32_t seed, float* __restrict__ dX,
-                          float* __restrict__ dqk) {
+                          const int32_t* __restrict__ count, int64_t n_cap, int len, int dm, int n_head, float p_drop,
+                          uint32_t seed, float* __restrict__ dqk) {
   __shared__ float ds[SP_MAXL][SP_MAXL + 1];
+  __shared__ float qs[SP_MAXL][SPB_CW + 1];
+  __shared__ float ks[SP_MAXL][SPB_CW + 1];
   __shared__ float dpb[SP_MAXL];
-  __shared__ float pb[4][SP_MAXL];          // pbar of up to 4 heads
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
   const int hd = dm / n_head;
   const float scale = sqrtf(1.0f / (float)hd);
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int n_pairs = len * len;
-  const int64_t n = seq_rows(count, n_cap);
-  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+  const int64_t total = seq_rows(count, n_cap) * n_head;
+  for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const int64_t i = item / n_head;
+    const int h = (int)(item % n_head);
     const float* xrow = x + i * len * (int64_t)dm;
+    const float* gx = dxbar + item * (int64_t)dm;
     __syncthreads();
-    for (int e = tid; e < n_head * len; e += SP_THREADS) pb[e / len][e % len] = pbar[(i * n_head) * len + e];
-    __syncthreads();
-    // value path: dX_j = sum_h pbar_hj dxbar_h
-    for (int c = tid; c < dm; c += SP_THREADS) {
-      float g[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) g[h] = h < n_head ? dxbar[(i * n_head + h) * (int64_t)dm + c] : 0.f;
-      for (int j = 0; j < len; ++j) {
-        float s = 0.f;
-#pragma unroll
-        for (int h = 0; h < 4; ++h)
-          if (h < n_head) s = fmaf(pb[h][j], g[h], s);
-        dX[(i * len + j) * (int64_t)dm + c] = s;
-      }
+    for (int j = warp; j < len; j += SP_THREADS / 32) {
+      float s = 0.f;
+      for (int c = lane; c < dm; c += 32) s = fmaf(gx[c], xrow[(int64_t)j * dm + c], s);
+      s = warp_sum(s);
+      if (lane == 0) dpb[j] = (s + dpsum[item]) / (float)len;
     }
-    for (int h = 0; h < n_head; ++h) {
-      const int64_t item = i * n_head + h;
-      const float* gx = dxbar + item * (int64_t)dm;
-      __syncthreads();
-      for (int j = warp; j < len; j += SP_THREADS / 32) {
-        float s = 0.f;
-        for (int c = lane; c < dm; c += 32) s = fmaf(gx[c], xrow[(int64_t)j * dm + c], s);
-        s = warp_sum(s);
-        if (lane == 0) dpb[j] = (s + dpsum[item]) / (float)len;
+    __syncthreads();
+    const float* Pin = P + item * n_pairs;
+    for (int q = warp; q < len; q += SP_THREADS / 32) {          // one warp per query row
+      float dot = 0.f;
+      for (int c = lane; c < len; c += 32) {
+        const bool keep = seq_keep(seed, 3u, (uint32_t)(item * n_pairs + q * len + c), p_drop);
+        const float dp = keep ? dpb[c] * inv_keep : 0.f;
+        ds[q][c] = dp;
+        dot = fmaf(Pin[q * len + c], dp, dot);
+      }
+      dot = warp_sum(dot);
+      for (int c = lane; c < len; c += 32) ds[q][c] = Pin[q * len + c] * (ds[q][c] - dot) * scale;
+    }
+    const float* qbase = qk + i * len * ld_qk + h * hd;
+    const float* kbase = qbase + dm;
+    float* dqbase = dqk + i * len * ld_qk + h * hd;
+    float* dkbase = dqbase + dm;
+    for (int c0 = 0; c0 < hd; c0 += SPB_CW) {
+      const int cw = (hd - c0) < SPB_CW ? (hd - c0) : SPB_CW;
+      __syncthreads();                                   // ds complete / previous chunk consumed
+      for (int e = tid; e < len * SPB_CW; e += SP_THREADS) {
+        const int j = e / SPB_CW, c = e % SPB_CW;
+        qs[j][c] = c < cw ? qbase[(int64_t)j * ld_qk + c0 + c] : 0.f;
+        ks[j][c] = c < cw ? kbase[(int64_t)j * ld_qk + c0 + c] : 0.f;
       }
       __syncthreads();
-      const float* Pin = P + item * n_pairs;
-      for (int q = warp; q < len; q += SP_THREADS / 32) {          // one warp per query row
-        float dot = 0.f;
-        for (int c = lane; c < len; c += 32) {
-          const bool keep = seq_keep(seed, 3u, (uint32_t)(item * n_pairs + q * len + c), p_drop);
-          const float dp = keep ? dpb[c] * inv_keep : 0.f;
-          const float p = Pin[q * len + c];
-          ds[q][c] = dp;
-          dot = fmaf(p, dp, dot);
-        }
-        dot = warp_sum(dot);
-        for (int c = lane; c < len; c += 32) ds[q][c] = Pin[q * len + c] * (ds[q][c] - dot) * scale;
-      }
-      __syncthreads();
-      const float* qbase = qk + i * len * ld_qk + h * hd;
-      const float* kbase = qbase + dm;
-      float* dqbase = dqk + i * len * ld_qk + h * hd;
-      float* dkbase = dqbase + dm;
-      for (int c = tid; c < hd; c += SP_THREADS) {
-        float qc[SP_MAXL], kc[SP_MAXL];
-#pragma unroll
-        for (int j = 0; j < SP_MAXL; ++j)
-          if (j < len) {
-            qc[j] = qbase[(int64_t)j * ld_qk + c];
-            kc[j] = kbase[(int64_t)j * ld_qk + c];
-          }
-#pragma unroll 1
-        for (int q = 0; q < len; ++q) {
-          float s = 0.f;
-#pragma unroll
-          for (int j = 0; j < SP_MAXL; ++j)
-            if (j < len) s = fmaf(ds[q][j], kc[j], s);
-          dqbase[(int64_t)q * ld_qk + c] = s;
-        }
-#pragma unroll 1
+      // outputs (row r, column c): a warp shares r (dS broadcast) and sweeps 32 consecutive columns
+      for (int o = tid; o < len * SPB_CW; o += SP_THREADS) {
+        const int r = o / SPB_CW, c = o % SPB_CW;
+        if (c >= cw) continue;
+        float sq = 0.f, sk = 0.f;
         for (int j = 0; j < len; ++j) {
-          float s = 0.f;
-#pragma unroll
-          for (int q = 0; q < SP_MAXL; ++q)
-            if (q < len) s = fmaf(ds[q][j], qc[q], s);
-          dkbase[(int64_t)j * ld_qk + c] = s;
+          sq = fmaf(ds[r][j], ks[j][c], sq);             // dQ_r = sum_j dS_rj K_j
+          sk = fmaf(ds[j][r], qs[j][c], sk);             // dK_r = sum_i dS_ir Q_i
         }
+        dqbase[(int64_t)r * ld_qk + c0 + c] = sq;
+        dkbase[(int64_t)r * ld_qk + c0 + c] = sk;
       }
     }
   }
@@ -256,16 +256,21 @@ train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restri
 
 extern "C" int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, const float* x, const float* qk,
                                         int64_t ld_qk, const float* P, const float* pbar, const int32_t* count,
-                                        int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* dX, float* dqk,
-                                        void* stream) {
+                                        int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* dX,
+                                        float* dqk, void* stream) {
   if (dxbar == nullptr || dpsum == nullptr || x == nullptr || qk == nullptr || P == nullptr || pbar == nullptr ||
       dX == nullptr || dqk == nullptr || n < 0 || len <= 0 || len > SP_MAXL || d_model <= 0 || n_head <= 0 ||
-      n_head > 4 || d_model % n_head != 0 || ld_qk < 2 * (int64_t)d_model)
+      d_model % n_head != 0 || ld_qk < 2 * (int64_t)d_model)
     return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
-  int64_t grid = n < 148 * 4 ? n : 148 * 4;
-  train_seq_pool_bwd_kernel<<<(unsigned)grid, SP_THREADS, 0, as_stream(stream)>>>(
-      dxbar, dpsum, x, qk, ld_qk, P, pbar, count, n, len, d_model, n_head, p_drop, (uint32_t)seed, dX, dqk);
+  cudaStream_t st = as_stream(stream);
+  int64_t gv = (n * len * d_model + 255) / 256;
+  if (gv > 148 * 16) gv = 148 * 16;
+  train_seq_pool_bwd_value_kernel<<<(unsigned)gv, 256, 0, st>>>(dxbar, pbar, count, n, len, d_model, n_head, dX);
+  int64_t grid = n * n_head;
+  if (grid > 148 * 6) grid = 148 * 6;
+  train_seq_pool_bwd_kernel<<<(unsigned)grid, SP_THREADS, 0, st>>>(dxbar, dpsum, x, qk, ld_qk, P, count, n, len, d_model,
+                                                                   n_head, p_drop, (uint32_t)seed, dqk);
   return tiger_launch_status();
 }
 
