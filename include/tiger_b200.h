@@ -513,6 +513,18 @@ int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev
 int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_start, const int32_t* seg_group, int32_t* seg_step, float* seg_bc, int n_seg, float* gates, int64_t max_seg, float lr, float beta1, float beta2, float eps, float grad_scale, int zero_grad, void* stream);
 
 
+/* Large products of the training step with BOTH operands pre-split into tf32 head / tail planes and pre-tiled as the
+ * shared-memory image of every pipeline stage (csrc/gemm_pp.cu): tiger_gemm_pp_pack converts an operand once
+ * (row-major, or transposed = element (row, k) at src[k*ld + row]; rows / reduction length optionally bounded by
+ * *row_count / *k_count times per_count), tiger_sgemm_pp multiplies two packs - TMA bulk copies feed the tensor cores,
+ * no thread touches operand data.  Same semantics as tiger_sgemm_ex (accumulate: atomic adds, K split over k_parts). */
+int64_t tiger_gemm_pp_pack_bytes(int64_t rows, int64_t k_dim);
+int tiger_gemm_pp_pack(const float* src, int64_t ld, int trans, int64_t rows, int64_t k_dim, const int32_t* row_count,
+                       const int32_t* k_count, int64_t per_count, float* out, void* stream);
+int tiger_sgemm_pp(const float* apack, const float* wpack, const float* bias, float* C, int64_t ldc, int64_t m_rows,
+                   int n_cols, int64_t k_dim, const int32_t* m_count, const int32_t* k_count, int64_t per_count,
+                   float alpha, int relu, int accumulate, int k_parts, void* stream);
+
 /* Seq-restarter training step (csrc/train_seq.cu): SeqRestarter.forward under autograd (restarters.py:51-114 as
  * called from tiger.py:574-590) - L x L self-attention per (node, head) with dropout, folded through the mean over
  * positions (exact by linearity), forward and backward; value-bias term, token gradients (anony_emb, TimeEncode),

@@ -562,3 +562,51 @@ def test_sgemm_ex_mn_major_equals_scalar_transposed_path(m, n, k, monkeypatch):
     out = torch.empty(600, n, device='cuda')
     ops.sgemm_ex(dY, Wt, out, m=600, n=n, k=dY.shape[1], trans_w=True)
     assert_close(out.cpu().numpy(), (dY.double() @ Wt.double()).cpu().numpy(), 3e-6, 'dgrad transposed W')
+
+
+# ------------------------------------------------------------------ pre-packed TMA-fed product (large GEMMs)
+@pytest.mark.parametrize('m,n,k,ta,tw,acc', [
+    (11240, 1720, 860, False, False, False),     # seq restarter q/k in-projection
+    (11240, 860, 1720, False, True, False),      # its input gradient
+    (1720, 860, 11240, True, True, True),        # its weight gradient
+    (6000, 344, 516, False, False, False),       # attention k projection
+    (344, 516, 6000, True, True, True),          # attention weight gradient
+    (300, 130, 70, False, False, False),         # ragged edges, small
+])
+def test_sgemm_pp_matches_float64(m, n, k, ta, tw, acc, monkeypatch):
+    monkeypatch.setattr(ops, 'BIG_GEMM_FLOPS', 0.0)
+    g = torch.Generator(device='cuda').manual_seed(m + n)
+    A = torch.randn((k, m) if ta else (m, k), device='cuda', generator=g)
+    W = torch.randn((k, n) if tw else (n, k), device='cuda', generator=g)
+    opA, opW = (A.t() if ta else A).double(), (W.t() if tw else W).double()
+    if acc:
+        out = torch.randn(m, n, device='cuda', generator=g)
+        want = out.double() + 0.5 * (opA @ opW.t())
+        ops.sgemm_big(A, W, out, m=m, n=n, k=k, trans_a=ta, trans_w=tw, accumulate=True, k_parts=max(1, k // 256), alpha=0.5)
+    else:
+        bias = torch.randn(n, device='cuda', generator=g)
+        out = torch.empty(m, n, device='cuda')
+        want = torch.relu(opA @ opW.t() + bias.double())
+        ops.sgemm_big(A, W, out, m=m, n=n, k=k, trans_a=ta, trans_w=tw, bias=bias, relu=True)
+    assert_close(out.cpu().numpy(), want.cpu().numpy(), 3e-6, f'sgemm_pp {m}x{n}x{k}')
+
+
+def test_sgemm_pp_device_counts(monkeypatch):
+    """Row count (forward / input gradient) and reduction length (weight gradient) from device memory."""
+    monkeypatch.setattr(ops, 'BIG_GEMM_FLOPS', 0.0)
+    g = torch.Generator(device='cuda').manual_seed(9)
+    cap, L, rows, kdim, n = 400, 40, 281, 860, 1720
+    X = torch.randn(cap * L, kdim, device='cuda', generator=g)
+    Wt = torch.randn(n, kdim, device='cuda', generator=g)
+    cnt = torch.tensor([rows], dtype=torch.int32, device='cuda')
+    out = torch.zeros(cap * L, n, device='cuda')
+    ops.sgemm_big(X, Wt, out, m=cap * L, n=n, k=kdim, m_count=cnt, rows_per_count=L)
+    want = X[:rows * L].double() @ Wt.double().t()
+    assert_close(out[:rows * L].cpu().numpy(), want.cpu().numpy(), 3e-6, 'pp forward with row count')
+    assert float(out[rows * L:].abs().max()) == 0.0
+    dY = torch.randn(cap * L, n, device='cuda', generator=g)
+    dW = torch.zeros(n, kdim, device='cuda')
+    ops.sgemm_big(dY, X, dW, m=n, n=kdim, k=cap * L, trans_a=True, trans_w=True, accumulate=True, k_parts=44, k_count=cnt,
+                  rows_per_count=L)
+    want = dY[:rows * L].double().t() @ X[:rows * L].double()
+    assert_close(dW.cpu().numpy(), want.cpu().numpy(), 3e-6, 'pp weight gradient with reduction count')

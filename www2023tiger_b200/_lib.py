@@ -86,6 +86,9 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_train_seq_tokens_bwd': 'pplippiipppppp',
     'tiger_train_dropout': 'ppllfiip',
     'tiger_train_axpy': 'pppllfp',
+    'tiger_gemm_pp_pack_bytes': 'll',
+    'tiger_gemm_pp_pack': 'plillpplpp',
+    'tiger_sgemm_pp': 'ppppllilpplfiiip',
     'tiger_sgemm_ex': 'pli' + 'pli' + 'ppl' + 'lil' + 'ppl' + 'fiii' + 'p',
     'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_gemm_pick_bn': 'lii',

@@ -461,6 +461,46 @@ def sgemm_ex(a: Tensor, w: Tensor, out: Tensor, *, m: int, n: int, k: int, trans
     return out
 
 
+class PPScratch:
+    """Two growing scratch buffers for the packed operands of sgemm_big (stream-ordered reuse: a product is always
+    launched right behind its two packs on the same stream)."""
+
+    def __init__(self):
+        self.bufs = [None, None]
+
+    def get(self, which: int, nbytes: int, device) -> Tensor:
+        b = self.bufs[which]
+        if b is None or b.numel() * 4 < nbytes or b.device != device:
+            b = self.bufs[which] = torch.empty((nbytes + 3) // 4, dtype=f32, device=device)
+        return b
+
+
+_pp_scratch = PPScratch()
+BIG_GEMM_FLOPS = float(__import__('os').environ.get('TIGER_BIG_GEMM_FLOPS', 1.5e9))   # products above this many flops (by launch capacity) go through the pre-packed TMA-fed kernel
+
+
+def sgemm_big(a: Tensor, w: Tensor, out: Tensor, *, m: int, n: int, k: int, trans_a: bool = False,
+              trans_w: bool = False, bias: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0,
+              accumulate: bool = False, k_parts: int = 1, m_count: Optional[Tensor] = None,
+              k_count: Optional[Tensor] = None, rows_per_count: int = 1) -> Tensor:
+    """sgemm_ex for large products: both operands are converted once (tiger_gemm_pp_pack: tf32 head / tail planes in
+    stage-image order) and multiplied by the TMA-fed kernel (tiger_sgemm_pp).  Small products (where the two
+    conversion passes would cost more than they save) fall through to sgemm_ex."""
+    if 2.0 * m * n * k < BIG_GEMM_FLOPS:
+        return sgemm_ex(a, w, out, m=m, n=n, k=k, trans_a=trans_a, trans_w=trans_w, bias=bias, relu=relu, alpha=alpha,
+                        accumulate=accumulate, k_parts=k_parts, m_count=m_count, k_count=k_count,
+                        rows_per_count=rows_per_count)
+    check_cuda_strided(a, w, out)
+    lib = _lib.load()
+    ap = _pp_scratch.get(0, lib.tiger_gemm_pp_pack_bytes(m, k), a.device)
+    wp = _pp_scratch.get(1, lib.tiger_gemm_pp_pack_bytes(n, k), a.device)
+    call('tiger_gemm_pp_pack', ptr(a), a.stride(0), int(trans_a), m, k, ptr(m_count), ptr(k_count), rows_per_count, ptr(ap))
+    call('tiger_gemm_pp_pack', ptr(w), w.stride(0), int(trans_w), n, k, None, ptr(k_count), rows_per_count, ptr(wp))
+    call('tiger_sgemm_pp', ptr(ap), ptr(wp), ptr(bias), ptr(out), out.stride(0), m, n, k, ptr(m_count), ptr(k_count),
+         rows_per_count, float(alpha), int(relu), int(accumulate), k_parts)
+    return out
+
+
 class WeightPack:
     """tf32 head / tail pack of a weight [N, K] for the tensor-core GEMM (tiger_gemm_pack_weight)."""
 

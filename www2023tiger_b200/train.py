@@ -111,7 +111,7 @@ def _param_group(name: str) -> int:
 
 
 def _linear_fwd(x, w, b, out, *, m, relu=False, m_count=None, per=1):
-    ops.sgemm_ex(x, w, out, m=m, n=w.shape[0], k=w.shape[1], bias=b, relu=relu, m_count=m_count, rows_per_count=per)
+    ops.sgemm_big(x, w, out, m=m, n=w.shape[0], k=w.shape[1], bias=b, relu=relu, m_count=m_count, rows_per_count=per)
 
 
 def _linear_bwd(dy, x, w, gw, gb, dx, *, m, k_parts=None, count=None, per=1, accumulate_dx=False):
@@ -120,13 +120,13 @@ def _linear_bwd(dy, x, w, gw, gb, dx, *, m, k_parts=None, count=None, per=1, acc
     # K split of the weight gradient: <= 256 reduction steps per CTA (accumulator truncation grows with the length)
     k_parts = max(1, min(128, (m + 255) // 256))
     if gw is not None:
-        ops.sgemm_ex(dy, x, gw, m=n, n=k, k=m, trans_a=True, trans_w=True, accumulate=True, k_parts=k_parts,
-                     k_count=count, rows_per_count=per)
+        ops.sgemm_big(dy, x, gw, m=n, n=k, k=m, trans_a=True, trans_w=True, accumulate=True, k_parts=k_parts,
+                      k_count=count, rows_per_count=per)
     if gb is not None:
         call('tiger_train_colsum', ptr(dy), dy.stride(0), m, ptr(count), per, n, 1.0, ptr(gb))
     if dx is not None:
-        ops.sgemm_ex(dy, w, dx, m=m, n=k, k=n, trans_w=True, m_count=count, rows_per_count=per,
-                     accumulate=accumulate_dx)
+        ops.sgemm_big(dy, w, dx, m=m, n=k, k=n, trans_w=True, m_count=count, rows_per_count=per,
+                      accumulate=accumulate_dx)
 
 
 class NativeTrainer:

@@ -64,8 +64,8 @@ class SeqRestarterTrainer:
              ptr(self.mask), ptr(self.prev_ts))
         in_w, in_b = P[N['in_w']], P[N['in_b']]
         mc = dict(m_count=count)
-        ops.sgemm_ex(self.X, in_w[:2 * dm], self.QK, m=n * L, n=2 * dm, k=dm, bias=in_b[:2 * dm], m_count=count,
-                     rows_per_count=L)
+        ops.sgemm_big(self.X, in_w[:2 * dm], self.QK, m=n * L, n=2 * dm, k=dm, bias=in_b[:2 * dm], m_count=count,
+                      rows_per_count=L)
         call('tiger_train_seq_pool', ptr(self.QK), 2 * dm, ptr(self.X), ptr(self.mask), ptr(count), n, L, dm, H, p, seed,
              ptr(self.P), ptr(self.pbar), ptr(self.psum), ptr(self.xbar))
         for h in range(H):
@@ -126,10 +126,10 @@ class SeqRestarterTrainer:
         # attention probabilities -> q / k, value path -> tokens
         call('tiger_train_seq_pool_bwd', ptr(self.dxbar), ptr(self.dpsum), ptr(self.X), ptr(self.QK), 2 * dm, ptr(self.P),
              ptr(self.pbar), ptr(count), n, L, dm, H, p, seed, ptr(self.dX), ptr(self.dQK))
-        ops.sgemm_ex(self.dQK, self.X, g_in_w[:2 * dm], m=2 * dm, n=dm, k=n * L, trans_a=True, trans_w=True,
-                     accumulate=True, k_parts=_parts(n * L), k_count=count, rows_per_count=L)
+        ops.sgemm_big(self.dQK, self.X, g_in_w[:2 * dm], m=2 * dm, n=dm, k=n * L, trans_a=True, trans_w=True,
+                      accumulate=True, k_parts=_parts(n * L), k_count=count, rows_per_count=L)
         colsum(self.dQK, 2 * dm, g_in_b[:2 * dm], rows=n * L, per=L)
-        ops.sgemm_ex(self.dQK, in_w[:2 * dm], self.dX, m=n * L, n=dm, k=2 * dm, trans_w=True, accumulate=True,
-                     m_count=count, rows_per_count=L)
+        ops.sgemm_big(self.dQK, in_w[:2 * dm], self.dX, m=n * L, n=dm, k=2 * dm, trans_w=True, accumulate=True,
+                      m_count=count, rows_per_count=L)
         call('tiger_train_seq_tokens_bwd', ptr(self.dX), ptr(count), n, L, ptr(ctx['an']), ptr(ctx['ht']), d, de,
              ptr(P[N['tw']]), ptr(P[N['tb']]), ptr(G[N['an']]), ptr(G[N['tw']]), ptr(G[N['tb']]))
