@@ -41,17 +41,18 @@ __global__ void gemm_pp_pack_kernel(const float* __restrict__ src, int64_t ld, i
     const int64_t c = (int64_t)(*k_count) * per_count;
     k_eff = c < k_dim ? c : k_dim;
   }
-  const int64_t tiles = (rows + PP_BM - 1) / PP_BM;
-  const int64_t total = tiles * n_kb * UMMA_KCH * PP_BM;
+  // only the tiles / k-blocks inside the device-side bounds are written: tiger_sgemm_pp applies the same bounds, and a
+  // launch sized for a capacity (6,600 restart rows x 40 tokens) must not sweep it (155 us at first)
+  const int64_t tiles = (rows_eff + PP_BM - 1) / PP_BM;
+  const int64_t kb_eff = (k_eff + UMMA_BK - 1) / UMMA_BK;
+  const int64_t total = tiles * kb_eff * UMMA_KCH * PP_BM;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i % PP_BM);
     const int kc = (int)((i / PP_BM) % UMMA_KCH);
-    const int64_t kb = (i / (PP_BM * UMMA_KCH)) % n_kb;
-    const int64_t t = i / (PP_BM * UMMA_KCH * n_kb);
+    const int64_t kb = (i / (PP_BM * UMMA_KCH)) % kb_eff;
+    const int64_t t = i / (PP_BM * UMMA_KCH * kb_eff);
     const int64_t row = t * PP_BM + r;
     const int64_t k = kb * UMMA_BK + kc * 4;
-    // tiles / k-blocks entirely beyond the device-side bounds are never read by tiger_sgemm_pp (same bounds there)
-    if (t * PP_BM >= rows_eff || kb * UMMA_BK >= k_eff) continue;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < rows_eff && k < k_eff) {
       if (!trans) {
@@ -301,13 +302,21 @@ extern "C" int tiger_sgemm_pp(const float* apack, const float* wpack, const floa
   g.alpha = alpha; g.relu = relu; g.accumulate = accumulate ? 1 : 0;
   g.stages = PP_MAX_STAGES;
   g.vec_c = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
+  const int64_t tiles = ((m_rows + PP_BM - 1) / PP_BM) * ((n_cols + PP_BN - 1) / PP_BN);
   int64_t parts = 1;
   if (accumulate) {
-    parts = k_parts < g.n_kb_total ? k_parts : g.n_kb_total;
+    // K split: enough CTAs for about two waves, at most ~2048 reduction steps per accumulator set (the tensor core
+    // truncates when it adds into its fp32 accumulator), but no more - every part adds its whole tile with atomics
+    // (98 tiles x 63 parts of the seq restarter's weight gradient were 93 M atomic adds: 514 us)
+    int64_t want = (2 * (int64_t)sms + tiles - 1) / tiles;
+    const int64_t by_len = (k_dim + 2047) / 2048;
+    want = want > by_len ? want : by_len;
+    want = want < k_parts ? want : k_parts;
+    parts = want < g.n_kb_total ? want : g.n_kb_total;
+    if (parts < 1) parts = 1;
     g.kblk_per_part = (int)((g.n_kb_total + parts - 1) / parts);
     parts = (g.n_kb_total + g.kblk_per_part - 1) / g.kblk_per_part;
   }
-  const int64_t tiles = ((m_rows + PP_BM - 1) / PP_BM) * ((n_cols + PP_BN - 1) / PP_BN);
   dim3 grid((unsigned)(tiles < sms ? tiles : sms), (unsigned)parts);
   gemm_pp_kernel<<<grid, PP_THREADS, (size_t)g.stages * 2 * PP_STAGE_FLOATS * 4 + 256, as_stream(stream)>>>(g);
   return tiger_launch_status();
