@@ -40,14 +40,19 @@ __device__ __forceinline__ int64_t seq_rows(const int32_t* count, int64_t n, int
 // ------------------------------------------------------------------------------------------
 // forward: per (node, head) L x L scores, key-padding mask, softmax, dropout, mean over the query positions,
 // pooled tokens.  Keeps P (softmax output) [n, H, L, L], pbar [n, H, L], psum [n, H].
+// Scores: the head's q / k columns are staged in chunks of 32 columns, TRANSPOSED ([column][position]), and every
+// thread owns a 2 x 4 block of (query, key) pairs: per column one 8-byte and one 16-byte shared-memory load feed
+// 8 FMAs (the first version read two scalars per FMA and was bound by the shared-memory pipe: 207 us for 562
+// items, profiles/r02_train_kernels.md).
 // ------------------------------------------------------------------------------------------
+#define SP_LP 68      // padded positions per staged column: multiple of 4 (vector loads), 68 % 32 = 4 spreads the stores
 __global__ void __launch_bounds__(SP_THREADS)
 train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ x,
                       const uint8_t* __restrict__ mask, const int32_t* __restrict__ count, int64_t n, int len, int dm,
-                      int n_head, float p_drop, uint32_t seed, float* __restrict__ P, float* __restrict__ pbar_out, float* __restrict__ psum_out,
-                      float* __restrict__ xbar) {
-  __shared__ float qs[SP_MAXL][SP_CW + 1];
-  __shared__ float ks[SP_MAXL][SP_CW + 1];
+                      int n_head, float p_drop, uint32_t seed, float* __restrict__ P, float* __restrict__ pbar_out,
+                      float* __restrict__ psum_out, float* __restrict__ xbar) {
+  __shared__ __align__(16) float qsT[SP_CW][SP_LP];
+  __shared__ __align__(16) float ksT[SP_CW][SP_LP];
   __shared__ float sc[SP_MAXL][SP_MAXL + 1];
   __shared__ float pbar[SP_MAXL];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
@@ -55,15 +60,22 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
   const float scale = sqrtf(1.0f / (float)hd);
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int n_pairs = len * len;
+  const int q_tiles = (len + 1) / 2, k_tiles = (len + 3) / 4, n_tiles = q_tiles * k_tiles;   // <= 32 * 16
   const int64_t total = seq_rows(count, n) * n_head;
+  for (int e = tid; e < SP_CW * SP_LP; e += SP_THREADS) {       // the padding positions stay zero
+    (&qsT[0][0])[e] = 0.f;
+    (&ksT[0][0])[e] = 0.f;
+  }
   for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
     const int64_t i = item / n_head;
     const int h = (int)(item % n_head);
     const float* qbase = qk + i * len * ld_qk + h * hd;
     const float* kbase = qbase + dm;
-    float acc[SP_MAXP];
+    float acc[2][8];
 #pragma unroll
-    for (int r = 0; r < SP_MAXP; ++r) acc[r] = 0.f;
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[t][r] = 0.f;
     for (int c0 = 0; c0 < hd; c0 += SP_CW) {
       const int cw = (hd - c0) < SP_CW ? (hd - c0) : SP_CW;
       __syncthreads();
@@ -71,32 +83,45 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
         const int j = e / SP_CW, c = e % SP_CW;
         float qv = 0.f, kv = 0.f;
         if (c < cw) {
-          qv = qbase[(int64_t)j * ld_qk + c0 + c] * scale;
+          qv = qbase[(int64_t)j * ld_qk + c0 + c] * scale;       // torch scales q before q.k^T
           kv = kbase[(int64_t)j * ld_qk + c0 + c];
         }
-        qs[j][c] = qv;
-        ks[j][c] = kv;
+        qsT[c][j] = qv;
+        ksT[c][j] = kv;
       }
       __syncthreads();
 #pragma unroll
-      for (int r = 0; r < SP_MAXP; ++r) {
-        const int p = tid + r * SP_THREADS;
-        if (p < n_pairs) {
-          const int j = p / len, i2 = p % len;
-          float s = acc[r];
+      for (int t = 0; t < 2; ++t) {
+        const int tile = tid + t * SP_THREADS;
+        if (tile < n_tiles) {
+          const int qt = tile / k_tiles, kt = tile % k_tiles;
 #pragma unroll 8
-          for (int c = 0; c < SP_CW; ++c) s = fmaf(qs[j][c], ks[i2][c], s);
-          acc[r] = s;
+          for (int c = 0; c < SP_CW; ++c) {
+            const float2 q2 = *reinterpret_cast<const float2*>(&qsT[c][2 * qt]);
+            const float4 k4 = *reinterpret_cast<const float4*>(&ksT[c][4 * kt]);
+            acc[t][0] = fmaf(q2.x, k4.x, acc[t][0]);
+            acc[t][1] = fmaf(q2.x, k4.y, acc[t][1]);
+            acc[t][2] = fmaf(q2.x, k4.z, acc[t][2]);
+            acc[t][3] = fmaf(q2.x, k4.w, acc[t][3]);
+            acc[t][4] = fmaf(q2.y, k4.x, acc[t][4]);
+            acc[t][5] = fmaf(q2.y, k4.y, acc[t][5]);
+            acc[t][6] = fmaf(q2.y, k4.z, acc[t][6]);
+            acc[t][7] = fmaf(q2.y, k4.w, acc[t][7]);
+          }
         }
       }
     }
     const uint8_t* mrow = mask + i * len;
 #pragma unroll
-    for (int r = 0; r < SP_MAXP; ++r) {
-      const int p = tid + r * SP_THREADS;
-      if (p < n_pairs) {
-        const int j = p / len, i2 = p % len;
-        sc[j][i2] = mrow[i2] ? -INFINITY : acc[r];
+    for (int t = 0; t < 2; ++t) {
+      const int tile = tid + t * SP_THREADS;
+      if (tile < n_tiles) {
+        const int qt = tile / k_tiles, kt = tile % k_tiles;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int q = 2 * qt + (r >> 2), k = 4 * kt + (r & 3);
+          if (q < len && k < len) sc[q][k] = mrow[k] ? -INFINITY : acc[t][r];
+        }
       }
     }
     __syncthreads();
@@ -143,15 +168,15 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
 }
 
 extern "C" int tiger_train_seq_pool(const float* qk, int64_t ld_qk, const float* x, const uint8_t* mask,
-                                    const int32_t* count, int64_t n, int len, int d_model, int n_head, float p_drop, int seed, float* P, float* pbar,
-                                    float* psum, float* xbar, void* stream) {
+                                    const int32_t* count, int64_t n, int len, int d_model, int n_head, float p_drop,
+                                    int seed, float* P, float* pbar, float* psum, float* xbar, void* stream) {
   if (qk == nullptr || x == nullptr || mask == nullptr || P == nullptr || pbar == nullptr || psum == nullptr ||
       xbar == nullptr || n < 0 || len <= 0 || len > SP_MAXL || d_model <= 0 || n_head <= 0 || d_model % n_head != 0 ||
       ld_qk < 2 * (int64_t)d_model || p_drop < 0.f || p_drop >= 1.f)
     return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
   int64_t grid = n * n_head;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 6) grid = 148 * 6;
   train_seq_pool_kernel<<<(unsigned)grid, SP_THREADS, 0, as_stream(stream)>>>(
       qk, ld_qk, x, mask, count, n, len, d_model, n_head, p_drop, (uint32_t)seed, P, pbar, psum, xbar);
   return tiger_launch_status();
@@ -185,21 +210,29 @@ __global__ void train_seq_pool_bwd_value_kernel(const float* __restrict__ dxbar,
 }
 
 #define SPB_CW 32
+// shared memory (dynamic): dS [L][LP] and its transpose [L][LP] (LP = L rounded up to 4, + 4), q / k column chunks
+// [L][SPB_CW].  Every thread owns a 4 x 2 block of (row, column) outputs of BOTH products: per reduction step two
+// 16-byte loads of dS / dS^T and two 8-byte loads of k / q feed 16 FMAs.
 __global__ void __launch_bounds__(SP_THREADS)
 train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restrict__ dpsum, const float* __restrict__ x,
                           const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ P,
                           const int32_t* __restrict__ count, int64_t n_cap, int len, int dm, int n_head, float p_drop,
                           uint32_t seed, float* __restrict__ dqk) {
-  __shared__ float ds[SP_MAXL][SP_MAXL + 1];
-  __shared__ float qs[SP_MAXL][SPB_CW + 1];
-  __shared__ float ks[SP_MAXL][SPB_CW + 1];
-  __shared__ float dpb[SP_MAXL];
+  extern __shared__ __align__(16) float spb_smem[];
+  const int LP = ((len + 3) & ~3) + 4;
+  float* ds = spb_smem;                    // ds[i * LP + r]  = dS[i][r]
+  float* dsT = ds + len * LP;              // dsT[j * LP + r] = dS[r][j]
+  float* qs = dsT + len * LP;              // qs[j * SPB_CW + c]
+  float* ks = qs + len * SPB_CW;
+  float* dpb = ks + len * SPB_CW;          // [len]
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id_in_block();
   const int hd = dm / n_head;
   const float scale = sqrtf(1.0f / (float)hd);
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int n_pairs = len * len;
+  const int r_tiles = (len + 3) / 4, c_tiles = SPB_CW / 2;      // <= 16 x 16 thread tiles
   const int64_t total = seq_rows(count, n_cap) * n_head;
+  for (int e = tid; e < 2 * len * LP; e += SP_THREADS) ds[e] = 0.f;      // padding columns stay zero
   for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
     const int64_t i = item / n_head;
     const int h = (int)(item % n_head);
@@ -219,11 +252,15 @@ train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restri
       for (int c = lane; c < len; c += 32) {
         const bool keep = seq_keep(seed, 3u, (uint32_t)(item * n_pairs + q * len + c), p_drop);
         const float dp = keep ? dpb[c] * inv_keep : 0.f;
-        ds[q][c] = dp;
+        ds[q * LP + c] = dp;
         dot = fmaf(Pin[q * len + c], dp, dot);
       }
       dot = warp_sum(dot);
-      for (int c = lane; c < len; c += 32) ds[q][c] = Pin[q * len + c] * (ds[q][c] - dot) * scale;
+      for (int c = lane; c < len; c += 32) {
+        const float v = Pin[q * len + c] * (ds[q * LP + c] - dot) * scale;
+        ds[q * LP + c] = v;
+        dsT[c * LP + q] = v;
+      }
     }
     const float* qbase = qk + i * len * ld_qk + h * hd;
     const float* kbase = qbase + dm;
@@ -231,24 +268,40 @@ train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restri
     float* dkbase = dqbase + dm;
     for (int c0 = 0; c0 < hd; c0 += SPB_CW) {
       const int cw = (hd - c0) < SPB_CW ? (hd - c0) : SPB_CW;
-      __syncthreads();                                   // ds complete / previous chunk consumed
+      __syncthreads();                                   // dS complete / previous chunk consumed
       for (int e = tid; e < len * SPB_CW; e += SP_THREADS) {
         const int j = e / SPB_CW, c = e % SPB_CW;
-        qs[j][c] = c < cw ? qbase[(int64_t)j * ld_qk + c0 + c] : 0.f;
-        ks[j][c] = c < cw ? kbase[(int64_t)j * ld_qk + c0 + c] : 0.f;
+        qs[e] = c < cw ? qbase[(int64_t)j * ld_qk + c0 + c] : 0.f;
+        ks[e] = c < cw ? kbase[(int64_t)j * ld_qk + c0 + c] : 0.f;
       }
       __syncthreads();
-      // outputs (row r, column c): a warp shares r (dS broadcast) and sweeps 32 consecutive columns
-      for (int o = tid; o < len * SPB_CW; o += SP_THREADS) {
-        const int r = o / SPB_CW, c = o % SPB_CW;
-        if (c >= cw) continue;
-        float sq = 0.f, sk = 0.f;
+      if (tid < r_tiles * c_tiles) {
+        const int rt = tid / c_tiles, ct = tid % c_tiles;
+        float aq[8], ak[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) aq[e] = ak[e] = 0.f;
         for (int j = 0; j < len; ++j) {
-          sq = fmaf(ds[r][j], ks[j][c], sq);             // dQ_r = sum_j dS_rj K_j
-          sk = fmaf(ds[j][r], qs[j][c], sk);             // dK_r = sum_i dS_ir Q_i
+          const float4 sT = *reinterpret_cast<const float4*>(dsT + j * LP + 4 * rt);   // dS[r0..r0+3][j]
+          const float4 sR = *reinterpret_cast<const float4*>(ds + j * LP + 4 * rt);    // dS[j][r0..r0+3]
+          const float2 k2 = *reinterpret_cast<const float2*>(ks + j * SPB_CW + 2 * ct);
+          const float2 q2 = *reinterpret_cast<const float2*>(qs + j * SPB_CW + 2 * ct);
+          aq[0] = fmaf(sT.x, k2.x, aq[0]); aq[1] = fmaf(sT.x, k2.y, aq[1]);
+          aq[2] = fmaf(sT.y, k2.x, aq[2]); aq[3] = fmaf(sT.y, k2.y, aq[3]);
+          aq[4] = fmaf(sT.z, k2.x, aq[4]); aq[5] = fmaf(sT.z, k2.y, aq[5]);
+          aq[6] = fmaf(sT.w, k2.x, aq[6]); aq[7] = fmaf(sT.w, k2.y, aq[7]);
+          ak[0] = fmaf(sR.x, q2.x, ak[0]); ak[1] = fmaf(sR.x, q2.y, ak[1]);
+          ak[2] = fmaf(sR.y, q2.x, ak[2]); ak[3] = fmaf(sR.y, q2.y, ak[3]);
+          ak[4] = fmaf(sR.z, q2.x, ak[4]); ak[5] = fmaf(sR.z, q2.y, ak[5]);
+          ak[6] = fmaf(sR.w, q2.x, ak[6]); ak[7] = fmaf(sR.w, q2.y, ak[7]);
         }
-        dqbase[(int64_t)r * ld_qk + c0 + c] = sq;
-        dkbase[(int64_t)r * ld_qk + c0 + c] = sk;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int r = 4 * rt + (e >> 1), c = 2 * ct + (e & 1);
+          if (r < len && c < cw) {
+            dqbase[(int64_t)r * ld_qk + c0 + c] = aq[e];       // dQ_r = sum_j dS_rj K_j
+            dkbase[(int64_t)r * ld_qk + c0 + c] = ak[e];       // dK_r = sum_i dS_ir Q_i
+          }
+        }
       }
     }
   }
@@ -269,8 +322,16 @@ extern "C" int tiger_train_seq_pool_bwd(const float* dxbar, const float* dpsum, 
   train_seq_pool_bwd_value_kernel<<<(unsigned)gv, 256, 0, st>>>(dxbar, pbar, count, n, len, d_model, n_head, dX);
   int64_t grid = n * n_head;
   if (grid > 148 * 6) grid = 148 * 6;
-  train_seq_pool_bwd_kernel<<<(unsigned)grid, SP_THREADS, 0, st>>>(dxbar, dpsum, x, qk, ld_qk, P, count, n, len, d_model,
-                                                                   n_head, p_drop, (uint32_t)seed, dqk);
+  const int lp = ((len + 3) & ~3) + 4;
+  const size_t smem = (size_t)(2 * len * lp + 2 * len * SPB_CW + len) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(train_seq_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024) != cudaSuccess)
+      return TIGER_ECUDA;
+    attr_set = true;
+  }
+  train_seq_pool_bwd_kernel<<<(unsigned)grid, SP_THREADS, smem, st>>>(dxbar, dpsum, x, qk, ld_qk, P, count, n, len,
+                                                                      d_model, n_head, p_drop, (uint32_t)seed, dqk);
   return tiger_launch_status();
 }
 
