@@ -549,6 +549,26 @@ def run_b200(args):
                     'counters': counters,
                     'note': 'entry-point granularity (CUDA events around the C-ABI call, eager launches); at batch 200 '
                             'every kernel is latency bound - see bench.py --micro for the HBM fractions at 256k rows'}
+        # K7: the seq restarter's dense products (q/k in-projection of R x L tokens, value / out / out_fn / merger
+        # products of R rows) - the dominant entry point of the seq-restarter configurations
+        sg = kernels.get('tiger_sgemm_nt')
+        if rst == 'seq' and sg:
+            dm, L = 4 * d + de, HIST_LEN
+            flops = counters['R'] * 2.0 * (L * dm * 2 * dm + 2 * dm * dm + dm * d + 2 * d * d)
+            tf32_peak = float(peaks.get('bf16_tflops', 1590.0)) / 2.0
+            sg['tensor'] = {'bound': 'tensor', 'useful_tflops': flops / (sg['us'] * 1e-6) / 1e12,
+                            'issued_tflops': 3.0 * flops / (sg['us'] * 1e-6) / 1e12, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                            'frac': 3.0 * flops / (sg['us'] * 1e-6) / 1e12 / tf32_peak, 'restarted_nodes_per_batch': counters['R'],
+                            'note': 'seq restarter (K7): 7 launches per batch on ~R x 40 tokens; latency bound at this '
+                                    'size (54 dependent k-steps per product), see profiles/r02_launches_wikipedia_infer.md'}
+            if top == 'tiger_sgemm_nt':
+                roofline = {'bound': 'tensor', 'kernel': top, 'achieved': sg['tensor']['issued_tflops'], 'peak': tf32_peak,
+                            'unit': 'TFLOP/s', 'frac': sg['tensor']['frac'], 'traffic': None,
+                            'peak_source': 'half of the measured bf16 GEMM peak (tf32 runs at half the bf16 rate)',
+                            'launch_us': sg['us'], 'launches_per_step': sg['launches_per_step'], 'flops_per_step': flops,
+                            'counters': counters,
+                            'note': 'entry-point granularity (CUDA events around the eager C-ABI calls); issued = 3 x useful '
+                                    'flops (tf32x3)'}
         # the dense kernel of the path: GRU gate GEMM on the tensor cores (tf32x3: 3 MMAs per useful product)
         g = kernels.get('tiger_gru_update')
         if g:
@@ -779,11 +799,12 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
         except OSError:
             pass
         flops = train_flops(counters, d, de, B, K_NEIGH, HIST_LEN, rst == 'seq')
-        g = kernels.get('tiger_sgemm_ex')
+        dense = [kernels[k] for k in ('tiger_sgemm_ex', 'tiger_sgemm_pp', 'tiger_gemm_pp_pack') if k in kernels]
+        g = {'us': sum(x['us'] for x in dense), 'launches_per_step': sum(x['launches_per_step'] for x in dense)} if dense else None
         tf32_peak = float(peaks.get('bf16_tflops', 1590.0)) / 2.0
         if g:
             ach = 3.0 * flops / (g['us'] * 1e-6) / 1e12
-            roofline = {'bound': 'tensor', 'kernel': 'tiger_sgemm_ex', 'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+            roofline = {'bound': 'tensor', 'kernel': 'tiger_sgemm_ex + tiger_sgemm_pp (+ tiger_gemm_pp_pack)', 'achieved': ach, 'peak': tf32_peak, 'unit': 'TFLOP/s',
                         'frac': ach / tf32_peak, 'traffic': None, 'useful_tflops': ach / 3.0, 'launch_us': g['us'],
                         'launches_per_step': g['launches_per_step'], 'flops_per_step': flops, 'counters': counters,
                         'peak_source': 'half of the measured bf16 GEMM peak (tf32 runs at half the bf16 rate)'

@@ -4,6 +4,7 @@ Every function takes CUDA tensors, allocates its outputs with torch (device memo
 only thing torch does here), launches on the current stream and never synchronises.
 """
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -533,11 +534,13 @@ def sgemm_nt_packed(a: Tensor, pack: WeightPack, bias: Optional[Tensor], out: Te
 
 
 def sgemm_nt_packed_splitk_fused(a: Tensor, pack: WeightPack, bias: Optional[Tensor], out: Tensor, k_parts: int, *,
-                                 relu: bool = False, alpha: float = 1.0) -> Tensor:
+                                 relu: bool = False, alpha: float = 1.0, m_rows: Optional[int] = None,
+                                 count: Optional[Tensor] = None) -> Tensor:
     """As sgemm_nt_packed with K split over a thread-block cluster of k_parts CTAs per tile (DSMEM reduction)."""
     check_cuda_strided(a, out)
     call('tiger_sgemm_nt_packed_splitk_fused', ptr(a), a.stride(0), ptr(pack.data), pack.bn, ptr(bias), ptr(out),
-         out.stride(0), k_parts, a.shape[0], None, 1, pack.n, pack.k, float(alpha), int(relu))
+         out.stride(0), k_parts, a.shape[0] if m_rows is None else m_rows, ptr(count), 1, pack.n, pack.k, float(alpha),
+         int(relu))
     return out
 
 
@@ -599,6 +602,16 @@ class SeqRestarterOp:
         self.fn_w, self.fn_b = g('out_fn.weight'), g('out_fn.bias')
         self.fc1_w, self.fc1_b = g('merger.fc1.weight'), g('merger.fc1.bias')
         self.fc2_w, self.fc2_b = g('merger.fc2.weight'), g('merger.fc2.bias')
+        # The products on the n pooled rows (value projection per head, out-projection, out_fn, merger) have a handful of
+        # rows and K = d_model: one CTA per tile would walk 54 dependent k-steps (33 us each, ncu).  Their weights are
+        # packed once per parameter update and K is split over a cluster of up to 8 CTAs (DSMEM reduction).
+        dm, hd, d = self.dm, self.dm // self.H, self.d
+        self._small = os.environ.get('TIGER_SEQ_UNPACKED') != '1'
+        if self._small:
+            mk = lambda w: WeightPack(w.contiguous(), m_rows_hint=128)
+            self.pk_v = [mk(self.in_w[2 * dm + h * hd:2 * dm + (h + 1) * hd]) for h in range(self.H)]
+            self.pk_out, self.pk_fn = mk(self.out_w), mk(self.fn_w)
+            self.pk_fc1, self.pk_fc2 = mk(self.fc1_w[:, :d]), mk(self.fc2_w)
 
     def history(self, csr: DeviceCSR, nids: Tensor, q_ts: Tensor, n: int, *, ts_period: int = 0,
                 count: Optional[Tensor] = None):
@@ -624,6 +637,17 @@ class SeqRestarterOp:
         # which stays as the plain reference kernel of the C ABI)
         call('tiger_train_seq_pool', ptr(self.qk), self.qk.stride(0), ptr(self.x), ptr(self.mask), ptr(count), n, L, dm,
              H, 0.0, 0, ptr(self.P), ptr(self.pbar), ptr(self.psum), ptr(self.xbar))
+        if self._small:
+            kw = dict(m_rows=n, count=count)
+            for h in range(H):
+                rows = slice(2 * dm + h * hd, 2 * dm + (h + 1) * hd)
+                sgemm_nt_packed_splitk_fused(self.xbar[:, h * dm:(h + 1) * dm], self.pk_v[h], self.in_b[rows],
+                                             self.att[:, h * hd:(h + 1) * hd], 8, **kw)
+            sgemm_nt_packed_splitk_fused(self.att, self.pk_out, self.out_b, self.o, 8, relu=True, **kw)
+            sgemm_nt_packed_splitk_fused(self.o, self.pk_fn, self.fn_b, self.h_left, 8, **kw)
+            sgemm_nt_packed_splitk_fused(self.h_left, self.pk_fc1, self.fc1_b, self.hid, 2, relu=True, **kw)
+            sgemm_nt_packed_splitk_fused(self.hid, self.pk_fc2, self.fc2_b, self.h_right, 2, **kw)
+            return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
         for h in range(H):
             rows = slice(2 * dm + h * hd, 2 * dm + (h + 1) * hd)
             sgemm_nt(self.xbar[:, h * dm:(h + 1) * dm], self.in_w[rows], self.in_b[rows],
