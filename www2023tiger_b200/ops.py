@@ -603,10 +603,13 @@ class SeqRestarterOp:
         self.fc1_w, self.fc1_b = g('merger.fc1.weight'), g('merger.fc1.bias')
         self.fc2_w, self.fc2_b = g('merger.fc2.weight'), g('merger.fc2.bias')
         # The products on the n pooled rows (value projection per head, out-projection, out_fn, merger) have a handful of
-        # rows and K = d_model: one CTA per tile would walk 54 dependent k-steps (33 us each, ncu).  Their weights are
-        # packed once per parameter update and K is split over a cluster of up to 8 CTAs (DSMEM reduction).
+        # rows and K = d_model: one CTA per tile walks 54 dependent k-steps (33 us each, ncu).  Tried: packed weights with
+        # K split over a cluster of up to 8 CTAs (DSMEM reduction) - measured SLOWER in the captured step (wikipedia
+        # 0.333 -> 0.410 ms, mooc 0.126 -> 0.212 ms): the launch is sized for the row capacity (52 row tiles x column tiles
+        # x 8 cluster CTAs, almost all of which only exit) and cluster launches cost more than plain ones.  Kept behind
+        # TIGER_SEQ_SPLITK=1; the default is the persistent staging kernel.
         dm, hd, d = self.dm, self.dm // self.H, self.d
-        self._small = os.environ.get('TIGER_SEQ_UNPACKED') != '1'
+        self._small = os.environ.get('TIGER_SEQ_SPLITK') == '1'
         if self._small:
             mk = lambda w: WeightPack(w.contiguous(), m_rows_hint=128)
             self.pk_v = [mk(self.in_w[2 * dm + h * hd:2 * dm + (h + 1) * hd]) for h in range(self.H)]
