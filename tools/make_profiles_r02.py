@@ -1,0 +1,65 @@
+"""Copies the round-2 measurement artefacts from gpurun_out/ into profiles/ and refreshes the number tables of DESIGN.md
+(between the <!-- NAME --> markers) from them."""
+import glob, json, os, re, shutil
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+O, P = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
+
+
+def load(path):
+    try:
+        return json.loads(open(path).read().strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def fill(text, name, body):
+    return re.sub(rf'<!-- {name} -->.*?<!-- /{name} -->', f'<!-- {name} -->\n{body}\n<!-- /{name} -->', text, flags=re.S)
+
+
+def main():
+    for f in glob.glob(os.path.join(O, 'r02_bench_*.json')) + glob.glob(os.path.join(O, 'r02_train_*.json')) + \
+            glob.glob(os.path.join(O, 'r02_ddp_*_n?.json')) + glob.glob(os.path.join(O, 'r02_reference_*.json')) + \
+            glob.glob(os.path.join(O, 'r02_micro.json')):
+        if load(f) is not None:
+            shutil.copy(f, os.path.join(P, os.path.basename(f)))
+    design = open(os.path.join(ROOT, 'DESIGN.md')).read()
+    rows = ['| workload (BASELINE config) | mode | ms / step | events/s (`value`) | events/s (`e2e`) | reference on 16 host cores | e2e / reference | parity checked in the run |',
+            '|---|---|---|---|---|---|---|---|']
+    names = {'wikipedia': 'Wikipedia-shaped, seq restarter [0]', 'reddit': 'Reddit-shaped, static restarter [1]',
+             'mooc': 'MOOC-shaped, seq, msg/upd right, dim 100 [2]', 'lastfm': 'LastFM-shaped, seq, no edge feats, dim 100 [3]',
+             'scaled': 'scaled: 1 M nodes, 50 M events, seq [4]'}
+    for mode, pat in (('infer', 'r02_bench_%s.json'), ('train', 'r02_train_%s.json')):
+        for w in ('wikipedia', 'reddit', 'mooc', 'lastfm', 'scaled'):
+            d = load(os.path.join(P, pat % w))
+            if d is None:
+                continue
+            cb, e2e = d.get('cpu_baseline') or {}, (d.get('e2e') or {}).get('value')
+            ratio = f"{e2e / cb['value']:.0f} x" if e2e and cb.get('value') else ''
+            par = d.get('parity') or {}
+            rows.append(f"| {names[w]} | {mode} | {d['ms_per_step']:.4f} | {d['value']:,.0f} | {e2e:,.0f} | "
+                        f"{cb.get('value', 0):,.0f} ({cb.get('kind')}) | {ratio} | {'yes, vs ' + par.get('against', '') if par else 'no'} |")
+            if mode == 'infer' and d.get('train_step'):
+                t = d['train_step']
+                rows.append(f"| ... same run, `train_step` (100 steps) | train | {t['ms_per_step']:.4f} | {t['value']:,.0f} | | | | |")
+    design = fill(design, 'BENCH_TABLE', '\n'.join(rows))
+    rows = ['| N | events/s (all ranks) | ms / step (slowest rank) | all-reduce bytes / step | vs N = 1 |', '|---|---|---|---|---|']
+    base = None
+    for n in (1, 2, 4, 8):
+        d = load(os.path.join(P, f'r02_ddp_scaled_train_n{n}.json'))
+        if d is None:
+            continue
+        base = base or d['value']
+        rows.append(f"| {n} | {d['value']:,.0f} | {d['ms_per_step']:.3f} | {d['train']['allreduce_bytes_per_step']:,} | "
+                    f"{d['value'] / base:.2f} x (efficiency {d['value'] / base / n:.3f}) |")
+    design = fill(design, 'DDP_TABLE', '\n'.join(rows))
+    m = load(os.path.join(P, 'r02_micro.json'))
+    if m:
+        design = fill(design, 'MICRO', ', '.join(f"`{k}` {v['frac_of_peak']:.2f}" for k, v in m['micro'].items()) + '.')
+    open(os.path.join(ROOT, 'DESIGN.md'), 'w').write(design)
+    print(design[design.index('<!-- BENCH_TABLE -->'):design.index('<!-- /BENCH_TABLE -->')])
+    print(design[design.index('<!-- DDP_TABLE -->'):design.index('<!-- /DDP_TABLE -->')])
+
+
+if __name__ == '__main__':
+    main()

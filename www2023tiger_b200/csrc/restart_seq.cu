@@ -222,3 +222,115 @@ extern "C" int tiger_seq_attn_pool(const float* qk, int64_t ld_qk, const float* 
                                                                               d_model, n_head, xbar);
   return tiger_launch_status();
 }
+
+// ------------------------------------------------------------------------------------------
+// Small-R tail of the seq restarter.  After the pooling kernel the path is five dependent layers on the n pooled
+// rows - value projection per head, out-projection (+ReLU), out_fn, merger fc1 (+ReLU), fc2 - and in steady state
+// n is ~20-50 (the nodes a batch touches for the first time).  As tensor-core products each layer is one CTA per
+// tile walking 54 dependent k-steps (K = d_model = 860): 6 launches x 33 us for a few hundred MFLOP.  Here one CTA
+// owns one row and runs all five layers as matrix-vector products out of shared memory, one warp per output
+// channel, weights streamed from L2 with 16-byte loads (6.6 MB per row).  Above `max_rows` restarted rows (the
+// first batches of a chunk) the kernel exits at once and the GEMM chain runs instead: tiger_seq_gate_count splits
+// the device-side row count into (count if <= max_rows else 0, count if > max_rows else 0).
+// ------------------------------------------------------------------------------------------
+__global__ void seq_gate_count_kernel(const int32_t* __restrict__ count, int32_t max_rows, int32_t* __restrict__ small,
+                                      int32_t* __restrict__ big) {
+  const int32_t c = *count;
+  *small = c <= max_rows ? c : 0;
+  *big = c > max_rows ? c : 0;
+}
+
+extern "C" int tiger_seq_gate_count(const int32_t* count, int max_rows, int32_t* count_small, int32_t* count_big,
+                                    void* stream) {
+  if (count == nullptr || count_small == nullptr || count_big == nullptr) return TIGER_EINVAL;
+  seq_gate_count_kernel<<<1, 1, 0, as_stream(stream)>>>(count, max_rows, count_small, count_big);
+  return tiger_launch_status();
+}
+
+// y[c] = act(bias[c] + W[c, :k] . x) for c in [0, n_out): one warp per output channel
+__device__ __forceinline__ void tail_layer(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias,
+                                           const float* x, int k, int n_out, bool relu, float* y, int warp, int n_warps,
+                                           int lane) {
+  const bool vec = ((((uintptr_t)W) & 15) == 0) && (ldw & 3) == 0 && (k & 3) == 0;
+  for (int c = warp; c < n_out; c += n_warps) {
+    const float* w = W + (int64_t)c * ldw;
+    float acc = 0.f;
+    if (vec) {
+      const float4* w4 = reinterpret_cast<const float4*>(w);
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      for (int i = lane; i < (k >> 2); i += 32) {
+        const float4 a = __ldg(w4 + i), b = x4[i];
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
+    } else {
+      for (int i = lane; i < k; i += 32) acc = fmaf(__ldg(w + i), x[i], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float v = acc + bias[c];
+      y[c] = relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+}
+
+#define TAIL_THREADS 512
+__global__ void __launch_bounds__(TAIL_THREADS)
+seq_tail_kernel(const float* __restrict__ xbar, const int32_t* __restrict__ count, int64_t n_cap, int dm, int n_head,
+                int d, const float* __restrict__ wv, const float* __restrict__ bv, const float* __restrict__ wo,
+                const float* __restrict__ bo, const float* __restrict__ wfn, const float* __restrict__ bfn,
+                const float* __restrict__ wfc1, int64_t ld_fc1, const float* __restrict__ bfc1,
+                const float* __restrict__ wfc2, const float* __restrict__ bfc2, float* __restrict__ h_left,
+                float* __restrict__ h_right) {
+  extern __shared__ __align__(16) float tail_smem[];
+  int64_t n = n_cap;
+  if (count != nullptr) {
+    const int64_t c = *count;
+    n = c < n ? c : n;
+  }
+  const int hd = dm / n_head;
+  const int dmp = (dm + 3) & ~3, dp = (d + 3) & ~3;
+  float* xb = tail_smem;                       // [n_head][dmp]
+  float* att = xb + n_head * dmp;              // [dmp]
+  float* o = att + dmp;                        // [dmp]
+  float* hl = o + dmp;                         // [dp]
+  float* hid = hl + dp;                        // [dp]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = TAIL_THREADS / 32;
+  for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < n_head * dm; i += TAIL_THREADS) xb[(i / dm) * dmp + (i % dm)] = xbar[r * n_head * dm + i];
+    __syncthreads();
+    for (int h = 0; h < n_head; ++h)            // value projection of the head's pooled tokens
+      tail_layer(wv + (int64_t)h * hd * dm, dm, bv + h * hd, xb + h * dmp, dm, hd, false, att + h * hd, warp, n_warps, lane);
+    __syncthreads();
+    tail_layer(wo, dm, bo, att, dm, dm, true, o, warp, n_warps, lane);
+    __syncthreads();
+    tail_layer(wfn, dm, bfn, o, dm, d, false, hl, warp, n_warps, lane);
+    __syncthreads();
+    for (int c = tid; c < d; c += TAIL_THREADS) h_left[r * d + c] = hl[c];
+    tail_layer(wfc1, ld_fc1, bfc1, hl, d, d, true, hid, warp, n_warps, lane);
+    __syncthreads();
+    tail_layer(wfc2, d, bfc2, hid, d, d, false, hl, warp, n_warps, lane);
+    __syncthreads();
+    for (int c = tid; c < d; c += TAIL_THREADS) h_right[r * d + c] = hl[c];
+  }
+}
+
+extern "C" int tiger_seq_tail(const float* xbar, const int32_t* count, int64_t n, int d_model, int n_head, int d,
+                              const float* w_v, const float* b_v, const float* w_out, const float* b_out,
+                              const float* w_fn, const float* b_fn, const float* w_fc1, int64_t ld_fc1, const float* b_fc1,
+                              const float* w_fc2, const float* b_fc2, int max_rows, float* h_left, float* h_right,
+                              void* stream) {
+  if (xbar == nullptr || w_v == nullptr || w_out == nullptr || w_fn == nullptr || w_fc1 == nullptr || w_fc2 == nullptr ||
+      h_left == nullptr || h_right == nullptr || n < 0 || d_model <= 0 || n_head <= 0 || d_model % n_head != 0 || d <= 0 ||
+      max_rows <= 0 || ld_fc1 < d)
+    return TIGER_EINVAL;
+  if (n == 0) return TIGER_OK;
+  const int dmp = (d_model + 3) & ~3, dp = (d + 3) & ~3;
+  const size_t smem = (size_t)((n_head + 2) * dmp + 2 * dp) * sizeof(float);
+  if (smem > 48 * 1024) return TIGER_EINVAL;
+  const int64_t grid = n < max_rows ? n : max_rows;
+  seq_tail_kernel<<<(unsigned)grid, TAIL_THREADS, smem, as_stream(stream)>>>(
+      xbar, count, n, d_model, n_head, d, w_v, b_v, w_out, b_out, w_fn, b_fn, w_fc1, ld_fc1, b_fc1, w_fc2, b_fc2, h_left,
+      h_right);
+  return tiger_launch_status();
+}
