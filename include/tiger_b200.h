@@ -350,14 +350,18 @@ int tiger_seq_tokens(const int64_t* nids, const int32_t* count, int64_t n, int l
 
 /* Small-R tail of SeqRestarter.forward (restarters.py:106-114 after the attention): value projection of the pooled
  * tokens per head, out-projection + ReLU, out_fn, merger (fc1 on its first d input columns + ReLU, fc2) as five
- * matrix-vector layers, one CTA per restarted row.  Rows: min(n, *count); the caller passes the count gated by
+ * matrix-vector layers (one warp per output channel; att [n, d_model], o [n, d_model], hid [n, d] are the intermediate
+ * rows).  Training-mode forward (tiger_train_seq_pool with dropout): psum [n, n_head] scales the value bias, p_drop /
+ * seed drop the merger's hidden layer exactly like tiger_train_dropout(stream 4); NULL / 0 for inference.
+ * Rows: min(n, *count); the caller passes the count gated by
  * tiger_seq_gate_count (count_small = count if count <= max_rows else 0, count_big = the complement), so that few rows
  * take this kernel and many rows the tensor-core products. */
 int tiger_seq_gate_count(const int32_t* count, int max_rows, int32_t* count_small, int32_t* count_big, void* stream);
 int tiger_seq_tail(const float* xbar, const int32_t* count, int64_t n, int d_model, int n_head, int d, const float* w_v,
                    const float* b_v, const float* w_out, const float* b_out, const float* w_fn, const float* b_fn,
                    const float* w_fc1, int64_t ld_fc1, const float* b_fc1, const float* w_fc2, const float* b_fc2,
-                   int max_rows, float* h_left, float* h_right, void* stream);
+                   const float* psum, float p_drop, int seed, float* att, float* o, float* hid, float* h_left,
+                   float* h_right, void* stream);
 
 /* C[m,n] = act(sum_k A[m,k] * W[n,k] + bias[n]): fp32 FFMA GEMM on row-major A [M,K] and nn.Linear
  * style weights W [N,K] (bias may be NULL; relu != 0 applies max(.,0)).  The row count is

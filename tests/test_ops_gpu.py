@@ -325,8 +325,9 @@ def test_seq_restarter_matches_reference_golden(gu, name):
         assert np.array_equal(gu.cpu(pt), g.b(ib, 'r_hist_ts')[:, -1])
 
 
+@pytest.mark.parametrize('n_pick', [70, 30, 1])       # > / <= SeqRestarterOp.tail_rows: tensor-core products / fused tail
 @pytest.mark.parametrize('d,de,L,with_nf', [(172, 172, 40, False), (100, 4, 40, False), (24, 10, 64, True)])
-def test_seq_restarter_matches_oracle(gu, d, de, L, with_nf):
+def test_seq_restarter_matches_oracle(gu, d, de, L, with_nf, n_pick):
     """Restarter with computation_graph=None: history looked up on the device CSR (restart path)."""
     st = make_stream(StreamShape('s', 150, 25, 8000, de, None, horizon=5000.), seed=6, nfeat_dim=d if with_nf else 0)
     N = st.n_nodes
@@ -334,7 +335,7 @@ def test_seq_restarter_matches_oracle(gu, d, de, L, with_nf):
     graph = O.OracleGraph(st.src, st.dst, st.ts, st.eids, n_nodes=N)
     model = O.OracleTIGER(W, graph, N, d, st.efeats, st.nfeats, restarter='seq', hist_len=L)
     rng = np.random.RandomState(0)
-    nids = np.concatenate([[0], rng.choice(np.arange(1, N), 70, replace=False)]).astype(np.int64)
+    nids = np.concatenate([[0], rng.choice(np.arange(1, N), n_pick, replace=False)]).astype(np.int64)
     t = np.float32(3000.0)
     ref_l, ref_r, ref_pt = model.restarter_forward(nids, np.full(len(nids), t, dtype=np.float32))
     csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
@@ -355,6 +356,22 @@ def test_seq_restarter_matches_oracle(gu, d, de, L, with_nf):
     assert_close(gu.cpu(hl[:n]), ref_l.numpy(), TOL, 'h_left')
     assert_close(gu.cpu(hr[:n]), ref_r.numpy(), TOL, 'h_right')
     assert np.array_equal(gu.cpu(pt[:n]), ref_pt.numpy())
+    # rows past the count are not written by either route
+    assert op.tail_rows == 64
+    hl_a, hr_a = hl.clone(), hr.clone()
+    op.tail_rows = 0
+    op.h_left.fill_(-3.0), op.h_right.fill_(-3.0)
+    hl_b, hr_b, _ = op.forward(dn, 128, None if st.nfeats is None else gu.dev(st.nfeats, torch.float32),
+                               gu.dev(st.efeats, torch.float32), count=count)
+    assert_close(gu.cpu(hl_a[:n]), gu.cpu(hl_b[:n]), TOL, 'tail vs products, left')
+    assert_close(gu.cpu(hr_a[:n]), gu.cpu(hr_b[:n]), TOL, 'tail vs products, right')
+    assert (gu.cpu(hl_b[n:]) == -3.0).all() and (gu.cpu(hr_b[n:]) == -3.0).all()
+    op.tail_rows = 64
+    op.h_left.fill_(-3.0), op.h_right.fill_(-3.0)
+    hl_c, hr_c, _ = op.forward(dn, 128, None if st.nfeats is None else gu.dev(st.nfeats, torch.float32),
+                               gu.dev(st.efeats, torch.float32), count=count)
+    assert (gu.cpu(hl_c[n:]) == -3.0).all() and (gu.cpu(hr_c[n:]) == -3.0).all()
+    assert torch.equal(hl_c[:n], hl_a[:n]) and torch.equal(hr_c[:n], hr_a[:n])
 
 
 # ------------------------------------------------------------------ packed-weight tensor-core GEMM

@@ -90,7 +90,7 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_gemm_pp_pack': 'plillpplpp',
     'tiger_sgemm_pp': 'ppppllilpplfiiip',
     'tiger_seq_gate_count': 'pipp' + 'p',
-    'tiger_seq_tail': 'ppliii' + 'pppppp' + 'plp' + 'pp' + 'i' + 'pp' + 'p',
+    'tiger_seq_tail': 'ppliii' + 'pppppp' + 'plp' + 'pp' + 'pfi' + 'ppppp' + 'p',
     'tiger_sgemm_ex': 'pli' + 'pli' + 'ppl' + 'lil' + 'ppl' + 'fiii' + 'p',
     'tiger_sgemm_nt_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_gemm_pick_bn': 'lii',

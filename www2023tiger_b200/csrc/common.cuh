@@ -68,6 +68,18 @@ static inline int tiger_launch_chain(void (*kernel)(KP...), dim3 grid, dim3 bloc
   return tiger_launch_status();
 }
 
+// Counter-based dropout mask of the seq restarter's training step: element `idx` of mask stream `stream` (3: attention
+// probabilities, 4: merger hidden layer) under `seed` is kept with probability 1 - p.
+__device__ __forceinline__ uint32_t seq_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool seq_keep(uint32_t seed, uint32_t stream, uint32_t idx, float p) {
+  if (p <= 0.f) return true;
+  const uint32_t h = seq_mix32(idx ^ seq_mix32(seed + 0x9E3779B9u * (stream + 1u)));
+  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id_in_block() { return threadIdx.x >> 5; }
 

@@ -227,11 +227,12 @@ extern "C" int tiger_seq_attn_pool(const float* qk, int64_t ld_qk, const float* 
 // Small-R tail of the seq restarter.  After the pooling kernel the path is five dependent layers on the n pooled
 // rows - value projection per head, out-projection (+ReLU), out_fn, merger fc1 (+ReLU), fc2 - and in steady state
 // n is ~20-50 (the nodes a batch touches for the first time).  As tensor-core products each layer is one CTA per
-// tile walking 54 dependent k-steps (K = d_model = 860): 6 launches x 33 us for a few hundred MFLOP.  Here one CTA
-// owns one row and runs all five layers as matrix-vector products out of shared memory, one warp per output
-// channel, weights streamed from L2 with 16-byte loads (6.6 MB per row).  Above `max_rows` restarted rows (the
-// first batches of a chunk) the kernel exits at once and the GEMM chain runs instead: tiger_seq_gate_count splits
-// the device-side row count into (count if <= max_rows else 0, count if > max_rows else 0).
+// tile walking 54 dependent k-steps (K = d_model = 860): 6 launches x 33 us for a few hundred MFLOP.  Here each layer
+// is a matrix-vector kernel with one warp per output channel (108 CTAs for the d_model-wide layers), chained by
+// programmatic dependent launch so that a layer's weight rows are already in registers when its input arrives.
+// (First attempt: all five layers in one CTA per row - 139 us, one row's 6.6 MB of weights through one SM.)  With
+// many restarted rows (the first batches of a chunk) the tensor-core products win: tiger_seq_gate_count splits the
+// device-side row count into (count if <= max_rows else 0, count if > max_rows else 0) and both routes are launched.
 // ------------------------------------------------------------------------------------------
 __global__ void seq_gate_count_kernel(const int32_t* __restrict__ count, int32_t max_rows, int32_t* __restrict__ small,
                                       int32_t* __restrict__ big) {
@@ -247,90 +248,107 @@ extern "C" int tiger_seq_gate_count(const int32_t* count, int max_rows, int32_t*
   return tiger_launch_status();
 }
 
-// y[c] = act(bias[c] + W[c, :k] . x) for c in [0, n_out): one warp per output channel
-__device__ __forceinline__ void tail_layer(const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias,
-                                           const float* x, int k, int n_out, bool relu, float* y, int warp, int n_warps,
-                                           int lane) {
-  const bool vec = ((((uintptr_t)W) & 15) == 0) && (ldw & 3) == 0 && (k & 3) == 0;
-  for (int c = warp; c < n_out; c += n_warps) {
-    const float* w = W + (int64_t)c * ldw;
-    float acc = 0.f;
-    if (vec) {
-      const float4* w4 = reinterpret_cast<const float4*>(w);
-      const float4* x4 = reinterpret_cast<const float4*>(x);
-      for (int i = lane; i < (k >> 2); i += 32) {
-        const float4 a = __ldg(w4 + i), b = x4[i];
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-      }
-    } else {
-      for (int i = lane; i < k; i += 32) acc = fmaf(__ldg(w + i), x[i], acc);
+// One layer y[r, g*n_out + c] = act(bias[g*n_out + c] + W[g*n_out + c, :k] . x[r, g*x_grp_off : +k]) on the first
+// min(n_cap, *count) rows.  One warp per output channel keeps the channel's weight row in registers (fetched before
+// the wait on the producing kernel: weights do not depend on it) and walks the rows in groups of TAIL_RT staged in
+// shared memory.  Group g (blockIdx.y) is the attention head of the value projection, 0 elsewhere.
+#define TAIL_WARPS 8
+#define TAIL_RT 8
+template <int KREG>
+__global__ void __launch_bounds__(TAIL_WARPS * 32)
+seq_tail_layer_kernel(const float* __restrict__ x, int64_t ldx, int64_t x_grp_off, const float* __restrict__ W, int64_t ldw,
+                      const float* __restrict__ bias, const float* __restrict__ bias_scale, float* __restrict__ y, int64_t ldy,
+                      const int32_t* __restrict__ count, int64_t n_cap, int k, int n_out, int relu, float p_drop,
+                      uint32_t seed) {
+  extern __shared__ __align__(16) float tail_xs[];          // [TAIL_RT][32 * KREG]
+  constexpr int KP = 32 * KREG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.y, c = blockIdx.x * TAIL_WARPS + warp;
+  const bool live = c < n_out;
+  float wr[KREG];
+  float b = 0.f;
+  {
+    const float* w = W + ((int64_t)g * n_out + (live ? c : 0)) * ldw;
+#pragma unroll
+    for (int j = 0; j < KREG; ++j) {
+      const int idx = lane + 32 * j;
+      wr[j] = (live && idx < k) ? __ldg(w + idx) : 0.f;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float v = acc + bias[c];
-      y[c] = relu ? fmaxf(v, 0.f) : v;
+    if (live && bias != nullptr) b = __ldg(bias + g * n_out + c);
+  }
+  pdl_trigger();
+  pdl_wait();
+  int64_t n = n_cap;
+  if (count != nullptr) {
+    const int64_t cc = *count;
+    n = cc < n ? cc : n;
+  }
+  const float* xg = x + (int64_t)g * x_grp_off;
+  for (int64_t r0 = 0; r0 < n; r0 += TAIL_RT) {
+    const int rows = (int)((n - r0) < TAIL_RT ? (n - r0) : TAIL_RT);
+    __syncthreads();
+    for (int i = tid; i < TAIL_RT * KP; i += TAIL_WARPS * 32) {
+      const int rr = i / KP, col = i % KP;
+      tail_xs[i] = (rr < rows && col < k) ? xg[(r0 + rr) * ldx + col] : 0.f;
+    }
+    __syncthreads();
+    float acc[TAIL_RT];
+#pragma unroll
+    for (int rr = 0; rr < TAIL_RT; ++rr) acc[rr] = 0.f;
+#pragma unroll
+    for (int j = 0; j < KREG; ++j) {
+#pragma unroll
+      for (int rr = 0; rr < TAIL_RT; ++rr) acc[rr] = fmaf(wr[j], tail_xs[rr * KP + lane + 32 * j], acc[rr]);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < TAIL_RT; ++rr) {
+      const float s = warp_sum(acc[rr]);
+      if (lane == rr) mine = s;
+    }
+    if (live && lane < rows) {
+      // bias_scale [n, groups]: the value bias under attention dropout is b * (row sum of the kept probabilities)
+      float v = mine + (bias_scale != nullptr ? b * bias_scale[(r0 + lane) * gridDim.y + g] : b);
+      if (relu) v = fmaxf(v, 0.f);
+      if (p_drop > 0.f)                                      // nn.Dropout of the merger (mask stream 4, element r * n_out + c)
+        v = seq_keep(seed, 4u, (uint32_t)((r0 + lane) * n_out + c), p_drop) ? v * (1.0f / (1.0f - p_drop)) : 0.f;
+      y[(r0 + lane) * ldy + (int64_t)g * n_out + c] = v;
     }
   }
 }
 
-#define TAIL_THREADS 512
-__global__ void __launch_bounds__(TAIL_THREADS)
-seq_tail_kernel(const float* __restrict__ xbar, const int32_t* __restrict__ count, int64_t n_cap, int dm, int n_head,
-                int d, const float* __restrict__ wv, const float* __restrict__ bv, const float* __restrict__ wo,
-                const float* __restrict__ bo, const float* __restrict__ wfn, const float* __restrict__ bfn,
-                const float* __restrict__ wfc1, int64_t ld_fc1, const float* __restrict__ bfc1,
-                const float* __restrict__ wfc2, const float* __restrict__ bfc2, float* __restrict__ h_left,
-                float* __restrict__ h_right) {
-  extern __shared__ __align__(16) float tail_smem[];
-  int64_t n = n_cap;
-  if (count != nullptr) {
-    const int64_t c = *count;
-    n = c < n ? c : n;
-  }
-  const int hd = dm / n_head;
-  const int dmp = (dm + 3) & ~3, dp = (d + 3) & ~3;
-  float* xb = tail_smem;                       // [n_head][dmp]
-  float* att = xb + n_head * dmp;              // [dmp]
-  float* o = att + dmp;                        // [dmp]
-  float* hl = o + dmp;                         // [dp]
-  float* hid = hl + dp;                        // [dp]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = TAIL_THREADS / 32;
-  for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
-    __syncthreads();
-    for (int i = tid; i < n_head * dm; i += TAIL_THREADS) xb[(i / dm) * dmp + (i % dm)] = xbar[r * n_head * dm + i];
-    __syncthreads();
-    for (int h = 0; h < n_head; ++h)            // value projection of the head's pooled tokens
-      tail_layer(wv + (int64_t)h * hd * dm, dm, bv + h * hd, xb + h * dmp, dm, hd, false, att + h * hd, warp, n_warps, lane);
-    __syncthreads();
-    tail_layer(wo, dm, bo, att, dm, dm, true, o, warp, n_warps, lane);
-    __syncthreads();
-    tail_layer(wfn, dm, bfn, o, dm, d, false, hl, warp, n_warps, lane);
-    __syncthreads();
-    for (int c = tid; c < d; c += TAIL_THREADS) h_left[r * d + c] = hl[c];
-    tail_layer(wfc1, ld_fc1, bfc1, hl, d, d, true, hid, warp, n_warps, lane);
-    __syncthreads();
-    tail_layer(wfc2, d, bfc2, hid, d, d, false, hl, warp, n_warps, lane);
-    __syncthreads();
-    for (int c = tid; c < d; c += TAIL_THREADS) h_right[r * d + c] = hl[c];
-  }
+static int tail_layer(const float* x, int64_t ldx, int64_t x_grp_off, int groups, const float* W, int64_t ldw,
+                      const float* bias, const float* bias_scale, float* y, int64_t ldy, const int32_t* count, int64_t n, int k,
+                      int n_out, int relu, float p_drop, uint32_t seed, cudaStream_t st) {
+  const dim3 grid((unsigned)((n_out + TAIL_WARPS - 1) / TAIL_WARPS), (unsigned)groups), block(TAIL_WARPS * 32);
+  if (k <= 256)
+    return tiger_launch_chain(seq_tail_layer_kernel<8>, grid, block, TAIL_RT * 256 * sizeof(float), st, dim3(1, 1, 1), x, ldx,
+                              x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
+  if (k <= 512)
+    return tiger_launch_chain(seq_tail_layer_kernel<16>, grid, block, TAIL_RT * 512 * sizeof(float), st, dim3(1, 1, 1), x,
+                              ldx, x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
+  return tiger_launch_chain(seq_tail_layer_kernel<32>, grid, block, TAIL_RT * 1024 * sizeof(float), st, dim3(1, 1, 1), x, ldx,
+                            x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
 }
 
 extern "C" int tiger_seq_tail(const float* xbar, const int32_t* count, int64_t n, int d_model, int n_head, int d,
                               const float* w_v, const float* b_v, const float* w_out, const float* b_out,
                               const float* w_fn, const float* b_fn, const float* w_fc1, int64_t ld_fc1, const float* b_fc1,
-                              const float* w_fc2, const float* b_fc2, int max_rows, float* h_left, float* h_right,
-                              void* stream) {
+                              const float* w_fc2, const float* b_fc2, const float* psum, float p_drop, int seed, float* att,
+                              float* o, float* hid, float* h_left, float* h_right, void* stream) {
   if (xbar == nullptr || w_v == nullptr || w_out == nullptr || w_fn == nullptr || w_fc1 == nullptr || w_fc2 == nullptr ||
-      h_left == nullptr || h_right == nullptr || n < 0 || d_model <= 0 || n_head <= 0 || d_model % n_head != 0 || d <= 0 ||
-      max_rows <= 0 || ld_fc1 < d)
+      att == nullptr || o == nullptr || hid == nullptr || h_left == nullptr || h_right == nullptr || n < 0 ||
+      d_model <= 0 || d_model > 1024 || p_drop < 0.f || p_drop >= 1.f || n_head <= 0 || d_model % n_head != 0 || d <= 0 || d > 1024 || ld_fc1 < d)
     return TIGER_EINVAL;
   if (n == 0) return TIGER_OK;
-  const int dmp = (d_model + 3) & ~3, dp = (d + 3) & ~3;
-  const size_t smem = (size_t)((n_head + 2) * dmp + 2 * dp) * sizeof(float);
-  if (smem > 48 * 1024) return TIGER_EINVAL;
-  const int64_t grid = n < max_rows ? n : max_rows;
-  seq_tail_kernel<<<(unsigned)grid, TAIL_THREADS, smem, as_stream(stream)>>>(
-      xbar, count, n, d_model, n_head, d, w_v, b_v, w_out, b_out, w_fn, b_fn, w_fc1, ld_fc1, b_fc1, w_fc2, b_fc2, h_left,
-      h_right);
-  return tiger_launch_status();
+  cudaStream_t st = as_stream(stream);
+  const int dm = d_model, hd = d_model / n_head;
+  const uint32_t sd = (uint32_t)seed;
+  int rc = tail_layer(xbar, (int64_t)n_head * dm, dm, n_head, w_v, dm, b_v, psum, att, dm, count, n, dm, hd, 0, 0.f, sd, st);
+  if (rc == TIGER_OK) rc = tail_layer(att, dm, 0, 1, w_out, dm, b_out, nullptr, o, dm, count, n, dm, dm, 1, 0.f, sd, st);
+  if (rc == TIGER_OK) rc = tail_layer(o, dm, 0, 1, w_fn, dm, b_fn, nullptr, h_left, d, count, n, dm, d, 0, 0.f, sd, st);
+  if (rc == TIGER_OK)
+    rc = tail_layer(h_left, d, 0, 1, w_fc1, ld_fc1, b_fc1, nullptr, hid, d, count, n, d, d, 1, p_drop, sd, st);
+  if (rc == TIGER_OK) rc = tail_layer(hid, d, 0, 1, w_fc2, d, b_fc2, nullptr, h_right, d, count, n, d, d, 0, 0.f, sd, st);
+  return rc;
 }

@@ -9,15 +9,6 @@
 // (psum_h = 1 without dropout).  Only the q / k in-projection runs on all n * L tokens.
 #include "common.cuh"
 
-__device__ __forceinline__ uint32_t seq_mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ bool seq_keep(uint32_t seed, uint32_t stream, uint32_t idx, float p) {
-  if (p <= 0.f) return true;
-  const uint32_t h = seq_mix32(idx ^ seq_mix32(seed + 0x9E3779B9u * (stream + 1u)));
-  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p;
-}
 __device__ __forceinline__ float seq_sin_reduced(float x) {
   const double xd = (double)x;
   const double n = rint(xd * 0.15915494309189535);

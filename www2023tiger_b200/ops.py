@@ -592,6 +592,11 @@ class SeqRestarterOp:
         self.h_left, self.hid, self.h_right = z(cap, d), z(cap, d), z(cap, d)
         self.prev_ts = z(cap)
         self.tmin = z(1, dt=f64)
+        # [count if count <= TAIL_ROWS else 0, count if count > TAIL_ROWS else 0]: few restarted rows take the fused
+        # matrix-vector tail (tiger_seq_tail), many rows the tensor-core products
+        self.tail_rows = int(os.environ.get('TIGER_SEQ_TAIL_ROWS', '64')) if self.dm <= 1024 else 0
+        self.cnt_gate = z(2, dt=torch.int32)
+        self._aux = self._ev_a = self._ev_b = None
 
     def set_weights(self, W, prefix: str = 'restarter_fn.'):
         g = lambda k: W[prefix + k].detach().to(self.x.device, f32).contiguous()
@@ -640,6 +645,46 @@ class SeqRestarterOp:
         # which stays as the plain reference kernel of the C ABI)
         call('tiger_train_seq_pool', ptr(self.qk), self.qk.stride(0), ptr(self.x), ptr(self.mask), ptr(count), n, L, dm,
              H, 0.0, 0, ptr(self.P), ptr(self.pbar), ptr(self.psum), ptr(self.xbar))
+        if self.tail_rows > 0:
+            # steady state restarts a few dozen rows per batch: five dependent layers as matrix-vector products (33 us
+            # per tensor-core launch x 6 otherwise, profiles/r02_launches.md)
+            tail = lambda cnt: call(
+                'tiger_seq_tail', ptr(self.xbar), ptr(cnt), n, dm, H, d, ptr(self.in_w[2 * dm:]), ptr(self.in_b[2 * dm:]),
+                ptr(self.out_w), ptr(self.out_b), ptr(self.fn_w), ptr(self.fn_b), ptr(self.fc1_w), self.fc1_w.stride(0),
+                ptr(self.fc1_b), ptr(self.fc2_w), ptr(self.fc2_b), None, 0.0, 0, ptr(self.att), ptr(self.o), ptr(self.hid),
+                ptr(self.h_left), ptr(self.h_right))
+            if count is None:
+                if n <= self.tail_rows:
+                    tail(None)
+                    return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
+            else:
+                # device-side row count: both routes are launched, the gate gives one of them zero rows.  Under graph
+                # capture they are parallel branches (the idle route's launches cost ~2 us each in a serial chain)
+                call('tiger_seq_gate_count', ptr(count), self.tail_rows, ptr(self.cnt_gate), ptr(self.cnt_gate[1:]))
+                count = self.cnt_gate[1:]
+                if os.environ.get('TIGER_SEQ_NO_GEMM') == '1':        # (debug aid: tail route only)
+                    tail(self.cnt_gate)
+                    return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
+                cur = torch.cuda.current_stream()
+                if torch.cuda.is_current_stream_capturing() and os.environ.get('TIGER_SEQ_TAIL_SERIAL') != '1':
+                    if self._aux is None:
+                        self._aux, self._ev_a, self._ev_b = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
+                    self._ev_a.record(cur)
+                    with torch.cuda.stream(self._aux):
+                        self._aux.wait_event(self._ev_a)
+                        tail(self.cnt_gate)
+                        self._ev_b.record(self._aux)
+                    self._products(n, count)
+                    cur.wait_event(self._ev_b)
+                    return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
+                tail(self.cnt_gate)
+        self._products(n, count)
+        return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
+
+    def _products(self, n: int, count: Optional[Tensor]):
+        """The layers after the pooling kernel as tensor-core products."""
+        dm, d, H = self.dm, self.d, self.H
+        hd = dm // H
         if self._small:
             kw = dict(m_rows=n, count=count)
             for h in range(H):
@@ -650,7 +695,7 @@ class SeqRestarterOp:
             sgemm_nt_packed_splitk_fused(self.o, self.pk_fn, self.fn_b, self.h_left, 8, **kw)
             sgemm_nt_packed_splitk_fused(self.h_left, self.pk_fc1, self.fc1_b, self.hid, 2, relu=True, **kw)
             sgemm_nt_packed_splitk_fused(self.hid, self.pk_fc2, self.fc2_b, self.h_right, 2, **kw)
-            return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
+            return
         for h in range(H):
             rows = slice(2 * dm + h * hd, 2 * dm + (h + 1) * hd)
             sgemm_nt(self.xbar[:, h * dm:(h + 1) * dm], self.in_w[rows], self.in_b[rows],
@@ -659,9 +704,8 @@ class SeqRestarterOp:
         sgemm_nt(self.o, self.fn_w, self.fn_b, self.h_left, m_rows=n, count=count)
         sgemm_nt(self.h_left, self.fc1_w, self.fc1_b, self.hid, m_rows=n, k_dim=d, relu=True, count=count)
         sgemm_nt(self.hid, self.fc2_w, self.fc2_b, self.h_right, m_rows=n, count=count)
-        return self.h_left[:n], self.h_right[:n], self.prev_ts[:n]
 
-    LAUNCHES = 5 + 7   # min_time, find_recent, reindex, tokens, pool + 7 GEMMs
+    LAUNCHES = 5 + 7 + 6   # min_time, find_recent, reindex, tokens, pool + 7 GEMMs + gate_count, 5 tail layers
 
 
 def store_messages_dense(src, dst, eids, ts, winner, src_vals, dst_vals, src_prev_ts, dst_prev_ts, nfeats, efeats,

@@ -1,6 +1,8 @@
 """Training step of the seq restarter (SeqRestarter.forward under autograd: reference tiger/model/restarters.py:51-114
 as called from TIGER.contrast_and_mutual_learning, tiger.py:574-590) on the kernels of csrc/train_seq.cu and the
 tensor-core products of csrc/gemm.cu.  Used by `www2023tiger_b200.train.NativeTrainer`."""
+import os
+
 import torch
 from torch import Tensor
 
@@ -39,6 +41,10 @@ class SeqRestarterTrainer:
         # names of this module's parameters inside the flat buffers
         self.prefix = next(n for n, p in zip(fp.names, fp.params) if p is module.anony_emb.weight)[:-len('anony_emb.weight')]
         self._ctx = None
+        # few rows (the lazy restart of a steady-state batch) take the matrix-vector tail of csrc/restart_seq.cu, many
+        # rows (the collated positives, the first batches of a chunk) the tensor-core products: ops.SeqRestarterOp
+        self.tail_rows = int(os.environ.get('TIGER_SEQ_TAIL_ROWS', '64')) if dm <= 1024 else 0
+        self.cnt_gate = z(2, dt=torch.int32)
 
     def _names(self):
         r = self.prefix
@@ -68,6 +74,21 @@ class SeqRestarterTrainer:
                       rows_per_count=L)
         call('tiger_train_seq_pool', ptr(self.QK), 2 * dm, ptr(self.X), ptr(self.mask), ptr(count), n, L, dm, H, p, seed,
              ptr(self.P), ptr(self.pbar), ptr(self.psum), ptr(self.xbar))
+        ctx = dict(n=n, count=count, p=p, seed=seed, an=an, ht=ht, pred_l=pred_l, keep=(hn, he, hdirs, nids))
+        if self.tail_rows > 0 and (count is not None or n <= self.tail_rows):
+            small = None
+            if count is not None:
+                call('tiger_seq_gate_count', ptr(count), self.tail_rows, ptr(self.cnt_gate), ptr(self.cnt_gate[1:]))
+                small, count = self.cnt_gate, self.cnt_gate[1:]
+                mc = dict(m_count=count)
+            fc1_w = P[N['fc1_w']]
+            call('tiger_seq_tail', ptr(self.xbar), ptr(small), n, dm, H, d, ptr(in_w[2 * dm:]), ptr(in_b[2 * dm:]),
+                 ptr(P[N['out_w']]), ptr(P[N['out_b']]), ptr(P[N['fn_w']]), ptr(P[N['fn_b']]), ptr(fc1_w), fc1_w.stride(0),
+                 ptr(P[N['fc1_b']]), ptr(P[N['fc2_w']]), ptr(P[N['fc2_b']]), ptr(self.psum), p, seed, ptr(self.att),
+                 ptr(self.o), ptr(self.hid), ptr(pred_l), ptr(pred_r))
+            if small is None:
+                self._ctx = ctx
+                return
         for h in range(H):
             rows = slice(2 * dm + h * hd, 2 * dm + (h + 1) * hd)
             ops.sgemm_ex(self.xbar[:, h * dm:(h + 1) * dm], in_w[rows], self.att[:, h * hd:(h + 1) * hd], m=n, n=hd, k=dm,
@@ -80,7 +101,7 @@ class SeqRestarterTrainer:
         ops.sgemm_ex(pred_l, P[N['fc1_w']][:, :d], self.hid, m=n, n=d, k=d, bias=P[N['fc1_b']], relu=True, **mc)
         call('tiger_train_dropout', ptr(self.hid), ptr(count), d, n * d, p, seed, 4)
         ops.sgemm_ex(self.hid, P[N['fc2_w']], pred_r, m=n, n=d, k=d, bias=P[N['fc2_b']], **mc)
-        self._ctx = dict(n=n, count=count, p=p, seed=seed, an=an, ht=ht, pred_l=pred_l, keep=(hn, he, hdirs, nids))
+        self._ctx = ctx
 
     def backward(self, dpred_l: Tensor, dpred_r: Tensor, g: float):
         ctx = self._ctx
