@@ -194,6 +194,85 @@ def test_full_size_stream_properties(gu, name):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize('name,restarter,start', [('reddit', 'static', 200_000), ('wikipedia', 'seq', 100_000)])
+def test_full_size_stream_matches_oracle_for_50_batches(gu, name, restarter, start):
+    """BASELINE-size stream, tables and dimensions (d = d_e = 172, K = 10, B = 200, hist_len 40): the pipelined graph
+    replay against the CPU oracle for 50 consecutive batches from the middle of the stream (lazy restart from a fresh
+    memory, histories from the full graph), every score / embedding / index list and the final state."""
+    shape = SHAPES[name]
+    st = make_stream(shape, seed=0)
+    N, d, B, K, H, n_batches = st.n_nodes, 172, 200, 10, 2, 50
+    W = perturb_biases(random_weights(d, 172, n_nodes=N, restarter=restarter, nonzero_static=True, seed=2))
+    neg = NegativeSampler(st.src, st.dst, seed=0).pre_sample_neg_dsts(st.n_events)
+    graph, model = gu.oracle_from(W, st.src, st.dst, st.ts, st.eids, N=N, dim=d, efeats=st.efeats, nfeats=None, K=K, H=H,
+                                  msg_src='left', upd_src='right', restarter=restarter)
+    outs = run_oracle(model, graph, st, neg, B, K, n_batches, True, start)
+    csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
+    e = gu.engine_from(W, csr, N=N, dim=d, efeats=st.efeats, nfeats=None, K=K, H=H, B=B, msg_src='left',
+                       upd_src='right', restarter=restarter, lazy_restart=True)
+    cols = lambda ib: tuple(a[start + ib * B:start + (ib + 1) * B] for a in (st.src, st.dst, neg, st.ts, st.eids))
+    runner = StreamRunner(e)
+    e.set_batch(*cols(0))
+    runner.capture(warmup=1)
+    e.reset()
+    for ib in range(n_batches):
+        ps, ns, loss = runner.wait(runner.submit_host(*cols(ib)))
+        o, what = outs[ib], f'{name} batch {ib} '
+        assert_close(ps.numpy(), o['pos_scores'].numpy(), TOL, what + 'pos')
+        assert_close(ns.numpy(), o['neg_scores'].numpy(), TOL, what + 'neg')
+        assert_close(np.array([float(loss)]), o['loss'].reshape(1).numpy(), TOL, what + 'loss')
+        assert_close(gu.cpu(e.emb), o['h_left_with_negs'].numpy(), TOL, what + 'emb')
+        assert np.array_equal(gu.cpu(e.outdated[:int(e.counts[1])]), o['outdated']), what
+    e.check_errors()
+    check_state(gu, e, model.left_vals.numpy(), model.right_vals.numpy(), model.left_ts.numpy(), model.right_ts.numpy(),
+                model.msg_vals.numpy(), model.msg_ts.numpy(), np.nonzero(model.has_msg)[0], name + ' final ')
+
+
+@pytest.mark.parametrize('name,restarter,start,n_batches', [('reddit', 'static', 200_000, 2000),
+                                                            ('wikipedia', 'seq', 20_000, 650)])
+def test_graph_pipeline_equals_serial_launches_at_full_size(gu, name, restarter, start, n_batches):
+    """The captured pipeline (restarter beside the GRU, write-back beside the attention, tail beside the products,
+    finder / scorer of neighbouring batches overlapped, n_slots batches in flight) against eager single-stream
+    launches of the same kernels, bit for bit, over thousands of consecutive BASELINE-size batches."""
+    shape = SHAPES[name]
+    st = make_stream(shape, seed=0)
+    N, d, B, K, H = st.n_nodes, 172, 200, 10, 2
+    W = perturb_biases(random_weights(d, 172, n_nodes=N, restarter=restarter, nonzero_static=True, seed=5))
+    neg = NegativeSampler(st.src, st.dst, seed=0).pre_sample_neg_dsts(st.n_events)
+    csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, N)
+    e = gu.engine_from(W, csr, N=N, dim=d, efeats=st.efeats, nfeats=None, K=K, H=H, B=B, msg_src='left',
+                       upd_src='right', restarter=restarter, lazy_restart=True, want_targets=False)
+    assert start + n_batches * B <= st.n_events
+    cols = lambda ib: tuple(a[start + ib * B:start + (ib + 1) * B] for a in (st.src, st.dst, neg, st.ts, st.eids))
+    state = lambda: [t.clone() for t in (e.left_vals, e.right_vals, e.msg_vals, e.left_ts, e.right_ts, e.msg_ts, e.has_msg)]
+    e.reset()
+    ref = torch.empty(n_batches, e.out_buf.numel())
+    for ib in range(n_batches):
+        e.set_batch(*cols(ib))
+        e.step()
+        ref[ib] = e.out_buf
+    e.check_errors()
+    final_ref = state()
+    runner = StreamRunner(e)
+    e.set_batch(*cols(0))
+    runner.capture(warmup=1)
+    e.reset()
+    pending, got = [], []
+    for ib in range(n_batches):
+        pending.append(runner.submit_host(*cols(ib)))
+        if len(pending) >= runner.n_slots:
+            ps, ns, loss = runner.wait(pending.pop(0))
+            got.append(torch.cat([ps, ns, loss.reshape(1)]).clone())
+    while pending:
+        ps, ns, loss = runner.wait(pending.pop(0))
+        got.append(torch.cat([ps, ns, loss.reshape(1)]).clone())
+    e.check_errors()
+    bad = [ib for ib in range(n_batches) if not torch.equal(got[ib], ref[ib])]
+    assert not bad, f'{len(bad)} batches differ, first {bad[:5]}'
+    for a, b in zip(final_ref, state()):
+        assert torch.equal(a, b)
+
+
 def test_pipelined_host_and_device_paths_match_eager_steps(gu):
     """StreamRunner keeps n_slots batches in flight (upload + finder of batch i+1 and download of batch i-1 beside
     the model kernels of batch i, per-slot buffers): the results must be bit-identical to eager, strictly

@@ -20,8 +20,9 @@ B="python bench.py --workload reddit --steps 20 --warmup 5 --cpu-batches 0 --pro
 $B > $O/plain_b.log 2>&1 && ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
   --log-file $O/${TAG}_launches_reddit_infer.csv $B > $O/ncu_b.log 2>&1
 for w in wikipedia reddit; do
+  SKIP=3600; if [ $w = reddit ]; then SKIP=1200; fi     # ~30 warm-up steps of the workload's launches
   B="python bench.py --mode train --workload $w --steps 8 --warmup 30 --profile-steps 0 --cpu-batches 0 --no-e2e"
-  $B > $O/plain_c.log 2>&1 && ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none --launch-skip 3600 -c 1000 --csv \
+  $B > $O/plain_c.log 2>&1 && ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none --launch-skip $SKIP -c 1000 --csv \
     --log-file $O/${TAG}_launches_${w}_train.csv $B > $O/ncu_c.log 2>&1
 done
 python bench.py --micro > $O/${TAG}_micro.json 2> $O/${TAG}_micro.err; echo micro_rc=$?
