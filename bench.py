@@ -1057,6 +1057,48 @@ def run_micro(args):
     timed('tiger_left_writeback',
           lambda: ops.left_writeback(pos, B, winner, h_left, d, ev_ts, table, left_ts, active),
           2 * B * (2 * d * 4 + 8 + 4 + 6), note='2R embedding rows persisted into the left memory')
+    # GRU update (update_modules.py:30-37 behind tiger.py:331-345): R outdated nodes, message + memory rows gathered
+    # from the 1M-row tables.  688 + 172 -> 516 gate pre-activations per row: at this size the kernel is bound by the
+    # tensor pipe (tf32x3), reported beside the HBM figure.
+    from www2023tiger_b200.init import random_weights
+    try:
+        tpeak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops']) / 2
+    except (OSError, KeyError):
+        tpeak = 1100.0
+    W = {k: v.to(dev) for k, v in random_weights(d, de, seed=args.seed).items()}
+    c = 'right_mem_updater.cell.'
+    gpack = ops.GruPack(W[c + 'weight_ih'], W[c + 'weight_hh'], W[c + 'bias_ih'], W[c + 'bias_hh'])
+    gru_out = torch.empty(R, d, device=dev)
+    timed('tiger_gru_update', lambda: ops.gru_update(gpack, node_ids=ids, x_table=msg_vals, h_table=table, n_rows=R,
+                                                    out=gru_out),
+          R * ((M + 2 * d) * 4 + 8), note='R rows: message row (M floats) + memory row gathered by node id, h_new written')
+    fl = 2.0 * R * 3 * d * (M + d)
+    t = results['tiger_gru_update']
+    t['tensor'] = {'useful_tflops': fl / (t['us'] * 1e-6) / 1e12, 'issued_tflops': 3 * fl / (t['us'] * 1e-6) / 1e12,
+                   'peak': tpeak, 'frac': 3 * fl / (t['us'] * 1e-6) / 1e12 / tpeak,
+                   'peak_source': 'half of the measured bf16 GEMM peak (tf32 runs at half the bf16 rate); tf32x3 issues 3 MMAs per product'}
+    # temporal attention (temporal_agg_modules.py:29-83,210-235): Q queries x K neighbors gathered from the 1M-row
+    # memory and the 4M-row edge-feature table, folded projections, softmax pooling, merger
+    Q = max(R // 4, 1024)
+    apack = ops.AttnPack(d, de, dev, 2)
+    a = 'temporal_embedding_fn.fns.0.'
+    apack.refresh(W[a + 'mha_fn.q_proj_weight'], W[a + 'mha_fn.k_proj_weight'], W[a + 'mha_fn.v_proj_weight'],
+                  W[a + 'mha_fn.in_proj_bias'], W[a + 'mha_fn.out_proj.weight'], W[a + 'mha_fn.out_proj.bias'],
+                  W[a + 'merger.fc1.weight'], W[a + 'merger.fc1.bias'], W[a + 'merger.fc2.weight'], W[a + 'merger.fc2.bias'],
+                  W['time_encoder.basis_freq'], W['time_encoder.phase'])
+    centers = torch.randint(1, N, (Q,), device=dev, generator=g)
+    q_ts = torch.rand(Q, device=dev, generator=g) * 1e6 + 2e6
+    nn_ids = torch.randint(1, N, (Q, K), device=dev, generator=g)
+    nn_eids = torch.randint(1, n_e + 1, (Q, K), device=dev, generator=g)
+    nn_ts = q_ts[:, None] - torch.rand(Q, K, device=dev, generator=g) * 1e5
+    att_out = torch.empty(Q, d, device=dev)
+    timed('tiger_temporal_attention',
+          lambda: ops.temporal_attention(apack, 2, centers, q_ts, nn_ids, nn_eids, nn_ts, rows_a=table2, rows_b=h_new,
+                                         sel=gru_row, nfeats=None, efeats=efeats, out=att_out),
+          Q * (d * 4 + 12 + K * ((d + de) * 4 + 20 + 4) + d * 4), n=10,
+          note=f'{Q} queries x {K} neighbors: center row + K (memory row + edge-feature row + ids/ts + sel) gathered, [Q, d] written')
+    results['tiger_temporal_attention']['rows'] = Q
+    del apack, gpack
     del msg_vals, efeats
     # neighbor finder (graph.py:44-53,117-127): R queries over a 1M-node / 8M-event CSR
     from www2023tiger_b200.synthetic import StreamShape, make_stream

@@ -1,6 +1,8 @@
 """Copies the round-2 measurement artefacts from gpurun_out/ into profiles/ and refreshes the number tables of DESIGN.md
 (between the <!-- NAME --> markers) from them."""
-import glob, json, os, re, shutil
+import glob, json, os, re, shutil, sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 O, P = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
@@ -55,7 +57,22 @@ def main():
     design = fill(design, 'DDP_TABLE', '\n'.join(rows))
     m = load(os.path.join(P, 'r02_micro.json'))
     if m:
-        design = fill(design, 'MICRO', ', '.join(f"`{k}` {v['frac_of_peak']:.2f}" for k, v in m['micro'].items()) + '.')
+        def one(k, v):
+            t = v.get('tensor')
+            return f"`{k}` {v['frac_of_peak']:.2f}" + (f" (tensor pipe {t['frac']:.2f} of the tf32 peak: compute bound at {v['rows']:,} rows)" if t else '')
+        design = fill(design, 'MICRO', ', '.join(one(k, v) for k, v in m['micro'].items()) + '.')
+    csvf = os.path.join(O, 'r02_micro_ncu.csv')
+    if os.path.exists(csvf):
+        import ncu_csv_table
+        open(os.path.join(P, 'r02_micro_ncu.md'), 'w').write(
+            '# Round 2 - ncu of `bench.py --micro` (tools/gpu_micro_ncu.sh)\n\n'
+            '262,144 rows (65,536 attention queries x 10 neighbors) over 1,000,001-row memories (688 MB each), a 1 M x 688 message '
+            'store and 4 M x 172 edge features: per-launch DRAM bytes and pipe utilisation next to the CUDA-event timings of '
+            '`profiles/r02_micro.json`.  Times under ncu are serialised and cold-clock; the byte counts are what matters: '
+            'gather / scatter / write-back kernels move 1.0-1.2 x their algorithmic bytes.  `gru_update_kernel` and the three '
+            'attention kernels (`gemm_tf32x3_ts_kernel` x 3, `attn_score_pool_kernel`) are NOT memory bound at this size - they '
+            'were shaped for the latency of one 200-event batch (one 600-query launch), see DESIGN.md section 6.\n\n'
+            + ncu_csv_table.table(csvf) + '\n')
     open(os.path.join(ROOT, 'DESIGN.md'), 'w').write(design)
     print(design[design.index('<!-- BENCH_TABLE -->'):design.index('<!-- /BENCH_TABLE -->')])
     print(design[design.index('<!-- DDP_TABLE -->'):design.index('<!-- /DDP_TABLE -->')])
