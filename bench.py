@@ -718,6 +718,21 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     ms = max_over_ranks(ev0.elapsed_time(ev1), world, dev)
     tr.check_errors()
     value = world * K * B / (ms * 1e-3)
+    if world > 1 and os.environ.get('TIGER_BENCH_DDP_EXP') == '1':
+        # experiment (stderr only): where the multi-rank step time goes - no collective / one bucket / three slices
+        for name, ar, sliced in (('no all-reduce', None, True), ('one bucket after backward', allreduce, False),
+                                 ('three slices (default)', allreduce, True)):
+            tr.reset_stream()
+            for i in range(Wm + K):
+                if i == Wm:
+                    wl.barrier()
+                    ev0.record()
+                tr.step_stream(dev_in[i % avail], mutual_coef=1.0, grad_scale=1.0 / world, allreduce=ar, sliced=sliced)
+            ev1.record()
+            wl.barrier()
+            own = ev0.elapsed_time(ev1) / K
+            worst = max_over_ranks(ev0.elapsed_time(ev1), world, dev) / K
+            print(f'[ddp-exp] rank {rank} {name}: own {own:.3f} ms/step, slowest rank {worst:.3f}', file=sys.stderr, flush=True)
     if world > 1:
         dist.all_reduce(losses)                    # the reference all-reduces its loss scalars (:209-211)
     mean_losses = (losses / (K * world)).cpu().tolist()

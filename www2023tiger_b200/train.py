@@ -399,13 +399,13 @@ class NativeTrainer:
                           hits_from_table=(m.hit_type == 'bin'), targets=targets, train=train)
 
     def step_stream(self, inp: Tensor, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, allreduce=None,
-                    lr: Optional[float] = None):
+                    lr: Optional[float] = None, sliced: bool = True):
         closs, mloss = self.forward_stream(inp)
         if allreduce is None:
             self.backward(1.0, mutual_coef)
         else:
             # one bucket per slice of the flat gradient buffer, started as soon as the backward pass has completed it
-            ranges = self.fp.comm_ranges()
+            ranges = self.fp.comm_ranges() if sliced else None
             works = []
             if ranges is None:
                 self.backward(1.0, mutual_coef)
