@@ -161,6 +161,19 @@ def test_training_through_torch_optimizer_and_native_adam_agree():
     g = Golden('seq_left_right')
     dl, a = setup(g)
     _, b_ = setup(g)
+
+    def eval_batch(model, bt):
+        """Inference route (weight packs of the kernels, cached per module) from a fresh memory."""
+        model.eval()
+        model.reset()
+        with torch.no_grad():
+            out = model.contrast_learning(*bt)
+        model.train()
+        model.reset()
+        return [cpu(t) for t in (out if isinstance(out, (tuple, list)) else (out,))]
+
+    probe = to_dev(next(iter(dl)))
+    before = eval_batch(b_, probe)                 # builds the packs from the initial weights
     a.train(), b_.train()
     a.reset(), b_.reset()
     tr = b_.native_trainer(g.bs, lr=1e-3)
@@ -179,6 +192,12 @@ def test_training_through_torch_optimizer_and_native_adam_agree():
     # same algorithm, same data; Adam normalises gradients, so round-off in near-zero gradients may move single
     # weights differently - the loss trajectories must still agree closely
     assert np.allclose(la, lb, rtol=1e-4), (la, lb)
+    # the native Adam kernel writes the parameters through raw pointers: the inference operators must notice (their
+    # packs are keyed on the parameters' version counters) and agree with the torch-optimised twin
+    ea, eb = eval_batch(a, probe), eval_batch(b_, probe)
+    for x, y in zip(ea, eb):
+        assert np.allclose(x, y, rtol=2e-3, atol=2e-4), np.abs(x - y).max()
+    assert np.abs(eb[1] - before[1]).max() > 1e-3, 'evaluation after training still used the initial weights'
 
 
 def _mix32(x):

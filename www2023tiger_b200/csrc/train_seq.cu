@@ -27,6 +27,7 @@ __device__ __forceinline__ int64_t seq_rows(const int32_t* count, int64_t n, int
 #define SP_CW 32
 #define SP_MAXL 64
 #define SP_MAXP ((SP_MAXL * SP_MAXL + SP_THREADS - 1) / SP_THREADS)
+#define SP_PRE ((SP_MAXL * SP_CW + SP_THREADS - 1) / SP_THREADS)
 
 // ------------------------------------------------------------------------------------------
 // forward: per (node, head) L x L scores, key-padding mask, softmax, dropout, mean over the query positions,
@@ -67,20 +68,37 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
     for (int t = 0; t < 2; ++t)
 #pragma unroll
       for (int r = 0; r < 8; ++r) acc[t][r] = 0.f;
-    for (int c0 = 0; c0 < hd; c0 += SP_CW) {
-      const int cw = (hd - c0) < SP_CW ? (hd - c0) : SP_CW;
-      __syncthreads();
-      for (int e = tid; e < len * SP_CW; e += SP_THREADS) {
+    // the next chunk's q / k elements are fetched into registers while the current chunk is multiplied (with ~23 items
+    // per launch in the inference step the kernel is one CTA's latency chain: 14 chunks x (global load -> smem -> FMA))
+    float qreg[SP_PRE], kreg[SP_PRE];
+    auto fetch = [&](int c0) {
+#pragma unroll
+      for (int t = 0; t < SP_PRE; ++t) {
+        const int e = tid + t * SP_THREADS;
         const int j = e / SP_CW, c = e % SP_CW;
         float qv = 0.f, kv = 0.f;
-        if (c < cw) {
+        if (j < len && c0 + c < hd) {
           qv = qbase[(int64_t)j * ld_qk + c0 + c] * scale;       // torch scales q before q.k^T
           kv = kbase[(int64_t)j * ld_qk + c0 + c];
         }
-        qsT[c][j] = qv;
-        ksT[c][j] = kv;
+        qreg[t] = qv;
+        kreg[t] = kv;
+      }
+    };
+    fetch(0);
+    for (int c0 = 0; c0 < hd; c0 += SP_CW) {
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < SP_PRE; ++t) {
+        const int e = tid + t * SP_THREADS;
+        const int j = e / SP_CW, c = e % SP_CW;
+        if (j < len) {
+          qsT[c][j] = qreg[t];
+          ksT[c][j] = kreg[t];
+        }
       }
       __syncthreads();
+      if (c0 + SP_CW < hd) fetch(c0 + SP_CW);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int tile = tid + t * SP_THREADS;
@@ -152,6 +170,7 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
     float* orow = xbar + (i * n_head + h) * (int64_t)dm;
     for (int c = tid; c < dm; c += SP_THREADS) {
       float s = 0.f;
+#pragma unroll 8
       for (int j = 0; j < len; ++j) s = fmaf(pbar[j], xrow[(int64_t)j * dm + c], s);
       orow[c] = s;
     }

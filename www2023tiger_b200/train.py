@@ -100,6 +100,9 @@ class FlatParams:
              ptr(self.seg_start), ptr(self.seg_group), ptr(self.seg_step), ptr(self.seg_bc), len(self.names),
              ptr(self.gates), self.max_seg, float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale),
              int(zero_grad))
+        # the kernel wrote the parameters through raw pointers: bump their version counters so that the weight packs of
+        # the inference operators (keyed on (data_ptr, _version) in tiger/model/*.py) are rebuilt before the next eval
+        torch._C._increment_version(self.params)
 
 
 def _param_group(name: str) -> int:
