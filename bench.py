@@ -795,7 +795,8 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
                     torch.cuda.synchronize()
                     records.clear()
                     counts.clear()
-                tr.step_stream(dev_in[i], mutual_coef=1.0, grad_scale=1.0 / world, allreduce=allreduce)
+                # rank 0 alone runs this breakdown: no collective here (the other ranks have left the loop)
+                tr.step_stream(dev_in[i], mutual_coef=1.0, grad_scale=1.0 / world, allreduce=None)
                 counts.append(torch.cat([tr.counts[:3].long(), tr.t_count.long()]))
         finally:
             ops.call = T.call = TS.call = orig
