@@ -687,8 +687,7 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     losses = torch.zeros(2, device=dev)
     comm_bytes = tr.fp.grad_all.numel() * 4 if world > 1 else 0
 
-    def allreduce(t):
-        return dist.all_reduce(t, async_op=True) if world > 1 else None
+    allreduce = (lambda t: dist.all_reduce(t, async_op=True)) if world > 1 else None
 
     def device_step(i):
         j = i % avail
@@ -702,6 +701,14 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     par = None
     if parity and arm is not None and args.parity_batches > 0 and arm.kind == 'reference':
         par = check_train_parity(args, wl, model, tr)
+    # single GPU: the step is replayed as one CUDA graph (the eager step is bound by the host's ~80-140 Python -> C calls);
+    # with a gradient all-reduce (N > 1) the launches stay eager.  TIGER_TRAIN_EAGER=1 keeps eager launches.
+    graphed = world == 1 and os.environ.get('TIGER_TRAIN_EAGER') != '1'
+    if graphed:
+        tr.reset_stream()
+        tr.capture_stream(mutual_coef=1.0, grad_scale=1.0 / world)
+        for i in range(3):                         # two eager steps + the capture, off the clock
+            device_step(i)
     tr.reset_stream()
     Wm, K = warmup, steps
     for i in range(Wm):
@@ -711,8 +718,10 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     losses.zero_()
     ev0.record()
+    t_host = time.perf_counter()
     for i in range(Wm, Wm + K):
         device_step(i)
+    host_ms = (time.perf_counter() - t_host) / K * 1e3      # host time to ISSUE one step (launches are asynchronous)
     ev1.record()
     wl.barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1), world, dev)
@@ -773,6 +782,7 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
 
     # ---- per-entry-point CUDA-event breakdown + launch count ----
     kernels, roofline, launches = None, None, None
+    tr.release_graph()
     if rank == 0 and profile_steps > 0:
         from www2023tiger_b200 import _lib
         tr.reset_stream()
@@ -841,7 +851,7 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     return {'value': value, 'ms_per_step': ms / K, 'e2e': e2e_out, 'gpu_launches': int(round((launches or 0) * K)),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu_out, 'parity': par, 'kernels': kernels,
             'train': {'lr': lr, 'optimizer': 'Adam (flat buffer, per-tensor step counters)', 'params': tr.fp.numel,
-                      'allreduce_bytes_per_step': comm_bytes, 'mean_contrast_loss': mean_losses[0],
+                      'allreduce_bytes_per_step': comm_bytes, 'host_issue_ms_per_step': host_ms, 'cuda_graph': graphed, 'mean_contrast_loss': mean_losses[0],
                       'mean_mutual_loss': mean_losses[1], 'dropout': 0.1, 'steps': K}}
 
 

@@ -524,7 +524,11 @@ int tiger_train_score_build(const float* z, const float* hits, const int64_t* ne
 int tiger_train_score_head(float* hid, const float* fc2_w, const float* fc2_b, int64_t batch, int d, float p_drop, int seed, float* scores, float* loss, float* dscore, void* stream);
 int tiger_train_score_head_bwd(const float* dscore, float g, const float* hid, const float* fc2_w, int64_t batch, int d, float p_drop, float* dhid, float* g_fc2_w, float* g_fc2_b, void* stream);
 int tiger_train_score_build_bwd(const float* dpair, const uint8_t* codes, int64_t batch, int d, float* dz, float* g_hit_emb, void* stream);
-int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev_left, const float* hprev_right, const int64_t* index, const int32_t* count, int64_t n, int d, float* loss, float* dpred_l, float* dpred_r, float* n_valid_out, void* stream);
+int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev_left, const float* hprev_right, const int64_t* index, const int32_t* count, int64_t n, int d, float* loss, float* dpred_l, float* dpred_r, float* n_valid_out, float* work /* [2n] scratch */, void* stream);
+/* CUDA-graph replay of the training step: registers a device int32 step counter (NULL clears it) that every dropout
+ * kernel adds (x 101, the host's per-step seed increment) to the seed it was launched with, so that replays of one
+ * captured step draw the masks of consecutive steps.  Process-wide per device; call outside stream capture. */
+int tiger_train_seed_step(const int32_t* step);
 int tiger_train_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_start, const int32_t* seg_group, int32_t* seg_step, float* seg_bc, int n_seg, float* gates, int64_t max_seg, float lr, float beta1, float beta2, float eps, float grad_scale, int zero_grad, void* stream);
 
 

@@ -319,3 +319,69 @@ def test_native_step_matches_autograd_route_at_baseline_dimensions(name, monkeyp
             [p.grad is None for _, p in unique_named_params(ref)], what
         check_grads(got, want, what)
     native._trainer.check_errors()
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident stream loop (NativeTrainer.attach_stream / step_stream) and its CUDA-graph replay
+# ------------------------------------------------------------------------------------------
+def stream_setup(restarter, seed=0, dropout=0.1, B=50):
+    import gpu_utils as gu
+    from www2023tiger_b200.init import build_model
+    from www2023tiger_b200.synthetic import NegativeSampler, StreamShape, make_stream
+    st = make_stream(StreamShape('g', 260, 40, 6000, 12, None, horizon=5000.), seed=3)
+    neg = NegativeSampler(st.src, st.dst, seed=0).pre_sample_neg_dsts(st.n_events)
+    csr = gu.device_csr(st.src, st.dst, st.ts, st.eids, st.n_nodes)
+    torch.manual_seed(seed)
+    model = build_model(None, torch.from_numpy(st.efeats).to(DEV), Graph.from_csr(csr), st.n_nodes, st.n_events, DEV,
+                        dim=st.dim, n_layers=1, n_heads=2, n_neighbors=5, hit_type='bin', dropout=dropout,
+                        restarter_type=restarter, hist_len=8, msg_src='left', upd_src='right')
+    model.train()
+    tr = model.native_trainer(B, lr=1e-3, seed=7)
+    tr.attach_stream(csr, 8)
+    n = 40
+    rec = np.empty((n, 5 * B), dtype=np.int64)
+    s = slice(1000, 1000 + n * B)
+    for k, col in enumerate((st.src, st.dst, neg, st.eids)):
+        rec[:, k * B:(k + 1) * B] = col[s].reshape(n, B)
+    rec[:, 4 * B:] = st.ts[s].astype(np.float64).reshape(n, B).view(np.int64)
+    return model, tr, torch.from_numpy(rec).to(DEV)
+
+
+@pytest.mark.parametrize('restarter', ['seq', 'static'])
+def test_stream_step_graph_replay_matches_eager_launches(restarter):
+    """Same model, same batches, dropout ON: eager launches with host seeds vs the captured step whose kernels add
+    the device-side step counter to the captured seed - the masks, hence the losses, must follow the same sequence."""
+    ma, ta, rec = stream_setup(restarter)
+    mb, tb, _ = stream_setup(restarter)
+    for (ka, pa), (kb, pb) in zip(unique_named_params(ma), unique_named_params(mb)):
+        assert ka == kb and torch.equal(pa, pb)
+    ta.reset_stream(), tb.reset_stream()
+    tb.capture_stream(mutual_coef=1.0, grad_scale=1.0)
+    la, lb = [], []
+    try:
+        for i in range(rec.shape[0]):
+            c, m = ta.step_stream(rec[i], mutual_coef=1.0, grad_scale=1.0)
+            la.append((float(c), float(m)))
+            if i == 25:                        # an eager step with other arguments in between: the counter re-aligns
+                c2, m2 = tb.step_stream(rec[i], mutual_coef=1.0, grad_scale=1.0, sliced=False, allreduce=lambda t: None)
+            else:
+                c2, m2 = tb.step_stream(rec[i], mutual_coef=1.0, grad_scale=1.0)
+            lb.append((float(c2), float(m2)))
+        assert tb._graph is not None and tb._g_replays >= rec.shape[0] - 4
+        assert int(tb.g_count) == rec.shape[0] - tb._g_base
+        ta.check_errors(), tb.check_errors()
+    finally:
+        tb.release_graph()
+    la, lb = np.array(la), np.array(lb)
+    assert np.isfinite(la).all() and la[:, 0].std() > 0
+    # identical masks and data; the weight gradients are summed with atomics (order differs run to run) and Adam
+    # normalises them, so single weights drift at round-off level
+    assert np.allclose(la, lb, rtol=2e-3, atol=1e-5), np.abs(la - lb).max()
+    for (k, pa), (_, pb) in zip(unique_named_params(ma), unique_named_params(mb)):
+        assert torch.allclose(pa, pb, rtol=0, atol=2e-3), k
+    # a different mask sequence would not pass: the same run with another seed differs by far more
+    mc, tc, _ = stream_setup(restarter)
+    tc.seed = 8
+    tc.reset_stream()
+    lc = np.array([[float(x) for x in tc.step_stream(rec[i], mutual_coef=1.0, grad_scale=1.0)] for i in range(rec.shape[0])])
+    assert np.abs(lc - la).max() > 10 * np.abs(lb - la).max()

@@ -77,7 +77,8 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_train_score_head': 'ppplifipppp',
     'tiger_train_score_head_bwd': 'pfpplifpppp',
     'tiger_train_score_build_bwd': 'pplippp',
-    'tiger_train_mse': 'pppppplippppp',
+    'tiger_train_seed_step': 'p',
+    'tiger_train_mse': 'pppppplipppppp',
     'tiger_train_adam': 'ppppppppiplfffffip',
     'tiger_train_seq_pool': 'plpppliiifippppp',
     'tiger_train_seq_pool_bwd': 'pppplpppliiifippp',

@@ -68,6 +68,22 @@ static inline int tiger_launch_chain(void (*kernel)(KP...), dim3 grid, dim3 bloc
   return tiger_launch_status();
 }
 
+// Dropout seeds under CUDA-graph replay.  The training step draws its masks from (seed, site, element) with a seed
+// that advances by 101 per step on the host (train.py).  A captured step would replay the seed of the capture step, so
+// the kernels add a device-side step counter (incremented inside the graph) when one is registered:
+// tiger_train_seed_step(ptr).  Eager launches (no counter registered) use the host seed as given; the k-th replay
+// draws exactly the masks the k-th eager step after the capture point would have drawn.
+static __device__ const int32_t* tiger_seed_step_ptr = nullptr;        // one copy per translation unit
+__device__ __forceinline__ uint32_t tiger_step_seed(uint32_t seed) {
+  const int32_t* p = tiger_seed_step_ptr;
+  return p == nullptr ? seed : ((seed + 101u * (uint32_t)(*p)) & 0x7fffffffu);
+}
+static inline int tiger_seed_step_set_here(const int32_t* p) {
+  return cudaMemcpyToSymbol(tiger_seed_step_ptr, &p, sizeof(p)) == cudaSuccess ? TIGER_OK : TIGER_ECUDA;
+}
+int tiger_seed_step_set_train_seq(const int32_t* p);       // csrc/train_seq.cu
+int tiger_seed_step_set_restart_seq(const int32_t* p);     // csrc/restart_seq.cu
+
 // Counter-based dropout mask of the seq restarter's training step: element `idx` of mask stream `stream` (3: attention
 // probabilities, 4: merger hidden layer) under `seed` is kept with probability 1 - p.
 __device__ __forceinline__ uint32_t seq_mix32(uint32_t x) {

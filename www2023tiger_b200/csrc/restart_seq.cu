@@ -260,6 +260,7 @@ seq_tail_layer_kernel(const float* __restrict__ x, int64_t ldx, int64_t x_grp_of
                       const float* __restrict__ bias, const float* __restrict__ bias_scale, float* __restrict__ y, int64_t ldy,
                       const int32_t* __restrict__ count, int64_t n_cap, int k, int n_out, int relu, float p_drop,
                       uint32_t seed) {
+  seed = tiger_step_seed(seed);
   extern __shared__ __align__(16) float tail_xs[];          // [TAIL_RT][32 * KREG]
   constexpr int KP = 32 * KREG;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -352,3 +353,5 @@ extern "C" int tiger_seq_tail(const float* xbar, const int32_t* count, int64_t n
   if (rc == TIGER_OK) rc = tail_layer(hid, d, 0, 1, w_fc2, d, b_fc2, nullptr, h_right, d, count, n, d, d, 0, 0.f, sd, st);
   return rc;
 }
+
+int tiger_seed_step_set_restart_seq(const int32_t* p) { return tiger_seed_step_set_here(p); }

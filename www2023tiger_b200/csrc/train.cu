@@ -249,6 +249,7 @@ train_attn_core_kernel(const float* __restrict__ Q, int64_t ldq, const float* __
                        int64_t ldkv, const int64_t* __restrict__ nn, int64_t n_q, int K, int n_head, int hd,
                        float p_drop, uint32_t seed, float* __restrict__ attn, int64_t ld_attn, float* __restrict__ P,
                        uint32_t* __restrict__ keep_bits, uint8_t* __restrict__ empty) {
+  seed = tiger_step_seed(seed);
   // KT > 0: K is a compile-time constant, so the per-neighbor loops below unroll without branches and the K dot
   // products / reductions of one (query, head) overlap instead of forming one dependent chain each
   constexpr int KU = KT > 0 ? KT : ATT_MAXK;
@@ -677,17 +678,18 @@ extern "C" int tiger_train_score_build(const float* z, const float* hits, const 
   return tiger_launch_status();
 }
 
-// One CTA.  hid [2B, d] = relu(fc1(pair)) is overwritten with its dropped-out version; score = hid' . w + b;
+// hid [2B, d] = relu(fc1(pair)) is overwritten with its dropped-out version; score = hid' . w + b;
 // loss = mean BCE-with-logits (labels 1 for rows < B, else 0); dscore = (sigmoid(score) - label) / 2B.
-__global__ void __launch_bounds__(1024)
+// Two launches: warp per row over the whole grid, then one CTA sums the 2B per-row losses in a fixed order (as a single
+// CTA walking all rows the kernel was one latency chain of 13 rows per warp: 27 us, profiles/r02_launches.md).
+__global__ void __launch_bounds__(256)
 train_score_head_kernel(float* __restrict__ hid, const float* __restrict__ w, const float* __restrict__ b, int64_t B,
-                        int d, float p_drop, uint32_t seed, float* __restrict__ scores, float* __restrict__ loss,
-                        float* __restrict__ dscore) {
-  __shared__ float red[32];
-  const int lane = lane_id(), warp = warp_id_in_block(), n_warps = blockDim.x >> 5;
+                        int d, float p_drop, uint32_t seed, float* __restrict__ scores, float* __restrict__ dscore) {
+  seed = tiger_step_seed(seed);
+  const int lane = lane_id();
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-  float local = 0.f;
-  for (int64_t r = warp; r < 2 * B; r += n_warps) {
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block(); r < 2 * B; r += n_warps) {
     float* row = hid + r * d;
     float acc = 0.f;
     for (int c = lane; c < d; c += 32) {
@@ -700,16 +702,27 @@ train_score_head_kernel(float* __restrict__ hid, const float* __restrict__ w, co
     if (lane == 0) {
       const float y = r < B ? 1.f : 0.f;
       scores[r] = acc;
-      local += fmaxf(acc, 0.f) - acc * y + log1pf(expf(-fabsf(acc)));
       dscore[r] = (sigmoidf_acc(acc) - y) / (float)(2 * B);
     }
   }
+}
+
+__global__ void __launch_bounds__(1024)
+train_bce_mean_kernel(const float* __restrict__ scores, int64_t B, float* __restrict__ loss) {
+  __shared__ float red[32];
+  const int lane = lane_id(), warp = warp_id_in_block(), n_warps = blockDim.x >> 5;
+  float local = 0.f;
+  for (int64_t r = threadIdx.x; r < 2 * B; r += blockDim.x) {
+    const float acc = scores[r], y = r < B ? 1.f : 0.f;
+    local += fmaxf(acc, 0.f) - acc * y + log1pf(expf(-fabsf(acc)));
+  }
+  local = warp_sum(local);
   if (lane == 0) red[warp] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int k = 0; k < n_warps; ++k) s += red[k];      // fixed order: deterministic
-    loss[0] = s / (float)(2 * B);
+    float t = 0.f;
+    for (int k = 0; k < n_warps; ++k) t += red[k];      // fixed order: deterministic
+    loss[0] = t / (float)(2 * B);
   }
 }
 
@@ -719,13 +732,17 @@ extern "C" int tiger_train_score_head(float* hid, const float* fc2_w, const floa
   if (hid == nullptr || fc2_w == nullptr || fc2_b == nullptr || scores == nullptr || loss == nullptr ||
       dscore == nullptr || batch <= 0 || d <= 0 || p_drop < 0.f || p_drop >= 1.f)
     return TIGER_EINVAL;
-  train_score_head_kernel<<<1, 1024, 0, as_stream(stream)>>>(hid, fc2_w, fc2_b, batch, d, p_drop, (uint32_t)seed, scores,
-                                                            loss, dscore);
+  int64_t grid = (2 * batch + 7) / 8;
+  if (grid > 148 * 4) grid = 148 * 4;
+  train_score_head_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(hid, fc2_w, fc2_b, batch, d, p_drop,
+                                                                        (uint32_t)seed, scores, dscore);
+  train_bce_mean_kernel<<<1, 1024, 0, as_stream(stream)>>>(scores, batch, loss);
   return tiger_launch_status();
 }
 
 // dhid[r, c] = g dscore_r w_c / (1 - p) where hid'[r, c] > 0 (kept and past the ReLU), else 0;
-// g_w[c] += g sum_r dscore_r hid'[r, c];  g_b += g sum_r dscore_r.   One CTA per 32 columns.
+// g_w[c] += g sum_r dscore_r hid'[r, c];  g_b += g sum_r dscore_r.   CTA (x, y) = 32 columns x one slice of the rows.
+#define SHB_ROWS 64
 __global__ void __launch_bounds__(256)
 train_score_head_bwd_kernel(const float* __restrict__ dscore, float g, const float* __restrict__ hid,
                             const float* __restrict__ w, int64_t B, int d, float p_drop, float* __restrict__ dhid,
@@ -734,8 +751,10 @@ train_score_head_bwd_kernel(const float* __restrict__ dscore, float g, const flo
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int wrp = threadIdx.x >> 5;
   const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const int64_t r0 = (int64_t)blockIdx.y * SHB_ROWS;
+  const int64_t r1 = (r0 + SHB_ROWS < 2 * B) ? r0 + SHB_ROWS : 2 * B;
   float acc = 0.f, accb = 0.f;
-  for (int64_t r = wrp; r < 2 * B; r += 8) {
+  for (int64_t r = r0 + wrp; r < r1; r += 8) {
     const float ds = g * dscore[r];
     if (c < d) {
       const float h = hid[r * d + c];
@@ -747,19 +766,19 @@ train_score_head_bwd_kernel(const float* __restrict__ dscore, float g, const flo
   part[wrp][threadIdx.x & 31] = acc;
   __syncthreads();
   if (wrp == 0 && c < d) {
-    float s = 0.f;
+    float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x];
-    atomicAdd(g_w + c, s);
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+    atomicAdd(g_w + c, t);
   }
   __syncthreads();
   if (blockIdx.x == 0) {
     part[wrp][threadIdx.x & 31] = (threadIdx.x & 31) == 0 ? accb : 0.f;
     __syncthreads();
     if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int k = 0; k < 8; ++k) s += part[k][0];
-      atomicAdd(g_b, s);
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += part[k][0];
+      atomicAdd(g_b, t);
     }
   }
 }
@@ -770,8 +789,9 @@ extern "C" int tiger_train_score_head_bwd(const float* dscore, float g, const fl
   if (dscore == nullptr || hid == nullptr || fc2_w == nullptr || dhid == nullptr || g_fc2_w == nullptr ||
       g_fc2_b == nullptr || batch <= 0 || d <= 0)
     return TIGER_EINVAL;
-  train_score_head_bwd_kernel<<<(unsigned)((d + 31) / 32), 256, 0, as_stream(stream)>>>(dscore, g, hid, fc2_w, batch, d,
-                                                                                       p_drop, dhid, g_fc2_w, g_fc2_b);
+  const dim3 grid((unsigned)((d + 31) / 32), (unsigned)((2 * batch + SHB_ROWS - 1) / SHB_ROWS));
+  train_score_head_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dscore, g, hid, fc2_w, batch, d, p_drop, dhid, g_fc2_w,
+                                                                  g_fc2_b);
   return tiger_launch_status();
 }
 
@@ -820,68 +840,90 @@ extern "C" int tiger_train_score_build_bwd(const float* dpair, const uint8_t* co
 
 // ------------------------------------------------------------------------------------------
 // mutual loss (tiger.py:574-592): MSE between [pred_left; pred_right] and [h_prev_left[index]; h_prev_right[index]]
-// over the rows whose target is not all-zero.  One CTA (P <= 2B rows).  dpred = 2 (pred - t) / (n_valid d), 0 for
-// invalid rows (the caller scales it with the upstream gradient).
+// over the rows whose target is not all-zero.  dpred = 2 (pred - t) / (n_valid d), 0 for invalid rows (the caller
+// scales it with the upstream gradient).  Two grid-wide launches (P <= 2048 rows): warp per row -> validity, the
+// row's squared error into `work` (-1 = invalid row) and the unscaled gradient; then every CTA derives n_valid from
+// `work` (fixed order), scales its share of the gradient and CTA 0 writes the loss.  (One CTA walking all rows twice
+// was 49 us, profiles/r02_launches.md.)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-train_mse_kernel(const float* __restrict__ pred_l, const float* __restrict__ pred_r, const float* __restrict__ hpl,
-                 const float* __restrict__ hpr, const int64_t* __restrict__ index, const int32_t* __restrict__ count,
-                 int64_t P, int d, float* __restrict__ loss, float* __restrict__ dpred_l, float* __restrict__ dpred_r,
-                 float* __restrict__ n_valid_out) {
-  __shared__ float red[32];
-  __shared__ int red_n[32];
-  __shared__ uint8_t valid[2 * 2048];
-  const int lane = lane_id(), warp = warp_id_in_block(), n_warps = blockDim.x >> 5;
+__global__ void __launch_bounds__(256)
+train_mse_rows_kernel(const float* __restrict__ pred_l, const float* __restrict__ pred_r, const float* __restrict__ hpl,
+                      const float* __restrict__ hpr, const int64_t* __restrict__ index, const int32_t* __restrict__ count,
+                      int64_t P, int d, float* __restrict__ dpred_l, float* __restrict__ dpred_r, float* __restrict__ work) {
+  const int lane = lane_id();
   const int64_t rows = bounded_rows(count, P);
-  int nv = 0;
-  for (int64_t r = warp; r < 2 * rows; r += n_warps) {
-    const bool left = r < rows;
-    const int64_t k = left ? r : r - rows;
-    const float* t = (left ? hpl : hpr) + index[k] * d;
-    bool nz = false;
-    for (int c = lane; c < d; c += 32) nz |= t[c] != 0.f;
-    nz = __any_sync(TIGER_FULL_MASK, nz);
-    if (lane == 0) valid[r] = nz;
-    nv += nz ? 1 : 0;
-  }
-  if (lane == 0) red_n[warp] = nv;
-  __syncthreads();
-  int n_valid = 0;
-  for (int k = 0; k < n_warps; ++k) n_valid += red_n[k];
-  const float inv = n_valid > 0 ? 1.0f / ((float)n_valid * (float)d) : 0.f;
-  float local = 0.f;
-  for (int64_t r = warp; r < 2 * rows; r += n_warps) {
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_in_block(); r < 2 * rows; r += n_warps) {
     const bool left = r < rows;
     const int64_t k = left ? r : r - rows;
     const float* t = (left ? hpl : hpr) + index[k] * d;
     const float* p = (left ? pred_l : pred_r) + k * d;
     float* gbase = left ? dpred_l : dpred_r;
-    const bool ok = valid[r] != 0;
+    bool nz = false;
+    float sse = 0.f;
     for (int c = lane; c < d; c += 32) {
-      const float e = p[c] - t[c];
-      if (ok) local = fmaf(e, e, local);
-      if (gbase != nullptr) gbase[k * d + c] = ok ? 2.0f * e * inv : 0.f;
+      const float tv = t[c];
+      const float e = p[c] - tv;
+      nz |= tv != 0.f;
+      sse = fmaf(e, e, sse);
+      if (gbase != nullptr) gbase[k * d + c] = 2.0f * e;
     }
+    nz = __any_sync(TIGER_FULL_MASK, nz);
+    sse = warp_sum(sse);
+    if (lane == 0) work[r] = nz ? sse : -1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+train_mse_finish_kernel(const int32_t* __restrict__ count, int64_t P, int d, const float* __restrict__ work,
+                        float* __restrict__ loss, float* __restrict__ dpred_l, float* __restrict__ dpred_r,
+                        float* __restrict__ n_valid_out) {
+  __shared__ float red[8];
+  __shared__ int red_n[8];
+  const int lane = lane_id(), warp = warp_id_in_block();
+  const int64_t rows = bounded_rows(count, P);
+  float local = 0.f;
+  int nv = 0;
+  for (int64_t r = threadIdx.x; r < 2 * rows; r += blockDim.x) {      // same order in every CTA: same n_valid / loss
+    const float v = work[r];
+    if (v >= 0.f) { local += v; ++nv; }
   }
   local = warp_sum(local);
-  if (lane == 0) red[warp] = local;
+  nv = __reduce_add_sync(TIGER_FULL_MASK, nv);
+  if (lane == 0) { red[warp] = local; red_n[warp] = nv; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int k = 0; k < n_warps; ++k) s += red[k];
-    loss[0] = s * inv;
+  float total = 0.f;
+  int n_valid = 0;
+  for (int k = 0; k < 8; ++k) { total += red[k]; n_valid += red_n[k]; }
+  const float inv = n_valid > 0 ? 1.0f / ((float)n_valid * (float)d) : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    loss[0] = total * inv;
     if (n_valid_out != nullptr) n_valid_out[0] = (float)n_valid;
+  }
+  if (dpred_l == nullptr) return;
+  const int64_t total_e = 2 * rows * d;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total_e; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / d;
+    const bool left = r < rows;
+    float* gp = (left ? dpred_l : dpred_r) + (e - (left ? 0 : rows * d));
+    *gp = work[r] >= 0.f ? *gp * inv : 0.f;
   }
 }
 
 extern "C" int tiger_train_mse(const float* pred_l, const float* pred_r, const float* hprev_left,
                                const float* hprev_right, const int64_t* index, const int32_t* count, int64_t n, int d,
-                               float* loss, float* dpred_l, float* dpred_r, float* n_valid_out, void* stream) {
+                               float* loss, float* dpred_l, float* dpred_r, float* n_valid_out, float* work,
+                               void* stream) {
   if (pred_l == nullptr || pred_r == nullptr || hprev_left == nullptr || hprev_right == nullptr || index == nullptr ||
-      loss == nullptr || n < 0 || n > 2048 || d <= 0 || (dpred_l == nullptr) != (dpred_r == nullptr))
+      loss == nullptr || work == nullptr || n < 0 || n > 2048 || d <= 0 || (dpred_l == nullptr) != (dpred_r == nullptr))
     return TIGER_EINVAL;
-  train_mse_kernel<<<1, 1024, 0, as_stream(stream)>>>(pred_l, pred_r, hprev_left, hprev_right, index, count, n, d, loss,
-                                                     dpred_l, dpred_r, n_valid_out);
+  int64_t grid = (2 * n + 7) / 8;
+  if (grid < 1) grid = 1;
+  if (grid > 148 * 2) grid = 148 * 2;
+  train_mse_rows_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(pred_l, pred_r, hprev_left, hprev_right, index,
+                                                                      count, n, d, dpred_l, dpred_r, work);
+  train_mse_finish_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(count, n, d, work, loss, dpred_l, dpred_r,
+                                                                        n_valid_out);
   return tiger_launch_status();
 }
 
@@ -952,4 +994,12 @@ extern "C" int tiger_train_adam(float* params, float* grads, float* exp_avg, flo
                                           grad_scale, zero_grad);
   if (zero_grad && gates != nullptr) train_zero_gates_kernel<<<1, 32, 0, st>>>(gates, 2);
   return tiger_launch_status();
+}
+
+// Registers (or clears, with NULL) the device-side step counter the dropout kernels add to their seeds: see common.cuh.
+extern "C" int tiger_train_seed_step(const int32_t* step) {
+  int rc = tiger_seed_step_set_here(step);
+  if (rc == TIGER_OK) rc = tiger_seed_step_set_train_seq(step);
+  if (rc == TIGER_OK) rc = tiger_seed_step_set_restart_seq(step);
+  return rc;
 }

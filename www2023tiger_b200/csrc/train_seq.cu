@@ -43,6 +43,7 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
                       const uint8_t* __restrict__ mask, const int32_t* __restrict__ count, int64_t n, int len, int dm,
                       int n_head, float p_drop, uint32_t seed, float* __restrict__ P, float* __restrict__ pbar_out,
                       float* __restrict__ psum_out, float* __restrict__ xbar) {
+  seed = tiger_step_seed(seed);
   __shared__ __align__(16) float qsT[SP_CW][SP_LP];
   __shared__ __align__(16) float ksT[SP_CW][SP_LP];
   __shared__ float sc[SP_MAXL][SP_MAXL + 1];
@@ -228,6 +229,7 @@ train_seq_pool_bwd_kernel(const float* __restrict__ dxbar, const float* __restri
                           const float* __restrict__ qk, int64_t ld_qk, const float* __restrict__ P,
                           const int32_t* __restrict__ count, int64_t n_cap, int len, int dm, int n_head, float p_drop,
                           uint32_t seed, float* __restrict__ dqk) {
+  seed = tiger_step_seed(seed);
   extern __shared__ __align__(16) float spb_smem[];
   const int LP = ((len + 3) & ~3) + 4;
   float* ds = spb_smem;                    // ds[i * LP + r]  = dS[i][r]
@@ -475,6 +477,7 @@ extern "C" int tiger_train_seq_tokens_bwd(const float* dX, const int32_t* count,
 // x[i] = keep(i) ? x[i] / (1 - p) : 0 in place (nn.Dropout in training mode; MergeLayer, basic_modules.py:16-19)
 __global__ void train_dropout_kernel(float* __restrict__ x, const int32_t* __restrict__ count, int64_t per,
                                      int64_t n_cap, float p, uint32_t seed, uint32_t stream_id) {
+  seed = tiger_step_seed(seed);
   const float inv_keep = 1.0f / (1.0f - p);
   const int64_t n = seq_rows(count, n_cap, per);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -509,3 +512,5 @@ extern "C" int tiger_train_axpy(float* y, const float* x, const int32_t* count, 
   train_axpy_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(y, x, count, per_count > 0 ? per_count : 1, n, alpha);
   return tiger_launch_status();
 }
+
+int tiger_seed_step_set_train_seq(const int32_t* p) { return tiger_seed_step_set_here(p); }

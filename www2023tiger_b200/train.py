@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch import Tensor
 
-from . import ops
+from . import _lib, ops
 from ._lib import call, ptr, raise_on_err_flags
 
 f32, i32, i64, u8 = torch.float32, torch.int32, torch.int64, torch.uint8
@@ -103,6 +103,24 @@ class FlatParams:
         # the kernel wrote the parameters through raw pointers: bump their version counters so that the weight packs of
         # the inference operators (keyed on (data_ptr, _version) in tiger/model/*.py) are rebuilt before the next eval
         torch._C._increment_version(self.params)
+
+
+_SEED_WORDS: Dict[int, Tensor] = {}
+
+
+def _seed_step_word(device) -> Tensor:
+    """The device word the dropout kernels add (x 101) to their seeds: one per device, registered with the library once
+    and zero except while a captured training step replays (NativeTrainer.capture_stream)."""
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SEED_WORDS:
+        word = torch.zeros(1, dtype=i32, device=torch.device('cuda', idx))
+        with torch.cuda.device(idx):
+            rc = _lib.load().tiger_train_seed_step(word.data_ptr())
+        if rc != 0:
+            raise _lib.TigerLibraryError(f'tiger_train_seed_step failed with code {rc}')
+        _SEED_WORDS[idx] = word
+    return _SEED_WORDS[idx]
 
 
 def _param_group(name: str) -> int:
@@ -187,6 +205,7 @@ class NativeTrainer:
         self.dhid_s, self.dpair = z(2 * B, d), z(2 * B, 2 * d)
         # --- restarter / mutual loss
         self.mloss = z(1)
+        self.mse_work = z(4 * B)
         self.pred_l, self.pred_r = z(2 * B, d), z(2 * B, d)
         self.dpred_l, self.dpred_r = z(2 * B, d), z(2 * B, d)
         self.restarter = model.restarter_fn
@@ -199,6 +218,8 @@ class NativeTrainer:
         else:
             raise NotImplementedError(kind(self.restarter))
         self._ctx = None
+        self._graph = self.g_inp = self.g_count = self._g_args = None
+        self._g_base = self._g_replays = 0
 
     # ------------------------------------------------------------------ parameter handles
     def P_(self, name: str) -> Tensor:
@@ -307,7 +328,7 @@ class NativeTrainer:
                 self.seq.forward(nids, targets['hist'], fg, self.pred_l, self.pred_r, seed, train, n=n_pos, count=cnt)
             call('tiger_train_mse', ptr(self.pred_l), ptr(self.pred_r), ptr(self.hprev_left), ptr(self.hprev_right),
                  ptr(targets['index']), ptr(cnt), n_pos, d, ptr(self.mloss), ptr(self.dpred_l), ptr(self.dpred_r),
-                 ptr(self.fp.gates[1:]))
+                 ptr(self.fp.gates[1:]), ptr(self.mse_work))
         else:
             self.mloss.zero_()
         # ---- steps 5-6 (tiger.py:244-255), no grad
@@ -401,8 +422,63 @@ class NativeTrainer:
         return self._core(B, batch_nids, self.ts32, eids, self.nn_, self.ne_, self.nt_, hits=None,
                           hits_from_table=(m.hit_type == 'bin'), targets=targets, train=train)
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the stream step
+    def capture_stream(self, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, lr: Optional[float] = None):
+        """Arms the CUDA-graph replay of forward_stream + backward + Adam (single GPU: no collective); `step_stream`
+        then copies the 8 kB batch record into the graph's input buffer and replays.  The eager step is bound by the
+        host - 78 (static restarter) to 139 (seq) C-ABI calls from Python per step, ~1.05 ms / ~2.9 ms of issue time
+        against 1.08 / 3.03 ms per step (bench.py `host_issue_ms_per_step`) - the replay costs two calls.
+        Dropout: the captured kernels carry the capture step's seed and add a device-side step counter
+        (csrc/common.cuh: tiger_step_seed): the graph copies its replay count into the registered word at its start
+        and clears the word at its end, so replay k draws the masks of eager step k while eager launches between
+        replays (of this or any other trainer) see zero.  The first two `step_stream` calls still launch eagerly (they
+        create the lazily sized workspaces), the third one captures; calls with an `allreduce` or other arguments
+        than the captured ones stay eager."""
+        assert self._graph is None, 'release_graph() first'
+        self.g_inp = torch.zeros(5 * self.B, dtype=i64, device=self.device)
+        self.g_count = torch.zeros(1, dtype=i32, device=self.device)
+        self._g_args = dict(mutual_coef=mutual_coef, grad_scale=grad_scale, lr=lr)
+        return self
+
+    def _capture_now(self, inp: Tensor):
+        a = self._g_args
+        word = _seed_step_word(self.device)
+        self.g_inp.copy_(inp)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        base = self.n_steps
+        self.g_count.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            word.copy_(self.g_count)
+            closs, mloss = self.forward_stream(self.g_inp)
+            self.backward(1.0, a['mutual_coef'])
+            self.fp.adam(self.lr if a['lr'] is None else a['lr'], grad_scale=a['grad_scale'])
+            word.zero_()
+            self.g_count.add_(1)
+        self.n_steps = base                    # the capture itself ran nothing
+        self._graph, self._g_base, self._g_out, self._g_replays = graph, base, (closs, mloss), 0
+
+    def release_graph(self):
+        """Back to eager launches."""
+        self._graph = self.g_inp = self.g_count = self._g_args = None
+
     def step_stream(self, inp: Tensor, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, allreduce=None,
                     lr: Optional[float] = None, sliced: bool = True):
+        if self._g_args is not None and allreduce is None and \
+                self._g_args == dict(mutual_coef=mutual_coef, grad_scale=grad_scale, lr=lr) and \
+                (self._graph is not None or self.n_steps >= 2):
+            if self._graph is None:
+                self._capture_now(inp)
+            if self.n_steps != self._g_base + self._g_replays:      # eager steps in between: re-align the counter
+                self.g_count.fill_(self.n_steps - self._g_base)
+                self._g_replays = self.n_steps - self._g_base
+            self.g_inp.copy_(inp, non_blocking=True)
+            self._graph.replay()
+            self.n_steps += 1
+            self._g_replays += 1
+            torch._C._increment_version(self.fp.params)
+            return self._g_out
         closs, mloss = self.forward_stream(inp)
         if allreduce is None:
             self.backward(1.0, mutual_coef)
