@@ -19,6 +19,41 @@ def fill(text, name, body):
     return re.sub(rf'<!-- {name} -->.*?<!-- /{name} -->', f'<!-- {name} -->\n{body}\n<!-- /{name} -->', text, flags=re.S)
 
 
+def full_table(md_path):
+    """tools/ncu_summary.py output (one block per profiled launch of an `ncu --set full` capture) -> one row per
+    (kernel, grid): launches, mean duration, DRAM bytes, tensor / FMA pipe, issue slots, L2 hit rate, registers."""
+    import collections
+    blocks = open(md_path).read().split('\n## ')[1:]
+    agg = collections.OrderedDict()
+    for b in blocks:
+        lines = b.strip().splitlines()
+        name = lines[0].strip().replace('void ', '')
+        vals = {}
+        for ln in lines[1:]:
+            c = [x.strip() for x in ln.strip('|').split('|')]
+            if len(c) == 3 and c[0] not in ('metric', '---'):
+                try:
+                    vals[c[0]] = (float(c[1].replace(',', '')), c[2])
+                except ValueError:
+                    vals[c[0]] = (c[1], c[2])
+        key = (name, vals.get('launch__grid_size', ('?',))[0], vals.get('launch__block_size', ('?',))[0])
+        agg.setdefault(key, []).append(vals)
+    scale = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}
+    rows = ['| kernel | grid | block | launches | us/launch | DRAM read MB | DRAM write MB | tensor pipe % | FMA pipe % | issue slots % | L2 hit % | regs |',
+            '|---|---|---|---|---|---|---|---|---|---|---|---|']
+    def mean(vs, k, conv=False):
+        xs = [v[k][0] * (scale.get(v[k][1], 1.0) if conv else 1.0) for v in vs if k in v and isinstance(v[k][0], float)]
+        return sum(xs) / len(xs) if xs else float('nan')
+    for (name, grid, block), vs in agg.items():
+        rows.append(f"| {name} | {grid:.0f} | {block:.0f} | {len(vs)} | {mean(vs, 'gpu__time_duration.sum', True):.1f} | "
+                    f"{mean(vs, 'dram__bytes_read.sum', True):.2f} | {mean(vs, 'dram__bytes_write.sum', True):.2f} | "
+                    f"{mean(vs, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{mean(vs, 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{mean(vs, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{mean(vs, 'lts__t_sector_hit_rate.pct'):.1f} | {mean(vs, 'launch__registers_per_thread'):.0f} |")
+    return '\n'.join(rows)
+
+
 def main():
     for f in glob.glob(os.path.join(O, 'r02_bench_*.json')) + glob.glob(os.path.join(O, 'r02_train_*.json')) + \
             glob.glob(os.path.join(O, 'r02_ddp_*_n?.json')) + glob.glob(os.path.join(O, 'r02_reference_*.json')) + \
@@ -73,6 +108,17 @@ def main():
             'attention kernels (`gemm_tf32x3_ts_kernel` x 3, `attn_score_pool_kernel`) are NOT memory bound at this size - they '
             'were shaped for the latency of one 200-event batch (one 600-query launch), see DESIGN.md section 6.\n\n'
             + ncu_csv_table.table(csvf) + '\n')
+    full = os.path.join(O, 'prof_r02_train_wikipedia.md')
+    if os.path.exists(full):
+        det = os.path.join(O, 'prof_r02_train_wikipedia_details.txt')
+        open(os.path.join(P, 'r02_train_kernels.md'), 'w').write(
+            '# Round 2 - `ncu --set full` of the training step\'s heavy kernels (Wikipedia-shaped stream, seq restarter)\n\n'
+            '`tools/gpu_ncu_full_train.sh` (the capture runs after the identical command exited 0 without ncu; eager launches, '
+            '`TIGER_TRAIN_EAGER=1`, of the kernels the graph replay launches; ~56 launches of one steady-state step).  The report '
+            'itself (~100 MB) stays on the GPU box; this is `ncu -i ... --page raw --csv` reduced by `tools/ncu_summary.py`, one row '
+            'per (kernel, grid), means over the launches.  Durations under ncu are serialised and cold-clock.\n\n'
+            + full_table(full) + '\n\n## Most frequent `--page details` lines (stall reasons, occupancy limiters)\n\n```\n'
+            + (open(det).read() if os.path.exists(det) else '') + '```\n')
     open(os.path.join(ROOT, 'DESIGN.md'), 'w').write(design)
     print(design[design.index('<!-- BENCH_TABLE -->'):design.index('<!-- /BENCH_TABLE -->')])
     print(design[design.index('<!-- DDP_TABLE -->'):design.index('<!-- /DDP_TABLE -->')])
