@@ -456,17 +456,6 @@ int tiger_sgemm_nt_packed_sum(const float* A_parts, int64_t lda, int64_t a_part_
                               int64_t m_rows, const int32_t* count, int64_t rows_per_count, int k_dim, float alpha,
                               int relu, void* stream);
 
-/* FFMA (CUDA-core) implementation of the same two operators: the measured baseline the tensor-core
- * kernels are compared with in bench.py --micro and tests; never on the product path. */
-int tiger_sgemm_ffma(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
-                     int64_t ldc, int64_t m_rows, const int32_t* count, int64_t rows_per_count, int n_cols,
-                     int k_dim, int relu, void* stream);
-int tiger_sgemm_ffma_batched(const float* A, int64_t lda, int64_t stride_a, const float* W, int64_t ldw,
-                             int64_t stride_w, const float* bias, int64_t stride_bias, float* C, int64_t ldc,
-                             int64_t stride_c, int batch, int64_t m_rows, const int32_t* count,
-                             int64_t rows_per_count, int n_cols, int k_dim, float alpha, int relu,
-                             const uint8_t* row_zero, void* stream);
-
 /* Self-attention weights of SeqRestarter's MHA (restarters.py:106, torch MHA need_weights branch),
  * reduced to what the mean over positions needs: for node i and head h
  *   p_h = softmax_keys((q_h * sqrt(1/hd)) k_h^T + mask)   [len x len], pbar_h = mean over queries,

@@ -98,8 +98,6 @@ _SIGNATURES: Dict[str, str] = {
     'tiger_gemm_pack_bytes': 'iii',
     'tiger_gemm_pack_weight': 'plpiiiip' + 'p',
     'tiger_sgemm_nt_packed': 'plpippllpliifi' + 'p',
-    'tiger_sgemm_ffma': 'plplp' + 'pl' + 'lpl' + 'iii' + 'p',
-    'tiger_sgemm_ffma_batched': 'pll' + 'pll' + 'pl' + 'pll' + 'il' + 'pl' + 'ii' + 'fi' + 'p' + 'p',
     'tiger_seq_attn_pool': 'plpp' + 'pli' + 'iip' + 'p',
     'tiger_static_restart': 'ppl' + 'plp' + 'pp' + 'ppi' + 'ppp' + 'ppp' + 'pp' + 'p',
 }

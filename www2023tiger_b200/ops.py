@@ -437,13 +437,13 @@ def static_restart(nids: Tensor, n: int, csr: DeviceCSR, left_emb: Tensor, right
 # ------------------------------------------------------------------------------------------
 def sgemm_nt(a: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, *, m_rows: Optional[int] = None,
              k_dim: Optional[int] = None, relu: bool = False, count: Optional[Tensor] = None,
-             rows_per_count: int = 1, ffma_baseline: bool = False) -> Tensor:
+             rows_per_count: int = 1) -> Tensor:
     """out[m, n] = act(a[m, :k] @ w[n, :k].T + bias[n]); a/w/out may be column slices of wider buffers.
-    Tensor cores (tf32x3); `ffma_baseline` selects the CUDA-core kernel kept for comparison only."""
+    Tensor cores (tf32x3)."""
     check_cuda_strided(a, w, out)
     m = a.shape[0] if m_rows is None else m_rows
     k = a.shape[1] if k_dim is None else k_dim
-    call('tiger_sgemm_ffma' if ffma_baseline else 'tiger_sgemm_nt', ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), m,
+    call('tiger_sgemm_nt', ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), m,
          ptr(count), rows_per_count, w.shape[0], k, int(relu))
     return out
 
