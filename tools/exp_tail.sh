@@ -1,6 +1,12 @@
-# train benches with the CUDA-graph replay on / off
-for w in reddit wikipedia; do
-for v in "TIGER_TRAIN_EAGER=0" "TIGER_TRAIN_EAGER=1"; do
-env $v python bench.py --workload $w --mode train --steps 200 --warmup 20 --cpu-batches 10 2>gpurun_out/exp_train.err | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('train $w $v',d['ms_per_step'],d['e2e']['value'],d.get('parity_checked'), d['train'].get('host_issue_ms_per_step'), d['train'].get('cuda_graph'), d['train'].get('mean_contrast_loss'), d['train'].get('mean_mutual_loss'))" || tail -5 gpurun_out/exp_train.err
-done; done
+# after the vectorised tail kernel: suites, then the seq-restarter inference lines + launch list again
+O=gpurun_out
+python -m pytest tests/test_train_gpu.py tests/test_ops_gpu.py tests/test_engine_gpu.py tests/test_dropin_gpu.py -m gpu -x -q 2>&1 | tail -4
+for w in wikipedia mooc lastfm scaled; do
+  python bench.py --workload $w > $O/r02_bench_$w.json 2> $O/r02_bench_$w.err; echo "bench $w rc=$?"
+  tail -1 $O/r02_bench_$w.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$w',d['ms_per_step'],d['e2e']['value'],d.get('parity_checked'), (d.get('train_step') or {}).get('ms_per_step'))"
+done
+B="python bench.py --workload wikipedia --steps 20 --warmup 5 --cpu-batches 0 --profile-steps 0 --no-e2e --train-steps 0"
+$B > $O/plain_a.log 2>&1 && ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
+  --log-file $O/r02_launches_wikipedia_infer.csv $B > $O/ncu_a.log 2>&1
+echo ncu_rc=$?

@@ -54,6 +54,42 @@ def full_table(md_path):
     return '\n'.join(rows)
 
 
+def launches_md():
+    """profiles/r02_launches.md from the four ncu launch lists of tools/profile_pass_r02.sh."""
+    import subprocess
+    ms = lambda f, key=None: (lambda d: None if d is None else (d[key]['ms_per_step'] if key else d['ms_per_step']))(load(os.path.join(P, f)))
+    parts = [('wikipedia_infer', 2, 'Inference step, Wikipedia-shaped stream, seq restarter (BASELINE configs[0])', ms('r02_bench_wikipedia.json'), 'graph-replayed'),
+             ('reddit_infer', 1, "Inference step, Reddit-shaped stream, static restarter (BASELINE configs[1], the driver's default)", ms('r02_bench_reddit.json'), 'graph-replayed'),
+             ('wikipedia_train', 3, 'Training step, Wikipedia-shaped stream, seq restarter (forward + backward + Adam)', ms('r02_train_wikipedia.json'), 'graph-replayed (the list was taken with eager launches of the same kernels)'),
+             ('reddit_train', 1, 'Training step, Reddit-shaped stream, static restarter (forward + backward + Adam)', ms('r02_train_reddit.json'), 'graph-replayed (the list was taken with eager launches of the same kernels)')]
+    out = ['# Round 2 - ncu launch lists (`--metrics gpu__time_duration.sum --clock-control none --cache-control none`), batch 200\n',
+           'Commands: `tools/profile_pass_r02.sh` (each ncu command runs only after the identical command exited 0 without ncu). '
+           'Tables by `tools/launch_table_steps.py` (steps delimited by the launches of the 3B-query neighbor finder; mean over the '
+           'last complete steps of the capture = steady state). Per-launch times under ncu are serialised: they exclude the overlap '
+           'the captured inference step has (finder on the copy-in stream, restarter beside the GRU, write-back branch beside the '
+           'attention chain, tail layers beside the idle tensor-core route, programmatic dependent launch), so the SHARE column is '
+           'what compares with bench.py.\n']
+    for name, per, title, t, how in parts:
+        f = os.path.join(O, f'r02_launches_{name}.csv')
+        if not os.path.exists(f) or os.path.getsize(f) == 0:
+            continue
+        tab = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'launch_table_steps.py'), f, 'find_recent_kernel', str(per), '4'],
+                             capture_output=True, text=True).stdout
+        out.append(f'## {title}; bench: {t:.4f} ms/step {how}\n\n{tab}')
+        if name == 'wikipedia_infer':
+            out.append('K7 (seq restarter, ~23 restarted nodes per batch = 920 tokens): `seq_tokens` -> q/k in-projection '
+                       '(`gemm_tf32x3_kernel`, persistent over tiles: 33 us of the 7 launches; the other six are the tensor-core '
+                       'route of the five post-pooling layers, launched with ZERO rows - ~10 us each serialised here, a parallel '
+                       'branch of the captured graph) -> `train_seq_pool_kernel` with dropout 0 -> `seq_gate_count` -> five '
+                       '`seq_tail_layer_kernel` launches (value projection per head, out-projection + ReLU, out_fn, merger fc1 + '
+                       'ReLU, fc2) as matrix-vector kernels: 16 us for the 860-wide layers, 7 us for the 172-wide ones '
+                       '(serialised: includes the weight-row fetch that overlaps the previous layer under programmatic dependent '
+                       'launch). Before this round\'s tail kernel the six products on ~23 rows cost 6 x 33 us (54 dependent '
+                       'k-steps each); the first tail version (32 dependent load -> store iterations per staged pass) took 38 us '
+                       'per layer.\n')
+    open(os.path.join(P, 'r02_launches.md'), 'w').write('\n'.join(out))
+
+
 def main():
     for f in glob.glob(os.path.join(O, 'r02_bench_*.json')) + glob.glob(os.path.join(O, 'r02_train_*.json')) + \
             glob.glob(os.path.join(O, 'r02_ddp_*_n?.json')) + glob.glob(os.path.join(O, 'r02_reference_*.json')) + \
@@ -116,9 +152,11 @@ def main():
             '`tools/gpu_ncu_full_train.sh` (the capture runs after the identical command exited 0 without ncu; eager launches, '
             '`TIGER_TRAIN_EAGER=1`, of the kernels the graph replay launches; ~56 launches of one steady-state step).  The report '
             'itself (~100 MB) stays on the GPU box; this is `ncu -i ... --page raw --csv` reduced by `tools/ncu_summary.py`, one row '
-            'per (kernel, grid), means over the launches.  Durations under ncu are serialised and cold-clock.\n\n'
+            'per (kernel, grid), means over the launches.  Durations under ncu are serialised and cold-clock.  The `seq_tail_layer_kernel` '
+            'rows predate the vectorised staging of that kernel (16 us per 860-wide layer afterwards, `r02_launches.md`).\n\n'
             + full_table(full) + '\n\n## Most frequent `--page details` lines (stall reasons, occupancy limiters)\n\n```\n'
             + (open(det).read() if os.path.exists(det) else '') + '```\n')
+    launches_md()
     open(os.path.join(ROOT, 'DESIGN.md'), 'w').write(design)
     print(design[design.index('<!-- BENCH_TABLE -->'):design.index('<!-- /BENCH_TABLE -->')])
     print(design[design.index('<!-- DDP_TABLE -->'):design.index('<!-- /DDP_TABLE -->')])

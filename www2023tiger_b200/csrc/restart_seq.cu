@@ -254,7 +254,7 @@ extern "C" int tiger_seq_gate_count(const int32_t* count, int max_rows, int32_t*
 // shared memory.  Group g (blockIdx.y) is the attention head of the value projection, 0 elsewhere.
 #define TAIL_WARPS 8
 #define TAIL_RT 8
-template <int KREG>
+template <int KREG, bool VEC>
 __global__ void __launch_bounds__(TAIL_WARPS * 32)
 seq_tail_layer_kernel(const float* __restrict__ x, int64_t ldx, int64_t x_grp_off, const float* __restrict__ W, int64_t ldw,
                       const float* __restrict__ bias, const float* __restrict__ bias_scale, float* __restrict__ y, int64_t ldy,
@@ -263,17 +263,29 @@ seq_tail_layer_kernel(const float* __restrict__ x, int64_t ldx, int64_t x_grp_of
   seed = tiger_step_seed(seed);
   extern __shared__ __align__(16) float tail_xs[];          // [TAIL_RT][32 * KREG]
   constexpr int KP = 32 * KREG;
+  constexpr int NT = TAIL_WARPS * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.y, c = blockIdx.x * TAIL_WARPS + warp;
   const bool live = c < n_out;
+  // VEC (16-byte aligned rows, k % 4 == 0): lane l holds elements [4 (l + 32 j), +4) of the weight row, else l + 32 j
   float wr[KREG];
   float b = 0.f;
   {
     const float* w = W + ((int64_t)g * n_out + (live ? c : 0)) * ldw;
+    if (VEC) {
+      const float4* w4 = reinterpret_cast<const float4*>(w);
 #pragma unroll
-    for (int j = 0; j < KREG; ++j) {
-      const int idx = lane + 32 * j;
-      wr[j] = (live && idx < k) ? __ldg(w + idx) : 0.f;
+      for (int j = 0; j < KREG / 4; ++j) {
+        const int i4 = lane + 32 * j;
+        const float4 v = (live && 4 * i4 < k) ? __ldg(w4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wr[4 * j] = v.x; wr[4 * j + 1] = v.y; wr[4 * j + 2] = v.z; wr[4 * j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < KREG; ++j) {
+        const int idx = lane + 32 * j;
+        wr[j] = (live && idx < k) ? __ldg(w + idx) : 0.f;
+      }
     }
     if (live && bias != nullptr) b = __ldg(bias + g * n_out + c);
   }
@@ -288,18 +300,48 @@ seq_tail_layer_kernel(const float* __restrict__ x, int64_t ldx, int64_t x_grp_of
   for (int64_t r0 = 0; r0 < n; r0 += TAIL_RT) {
     const int rows = (int)((n - r0) < TAIL_RT ? (n - r0) : TAIL_RT);
     __syncthreads();
-    for (int i = tid; i < TAIL_RT * KP; i += TAIL_WARPS * 32) {
-      const int rr = i / KP, col = i % KP;
-      tail_xs[i] = (rr < rows && col < k) ? xg[(r0 + rr) * ldx + col] : 0.f;
+    if (VEC) {
+      // all loads of the pass first (KREG / 4 independent 16-byte loads per thread), then the stores: the first version
+      // walked 32 dependent load -> store iterations per pass and took 38 us per layer under ncu
+      constexpr int NV = TAIL_RT * KP / 4 / NT;
+      float4 v[NV];
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int i = tid + t * NT;
+        const int rr = i / (KP / 4), c4 = i % (KP / 4);
+        v[t] = (rr < rows && 4 * c4 < k) ? *reinterpret_cast<const float4*>(xg + (r0 + rr) * ldx + 4 * c4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int t = 0; t < NV; ++t) reinterpret_cast<float4*>(tail_xs)[tid + t * NT] = v[t];
+    } else {
+      for (int i = tid; i < TAIL_RT * KP; i += NT) {
+        const int rr = i / KP, col = i % KP;
+        tail_xs[i] = (rr < rows && col < k) ? xg[(r0 + rr) * ldx + col] : 0.f;
+      }
     }
     __syncthreads();
     float acc[TAIL_RT];
 #pragma unroll
     for (int rr = 0; rr < TAIL_RT; ++rr) acc[rr] = 0.f;
+    if (VEC) {
 #pragma unroll
-    for (int j = 0; j < KREG; ++j) {
+      for (int j = 0; j < KREG / 4; ++j) {
 #pragma unroll
-      for (int rr = 0; rr < TAIL_RT; ++rr) acc[rr] = fmaf(wr[j], tail_xs[rr * KP + lane + 32 * j], acc[rr]);
+        for (int rr = 0; rr < TAIL_RT; ++rr) {
+          const float4 x4 = *reinterpret_cast<const float4*>(&tail_xs[rr * KP + 4 * (lane + 32 * j)]);
+          acc[rr] = fmaf(wr[4 * j], x4.x, acc[rr]);
+          acc[rr] = fmaf(wr[4 * j + 1], x4.y, acc[rr]);
+          acc[rr] = fmaf(wr[4 * j + 2], x4.z, acc[rr]);
+          acc[rr] = fmaf(wr[4 * j + 3], x4.w, acc[rr]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < KREG; ++j) {
+#pragma unroll
+        for (int rr = 0; rr < TAIL_RT; ++rr) acc[rr] = fmaf(wr[j], tail_xs[rr * KP + lane + 32 * j], acc[rr]);
+      }
     }
     float mine = 0.f;
 #pragma unroll
@@ -318,18 +360,32 @@ seq_tail_layer_kernel(const float* __restrict__ x, int64_t ldx, int64_t x_grp_of
   }
 }
 
+template <int KREG>
+static int tail_launch(bool vec, dim3 grid, dim3 block, cudaStream_t st, const float* x, int64_t ldx, int64_t x_grp_off,
+                       const float* W, int64_t ldw, const float* bias, const float* bias_scale, float* y, int64_t ldy,
+                       const int32_t* count, int64_t n, int k, int n_out, int relu, float p_drop, uint32_t seed) {
+  const size_t smem = (size_t)TAIL_RT * 32 * KREG * sizeof(float);
+  if (vec)
+    return tiger_launch_chain(seq_tail_layer_kernel<KREG, true>, grid, block, smem, st, dim3(1, 1, 1), x, ldx, x_grp_off, W, ldw,
+                              bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
+  return tiger_launch_chain(seq_tail_layer_kernel<KREG, false>, grid, block, smem, st, dim3(1, 1, 1), x, ldx, x_grp_off, W, ldw,
+                            bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
+}
+
 static int tail_layer(const float* x, int64_t ldx, int64_t x_grp_off, int groups, const float* W, int64_t ldw,
                       const float* bias, const float* bias_scale, float* y, int64_t ldy, const int32_t* count, int64_t n, int k,
                       int n_out, int relu, float p_drop, uint32_t seed, cudaStream_t st) {
   const dim3 grid((unsigned)((n_out + TAIL_WARPS - 1) / TAIL_WARPS), (unsigned)groups), block(TAIL_WARPS * 32);
+  const bool vec = (k & 3) == 0 && (ldx & 3) == 0 && (ldw & 3) == 0 && (x_grp_off & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
   if (k <= 256)
-    return tiger_launch_chain(seq_tail_layer_kernel<8>, grid, block, TAIL_RT * 256 * sizeof(float), st, dim3(1, 1, 1), x, ldx,
-                              x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
+    return tail_launch<8>(vec, grid, block, st, x, ldx, x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu,
+                          p_drop, seed);
   if (k <= 512)
-    return tiger_launch_chain(seq_tail_layer_kernel<16>, grid, block, TAIL_RT * 512 * sizeof(float), st, dim3(1, 1, 1), x,
-                              ldx, x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
-  return tiger_launch_chain(seq_tail_layer_kernel<32>, grid, block, TAIL_RT * 1024 * sizeof(float), st, dim3(1, 1, 1), x, ldx,
-                            x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu, p_drop, seed);
+    return tail_launch<16>(vec, grid, block, st, x, ldx, x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu,
+                           p_drop, seed);
+  return tail_launch<32>(vec, grid, block, st, x, ldx, x_grp_off, W, ldw, bias, bias_scale, y, ldy, count, n, k, n_out, relu,
+                         p_drop, seed);
 }
 
 extern "C" int tiger_seq_tail(const float* xbar, const int32_t* count, int64_t n, int d_model, int n_head, int d,
