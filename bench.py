@@ -66,6 +66,9 @@ def parse_args():
     p.add_argument('--parity-batches', type=int, default=3,
                    help='batches replayed after a reset and compared with the CPU arm (0 = off)')
     p.add_argument('--cpu-kind', default='auto', choices=['auto', 'reference', 'port'])
+    p.add_argument('--api', default='engine', choices=['engine', 'dropin'],
+                   help="engine: the fused per-batch engine (the benchmarked path); dropin: the reference's own evaluation "
+                        "loop (eval_edge_prediction) on the tiger/ mirror classes, host collation and host restart sets included")
     p.add_argument('--train-steps', type=int, default=100,
                    help='infer mode: also time this many training steps (fwd + bwd + all-reduce + Adam) of the same '
                         'configuration and report them under "train_step" (0 = off)')
@@ -1157,6 +1160,78 @@ def run_micro(args):
     print(json.dumps(line))
 
 
+def run_dropin(args):
+    """`--api dropin`: what a user of the reference gets WITHOUT changing a line of their script - the mirror classes of
+    www2023tiger_b200/tiger behind the reference's own loop `eval_edge_prediction(model, dl, device, restart_mode=True)`
+    (eval_utils.py:15-68): per batch a DataLoader item list -> GraphCollator (device finder, host copy of the involved
+    ids: the signature hands them to the driver) -> Python-set restart bookkeeping (`ts.min().item()`) -> TIGER.restart ->
+    contrast_learning on the kernel route -> scores; AP / AUC with sklearn at the end.  Timed with the wall clock around
+    the call (synchronised on both sides): there is no device-resident variant of this loop, so `value` repeats `e2e`."""
+    import torch
+    from torch.utils.data import DataLoader
+    from www2023tiger_b200 import ops
+    from www2023tiger_b200.init import build_model
+    from www2023tiger_b200.tiger.data.data_loader import GraphCollator, InteractionData
+    from www2023tiger_b200.tiger.data.graph import Graph
+    from www2023tiger_b200.tiger.eval_utils import eval_edge_prediction
+
+    wl = DeviceWorkload(args)
+    if wl.world > 1:
+        raise SystemExit('--api dropin is a single-process loop')
+    st, neg, shape, rst, dev, lo, B = wl.st, wl.neg, wl.shape, wl.rst, wl.dev, wl.lo, BATCH
+    Wm, K = args.warmup, min(args.steps, wl.avail - args.warmup)
+    graph = Graph.from_csr(wl.csr)
+    torch.manual_seed(args.seed)
+    model = build_model(None, wl.efeats, graph, wl.N, st.n_events, dev, dim=shape.dim, n_layers=1, n_heads=N_HEAD,
+                        n_neighbors=K_NEIGH, hit_type='bin', dropout=0.1, restarter_type=rst, hist_len=HIST_LEN,
+                        msg_src=shape.msg_src, upd_src=shape.upd_src)
+    if wl.arm is not None and wl.arm.kind == 'reference':
+        res = model.load_state_dict(wl.arm.weights(), strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+    coll = GraphCollator(graph, K_NEIGH, 1, restarter=rst, hist_len=HIST_LEN)
+
+    def loader(first, n):
+        s = slice(lo + first * B, lo + (first + n) * B)
+        data = InteractionData(st.src[s], st.dst[s], st.ts[s], st.eids[s], np.zeros(n * B, dtype=np.int64), seed=0,
+                               eval=True, neg_dst=neg[s])
+        return DataLoader(data, batch_size=B, collate_fn=coll)
+
+    calls = [0]
+    orig = ops.call
+
+    def counted(name, *a):
+        calls[0] += 1
+        orig(name, *a)
+    model.reset()
+    seen = set()
+    eval_edge_prediction(model, loader(0, Wm), dev, restart_mode=True, uptodate_nodes=seen)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(wl.local_rank)
+    ops.call = counted
+    t0 = time.perf_counter()
+    try:
+        ap, auc = eval_edge_prediction(model, loader(Wm, K), dev, restart_mode=True, uptodate_nodes=seen)
+        torch.cuda.synchronize()
+    finally:
+        ops.call = orig
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    cpu = None
+    if wl.arm is not None:
+        n, dtc = wl.arm.time(0, min(args.cpu_batches, K), args.cpu_seconds)
+        cpu = {'value': n * B / dtc, 'unit': UNIT, 'cores': wl.arm.cores, 'kind': wl.arm.kind,
+               'sample': wl.arm.describe(n, 2), 'ms_per_step': dtc / n * 1e3}
+    value = K * B / dt
+    cfg = workload_config(args, shape, st, 1)
+    cfg['api'] = "dropin: eval_edge_prediction(model, DataLoader(InteractionData, collate_fn=GraphCollator), restart_mode=True) on the tiger/ mirror"
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': K, 'warmup': Wm, 'ms_per_step': dt / K * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 5 * B * 8, 'd2h_bytes_per_step': 2 * B * 4,
+                    'note': 'wall clock around the reference-facing call; host collation, restart sets and AP / AUC included'},
+            'gpu_launches': calls[0], 'clocks': clk, 'roofline': None, 'cpu_baseline': cpu, 'ap': ap, 'auc': auc}
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
     if args.micro:
@@ -1165,6 +1240,8 @@ def main():
         run_reference(args)
     elif args.mode == 'train':
         run_train(args)
+    elif args.api == 'dropin':
+        run_dropin(args)
     else:
         run_b200(args)
 

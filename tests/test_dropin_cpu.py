@@ -60,3 +60,24 @@ def test_interaction_data_negatives_follow_reference_rng():
     a = s.sample(7)
     s.reset_random_state()
     assert np.array_equal(a[1], s.sample(7)[1])
+
+
+def test_ap_and_auc_equal_sklearn():
+    """The chunk metrics of eval_edge_prediction (reference eval_utils.py:55-62 calls sklearn) restated in numpy."""
+    from sklearn import metrics
+    from tiger.eval_utils import average_precision_score, roc_auc_score
+    rng = np.random.RandomState(0)
+    for trial in range(40):
+        n = int(rng.randint(2, 400))
+        label = np.r_[np.ones(n), np.zeros(n)]
+        score = rng.rand(2 * n)
+        if trial % 3 == 0:
+            score = np.round(score, 1)                 # many ties
+        if trial % 7 == 0:
+            score[:] = 0.5                             # all tied
+        if trial % 5 == 0:
+            keep = rng.rand(2 * n) > 0.3               # unbalanced, as after dropping non-finite scores
+            keep[0] = keep[-1] = True
+            label, score = label[keep], score[keep]
+        assert abs(average_precision_score(label, score) - metrics.average_precision_score(label, score)) < 1e-12
+        assert abs(roc_auc_score(label, score) - metrics.roc_auc_score(label, score)) < 1e-12

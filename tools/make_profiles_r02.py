@@ -93,7 +93,7 @@ def launches_md():
 def main():
     for f in glob.glob(os.path.join(O, 'r02_bench_*.json')) + glob.glob(os.path.join(O, 'r02_train_*.json')) + \
             glob.glob(os.path.join(O, 'r02_ddp_*_n?.json')) + glob.glob(os.path.join(O, 'r02_reference_*.json')) + \
-            glob.glob(os.path.join(O, 'r02_micro.json')):
+            glob.glob(os.path.join(O, 'r02_micro.json')) + glob.glob(os.path.join(O, 'r02_dropin_*.json')):
         if load(f) is not None:
             shutil.copy(f, os.path.join(P, os.path.basename(f)))
     design = open(os.path.join(ROOT, 'DESIGN.md')).read()

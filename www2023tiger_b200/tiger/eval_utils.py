@@ -27,10 +27,40 @@ def _lazy_restart(model, cg, ts, uptodate_nodes: set, device):
     uptodate_nodes.update(fresh)
 
 
+def average_precision_score(label: np.ndarray, score: np.ndarray) -> float:
+    """sklearn.metrics.average_precision_score for binary labels: AP = sum_n (R_n - R_{n-1}) P_n over the distinct
+    score thresholds, descending.  The reference calls sklearn once per 200-event chunk (eval_utils.py:55-62), where its
+    input validation costs ~2 ms per call - more than the whole device path of the batch; same numbers
+    (tests/test_dropin_cpu.py compares against sklearn, ties included)."""
+    order = np.argsort(-score, kind='mergesort')
+    y, sc = label[order].astype(np.float64), score[order]
+    last = np.r_[np.nonzero(np.diff(sc))[0], len(sc) - 1]           # last index of every group of equal scores
+    tps = np.cumsum(y)[last]
+    precision = tps / (last + 1.0)
+    recall = tps / tps[-1] if tps[-1] > 0 else np.full_like(tps, np.nan)
+    return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+
+
+def roc_auc_score(label: np.ndarray, score: np.ndarray) -> float:
+    """sklearn.metrics.roc_auc_score for binary labels (trapezoidal ROC area = Mann-Whitney U with average ranks
+    for ties)."""
+    order = np.argsort(score, kind='mergesort')
+    sc = score[order]
+    starts = np.r_[0, np.nonzero(np.diff(sc))[0] + 1]
+    ends = np.r_[starts[1:], len(sc)]
+    rank_of_group = (starts + ends + 1) / 2.0                       # average 1-based rank of each tie group
+    ranks = np.empty(len(sc))
+    ranks[order] = np.repeat(rank_of_group, ends - starts)
+    pos = label > 0
+    n_pos, n_neg = int(pos.sum()), int((~pos).sum())
+    if n_pos == 0 or n_neg == 0:
+        raise ValueError('Only one class present in y_true. ROC AUC score is not defined in that case.')
+    return float((ranks[pos].sum() - n_pos * (n_pos + 1) / 2.0) / (n_pos * n_neg))
+
+
 def eval_edge_prediction(model, dl, device: torch.device, restart_mode: bool,
                          uptodate_nodes: Optional[set] = None, mean_over_n_samples: int = 200
                          ) -> Tuple[float, float]:
-    from sklearn.metrics import average_precision_score, roc_auc_score
     model.eval()
     uptodate_nodes = set() if uptodate_nodes is None else uptodate_nodes
     pos_all, neg_all = [], []
