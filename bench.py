@@ -704,14 +704,28 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     par = None
     if parity and arm is not None and args.parity_batches > 0 and arm.kind == 'reference':
         par = check_train_parity(args, wl, model, tr)
-    # single GPU: the step is replayed as one CUDA graph (the eager step is bound by the host's ~80-140 Python -> C calls);
-    # with a gradient all-reduce (N > 1) the launches stay eager.  TIGER_TRAIN_EAGER=1 keeps eager launches.
-    graphed = world == 1 and os.environ.get('TIGER_TRAIN_EAGER') != '1'
+    # The step is replayed as one CUDA graph (the eager step is bound by the host's ~80-140 Python -> C calls); at N > 1 the
+    # three gradient all-reduce slices are captured with it (NCCL through torch.distributed is capturable).
+    # TIGER_TRAIN_EAGER=1 keeps eager launches.  A capture that fails on any rank puts every rank back on eager launches.
+    graphed = os.environ.get('TIGER_TRAIN_EAGER') != '1'
+    graph_error = None
     if graphed:
         tr.reset_stream()
-        tr.capture_stream(mutual_coef=1.0, grad_scale=1.0 / world)
-        for i in range(3):                         # two eager steps + the capture, off the clock
-            device_step(i)
+        tr.capture_stream(mutual_coef=1.0, grad_scale=1.0 / world, allreduce=allreduce)
+        try:
+            for i in range(3):                     # two eager steps + the capture, off the clock
+                device_step(i)
+            torch.cuda.synchronize()
+        except Exception as e:                     # noqa: BLE001 - reported in the JSON line, eager launches take over
+            graph_error = f'{type(e).__name__}: {e}'[:300]
+        ok = torch.tensor([0.0 if graph_error else 1.0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) < 1.0:
+            graphed = False
+            graph_error = graph_error or 'capture failed on another rank'
+            tr.release_graph()
+            print(f'[bench] CUDA-graph capture of the training step failed ({graph_error}); eager launches', file=sys.stderr)
     tr.reset_stream()
     Wm, K = warmup, steps
     for i in range(Wm):
@@ -854,7 +868,7 @@ def measure_train(args, wl, steps, warmup, *, parity, cpu, e2e, profile_steps):
     return {'value': value, 'ms_per_step': ms / K, 'e2e': e2e_out, 'gpu_launches': int(round((launches or 0) * K)),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu_out, 'parity': par, 'kernels': kernels,
             'train': {'lr': lr, 'optimizer': 'Adam (flat buffer, per-tensor step counters)', 'params': tr.fp.numel,
-                      'allreduce_bytes_per_step': comm_bytes, 'host_issue_ms_per_step': host_ms, 'cuda_graph': graphed, 'mean_contrast_loss': mean_losses[0],
+                      'allreduce_bytes_per_step': comm_bytes, 'host_issue_ms_per_step': host_ms, 'cuda_graph': graphed, 'cuda_graph_error': graph_error, 'mean_contrast_loss': mean_losses[0],
                       'mean_mutual_loss': mean_losses[1], 'dropout': 0.1, 'steps': K}}
 
 

@@ -423,8 +423,9 @@ class NativeTrainer:
                           hits_from_table=(m.hit_type == 'bin'), targets=targets, train=train)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the stream step
-    def capture_stream(self, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, lr: Optional[float] = None):
-        """Arms the CUDA-graph replay of forward_stream + backward + Adam (single GPU: no collective); `step_stream`
+    def capture_stream(self, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, lr: Optional[float] = None,
+                       allreduce=None, sliced: bool = True):
+        """Arms the CUDA-graph replay of forward_stream + backward [+ the sliced gradient all-reduce] + Adam; `step_stream`
         then copies the 8 kB batch record into the graph's input buffer and replays.  The eager step is bound by the
         host - 78 (static restarter) to 139 (seq) C-ABI calls from Python per step, ~1.05 ms / ~2.9 ms of issue time
         against 1.08 / 3.03 ms per step (bench.py `host_issue_ms_per_step`) - the replay costs two calls.
@@ -432,12 +433,14 @@ class NativeTrainer:
         (csrc/common.cuh: tiger_step_seed): the graph copies its replay count into the registered word at its start
         and clears the word at its end, so replay k draws the masks of eager step k while eager launches between
         replays (of this or any other trainer) see zero.  The first two `step_stream` calls still launch eagerly (they
-        create the lazily sized workspaces), the third one captures; calls with an `allreduce` or other arguments
-        than the captured ones stay eager."""
+        create the lazily sized workspaces and, with `allreduce`, the NCCL communicator), the third one captures; calls
+        with other arguments than the captured ones (`allreduce` must be the same callable) stay eager.  NCCL
+        collectives issued through torch.distributed are capturable: the slices become graph nodes on NCCL's stream
+        beside the rest of the backward pass."""
         assert self._graph is None, 'release_graph() first'
         self.g_inp = torch.zeros(5 * self.B, dtype=i64, device=self.device)
         self.g_count = torch.zeros(1, dtype=i32, device=self.device)
-        self._g_args = dict(mutual_coef=mutual_coef, grad_scale=grad_scale, lr=lr)
+        self._g_args = dict(mutual_coef=mutual_coef, grad_scale=grad_scale, lr=lr, allreduce=allreduce, sliced=sliced)
         return self
 
     def _capture_now(self, inp: Tensor):
@@ -451,9 +454,7 @@ class NativeTrainer:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
             word.copy_(self.g_count)
-            closs, mloss = self.forward_stream(self.g_inp)
-            self.backward(1.0, a['mutual_coef'])
-            self.fp.adam(self.lr if a['lr'] is None else a['lr'], grad_scale=a['grad_scale'])
+            closs, mloss = self._step_eager(self.g_inp, **a)
             word.zero_()
             self.g_count.add_(1)
         self.n_steps = base                    # the capture itself ran nothing
@@ -465,9 +466,8 @@ class NativeTrainer:
 
     def step_stream(self, inp: Tensor, *, mutual_coef: float = 1.0, grad_scale: float = 1.0, allreduce=None,
                     lr: Optional[float] = None, sliced: bool = True):
-        if self._g_args is not None and allreduce is None and \
-                self._g_args == dict(mutual_coef=mutual_coef, grad_scale=grad_scale, lr=lr) and \
-                (self._graph is not None or self.n_steps >= 2):
+        key = dict(mutual_coef=mutual_coef, grad_scale=grad_scale, lr=lr, allreduce=allreduce, sliced=sliced)
+        if self._g_args is not None and self._g_args == key and (self._graph is not None or self.n_steps >= 2):
             if self._graph is None:
                 self._capture_now(inp)
             if self.n_steps != self._g_base + self._g_replays:      # eager steps in between: re-align the counter
@@ -479,6 +479,9 @@ class NativeTrainer:
             self._g_replays += 1
             torch._C._increment_version(self.fp.params)
             return self._g_out
+        return self._step_eager(inp, **key)
+
+    def _step_eager(self, inp: Tensor, *, mutual_coef, grad_scale, allreduce, lr, sliced):
         closs, mloss = self.forward_stream(inp)
         if allreduce is None:
             self.backward(1.0, mutual_coef)
