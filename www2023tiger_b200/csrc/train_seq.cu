@@ -79,8 +79,8 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
         const int j = e / SP_CW, c = e % SP_CW;
         float qv = 0.f, kv = 0.f;
         if (j < len && c0 + c < hd) {
-          qv = qbase[(int64_t)j * ld_qk + c0 + c] * scale;       // torch scales q before q.k^T
-          kv = kbase[(int64_t)j * ld_qk + c0 + c];
+          qv = qbase[(int64_t)j * ld_qk + c0 + c];               // consumed (scaled) only when stored to shared memory:
+          kv = kbase[(int64_t)j * ld_qk + c0 + c];               // multiplying here would wait for the load at once
         }
         qreg[t] = qv;
         kreg[t] = kv;
@@ -94,7 +94,7 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
         const int e = tid + t * SP_THREADS;
         const int j = e / SP_CW, c = e % SP_CW;
         if (j < len) {
-          qsT[c][j] = qreg[t];
+          qsT[c][j] = qreg[t] * scale;                           // torch scales q before q.k^T
           ksT[c][j] = kreg[t];
         }
       }
@@ -169,11 +169,25 @@ train_seq_pool_kernel(const float* __restrict__ qk, int64_t ld_qk, const float* 
     }
     const float* xrow = x + i * len * (int64_t)dm;
     float* orow = xbar + (i * n_head + h) * (int64_t)dm;
-    for (int c = tid; c < dm; c += SP_THREADS) {
-      float s = 0.f;
+    if ((dm & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(xbar) & 15) == 0) {
+      // four columns per thread, 16-byte loads, eight token rows in flight (was: one column, 160 dependent rounds)
+      for (int c4 = tid; c4 < (dm >> 2); c4 += SP_THREADS) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-      for (int j = 0; j < len; ++j) s = fmaf(pbar[j], xrow[(int64_t)j * dm + c], s);
-      orow[c] = s;
+        for (int j = 0; j < len; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(xrow + (int64_t)j * dm + 4 * c4);
+          const float w = pbar[j];
+          a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+        }
+        *reinterpret_cast<float4*>(orow + 4 * c4) = a;
+      }
+    } else {
+      for (int c = tid; c < dm; c += SP_THREADS) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < len; ++j) s = fmaf(pbar[j], xrow[(int64_t)j * dm + c], s);
+        orow[c] = s;
+      }
     }
   }
 }
