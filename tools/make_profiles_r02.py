@@ -86,8 +86,7 @@ def launches_md():
                        '(serialised: includes the weight-row fetch that overlaps the previous layer under programmatic dependent '
                        'launch). Before this round\'s tail kernel the six products on ~23 rows cost 6 x 33 us (54 dependent '
                        'k-steps each); the first tail version (32 dependent load -> store iterations per staged pass) took 38 us '
-                       'per layer.  The `train_seq_pool_kernel` row predates that kernel\'s last change (q scaled at the shared-memory store so '
-                       'that the prefetch no longer waits for its load, 16-byte pooled-token loads): step 0.227 -> 0.211 ms.\n')
+                       'per layer.\n')
     open(os.path.join(P, 'r02_launches.md'), 'w').write('\n'.join(out))
 
 
